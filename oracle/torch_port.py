@@ -1,0 +1,255 @@
+"""Reference CPU execution path, restated -- TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+The reference has no kernels of its own: its CPU path is a sequence of stock torch ops
+(``nn.Conv2d`` / ``nn.ConvTranspose2d`` / ``F.conv2d`` / elementwise ATen).  This module restates
+that sequence functionally on a plain ``state_dict`` so that it can (a) run on the GPU box, where
+/root/reference does not exist, as the timed CPU baseline of ``bench.py`` and (b) serve as the
+stage-wise parity reference at sizes where the plain-C oracle would take minutes.  It is pinned
+to the real reference by tests/golden (tests/test_oracle_golden.py).
+
+All citations are relative to /root/reference/CompressAI.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# ---- layers ---------------------------------------------------------------------------------
+def conv(sd: Dict[str, Tensor], name: str, x: Tensor, stride: int = 2) -> Tensor:
+    """compressai/models/utils.py:128-135"""
+    w = sd[name + ".weight"]
+    return F.conv2d(x, w, sd[name + ".bias"], stride=stride, padding=w.shape[-1] // 2)
+
+
+def deconv(sd: Dict[str, Tensor], name: str, x: Tensor, stride: int = 2) -> Tensor:
+    """compressai/models/utils.py:138-146"""
+    w = sd[name + ".weight"]
+    return F.conv_transpose2d(x, w, sd[name + ".bias"], stride=stride, padding=w.shape[-1] // 2,
+                              output_padding=stride - 1)
+
+
+def lower_bound(x: Tensor, bound: float) -> Tensor:
+    """compressai/ops/bound_ops.py:36-37"""
+    return torch.max(x, torch.tensor([bound], dtype=x.dtype))
+
+
+def gdn(sd: Dict[str, Tensor], name: str, x: Tensor, inverse: bool = False, beta_min: float = 1e-6) -> Tensor:
+    """compressai/layers/gdn.py:77-92 + compressai/ops/parametrizers.py:47-64"""
+    pedestal = (2.0 ** -18) ** 2
+    beta = lower_bound(sd[name + ".beta"], (beta_min + pedestal) ** 0.5) ** 2 - pedestal
+    gamma = lower_bound(sd[name + ".gamma"], pedestal ** 0.5) ** 2 - pedestal
+    C = x.shape[1]
+    norm = F.conv2d(x ** 2, gamma.reshape(C, C, 1, 1), beta)
+    norm = torch.sqrt(norm) if inverse else torch.rsqrt(norm)
+    return x * norm
+
+
+# ---- entropy models -------------------------------------------------------------------------
+def quantize(x: Tensor, mode: str, means: Optional[Tensor] = None, noise: Optional[Tensor] = None) -> Tensor:
+    """compressai/entropy_models/entropy_models.py:157-182 (noise passed in)"""
+    if mode == "noise":
+        return x + noise
+    out = x.clone()
+    if means is not None:
+        out -= means
+    out = torch.round(out)
+    if mode == "dequantize":
+        if means is not None:
+            out += means
+        return out
+    assert mode == "symbols"
+    return out.int()
+
+
+def eb_logits_cumulative(sd: Dict[str, Tensor], name: str, v: Tensor) -> Tensor:
+    """entropy_models.py:457-477; v is (C, 1, L)"""
+    logits = v
+    for i in range(5):
+        logits = torch.matmul(F.softplus(sd[f"{name}._matrix{i}"]), logits)
+        logits = logits + sd[f"{name}._bias{i}"]
+        if i < 4:
+            logits = logits + torch.tanh(sd[f"{name}._factor{i}"]) * torch.tanh(logits)
+    return logits
+
+
+def eb_likelihood(sd, name, v):
+    """entropy_models.py:480-492"""
+    lower = eb_logits_cumulative(sd, name, v - 0.5)
+    upper = eb_logits_cumulative(sd, name, v + 0.5)
+    sign = -torch.sign(lower + upper)
+    return torch.abs(torch.sigmoid(sign * upper) - torch.sigmoid(sign * lower))
+
+
+def eb_forward(sd, name, x, noise=None, lik_bound: float = 1e-9):
+    """entropy_models.py:495-540; returns (x_hat, likelihood) shaped like x (N, C, ...)."""
+    C = x.shape[1]
+    perm = [1, 0] + list(range(2, x.dim()))
+    xp = x.permute(*perm).contiguous()
+    shape = xp.shape
+    values = xp.reshape(C, 1, -1)
+    medians = sd[f"{name}.quantiles"][:, :, 1:2]
+    if noise is not None:
+        outputs = values + noise.permute(*perm).reshape(C, 1, -1)
+    else:
+        outputs = quantize(values, "dequantize", medians)
+    lik = eb_likelihood(sd, name, outputs)
+    if lik_bound > 0:
+        lik = lower_bound(lik, lik_bound)
+    outputs = outputs.reshape(shape).permute(*perm).contiguous()
+    lik = lik.reshape(shape).permute(*perm).contiguous()
+    return outputs, lik
+
+
+def gc_likelihood(x_hat, scales, means=None, scale_bound: float = 0.11):
+    """entropy_models.py:692-709"""
+    values = x_hat - means if means is not None else x_hat
+    scales = lower_bound(scales, scale_bound)
+    values = torch.abs(values)
+    const = float(-(2 ** -0.5))
+    upper = 0.5 * torch.erfc(const * ((0.5 - values) / scales))
+    lower = 0.5 * torch.erfc(const * ((-0.5 - values) / scales))
+    return upper - lower
+
+
+def gc_forward(x, scales, means=None, noise=None, scale_bound=0.11, lik_bound=1e-9):
+    """entropy_models.py:715-731"""
+    out = quantize(x, "noise" if noise is not None else "dequantize", means, noise)
+    lik = gc_likelihood(out, scales, means, scale_bound)
+    if lik_bound > 0:
+        lik = lower_bound(lik, lik_bound)
+    return out, lik
+
+
+def get_scale_table(lo: float = 0.11, hi: float = 256.0, levels: int = 64) -> Tensor:
+    """compressai/models/google.py:208-214"""
+    return torch.exp(torch.linspace(math.log(lo), math.log(hi), levels))
+
+
+def build_indexes(scales: Tensor, scale_table: Tensor, scale_bound: float = 0.11) -> Tensor:
+    """entropy_models.py:735-740"""
+    scales = lower_bound(scales, scale_bound)
+    indexes = scales.new_full(scales.size(), len(scale_table) - 1).int()
+    for s in scale_table[:-1]:
+        indexes -= (scales <= s).int()
+    return indexes
+
+
+def eb_build_indexes(size) -> Tensor:
+    """entropy_models.py:542-553"""
+    C = size[1]
+    view = [1] * len(size)
+    view[1] = -1
+    return torch.arange(C).view(*view).int().repeat(size[0], 1, *size[2:])
+
+
+# ---- models ---------------------------------------------------------------------------------
+def _seq_g_a(sd, x):
+    """models/google.py:143-151 (same layer stack in all three model families)"""
+    for i in (0, 2, 4):
+        x = gdn(sd, f"g_a.{i + 1}", conv(sd, f"g_a.{i}", x))
+    return conv(sd, "g_a.6", x)
+
+
+def _seq_g_s(sd, y_hat):
+    """models/google.py:153-161"""
+    x = y_hat
+    for i in (0, 2, 4):
+        x = gdn(sd, f"g_s.{i + 1}", deconv(sd, f"g_s.{i}", x), inverse=True)
+    return deconv(sd, "g_s.6", x)
+
+
+def factorized_forward(sd, x, noise=None):
+    """FactorizedPrior.forward: models/google.py:172-182"""
+    y = _seq_g_a(sd, x)
+    y_hat, y_lik = eb_forward(sd, "entropy_bottleneck", y, noise)
+    x_hat = _seq_g_s(sd, y_hat)
+    return {"x_hat": x_hat, "likelihoods": {"y": y_lik}, "y": y, "y_hat": y_hat}
+
+
+def _h_a(sd, y, act):
+    z = act(conv(sd, "h_a.0", y, stride=1))
+    z = act(conv(sd, "h_a.2", z))
+    return conv(sd, "h_a.4", z)
+
+
+def hyperprior_forward(sd, x):
+    """ScaleHyperprior.forward: models/google.py:281-295"""
+    y = _seq_g_a(sd, x)
+    z = _h_a(sd, torch.abs(y), F.relu)
+    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z)
+    s = F.relu(deconv(sd, "h_s.0", z_hat))
+    s = F.relu(deconv(sd, "h_s.2", s))
+    scales_hat = F.relu(conv(sd, "h_s.4", s, stride=1))
+    y_hat, y_lik = gc_forward(y, scales_hat)
+    x_hat = _seq_g_s(sd, y_hat)
+    return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "y": y, "z": z, "z_hat": z_hat,
+            "scales_hat": scales_hat, "y_hat": y_hat}
+
+
+def _mean_scale_params(sd, z_hat):
+    """MeanScaleHyperprior h_s: models/google.py:371-377"""
+    s = F.leaky_relu(deconv(sd, "h_s.0", z_hat))
+    s = F.leaky_relu(deconv(sd, "h_s.2", s))
+    return conv(sd, "h_s.4", s, stride=1)
+
+
+def mean_scale_forward(sd, x):
+    """MeanScaleHyperprior.forward: models/google.py:379-391"""
+    y = _seq_g_a(sd, x)
+    z = _h_a(sd, y, F.leaky_relu)
+    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z)
+    gaussian_params = _mean_scale_params(sd, z_hat)
+    scales_hat, means_hat = gaussian_params.chunk(2, 1)
+    y_hat, y_lik = gc_forward(y, scales_hat, means_hat)
+    x_hat = _seq_g_s(sd, y_hat)
+    return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "y": y, "z": z, "z_hat": z_hat,
+            "scales_hat": scales_hat, "means_hat": means_hat, "y_hat": y_hat}
+
+
+def mean_scale_compress_symbols(sd, x, scale_table):
+    """MeanScaleHyperprior.compress up to the int32 symbols/indexes handed to the rANS coder:
+    models/google.py:393-404 + entropy_models.py:237-246,559-566.  z_hat is what
+    entropy_bottleneck.decompress would return: dequantize(symbols, medians)."""
+    y = _seq_g_a(sd, x)
+    z = _h_a(sd, y, F.leaky_relu)
+    medians = sd["entropy_bottleneck.quantiles"][:, 0, 1].reshape(1, -1, 1, 1)
+    z_symbols = quantize(z, "symbols", medians)
+    z_indexes = eb_build_indexes(z.size())
+    z_hat = z_symbols.float() + medians
+    gaussian_params = _mean_scale_params(sd, z_hat)
+    scales_hat, means_hat = gaussian_params.chunk(2, 1)
+    y_indexes = build_indexes(scales_hat, scale_table)
+    y_symbols = quantize(y, "symbols", means_hat)
+    return {"y_symbols": y_symbols, "y_indexes": y_indexes, "z_symbols": z_symbols, "z_indexes": z_indexes,
+            "y": y, "z": z, "scales_hat": scales_hat, "means_hat": means_hat}
+
+
+def hyperprior_compress_symbols(sd, x, scale_table):
+    """ScaleHyperprior.compress up to symbols/indexes: models/google.py:324-332"""
+    y = _seq_g_a(sd, x)
+    z = _h_a(sd, torch.abs(y), F.relu)
+    medians = sd["entropy_bottleneck.quantiles"][:, 0, 1].reshape(1, -1, 1, 1)
+    z_symbols = quantize(z, "symbols", medians)
+    z_indexes = eb_build_indexes(z.size())
+    z_hat = z_symbols.float() + medians
+    s = F.relu(deconv(sd, "h_s.0", z_hat))
+    s = F.relu(deconv(sd, "h_s.2", s))
+    scales_hat = F.relu(conv(sd, "h_s.4", s, stride=1))
+    y_indexes = build_indexes(scales_hat, scale_table)
+    y_symbols = quantize(y, "symbols")
+    return {"y_symbols": y_symbols, "y_indexes": y_indexes, "z_symbols": z_symbols, "z_indexes": z_indexes,
+            "y": y, "z": z, "scales_hat": scales_hat}
+
+
+FORWARD = {"factorized": factorized_forward, "hyperprior": hyperprior_forward, "mean-scale": mean_scale_forward}
+
+
+def bpp(out, num_pixels: int) -> float:
+    """utils/eval_model/__main__t.py:197-200"""
+    return float(sum(torch.log(l).sum() / (-math.log(2) * num_pixels) for l in out["likelihoods"].values()))

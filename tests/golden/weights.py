@@ -1,0 +1,113 @@
+"""Deterministic, gain-calibrated weights for parity tests.
+
+The reference's zoo can only give random-init weights offline, and with those every latent is
+<< 1, every symbol is 0 and every CDF index is 0 -- parity would be vacuous.
+This recipe draws every parameter from ``numpy.random.RandomState`` (frozen MT19937 stream, so
+the values are identical wherever numpy runs) with per-layer gains chosen so that symbols span
+roughly [-25, 25] and the predicted scales populate most of the 64 scale-table bins.  The same
+arrays are loaded into the reference modules (when generating goldens) and into the mmcodec
+modules / the oracle (when testing), by ``state_dict`` key, which is the reference's contract
+(SURVEY.md Appendix D).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _conv_w(rs, cout, cin, k, gain):
+    return (rs.standard_normal((cout, cin, k, k)) * (gain / np.sqrt(cin * k * k))).astype(np.float32)
+
+
+def _deconv_w(rs, cin, cout, k, gain, stride=2):
+    return (rs.standard_normal((cin, cout, k, k)) * (gain / np.sqrt(cin * k * k / stride ** 2))).astype(np.float32)
+
+
+def _bias(rs, c, scale=0.1):
+    return (rs.standard_normal(c) * scale).astype(np.float32)
+
+
+def _gdn(rs, sd, name, C):
+    ped = 2.0 ** -36
+    beta = rs.uniform(0.5, 2.0, C)
+    gamma = 0.1 * np.eye(C) + np.abs(rs.standard_normal((C, C))) * 0.004
+    sd[name + ".beta"] = np.sqrt(beta + ped).astype(np.float32)
+    sd[name + ".gamma"] = np.sqrt(gamma + ped).astype(np.float32)
+
+
+def _entropy_bottleneck(rs, sd, name, C):
+    filters = (1, 3, 3, 3, 3, 1)
+    scale = 10.0 ** (1 / 5)
+    for i in range(5):
+        init = np.log(np.expm1(1 / scale / filters[i + 1]))
+        sd[f"{name}._matrix{i}"] = (init + rs.standard_normal((C, filters[i + 1], filters[i])) * 0.3).astype(np.float32)
+        sd[f"{name}._bias{i}"] = rs.uniform(-0.5, 0.5, (C, filters[i + 1], 1)).astype(np.float32)
+        if i < 4:
+            sd[f"{name}._factor{i}"] = (rs.standard_normal((C, filters[i + 1], 1)) * 0.5).astype(np.float32)
+    med = rs.standard_normal(C)
+    q = np.stack([med - rs.uniform(5, 15, C), med, med + rs.uniform(5, 15, C)], axis=1)
+    sd[f"{name}.quantiles"] = q.reshape(C, 1, 3).astype(np.float32)
+
+
+def make_state_dict(arch: str, N: int, M: int, seed: int = 0, in_ch: int = 3):
+    """arch in {"factorized", "hyperprior", "mean-scale"}; returns {key: np.ndarray(float32)}."""
+    rs = np.random.RandomState(seed)
+    sd = {}
+    # g_a: conv, GDN, conv, GDN, conv, GDN, conv   (models/google.py:143-151)
+    chans = [in_ch, N, N, N, M]
+    for li, i in enumerate((0, 2, 4, 6)):
+        gain = 3.0 if i < 6 else 5.0
+        sd[f"g_a.{i}.weight"] = _conv_w(rs, chans[li + 1], chans[li], 5, gain)
+        sd[f"g_a.{i}.bias"] = _bias(rs, chans[li + 1])
+        if i < 6:
+            _gdn(rs, sd, f"g_a.{i + 1}", N)
+    # g_s: deconv, IGDN, ... , deconv   (models/google.py:153-161)
+    chans = [M, N, N, N, in_ch]
+    for li, i in enumerate((0, 2, 4, 6)):
+        gain = 0.12 if i == 0 else (0.5 if i < 6 else 0.3)
+        sd[f"g_s.{i}.weight"] = _deconv_w(rs, chans[li], chans[li + 1], 5, gain)
+        sd[f"g_s.{i}.bias"] = _bias(rs, chans[li + 1])
+        if i < 6:
+            _gdn(rs, sd, f"g_s.{i + 1}", N)
+    if arch == "factorized":
+        _entropy_bottleneck(rs, sd, "entropy_bottleneck", M)
+        return sd
+    _entropy_bottleneck(rs, sd, "entropy_bottleneck", N)
+    # h_a: conv3x3 s1, act, conv5 s2, act, conv5 s2   (models/google.py:254-260,363-369)
+    sd["h_a.0.weight"] = _conv_w(rs, N, M, 3, 1.0)
+    sd["h_a.0.bias"] = _bias(rs, N)
+    sd["h_a.2.weight"] = _conv_w(rs, N, N, 5, 1.0)
+    sd["h_a.2.bias"] = _bias(rs, N)
+    sd["h_a.4.weight"] = _conv_w(rs, N, N, 5, 1.0)
+    sd["h_a.4.bias"] = _bias(rs, N, 0.5)
+    if arch == "hyperprior":
+        # h_s: deconv(N,N), ReLU, deconv(N,N), ReLU, conv3x3(N,M), ReLU   (models/google.py:262-269)
+        sd["h_s.0.weight"] = _deconv_w(rs, N, N, 5, 1.0)
+        sd["h_s.0.bias"] = _bias(rs, N)
+        sd["h_s.2.weight"] = _deconv_w(rs, N, N, 5, 1.5)
+        sd["h_s.2.bias"] = _bias(rs, N)
+        sd["h_s.4.weight"] = _conv_w(rs, M, N, 3, 2.0)
+        sd["h_s.4.bias"] = (_bias(rs, M, 0.3) + 2.0).astype(np.float32)
+    elif arch == "mean-scale":
+        # h_s: deconv(N,M), LeakyReLU, deconv(M,3M/2), LeakyReLU, conv3x3(3M/2, 2M)   (models/google.py:371-377)
+        M32 = M * 3 // 2
+        sd["h_s.0.weight"] = _deconv_w(rs, N, M, 5, 1.0)
+        sd["h_s.0.bias"] = _bias(rs, M)
+        sd["h_s.2.weight"] = _deconv_w(rs, M, M32, 5, 1.5)
+        sd["h_s.2.bias"] = _bias(rs, M32)
+        w = _conv_w(rs, 2 * M, M32, 3, 2.0)
+        w[M:] *= 0.25  # second half of the channels are the means (models/google.py:384)
+        sd["h_s.4.weight"] = w
+        b = _bias(rs, 2 * M, 0.3)
+        b[:M] += 2.0
+        sd["h_s.4.bias"] = b.astype(np.float32)
+    else:
+        raise ValueError(arch)
+    return sd
+
+
+def make_image(B: int, H: int, W: int, seed: int = 1234, C: int = 3):
+    """Smooth-ish synthetic image batch in [0, 1] (low-pass noise + fine noise)."""
+    rs = np.random.RandomState(seed)
+    coarse = rs.uniform(0, 1, (B, C, (H + 7) // 8, (W + 7) // 8))
+    img = np.kron(coarse, np.ones((8, 8)))[:, :, :H, :W] * 0.8 + rs.uniform(0, 0.2, (B, C, H, W))
+    return img.astype(np.float32)

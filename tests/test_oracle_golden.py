@@ -1,0 +1,166 @@
+"""Pins the CPU oracle (oracle/oracle.c + oracle/torch_port.py) to the reference's own outputs
+(tests/golden/*.npz, produced by tests/golden/gen_golden.py from /root/reference/CompressAI) and
+to the reference's known-answer tests.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import torch_port as tp
+from weights import make_state_dict
+
+
+def rel_err(a, b, floor):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+
+
+def test_quantize_kat(kernels_golden):
+    g = kernels_golden
+    # reference KAT, SURVEY.md Appendix C / tests/test_entropy_models.py:74-79
+    assert np.array_equal(oracle.quantize_symbols(g["q_kat_x"]), g["q_kat_sym"])
+    assert np.array_equal(oracle.quantize_symbols(np.array([0.5, 1.5, 2.5, -0.5, -1.5, -2.5, -0.0], np.float32)),
+                          np.array([0, 2, 2, 0, -2, -2, 0], np.int32))
+
+
+def test_quantize_dequantize(kernels_golden):
+    g = kernels_golden
+    x, m = g["q_x"], g["q_means"]
+    assert np.array_equal(oracle.quantize_symbols(x, m), g["q_sym_means"])
+    assert np.array_equal(oracle.quantize_dequantize(x, m), g["q_deq_means"])
+    assert np.array_equal(oracle.quantize_symbols(x), g["q_sym_nomeans"])
+    assert np.array_equal(oracle.quantize_dequantize(x), g["q_deq_nomeans"])
+    C, inner = x.shape[1], x.shape[2] * x.shape[3]
+    assert np.array_equal(oracle.quantize_symbols(x, g["q_chmeans"], C=C, inner=inner), g["q_sym_chmeans"])
+    assert np.array_equal(oracle.dequantize(g["q_sym_means"], m), g["dq_means"])
+    assert np.array_equal(oracle.dequantize(g["q_sym_means"]), g["dq_nomeans"])
+
+
+def test_build_indexes(kernels_golden):
+    g = kernels_golden
+    assert np.array_equal(oracle.build_indexes(g["bi_scales"], g["scale_table"]), g["bi_indexes"])
+    # SURVEY.md Appendix C vector
+    t = g["scale_table"]
+    s = np.array([-1, 0, 0.11, t[0], t[1], 1.0, t[62], 200, 256, 1e6, np.nan], np.float32)
+    assert oracle.build_indexes(s, t).tolist() == [0, 0, 0, 0, 1, 18, 62, 61, 63, 63, 63]
+    # torch port agrees too
+    assert np.array_equal(tp.build_indexes(torch.from_numpy(g["bi_scales"]), torch.from_numpy(t)).numpy(), g["bi_indexes"])
+    assert np.array_equal(tp.get_scale_table().numpy(), t)
+
+
+def test_channel_indexes(kernels_golden):
+    assert np.array_equal(oracle.channel_indexes((2, 8, 3, 5)), kernels_golden["eb_indexes"])
+
+
+def test_gc_forward(kernels_golden):
+    g = kernels_golden
+    y, s, m = g["gc_y"], g["gc_scales"], g["gc_means"]
+    yh, lik = oracle.gc_forward(y, s, m)
+    assert np.array_equal(yh, g["gc_yhat_means"])
+    assert rel_err(lik, g["gc_lik_means"], 1e-9) < 1e-4
+    yh, lik = oracle.gc_forward(y, s)
+    assert np.array_equal(yh, g["gc_yhat_nomeans"])
+    assert rel_err(lik, g["gc_lik_nomeans"], 1e-9) < 1e-4
+    yh, lik = oracle.gc_forward(y, s, m, noise=g["gc_noise"])
+    assert np.array_equal(yh, g["gc_yhat_noise"])
+    assert rel_err(lik, g["gc_lik_noise"], 1e-9) < 1e-4
+    # floor: forward(y=50, sigma=2) -> 1e-9
+    _, l = oracle.gc_forward(np.array([50.0], np.float32), np.array([2.0], np.float32))
+    assert l[0] == np.float32(1e-9)
+
+
+def _eb_lists(g):
+    return ([g[f"eb_param__matrix{i}"] for i in range(5)], [g[f"eb_param__bias{i}"] for i in range(5)],
+            [g[f"eb_param__factor{i}"] for i in range(4)])
+
+
+def test_eb_forward(kernels_golden):
+    g = kernels_golden
+    mats, bias, fac = _eb_lists(g)
+    med = g["eb_param_quantiles"][:, 0, 1]
+    x = g["eb_x"]
+    C, inner = x.shape[1], x.shape[2] * x.shape[3]
+    xh, lik = oracle.eb_forward(x, mats, bias, fac, med, C, inner)
+    assert np.array_equal(xh, g["eb_xhat"])
+    assert rel_err(lik, g["eb_lik"], 1e-9) < 1e-4
+    xh, lik = oracle.eb_forward(x, mats, bias, fac, med, C, inner, noise=g["eb_noise"])
+    assert np.array_equal(xh, g["eb_xhat_noise"])
+    assert rel_err(lik, g["eb_lik_noise"], 1e-9) < 1e-4
+    lg = oracle.eb_logits_cumulative(x, mats, bias, fac, C, inner)
+    assert np.max(np.abs(lg - g["eb_logits"])) < 2e-4
+    xh, lik = oracle.eb_forward(g["eb_x_2d"], mats, bias, fac, med, C, 1)
+    assert np.array_equal(xh, g["eb_xhat_2d"])
+    assert rel_err(lik, g["eb_lik_2d"], 1e-9) < 1e-4
+
+
+def test_gdn(kernels_golden):
+    g = kernels_golden
+    x = g["gdn_x"]
+    y = oracle.gdn_forward(x, g["gdn_beta"], g["gdn_gamma"])
+    assert np.max(np.abs(y - g["gdn_y"])) < 1e-5
+    y = oracle.gdn_forward(x, g["gdn_beta"], g["gdn_gamma"], inverse=True)
+    assert np.max(np.abs(y - g["gdn_y_inv"]) / np.maximum(np.abs(g["gdn_y_inv"]), 1.0)) < 1e-5
+    # closed form at init, tests/test_layers.py:145-146: y = x / sqrt(1 + 0.1 x^2)
+    C = x.shape[1]
+    ped = 2.0 ** -36
+    beta0 = np.sqrt(np.ones(C) + ped).astype(np.float32)
+    gamma0 = np.sqrt(0.1 * np.eye(C) + ped).astype(np.float32)
+    y0 = oracle.gdn_forward(x, beta0, gamma0)
+    assert np.max(np.abs(y0 - x / np.sqrt(1 + 0.1 * x ** 2))) < 1e-5
+    assert np.max(np.abs(y0 - g["gdn_init_y"])) < 1e-5
+
+
+def test_lower_bound(kernels_golden):
+    g = kernels_golden
+    y = oracle.lower_bound(g["lb_x"], 0.11)
+    assert np.array_equal(y, g["lb_y"], equal_nan=True)
+    dx = oracle.lower_bound_bwd(g["lb_x"], g["lb_g"], 0.11)
+    assert np.array_equal(dx, g["lb_dx"])
+
+
+def test_pmf_to_quantized_cdf(kernels_golden):
+    g = kernels_golden
+    # reference KAT tests/test_ops.py:104-106
+    assert oracle.pmf_to_quantized_cdf([0.1, 0.2, 0, 0], 16).tolist() == [0, 21845, 65534, 65535, 65536]
+    assert np.array_equal(oracle.pmf_to_quantized_cdf([0.1, 0.2, 0, 0], 16), g["cdf_kat"])
+    for p, c, L in zip(g["cdf_pmfs"], g["cdf_cdfs"], g["cdf_lens"]):
+        assert np.array_equal(oracle.pmf_to_quantized_cdf(p[:L], 16), c[:L + 1])
+    for bad in ([-0.1, 0.5], [float("inf"), 0.5], [float("nan"), 0.5]):  # tests/test_ops.py:108-118
+        with pytest.raises(ValueError):
+            oracle.pmf_to_quantized_cdf(bad, 16)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_conv_deconv(kernels_golden, tag):
+    g = kernels_golden
+    k, s = g[f"conv_{tag}_cfg"]
+    y = oracle.conv2d(g[f"conv_{tag}_x"], g[f"conv_{tag}_w"], g[f"conv_{tag}_b"], stride=int(s))
+    assert y.shape == g[f"conv_{tag}_y"].shape
+    assert np.max(np.abs(y - g[f"conv_{tag}_y"])) < 1e-4
+    k, s = g[f"deconv_{tag}_cfg"]
+    y = oracle.conv_transpose2d(g[f"deconv_{tag}_x"], g[f"deconv_{tag}_w"], g[f"deconv_{tag}_b"], stride=int(s))
+    assert y.shape == g[f"deconv_{tag}_y"].shape
+    assert np.max(np.abs(y - g[f"deconv_{tag}_y"])) < 1e-4
+
+
+@pytest.mark.parametrize("arch,N,M", [("factorized", 128, 192), ("hyperprior", 128, 192), ("mean-scale", 192, 320)])
+def test_torch_port_models(models_golden, arch, N, M):
+    """The torch port reproduces the reference model forward and its compress() symbols/indexes."""
+    g = models_golden
+    tag = arch.replace("-", "_")
+    sd = {k: torch.from_numpy(v) for k, v in make_state_dict(arch, N, M, seed=0).items()}
+    x = torch.from_numpy(g["x"])
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        out = tp.FORWARD[arch](sd, x)
+    assert np.max(np.abs(out["x_hat"].numpy() - g[f"{tag}_x_hat"])) < 1e-4
+    for k, l in out["likelihoods"].items():
+        assert rel_err(l.numpy(), g[f"{tag}_lik_{k}"], 1e-9) < 1e-4
+    B = x.shape[0]
+    if arch == "factorized":
+        return
+    fn = tp.hyperprior_compress_symbols if arch == "hyperprior" else tp.mean_scale_compress_symbols
+    with torch.no_grad():
+        c = fn(sd, x, tp.get_scale_table())
+    for name in ("y_symbols", "y_indexes", "z_symbols", "z_indexes"):
+        assert np.array_equal(c[name].reshape(B, -1).numpy(), g[f"{tag}_{name}"]), name
+    assert c["y_symbols"].abs().max() > 5 and c["y_indexes"].unique().numel() > 20  # non-degenerate fixture
