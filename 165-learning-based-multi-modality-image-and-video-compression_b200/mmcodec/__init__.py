@@ -1,0 +1,18 @@
+"""mmcodec -- B200-native (sm_100a) hot path of the CompressAI-based multi-modality learned codec
+(SZU-AdvTech-2022/165).  The public surface mirrors the reference's modules:
+
+    mmcodec.layers           GDN, conv, deconv, LowerBound, NonNegativeParametrizer
+    mmcodec.entropy_models   EntropyModel, EntropyBottleneck, GaussianConditional
+    mmcodec.models           CompressionModel, FactorizedPrior, ScaleHyperprior, MeanScaleHyperprior
+    mmcodec.ops              functional access to every entry point of include/mmcodec.h
+
+All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
+"""
+from . import _lib, entropy_models, layers, models, ops, transforms  # noqa: F401
+from ._lib import MmcodecError, build  # noqa: F401
+from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional  # noqa: F401
+from .layers import GDN, LowerBound, NonNegativeParametrizer, conv, deconv  # noqa: F401
+from .models import (CompressionModel, FactorizedPrior, MeanScaleHyperprior, ScaleHyperprior,  # noqa: F401
+                     build_model, get_scale_table)
+
+__version__ = "0.1.0"

@@ -1,0 +1,314 @@
+"""Host-side mirror of ``compressai.models.google`` for the hot path: CompressionModel,
+FactorizedPrior, ScaleHyperprior, MeanScaleHyperprior with the reference's constructor
+arguments, sub-module names (hence ``state_dict`` keys) and return structures
+(compressai/models/google.py:58-416).  ``forward`` keeps every intermediate on the device in the
+kernels' native layouts: NHWC bf16 between transform layers, NHWC fp32 for the latents that feed
+the entropy stage; tensors returned to the caller have the reference's logical (N, C, H, W) shape
+(channels-last strided for the latent-sized ones, planar for x_hat).
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import ops
+from .entropy_models import EntropyBottleneck, GaussianConditional
+from .layers import GDN, conv, deconv
+from .transforms import TransformStack, run_layers
+
+__all__ = ["CompressionModel", "FactorizedPrior", "ScaleHyperprior", "MeanScaleHyperprior", "get_scale_table",
+           "SCALES_MIN", "SCALES_MAX", "SCALES_LEVELS", "MODELS", "CFGS", "build_model"]
+
+SCALES_MIN = 0.11
+SCALES_MAX = 256
+SCALES_LEVELS = 64
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
+    """compressai/models/google.py:208-214 (computed on the host by torch, then kept as a buffer)"""
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+def _resize_registered_buffers(module, module_name, buffer_names, state_dict):
+    """Resize variable-length CDF buffers before load_state_dict (compressai/models/utils.py:90-125)."""
+    for name in buffer_names:
+        key = f"{module_name}.{name}"
+        if key not in state_dict:
+            raise RuntimeError(f'Missing key "{key}" in state_dict')
+        new = state_dict[key]
+        cur = getattr(module, name)
+        if cur.shape != new.shape:
+            setattr(module, name, torch.empty(new.shape, dtype=cur.dtype, device=cur.device))
+
+
+def _nhwc_to_logical(t: Tensor) -> Tensor:
+    return t.permute(0, 3, 1, 2)
+
+
+class CompressionModel(nn.Module):
+    """compressai/models/google.py:58-123"""
+
+    def __init__(self, entropy_bottleneck_channels, init_weights=None):
+        super().__init__()
+        self.entropy_bottleneck = EntropyBottleneck(entropy_bottleneck_channels)
+        if init_weights is not None:
+            warnings.warn("init_weights was removed as it was never functional", DeprecationWarning)
+
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def _tag_layer_names(self):
+        """Give every conv its state_dict prefix (g_a.0, h_s.4, ...) for profiling labels."""
+        for name, m in self.named_modules():
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                m._mmc_name = name
+
+    def forward(self, *args):
+        raise NotImplementedError()
+
+    def update(self, force=False):
+        updated = False
+        for m in self.children():
+            if not isinstance(m, EntropyBottleneck):
+                continue
+            updated |= m.update(force=force)
+        return updated
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        _resize_registered_buffers(self.entropy_bottleneck, "entropy_bottleneck",
+                                   ["_quantized_cdf", "_offset", "_cdf_length"], state_dict)
+        return super().load_state_dict(state_dict, strict=strict)
+
+    @staticmethod
+    def bpp(out, num_pixels=None) -> float:
+        """sum over likelihood tensors of log(l).sum() / (-ln2 * pixels)
+        (compressai/utils/eval_model/__main__t.py:197-200), reduced on the device."""
+        acc = None
+        for lk in out["likelihoods"].values():
+            acc = ops.bits(lk, acc)
+        if num_pixels is None:
+            x = out["x_hat"]
+            num_pixels = x.size(0) * x.size(2) * x.size(3)
+        return float(acc.item()) / num_pixels
+
+
+def _g_a(N, M, channel):
+    return TransformStack(conv(channel, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
+
+
+def _g_s(N, M, channel):
+    return TransformStack(deconv(M, N), GDN(N, inverse=True), deconv(N, N), GDN(N, inverse=True), deconv(N, N),
+                          GDN(N, inverse=True), deconv(N, channel))
+
+
+class FactorizedPrior(CompressionModel):
+    """compressai/models/google.py:127-204"""
+
+    def __init__(self, N, M, channel=3, **kwargs):
+        super().__init__(entropy_bottleneck_channels=M, **kwargs)
+        self.g_a = _g_a(N, M, channel)
+        self.g_s = _g_s(N, M, channel)
+        self.N = N
+        self.M = M
+        self._tag_layer_names()
+
+    @property
+    def downsampling_factor(self) -> int:
+        return 2 ** 4
+
+    def forward(self, x):
+        """models/google.py:172-182"""
+        eb = self.entropy_bottleneck
+        y = run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32")
+        y_l = _nhwc_to_logical(y)
+        noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
+        y_hat, y_lik, y_hat_bf16 = ops.eb_forward(y_l, eb._params(), noise, eb._lik_bound(), want_bf16=True)
+        x_hat = run_layers(list(self.g_s), y_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nchw_f32")
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik}}
+
+    @classmethod
+    def from_state_dict(cls, state_dict, channel=3):
+        N = state_dict["g_a.0.weight"].size(0)
+        M = state_dict["g_a.6.weight"].size(0)
+        net = cls(N, M, channel=channel)
+        net.load_state_dict(state_dict)
+        return net
+
+    def symbols_and_indexes(self, x):
+        """compress() up to the rANS call (models/google.py:196-199)."""
+        y = _nhwc_to_logical(run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32"))
+        y_symbols, y_indexes = self.entropy_bottleneck.symbols_and_indexes(y)
+        return {"y_symbols": y_symbols, "y_indexes": y_indexes, "shape": y.size()[-2:]}
+
+    def compress(self, x):
+        self.symbols_and_indexes(x)
+        return self.entropy_bottleneck.compress(_nhwc_to_logical(run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32")))
+
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 1
+        return self.entropy_bottleneck.decompress(strings[0], shape)
+
+
+class ScaleHyperprior(CompressionModel):
+    """compressai/models/google.py:218-344"""
+
+    def __init__(self, N, M, channel=3, **kwargs):
+        super().__init__(entropy_bottleneck_channels=N, **kwargs)
+        self.g_a = _g_a(N, M, channel)
+        self.g_s = _g_s(N, M, channel)
+        self.h_a = TransformStack(conv(M, N, stride=1, kernel_size=3), nn.ReLU(inplace=True), conv(N, N),
+                                  nn.ReLU(inplace=True), conv(N, N))
+        self.h_s = TransformStack(deconv(N, N), nn.ReLU(inplace=True), deconv(N, N), nn.ReLU(inplace=True),
+                                  conv(N, M, stride=1, kernel_size=3), nn.ReLU(inplace=True))
+        self.gaussian_conditional = GaussianConditional(None)
+        self.N = int(N)
+        self.M = int(M)
+        self._tag_layer_names()
+
+    @property
+    def downsampling_factor(self) -> int:
+        return 2 ** (4 + 2)
+
+    # -- shared pieces -------------------------------------------------------------------------
+    def _analysis(self, x):
+        """y = g_a(x) (fp32 NHWC) and z = h_a(|y|) (fp32 NHWC); |y| is written by g_a's last kernel."""
+        y, y_abs = run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32", out2=1)
+        z = run_layers(list(self.h_a), y_abs, "nhwc_bf16", "nhwc_f32")
+        return y, z
+
+    def forward(self, x):
+        """models/google.py:281-295"""
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y, z = self._analysis(x)
+        z_l = _nhwc_to_logical(z)
+        z_noise = torch.empty_like(z_l).uniform_(-0.5, 0.5) if self.training else None
+        z_hat, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True)
+        scales_hat = run_layers(list(self.h_s), z_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nhwc_f32")
+        y_l = _nhwc_to_logical(y)
+        y_noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
+        y_hat, y_lik, y_hat_bf16 = ops.gc_forward(y_l, _nhwc_to_logical(scales_hat), None, y_noise,
+                                                  gc.lower_bound_scale._sync_bound(), gc._lik_bound(), want_bf16=True)
+        x_hat = run_layers(list(self.g_s), y_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nchw_f32")
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        _resize_registered_buffers(self.gaussian_conditional, "gaussian_conditional",
+                                   ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        return super().load_state_dict(state_dict, strict=strict)
+
+    @classmethod
+    def from_state_dict(cls, state_dict, channel=3):
+        N = state_dict["g_a.0.weight"].size(0)
+        M = state_dict["g_a.6.weight"].size(0)
+        net = cls(N, M, channel=channel)
+        net.load_state_dict(state_dict)
+        return net
+
+    def update(self, scale_table=None, force=False):
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= super().update(force=force)
+        return updated
+
+    def _z_path(self, z):
+        """z symbols/indexes and z_hat = dequantize(symbols, medians), i.e. what
+        entropy_bottleneck.decompress(entropy_bottleneck.compress(z)) returns (models/google.py:327-328)."""
+        eb = self.entropy_bottleneck
+        z_l = _nhwc_to_logical(z)
+        z_symbols, z_indexes = eb.symbols_and_indexes(z_l)
+        medians = eb._get_medians().detach().reshape(1, -1, 1, 1)
+        z_hat = eb.dequantize(z_symbols, medians)
+        return z_symbols, z_indexes, z_hat
+
+    def symbols_and_indexes(self, x):
+        """compress() up to the two rANS calls (models/google.py:324-332)."""
+        gc = self.gaussian_conditional
+        y, z = self._analysis(x)
+        z_symbols, z_indexes, z_hat = self._z_path(z)
+        z_hat_bf16 = ops.to_bf16(z_hat).permute(0, 2, 3, 1)
+        scales_hat = _nhwc_to_logical(run_layers(list(self.h_s), z_hat_bf16, "nhwc_bf16", "nhwc_f32"))
+        y_indexes = gc.build_indexes(scales_hat)
+        y_symbols, y_indexes = gc.symbols_and_indexes(_nhwc_to_logical(y), y_indexes)
+        return {"y_symbols": y_symbols, "y_indexes": y_indexes, "z_symbols": z_symbols, "z_indexes": z_indexes,
+                "shape": z_symbols.size()[-2:]}
+
+    def compress(self, x):
+        self.symbols_and_indexes(x)
+        raise NotImplementedError("rANS byte coder not part of libmmcodec yet; see symbols_and_indexes()")
+
+    def decompress(self, strings, shape):
+        assert isinstance(strings, list) and len(strings) == 2
+        return self.entropy_bottleneck.decompress(strings[1], shape)
+
+
+class MeanScaleHyperprior(ScaleHyperprior):
+    """compressai/models/google.py:348-416"""
+
+    def __init__(self, N, M, channel=3, **kwargs):
+        super().__init__(N, M, channel, **kwargs)
+        self.h_a = TransformStack(conv(M, N, stride=1, kernel_size=3), nn.LeakyReLU(inplace=True), conv(N, N),
+                                  nn.LeakyReLU(inplace=True), conv(N, N))
+        self.h_s = TransformStack(deconv(N, M), nn.LeakyReLU(inplace=True), deconv(M, M * 3 // 2),
+                                  nn.LeakyReLU(inplace=True), conv(M * 3 // 2, M * 2, stride=1, kernel_size=3))
+        self._tag_layer_names()
+
+    def _analysis(self, x):
+        """No abs() in the mean-scale model (models/google.py:381): h_a reads y itself."""
+        y, y_bf16 = run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32", out2=2)
+        z = run_layers(list(self.h_a), y_bf16, "nhwc_bf16", "nhwc_f32")
+        return y, z
+
+    def _gaussian_params(self, z_hat_bf16_nhwc):
+        """scales_hat, means_hat = h_s(z_hat).chunk(2, 1) (models/google.py:383-384) as NHWC fp32 views."""
+        params = run_layers(list(self.h_s), z_hat_bf16_nhwc, "nhwc_bf16", "nhwc_f32")   # (B, H, W, 2M)
+        return params[..., : self.M], params[..., self.M:]
+
+    def forward(self, x):
+        """models/google.py:379-391"""
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        y, z = self._analysis(x)
+        z_l = _nhwc_to_logical(z)
+        z_noise = torch.empty_like(z_l).uniform_(-0.5, 0.5) if self.training else None
+        z_hat, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True)
+        scales_hat, means_hat = self._gaussian_params(z_hat_bf16.permute(0, 2, 3, 1))
+        y_l = _nhwc_to_logical(y)
+        y_noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
+        y_hat, y_lik, y_hat_bf16 = ops.gc_forward(y_l, _nhwc_to_logical(scales_hat), _nhwc_to_logical(means_hat), y_noise,
+                                                  gc.lower_bound_scale._sync_bound(), gc._lik_bound(), want_bf16=True)
+        x_hat = run_layers(list(self.g_s), y_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nchw_f32")
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}
+
+    def symbols_and_indexes(self, x):
+        """compress() up to the two rANS calls (models/google.py:393-404)."""
+        gc = self.gaussian_conditional
+        y, z = self._analysis(x)
+        z_symbols, z_indexes, z_hat = self._z_path(z)
+        scales_hat, means_hat = self._gaussian_params(ops.to_bf16(z_hat).permute(0, 2, 3, 1))
+        y_indexes = gc.build_indexes(_nhwc_to_logical(scales_hat))
+        y_symbols, y_indexes = gc.symbols_and_indexes(_nhwc_to_logical(y), y_indexes, means=_nhwc_to_logical(means_hat))
+        return {"y_symbols": y_symbols, "y_indexes": y_indexes, "z_symbols": z_symbols, "z_indexes": z_indexes,
+                "shape": z_symbols.size()[-2:]}
+
+
+MODELS = {"bmshj2018-factorized": FactorizedPrior, "bmshj2018-hyperprior": ScaleHyperprior, "mbt2018-mean": MeanScaleHyperprior}
+
+# (N, M) per quality, compressai/zoo/image.py:189-220
+CFGS = {
+    "bmshj2018-factorized": {q: ((128, 192) if q <= 5 else (192, 320)) for q in range(1, 9)},
+    "bmshj2018-hyperprior": {q: ((128, 192) if q <= 5 else (192, 320)) for q in range(1, 9)},
+    "mbt2018-mean": {q: ((128, 192) if q <= 4 else (192, 320)) for q in range(1, 9)},
+}
+
+
+def build_model(architecture: str, quality: int, channel: int = 3, **kwargs):
+    """Random-init model by zoo name (compressai/zoo/image.py:249-273 without the pretrained download)."""
+    if architecture not in MODELS:
+        raise ValueError(f'Invalid architecture name "{architecture}"')
+    if quality not in CFGS[architecture]:
+        raise ValueError(f'Invalid quality value "{quality}"')
+    return MODELS[architecture](*CFGS[architecture][quality], channel=channel, **kwargs)

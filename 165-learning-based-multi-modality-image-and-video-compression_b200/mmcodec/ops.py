@@ -1,0 +1,402 @@
+"""Functional front-end of the C ABI on torch CUDA tensors.
+
+torch is plumbing here (device memory, streams); every function enqueues hand-written kernels of
+libmmcodec.so on the current CUDA stream.  CPU tensors are rejected: there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmcodec runs on CUDA tensors only (B200 / sm_100a); got a CPU tensor. "
+                               "There is no CPU fallback.")
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32c(t: Tensor) -> Tensor:
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def _is_channels_last(t: Tensor) -> bool:
+    return t.dim() >= 3 and not t.is_contiguous() and t.permute(0, *range(2, t.dim()), 1).is_contiguous()
+
+
+def _view_oci(t: Tensor) -> Tuple[Tensor, int, int, int]:
+    """Return (tensor, outer, C, inner) for a logical (N, C, *spatial) tensor, keeping a channels-last
+    memory layout if it has one, otherwise forcing NCHW-contiguous."""
+    if t.dim() < 2:
+        raise ValueError("expected a tensor with at least 2 dimensions (N, C, ...)")
+    C = t.shape[1]
+    if _is_channels_last(t):
+        return t, t.numel() // C if C else 0, C, 1
+    t = t.contiguous()
+    inner = int(np.prod(t.shape[2:])) if t.dim() > 2 else 1
+    return t, t.shape[0], C, inner
+
+
+def _like_layout(t: Tensor, ref: Tensor) -> Tensor:
+    """Make t (same logical shape as ref) share ref's memory layout."""
+    t = t.expand_as(ref) if t.shape != ref.shape else t
+    if t.stride() == ref.stride() and t.dtype == torch.float32:
+        return t
+    out = torch.empty_like(ref, dtype=torch.float32)
+    out.copy_(t)
+    return out
+
+
+def _means_arg(x: Tensor, means: Optional[Tensor], C: int):
+    """Classify a broadcastable means tensor: none / per-channel / full."""
+    if means is None:
+        return L.MEANS_NONE, None
+    if means.dim() == x.dim() and means.shape[1] == C and means.numel() == C:
+        return L.MEANS_PER_CHANNEL, _f32c(means.reshape(-1))
+    return L.MEANS_FULL, _like_layout(means, x)
+
+
+# ---- quantize / dequantize ---------------------------------------------------------------------
+def quantize_symbols(x: Tensor, means: Optional[Tensor] = None) -> Tensor:
+    """EntropyModel.quantize(x, "symbols", means) -> int32 (entropy_models.py:157-182)."""
+    _require_cuda(x, means)
+    x = x.float()
+    if x.dim() < 2:
+        xv, outer, C, inner = x.contiguous(), 1, 1, x.numel()
+    else:
+        xv, outer, C, inner = _view_oci(x)
+    mode, m = _means_arg(xv, means, C)
+    out = torch.empty_like(xv, dtype=torch.int32)
+    L.check(L.lib().mmc_quantize_symbols(_ptr(xv), _ptr(m), mode, outer, C, inner, _ptr(out), _stream()))
+    return out
+
+
+def quantize_dequantize(x: Tensor, means: Optional[Tensor] = None) -> Tensor:
+    """EntropyModel.quantize(x, "dequantize", means) (entropy_models.py:169-178)."""
+    _require_cuda(x, means)
+    x = x.float()
+    if x.dim() < 2:
+        xv, outer, C, inner = x.contiguous(), 1, 1, x.numel()
+    else:
+        xv, outer, C, inner = _view_oci(x)
+    mode, m = _means_arg(xv, means, C)
+    out = torch.empty_like(xv)
+    L.check(L.lib().mmc_quantize_dequantize(_ptr(xv), _ptr(m), mode, outer, C, inner, _ptr(out), _stream()))
+    return out
+
+
+def quantize_noise(x: Tensor, noise: Tensor) -> Tensor:
+    _require_cuda(x, noise)
+    x = _f32c(x)
+    noise = _f32c(noise)
+    out = torch.empty_like(x)
+    L.check(L.lib().mmc_quantize_noise(_ptr(x), _ptr(noise), x.numel(), _ptr(out), _stream()))
+    return out
+
+
+def dequantize(symbols: Tensor, means: Optional[Tensor] = None) -> Tensor:
+    """EntropyModel.dequantize (entropy_models.py:190-199)."""
+    _require_cuda(symbols, means)
+    s = symbols.int()
+    if s.dim() < 2:
+        sv, outer, C, inner = s.contiguous(), 1, 1, s.numel()
+    else:
+        sv, outer, C, inner = _view_oci(s)
+    mode, m = _means_arg(sv, means, C)
+    out = torch.empty_like(sv, dtype=torch.float32)
+    L.check(L.lib().mmc_dequantize(_ptr(sv), _ptr(m), mode, outer, C, inner, _ptr(out), _stream()))
+    return out
+
+
+def lower_bound(x: Tensor, bound: float) -> Tensor:
+    _require_cuda(x)
+    x = _f32c(x)
+    out = torch.empty_like(x)
+    L.check(L.lib().mmc_lower_bound(_ptr(x), float(bound), x.numel(), _ptr(out), _stream()))
+    return out
+
+
+def lower_bound_bwd(x: Tensor, grad_out: Tensor, bound: float) -> Tensor:
+    _require_cuda(x, grad_out)
+    x, g = _f32c(x), _f32c(grad_out)
+    out = torch.empty_like(x)
+    L.check(L.lib().mmc_lower_bound_bwd(_ptr(x), _ptr(g), float(bound), x.numel(), _ptr(out), _stream()))
+    return out
+
+
+def build_indexes(scales: Tensor, scale_table: Tensor, bound: float) -> Tensor:
+    """GaussianConditional.build_indexes (entropy_models.py:735-740)."""
+    _require_cuda(scales, scale_table)
+    s = scales.float()
+    if not (s.is_contiguous() or _is_channels_last(s)):
+        s = s.contiguous()
+    table = _f32c(scale_table)
+    out = torch.empty_like(s, dtype=torch.int32)
+    L.check(L.lib().mmc_build_indexes(_ptr(s), _ptr(table), table.numel(), float(bound), s.numel(), _ptr(out), _stream()))
+    return out
+
+
+def channel_indexes(size, device) -> Tensor:
+    """EntropyBottleneck._build_indexes (entropy_models.py:542-553)."""
+    size = tuple(int(s) for s in size)
+    out = torch.empty(size, dtype=torch.int32, device=device)
+    _require_cuda(out)
+    C = size[1]
+    inner = int(np.prod(size[2:])) if len(size) > 2 else 1
+    L.check(L.lib().mmc_channel_indexes(size[0], C, inner, _ptr(out), _stream()))
+    return out
+
+
+# ---- entropy models ----------------------------------------------------------------------------
+def make_eb_params(matrices, biases, factors, medians: Optional[Tensor]):
+    keep = [_f32c(t.detach()) for t in list(matrices) + list(biases) + list(factors)]
+    med = _f32c(medians.detach().reshape(-1)) if medians is not None else None
+    p = L.EbParams()
+    for k in range(5):
+        p.matrix[k] = keep[k].data_ptr()
+        p.bias[k] = keep[5 + k].data_ptr()
+    for k in range(4):
+        p.factor[k] = keep[10 + k].data_ptr()
+    p.medians = med.data_ptr() if med is not None else None
+    keep.append(med)
+    return p, keep
+
+
+def eb_forward(x: Tensor, params, noise: Optional[Tensor] = None, likelihood_bound: float = 1e-9,
+               want_bf16: bool = False, bits: Optional[Tensor] = None):
+    """EntropyBottleneck.forward on a logical (N, C, *spatial) tensor (entropy_models.py:495-540).
+    Returns (x_hat, likelihood[, x_hat_bf16]) in x's memory layout."""
+    _require_cuda(x, noise)
+    p, _keep = params
+    xv, outer, C, inner = _view_oci(x.float())
+    nz = _like_layout(noise, xv) if noise is not None else None
+    x_hat = torch.empty_like(xv)
+    lik = torch.empty_like(xv)
+    xb = torch.empty_like(xv, dtype=torch.bfloat16) if want_bf16 else None
+    with _Timed("entropy_bottleneck|eb"):
+        L.check(L.lib().mmc_eb_forward(_ptr(xv), _ptr(nz), ctypes.byref(p), float(likelihood_bound), outer, C, inner,
+                                       _ptr(x_hat), _ptr(xb), _ptr(lik), _ptr(bits), _stream()))
+    return (x_hat, lik, xb) if want_bf16 else (x_hat, lik)
+
+
+def eb_logits_cumulative(x: Tensor, params) -> Tensor:
+    """_logits_cumulative on a logical (N, C, *spatial) tensor (entropy_models.py:457-477)."""
+    _require_cuda(x)
+    p, _keep = params
+    xv, outer, C, inner = _view_oci(x.float())
+    out = torch.empty_like(xv)
+    L.check(L.lib().mmc_eb_logits_cumulative(_ptr(xv), ctypes.byref(p), outer, C, inner, _ptr(out), _stream()))
+    return out
+
+
+def gc_forward(x: Tensor, scales: Tensor, means: Optional[Tensor] = None, noise: Optional[Tensor] = None,
+               scale_bound: float = 0.11, likelihood_bound: float = 1e-9, want_bf16: bool = False,
+               bits: Optional[Tensor] = None):
+    """GaussianConditional.forward (entropy_models.py:715-731); elementwise, any common layout."""
+    _require_cuda(x, scales, means, noise)
+    xv = x.float()
+    if not (xv.is_contiguous() or _is_channels_last(xv)):
+        xv = xv.contiguous()
+    s = _like_layout(scales, xv)
+    m = _like_layout(means, xv) if means is not None else None
+    nz = _like_layout(noise, xv) if noise is not None else None
+    x_hat = torch.empty_like(xv)
+    lik = torch.empty_like(xv)
+    xb = torch.empty_like(xv, dtype=torch.bfloat16) if want_bf16 else None
+    with _Timed("gaussian_conditional|gc"):
+        L.check(L.lib().mmc_gc_forward(_ptr(xv), _ptr(s), _ptr(m), _ptr(nz), float(scale_bound), float(likelihood_bound),
+                                       xv.numel(), _ptr(x_hat), _ptr(xb), _ptr(lik), _ptr(bits), _stream()))
+    return (x_hat, lik, xb) if want_bf16 else (x_hat, lik)
+
+
+def bits(likelihood: Tensor, accum: Optional[Tensor] = None) -> Tensor:
+    """-sum(log2(likelihood)) accumulated into a 1-element fp32 tensor (examples/train.py:74-77)."""
+    _require_cuda(likelihood)
+    lk = likelihood.float()
+    if not (lk.is_contiguous() or _is_channels_last(lk)):
+        lk = lk.contiguous()
+    if accum is None:
+        accum = torch.zeros(1, dtype=torch.float32, device=lk.device)
+    L.check(L.lib().mmc_bits(_ptr(lk), lk.numel(), _ptr(accum), _stream()))
+    return accum
+
+
+def pmf_to_quantized_cdf(pmf, precision: int = 16):
+    """compressai._CXX.pmf_to_quantized_cdf (cpp_exts/ops/ops.cpp:40-109); host-side, returns list[int]."""
+    arr = np.ascontiguousarray(np.asarray(pmf, dtype=np.float32).reshape(-1))
+    cdf = np.empty(arr.size + 1, np.uint32)
+    L.check(L.lib().mmc_pmf_to_quantized_cdf_host(arr.ctypes.data, arr.size, int(precision), cdf.ctypes.data))
+    return cdf.tolist()
+
+
+# ---- GDN -----------------------------------------------------------------------------------------
+def gdn_reparam(beta: Tensor, gamma: Tensor, beta_bound: float, gamma_bound: float, pedestal: float,
+                want_bf16: bool = False):
+    _require_cuda(beta, gamma)
+    beta, gamma = _f32c(beta.detach()), _f32c(gamma.detach())
+    C = beta.numel()
+    be = torch.empty_like(beta)
+    ge = torch.empty_like(gamma)
+    gb = torch.empty_like(gamma, dtype=torch.bfloat16) if want_bf16 else None
+    L.check(L.lib().mmc_gdn_reparam(_ptr(beta), _ptr(gamma), C, float(beta_bound), float(gamma_bound), float(pedestal),
+                                    _ptr(be), _ptr(ge), _ptr(gb), _stream()))
+    return be, ge, gb
+
+
+def gdn_forward(x: Tensor, beta_eff: Tensor, gamma_eff: Tensor, inverse: bool) -> Tensor:
+    """GDN.forward on a logical (B, C, H, W) fp32 tensor (layers/gdn.py:77-92)."""
+    _require_cuda(x)
+    if x.dim() != 4:
+        raise ValueError("GDN expects a 4-D (B, C, H, W) tensor")
+    xv = x.float()
+    B, C, H, W = xv.shape
+    if _is_channels_last(xv):
+        layout = L.NHWC
+    else:
+        xv, layout = xv.contiguous(), L.NCHW
+    y = torch.empty_like(xv)
+    L.check(L.lib().mmc_gdn_forward(_ptr(xv), _ptr(beta_eff), _ptr(gamma_eff), int(bool(inverse)), B, C, H * W, layout,
+                                    _ptr(y), _stream()))
+    return y
+
+
+# ---- convolutions ----------------------------------------------------------------------------------
+def conv_desc(transposed, B, H, W, Cin, Cout, k, stride, in_dtype, in_layout, out_dtype, out_layout, act=L.ACT_NONE,
+              gdn=L.GDN_NONE, out2=0) -> L.ConvDesc:
+    return L.ConvDesc(int(bool(transposed)), B, H, W, Cin, Cout, k, stride, in_dtype, in_layout, out_dtype, out_layout,
+                      act, gdn, int(out2))
+
+
+def conv_out_size(d: L.ConvDesc) -> Tuple[int, int]:
+    ho, wo = ctypes.c_int(), ctypes.c_int()
+    L.check(L.lib().mmc_conv_out_size(ctypes.byref(d), ctypes.byref(ho), ctypes.byref(wo)))
+    return ho.value, wo.value
+
+
+def _alloc_out(d: L.ConvDesc, device):
+    Ho, Wo = conv_out_size(d)
+    dt = torch.float32 if d.out_dtype == L.F32 else torch.bfloat16
+    shape = (d.B, d.Cout, Ho, Wo) if d.out_layout == L.NCHW else (d.B, Ho, Wo, d.Cout)
+    y = torch.empty(shape, dtype=dt, device=device)
+    y2 = torch.empty((d.B, Ho, Wo, d.Cout), dtype=torch.bfloat16, device=device) if d.out2_bf16 else None
+    return y, y2
+
+
+def conv_forward_direct(d: L.ConvDesc, x: Tensor, w: Tensor, bias: Optional[Tensor], beta_eff=None, gamma_eff=None,
+                        name: str = "conv"):
+    """CUDA-core conv / deconv.  x is the raw buffer in the layout/dtype the descriptor names."""
+    _require_cuda(x, w)
+    y, y2 = _alloc_out(d, x.device)
+    with _Timed(name + "|direct"):
+        L.check(L.lib().mmc_conv_forward_direct(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(beta_eff),
+                                                _ptr(gamma_eff), _ptr(y), _ptr(y2), _stream()))
+    return (y, y2) if d.out2_bf16 else y
+
+
+def conv_pack_weights(d: L.ConvDesc, w: Tensor) -> Tensor:
+    _require_cuda(w)
+    nbytes = ctypes.c_size_t()
+    L.check(L.lib().mmc_conv_pack_weights(ctypes.byref(d), None, None, ctypes.byref(nbytes), None))
+    packed = torch.empty(nbytes.value, dtype=torch.uint8, device=w.device)
+    wf = _f32c(w.detach())
+    L.check(L.lib().mmc_conv_pack_weights(ctypes.byref(d), _ptr(wf), _ptr(packed), ctypes.byref(nbytes), _stream()))
+    return packed
+
+
+def conv_forward_tc(d: L.ConvDesc, x: Tensor, w_packed: Tensor, bias: Optional[Tensor], beta_eff=None,
+                    gamma_bf16=None, name: str = "conv"):
+    """Tensor-core (tcgen05) implicit-GEMM conv / deconv on NHWC bf16 input."""
+    _require_cuda(x, w_packed)
+    y, y2 = _alloc_out(d, x.device)
+    with _Timed(name + "|tc"):
+        L.check(L.lib().mmc_conv_forward_tc(ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(beta_eff),
+                                            _ptr(gamma_bf16), _ptr(y), _ptr(y2), _stream()))
+    return (y, y2) if d.out2_bf16 else y
+
+
+def nchw_to_nhwc_bf16(x: Tensor) -> Tensor:
+    _require_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    y = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().mmc_nchw_f32_to_nhwc_bf16(_ptr(x), B, C, H * W, _ptr(y), _stream()))
+    return y
+
+
+def to_bf16(x: Tensor) -> Tensor:
+    """fp32 -> bf16 copy of a dense tensor, keeping its memory layout."""
+    _require_cuda(x)
+    x = x.float()
+    if not (x.is_contiguous() or _is_channels_last(x)):
+        x = x.contiguous()
+    y = torch.empty_like(x, dtype=torch.bfloat16)
+    L.check(L.lib().mmc_f32_to_bf16(_ptr(x), x.numel(), _ptr(y), _stream()))
+    return y
+
+
+def nhwc_bf16_to_nchw(x: Tensor) -> Tensor:
+    _require_cuda(x)
+    B, H, W, C = x.shape
+    y = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    L.check(L.lib().mmc_nhwc_bf16_to_nchw_f32(_ptr(x.contiguous()), B, C, H * W, _ptr(y), _stream()))
+    return y
+
+
+# ---- optional per-launch device timing (bench.py roofline pass; off by default) ---------------------
+_profile = None
+
+
+def start_profile():
+    global _profile
+    _profile = []
+    return _profile
+
+
+def stop_profile():
+    """Returns {name: mean ms per launch} for everything recorded since start_profile()."""
+    global _profile
+    rec, _profile = _profile or [], None
+    torch.cuda.synchronize()
+    acc = {}
+    for name, e0, e1 in rec:
+        acc.setdefault(name, []).append(e0.elapsed_time(e1))
+    return {k: sum(v) / len(v) for k, v in acc.items()}
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _profile is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profile.append((self.name, self.e0, e1))
+
+
+def launch_count() -> int:
+    return int(L.lib().mmc_launch_count())
+
+
+def reset_launch_count() -> None:
+    L.lib().mmc_reset_launch_count()

@@ -1,0 +1,157 @@
+"""Executor for the analysis / synthesis / hyper transform stacks (g_a, g_s, h_a, h_s).
+
+A stack is the reference's ``nn.Sequential`` of conv/deconv layers, each optionally followed by GDN
+/ IGDN / ReLU / LeakyReLU (compressai/models/google.py:143-161,254-269,363-377).  The executor
+groups every conv with the op that follows it into ONE fused kernel launch, keeps activations
+between layers as NHWC bf16 and touches fp32 only at the API edges.
+
+Kernel choice per layer is by shape, not by backend: the tcgen05 implicit-GEMM kernel
+(``mmc_conv_forward_tc``) takes every layer with Cin % 64 == 0 and Cout % 16 == 0; the CUDA-core
+kernel (``mmc_conv_forward_direct``) takes the rest (3-channel image edges, odd test shapes).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib as L
+from . import ops
+
+FORMATS = ("nchw_f32", "nhwc_bf16", "nhwc_f32")
+
+# Set by mmcodec.config; tests flip it to cross-check the two kernels against each other.
+use_tensor_cores = False
+
+
+@dataclass
+class Step:
+    conv: nn.Module
+    transposed: bool
+    act: int = L.ACT_NONE
+    gdn: Optional[nn.Module] = None
+
+
+def parse_layers(layers) -> List[Step]:
+    from .layers import GDN
+    steps: List[Step] = []
+    for m in layers:
+        if isinstance(m, nn.ConvTranspose2d):
+            steps.append(Step(m, True))
+        elif isinstance(m, nn.Conv2d):
+            steps.append(Step(m, False))
+        elif isinstance(m, GDN):
+            if not steps or steps[-1].gdn is not None or steps[-1].act != L.ACT_NONE:
+                raise NotImplementedError("GDN must directly follow a conv/deconv layer in a fused stack")
+            steps[-1].gdn = m
+        elif isinstance(m, nn.LeakyReLU):
+            if not steps or steps[-1].gdn is not None or abs(m.negative_slope - 0.01) > 1e-12:
+                raise NotImplementedError("only LeakyReLU(0.01) directly after a conv/deconv is fused")
+            steps[-1].act = L.ACT_LEAKY_RELU
+        elif isinstance(m, nn.ReLU):
+            if not steps or steps[-1].gdn is not None:
+                raise NotImplementedError("ReLU must directly follow a conv/deconv layer in a fused stack")
+            steps[-1].act = L.ACT_RELU
+        else:
+            raise NotImplementedError(f"layer {type(m).__name__} is not part of the accelerated transform path")
+    for s in steps:
+        c = s.conv
+        k = c.kernel_size[0]
+        if (c.kernel_size[0] != c.kernel_size[1] or k not in (1, 3, 5) or c.stride[0] != c.stride[1]
+                or c.stride[0] not in (1, 2) or c.padding != (k // 2, k // 2) or c.dilation != (1, 1) or c.groups != 1
+                or (s.transposed and c.output_padding != (c.stride[0] - 1, c.stride[0] - 1))):
+            raise NotImplementedError("only conv()/deconv()-style layers (k in {1,3,5}, stride in {1,2}, padding=k//2, "
+                                      "output_padding=stride-1) are on the accelerated path")
+    return steps
+
+
+def _tc_eligible(cin: int, cout: int) -> bool:
+    return use_tensor_cores and hasattr(L.lib(), "mmc_conv_forward_tc") and tc_available() and cin % 64 == 0 and cout % 16 == 0
+
+
+_tc_ok = None
+
+
+def tc_available() -> bool:
+    global _tc_ok
+    if _tc_ok is None:
+        _tc_ok = True
+    return _tc_ok
+
+
+def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0):
+    """Run a conv stack.  ``x``: (B,C,H,W) fp32 for "nchw_f32", (B,H,W,C) for the NHWC formats.
+    Returns the output in ``out_fmt``; "nchw_f32" results may be channels-last strided views (same
+    logical shape and values as the reference's NCHW tensor).  With ``out2`` (1: |output|, 2: output)
+    also returns that tensor as NHWC bf16 (the h_a input, models/google.py:283,381)."""
+    assert in_fmt in FORMATS and out_fmt in FORMATS
+    ops._require_cuda(x)
+    steps = parse_layers(layers)
+    if not steps:
+        raise ValueError("empty transform stack")
+    with torch.no_grad():
+        cur, fmt = x, in_fmt
+        if fmt == "nchw_f32":
+            if x.dim() != 4:
+                raise ValueError("expected a 4-D (B, C, H, W) input")
+            cur = x.float()
+            if ops._is_channels_last(cur):
+                cur, fmt = cur.permute(0, 2, 3, 1), "nhwc_f32"   # already NHWC in memory
+            else:
+                cur = cur.contiguous()
+        y2 = None
+        for i, s in enumerate(steps):
+            last = i == len(steps) - 1
+            c = s.conv
+            cin, cout = (c.in_channels, c.out_channels)
+            if fmt == "nchw_f32":
+                B, C, H, W = cur.shape
+            else:
+                B, H, W, C = cur.shape
+            if C != cin:
+                raise ValueError(f"expected {cin} input channels, got {C}")
+            tc = _tc_eligible(cin, cout)
+            if tc and fmt != "nhwc_bf16":
+                # API-edge input of a tensor-core layer: one conversion pass to NHWC bf16
+                cur = ops.nchw_to_nhwc_bf16(cur) if fmt == "nchw_f32" else ops.to_bf16(cur)
+                fmt = "nhwc_bf16"
+            if not last:
+                ofmt = "nhwc_bf16"
+            elif out_fmt == "nchw_f32":
+                # narrow outputs (the 3-channel image) are written planar; wide ones stay NHWC in memory
+                ofmt = "nchw_f32" if (not tc and cout <= 4) else "nhwc_f32"
+            else:
+                ofmt = out_fmt
+            d = ops.conv_desc(s.transposed, B, H, W, cin, cout, c.kernel_size[0], c.stride[0],
+                              L.F32 if fmt.endswith("f32") else L.BF16, L.NCHW if fmt.startswith("nchw") else L.NHWC,
+                              L.F32 if ofmt.endswith("f32") else L.BF16, L.NCHW if ofmt.startswith("nchw") else L.NHWC,
+                              act=s.act, gdn=(L.GDN_NONE if s.gdn is None else (L.GDN_INVERSE if s.gdn.inverse else L.GDN_FORWARD)),
+                              out2=(out2 if last else 0))
+            beta_eff = gamma_eff = gamma_bf16 = None
+            if s.gdn is not None:
+                beta_eff, gamma_eff, gamma_bf16 = s.gdn.effective_params()
+            bias = c.bias.detach() if c.bias is not None else None
+            if bias is not None and bias.dtype != torch.float32:
+                bias = bias.float()
+            name = getattr(c, "_mmc_name", "conv")
+            if tc:
+                out = ops.conv_forward_tc(d, cur, c.packed_weight(d), bias, beta_eff, gamma_bf16, name=name)
+            else:
+                out = ops.conv_forward_direct(d, cur, c.f32_weight(), bias, beta_eff, gamma_eff, name=name)
+            if d.out2_bf16:
+                out, y2 = out
+            cur, fmt = out, ofmt
+        if out_fmt == "nchw_f32" and fmt == "nhwc_f32":
+            cur = cur.permute(0, 3, 1, 2)   # logical NCHW, channels-last memory
+        return (cur, y2) if out2 else cur
+
+
+class TransformStack(nn.Sequential):
+    """``nn.Sequential`` with the same children / state_dict keys as the reference's g_a, g_s, h_a,
+    h_s; ``forward`` runs the fused executor instead of calling the children one by one."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return run_layers(list(self), x, "nchw_f32", "nchw_f32")

@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: img/s of the codec forward + likelihoods on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N=1)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W   (N>1, one rank per GPU)
+    python bench.py --impl reference ...                     (reference CPU path, see below)
+
+Workload (BASELINE.json configs[1]): bmshj2018-hyperprior quality 4 (N=128, M=192), eval forward
+(g_a, h_a, EntropyBottleneck, h_s, GaussianConditional, g_s) on a batch of 64 synthetic 768x512 RGB
+images per GPU, random-init weights.  A "step" is one forward over one batch.  Images are
+independent, so N GPUs run N replicas on disjoint batch shards with no data-path collective
+(weak scaling: 64 images per GPU); the only collectives are the timing barrier and a MAX over
+ranks of the device time.
+
+Prints ONE JSON line (rank 0).  `value` = images/s with the batch resident in HBM; `e2e` = the
+same through the public module API with pinned host buffers, H2D and D2H inside the timed region.
+`--impl reference` times the reference's CPU execution path (oracle/torch_port.py, the restated
+stock-torch-op sequence the reference runs; the reference itself is Python and cannot travel to
+the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "165-learning-based-multi-modality-image-and-video-compression_b200")
+for p in (ROOT, PKG_DIR, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "img/s (768x512 codec fwd+likelihoods)"
+UNIT = "img/s"
+ARCH, QUALITY, N_CH, M_CH = "bmshj2018-hyperprior", 4, 128, 192
+H, W = 512, 768
+WORKLOAD = "bmshj2018-hyperprior q4 eval forward, batch 64 x 768x512 RGB (BASELINE.json configs[1])"
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of `total` independent units for `rank` (no collective needed)."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def conv_flops_per_image():
+    """Algorithmic FLOPs per 768x512 image: 2*Cin*Cout*k*k*Hout*Wout per conv,
+    2*Cin*Cout*k*k*Hin*Win per deconv, 2*C*C*H*W per GDN/IGDN."""
+    N, M = N_CH, M_CH
+    layers = []  # (name, flops, min_bytes)
+    def conv(name, cin, cout, k, ho, wo, gdn=False):
+        f = 2.0 * cin * cout * k * k * ho * wo + (2.0 * cout * cout * ho * wo if gdn else 0.0)
+        layers.append((name, f))
+    conv("g_a.0", 3, N, 5, 256, 384, True); conv("g_a.2", N, N, 5, 128, 192, True)
+    conv("g_a.4", N, N, 5, 64, 96, True); conv("g_a.6", N, M, 5, 32, 48)
+    conv("h_a.0", M, N, 3, 32, 48); conv("h_a.2", N, N, 5, 16, 24); conv("h_a.4", N, N, 5, 8, 12)
+    conv("h_s.0", N, N, 5, 8, 12); conv("h_s.2", N, N, 5, 16, 24); conv("h_s.4", N, M, 3, 32, 48)   # deconv: Hin*Win
+    conv("g_s.0", M, N, 5, 32, 48); conv("g_s.2", N, N, 5, 64, 96); conv("g_s.4", N, N, 5, 128, 192)
+    conv("g_s.6", N, 3, 5, 256, 384)
+    # IGDN terms (at the deconv OUTPUT resolution)
+    layers.append(("igdn", 2.0 * N * N * (64 * 96 + 128 * 192 + 256 * 384)))
+    return dict(layers)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
+
+
+def cpu_reference_throughput(batch: int, steps: int, warmup: int):
+    """Reference CPU path (oracle/torch_port.py) on all host cores; returns (img/s, ms_per_step, cores)."""
+    import torch
+    from oracle import torch_port as tp
+    import mmcodec
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    net = mmcodec.build_model(ARCH, QUALITY).eval()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.rand(batch, 3, H, W, generator=torch.Generator().manual_seed(1234))
+    with torch.no_grad():
+        for _ in range(warmup):
+            tp.hyperprior_forward(sd, x)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = tp.hyperprior_forward(sd, x)
+        dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, cores, tp.bpp(out, batch * H * W)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        b = 2
+        v, ms, cores, _ = cpu_reference_throughput(b, max(1, args.steps), max(1, min(args.warmup, 1)))
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "sample": f"{b} images per step on the host CPU"},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"{b}-image batches of the same model/resolution, torch CPU ops, {cores} threads"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mmcodec
+    from mmcodec import ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    torch.manual_seed(0)
+    net = mmcodec.build_model(ARCH, QUALITY).eval()
+    net.update()
+    net = net.to(dev)
+    # every rank draws the global batch stream and keeps its own shard (independent images)
+    lo, hi = shard_range(B * world, rank, world)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.rand(B, 3, H, W, generator=gen).pin_memory()
+    x = x_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = net(x)
+        barrier()
+        ops.reset_launch_count()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            out = net(x)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        launches = ops.launch_count()
+        bpp = net.bpp(out)
+
+        # ---- end to end: pinned host -> device, forward, results -> pinned host -------------
+        xh_host = torch.empty(B, 3, H, W).pin_memory()
+        ly_host = torch.empty(out["likelihoods"]["y"].shape).pin_memory()
+        lz_host = torch.empty(out["likelihoods"]["z"].shape).pin_memory()
+        x_dev = torch.empty_like(x)
+
+        def e2e_step():
+            x_dev.copy_(x_host, non_blocking=True)
+            o = net(x_dev)
+            xh_host.copy_(o["x_hat"], non_blocking=True)
+            ly_host.copy_(o["likelihoods"]["y"], non_blocking=True)
+            lz_host.copy_(o["likelihoods"]["z"], non_blocking=True)
+
+        e2e_step()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+        if rank == 0:
+            sampler.stop_flag.set()
+            sampler.join(2)
+
+        # ---- per-layer device times for the roofline (separate pass, events around each launch) ---
+        prof = ops.start_profile()
+        for _ in range(2):
+            net(x)
+        torch.cuda.synchronize()
+        layer_ms = ops.stop_profile()
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    with contextlib.suppress(Exception):
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    flops = conv_flops_per_image()
+    # dominant kernel = the conv launch with the largest device time in the profiled pass
+    roofline = None
+    if layer_ms:
+        name, ms = max(layer_ms.items(), key=lambda kv: kv[1])
+        key = name.split("|")[0]
+        f = flops.get(key, 0.0) + (flops["igdn"] * {"g_s.0": 64 * 96, "g_s.2": 128 * 192, "g_s.4": 256 * 384}.get(key, 0) / (64 * 96 + 128 * 192 + 256 * 384))
+        achieved = f * B / (ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "ms_per_launch": ms, "layer_ms": {k: round(v, 4) for k, v in layer_ms.items()}}
+
+    value = B * world * args.steps / (ms_total * 1e-3)
+    e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
+    h2d = x_host.numel() * 4
+    d2h = (xh_host.numel() + ly_host.numel() + lz_host.numel()) * 4
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "image": "768x512", "weights": "random init",
+                       "parallelism": f"batch-sharded replicas x{world}, no data-path collective",
+                       "l2": "inputs larger than L2 (302 MB fp32 batch, >1.5 GB first activation), no flush needed"},
+            "bpp": bpp, "gpu_launches": launches, "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        with contextlib.redirect_stdout(io.StringIO()):
+            v, ms, cores, cpu_bpp = cpu_reference_throughput(2, 3, 1)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"3 steps of 2 images (same model/resolution) on {cores} host threads, torch CPU ops",
+                                "bpp": cpu_bpp}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,206 @@
+/*
+ * mmcodec.h -- C ABI of libmmcodec.so, the B200 (sm_100a) implementation of the learned-codec
+ * hot path of SZU-AdvTech-2022/165 (a CompressAI 1.2.0.dev0 fork).
+ *
+ * The reference has no FFI for this path: the path is Python modules calling stock torch ops
+ * (SURVEY.md section 8b).  Each entry point below therefore replaces one reference *function*;
+ * the citation (file:line, relative to /root/reference/CompressAI) is the interface it stands in
+ * for.  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller unless the name ends in _host.
+ *    The library borrows buffers for the duration of the enqueued work (stream ordered) and
+ *    never allocates persistent device memory.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *  - Return value: MMC_OK or a negative error code; mmc_last_error() gives the thread-local
+ *    message.  Nothing aborts, nothing falls back to the CPU.
+ *  - Elementwise entropy-stage tensors are viewed as [outer][C][inner]:
+ *      NCHW contiguous  : outer = N,       inner = H*W
+ *      channels-last    : outer = N*H*W,   inner = 1
+ *  - Activations between transform layers are NHWC bf16 ("channels-last"); fp32 appears at the
+ *    API edges (image in, latents / likelihoods / reconstruction out).
+ */
+#ifndef MMCODEC_H
+#define MMCODEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMC_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define MMC_API __attribute__((visibility("default")))
+#else
+#define MMC_API
+#endif
+
+enum mmc_status {
+    MMC_OK = 0,
+    MMC_EINVAL = -1,       /* bad shape / alignment / argument -> ValueError on the Python side */
+    MMC_ECUDA = -2,        /* CUDA launch or driver error      -> RuntimeError */
+    MMC_EUNSUPPORTED = -3, /* valid in the reference, not implemented here (fails loudly) */
+    MMC_EDOMAIN = -4       /* pmf_to_quantized_cdf domain error -> ValueError (ops.cpp:46-52) */
+};
+
+enum mmc_means_mode { MMC_MEANS_NONE = 0, MMC_MEANS_FULL = 1, MMC_MEANS_PER_CHANNEL = 2 };
+
+enum mmc_dtype { MMC_F32 = 0, MMC_BF16 = 1 };
+enum mmc_layout { MMC_NCHW = 0, MMC_NHWC = 1 };
+
+/* activation fused after bias (and before GDN where both are given) */
+enum mmc_act {
+    MMC_ACT_NONE = 0,
+    MMC_ACT_RELU = 1,       /* nn.ReLU        models/google.py:256,264 */
+    MMC_ACT_LEAKY_RELU = 2, /* nn.LeakyReLU() models/google.py:365,373 (slope 0.01) */
+    MMC_ACT_ABS = 3         /* torch.abs(y)   models/google.py:283 (only for the secondary output) */
+};
+
+enum mmc_gdn_mode { MMC_GDN_NONE = 0, MMC_GDN_FORWARD = 1, MMC_GDN_INVERSE = 2 };
+
+MMC_API int mmc_version(void);
+MMC_API const char *mmc_last_error(void);
+/* Number of kernels this library has launched on the calling thread since the last reset
+ * (bench.py's "gpu_launches"). */
+MMC_API int64_t mmc_launch_count(void);
+MMC_API void mmc_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Entropy stage (HBM-bound elementwise kernels)
+ * ------------------------------------------------------------------------------------------- */
+
+/* EntropyModel.quantize(mode="symbols")   compressai/entropy_models/entropy_models.py:157-182
+ * out = int32(rint(x - mean)).  Bit-exact w.r.t. the reference for |x - mean| < 2^31. */
+MMC_API int mmc_quantize_symbols(const float *x, const float *means, int means_mode, int64_t outer, int64_t C,
+                         int64_t inner, int32_t *out, void *stream);
+
+/* EntropyModel.quantize(mode="dequantize")   entropy_models.py:169-178.  out = rint(x - mean) + mean */
+MMC_API int mmc_quantize_dequantize(const float *x, const float *means, int means_mode, int64_t outer, int64_t C,
+                            int64_t inner, float *out, void *stream);
+
+/* EntropyModel.quantize(mode="noise")   entropy_models.py:163-167.  out = x + noise; the U(-1/2,1/2)
+ * tensor is drawn by the caller (torch generator) so both implementations consume the same noise. */
+MMC_API int mmc_quantize_noise(const float *x, const float *noise, int64_t n, float *out, void *stream);
+
+/* EntropyModel.dequantize   entropy_models.py:190-199.  out = float(sym) + mean */
+MMC_API int mmc_dequantize(const int32_t *symbols, const float *means, int means_mode, int64_t outer, int64_t C,
+                   int64_t inner, float *out, void *stream);
+
+/* LowerBound forward / backward   compressai/ops/bound_ops.py:36-42 */
+MMC_API int mmc_lower_bound(const float *x, float bound, int64_t n, float *out, void *stream);
+MMC_API int mmc_lower_bound_bwd(const float *x, const float *grad_out, float bound, int64_t n, float *grad_in,
+                        void *stream);
+
+/* GaussianConditional.build_indexes   entropy_models.py:735-740
+ * out = (levels-1) - #{i < levels-1 : max(scale, bound) <= table[i]}.  `table` is the fp32
+ * scale_table BUFFER (never regenerated); levels <= 256. */
+MMC_API int mmc_build_indexes(const float *scales, const float *table, int levels, float bound, int64_t n,
+                      int32_t *out, void *stream);
+
+/* EntropyBottleneck._build_indexes   entropy_models.py:542-553.  out[o][c][i] = c */
+MMC_API int mmc_channel_indexes(int64_t outer, int64_t C, int64_t inner, int32_t *out, void *stream);
+
+/* Raw EntropyBottleneck parameters for the default filters (3,3,3,3)   entropy_models.py:361-379.
+ * matrix[0] [C][3][1], matrix[1..3] [C][3][3], matrix[4] [C][1][3]; bias[0..3] [C][3][1],
+ * bias[4] [C][1][1]; factor[0..3] [C][3][1]; medians = quantiles[:,0,1] gathered to [C]. */
+typedef struct mmc_eb_params {
+    const float *matrix[5];
+    const float *bias[5];
+    const float *factor[4];
+    const float *medians;
+} mmc_eb_params;
+
+/* EntropyBottleneck.forward   entropy_models.py:495-540 (+ _logits_cumulative :457-477,
+ * _likelihood :480-492, LowerBound(1e-9) :527).  noise == NULL: eval (x_hat = rint(x-med)+med);
+ * noise != NULL: training (x_hat = x + noise).  Optional outputs (may be NULL):
+ *   x_hat_bf16 : bf16 copy of x_hat (feeds the synthesis transform),
+ *   bits       : one float, += -sum(log2(likelihood)) over this call (atomicAdd; caller zeroes). */
+MMC_API int mmc_eb_forward(const float *x, const float *noise, const mmc_eb_params *params, float likelihood_bound,
+                   int64_t outer, int64_t C, int64_t inner, float *x_hat, void *x_hat_bf16,
+                   float *likelihood, float *bits, void *stream);
+
+/* EntropyBottleneck._logits_cumulative   entropy_models.py:457-477 (used by update() and loss()) */
+MMC_API int mmc_eb_logits_cumulative(const float *x, const mmc_eb_params *params, int64_t outer, int64_t C,
+                             int64_t inner, float *logits, void *stream);
+
+/* GaussianConditional.forward   entropy_models.py:715-731 (+ _likelihood :692-709).
+ * means may be NULL; noise as above.  scales/means are fp32 with the same shape as x.
+ * Optional outputs as for mmc_eb_forward. */
+MMC_API int mmc_gc_forward(const float *x, const float *scales, const float *means, const float *noise,
+                   float scale_bound, float likelihood_bound, int64_t n, float *x_hat, void *x_hat_bf16,
+                   float *likelihood, float *bits, void *stream);
+
+/* sum(log2(likelihood)) * -1 accumulated into *bits (atomicAdd); examples/train.py:74-77 */
+MMC_API int mmc_bits(const float *likelihood, int64_t n, float *bits, void *stream);
+
+/* pmf_to_quantized_cdf   compressai/cpp_exts/ops/ops.cpp:40-109.  HOST function (called from
+ * update() once per model).  cdf_host has n+1 entries.  MMC_EDOMAIN on negative / non-finite. */
+MMC_API int mmc_pmf_to_quantized_cdf_host(const float *pmf_host, int n, int precision, uint32_t *cdf_host);
+
+/* ---------------------------------------------------------------------------------------------
+ * GDN   compressai/layers/gdn.py:77-92, compressai/ops/parametrizers.py:47-64
+ * ------------------------------------------------------------------------------------------- */
+
+/* beta_eff = max(beta, beta_bound)^2 - pedestal ; gamma_eff likewise ([C][C], row i = output
+ * channel).  gamma_eff_bf16 (optional) is the same matrix in bf16 for the fused conv epilogue. */
+MMC_API int mmc_gdn_reparam(const float *beta, const float *gamma, int C, float beta_bound, float gamma_bound,
+                    float pedestal, float *beta_eff, float *gamma_eff, void *gamma_eff_bf16, void *stream);
+
+/* Stand-alone GDN.forward on fp32 data: y = x * rsqrt(beta_i + sum_j gamma_ij x_j^2) (inverse: sqrt).
+ * layout: MMC_NCHW ([B][C][HW]) or MMC_NHWC ([B*HW][C]). */
+MMC_API int mmc_gdn_forward(const float *x, const float *beta_eff, const float *gamma_eff, int inverse, int64_t B,
+                    int C, int64_t HW, int layout, float *y, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Transforms: conv() / deconv()   compressai/models/utils.py:128-146
+ * ------------------------------------------------------------------------------------------- */
+typedef struct mmc_conv_desc {
+    int transposed;      /* 0: nn.Conv2d(k, stride, padding=k/2); 1: nn.ConvTranspose2d(k, stride,
+                            padding=k/2, output_padding=stride-1) */
+    int B, H, W;         /* input batch and spatial size */
+    int Cin, Cout;
+    int k;               /* 1, 3 or 5 */
+    int stride;          /* 1 or 2 */
+    int in_dtype;        /* mmc_dtype */
+    int in_layout;       /* mmc_layout */
+    int out_dtype;
+    int out_layout;
+    int act;             /* mmc_act applied to (acc + bias) */
+    int gdn;             /* mmc_gdn_mode applied after act; needs beta_eff / gamma_eff */
+    int out2_bf16;       /* secondary NHWC bf16 output y2: 0 none, 1 = |out| (torch.abs(y) feeding h_a,
+                            models/google.py:283), 2 = out (y feeding h_a in the mean-scale model, :381) */
+} mmc_conv_desc;
+
+/* Output spatial size for a descriptor (conv: ceil(H/stride); deconv: H*stride). */
+MMC_API int mmc_conv_out_size(const mmc_conv_desc *d, int *Ho, int *Wo);
+
+/* Pack fp32 weights (Conv2d [Cout][Cin][k][k] or ConvTranspose2d [Cin][Cout][k][k]) into the bf16
+ * tap-major layout [k*k][Cout][Cin_pad] the tensor-core kernels stream with TMA.
+ * Returns the packed size in bytes through *bytes when w_packed is NULL. */
+MMC_API int mmc_conv_pack_weights(const mmc_conv_desc *d, const float *w, void *w_packed, size_t *bytes,
+                          void *stream);
+
+/* Direct (CUDA-core, fp32 accumulate) convolution for any descriptor; reads fp32 weights in the
+ * torch layout.  Used for the 3-channel image-edge layers and as the on-device cross-check of the
+ * tensor-core path. */
+MMC_API int mmc_conv_forward_direct(const mmc_conv_desc *d, const void *x, const float *w, const float *bias,
+                            const float *beta_eff, const float *gamma_eff, void *y, void *y2, void *stream);
+
+/* Tensor-core implicit GEMM (TMA -> smem -> tcgen05.mma -> TMEM -> fused epilogue).
+ * Requires NHWC bf16 input, Cin % 64 == 0, Cout % 16 == 0, Cout <= 256 per pass. */
+MMC_API int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_packed, const float *bias,
+                        const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream);
+
+/* Layout / dtype conversion at the API edges. */
+MMC_API int mmc_nchw_f32_to_nhwc_bf16(const float *x, int64_t B, int C, int64_t HW, void *y, void *stream);
+MMC_API int mmc_nhwc_bf16_to_nchw_f32(const void *x, int64_t B, int C, int64_t HW, float *y, void *stream);
+MMC_API int mmc_nhwc_f32_to_nchw_f32(const float *x, int64_t B, int C, int64_t HW, float *y, void *stream);
+MMC_API int mmc_f32_to_bf16(const float *x, int64_t n, void *y, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMCODEC_H */

@@ -259,6 +259,8 @@ def model_goldens(out):
         with torch.no_grad():
             o = quiet(net, torch.from_numpy(x))
         tag = arch.replace("-", "_")
+        import json
+        out[f"{tag}_state_dict"] = np.array(json.dumps({k: [list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()}))
         out[f"{tag}_x_hat"] = t2n(o["x_hat"])
         for k, v in o["likelihoods"].items():
             out[f"{tag}_lik_{k}"] = t2n(v)

@@ -1,0 +1,209 @@
+"""CPU-only tests of the host side: the C-ABI library loads and exports every declared symbol, the
+module classes keep the reference's state_dict contract and error behaviour, update() builds the
+reference's CDF tables, and nothing silently falls back to the CPU.  No kernel is launched."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG_DIR, ROOT
+
+import mmcodec
+from mmcodec import _lib
+from weights import _entropy_bottleneck, make_state_dict
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "mmcodec.h")).read()
+    declared = set(re.findall(r"MMC_API[^;(]*?\b(mmc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    assert os.path.exists(_lib.LIB_PATH), "libmmcodec.so not built: run python __graft_entry__.py"
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), f"{name} declared in include/mmcodec.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.lib().mmc_version() == 100
+
+
+def test_library_links_no_torch():
+    """The drop-in boundary is a plain C ABI: no torch / python symbols in the shared object."""
+    import subprocess
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "python" not in out, out
+
+
+def test_no_cpu_fallback():
+    net = mmcodec.ScaleHyperprior(128, 192).eval()
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        net(torch.rand(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        mmcodec.GDN(8)(torch.rand(1, 8, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        mmcodec.EntropyBottleneck(8)(torch.rand(1, 8, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        mmcodec.conv(3, 8)(torch.rand(1, 3, 8, 8))
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(PKG_DIR, "mmcodec")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, re.M), f
+    for f in os.listdir(os.path.join(PKG_DIR, "csrc")):
+        assert "oracle" not in open(os.path.join(PKG_DIR, "csrc", f)).read(), f
+
+
+@pytest.mark.parametrize("arch,cls,N,M", [("factorized", mmcodec.FactorizedPrior, 128, 192),
+                                          ("hyperprior", mmcodec.ScaleHyperprior, 128, 192),
+                                          ("mean_scale", mmcodec.MeanScaleHyperprior, 192, 320)])
+def test_state_dict_contract(models_golden, arch, cls, N, M):
+    """Same keys, shapes and dtypes as the reference module after update()."""
+    ref = json.loads(str(models_golden[f"{arch}_state_dict"]))
+    net = cls(N, M).eval()
+    net.update(force=True)
+    mine = {k: [list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()}
+    assert set(mine) == set(ref), set(mine) ^ set(ref)
+    for k in ref:
+        assert mine[k][1] == ref[k][1], k
+        if not k.endswith("_quantized_cdf") and not k.endswith("_cdf_length") and not k.endswith("_offset"):
+            assert mine[k][0] == ref[k][0], k
+    # load_state_dict round trip incl. variable-size CDF buffers (models/utils.py:90-125)
+    net2 = cls(N, M)
+    net2.load_state_dict(net.state_dict())
+    assert torch.equal(net2.entropy_bottleneck._quantized_cdf, net.entropy_bottleneck._quantized_cdf)
+    net3 = cls.from_state_dict(net.state_dict())
+    assert net3.N == N and net3.M == M
+
+
+def test_compression_model_has_15_params():
+    """tests/test_models.py:54-58"""
+    assert len(list(mmcodec.CompressionModel(32).parameters())) == 15
+
+
+def test_gc_update_tables_match_reference(kernels_golden):
+    g = kernels_golden
+    gc = mmcodec.GaussianConditional(None)
+    assert gc.update_scale_table(mmcodec.get_scale_table())
+    assert np.array_equal(gc.scale_table.numpy(), g["scale_table"])
+    assert np.array_equal(gc._quantized_cdf.numpy(), g["gc_quantized_cdf"])
+    assert np.array_equal(gc._cdf_length.numpy(), g["gc_cdf_length"])
+    assert np.array_equal(gc._offset.numpy(), g["gc_offset"])
+    assert not gc.update_scale_table(mmcodec.get_scale_table())  # already initialised
+    t = mmcodec.get_scale_table()
+    assert t[0] == 0.11 and t[-1] == 256 and len(t) == 64  # tests/test_models.py:242-258
+
+
+def test_eb_update_tables_match_reference(kernels_golden):
+    g = kernels_golden
+    C = 8
+    w = {}
+    _entropy_bottleneck(np.random.RandomState(3), w, "eb", C)
+    eb = mmcodec.EntropyBottleneck(C)
+    sd = eb.state_dict()
+    for k, v in w.items():
+        sd[k[3:]].copy_(torch.from_numpy(v))
+    assert eb.update()
+    assert np.array_equal(eb._quantized_cdf.numpy(), g["eb_quantized_cdf"])
+    assert np.array_equal(eb._cdf_length.numpy(), g["eb_cdf_length"])
+    assert np.array_equal(eb._offset.numpy(), g["eb_offset"])
+    assert not eb.update()
+    assert eb.update(force=True)
+
+
+def test_pmf_to_quantized_cdf_host(kernels_golden):
+    g = kernels_golden
+    from mmcodec.ops import pmf_to_quantized_cdf
+    assert pmf_to_quantized_cdf([0.1, 0.2, 0.0, 0.0], 16) == [0, 21845, 65534, 65535, 65536]  # tests/test_ops.py:104-106
+    for p, c, L in zip(g["cdf_pmfs"], g["cdf_cdfs"], g["cdf_lens"]):
+        assert pmf_to_quantized_cdf(p[:L], 16) == c[:L + 1].tolist()
+    for bad in ([-0.1, 0.5], [float("inf"), 0.5], [float("nan"), 0.5]):  # tests/test_ops.py:108-118
+        with pytest.raises(ValueError):
+            pmf_to_quantized_cdf(bad, 16)
+
+
+def test_reference_error_behaviour():
+    gc = mmcodec.GaussianConditional(None)
+    with pytest.raises(ValueError, match="Invalid quantization mode"):
+        gc.quantize(torch.rand(1, 2, 3, 3), mode="toto")  # tests/test_entropy_models.py:49-55
+    with pytest.raises(ValueError):
+        mmcodec.GaussianConditional(1)  # invalid scale_table type, tests/test_entropy_models.py:287-310
+    with pytest.raises(ValueError):
+        mmcodec.GaussianConditional([])
+    with pytest.raises(ValueError):
+        mmcodec.GaussianConditional([1, 0.5])
+    with pytest.raises(ValueError):
+        mmcodec.GaussianConditional([0, 1])
+    with pytest.raises(ValueError):
+        mmcodec.GaussianConditional(None, scale_bound=-0.1)
+    with pytest.raises(ValueError, match="Invalid architecture"):
+        mmcodec.build_model("nope", 1)
+    with pytest.raises(ValueError, match="Invalid quality"):
+        mmcodec.build_model("bmshj2018-factorized", 9)
+    with pytest.raises(NotImplementedError):
+        mmcodec.EntropyBottleneck(8, filters=(3, 3))
+
+
+def test_zoo_configs_match_reference():
+    """(N, M) per quality, compressai/zoo/image.py:189-220; configs 1-3 of BASELINE.json."""
+    assert mmcodec.models.CFGS["bmshj2018-factorized"][1] == (128, 192)
+    assert mmcodec.models.CFGS["bmshj2018-hyperprior"][4] == (128, 192)
+    assert mmcodec.models.CFGS["bmshj2018-hyperprior"][6] == (192, 320)
+    assert mmcodec.models.CFGS["mbt2018-mean"][6] == (192, 320)
+    assert mmcodec.models.CFGS["mbt2018-mean"][4] == (128, 192)
+    net = mmcodec.build_model("mbt2018-mean", 6)
+    assert net.g_a[6].out_channels == 320 and net.h_s[4].out_channels == 640
+
+
+def test_gdn_init_and_parse():
+    from mmcodec.transforms import parse_layers
+    net = mmcodec.ScaleHyperprior(128, 192)
+    steps = parse_layers(list(net.g_a))
+    assert [s.gdn is not None for s in steps] == [True, True, True, False]
+    steps = parse_layers(list(net.h_s))
+    assert [s.transposed for s in steps] == [True, True, False] and all(s.act == _lib.ACT_RELU for s in steps)
+    g = mmcodec.GDN(16)
+    # reparametrised init: beta = sqrt(1 + 2^-36), gamma = sqrt(0.1 I + 2^-36)  (layers/gdn.py:66-74)
+    assert torch.allclose(g.beta ** 2 - 2.0 ** -36, torch.ones(16))
+    assert torch.allclose(g.gamma ** 2 - 2.0 ** -36, 0.1 * torch.eye(16), atol=1e-7)
+    with pytest.raises(NotImplementedError):
+        parse_layers([torch.nn.Conv2d(3, 8, 7, padding=3)])
+
+
+def test_synthetic_weights_are_stable():
+    """The deterministic weight recipe must be bit-stable: goldens were generated with it."""
+    sd = make_state_dict("hyperprior", 128, 192, seed=0)
+    assert abs(float(sd["g_a.0.weight"][0, 0, 0, 0]) - 0.61108565) < 1e-6
+    assert sd["g_s.6.weight"].shape == (128, 3, 5, 5)
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    lo, hi = bench.shard_range(64, rank, world)
+    t = torch.tensor([float(hi - lo)])
+    dist.all_reduce(t)
+    mx = torch.tensor([1.0 + rank])
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    q.put((rank, lo, hi, t.item(), mx.item()))
+    dist.destroy_process_group()
+
+
+def test_batch_sharding_world_size_2_gloo():
+    """N>1 path of bench.py: contiguous batch shards, no data-path collective, MAX-over-ranks timing."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    ps = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    assert res[0][1:3] == (0, 32) and res[1][1:3] == (32, 64)
+    assert res[0][3] == 64.0 and res[0][4] == 2.0
