@@ -1,0 +1,96 @@
+"""GPU parity tests of the tcgen05 implicit-GEMM conv / deconv kernel (mmc_conv_forward_tc) against the
+CPU oracle.  Inputs and weights are rounded to bf16 first, so the only differences left are fp32
+accumulation order, the bf16 x^2 / gamma of the fused GDN, and output rounding: tolerance 2e-3 of
+the output scale for fp32 outputs, 1e-2 for bf16 outputs (the bf16 tolerance BASELINE.json states)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from weights import _gdn
+
+pytestmark = pytest.mark.gpu
+
+from mmcodec import _lib as L  # noqa: E402
+from mmcodec import ops  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def bf16_round(a):
+    return torch.from_numpy(a).to(torch.bfloat16).float().numpy()
+
+
+CASES = [
+    # transposed, cin, cout, k, s, h, w, act, gdn, B
+    (False, 64, 64, 1, 1, 8, 16, L.ACT_NONE, L.GDN_NONE, 1),        # plain GEMM, exactly one tile
+    (False, 64, 128, 3, 1, 16, 24, L.ACT_RELU, L.GDN_NONE, 2),      # h_a.0 / h_s.4 shape class
+    (False, 128, 128, 5, 2, 32, 48, L.ACT_NONE, L.GDN_NONE, 2),     # g_a.2 class (stride-2 element-strided TMA box)
+    (False, 128, 128, 5, 2, 32, 48, L.ACT_NONE, L.GDN_FORWARD, 2),  # + fused GDN
+    (False, 128, 192, 5, 2, 16, 24, L.ACT_NONE, L.GDN_NONE, 1),     # g_a.6 class (N=192)
+    (False, 192, 320, 5, 2, 34, 60, L.ACT_NONE, L.GDN_NONE, 1),     # mbt2018-mean g_a.6: two N blocks, ragged 17x30 output
+    (False, 192, 192, 5, 2, 20, 28, L.ACT_NONE, L.GDN_FORWARD, 1),  # C=192 GDN (two 96-column norm chunks)
+    (False, 128, 128, 5, 2, 17, 23, L.ACT_LEAKY_RELU, L.GDN_NONE, 2),   # odd input size
+    (True, 192, 128, 5, 2, 8, 12, L.ACT_NONE, L.GDN_INVERSE, 2),    # g_s.0 class: 4-phase deconv + IGDN
+    (True, 128, 128, 5, 2, 16, 24, L.ACT_RELU, L.GDN_NONE, 1),      # h_s class
+    (True, 128, 128, 5, 2, 9, 7, L.ACT_NONE, L.GDN_INVERSE, 1),     # ragged deconv
+    (True, 64, 64, 3, 1, 6, 10, L.ACT_NONE, L.GDN_NONE, 1),         # stride-1 transposed conv
+    (False, 480, 640, 3, 1, 17, 30, L.ACT_NONE, L.GDN_NONE, 1),     # mbt2018-mean h_s.4: 4 N blocks of 160
+]
+
+
+@pytest.mark.parametrize("transposed,cin,cout,k,s,h,w,act,gdn,B", CASES)
+@pytest.mark.parametrize("out_f32", [True, False])
+def test_conv_tc_vs_oracle(transposed, cin, cout, k, s, h, w, act, gdn, B, out_f32):
+    rs = np.random.RandomState(cin + 7 * cout + k + h)
+    x = bf16_round(rs.standard_normal((B, cin, h, w)).astype(np.float32))
+    fan = cin * k * k / (s * s if transposed else 1)
+    wt = bf16_round((rs.standard_normal((cin, cout, k, k) if transposed else (cout, cin, k, k)) * (2.0 / np.sqrt(fan))).astype(np.float32))
+    b = rs.standard_normal(cout).astype(np.float32)
+    actname = {L.ACT_NONE: None, L.ACT_RELU: "relu", L.ACT_LEAKY_RELU: "leaky_relu"}[act]
+    ref = (oracle.conv_transpose2d if transposed else oracle.conv2d)(x, wt, b, stride=s, act=actname)
+    beta_eff = gamma_bf16 = None
+    if gdn != L.GDN_NONE:
+        gw = {}
+        _gdn(rs, gw, "g", cout)
+        ref = oracle.gdn_forward(ref, gw["g.beta"], gw["g.gamma"], inverse=(gdn == L.GDN_INVERSE))
+        beta_eff, _, gamma_bf16 = ops.gdn_reparam(torch.from_numpy(gw["g.beta"]).to(dev()), torch.from_numpy(gw["g.gamma"]).to(dev()),
+                                                  oracle.gdn_beta_bound(), oracle.GDN_GAMMA_BOUND, oracle.GDN_PEDESTAL, want_bf16=True)
+    xin = torch.from_numpy(x).to(dev()).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    d = ops.conv_desc(transposed, B, h, w, cin, cout, k, s, L.BF16, L.NHWC, L.F32 if out_f32 else L.BF16, L.NHWC,
+                      act=act, gdn=gdn, out2=1)
+    packed = ops.conv_pack_weights(d, torch.from_numpy(wt).to(dev()))
+    y, y2 = ops.conv_forward_tc(d, xin, packed, torch.from_numpy(b).to(dev()), beta_eff, gamma_bf16)
+    torch.cuda.synchronize()
+    y = y.float().permute(0, 3, 1, 2).cpu().numpy()
+    assert y.shape == ref.shape
+    scale = float(np.abs(ref).max())
+    err = np.abs(y - ref)
+    tol = (2e-3 if gdn == L.GDN_NONE else 6e-3) if out_f32 else 1e-2
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() < tol * scale, f"max err {err.max():.4g} (scale {scale:.4g}) at {worst}: got {y[worst]:.5g} want {ref[worst]:.5g}; " \
+                                    f"frac bad {(err > tol * scale).mean():.4f}"
+    e2 = np.abs(y2.float().permute(0, 3, 1, 2).cpu().numpy() - np.abs(ref))
+    assert e2.max() < 1e-2 * scale
+
+
+def test_conv_tc_matches_direct_kernel_at_model_scale():
+    """g_a.2-sized layer on a batch: tensor-core kernel vs the CUDA-core kernel on the same bf16 data."""
+    torch.manual_seed(0)
+    B, cin, cout, h, w = 4, 128, 128, 128, 192
+    x = torch.randn(B, h, w, cin, device=dev()).to(torch.bfloat16)
+    wt = (torch.randn(cout, cin, 5, 5, device=dev()) * 0.02).to(torch.bfloat16).float()
+    b = torch.randn(cout, device=dev())
+    d = ops.conv_desc(False, B, h, w, cin, cout, 5, 2, L.BF16, L.NHWC, L.F32, L.NHWC)
+    y_tc = ops.conv_forward_tc(d, x, ops.conv_pack_weights(d, wt), b)
+    y_dc = ops.conv_forward_direct(d, x, wt, b)
+    torch.cuda.synchronize()
+    assert float((y_tc - y_dc).abs().max()) < 2e-3 * float(y_dc.abs().max())
+
+
+def test_conv_tc_rejects_unsupported_shapes():
+    d = ops.conv_desc(False, 1, 8, 8, 3, 128, 5, 2, L.BF16, L.NHWC, L.BF16, L.NHWC)
+    with pytest.raises(NotImplementedError):
+        ops.conv_pack_weights(d, torch.zeros(128, 3, 5, 5, device=dev()))

@@ -11,7 +11,11 @@ from weights import make_state_dict
 
 
 def rel_err(a, b, floor):
-    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+    """max |a-b| / max(|b|, floor), after discounting 4 ulp(0.5) = 2.4e-7 of absolute error: the
+    likelihoods are differences of two CDF values of magnitude <= 1/2 (entropy_models.py:705-707,
+    :487-491), so the reference's own fp32 result carries that much cancellation noise."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.maximum(np.abs(a - b) - 2.4e-7, 0.0) / np.maximum(np.abs(b), floor)))
 
 
 def test_quantize_kat(kernels_golden):
