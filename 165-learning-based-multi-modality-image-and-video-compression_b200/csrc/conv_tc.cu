@@ -33,6 +33,7 @@ namespace mmc {
 constexpr int kTcThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kMaxTaps = 32;
+constexpr int kMaxCout = 1024;
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
 
 struct Tap {
@@ -51,7 +52,7 @@ struct TcParams {
     int Ho, Wo;
     int TH, TW, tiles_y, tiles_x;
     int Cout, Ntile, n_blocks;
-    int kchunks;     // Cin / 64
+    int kchunks;     // ceil(Cin / 64)
     int num_stages, acc_stages;
     int act, gdn, out_f32, out2;
     int gdn_chunk;
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
     __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2], gdn_bar, gload_bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bias_s[256], beta_s[256];
+    __shared__ float bias_s[kMaxCout], beta_s[256];
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = kABytes + P.Ntile * 128;
@@ -239,9 +240,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = threadIdx.x; i < 256; i += kTcThreads) {
+    for (int i = threadIdx.x; i < kMaxCout; i += kTcThreads) {
         bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.0f;
-        beta_s[i] = (P.gdn && i < P.Cout) ? P.beta[i] : 1.0f;
+        if (i < 256) beta_s[i] = (P.gdn && i < P.Cout) ? P.beta[i] : 1.0f;
     }
     tc_fence_before();
     __syncthreads();
@@ -481,7 +482,10 @@ static int tc_validate(const mmc_conv_desc *d, const char *name)
     MMC_CHECK_ARG(d->B >= 0 && d->H >= 1 && d->W >= 1 && d->Cin >= 1 && d->Cout >= 1, "%s: bad shape", name);
     MMC_CHECK_ARG(d->k == 1 || d->k == 3 || d->k == 5, "%s: kernel size %d not in {1,3,5}", name, d->k);
     MMC_CHECK_ARG(d->stride == 1 || d->stride == 2, "%s: stride %d not in {1,2}", name, d->stride);
-    MMC_UNSUPPORTED(d->Cin % 64 != 0, "%s: tensor-core path needs Cin %% 64 == 0 (got %d); use the direct kernel", name, d->Cin);
+    // Cin is walked in 64-channel TMA boxes; a ragged last box is zero-filled by TMA on both operands.
+    // The global row pitch (Cin * 2 B) must be a multiple of 16 B for the tensor maps.
+    MMC_UNSUPPORTED(d->Cin % 8 != 0 || d->Cin < 32, "%s: tensor-core path needs Cin %% 8 == 0 and Cin >= 32 (got %d); use the direct kernel", name, d->Cin);
+    MMC_UNSUPPORTED(d->Cout > kMaxCout, "%s: Cout=%d exceeds %d", name, d->Cout, kMaxCout);
     MMC_UNSUPPORTED(d->Cout % 16 != 0, "%s: tensor-core path needs Cout %% 16 == 0 (got %d); use the direct kernel", name, d->Cout);
     return MMC_OK;
 }
@@ -532,7 +536,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     int Ho, Wo;
     mmc_conv_out_size(d, &Ho, &Wo);
     P.Ho = Ho; P.Wo = Wo; P.B = d->B; P.Cout = d->Cout;
-    P.kchunks = d->Cin / 64;
+    P.kchunks = (d->Cin + 63) / 64;
     P.act = d->act; P.gdn = d->gdn; P.out_f32 = (d->out_dtype == MMC_F32); P.out2 = d->out2_bf16;
     P.bias = bias; P.beta = beta_eff; P.y = y; P.y2 = (__nv_bfloat16 *)y2;
 
@@ -582,7 +586,15 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     const size_t stage_bytes = kABytes + (size_t)P.Ntile * 128;
     size_t fixed = 1024;  // alignment slack
     if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (size_t)(d->Cout / 64) * kABytes;
-    const size_t budget = 220 * 1024;
+    // dynamic shared memory available next to the kernel's static allocation (227 KB per CTA on sm_100)
+    static size_t budget = 0;
+    if (budget == 0) {
+        cudaFuncAttributes fa;
+        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel));
+        size_t avail = 227 * 1024 - fa.sharedSizeBytes;
+        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        budget = avail;
+    }
     MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
     int stages = (int)((budget - fixed) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
@@ -616,11 +628,6 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         if (rc) return rc;
     }
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096));
-        attr_set = true;
-    }
     int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
     conv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(P);
     MMC_CHECK_LAUNCH(name);

@@ -6,7 +6,7 @@ groups every conv with the op that follows it into ONE fused kernel launch, keep
 between layers as NHWC bf16 and touches fp32 only at the API edges.
 
 Kernel choice per layer is by shape, not by backend: the tcgen05 implicit-GEMM kernel
-(``mmc_conv_forward_tc``) takes every layer with Cin % 64 == 0 and Cout % 16 == 0; the CUDA-core
+(``mmc_conv_forward_tc``) takes every layer with Cin % 8 == 0, Cin >= 32 and Cout % 16 == 0; the CUDA-core
 kernel (``mmc_conv_forward_direct``) takes the rest (3-channel image edges, odd test shapes).
 """
 from __future__ import annotations
@@ -24,7 +24,7 @@ from . import ops
 FORMATS = ("nchw_f32", "nhwc_bf16", "nhwc_f32")
 
 # Set by mmcodec.config; tests flip it to cross-check the two kernels against each other.
-use_tensor_cores = False
+use_tensor_cores = True
 
 
 @dataclass
@@ -68,18 +68,12 @@ def parse_layers(layers) -> List[Step]:
     return steps
 
 
-def _tc_eligible(cin: int, cout: int) -> bool:
-    return use_tensor_cores and hasattr(L.lib(), "mmc_conv_forward_tc") and tc_available() and cin % 64 == 0 and cout % 16 == 0
-
-
-_tc_ok = None
-
-
-def tc_available() -> bool:
-    global _tc_ok
-    if _tc_ok is None:
-        _tc_ok = True
-    return _tc_ok
+def _tc_eligible(cin: int, cout: int, gdn: bool) -> bool:
+    """Shapes the tcgen05 kernel takes (mmc_conv_forward_tc): 64-channel K boxes (ragged tail zero-filled),
+    N tiles that are multiples of 16; fused GDN needs the whole channel vector in one N tile."""
+    if not use_tensor_cores or cin % 8 != 0 or cin < 32 or cout % 16 != 0 or cout > 1024:
+        return False
+    return (not gdn) or cout in (64, 128, 192)
 
 
 def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0):
@@ -113,7 +107,7 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0):
                 B, H, W, C = cur.shape
             if C != cin:
                 raise ValueError(f"expected {cin} input channels, got {C}")
-            tc = _tc_eligible(cin, cout)
+            tc = _tc_eligible(cin, cout, s.gdn is not None)
             if tc and fmt != "nhwc_bf16":
                 # API-edge input of a tensor-core layer: one conversion pass to NHWC bf16
                 cur = ops.nchw_to_nhwc_bf16(cur) if fmt == "nchw_f32" else ops.to_bf16(cur)

@@ -190,7 +190,8 @@ MMC_API int mmc_conv_forward_direct(const mmc_conv_desc *d, const void *x, const
                             const float *beta_eff, const float *gamma_eff, void *y, void *y2, void *stream);
 
 /* Tensor-core implicit GEMM (TMA -> smem -> tcgen05.mma -> TMEM -> fused epilogue).
- * Requires NHWC bf16 input, Cin % 64 == 0, Cout % 16 == 0, Cout <= 256 per pass. */
+ * Requires NHWC bf16 input, Cin % 8 == 0 (>= 32), Cout % 16 == 0 (<= 1024; split into N tiles <= 256);
+ * fused GDN needs Cout in {64, 128, 192}.  Anything else returns MMC_EUNSUPPORTED. */
 MMC_API int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_packed, const float *bias,
                         const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream);
 
