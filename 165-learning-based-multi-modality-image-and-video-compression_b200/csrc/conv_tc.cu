@@ -30,15 +30,23 @@
 
 namespace mmc {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kMaxTaps = 32;
 constexpr int kMaxCout = 1024;
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
 
 struct Tap {
-    int16_t dy, dx;  // offset of the input patch for this tap (in input pixels)
-    int32_t brow;    // first row of this tap in the packed weight matrix (tap * Cout)
+    int16_t dy, dx;  // offset of the input patch for this tap (in A-grid units)
+    int32_t brow;    // first row of this tap in the packed weight matrix
+};
+
+// How the layer is mapped onto the GEMM machinery
+enum TcMode {
+    MODE_STD = 0,     // NHWC bf16 input, K block = (tap, 64-channel chunk)
+    MODE_PAD8 = 1,    // image-edge conv (Cin <= 8): zero-padded NHWC8 input, K block = one kernel row (8 px x 8 ch)
+    MODE_PHASES = 2   // narrow transposed conv (Cout <= 4): the stride^2 output phases are stacked along N
 };
 
 struct TcParams {
@@ -46,13 +54,15 @@ struct TcParams {
     Tap taps[kMaxTaps];
     int phase_begin[5];  // taps of phase p are [phase_begin[p], phase_begin[p+1])
     int n_phases;
-    int a_stride;    // element stride of the A box along W and H (conv stride; 1 for deconv phases)
+    int mode;
+    int a_sx, a_sy;  // A-box start = tile origin * (a_sx, a_sy) + tap offset
     int out_stride;  // output pixels per grid cell (deconv: stride; conv: 1)
     int B, Gh, Gw;   // per-phase pixel grid
     int Ho, Wo;
     int TH, TW, tiles_y, tiles_x;
     int Cout, Ntile, n_blocks;
-    int kchunks;     // ceil(Cin / 64)
+    int kchunks;     // K boxes per tap (ceil(Cin / 64); 1 in MODE_PAD8)
+    int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
     int num_stages, acc_stages;
     int act, gdn, out_f32, out2;
     int gdn_chunk;
@@ -189,6 +199,16 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &P, int tile)
     return t;
 }
 
+__device__ __forceinline__ void load16f(const float *sm, float *o)
+{
+    const float4 *p = reinterpret_cast<const float4 *>(sm);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 t = p[i];
+        o[4 * i] = t.x; o[4 * i + 1] = t.y; o[4 * i + 2] = t.z; o[4 * i + 3] = t.w;
+    }
+}
+
 // 16 consecutive output channels of one pixel -> global memory (bf16 or fp32 NHWC) [+ bf16 secondary]
 __device__ __forceinline__ void store16(const TcParams &P, int64_t off, const float *v)
 {
@@ -211,13 +231,17 @@ __device__ __forceinline__ void store16(const TcParams &P, int64_t off, const fl
     }
 }
 
+enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_PHASES = 2 };
+
+template <int kEpi>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
     __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2], gdn_bar, gload_bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bias_s[kMaxCout], beta_s[256];
+    __shared__ __align__(16) float bias_s[kMaxCout];
+    __shared__ __align__(16) float beta_s[256];
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int stage_bytes = kABytes + P.Ntile * 128;
@@ -228,13 +252,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 128); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiThreads); }
         mbar_init(&gdn_bar, 1);
         mbar_init(&gload_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&P.tmA);
         prefetch_tmap(&P.tmB);
-        if (P.gdn) prefetch_tmap(&P.tmG);
+        if (kEpi == EPI_GDN) prefetch_tmap(&P.tmG);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
@@ -242,7 +266,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = threadIdx.x; i < kMaxCout; i += kTcThreads) {
         bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.0f;
-        if (i < 256) beta_s[i] = (P.gdn && i < P.Cout) ? P.beta[i] : 1.0f;
+        if (i < 256) beta_s[i] = (kEpi == EPI_GDN && i < P.Cout) ? P.beta[i] : 1.0f;
     }
     tc_fence_before();
     __syncthreads();
@@ -252,7 +276,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            if (P.gdn) {
+            if (kEpi == EPI_GDN) {
                 mbar_expect_tx(&gload_bar, (uint32_t)(P.Cout * P.Cout * 2));
                 for (int kc = 0; kc < P.Cout / 64; ++kc)
                     tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * P.Cout * 128, kc * 64, 0);
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
                 TileCoord t = decode_tile(P, tile);
-                const int cx = t.x0 * P.a_stride, cy = t.y0 * P.a_stride;
+                const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
                 for (int tp = P.phase_begin[t.phase]; tp < P.phase_begin[t.phase + 1]; ++tp) {
                     const Tap tap = P.taps[tp];
                     for (int kc = 0; kc < P.kchunks; ++kc) {
@@ -295,8 +319,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)   // 4 x K=16 per 64-channel chunk: +32 B per step inside the swizzle atom
+                    for (int k = 0; k < P.ksteps; ++k)   // K=16 per step: +32 B inside the 128-byte swizzle atom
                         tc_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                     tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
                     if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
@@ -305,8 +328,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             }
         }
     } else {
-        // ===================== epilogue warps (2..5) =====================
+        // ===================== epilogue: 8 warps, 2 per TMEM lane quarter, each pair splits the columns ============
         const int q = warp & 3;                 // TMEM lane quarter this warp can access
+        const int half = (warp - 2) >> 2;       // 0: first half of the 16-column chunks, 1: second half
         const int row = q * 32 + lane;          // accumulator row == pixel of the tile
         const int th = row / P.TW, tw = row - th * P.TW;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -319,78 +343,114 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             const uint32_t aphase = (P.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
             const int gy = t.y0 + th, gx = t.x0 + tw;
             const bool valid = gy < P.Gh && gx < P.Gw;
-            const int py = t.phase / P.out_stride, px = t.phase - py * P.out_stride;
-            const int oy = gy * P.out_stride + py, ox = gx * P.out_stride + px;
-            const int64_t pix_off = (((int64_t)t.b * P.Ho + oy) * P.Wo + ox) * P.Cout + t.n0;
             const uint32_t acc_addr = tmem_base + lane_addr + (uint32_t)(as * P.Ntile);
 
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
 
-            if (!P.gdn) {
-                for (int c0 = 0; c0 < P.Ntile; c0 += 16) {
+            if (kEpi == EPI_PHASES) {
+                // ---- narrow transposed conv: column n = phase * Cout + c ; planar fp32 NCHW output ----
+                if (half == 0) {
                     float v[16];
-                    tmem_ld16(acc_addr + c0, v);
+                    tmem_ld16(acc_addr, v);
                     tmem_ld_wait();
+                    if (valid) {
+                        const int s = P.out_stride;
+                        float *yo = (float *)P.y;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = act_tc(v[i] + bias_s[t.n0 + c0 + i], P.act);
-                    if (valid) store16(P, pix_off + c0, v);
+                        for (int n = 0; n < 16; ++n) {
+                            const int ph = n / P.Cout, c = n - ph * P.Cout;
+                            if (ph < s * s) {
+                                const int py = ph / s, px = ph - py * s;
+                                const int64_t o = (((int64_t)t.b * P.Cout + c) * P.Ho + (gy * s + py)) * P.Wo + (gx * s + px);
+                                yo[o] = act_tc(v[n] + bias_s[c], P.act);
+                            }
+                        }
+                    }
                 }
             } else {
-                // ---- pass 1: x = acc + bias ; x^2 (bf16) -> swizzled K-major tile in shared memory ----
-                for (int c0 = 0; c0 < P.Cout; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(acc_addr + c0, v);
-                    tmem_ld_wait();
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        float a = act_tc(v[2 * i] + bias_s[c0 + 2 * i], P.act), b = act_tc(v[2 * i + 1] + bias_s[c0 + 2 * i + 1], P.act);
-                        pk[i] = pack_bf16(a * a, b * b);
-                    }
-                    uint8_t *tile_base = sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)row * 128;
-                    const int j0 = (c0 & 63) >> 3;   // 16-byte chunk index inside the 128-byte row
-                    *reinterpret_cast<uint4 *>(tile_base + (((j0) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4 *>(tile_base + (((j0 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-                tc_fence_before();
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                for (int g0 = 0; g0 < P.Cout; g0 += P.gdn_chunk) {
-                    if (threadIdx.x == 64) {
-                        // ---- norm[128 x chunk] = X2[128 x C] * gamma[g0:g0+chunk, :]^T on the tensor cores ----
-                        if (it == 0 && g0 == 0) mbar_wait(&gload_bar, 0);
-                        tc_fence_after();
-                        const uint32_t idesc = make_idesc(P.gdn_chunk);
-                        for (int kc = 0; kc < P.Cout / 64; ++kc) {
-                            const uint64_t adesc = make_desc(smem_u32(sA2 + (size_t)kc * kABytes));
-                            const uint64_t bdesc = make_desc(smem_u32(sG + (size_t)kc * P.Cout * 128 + (size_t)g0 * 128));
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc_mma(tmem_base + norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
-                        }
-                        tc_commit(&gdn_bar);
-                    }
-                    mbar_wait(&gdn_bar, gdn_phase);
-                    gdn_phase ^= 1;
-                    tc_fence_after();
-                    // ---- pass 2: y = x * rsqrt(beta + norm)  (IGDN: * sqrt) ----
-                    for (int c0 = g0; c0 < g0 + P.gdn_chunk; c0 += 16) {
-                        float v[16], nrm[16];
+                const int py = t.phase / P.out_stride, px = t.phase - py * P.out_stride;
+                const int oy = gy * P.out_stride + py, ox = gx * P.out_stride + px;
+                const int64_t pix_off = (((int64_t)t.b * P.Ho + oy) * P.Wo + ox) * P.Cout + t.n0;
+                const int nch = P.Ntile >> 4;                       // 16-column chunks in this tile
+                const int ch_lo = half ? (nch + 1) / 2 : 0;
+                const int ch_hi = half ? nch : (nch + 1) / 2;
+                if (kEpi == EPI_PLAIN) {
+                    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                        const int c0 = ch << 4;
+                        float v[16], bs[16];
                         tmem_ld16(acc_addr + c0, v);
-                        tmem_ld16(tmem_base + lane_addr + norm_col + (uint32_t)(c0 - g0), nrm);
+                        load16f(bias_s + t.n0 + c0, bs);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float x = act_tc(v[i] + bias_s[c0 + i], P.act);
-                            float n = beta_s[c0 + i] + nrm[i];
-                            v[i] = (P.gdn == MMC_GDN_INVERSE) ? x * sqrtf(n) : x * rsqrtf(n);
-                        }
+                        for (int i = 0; i < 16; ++i) v[i] = act_tc(v[i] + bs[i], P.act);
                         if (valid) store16(P, pix_off + c0, v);
                     }
-                    // all 128 threads are done with the norm columns (and, on the last chunk, with sA2)
+                } else {
+                    // ---- pass 1: x = acc + bias ; x^2 (bf16) -> swizzled K-major tile in shared memory ----
+                    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                        const int c0 = ch << 4;
+                        float v[16], bs[16];
+                        tmem_ld16(acc_addr + c0, v);
+                        load16f(bias_s + c0, bs);
+                        tmem_ld_wait();
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            float a = v[2 * i] + bs[2 * i], b = v[2 * i + 1] + bs[2 * i + 1];
+                            pk[i] = pack_bf16(a * a, b * b);
+                        }
+                        uint8_t *tile_base = sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)row * 128;
+                        const int j0 = (c0 & 63) >> 3;   // 16-byte chunk index inside the 128-byte row
+                        *reinterpret_cast<uint4 *>(tile_base + (((j0) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(tile_base + (((j0 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
                     tc_fence_before();
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    for (int g0 = 0; g0 < P.Cout; g0 += P.gdn_chunk) {
+                        if (threadIdx.x == 64) {
+                            // ---- norm[128 x chunk] = X2[128 x C] * gamma[g0:g0+chunk, :]^T on the tensor cores ----
+                            if (it == 0 && g0 == 0) mbar_wait(&gload_bar, 0);
+                            tc_fence_after();
+                            const uint32_t idesc = make_idesc(P.gdn_chunk);
+                            for (int kc = 0; kc < P.Cout / 64; ++kc) {
+                                const uint64_t adesc = make_desc(smem_u32(sA2 + (size_t)kc * kABytes));
+                                const uint64_t bdesc = make_desc(smem_u32(sG + (size_t)kc * P.Cout * 128 + (size_t)g0 * 128));
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma(tmem_base + norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                            }
+                            tc_commit(&gdn_bar);
+                        }
+                        mbar_wait(&gdn_bar, gdn_phase);
+                        gdn_phase ^= 1;
+                        tc_fence_after();
+                        // ---- pass 2: y = x * rsqrt(beta + norm)  (IGDN: x * sqrt(n) = x * n * rsqrt(n)) ----
+                        const int gch = P.gdn_chunk >> 4;
+                        const int g_lo = (g0 >> 4) + (half ? (gch + 1) / 2 : 0);
+                        const int g_hi = (g0 >> 4) + (half ? gch : (gch + 1) / 2);
+                        for (int ch = g_lo; ch < g_hi; ++ch) {
+                            const int c0 = ch << 4;
+                            float v[16], nrm[16], bs[16], bt[16];
+                            tmem_ld16(acc_addr + c0, v);
+                            tmem_ld16(tmem_base + lane_addr + norm_col + (uint32_t)(c0 - g0), nrm);
+                            load16f(bias_s + c0, bs);
+                            load16f(beta_s + c0, bt);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float x = v[i] + bs[i];
+                                const float n = bt[i] + nrm[i];
+                                const float r = rsqrtf(n);
+                                v[i] = (P.gdn == MMC_GDN_INVERSE) ? x * (n * r) : x * r;
+                            }
+                            if (valid) store16(P, pix_off + c0, v);
+                        }
+                        // every epilogue thread is done with the norm columns (and, on the last chunk, with sA2)
+                        tc_fence_before();
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
                 }
             }
             tc_fence_before();
@@ -407,25 +467,174 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
-// weight packing: fp32 torch layout -> bf16 [tap][Cout][Cin]
+// host-side plan shared by the weight packer and the launcher
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, int transposed, int Cin, int Cout,
-                                                          int kk, __nv_bfloat16 *__restrict__ out)
+struct Plan {
+    int mode;
+    int ntaps;
+    Tap taps[kMaxTaps];
+    int tap_ky[kMaxTaps], tap_kx[kMaxTaps];   // MODE_STD: kernel position; MODE_PAD8: ky only; MODE_PHASES: (dy, dx)
+    int phase_begin[5], n_phases;
+    int a_sx, a_sy, out_stride, Gh, Gw;
+    int kchunks, ksteps;
+    int Ntile, n_blocks;
+    int wrows, wcols;                          // packed weight matrix: [ntaps * wrows][wcols] bf16
+    int Ho, Wo, Hp, Wp;
+};
+
+static void pad8_extent(const mmc_conv_desc *d, int Ho, int Wo, int *Hp, int *Wp)
 {
-    int64_t n = (int64_t)kk * Cout * Cin;
+    const int pad = d->k / 2;
+    int hp = d->H + 2 * pad, wp = d->W + 2 * pad;
+    const int need_w = d->stride * (Wo - 1) + 8;   // every output column reads an 8-pixel window
+    const int need_h = d->stride * (Ho - 1) + d->k;
+    if (wp < need_w) wp = need_w;
+    if (hp < need_h) hp = need_h;
+    *Hp = hp;
+    *Wp = (wp + 1) & ~1;
+}
+
+static int make_plan(const mmc_conv_desc *d, Plan &pl, const char *name)
+{
+    MMC_CHECK_ARG(d != nullptr, "%s: descriptor is NULL", name);
+    MMC_CHECK_ARG(d->B >= 0 && d->H >= 1 && d->W >= 1 && d->Cin >= 1 && d->Cout >= 1, "%s: bad shape", name);
+    MMC_CHECK_ARG(d->k == 1 || d->k == 3 || d->k == 5, "%s: kernel size %d not in {1,3,5}", name, d->k);
+    MMC_CHECK_ARG(d->stride == 1 || d->stride == 2, "%s: stride %d not in {1,2}", name, d->stride);
+    MMC_UNSUPPORTED(d->Cout > kMaxCout, "%s: Cout=%d exceeds %d", name, d->Cout, kMaxCout);
+    memset(&pl, 0, sizeof(pl));
+    const int k = d->k, s = d->stride, pad = k / 2;
+    mmc_conv_out_size(d, &pl.Ho, &pl.Wo);
+    if (d->in_layout == MMC_NHWC_PAD8) {
+        // ---- image-edge convolution: one K box per kernel row = 8 pixels x 8 channels ----
+        MMC_UNSUPPORTED(d->transposed || d->Cin > 8 || d->Cout % 16 != 0, "%s: NHWC_PAD8 input needs a forward conv with Cin <= 8, Cout %% 16 == 0", name);
+        pl.mode = MODE_PAD8;
+        pl.n_phases = 1; pl.a_sx = 1; pl.a_sy = s; pl.out_stride = 1; pl.Gh = pl.Ho; pl.Gw = pl.Wo;
+        pl.kchunks = 1; pl.ksteps = (k * 8 + 15) / 16;
+        for (int ky = 0; ky < k; ++ky) {
+            pl.taps[pl.ntaps] = Tap{(int16_t)ky, 0, ky * d->Cout};
+            pl.tap_ky[pl.ntaps++] = ky;
+        }
+        pl.phase_begin[0] = 0; pl.phase_begin[1] = pl.ntaps;
+        pl.wrows = d->Cout; pl.wcols = 64;
+        pad8_extent(d, pl.Ho, pl.Wo, &pl.Hp, &pl.Wp);
+    } else if (d->transposed && d->Cout <= 4 && s == 2) {
+        // ---- narrow transposed conv: all stride^2 phases share the input patch; stack them along N ----
+        MMC_UNSUPPORTED(d->Cin % 8 != 0 || d->Cin < 32, "%s: tensor-core path needs Cin %% 8 == 0 and Cin >= 32 (got %d)", name, d->Cin);
+        pl.mode = MODE_PHASES;
+        pl.n_phases = 1; pl.a_sx = pl.a_sy = 1; pl.out_stride = s; pl.Gh = d->H; pl.Gw = d->W;
+        pl.kchunks = (d->Cin + 63) / 64; pl.ksteps = 4;
+        for (int dy = -2; dy <= 2; ++dy)
+            for (int dx = -2; dx <= 2; ++dx) {
+                bool used = false;   // oy = s*qy + py, iy = qy + dy  =>  ky = py + pad - s*dy
+                for (int py = 0; py < s; ++py)
+                    for (int px = 0; px < s; ++px) {
+                        int ky = py + pad - s * dy, kx = px + pad - s * dx;
+                        used |= (ky >= 0 && ky < k && kx >= 0 && kx < k);
+                    }
+                if (!used) continue;
+                pl.taps[pl.ntaps] = Tap{(int16_t)dy, (int16_t)dx, pl.ntaps * 16};
+                pl.tap_ky[pl.ntaps] = dy; pl.tap_kx[pl.ntaps] = dx;
+                ++pl.ntaps;
+            }
+        pl.phase_begin[0] = 0; pl.phase_begin[1] = pl.ntaps;
+        pl.wrows = 16; pl.wcols = d->Cin;
+    } else {
+        MMC_UNSUPPORTED(d->Cin % 8 != 0 || d->Cin < 32, "%s: tensor-core path needs Cin %% 8 == 0 and Cin >= 32 (got %d); use the direct kernel", name, d->Cin);
+        MMC_UNSUPPORTED(d->Cout % 16 != 0, "%s: tensor-core path needs Cout %% 16 == 0 (got %d); use the direct kernel", name, d->Cout);
+        pl.mode = MODE_STD;
+        pl.kchunks = (d->Cin + 63) / 64; pl.ksteps = 4;
+        pl.wrows = d->Cout; pl.wcols = d->Cin;
+        if (!d->transposed) {
+            pl.n_phases = 1; pl.a_sx = pl.a_sy = s; pl.out_stride = 1; pl.Gh = pl.Ho; pl.Gw = pl.Wo;
+            for (int ky = 0; ky < k; ++ky)
+                for (int kx = 0; kx < k; ++kx) {
+                    pl.taps[pl.ntaps] = Tap{(int16_t)(ky - pad), (int16_t)(kx - pad), pl.ntaps * d->Cout};
+                    pl.tap_ky[pl.ntaps] = ky; pl.tap_kx[pl.ntaps] = kx;
+                    ++pl.ntaps;
+                }
+            pl.phase_begin[1] = pl.ntaps;
+        } else {
+            // oy = iy*s - pad + ky  =>  for output phase py: ky == (py + pad) mod s, iy = qy + (py + pad - ky)/s
+            pl.n_phases = s * s; pl.a_sx = pl.a_sy = 1; pl.out_stride = s; pl.Gh = d->H; pl.Gw = d->W;
+            for (int ph = 0; ph < s * s; ++ph) {
+                const int py = ph / s, px = ph % s;
+                pl.phase_begin[ph] = pl.ntaps;
+                for (int ky = 0; ky < k; ++ky) {
+                    if (((py + pad - ky) % s) != 0) continue;
+                    for (int kx = 0; kx < k; ++kx) {
+                        if (((px + pad - kx) % s) != 0) continue;
+                        pl.taps[pl.ntaps] = Tap{(int16_t)((py + pad - ky) / s), (int16_t)((px + pad - kx) / s), pl.ntaps * d->Cout};
+                        pl.tap_ky[pl.ntaps] = ky; pl.tap_kx[pl.ntaps] = kx;
+                        ++pl.ntaps;
+                    }
+                }
+            }
+            pl.phase_begin[s * s] = pl.ntaps;
+        }
+    }
+    return MMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing: fp32 torch layout -> bf16 [tap][rows][cols] in the plan's K order
+// ---------------------------------------------------------------------------------------------
+struct PackParams {
+    int mode, transposed, Cin, Cout, k, stride, ntaps, wrows, wcols;
+    int16_t ta[kMaxTaps], tb[kMaxTaps];
+};
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, PackParams q, __nv_bfloat16 *__restrict__ out)
+{
+    const int kk = q.k * q.k, pad = q.k / 2;
+    int64_t n = (int64_t)q.ntaps * q.wrows * q.wcols;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        int ci = (int)(i % Cin);
-        int64_t r = i / Cin;
-        int co = (int)(r % Cout);
-        int tap = (int)(r / Cout);
-        int64_t src = transposed ? (((int64_t)ci * Cout + co) * kk + tap) : (((int64_t)co * Cin + ci) * kk + tap);
-        out[i] = __float2bfloat16_rn(__ldg(w + src));
+        int col = (int)(i % q.wcols);
+        int64_t r = i / q.wcols;
+        int row = (int)(r % q.wrows);
+        int tap = (int)(r / q.wrows);
+        float v = 0.0f;
+        if (q.mode == MODE_STD) {
+            int kpos = q.ta[tap] * q.k + q.tb[tap];
+            int64_t src = q.transposed ? (((int64_t)col * q.Cout + row) * kk + kpos) : (((int64_t)row * q.Cin + col) * kk + kpos);
+            v = __ldg(w + src);
+        } else if (q.mode == MODE_PAD8) {
+            int kx = col >> 3, c = col & 7, ky = q.ta[tap];
+            if (kx < q.k && c < q.Cin) v = __ldg(w + (((int64_t)row * q.Cin + c) * kk + ky * q.k + kx));
+        } else {
+            int ph = row / q.Cout, c = row - ph * q.Cout;
+            if (ph < q.stride * q.stride) {
+                int py = ph / q.stride, px = ph - py * q.stride;
+                int ky = py + pad - q.stride * q.ta[tap], kx = px + pad - q.stride * q.tb[tap];
+                if (ky >= 0 && ky < q.k && kx >= 0 && kx < q.k) v = __ldg(w + (((int64_t)col * q.Cout + c) * kk + ky * q.k + kx));
+            }
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+
+// NCHW fp32 image -> zero-padded NHWC bf16 with 8 channels per pixel ([B][Hp][Wp][8], 16 B per pixel)
+__global__ void __launch_bounds__(256) pad8_kernel(const float *__restrict__ x, int C, int H, int W, int pad, int Hp, int Wp,
+                                                  int64_t npix, uint4 *__restrict__ out)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
+        int px = (int)(i % Wp);
+        int64_t r = i / Wp;
+        int py = (int)(r % Hp);
+        int64_t b = r / Hp;
+        int iy = py - pad, ix = px - pad;
+        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            const float *src = x + (b * C * H + iy) * (int64_t)W + ix;
+            for (int c = 0; c < C; ++c) v[c] = __ldg(src + (int64_t)c * H * W);
+        }
+        out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// host side
+// tensor maps
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -465,28 +674,38 @@ static int pick_ntile(int cout)
     return 0;
 }
 
-static void pick_tile(int gh, int gw, int a_stride, int *TH, int *TW)
+static void pick_tile(int gh, int gw, int sx, int sy, int *TH, int *TW)
 {
     const int cand[][2] = {{8, 16}, {16, 8}, {4, 32}, {32, 4}, {2, 64}, {64, 2}, {1, 128}, {128, 1}};
     int64_t best = -1;
     for (auto &c : cand) {
-        if (c[0] * a_stride > 256 || c[1] * a_stride > 256) continue;   // TMA box limit
+        if (c[0] * sy > 256 || c[1] * sx > 256) continue;   // TMA box limit
         int64_t tiles = (int64_t)((gh + c[0] - 1) / c[0]) * ((gw + c[1] - 1) / c[1]);
         if (best < 0 || tiles < best) { best = tiles; *TH = c[0]; *TW = c[1]; }
     }
 }
 
-static int tc_validate(const mmc_conv_desc *d, const char *name)
+template <int kEpi>
+static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaStream_t st, const char *name)
 {
-    MMC_CHECK_ARG(d != nullptr, "%s: descriptor is NULL", name);
-    MMC_CHECK_ARG(d->B >= 0 && d->H >= 1 && d->W >= 1 && d->Cin >= 1 && d->Cout >= 1, "%s: bad shape", name);
-    MMC_CHECK_ARG(d->k == 1 || d->k == 3 || d->k == 5, "%s: kernel size %d not in {1,3,5}", name, d->k);
-    MMC_CHECK_ARG(d->stride == 1 || d->stride == 2, "%s: stride %d not in {1,2}", name, d->stride);
-    // Cin is walked in 64-channel TMA boxes; a ragged last box is zero-filled by TMA on both operands.
-    // The global row pitch (Cin * 2 B) must be a multiple of 16 B for the tensor maps.
-    MMC_UNSUPPORTED(d->Cin % 8 != 0 || d->Cin < 32, "%s: tensor-core path needs Cin %% 8 == 0 and Cin >= 32 (got %d); use the direct kernel", name, d->Cin);
-    MMC_UNSUPPORTED(d->Cout > kMaxCout, "%s: Cout=%d exceeds %d", name, d->Cout, kMaxCout);
-    MMC_UNSUPPORTED(d->Cout % 16 != 0, "%s: tensor-core path needs Cout %% 16 == 0 (got %d); use the direct kernel", name, d->Cout);
+    // dynamic shared memory available next to the kernel's static allocation (227 KB per CTA on sm_100)
+    static size_t budget = 0;
+    if (budget == 0) {
+        cudaFuncAttributes fa;
+        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi>));
+        size_t avail = 227 * 1024 - fa.sharedSizeBytes;
+        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        budget = avail;
+    }
+    MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
+    int stages = (int)((budget - fixed) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    TcParams Q = P;
+    Q.num_stages = stages;
+    const size_t smem = fixed + (size_t)stages * stage_bytes;
+    int grid = Q.total_tiles < kNumSMs ? Q.total_tiles : kNumSMs;
+    conv_tc_kernel<kEpi><<<grid, kTcThreads, smem, st>>>(Q);
+    MMC_CHECK_LAUNCH(name);
     return MMC_OK;
 }
 
@@ -496,17 +715,42 @@ using namespace mmc;
 
 extern "C" {
 
+int mmc_conv_pad8_size(const mmc_conv_desc *d, int *Hp, int *Wp)
+{
+    MMC_CHECK_ARG(d && Hp && Wp, "mmc_conv_pad8_size: NULL argument");
+    int Ho, Wo;
+    int rc = mmc_conv_out_size(d, &Ho, &Wo);
+    if (rc) return rc;
+    pad8_extent(d, Ho, Wo, Hp, Wp);
+    return MMC_OK;
+}
+
+int mmc_pad_nchw_to_nhwc8(const float *x, int64_t B, int C, int H, int W, int pad, int Hp, int Wp, void *out, void *stream)
+{
+    MMC_CHECK_ARG(B >= 0 && C >= 1 && C <= 8 && H >= 1 && W >= 1 && pad >= 0 && Hp >= H + pad && Wp >= W + pad,
+                  "mmc_pad_nchw_to_nhwc8: bad shape");
+    if (B == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && out && aligned16(out), "mmc_pad_nchw_to_nhwc8: NULL or unaligned buffer");
+    int64_t npix = B * Hp * Wp;
+    pad8_kernel<<<elementwise_grid(npix, 256), 256, 0, (cudaStream_t)stream>>>(x, C, H, W, pad, Hp, Wp, npix, (uint4 *)out);
+    MMC_CHECK_LAUNCH("mmc_pad_nchw_to_nhwc8");
+    return MMC_OK;
+}
+
 int mmc_conv_pack_weights(const mmc_conv_desc *d, const float *w, void *w_packed, size_t *bytes, void *stream)
 {
-    int rc = tc_validate(d, "mmc_conv_pack_weights");
+    Plan pl;
+    int rc = make_plan(d, pl, "mmc_conv_pack_weights");
     if (rc) return rc;
-    size_t need = (size_t)d->k * d->k * d->Cout * d->Cin * sizeof(__nv_bfloat16);
-    if (bytes) *bytes = need;
+    int64_t n = (int64_t)pl.ntaps * pl.wrows * pl.wcols;
+    if (bytes) *bytes = (size_t)n * sizeof(__nv_bfloat16);
     if (!w_packed) return MMC_OK;
     MMC_CHECK_ARG(w != nullptr, "mmc_conv_pack_weights: w is NULL");
-    int64_t n = (int64_t)d->k * d->k * d->Cout * d->Cin;
-    pack_weights_kernel<<<elementwise_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(w, d->transposed, d->Cin, d->Cout, d->k * d->k,
-                                                                                  (__nv_bfloat16 *)w_packed);
+    PackParams q;
+    q.mode = pl.mode; q.transposed = d->transposed; q.Cin = d->Cin; q.Cout = d->Cout; q.k = d->k; q.stride = d->stride;
+    q.ntaps = pl.ntaps; q.wrows = pl.wrows; q.wcols = pl.wcols;
+    for (int t = 0; t < kMaxTaps; ++t) { q.ta[t] = (int16_t)pl.tap_ky[t]; q.tb[t] = (int16_t)pl.tap_kx[t]; }
+    pack_weights_kernel<<<elementwise_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(w, q, (__nv_bfloat16 *)w_packed);
     MMC_CHECK_LAUNCH("mmc_conv_pack_weights");
     return MMC_OK;
 }
@@ -515,62 +759,44 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
                         const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream)
 {
     const char *name = "mmc_conv_forward_tc";
-    int rc = tc_validate(d, name);
+    Plan pl;
+    int rc = make_plan(d, pl, name);
     if (rc) return rc;
-    MMC_CHECK_ARG(d->in_dtype == MMC_BF16 && d->in_layout == MMC_NHWC, "%s: input must be NHWC bf16", name);
-    MMC_CHECK_ARG(d->out_layout == MMC_NHWC, "%s: output must be NHWC", name);
+    MMC_CHECK_ARG(d->in_dtype == MMC_BF16 && (d->in_layout == MMC_NHWC || d->in_layout == MMC_NHWC_PAD8), "%s: input must be NHWC bf16", name);
     MMC_CHECK_ARG(d->act >= 0 && d->act <= MMC_ACT_LEAKY_RELU, "%s: bad act", name);
     MMC_CHECK_ARG(d->gdn >= 0 && d->gdn <= MMC_GDN_INVERSE, "%s: bad gdn mode", name);
     MMC_CHECK_ARG(d->out2_bf16 >= 0 && d->out2_bf16 <= 2, "%s: bad out2_bf16", name);
     MMC_CHECK_ARG(d->gdn == MMC_GDN_NONE || (beta_eff && gamma_eff_bf16), "%s: GDN needs beta/gamma", name);
     MMC_CHECK_ARG(!d->out2_bf16 || y2, "%s: out2_bf16 set but y2 is NULL", name);
-    MMC_UNSUPPORTED(d->gdn != MMC_GDN_NONE && (d->Cout > 192 || d->Cout % 64 != 0),
-                    "%s: fused GDN supports Cout in {64,128,192} (got %d)", name, d->Cout);
+    if (pl.mode == MODE_PHASES) {
+        MMC_CHECK_ARG(d->out_layout == MMC_NCHW && d->out_dtype == MMC_F32 && d->gdn == MMC_GDN_NONE && !d->out2_bf16,
+                      "%s: narrow transposed conv writes planar fp32 NCHW without GDN / secondary output", name);
+    } else {
+        MMC_CHECK_ARG(d->out_layout == MMC_NHWC, "%s: output must be NHWC", name);
+        MMC_UNSUPPORTED(d->gdn != MMC_GDN_NONE && (d->Cout > 192 || d->Cout % 64 != 0),
+                        "%s: fused GDN supports Cout in {64,128,192} (got %d)", name, d->Cout);
+    }
     if (d->B == 0) return MMC_OK;
     MMC_CHECK_ARG(x && w_packed && y, "%s: NULL buffer", name);
     MMC_CHECK_ARG(aligned16(x) && aligned16(w_packed) && aligned16(y) && (!y2 || aligned16(y2)), "%s: buffers must be 16-byte aligned", name);
 
     TcParams P;
     memset(&P, 0, sizeof(P));
-    const int k = d->k, s = d->stride, pad = k / 2, kk = k * k;
-    int Ho, Wo;
-    mmc_conv_out_size(d, &Ho, &Wo);
-    P.Ho = Ho; P.Wo = Wo; P.B = d->B; P.Cout = d->Cout;
-    P.kchunks = (d->Cin + 63) / 64;
+    P.mode = pl.mode;
+    P.Ho = pl.Ho; P.Wo = pl.Wo; P.B = d->B; P.Cout = d->Cout;
+    P.kchunks = pl.kchunks; P.ksteps = pl.ksteps;
     P.act = d->act; P.gdn = d->gdn; P.out_f32 = (d->out_dtype == MMC_F32); P.out2 = d->out2_bf16;
     P.bias = bias; P.beta = beta_eff; P.y = y; P.y2 = (__nv_bfloat16 *)y2;
-
-    // ---- phases and taps ----
-    int nt = 0;
-    if (!d->transposed) {
-        P.n_phases = 1; P.a_stride = s; P.out_stride = 1; P.Gh = Ho; P.Gw = Wo;
-        P.phase_begin[0] = 0;
-        for (int ky = 0; ky < k; ++ky)
-            for (int kx = 0; kx < k; ++kx) P.taps[nt++] = Tap{(int16_t)(ky - pad), (int16_t)(kx - pad), (ky * k + kx) * d->Cout};
-        P.phase_begin[1] = nt;
-    } else {
-        // oy = iy*s - pad + ky  =>  for output phase py: ky == (py + pad) mod s, iy = qy + (py + pad - ky)/s
-        P.n_phases = s * s; P.a_stride = 1; P.out_stride = s; P.Gh = d->H; P.Gw = d->W;
-        for (int ph = 0; ph < s * s; ++ph) {
-            const int py = ph / s, px = ph % s;
-            P.phase_begin[ph] = nt;
-            for (int ky = 0; ky < k; ++ky) {
-                if (((py + pad - ky) % s) != 0) continue;
-                for (int kx = 0; kx < k; ++kx) {
-                    if (((px + pad - kx) % s) != 0) continue;
-                    P.taps[nt++] = Tap{(int16_t)((py + pad - ky) / s), (int16_t)((px + pad - kx) / s), (ky * k + kx) * d->Cout};
-                }
-            }
-        }
-        P.phase_begin[s * s] = nt;
-    }
-    (void)kk;
+    P.n_phases = pl.n_phases; P.a_sx = pl.a_sx; P.a_sy = pl.a_sy; P.out_stride = pl.out_stride; P.Gh = pl.Gh; P.Gw = pl.Gw;
+    for (int t = 0; t < pl.ntaps; ++t) P.taps[t] = pl.taps[t];
+    for (int i = 0; i < 5; ++i) P.phase_begin[i] = pl.phase_begin[i];
 
     // ---- tiling ----
-    P.Ntile = (d->gdn != MMC_GDN_NONE) ? d->Cout : pick_ntile(d->Cout);
+    if (pl.mode == MODE_PHASES) P.Ntile = 16;
+    else P.Ntile = (d->gdn != MMC_GDN_NONE) ? d->Cout : pick_ntile(d->Cout);
     MMC_UNSUPPORTED(P.Ntile == 0 || P.Ntile > 256, "%s: no valid N tile for Cout=%d", name, d->Cout);
-    P.n_blocks = d->Cout / P.Ntile;
-    pick_tile(P.Gh, P.Gw, P.a_stride, &P.TH, &P.TW);
+    P.n_blocks = (pl.mode == MODE_PHASES) ? 1 : d->Cout / P.Ntile;
+    pick_tile(P.Gh, P.Gw, pl.mode == MODE_PAD8 ? 1 : P.a_sx, P.a_sy, &P.TH, &P.TW);
     P.tiles_y = (P.Gh + P.TH - 1) / P.TH;
     P.tiles_x = (P.Gw + P.TW - 1) / P.TW;
     int64_t tpp = (int64_t)d->B * P.tiles_y * P.tiles_x * P.n_blocks;
@@ -578,41 +804,34 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     P.tiles_per_phase = (int)tpp;
     P.total_tiles = (int)(tpp * P.n_phases);
     P.gdn_chunk = 0;
-    if (d->gdn != MMC_GDN_NONE) P.gdn_chunk = (2 * P.Ntile + P.Ntile <= 512) ? P.Ntile : P.Ntile / 2;
+    if (d->gdn != MMC_GDN_NONE) P.gdn_chunk = (3 * P.Ntile <= 512) ? P.Ntile : P.Ntile / 2;
     P.acc_stages = (2 * P.Ntile + P.gdn_chunk <= 512) ? 2 : 1;
     MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
 
-    // ---- shared memory budget ----
     const size_t stage_bytes = kABytes + (size_t)P.Ntile * 128;
     size_t fixed = 1024;  // alignment slack
     if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (size_t)(d->Cout / 64) * kABytes;
-    // dynamic shared memory available next to the kernel's static allocation (227 KB per CTA on sm_100)
-    static size_t budget = 0;
-    if (budget == 0) {
-        cudaFuncAttributes fa;
-        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel));
-        size_t avail = 227 * 1024 - fa.sharedSizeBytes;
-        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
-        budget = avail;
-    }
-    MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
-    int stages = (int)((budget - fixed) / stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
-    P.num_stages = stages;
-    const size_t smem = fixed + (size_t)stages * stage_bytes;
 
     // ---- tensor maps ----
-    {
+    if (pl.mode == MODE_PAD8) {
+        // Overlapping-window view of the padded NHWC8 image: dim0 = 64 contiguous elements (8 pixels x 8 ch),
+        // dim1 = output column (stride * 16 B apart), dim2 = padded row, dim3 = image.
+        uint64_t dims[4] = {64, (uint64_t)pl.Wo, (uint64_t)pl.Hp, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)d->stride * 16, (uint64_t)pl.Wp * 16, (uint64_t)pl.Hp * pl.Wp * 16};
+        uint32_t box[4] = {64, (uint32_t)P.TW, (uint32_t)(P.TH * P.a_sy), 1};
+        uint32_t es[4] = {1, 1, (uint32_t)P.a_sy, 1};
+        rc = encode_map(&P.tmA, x, 4, dims, str, box, es, "padded image");
+    } else {
         uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
-        uint32_t box[4] = {64, (uint32_t)(P.TW * P.a_stride), (uint32_t)(P.TH * P.a_stride), 1};
-        uint32_t es[4] = {1, (uint32_t)P.a_stride, (uint32_t)P.a_stride, 1};
+        uint32_t box[4] = {64, (uint32_t)(P.TW * P.a_sx), (uint32_t)(P.TH * P.a_sy), 1};
+        uint32_t es[4] = {1, (uint32_t)P.a_sx, (uint32_t)P.a_sy, 1};
         rc = encode_map(&P.tmA, x, 4, dims, str, box, es, "activations");
-        if (rc) return rc;
     }
+    if (rc) return rc;
     {
-        uint64_t dims[2] = {(uint64_t)d->Cin, (uint64_t)k * k * d->Cout};
-        uint64_t str[1] = {(uint64_t)d->Cin * 2};
+        uint64_t dims[2] = {(uint64_t)pl.wcols, (uint64_t)pl.ntaps * pl.wrows};
+        uint64_t str[1] = {(uint64_t)pl.wcols * 2};
         uint32_t box[2] = {64, (uint32_t)P.Ntile};
         uint32_t es[2] = {1, 1};
         rc = encode_map(&P.tmB, w_packed, 2, dims, str, box, es, "weights");
@@ -627,11 +846,10 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         rc = encode_map(&P.tmG, gamma_eff_bf16, 2, dims, str, box, es, "gamma");
         if (rc) return rc;
     }
-
-    int grid = P.total_tiles < kNumSMs ? P.total_tiles : kNumSMs;
-    conv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(P);
-    MMC_CHECK_LAUNCH(name);
-    return MMC_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl.mode == MODE_PHASES) return launch_tc<EPI_PHASES>(P, fixed, stage_bytes, st, name);
+    if (d->gdn != MMC_GDN_NONE) return launch_tc<EPI_GDN>(P, fixed, stage_bytes, st, name);
+    return launch_tc<EPI_PLAIN>(P, fixed, stage_bytes, st, name);
 }
 
 }  // extern "C"

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libmmcodec.so")
 MMC_OK, MMC_EINVAL, MMC_ECUDA, MMC_EUNSUPPORTED, MMC_EDOMAIN = 0, -1, -2, -3, -4
 MEANS_NONE, MEANS_FULL, MEANS_PER_CHANNEL = 0, 1, 2
 F32, BF16 = 0, 1
-NCHW, NHWC = 0, 1
+NCHW, NHWC, NHWC_PAD8 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_ABS = 0, 1, 2, 3
 GDN_NONE, GDN_FORWARD, GDN_INVERSE = 0, 1, 2
 
@@ -55,6 +55,8 @@ _PROTOS = {
     "mmc_conv_pack_weights": (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, ctypes.POINTER(ctypes.c_size_t), c_vp]),
     "mmc_conv_forward_direct": (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mmc_conv_forward_tc": (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmc_conv_pad8_size": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "mmc_pad_nchw_to_nhwc8": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "mmc_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "mmc_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "mmc_nhwc_f32_to_nchw_f32": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),

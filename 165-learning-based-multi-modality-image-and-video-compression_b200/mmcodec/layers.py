@@ -123,7 +123,7 @@ class _PackedWeightMixin:
     whenever the Parameter's version or storage changes, e.g. after load_state_dict / optimizer step)."""
 
     def packed_weight(self, d: L.ConvDesc):
-        key = (self.weight._version, self.weight.data_ptr())
+        key = (self.weight._version, self.weight.data_ptr(), d.in_layout, d.out_layout, d.transposed)
         if getattr(self, "_pack_key", None) != key:
             self._pack = ops.conv_pack_weights(d, self.weight)
             self._pack_key = key

@@ -329,6 +329,19 @@ def conv_forward_tc(d: L.ConvDesc, x: Tensor, w_packed: Tensor, bias: Optional[T
     return (y, y2) if d.out2_bf16 else y
 
 
+def pad_to_nhwc8(x: Tensor, d: L.ConvDesc) -> Tensor:
+    """fp32 NCHW image (<= 8 channels) -> zero-padded bf16 [B][Hp][Wp][8] staging buffer for a NHWC_PAD8 conv."""
+    _require_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    hp, wp = ctypes.c_int(), ctypes.c_int()
+    L.check(L.lib().mmc_conv_pad8_size(ctypes.byref(d), ctypes.byref(hp), ctypes.byref(wp)))
+    out = torch.empty((B, hp.value, wp.value, 8), dtype=torch.bfloat16, device=x.device)
+    with _Timed("pad8|layout"):
+        L.check(L.lib().mmc_pad_nchw_to_nhwc8(_ptr(x), B, C, H, W, d.k // 2, hp.value, wp.value, _ptr(out), _stream()))
+    return out
+
+
 def nchw_to_nhwc_bf16(x: Tensor) -> Tensor:
     _require_cuda(x)
     x = _f32c(x)

@@ -107,8 +107,19 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0):
                 B, H, W, C = cur.shape
             if C != cin:
                 raise ValueError(f"expected {cin} input channels, got {C}")
-            tc = _tc_eligible(cin, cout, s.gdn is not None)
-            if tc and fmt != "nhwc_bf16":
+            stride, k = c.stride[0], c.kernel_size[0]
+            gdn_ok = s.gdn is None or cout in (64, 128, 192)
+            # shape class of this layer (see mmc_conv_forward_tc)
+            edge_in = (use_tensor_cores and not s.transposed and cin <= 8 and cout % 16 == 0 and cout <= 1024 and gdn_ok
+                       and k in (3, 5) and fmt == "nchw_f32")
+            edge_out = (use_tensor_cores and s.transposed and cout <= 4 and stride == 2 and last and out_fmt == "nchw_f32"
+                        and s.gdn is None and not out2 and cin % 8 == 0 and cin >= 32)
+            tc = edge_in or edge_out or _tc_eligible(cin, cout, s.gdn is not None)
+            in_layout = None
+            if edge_in:
+                dpad = ops.conv_desc(False, B, H, W, cin, cout, k, stride, L.BF16, L.NHWC_PAD8, L.BF16, L.NHWC)
+                cur, fmt, in_layout = ops.pad_to_nhwc8(cur, dpad), "nhwc_bf16", L.NHWC_PAD8
+            elif tc and fmt != "nhwc_bf16":
                 # API-edge input of a tensor-core layer: one conversion pass to NHWC bf16
                 cur = ops.nchw_to_nhwc_bf16(cur) if fmt == "nchw_f32" else ops.to_bf16(cur)
                 fmt = "nhwc_bf16"
@@ -116,11 +127,13 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0):
                 ofmt = "nhwc_bf16"
             elif out_fmt == "nchw_f32":
                 # narrow outputs (the 3-channel image) are written planar; wide ones stay NHWC in memory
-                ofmt = "nchw_f32" if (not tc and cout <= 4) else "nhwc_f32"
+                ofmt = "nchw_f32" if (edge_out or (not tc and cout <= 4)) else "nhwc_f32"
             else:
                 ofmt = out_fmt
-            d = ops.conv_desc(s.transposed, B, H, W, cin, cout, c.kernel_size[0], c.stride[0],
-                              L.F32 if fmt.endswith("f32") else L.BF16, L.NCHW if fmt.startswith("nchw") else L.NHWC,
+            if in_layout is None:
+                in_layout = L.NCHW if fmt.startswith("nchw") else L.NHWC
+            d = ops.conv_desc(s.transposed, B, H, W, cin, cout, k, stride,
+                              L.F32 if fmt.endswith("f32") else L.BF16, in_layout,
                               L.F32 if ofmt.endswith("f32") else L.BF16, L.NCHW if ofmt.startswith("nchw") else L.NHWC,
                               act=s.act, gdn=(L.GDN_NONE if s.gdn is None else (L.GDN_INVERSE if s.gdn.inverse else L.GDN_FORWARD)),
                               out2=(out2 if last else 0))

@@ -49,7 +49,13 @@ enum mmc_status {
 enum mmc_means_mode { MMC_MEANS_NONE = 0, MMC_MEANS_FULL = 1, MMC_MEANS_PER_CHANNEL = 2 };
 
 enum mmc_dtype { MMC_F32 = 0, MMC_BF16 = 1 };
-enum mmc_layout { MMC_NCHW = 0, MMC_NHWC = 1 };
+enum mmc_layout {
+    MMC_NCHW = 0,
+    MMC_NHWC = 1,
+    MMC_NHWC_PAD8 = 2 /* bf16 [B][Hp][Wp][8]: image with <= 8 channels, zero-padded by k/2 pixels and to 8
+                         channels (see mmc_conv_pad8_size / mmc_pad_nchw_to_nhwc8); tensor-core input of the
+                         image-edge convolutions (g_a.0: 3 -> N, depth branch: 1 -> N) */
+};
 
 /* activation fused after bias (and before GDN where both are given) */
 enum mmc_act {
@@ -190,10 +196,20 @@ MMC_API int mmc_conv_forward_direct(const mmc_conv_desc *d, const void *x, const
                             const float *beta_eff, const float *gamma_eff, void *y, void *y2, void *stream);
 
 /* Tensor-core implicit GEMM (TMA -> smem -> tcgen05.mma -> TMEM -> fused epilogue).
- * Requires NHWC bf16 input, Cin % 8 == 0 (>= 32), Cout % 16 == 0 (<= 1024; split into N tiles <= 256);
- * fused GDN needs Cout in {64, 128, 192}.  Anything else returns MMC_EUNSUPPORTED. */
+ * Three shape classes (chosen from the descriptor, same choice in mmc_conv_pack_weights):
+ *   - NHWC bf16 input, Cin % 8 == 0 (>= 32), Cout % 16 == 0 (<= 1024; split into N tiles <= 256), NHWC output;
+ *   - NHWC_PAD8 input (Cin <= 8) forward conv, Cout % 16 == 0, NHWC output;
+ *   - transposed, stride 2, Cout <= 4 (the reconstruction layer): planar fp32 NCHW output.
+ * Fused GDN needs Cout in {64, 128, 192}.  Anything else returns MMC_EUNSUPPORTED. */
 MMC_API int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_packed, const float *bias,
                         const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream);
+
+/* Staging for image-edge convolutions on the tensor cores (Cin <= 8): the fp32 NCHW image is copied once
+ * into a zero-padded 8-channel NHWC bf16 buffer [B][Hp][Wp][8]; the conv then reads each 5x5 (3x3) window row
+ * as one 128-byte TMA box.  mmc_conv_pad8_size gives (Hp, Wp) for a descriptor with in_layout NHWC_PAD8. */
+MMC_API int mmc_conv_pad8_size(const mmc_conv_desc *d, int *Hp, int *Wp);
+MMC_API int mmc_pad_nchw_to_nhwc8(const float *x, int64_t B, int C, int H, int W, int pad, int Hp, int Wp, void *out,
+                                  void *stream);
 
 /* Layout / dtype conversion at the API edges. */
 MMC_API int mmc_nchw_f32_to_nhwc_bf16(const float *x, int64_t B, int C, int64_t HW, void *y, void *stream);

@@ -94,3 +94,59 @@ def test_conv_tc_rejects_unsupported_shapes():
     d = ops.conv_desc(False, 1, 8, 8, 3, 128, 5, 2, L.BF16, L.NHWC, L.BF16, L.NHWC)
     with pytest.raises(NotImplementedError):
         ops.conv_pack_weights(d, torch.zeros(128, 3, 5, 5, device=dev()))
+
+
+@pytest.mark.parametrize("cin,cout,k,s,h,w,gdn,B", [
+    (3, 128, 5, 2, 64, 96, L.GDN_FORWARD, 2),    # g_a.0 of every image model (+GDN)
+    (3, 192, 5, 2, 37, 53, L.GDN_FORWARD, 1),    # N=192, odd image size
+    (1, 64, 5, 2, 32, 48, L.GDN_NONE, 2),        # 1-channel depth / IR input
+    (6, 128, 5, 2, 32, 64, L.GDN_NONE, 1),       # ssf2020 motion encoder input (two stacked frames)
+    (3, 64, 3, 1, 20, 28, L.GDN_NONE, 1),        # 3x3 stride-1 edge conv
+])
+def test_conv_tc_image_edge_input(cin, cout, k, s, h, w, gdn, B):
+    """Cin <= 8 convolution on the tensor cores through the zero-padded NHWC8 staging buffer."""
+    rs = np.random.RandomState(cin + cout + h)
+    x = bf16_round(rs.uniform(0, 1, (B, cin, h, w)).astype(np.float32))
+    wt = bf16_round((rs.standard_normal((cout, cin, k, k)) * (2.0 / np.sqrt(cin * k * k))).astype(np.float32))
+    b = rs.standard_normal(cout).astype(np.float32)
+    ref = oracle.conv2d(x, wt, b, stride=s)
+    beta_eff = gamma_bf16 = None
+    if gdn != L.GDN_NONE:
+        gw = {}
+        _gdn(rs, gw, "g", cout)
+        ref = oracle.gdn_forward(ref, gw["g.beta"], gw["g.gamma"])
+        beta_eff, _, gamma_bf16 = ops.gdn_reparam(torch.from_numpy(gw["g.beta"]).to(dev()), torch.from_numpy(gw["g.gamma"]).to(dev()),
+                                                  oracle.gdn_beta_bound(), oracle.GDN_GAMMA_BOUND, oracle.GDN_PEDESTAL, want_bf16=True)
+    d = ops.conv_desc(False, B, h, w, cin, cout, k, s, L.BF16, L.NHWC_PAD8, L.F32, L.NHWC, gdn=gdn)
+    xp = ops.pad_to_nhwc8(torch.from_numpy(x).to(dev()), d)
+    pad = k // 2
+    assert xp.shape[3] == 8 and torch.equal(xp[:, pad:pad + h, pad:pad + w, :cin].float().cpu(), torch.from_numpy(x).permute(0, 2, 3, 1))
+    assert float(xp[:, :pad].abs().max()) == 0 and float(xp[..., cin:].abs().max() if cin < 8 else 0) == 0
+    y = ops.conv_forward_tc(d, xp, ops.conv_pack_weights(d, torch.from_numpy(wt).to(dev())), torch.from_numpy(b).to(dev()), beta_eff, gamma_bf16)
+    torch.cuda.synchronize()
+    y = y.permute(0, 3, 1, 2).cpu().numpy()
+    assert y.shape == ref.shape
+    scale = float(np.abs(ref).max())
+    err = np.abs(y - ref)
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() < (2e-3 if gdn == L.GDN_NONE else 6e-3) * scale, f"max err {err.max():.4g} (scale {scale:.4g}) at {worst}; frac bad {(err > 6e-3 * scale).mean():.4f}"
+
+
+@pytest.mark.parametrize("cin,cout,k,h,w,B", [(128, 3, 5, 16, 24, 2), (192, 3, 5, 9, 7, 1), (64, 1, 5, 8, 16, 1), (128, 3, 3, 10, 12, 1)])
+def test_conv_tc_narrow_transposed_output(cin, cout, k, h, w, B):
+    """Reconstruction layer (deconv N -> 3, stride 2): the four output phases stacked along N, planar fp32 out."""
+    rs = np.random.RandomState(cin + cout + h)
+    x = bf16_round(rs.standard_normal((B, cin, h, w)).astype(np.float32))
+    wt = bf16_round((rs.standard_normal((cin, cout, k, k)) * (2.0 / np.sqrt(cin * k * k / 4))).astype(np.float32))
+    b = rs.standard_normal(cout).astype(np.float32)
+    ref = oracle.conv_transpose2d(x, wt, b, stride=2)
+    xin = torch.from_numpy(x).to(dev()).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    d = ops.conv_desc(True, B, h, w, cin, cout, k, 2, L.BF16, L.NHWC, L.F32, L.NCHW)
+    y = ops.conv_forward_tc(d, xin, ops.conv_pack_weights(d, torch.from_numpy(wt).to(dev())), torch.from_numpy(b).to(dev()))
+    torch.cuda.synchronize()
+    y = y.cpu().numpy()
+    assert y.shape == ref.shape
+    scale = float(np.abs(ref).max())
+    err = np.abs(y - ref)
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() < 2e-3 * scale, f"max err {err.max():.4g} (scale {scale:.4g}) at {worst}; frac bad {(err > 2e-3 * scale).mean():.4f}"
