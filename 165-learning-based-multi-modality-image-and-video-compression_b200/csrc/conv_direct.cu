@@ -224,7 +224,7 @@ static int validate_desc(const mmc_conv_desc *d, const char *name)
     MMC_CHECK_ARG(d->stride == 1 || d->stride == 2, "%s: stride %d not in {1,2}", name, d->stride);
     MMC_CHECK_ARG(d->in_dtype == MMC_F32 || d->in_dtype == MMC_BF16, "%s: bad in_dtype", name);
     MMC_CHECK_ARG(d->out_dtype == MMC_F32 || d->out_dtype == MMC_BF16, "%s: bad out_dtype", name);
-    MMC_CHECK_ARG(d->in_layout == MMC_NCHW || d->in_layout == MMC_NHWC, "%s: bad in_layout", name);
+    MMC_CHECK_ARG(d->in_layout == MMC_NCHW || d->in_layout == MMC_NHWC || d->in_layout == MMC_NHWC_PAD8, "%s: bad in_layout", name);
     MMC_CHECK_ARG(d->out_layout == MMC_NCHW || d->out_layout == MMC_NHWC, "%s: bad out_layout", name);
     MMC_CHECK_ARG(d->act >= 0 && d->act <= MMC_ACT_ABS, "%s: bad act", name);
     MMC_CHECK_ARG(d->gdn >= 0 && d->gdn <= MMC_GDN_INVERSE, "%s: bad gdn mode", name);
@@ -257,6 +257,7 @@ int mmc_conv_forward_direct(const mmc_conv_desc *d, const void *x, const float *
 {
     int rc = validate_desc(d, "mmc_conv_forward_direct");
     if (rc) return rc;
+    MMC_CHECK_ARG(d->in_layout != MMC_NHWC_PAD8, "mmc_conv_forward_direct: NHWC_PAD8 input is a tensor-core staging layout");
     MMC_CHECK_ARG(d->gdn == MMC_GDN_NONE || (beta_eff && gamma_eff), "mmc_conv_forward_direct: GDN needs beta/gamma");
     MMC_CHECK_ARG(d->out2_bf16 >= 0 && d->out2_bf16 <= 2, "mmc_conv_forward_direct: bad out2_bf16");
     MMC_CHECK_ARG(!d->out2_bf16 || y2, "mmc_conv_forward_direct: out2_bf16 set but y2 is NULL");
