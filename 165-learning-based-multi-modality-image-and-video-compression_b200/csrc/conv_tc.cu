@@ -46,7 +46,8 @@ struct Tap {
 enum TcMode {
     MODE_STD = 0,     // NHWC bf16 input, K block = (tap, 64-channel chunk)
     MODE_PAD8 = 1,    // image-edge conv (Cin <= 8): zero-padded NHWC8 input, K block = one kernel row (8 px x 8 ch)
-    MODE_PHASES = 2   // narrow transposed conv (Cout <= 4): the stride^2 output phases are stacked along N
+    MODE_SCATTER = 2  // narrow transposed conv as GEMM + col2im: N = k*k*Cout products per INPUT pixel, summed
+                      // into output pixels through shared memory (no tap loop, every activation is read once)
 };
 
 struct TcParams {
@@ -60,6 +61,9 @@ struct TcParams {
     int B, Gh, Gw;   // per-phase pixel grid
     int Ho, Wo;
     int TH, TW, tiles_y, tiles_x;
+    int step_y, step_x, off_y, off_x;   // tile origin = tile index * step - off (MODE_SCATTER tiles overlap by the halo)
+    int k, pad, halo_lo, halo_hi;       // MODE_SCATTER geometry
+    int spitch;                          // MODE_SCATTER: fp32 staging row pitch (floats)
     int Cout, Ntile, n_blocks;
     int kchunks;     // K boxes per tap (ceil(Cin / 64); 1 in MODE_PAD8)
     int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
@@ -193,8 +197,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams &P, int tile)
     int tx = r % P.tiles_x;  r /= P.tiles_x;
     int ty = r % P.tiles_y;
     t.b = r / P.tiles_y;
-    t.y0 = ty * P.TH;
-    t.x0 = tx * P.TW;
+    t.y0 = ty * P.step_y - P.off_y;
+    t.x0 = tx * P.step_x - P.off_x;
     t.n0 = nb * P.Ntile;
     return t;
 }
@@ -231,7 +235,7 @@ __device__ __forceinline__ void store16(const TcParams &P, int64_t off, const fl
     }
 }
 
-enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_PHASES = 2 };
+enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_SCATTER = 2 };
 
 template <int kEpi>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P)
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int stage_bytes = kABytes + P.Ntile * 128;
     uint8_t *sG = smem + (size_t)P.num_stages * stage_bytes;       // gamma: (Cout/64) tiles of [Cout][64] bf16
     uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * 2;               // x^2:   (Cout/64) tiles of [128][64] bf16
+    float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -348,26 +353,89 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
 
-            if (kEpi == EPI_PHASES) {
-                // ---- narrow transposed conv: column n = phase * Cout + c ; planar fp32 NCHW output ----
-                if (half == 0) {
-                    float v[16];
-                    tmem_ld16(acc_addr, v);
-                    tmem_ld_wait();
-                    if (valid) {
-                        const int s = P.out_stride;
-                        float *yo = (float *)P.y;
+            if (kEpi == EPI_SCATTER) {
+                // ---- GEMM + col2im: column n = (ky*k + kx)*Cout + c holds x[q] . w[:, c, ky, kx] for INPUT pixel q ----
+                {
+                    const int nch = P.Ntile >> 4;
+                    const int ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
+                    float *srow = sStage + (size_t)row * P.spitch;
+                    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                        float v[16];
+                        tmem_ld16(acc_addr + (ch << 4), v);
+                        tmem_ld_wait();
+                        float4 *dst = reinterpret_cast<float4 *>(srow + (ch << 4));
 #pragma unroll
-                        for (int n = 0; n < 16; ++n) {
-                            const int ph = n / P.Cout, c = n - ph * P.Cout;
-                            if (ph < s * s) {
-                                const int py = ph / s, px = ph - py * s;
-                                const int64_t o = (((int64_t)t.b * P.Cout + c) * P.Ho + (gy * s + py)) * P.Wo + (gx * s + px);
-                                yo[o] = act_tc(v[n] + bias_s[c], P.act);
+                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
+                // the accumulator is drained: hand the TMEM stage back before the gather pass
+                tc_fence_before();
+                mbar_arrive(&tmem_empty_bar[as]);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                {
+                    // Gather: one work item per (interior input-resolution pixel a, channel c) produces the s x s output
+                    // block (s*a + p); every product S[q][(ky,kx,c)] is consumed exactly once.
+                    const int s = P.out_stride, k = P.k;
+                    const int ih = P.TH - P.halo_lo - P.halo_hi, iw = P.TW - P.halo_lo - P.halo_hi;   // interior (input res)
+                    const int items = ih * iw * P.Cout;
+                    float *yo = (float *)P.y;
+                    for (int e = threadIdx.x - 64; e < items; e += kEpiThreads) {
+                        const int ax = e % iw;
+                        const int r2 = e / iw;
+                        const int ay = r2 % ih;
+                        const int c = r2 / ih;
+                        const int oy0 = (t.y0 + P.halo_lo + ay) * s, ox0 = (t.x0 + P.halo_lo + ax) * s;
+                        if (oy0 >= P.Ho || ox0 >= P.Wo) continue;
+                        const float b0 = bias_s[c];
+                        if (k == 5 && s == 2) {
+                            // pad = 2: ky has the parity of oy; input row = a + (py + 2 - ky) / 2  (all compile-time)
+                            float o00 = b0, o01 = b0, o10 = b0, o11 = b0;
+                            const float *base = sStage + (size_t)((P.halo_lo + ay) * P.TW + (P.halo_lo + ax)) * P.spitch + c;
+#pragma unroll
+                            for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+                                for (int kx = 0; kx < 5; ++kx) {
+                                    const int py = ky & 1, px = kx & 1;
+                                    const int dy = (py + 2 - ky) / 2, dx = (px + 2 - kx) / 2;
+                                    const float v = base[(dy * P.TW + dx) * P.spitch + (ky * 5 + kx) * P.Cout];
+                                    if (py == 0 && px == 0) o00 += v;
+                                    else if (py == 0) o01 += v;
+                                    else if (px == 0) o10 += v;
+                                    else o11 += v;
+                                }
                             }
+                            float *row0 = yo + (((int64_t)t.b * P.Cout + c) * P.Ho + oy0) * P.Wo + ox0;
+                            const bool two_x = ox0 + 1 < P.Wo, two_y = oy0 + 1 < P.Ho;
+                            if (two_x && ((P.Wo & 1) == 0)) {
+                                *reinterpret_cast<float2 *>(row0) = make_float2(act_tc(o00, P.act), act_tc(o01, P.act));
+                                if (two_y) *reinterpret_cast<float2 *>(row0 + P.Wo) = make_float2(act_tc(o10, P.act), act_tc(o11, P.act));
+                            } else {
+                                row0[0] = act_tc(o00, P.act);
+                                if (two_x) row0[1] = act_tc(o01, P.act);
+                                if (two_y) { row0[P.Wo] = act_tc(o10, P.act); if (two_x) row0[P.Wo + 1] = act_tc(o11, P.act); }
+                            }
+                        } else {
+                            for (int py = 0; py < s; ++py)
+                                for (int px = 0; px < s; ++px) {
+                                    const int oy = oy0 + py, ox = ox0 + px;
+                                    if (oy >= P.Ho || ox >= P.Wo) continue;
+                                    float acc = b0;
+                                    for (int ky = (oy + P.pad) % s; ky < k; ky += s) {   // ky = oy + pad - s*iy
+                                        const int iyl = (oy + P.pad - ky) / s - t.y0;
+                                        if (iyl < 0 || iyl >= P.TH) continue;
+                                        for (int kx = (ox + P.pad) % s; kx < k; kx += s) {
+                                            const int ixl = (ox + P.pad - kx) / s - t.x0;
+                                            if (ixl < 0 || ixl >= P.TW) continue;
+                                            acc += sStage[(size_t)(iyl * P.TW + ixl) * P.spitch + (ky * k + kx) * P.Cout + c];
+                                        }
+                                    }
+                                    yo[(((int64_t)t.b * P.Cout + c) * P.Ho + oy) * P.Wo + ox] = act_tc(acc, P.act);
+                                }
                         }
                     }
                 }
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // staging buffer free for the next tile
+                continue;
             } else {
                 const int py = t.phase / P.out_stride, px = t.phase - py * P.out_stride;
                 const int oy = gy * P.out_stride + py, ox = gx * P.out_stride + px;
@@ -473,13 +541,14 @@ struct Plan {
     int mode;
     int ntaps;
     Tap taps[kMaxTaps];
-    int tap_ky[kMaxTaps], tap_kx[kMaxTaps];   // MODE_STD: kernel position; MODE_PAD8: ky only; MODE_PHASES: (dy, dx)
+    int tap_ky[kMaxTaps], tap_kx[kMaxTaps];   // MODE_STD: kernel position; MODE_PAD8: ky only
     int phase_begin[5], n_phases;
     int a_sx, a_sy, out_stride, Gh, Gw;
     int kchunks, ksteps;
     int Ntile, n_blocks;
     int wrows, wcols;                          // packed weight matrix: [ntaps * wrows][wcols] bf16
     int Ho, Wo, Hp, Wp;
+    int halo_lo, halo_hi;                      // MODE_SCATTER: input rows/cols around an output pair that contribute to it
 };
 
 static void pad8_extent(const mmc_conv_desc *d, int Ho, int Wo, int *Hp, int *Wp)
@@ -517,27 +586,20 @@ static int make_plan(const mmc_conv_desc *d, Plan &pl, const char *name)
         pl.phase_begin[0] = 0; pl.phase_begin[1] = pl.ntaps;
         pl.wrows = d->Cout; pl.wcols = 64;
         pad8_extent(d, pl.Ho, pl.Wo, &pl.Hp, &pl.Wp);
-    } else if (d->transposed && d->Cout <= 4 && s == 2) {
-        // ---- narrow transposed conv: all stride^2 phases share the input patch; stack them along N ----
+    } else if (d->transposed && s == 2 && k >= 3 && k * k * d->Cout <= 256 && d->Cout <= 4) {
+        // ---- narrow transposed conv as GEMM + col2im: P[q][(ky,kx,c)] = x[q] . w[:, c, ky, kx] ----
         MMC_UNSUPPORTED(d->Cin % 8 != 0 || d->Cin < 32, "%s: tensor-core path needs Cin %% 8 == 0 and Cin >= 32 (got %d)", name, d->Cin);
-        pl.mode = MODE_PHASES;
+        pl.mode = MODE_SCATTER;
         pl.n_phases = 1; pl.a_sx = pl.a_sy = 1; pl.out_stride = s; pl.Gh = d->H; pl.Gw = d->W;
         pl.kchunks = (d->Cin + 63) / 64; pl.ksteps = 4;
-        for (int dy = -2; dy <= 2; ++dy)
-            for (int dx = -2; dx <= 2; ++dx) {
-                bool used = false;   // oy = s*qy + py, iy = qy + dy  =>  ky = py + pad - s*dy
-                for (int py = 0; py < s; ++py)
-                    for (int px = 0; px < s; ++px) {
-                        int ky = py + pad - s * dy, kx = px + pad - s * dx;
-                        used |= (ky >= 0 && ky < k && kx >= 0 && kx < k);
-                    }
-                if (!used) continue;
-                pl.taps[pl.ntaps] = Tap{(int16_t)dy, (int16_t)dx, pl.ntaps * 16};
-                pl.tap_ky[pl.ntaps] = dy; pl.tap_kx[pl.ntaps] = dx;
-                ++pl.ntaps;
-            }
-        pl.phase_begin[0] = 0; pl.phase_begin[1] = pl.ntaps;
-        pl.wrows = 16; pl.wcols = d->Cin;
+        pl.taps[0] = Tap{0, 0, 0};
+        pl.ntaps = 1;
+        pl.phase_begin[0] = 0; pl.phase_begin[1] = 1;
+        pl.wrows = (k * k * d->Cout + 15) & ~15; pl.wcols = d->Cin;
+        // output rows s*a .. s*a+s-1 receive input rows a - halo_lo .. a + halo_hi   (ky = oy + pad - s*iy in [0, k))
+        pl.halo_lo = -((pad - k + 1) / s);          // = ceil((k - 1 - pad) / s) for k - 1 >= pad
+        if ((k - 1 - pad) % s) pl.halo_lo = (k - 1 - pad + s - 1) / s;
+        pl.halo_hi = (s - 1 + pad) / s;
     } else {
         MMC_UNSUPPORTED(d->Cin % 8 != 0 || d->Cin < 32, "%s: tensor-core path needs Cin %% 8 == 0 and Cin >= 32 (got %d); use the direct kernel", name, d->Cin);
         MMC_UNSUPPORTED(d->Cout % 16 != 0, "%s: tensor-core path needs Cout %% 16 == 0 (got %d); use the direct kernel", name, d->Cout);
@@ -585,7 +647,7 @@ struct PackParams {
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, PackParams q, __nv_bfloat16 *__restrict__ out)
 {
-    const int kk = q.k * q.k, pad = q.k / 2;
+    const int kk = q.k * q.k;
     int64_t n = (int64_t)q.ntaps * q.wrows * q.wcols;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -601,13 +663,9 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
         } else if (q.mode == MODE_PAD8) {
             int kx = col >> 3, c = col & 7, ky = q.ta[tap];
             if (kx < q.k && c < q.Cin) v = __ldg(w + (((int64_t)row * q.Cin + c) * kk + ky * q.k + kx));
-        } else {
-            int ph = row / q.Cout, c = row - ph * q.Cout;
-            if (ph < q.stride * q.stride) {
-                int py = ph / q.stride, px = ph - py * q.stride;
-                int ky = py + pad - q.stride * q.ta[tap], kx = px + pad - q.stride * q.tb[tap];
-                if (ky >= 0 && ky < q.k && kx >= 0 && kx < q.k) v = __ldg(w + (((int64_t)col * q.Cout + c) * kk + ky * q.k + kx));
-            }
+        } else if (q.mode == MODE_SCATTER) {
+            int kpos = row / q.Cout, c = row - kpos * q.Cout;   // row n = (ky*k + kx)*Cout + c
+            if (kpos < kk) v = __ldg(w + (((int64_t)col * q.Cout + c) * kk + kpos));
         }
         out[i] = __float2bfloat16_rn(v);
     }
@@ -768,7 +826,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     MMC_CHECK_ARG(d->out2_bf16 >= 0 && d->out2_bf16 <= 2, "%s: bad out2_bf16", name);
     MMC_CHECK_ARG(d->gdn == MMC_GDN_NONE || (beta_eff && gamma_eff_bf16), "%s: GDN needs beta/gamma", name);
     MMC_CHECK_ARG(!d->out2_bf16 || y2, "%s: out2_bf16 set but y2 is NULL", name);
-    if (pl.mode == MODE_PHASES) {
+    if (pl.mode == MODE_SCATTER) {
         MMC_CHECK_ARG(d->out_layout == MMC_NCHW && d->out_dtype == MMC_F32 && d->gdn == MMC_GDN_NONE && !d->out2_bf16,
                       "%s: narrow transposed conv writes planar fp32 NCHW without GDN / secondary output", name);
     } else {
@@ -792,13 +850,24 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     for (int i = 0; i < 5; ++i) P.phase_begin[i] = pl.phase_begin[i];
 
     // ---- tiling ----
-    if (pl.mode == MODE_PHASES) P.Ntile = 16;
+    P.k = d->k; P.pad = d->k / 2; P.halo_lo = pl.halo_lo; P.halo_hi = pl.halo_hi;
+    if (pl.mode == MODE_SCATTER) P.Ntile = pl.wrows;
     else P.Ntile = (d->gdn != MMC_GDN_NONE) ? d->Cout : pick_ntile(d->Cout);
     MMC_UNSUPPORTED(P.Ntile == 0 || P.Ntile > 256, "%s: no valid N tile for Cout=%d", name, d->Cout);
-    P.n_blocks = (pl.mode == MODE_PHASES) ? 1 : d->Cout / P.Ntile;
-    pick_tile(P.Gh, P.Gw, pl.mode == MODE_PAD8 ? 1 : P.a_sx, P.a_sy, &P.TH, &P.TW);
-    P.tiles_y = (P.Gh + P.TH - 1) / P.TH;
-    P.tiles_x = (P.Gw + P.TW - 1) / P.TW;
+    P.n_blocks = (pl.mode == MODE_SCATTER) ? 1 : d->Cout / P.Ntile;
+    if (pl.mode == MODE_SCATTER) {
+        // overlapping input patches: consecutive tiles advance by the patch size minus the halo
+        P.TH = 8; P.TW = 16;
+        P.step_y = P.TH - pl.halo_lo - pl.halo_hi; P.step_x = P.TW - pl.halo_lo - pl.halo_hi;
+        P.off_y = P.off_x = pl.halo_lo;
+        P.spitch = P.Ntile + 4;
+        if (((P.spitch / 4) & 1) == 0) P.spitch += 4;   // pitch/4 odd: conflict-free 16-byte row-strided stores
+    } else {
+        pick_tile(P.Gh, P.Gw, pl.mode == MODE_PAD8 ? 1 : P.a_sx, P.a_sy, &P.TH, &P.TW);
+        P.step_y = P.TH; P.step_x = P.TW; P.off_y = P.off_x = 0;
+    }
+    P.tiles_y = (P.Gh + P.step_y - 1) / P.step_y;
+    P.tiles_x = (P.Gw + P.step_x - 1) / P.step_x;
     int64_t tpp = (int64_t)d->B * P.tiles_y * P.tiles_x * P.n_blocks;
     MMC_CHECK_ARG(tpp * P.n_phases < (1ll << 31), "%s: too many tiles", name);
     P.tiles_per_phase = (int)tpp;
@@ -811,6 +880,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     const size_t stage_bytes = kABytes + (size_t)P.Ntile * 128;
     size_t fixed = 1024;  // alignment slack
     if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (size_t)(d->Cout / 64) * kABytes;
+    if (pl.mode == MODE_SCATTER) fixed += (size_t)128 * P.spitch * sizeof(float);
 
     // ---- tensor maps ----
     if (pl.mode == MODE_PAD8) {
@@ -847,7 +917,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl.mode == MODE_PHASES) return launch_tc<EPI_PHASES>(P, fixed, stage_bytes, st, name);
+    if (pl.mode == MODE_SCATTER) return launch_tc<EPI_SCATTER>(P, fixed, stage_bytes, st, name);
     if (d->gdn != MMC_GDN_NONE) return launch_tc<EPI_GDN>(P, fixed, stage_bytes, st, name);
     return launch_tc<EPI_PLAIN>(P, fixed, stage_bytes, st, name);
 }

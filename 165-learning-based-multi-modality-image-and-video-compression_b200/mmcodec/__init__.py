@@ -8,7 +8,8 @@
 
 All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
 """
-from . import _lib, entropy_models, layers, models, ops, transforms  # noqa: F401
+from . import _lib, entropy_models, host_pipeline, layers, models, ops, transforms  # noqa: F401
+from .host_pipeline import HostPipeline  # noqa: F401
 from ._lib import MmcodecError, build  # noqa: F401
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional  # noqa: F401
 from .layers import GDN, LowerBound, NonNegativeParametrizer, conv, deconv  # noqa: F401

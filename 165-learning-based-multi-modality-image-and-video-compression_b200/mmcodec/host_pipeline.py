@@ -1,0 +1,104 @@
+"""Host-buffer entry point: ``CompressionModel.forward`` for callers whose images and results live in
+(pinned) host memory, which is how the reference's evaluation loop uses the model
+(compressai/utils/eval_model/__main__t.py:149-211: load image -> ``.to(device)`` -> forward -> metrics
+on the host).
+
+The batch is cut into micro-batches; the host->device copy of micro-batch i+1, the kernels of
+micro-batch i and the device->host copy of the results of micro-batch i-1 run concurrently on three
+CUDA streams (PCIe is full duplex, the copy engines are independent of the SMs).  Images are
+independent, so the results are bit-identical to one big forward.  On return the caller's current
+stream is ordered after every copy: ``torch.cuda.current_stream().synchronize()`` (or an event
+recorded on it) makes the host buffers valid.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+from torch import Tensor
+
+
+def _pinned_like(shape, channels_last: bool) -> Tensor:
+    """Pinned fp32 host tensor of logical `shape`; channels-last memory when the device tensor is, so that the
+    device->host copy is one flat memcpy per micro-batch."""
+    if channels_last and len(shape) == 4:
+        b, c, h, w = shape
+        return torch.empty((b, h, w, c), dtype=torch.float32).pin_memory().permute(0, 3, 1, 2)
+    return torch.empty(shape, dtype=torch.float32).pin_memory()
+
+
+class HostPipeline:
+    def __init__(self, net, micro_batch: int = 16, device: Optional[torch.device] = None):
+        self.net = net
+        self.micro_batch = int(micro_batch)
+        self.device = device or next(net.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("HostPipeline needs the model on a CUDA device (no CPU path)")
+        self.s_h2d = torch.cuda.Stream(self.device)
+        self.s_run = torch.cuda.Stream(self.device)
+        self.s_d2h = torch.cuda.Stream(self.device)
+        self._slots = None
+        self._out: Optional[Dict[str, Tensor]] = None
+
+    def _buffers(self, x_host: Tensor):
+        mb = min(self.micro_batch, x_host.shape[0])
+        shape = (mb,) + tuple(x_host.shape[1:])
+        if self._slots is None or tuple(self._slots[0].shape) != shape:
+            self._slots = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+        return self._slots, mb
+
+    def __call__(self, x_host: Tensor, out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+        """x_host: (B, C, H, W) fp32 host tensor (pinned for asynchronous copies).  Returns / fills
+        {"x_hat": (B,C,H,W), "likelihoods": {name: (B,C',H',W')}} pinned host tensors."""
+        if x_host.is_cuda:
+            raise ValueError("HostPipeline takes host tensors; call the model directly for device tensors")
+        B = x_host.shape[0]
+        slots, mb = self._buffers(x_host)
+        caller = torch.cuda.current_stream(self.device)
+        start = torch.cuda.Event()
+        start.record(caller)
+        for s in (self.s_h2d, self.s_run, self.s_d2h):
+            s.wait_event(start)
+        slot_free = [None, None]      # event: kernels that read slot k have finished
+        last_d2h = None
+        result = out if out is not None else self._out
+        if result is not None and result["x_hat"].shape[0] != B:
+            result = None
+        i = 0
+        for lo in range(0, B, mb):
+            hi = min(lo + mb, B)
+            k = i & 1
+            with torch.cuda.stream(self.s_h2d):
+                if slot_free[k] is not None:
+                    self.s_h2d.wait_event(slot_free[k])
+                xd = slots[k][: hi - lo]
+                xd.copy_(x_host[lo:hi], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.s_h2d)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(ev_in)
+                with torch.no_grad():
+                    o = self.net(xd)
+                ev_run = torch.cuda.Event()
+                ev_run.record(self.s_run)
+                slot_free[k] = ev_run
+            if result is None:
+                # first call: allocate pinned result buffers with the device tensors' memory formats
+                result = {"x_hat": _pinned_like((B,) + tuple(o["x_hat"].shape[1:]), False),
+                          "likelihoods": {n: _pinned_like((B,) + tuple(t.shape[1:]), not t.is_contiguous())
+                                          for n, t in o["likelihoods"].items()}}
+                if out is None:
+                    self._out = result
+            with torch.cuda.stream(self.s_d2h):
+                self.s_d2h.wait_event(ev_run)
+                result["x_hat"][lo:hi].copy_(o["x_hat"], non_blocking=True)
+                o["x_hat"].record_stream(self.s_d2h)
+                for n, t in o["likelihoods"].items():
+                    result["likelihoods"][n][lo:hi].copy_(t, non_blocking=True)
+                    t.record_stream(self.s_d2h)
+                last_d2h = torch.cuda.Event()
+                last_d2h.record(self.s_d2h)
+            i += 1
+        if last_d2h is not None:
+            caller.wait_event(last_d2h)
+        return result

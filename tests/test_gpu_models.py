@@ -192,3 +192,21 @@ def test_full_size_properties():
     med = eb._get_medians().detach().reshape(1, -1, 1, 1)
     z_hat = eb.dequantize(c["z_symbols"], med)
     assert torch.equal(eb.quantize(z_hat, "symbols", med), c["z_symbols"])
+
+
+def test_host_pipeline_matches_device_forward():
+    """Host-buffer API: pipelined micro-batches give exactly the results of one device forward."""
+    net, _ = load(mmcodec.ScaleHyperprior, "hyperprior", 128, 192)
+    x = torch.from_numpy(make_image(5, 64, 128, seed=11))
+    with torch.no_grad():
+        ref = net(x.to(dev()))
+    pipe = mmcodec.HostPipeline(net, micro_batch=2)
+    for _ in range(2):   # second call reuses the pinned result buffers
+        out = pipe(x.pin_memory())
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(out["x_hat"], ref["x_hat"].cpu())
+        for k in ref["likelihoods"]:
+            assert out["likelihoods"][k].shape == ref["likelihoods"][k].shape
+            assert torch.equal(out["likelihoods"][k], ref["likelihoods"][k].cpu())
+    with pytest.raises(ValueError):
+        pipe(x.to(dev()))
