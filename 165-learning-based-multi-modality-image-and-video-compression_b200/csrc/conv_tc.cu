@@ -68,6 +68,7 @@ struct TcParams {
     int kchunks;     // K boxes per tap (ceil(Cin / 64); 1 in MODE_PAD8)
     int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
     int num_stages, acc_stages;
+    int b_resident;  // whole packed weight matrix stays in shared memory (small layers); K blocks stream A only
     int act, gdn, out_f32, out2;
     int gdn_chunk;
     int tiles_per_phase, total_tiles;
@@ -235,6 +236,100 @@ __device__ __forceinline__ void store16(const TcParams &P, int64_t off, const fl
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused GDN / IGDN epilogue (compressai/layers/gdn.py:77-92) for one 128-pixel x C-channel tile.
+// Each of the 256 epilogue threads owns one pixel row and NCH 16-column chunks (C/2 channels); the
+// biased activations stay in registers across the tensor-core norm contraction.
+//   pass 1: x = acc + bias (all TMEM loads issued before one wait); x^2 -> bf16 swizzled K-major smem tile
+//   MMA   : norm[128 x chunk] = X2[128 x C] * gamma[chunk rows]^T      (one thread issues, tcgen05.commit -> mbarrier)
+//   pass 2: y = x * rsqrt(beta + norm)   (IGDN: x * sqrt(n) = x * n * rsqrt(n)); bf16 / fp32 NHWC stores
+// ---------------------------------------------------------------------------------------------
+struct GdnCtx {
+    const TcParams &P;
+    uint8_t *sA2, *sG;
+    uint64_t *gdn_bar, *gload_bar;
+    uint32_t tmem_base, acc_addr, lane_addr, norm_col;
+    int row, half;
+    bool valid;
+    int64_t pix_off;
+    int it;
+};
+
+template <int NCH, int G>
+__device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_s, const float *beta_s, uint32_t &gdn_phase)
+{
+    const TcParams &P = g.P;
+    constexpr int per = NCH / G;               // chunks of each norm group owned by this thread (its half of the group)
+    constexpr int gch = 2 * per;               // 16-column chunks per norm group (gdn_chunk / 16)
+    float x[NCH][16];
+    // chunk id of my j-th chunk: group (j / per), position (j % per) within my half of the group
+    auto chunk_of = [&](int j) { return (j / per) * gch + g.half * per + (j % per); };
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) tmem_ld16(g.acc_addr + (uint32_t)(chunk_of(j) << 4), x[j]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int c0 = chunk_of(j) << 4;
+        float bs[16];
+        load16f(bias_s + c0, bs);
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[j][i] += bs[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(x[j][2 * i] * x[j][2 * i], x[j][2 * i + 1] * x[j][2 * i + 1]);
+        uint8_t *tile_base = g.sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)g.row * 128;
+        const int j0 = (c0 & 63) >> 3;   // 16-byte chunk index inside the 128-byte row
+        *reinterpret_cast<uint4 *>(tile_base + (((j0) ^ (g.row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4 *>(tile_base + (((j0 + 1) ^ (g.row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+    tc_fence_before();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+    for (int grp = 0; grp < G; ++grp) {
+        const int g0 = grp * gch * 16;
+        if (threadIdx.x == 64) {
+            if (g.it == 0 && grp == 0) mbar_wait(g.gload_bar, 0);
+            tc_fence_after();
+            const uint32_t idesc = make_idesc(P.gdn_chunk);
+            for (int kc = 0; kc < P.Cout / 64; ++kc) {
+                const uint64_t adesc = make_desc(smem_u32(g.sA2 + (size_t)kc * kABytes));
+                const uint64_t bdesc = make_desc(smem_u32(g.sG + (size_t)kc * P.Cout * 128 + (size_t)g0 * 128));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma(g.tmem_base + g.norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+            }
+            tc_commit(g.gdn_bar);
+        }
+        mbar_wait(g.gdn_bar, gdn_phase);
+        gdn_phase ^= 1;
+        tc_fence_after();
+        // my chunks of this group: j in [grp*per, (grp+1)*per)
+        float nrm[per][16];
+#pragma unroll
+        for (int jj = 0; jj < per; ++jj)
+            tmem_ld16(g.tmem_base + g.lane_addr + g.norm_col + (uint32_t)((chunk_of(grp * per + jj) << 4) - g0), nrm[jj]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < per; ++jj) {
+            const int j = grp * per + jj;
+            const int c0 = chunk_of(j) << 4;
+            float bt[16], y[16];
+            load16f(beta_s + c0, bt);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float n = bt[i] + nrm[jj][i];
+                const float r = rsqrtf(n);
+                y[i] = (P.gdn == MMC_GDN_INVERSE) ? x[j][i] * (n * r) : x[j][i] * r;
+            }
+            if (g.valid) store16(P, g.pix_off + c0, y);
+        }
+        // every epilogue thread is done with the norm columns (and, after the last group, with sA2)
+        tc_fence_before();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+}
+
 enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_SCATTER = 2 };
 
 template <int kEpi>
@@ -242,16 +337,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-    __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2], gdn_bar, gload_bar;
+    __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2], gdn_bar, gload_bar, bres_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[kMaxCout];
     __shared__ __align__(16) float beta_s[256];
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int stage_bytes = kABytes + P.Ntile * 128;
+    const int b_tile_bytes = P.Ntile * 128;
+    const int stage_bytes = kABytes + (P.b_resident ? 0 : b_tile_bytes);
     uint8_t *sG = smem + (size_t)P.num_stages * stage_bytes;       // gamma: (Cout/64) tiles of [Cout][64] bf16
     uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * 2;               // x^2:   (Cout/64) tiles of [128][64] bf16
     float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
+    // resident weights (b_resident): one [Ntile][64] bf16 tile per K block, after the GDN / staging region
+    const size_t epi_bytes = (kEpi == EPI_GDN) ? (size_t)P.Cout * P.Cout * 2 + (size_t)(P.Cout / 64) * kABytes
+                           : (kEpi == EPI_SCATTER) ? (((size_t)128 * P.spitch * sizeof(float) + 1023) & ~(size_t)1023) : 0;
+    uint8_t *sBres = sG + epi_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -260,6 +360,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiThreads); }
         mbar_init(&gdn_bar, 1);
         mbar_init(&gload_bar, 1);
+        mbar_init(&bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         prefetch_tmap(&P.tmA);
         prefetch_tmap(&P.tmB);
@@ -286,6 +387,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 for (int kc = 0; kc < P.Cout / 64; ++kc)
                     tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * P.Cout * 128, kc * 64, 0);
             }
+            if (P.b_resident) {
+                const int nkb = P.phase_begin[1] * P.kchunks;
+                mbar_expect_tx(&bres_bar, (uint32_t)(nkb * b_tile_bytes));
+                for (int tp = 0; tp < P.phase_begin[1]; ++tp)
+                    for (int kc = 0; kc < P.kchunks; ++kc)
+                        tma_load_2d(&P.tmB, &bres_bar, sBres + (size_t)(tp * P.kchunks + kc) * b_tile_bytes, kc * 64, P.taps[tp].brow);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -298,7 +406,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                         uint8_t *a = smem + (size_t)stage * stage_bytes;
                         mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
                         tma_load_4d(&P.tmA, &full_bar[stage], a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
-                        tma_load_2d(&P.tmB, &full_bar[stage], a + kABytes, kc * 64, tap.brow + t.n0);
+                        if (!P.b_resident) tma_load_2d(&P.tmB, &full_bar[stage], a + kABytes, kc * 64, tap.brow + t.n0);
                         if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -311,6 +419,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            if (P.b_resident) mbar_wait(&bres_bar, 0);
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
                 TileCoord t = decode_tile(P, tile);
                 const int as = (P.acc_stages == 2) ? (it & 1) : 0;
@@ -323,7 +432,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = make_desc(a_addr), bdesc = make_desc(a_addr + kABytes);
+                    const uint64_t adesc = make_desc(a_addr);
+                    const uint64_t bdesc = make_desc(P.b_resident ? smem_u32(sBres + (size_t)kb * b_tile_bytes) : a_addr + kABytes);
                     for (int k = 0; k < P.ksteps; ++k)   // K=16 per step: +32 B inside the 128-byte swizzle atom
                         tc_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                     tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
@@ -444,81 +554,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 const int ch_lo = half ? (nch + 1) / 2 : 0;
                 const int ch_hi = half ? nch : (nch + 1) / 2;
                 if (kEpi == EPI_PLAIN) {
-                    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    // two TMEM loads in flight per wait
+                    for (int ch = ch_lo; ch < ch_hi; ch += 2) {
                         const int c0 = ch << 4;
-                        float v[16], bs[16];
+                        const bool two = ch + 1 < ch_hi;
+                        float v[16], w[16], bs[16];
                         tmem_ld16(acc_addr + c0, v);
+                        if (two) tmem_ld16(acc_addr + c0 + 16, w);
                         load16f(bias_s + t.n0 + c0, bs);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = act_tc(v[i] + bs[i], P.act);
                         if (valid) store16(P, pix_off + c0, v);
+                        if (two) {
+                            load16f(bias_s + t.n0 + c0 + 16, bs);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) w[i] = act_tc(w[i] + bs[i], P.act);
+                            if (valid) store16(P, pix_off + c0 + 16, w);
+                        }
                     }
                 } else {
-                    // ---- pass 1: x = acc + bias ; x^2 (bf16) -> swizzled K-major tile in shared memory ----
-                    for (int ch = ch_lo; ch < ch_hi; ++ch) {
-                        const int c0 = ch << 4;
-                        float v[16], bs[16];
-                        tmem_ld16(acc_addr + c0, v);
-                        load16f(bias_s + c0, bs);
-                        tmem_ld_wait();
-                        uint32_t pk[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            float a = v[2 * i] + bs[2 * i], b = v[2 * i + 1] + bs[2 * i + 1];
-                            pk[i] = pack_bf16(a * a, b * b);
-                        }
-                        uint8_t *tile_base = sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)row * 128;
-                        const int j0 = (c0 & 63) >> 3;   // 16-byte chunk index inside the 128-byte row
-                        *reinterpret_cast<uint4 *>(tile_base + (((j0) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4 *>(tile_base + (((j0 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-                    tc_fence_before();
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    for (int g0 = 0; g0 < P.Cout; g0 += P.gdn_chunk) {
-                        if (threadIdx.x == 64) {
-                            // ---- norm[128 x chunk] = X2[128 x C] * gamma[g0:g0+chunk, :]^T on the tensor cores ----
-                            if (it == 0 && g0 == 0) mbar_wait(&gload_bar, 0);
-                            tc_fence_after();
-                            const uint32_t idesc = make_idesc(P.gdn_chunk);
-                            for (int kc = 0; kc < P.Cout / 64; ++kc) {
-                                const uint64_t adesc = make_desc(smem_u32(sA2 + (size_t)kc * kABytes));
-                                const uint64_t bdesc = make_desc(smem_u32(sG + (size_t)kc * P.Cout * 128 + (size_t)g0 * 128));
-#pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    tc_mma(tmem_base + norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
-                            }
-                            tc_commit(&gdn_bar);
-                        }
-                        mbar_wait(&gdn_bar, gdn_phase);
-                        gdn_phase ^= 1;
-                        tc_fence_after();
-                        // ---- pass 2: y = x * rsqrt(beta + norm)  (IGDN: x * sqrt(n) = x * n * rsqrt(n)) ----
-                        const int gch = P.gdn_chunk >> 4;
-                        const int g_lo = (g0 >> 4) + (half ? (gch + 1) / 2 : 0);
-                        const int g_hi = (g0 >> 4) + (half ? gch : (gch + 1) / 2);
-                        for (int ch = g_lo; ch < g_hi; ++ch) {
-                            const int c0 = ch << 4;
-                            float v[16], nrm[16], bs[16], bt[16];
-                            tmem_ld16(acc_addr + c0, v);
-                            tmem_ld16(tmem_base + lane_addr + norm_col + (uint32_t)(c0 - g0), nrm);
-                            load16f(bias_s + c0, bs);
-                            load16f(beta_s + c0, bt);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                const float x = v[i] + bs[i];
-                                const float n = bt[i] + nrm[i];
-                                const float r = rsqrtf(n);
-                                v[i] = (P.gdn == MMC_GDN_INVERSE) ? x * (n * r) : x * r;
-                            }
-                            if (valid) store16(P, pix_off + c0, v);
-                        }
-                        // every epilogue thread is done with the norm columns (and, on the last chunk, with sA2)
-                        tc_fence_before();
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
-                    }
+                    GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it};
+                    // (chunks per thread, norm groups): C=128 -> one 128-column norm pass; C=192 -> two 96-column passes
+                    if (P.Cout == 128) epilogue_gdn<4, 1>(g, bias_s, beta_s, gdn_phase);
+                    else if (P.Cout == 192) epilogue_gdn<6, 2>(g, bias_s, beta_s, gdn_phase);
+                    else epilogue_gdn<2, 1>(g, bias_s, beta_s, gdn_phase);
                 }
             }
             tc_fence_before();
@@ -671,23 +731,41 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
     }
 }
 
-// NCHW fp32 image -> zero-padded NHWC bf16 with 8 channels per pixel ([B][Hp][Wp][8], 16 B per pixel)
+// NCHW fp32 image -> zero-padded NHWC bf16 with 8 channels per pixel ([B][Hp][Wp][8], 16 B per pixel).
+// One thread converts 4 horizontally adjacent pixels: up to 8 independent plane loads in flight, 64 B stored.
 __global__ void __launch_bounds__(256) pad8_kernel(const float *__restrict__ x, int C, int H, int W, int pad, int Hp, int Wp,
-                                                  int64_t npix, uint4 *__restrict__ out)
+                                                  int64_t nquads, uint4 *__restrict__ out)
 {
+    const int qpr = (Wp + 3) >> 2;   // quads per padded row
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += stride) {
-        int px = (int)(i % Wp);
-        int64_t r = i / Wp;
-        int py = (int)(r % Hp);
-        int64_t b = r / Hp;
-        int iy = py - pad, ix = px - pad;
-        float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
-            const float *src = x + (b * C * H + iy) * (int64_t)W + ix;
-            for (int c = 0; c < C; ++c) v[c] = __ldg(src + (int64_t)c * H * W);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
+        const int qx = (int)(i % qpr);
+        int64_t r = i / qpr;
+        const int py = (int)(r % Hp);
+        const int64_t b = r / Hp;
+        const int iy = py - pad;
+        float v[4][8];
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[p][c] = 0.0f;
+        if (iy >= 0 && iy < H) {
+            const float *row = x + (b * C * H + iy) * (int64_t)W;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if (c >= C) break;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int ix = qx * 4 + p - pad;
+                    if (ix >= 0 && ix < W) v[p][c] = __ldg(row + (int64_t)c * H * W + ix);
+                }
+            }
         }
-        out[i] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        uint4 *dst = out + (b * Hp + py) * (int64_t)Wp + qx * 4;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (qx * 4 + p < Wp)
+                dst[p] = make_uint4(pack_bf16(v[p][0], v[p][1]), pack_bf16(v[p][2], v[p][3]), pack_bf16(v[p][4], v[p][5]), pack_bf16(v[p][6], v[p][7]));
     }
 }
 
@@ -789,8 +867,8 @@ int mmc_pad_nchw_to_nhwc8(const float *x, int64_t B, int C, int H, int W, int pa
                   "mmc_pad_nchw_to_nhwc8: bad shape");
     if (B == 0) return MMC_OK;
     MMC_CHECK_ARG(x && out && aligned16(out), "mmc_pad_nchw_to_nhwc8: NULL or unaligned buffer");
-    int64_t npix = B * Hp * Wp;
-    pad8_kernel<<<elementwise_grid(npix, 256), 256, 0, (cudaStream_t)stream>>>(x, C, H, W, pad, Hp, Wp, npix, (uint4 *)out);
+    int64_t nquads = B * Hp * ((Wp + 3) / 4);
+    pad8_kernel<<<elementwise_grid(nquads, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, C, H, W, pad, Hp, Wp, nquads, (uint4 *)out);
     MMC_CHECK_LAUNCH("mmc_pad_nchw_to_nhwc8");
     return MMC_OK;
 }
@@ -877,10 +955,15 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     P.acc_stages = (2 * P.Ntile + P.gdn_chunk <= 512) ? 2 : 1;
     MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
 
-    const size_t stage_bytes = kABytes + (size_t)P.Ntile * 128;
     size_t fixed = 1024;  // alignment slack
     if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (size_t)(d->Cout / 64) * kABytes;
-    if (pl.mode == MODE_SCATTER) fixed += (size_t)128 * P.spitch * sizeof(float);
+    if (pl.mode == MODE_SCATTER) fixed += (((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023;
+    // Small layers (image-edge conv, reconstruction deconv): keep every weight tile resident in shared memory so that
+    // the K blocks stream activations only (halves the L2 -> SM traffic of those layers).
+    const size_t b_total = (size_t)pl.ntaps * pl.kchunks * P.Ntile * 128;
+    P.b_resident = (P.n_blocks == 1 && P.n_phases == 1 && b_total <= 96 * 1024 && fixed + b_total + 4 * kABytes <= 200 * 1024) ? 1 : 0;
+    if (P.b_resident) fixed += b_total;
+    const size_t stage_bytes = kABytes + (P.b_resident ? 0 : (size_t)P.Ntile * 128);
 
     // ---- tensor maps ----
     if (pl.mode == MODE_PAD8) {
