@@ -25,6 +25,7 @@
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
 // Persistent grid: one CTA per SM, tiles strided across CTAs.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -840,6 +841,10 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
     Q.num_stages = stages;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     int grid = Q.total_tiles < kNumSMs ? Q.total_tiles : kNumSMs;
+    if (const char *g = getenv("MMC_TC_GRID")) {   // profiling aid: restrict the persistent grid (profiles/probe_grid.py)
+        int v = atoi(g);
+        if (v >= 1 && v < grid) grid = v;
+    }
     conv_tc_kernel<kEpi><<<grid, kTcThreads, smem, st>>>(Q);
     MMC_CHECK_LAUNCH(name);
     return MMC_OK;
