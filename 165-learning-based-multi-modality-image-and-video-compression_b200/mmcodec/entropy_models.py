@@ -5,9 +5,9 @@ compressai/entropy_models/entropy_models.py; the per-element work runs in libmmc
 On the hot path (forward / quantize / dequantize / build_indexes / _build_indexes / _likelihood)
 everything is one fused kernel per call.  ``update()`` builds the CDF tables once per model
 (off the per-image path: SURVEY.md section 8f row 2) with a handful of tiny torch ops plus the
-library's host-side ``pmf_to_quantized_cdf``.  The rANS byte coder behind ``compress`` /
-``decompress`` is the reference's next row (section 8f row 1) and is not part of this library yet:
-``symbols_and_indexes`` exposes exactly the int32 tensors the reference hands to its coder.
+library's host-side ``pmf_to_quantized_cdf``.  ``compress`` / ``decompress`` hand the int32 symbols / indexes
+(``symbols_and_indexes``, exactly what the reference passes to ``encode_with_indexes``) to the library's host rANS
+coder, which is bitstream-compatible with ``compressai.ans``.
 """
 from __future__ import annotations
 
@@ -127,17 +127,32 @@ class EntropyModel(nn.Module):
         return symbols, indexes.int()
 
     def compress(self, inputs, indexes, means=None):
-        self.symbols_and_indexes(inputs, indexes, means)
-        raise NotImplementedError(
-            "The rANS byte coder (compressai.ans, SURVEY.md section 8f row 1) is not part of libmmcodec yet; "
-            "use symbols_and_indexes() for the int32 tensors the reference hands to its coder.")
+        """entropy_models.py:237-270: one rANS stream per image, byte-identical to the reference coder."""
+        if self.entropy_coder_name != "ans":
+            raise NotImplementedError(f'entropy coder "{self.entropy_coder_name}" is not available; libmmcodec implements "ans"')
+        symbols, indexes = self.symbols_and_indexes(inputs, indexes, means)
+        return ops.rans_encode(symbols, indexes, self._quantized_cdf, self._cdf_length, self._offset)
 
     def decompress(self, strings, indexes, dtype: torch.dtype = torch.float, means: Tensor = None):
+        """entropy_models.py:272-327"""
         if not isinstance(strings, (tuple, list)):
             raise ValueError("Invalid `strings` parameter type.")
         if not len(strings) == indexes.size(0):
             raise ValueError("Invalid strings or indexes parameters")
-        raise NotImplementedError("The rANS byte decoder is not part of libmmcodec yet (SURVEY.md section 8f row 1).")
+        if len(indexes.size()) < 2:
+            raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
+        self._check_cdf_size()
+        self._check_cdf_length()
+        self._check_offsets_size()
+        if means is not None:
+            if means.size()[:2] != indexes.size()[:2]:
+                raise ValueError("Invalid means or indexes parameters")
+            if means.size() != indexes.size():
+                for i in range(2, len(indexes.size())):
+                    if means.size(i) != 1:
+                        raise ValueError("Invalid means parameters")
+        symbols = ops.rans_decode(list(strings), indexes.int(), self._quantized_cdf, self._cdf_length, self._offset)
+        return self.dequantize(symbols, means, dtype)
 
 
 class EntropyBottleneck(EntropyModel):
@@ -269,14 +284,21 @@ class EntropyBottleneck(EntropyModel):
             means = medians.expand(x.size(0), *([-1] * (spatial_dims + 1)))
         return super().symbols_and_indexes(x, indexes, means)
 
+    def _expanded_medians(self, batch: int, spatial_dims: int) -> Tensor:
+        medians = self._extend_ndims(self._get_medians().detach(), spatial_dims)
+        return medians.expand(batch, *([-1] * (spatial_dims + 1)))
+
     def compress(self, x):
-        self.symbols_and_indexes(x)
-        return super().compress(x, self._build_indexes(x.size(), x.device), None)
+        """entropy_models.py:559-566"""
+        indexes = self._build_indexes(x.size(), x.device)
+        return super().compress(x, indexes, self._expanded_medians(x.size(0), len(x.size()) - 2))
 
     def decompress(self, strings, size):
+        """entropy_models.py:568-574"""
         output_size = (len(strings), self._quantized_cdf.size(0), *size)
         indexes = self._build_indexes(output_size, self._quantized_cdf.device)
-        return super().decompress(strings, indexes)
+        medians = self._expanded_medians(len(strings), len(size))
+        return super().decompress(strings, indexes, medians.dtype, medians)
 
 
 class GaussianConditional(EntropyModel):

@@ -145,12 +145,17 @@ class FactorizedPrior(CompressionModel):
         return {"y_symbols": y_symbols, "y_indexes": y_indexes, "shape": y.size()[-2:]}
 
     def compress(self, x):
-        self.symbols_and_indexes(x)
-        return self.entropy_bottleneck.compress(_nhwc_to_logical(run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32")))
+        """models/google.py:196-199"""
+        y = _nhwc_to_logical(run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32"))
+        y_strings = self.entropy_bottleneck.compress(y)
+        return {"strings": [y_strings], "shape": y.size()[-2:]}
 
     def decompress(self, strings, shape):
+        """models/google.py:201-205"""
         assert isinstance(strings, list) and len(strings) == 1
-        return self.entropy_bottleneck.decompress(strings[0], shape)
+        y_hat = self.entropy_bottleneck.decompress(strings[0], shape)
+        x_hat = run_layers(list(self.g_s), ops.to_bf16(y_hat).permute(0, 2, 3, 1).contiguous(), "nhwc_bf16", "nchw_f32")
+        return {"x_hat": x_hat.clamp_(0, 1)}
 
 
 class ScaleHyperprior(CompressionModel):
@@ -237,13 +242,30 @@ class ScaleHyperprior(CompressionModel):
         return {"y_symbols": y_symbols, "y_indexes": y_indexes, "z_symbols": z_symbols, "z_indexes": z_indexes,
                 "shape": z_symbols.size()[-2:]}
 
+    def _coder_tables(self, em):
+        return em._quantized_cdf, em._cdf_length, em._offset
+
     def compress(self, x):
-        self.symbols_and_indexes(x)
-        raise NotImplementedError("rANS byte coder not part of libmmcodec yet; see symbols_and_indexes()")
+        """models/google.py:324-332 (mean-scale: :393-404): symbols / indexes on the GPU, rANS streams on the host."""
+        c = self.symbols_and_indexes(x)
+        y_strings = ops.rans_encode(c["y_symbols"], c["y_indexes"], *self._coder_tables(self.gaussian_conditional))
+        z_strings = ops.rans_encode(c["z_symbols"], c["z_indexes"], *self._coder_tables(self.entropy_bottleneck))
+        return {"strings": [y_strings, z_strings], "shape": c["shape"]}
+
+    def _synthesis_from(self, y_hat):
+        x_hat = run_layers(list(self.g_s), ops.to_bf16(y_hat).permute(0, 2, 3, 1).contiguous(), "nhwc_bf16", "nchw_f32")
+        return {"x_hat": x_hat.clamp_(0, 1)}
 
     def decompress(self, strings, shape):
+        """models/google.py:334-344"""
         assert isinstance(strings, list) and len(strings) == 2
-        return self.entropy_bottleneck.decompress(strings[1], shape)
+        gc = self.gaussian_conditional
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        z_hat_bf16 = ops.to_bf16(z_hat).permute(0, 2, 3, 1).contiguous()
+        scales_hat = _nhwc_to_logical(run_layers(list(self.h_s), z_hat_bf16, "nhwc_bf16", "nhwc_f32"))
+        indexes = gc.build_indexes(scales_hat)
+        y_hat = gc.decompress(strings[0], indexes, z_hat.dtype)
+        return self._synthesis_from(y_hat)
 
 
 class MeanScaleHyperprior(ScaleHyperprior):
@@ -293,6 +315,17 @@ class MeanScaleHyperprior(ScaleHyperprior):
         y_symbols, y_indexes = gc.symbols_and_indexes(_nhwc_to_logical(y), y_indexes, means=_nhwc_to_logical(means_hat))
         return {"y_symbols": y_symbols, "y_indexes": y_indexes, "z_symbols": z_symbols, "z_indexes": z_indexes,
                 "shape": z_symbols.size()[-2:]}
+
+    def decompress(self, strings, shape):
+        """models/google.py:406-416"""
+        assert isinstance(strings, list) and len(strings) == 2
+        gc = self.gaussian_conditional
+        z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
+        scales_hat, means_hat = self._gaussian_params(ops.to_bf16(z_hat).permute(0, 2, 3, 1).contiguous())
+        scales_hat, means_hat = _nhwc_to_logical(scales_hat), _nhwc_to_logical(means_hat)
+        indexes = gc.build_indexes(scales_hat)
+        y_hat = gc.decompress(strings[0], indexes, means=means_hat)
+        return self._synthesis_from(y_hat)
 
 
 MODELS = {"bmshj2018-factorized": FactorizedPrior, "bmshj2018-hyperprior": ScaleHyperprior, "mbt2018-mean": MeanScaleHyperprior}

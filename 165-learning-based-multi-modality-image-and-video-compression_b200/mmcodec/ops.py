@@ -244,6 +244,51 @@ def pmf_to_quantized_cdf(pmf, precision: int = 16):
     return cdf.tolist()
 
 
+def _i32np(t):
+    a = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def rans_encode(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_lengths: Tensor, offsets: Tensor):
+    """compressai.ans.RansEncoder.encode_with_indexes for every image of a batch (rans_interface.cpp:108-213);
+    symbols / indexes are (B, ...) int32 tensors (any device), returns a list of B byte strings."""
+    sym, idx = _i32np(symbols), _i32np(indexes)
+    B = sym.shape[0]
+    n = sym[0].size if B else 0
+    tab, lens, offs = _i32np(cdf), _i32np(cdf_lengths).reshape(-1), _i32np(offsets).reshape(-1)
+    nbytes = np.zeros(max(B, 1), dtype=np.uint64)
+    cap = 4 * n + 64
+    for _ in range(2):
+        out = np.empty((max(B, 1), cap), dtype=np.uint8)
+        rc = L.lib().mmc_rans_encode_batch_host(sym.ctypes.data, idx.ctypes.data, B, n, tab.ctypes.data, tab.shape[0], tab.shape[1],
+                                                lens.ctypes.data, offs.ctypes.data, out.ctypes.data, cap, nbytes.ctypes.data)
+        if rc == L.MMC_EINVAL and B and int(nbytes.max()) > cap:
+            cap = int(nbytes.max())     # bypass-heavy stream: retry with the size the coder reported
+            continue
+        L.check(rc)
+        break
+    return [out[b, : int(nbytes[b])].tobytes() for b in range(B)]
+
+
+def rans_decode(strings, indexes: Tensor, cdf: Tensor, cdf_lengths: Tensor, offsets: Tensor) -> Tensor:
+    """compressai.ans.RansDecoder.decode_with_indexes for a batch (rans_interface.cpp:215-284); returns int32 symbols
+    shaped like `indexes`, on `indexes`' device."""
+    idx = _i32np(indexes)
+    B = idx.shape[0]
+    n = idx[0].size if B else 0
+    tab, lens, offs = _i32np(cdf), _i32np(cdf_lengths).reshape(-1), _i32np(offsets).reshape(-1)
+    blob = np.frombuffer(b"".join(strings), dtype=np.uint8) if strings else np.zeros(0, np.uint8)
+    blob = np.ascontiguousarray(blob)
+    sizes = np.array([len(s) for s in strings], dtype=np.uint64)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64) if B else np.zeros(0, np.uint64)
+    out = np.empty(idx.shape, dtype=np.int32)
+    L.check(L.lib().mmc_rans_decode_batch_host(blob.ctypes.data, starts.ctypes.data, sizes.ctypes.data, idx.ctypes.data, B, n,
+                                               tab.ctypes.data, tab.shape[0], tab.shape[1], lens.ctypes.data, offs.ctypes.data,
+                                               out.ctypes.data))
+    res = torch.from_numpy(out)
+    return res.to(indexes.device) if isinstance(indexes, torch.Tensor) else res
+
+
 # ---- GDN -----------------------------------------------------------------------------------------
 def gdn_reparam(beta: Tensor, gamma: Tensor, beta_bound: float, gamma_bound: float, pedestal: float,
                 want_bf16: bool = False):

@@ -71,6 +71,13 @@ def conv_flops_per_image():
     return dict(layers)
 
 
+def bench_config(batch: int, world: int):
+    """`config` of the JSON line; identical for both arms (the reference arm runs bounded samples of it)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "image": "768x512", "weights": "random init",
+            "parallelism": f"batch-sharded replicas x{world}, no data-path collective",
+            "l2": "inputs larger than L2 (302 MB fp32 batch, >1.5 GB first activation), no flush needed"}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -145,7 +152,7 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "sample": f"{b} images per step on the host CPU"},
+                "config": bench_config(args.batch, max(1, args.gpus)),
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{b}-image batches of the same model/resolution, torch CPU ops, {cores} threads"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -260,9 +267,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "image": "768x512", "weights": "random init",
-                       "parallelism": f"batch-sharded replicas x{world}, no data-path collective",
-                       "l2": "inputs larger than L2 (302 MB fp32 batch, >1.5 GB first activation), no flush needed"},
+            "config": bench_config(B, world),
             "bpp": bpp, "gpu_launches": launches, "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "bpp": e2e_bpp,

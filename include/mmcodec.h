@@ -146,6 +146,22 @@ MMC_API int mmc_bits(const float *likelihood, int64_t n, float *bits, void *stre
  * update() once per model).  cdf_host has n+1 entries.  MMC_EDOMAIN on negative / non-finite. */
 MMC_API int mmc_pmf_to_quantized_cdf_host(const float *pmf_host, int n, int precision, uint32_t *cdf_host);
 
+/* rANS byte coder, bitstream-compatible with compressai.ans.RansEncoder.encode_with_indexes /
+ * RansDecoder.decode_with_indexes   compressai/cpp_exts/rans/rans_interface.cpp:108-284 (one serial 64-bit rANS
+ * state per image, 16-bit precision, 4-bit bypass nibbles).  HOST functions on flat int32 buffers; the images of a
+ * batch are coded on parallel host threads.
+ *   symbols / indexes : [batch][n] int32 (host)      cdfs : [n_cdfs][cdf_stride] int32, row i valid for cdf_sizes[i]
+ *   encode: stream b is written at out + b * cap_per_stream, its length to nbytes[b]; MMC_EINVAL (with the required
+ *           lengths in nbytes) when cap_per_stream is too small or out is NULL.
+ *   decode: stream b is nbytes[b] bytes at streams + stream_offsets[b]. */
+MMC_API int mmc_rans_encode_batch_host(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n,
+                                       const int32_t *cdfs, int n_cdfs, int cdf_stride, const int32_t *cdf_sizes,
+                                       const int32_t *offsets, uint8_t *out, size_t cap_per_stream, size_t *nbytes);
+MMC_API int mmc_rans_decode_batch_host(const uint8_t *streams, const size_t *stream_offsets, const size_t *nbytes,
+                                       const int32_t *indexes, int batch, int64_t n, const int32_t *cdfs, int n_cdfs,
+                                       int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets,
+                                       int32_t *symbols_out);
+
 /* ---------------------------------------------------------------------------------------------
  * GDN   compressai/layers/gdn.py:77-92, compressai/ops/parametrizers.py:47-64
  * ------------------------------------------------------------------------------------------- */

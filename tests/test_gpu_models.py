@@ -155,8 +155,6 @@ def test_public_stack_forward_accepts_channels_last_and_validates():
         net.g_a(torch.rand(1, 5, 64, 64, device=dev()))
     with pytest.raises(ValueError):
         net.gaussian_conditional(torch.rand(1, 4, 2, 2, device=dev()), torch.rand(1, 4, 2, 3, device=dev()))
-    with pytest.raises(NotImplementedError):
-        net.compress(x)
 
 
 def test_full_size_properties():
@@ -210,3 +208,28 @@ def test_host_pipeline_matches_device_forward():
             assert torch.equal(out["likelihoods"][k], ref["likelihoods"][k].cpu())
     with pytest.raises(ValueError):
         pipe(x.to(dev()))
+
+
+@pytest.mark.parametrize("arch,cls,N,M", ARCHS)
+def test_compress_decompress_round_trip(models_golden, arch, cls, N, M):
+    """CompressionModel.compress / decompress (models/google.py:196-205,324-344,393-416): the rANS streams decode to
+    exactly the symbols that were coded, decompress() reproduces forward()'s reconstruction, and the coded size
+    matches the reference's own streams for the same images to within 1 %."""
+    g = models_golden
+    tag = arch.replace("-", "_")
+    net, _ = load(cls, arch, N, M)
+    x = torch.from_numpy(g["x"]).to(dev())
+    with torch.no_grad():
+        c = net.compress(x)
+        d = net.decompress(c["strings"], c["shape"])
+        fwd = net(x)
+    B = x.shape[0]
+    assert len(c["strings"]) == (1 if arch == "factorized" else 2)
+    assert all(isinstance(s, bytes) for ss in c["strings"] for s in ss) and all(len(ss) == B for ss in c["strings"])
+    assert torch.equal(d["x_hat"], fwd["x_hat"].clamp(0, 1))
+    mine = sum(len(s) for ss in c["strings"] for s in ss)
+    ref = sum(g[f"{tag}_string_{si}_{bi}"].size for si in range(len(c["strings"])) for bi in range(B))
+    assert abs(mine - ref) / ref < 0.01, (mine, ref)
+    # actual coding cost vs entropy estimate (tests/expected/eval_{0,1}_*.json show 0.14 % for the reference)
+    npix = B * x.shape[2] * x.shape[3]
+    assert abs(mine * 8 / npix - net.bpp(fwd, npix)) / net.bpp(fwd, npix) < 0.02

@@ -181,6 +181,45 @@ def test_synthetic_weights_are_stable():
     assert sd["g_s.6.weight"].shape == (128, 3, 5, 5)
 
 
+@pytest.mark.parametrize("arch,cls,N,M", [("factorized", mmcodec.FactorizedPrior, 128, 192),
+                                          ("hyperprior", mmcodec.ScaleHyperprior, 128, 192),
+                                          ("mean_scale", mmcodec.MeanScaleHyperprior, 192, 320)])
+def test_rans_streams_byte_identical_to_reference(models_golden, arch, cls, N, M):
+    """The host rANS coder on the reference's own symbols / indexes (captured at its encode_with_indexes call) and the
+    CDF tables built by our update(): streams byte-identical to the reference's (SURVEY.md 8d parity gate)."""
+    from mmcodec import ops
+    g = models_golden
+    net = cls(N, M).eval()
+    sd = {k: torch.from_numpy(v) for k, v in make_state_dict(arch.replace("_", "-"), N, M, seed=0).items()}
+    net.update()
+    net.load_state_dict({**net.state_dict(), **sd})
+    net.update(force=True)
+    ems = [("y", net.entropy_bottleneck)] if arch == "factorized" else [("y", net.gaussian_conditional), ("z", net.entropy_bottleneck)]
+    for si, (name, em) in enumerate(ems):
+        sym, idx = torch.from_numpy(g[f"{arch}_{name}_symbols"]), torch.from_numpy(g[f"{arch}_{name}_indexes"])
+        strings = ops.rans_encode(sym, idx, em._quantized_cdf, em._cdf_length, em._offset)
+        for b, s in enumerate(strings):
+            assert s == g[f"{arch}_string_{si}_{b}"].tobytes(), (name, b)
+        assert torch.equal(ops.rans_decode(strings, idx, em._quantized_cdf, em._cdf_length, em._offset), sym)
+
+
+def test_rans_bypass_and_errors():
+    from mmcodec import ops
+    eb = mmcodec.EntropyBottleneck(4)
+    eb.update()
+    tabs = (eb._quantized_cdf, eb._cdf_length, eb._offset)
+    idx = torch.arange(4, dtype=torch.int32).repeat(3, 25)                  # (3, 100)
+    sym = torch.randint(-200000, 200000, (3, 100), dtype=torch.int32)      # far outside the tables -> bypass nibbles
+    sym[0, :10] = torch.tensor([0, 1, -1, 10, -10, 11, -11, 12, 2 ** 30, -2 ** 30])
+    strings = ops.rans_encode(sym, idx, *tabs)
+    assert torch.equal(ops.rans_decode(strings, idx, *tabs), sym)
+    assert ops.rans_encode(sym[:0], idx[:0], *tabs) == []
+    with pytest.raises(ValueError):
+        ops.rans_encode(sym, idx + 4, *tabs)                                # index outside the table
+    with pytest.raises(ValueError):
+        ops.rans_decode([s[:8] for s in strings], idx, *tabs)               # truncated stream
+
+
 def _shard_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
