@@ -69,6 +69,7 @@ struct TcParams {
     int kchunks;     // K boxes per tap (ceil(Cin / 64); 1 in MODE_PAD8)
     int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
     int num_stages, acc_stages;
+    int debug;       // profiling aid (env MMC_TC_DEBUG): 1 = no TMA traffic after the pipeline is primed, 2 = no MMAs
     int b_resident;  // whole packed weight matrix stays in shared memory (small layers); K blocks stream A only
     int act, gdn, out_f32, out2;
     int gdn_chunk;
@@ -127,6 +128,18 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *tm, uint64_t *bar
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+// elect.sync: exactly one lane of the (converged) warp gets true
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -405,6 +418,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     for (int kc = 0; kc < P.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t *a = smem + (size_t)stage * stage_bytes;
+                        if (P.debug == 1 && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
+                            mbar_arrive(&full_bar[stage]);
+                            if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
                         mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
                         tma_load_4d(&P.tmA, &full_bar[stage], a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
                         if (!P.b_resident) tma_load_2d(&P.tmB, &full_bar[stage], a + kABytes, kc * 64, tap.brow + t.n0);
@@ -415,32 +433,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(P.Ntile);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0;
-            if (P.b_resident) mbar_wait(&bres_bar, 0);
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-                TileCoord t = decode_tile(P, tile);
-                const int as = (P.acc_stages == 2) ? (it & 1) : 0;
-                const uint32_t aphase = (P.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
-                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+        // The whole warp walks the pipeline (uniform control flow, every lane observes the barriers); one lane chosen
+        // by elect.sync issues the tcgen05.mma / tcgen05.commit instructions, fully unrolled per K block so that the
+        // descriptors are plain uniform-register increments.
+        const uint32_t idesc = make_idesc(P.Ntile);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        if (P.b_resident) mbar_wait(&bres_bar, 0);
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
+            TileCoord t = decode_tile(P, tile);
+            const int as = (P.acc_stages == 2) ? (it & 1) : 0;
+            const uint32_t aphase = (P.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+            mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * P.Ntile);
+            const int nkb = (P.phase_begin[t.phase + 1] - P.phase_begin[t.phase]) * P.kchunks;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * P.Ntile);
-                const int nkb = (P.phase_begin[t.phase + 1] - P.phase_begin[t.phase]) * P.kchunks;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = make_desc(a_addr);
-                    const uint64_t bdesc = make_desc(P.b_resident ? smem_u32(sBres + (size_t)kb * b_tile_bytes) : a_addr + kABytes);
-                    for (int k = 0; k < P.ksteps; ++k)   // K=16 per step: +32 B inside the 128-byte swizzle atom
-                        tc_mma(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t adesc = make_desc(a_addr);
+                const uint64_t bdesc = make_desc(P.b_resident ? smem_u32(sBres + (size_t)kb * b_tile_bytes) : a_addr + kABytes);
+                if (elect_one()) {
+                    if (P.debug != 2) {
+                        // K=16 per step: +32 B (= +2 in descriptor units) inside the 128-byte swizzle atom
+                        tc_mma(d_tmem, adesc, bdesc, idesc, kb != 0);
+                        tc_mma(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                        tc_mma(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                        if (P.ksteps == 4) tc_mma(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                    }
                     tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
-                    if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
+                    if (kb == nkb - 1) tc_commit(&tmem_full_bar[as]);   // accumulator complete -> epilogue
                 }
-                tc_commit(&tmem_full_bar[as]);      // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -841,6 +868,7 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
     Q.num_stages = stages;
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     int grid = Q.total_tiles < kNumSMs ? Q.total_tiles : kNumSMs;
+    if (const char *g = getenv("MMC_TC_DEBUG")) Q.debug = atoi(g);
     if (const char *g = getenv("MMC_TC_GRID")) {   // profiling aid: restrict the persistent grid (profiles/probe_grid.py)
         int v = atoi(g);
         if (v >= 1 && v < grid) grid = v;

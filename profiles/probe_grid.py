@@ -8,7 +8,7 @@ if len(sys.argv) > 1:
     import torch
     from mmcodec import ops, _lib as L
     dev = torch.device("cuda", 0)
-    B, cin, cout, h, w = 64, 128, 128, 256, 384
+    B, cin, cout, h, w = 64, 128, int(os.environ.get("PROBE_COUT", "128")), 256, 384
     x = torch.randn(B, h, w, cin, device=dev).to(torch.bfloat16)
     wt = torch.randn(cout, cin, 5, 5, device=dev) * 0.02
     b = torch.randn(cout, device=dev)
@@ -25,8 +25,17 @@ if len(sys.argv) > 1:
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     flops = 2.0 * cin * cout * 25 * B * (h // 2) * (w // 2)
-    print(json.dumps({"grid": os.environ.get("MMC_TC_GRID", "148"), "ms": ms, "tflops": flops / ms / 1e9}))
+    print(json.dumps({"grid": os.environ.get("MMC_TC_GRID", "148"), "cout": cout, "ms": ms, "tflops": flops / ms / 1e9}))
 else:
-    for g in (148, 111, 74, 37, 18):
+    for g in (148, 74):
         env = dict(os.environ, MMC_TC_GRID=str(g))
         print(subprocess.run([sys.executable, __file__, "run"], env=env, capture_output=True, text=True).stdout.strip())
+    # operand-bandwidth check: N = 64 / 128 / 256 with and without TMA traffic
+    for cout in (64, 128, 256):
+        for dbg in (0, 1):
+            env = dict(os.environ, PROBE_COUT=str(cout), MMC_TC_DEBUG=str(dbg))
+            print("cout", cout, "debug", dbg, subprocess.run([sys.executable, __file__, "run"], env=env, capture_output=True, text=True).stdout.strip())
+    # MMC_TC_DEBUG=1: TMA traffic off after priming (MMA + smem operand reads only); =2: MMAs off (TMA streaming only)
+    for dbg in (1, 2):
+        env = dict(os.environ, MMC_TC_DEBUG=str(dbg))
+        print("debug", dbg, subprocess.run([sys.executable, __file__, "run"], env=env, capture_output=True, text=True).stdout.strip())

@@ -35,6 +35,7 @@ def load(cls, arch, N, M):
     net = cls(N, M).eval()
     net.update()
     net.load_state_dict({**net.state_dict(), **sd})
+    net.update(force=True)   # CDF tables of the entropy bottleneck depend on the loaded parameters
     return net.to(dev()), sd
 
 
