@@ -69,11 +69,12 @@ struct TcParams {
     int kchunks;     // K boxes per tap (ceil(Cin / 64); 1 in MODE_PAD8)
     int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
     int num_stages, acc_stages;
-    int debug;       // profiling aid (env MMC_TC_DEBUG): 1 = no TMA traffic after the pipeline is primed, 2 = no MMAs
+    int debug;       // profiling aid (env MMC_TC_DEBUG): 1 = no TMA traffic after priming, 2 = no main-loop MMAs, 3 = no GDN MMAs
     int b_resident;  // whole packed weight matrix stays in shared memory (small layers); K blocks stream A only
     int act, gdn, out_f32, out2;
     int gdn_chunk;
     int tiles_per_phase, total_tiles;
+    int st_nb, st_tx, st_ty, st_b, st_ph;   // gridDim.x decomposed in the radices (n_blocks, tiles_x, tiles_y, B, phase)
     const float *bias;
     const float *beta;
     void *y;
@@ -194,6 +195,13 @@ __device__ __forceinline__ float act_tc(float v, int act)
     if (act == MMC_ACT_LEAKY_RELU) return v > 0.0f ? v : 0.01f * v;
     return v;
 }
+// MUFU.RSQ without the denormal fix-up sequence of rsqrtf(): the GDN norm is beta + sum(gamma x^2) >= beta_min > 0
+__device__ __forceinline__ float rsqrt_fast(float v)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -203,20 +211,43 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 struct TileCoord {
     int phase, b, y0, x0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const TcParams &P, int tile)
+// Tile index -> (phase, image, tile row, tile column, N block).  The persistent loop advances by gridDim.x tiles per
+// iteration; instead of four integer divisions per tile the coordinates are kept as a mixed-radix counter and the
+// step (decomposed on the host into the same radices) is added with carries.
+__device__ __forceinline__ TileCoord make_coord(const TcParams &P, int phase, int b, int ty, int tx, int nb)
 {
     TileCoord t;
-    t.phase = tile / P.tiles_per_phase;
-    int r = tile - t.phase * P.tiles_per_phase;
-    int nb = r % P.n_blocks; r /= P.n_blocks;
-    int tx = r % P.tiles_x;  r /= P.tiles_x;
-    int ty = r % P.tiles_y;
-    t.b = r / P.tiles_y;
+    t.phase = phase; t.b = b;
     t.y0 = ty * P.step_y - P.off_y;
     t.x0 = tx * P.step_x - P.off_x;
     t.n0 = nb * P.Ntile;
     return t;
 }
+struct TileIter {
+    int nb, tx, ty, b, phase;
+    __device__ __forceinline__ void init(const TcParams &P, int tile)
+    {
+        phase = tile / P.tiles_per_phase;
+        int r = tile - phase * P.tiles_per_phase;
+        nb = r % P.n_blocks; r /= P.n_blocks;
+        tx = r % P.tiles_x;  r /= P.tiles_x;
+        ty = r % P.tiles_y;
+        b = r / P.tiles_y;
+    }
+    __device__ __forceinline__ void advance(const TcParams &P)
+    {
+        nb += P.st_nb;
+        int c = nb >= P.n_blocks; nb -= c ? P.n_blocks : 0;
+        tx += P.st_tx + c;
+        c = tx >= P.tiles_x; tx -= c ? P.tiles_x : 0;
+        ty += P.st_ty + c;
+        c = ty >= P.tiles_y; ty -= c ? P.tiles_y : 0;
+        b += P.st_b + c;
+        c = b >= P.B; b -= c ? P.B : 0;
+        phase += P.st_ph + c;
+    }
+    __device__ __forceinline__ TileCoord coord(const TcParams &P) const { return make_coord(P, phase, b, ty, tx, nb); }
+};
 
 __device__ __forceinline__ void load16f(const float *sm, float *o)
 {
@@ -267,6 +298,7 @@ struct GdnCtx {
     bool valid;
     int64_t pix_off;
     int it;
+    const int64_t *pix_off_s;   // per-pixel output offsets of this tile (-1: outside the image)
 };
 
 template <int NCH, int G>
@@ -302,51 +334,90 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
 #pragma unroll
     for (int grp = 0; grp < G; ++grp) {
         const int g0 = grp * gch * 16;
-        if (threadIdx.x == 64) {
+        if ((threadIdx.x >> 5) == 2) {
+            // first epilogue warp: uniform control flow, one elected lane issues the (compile-time unrolled) MMAs
             if (g.it == 0 && grp == 0) mbar_wait(g.gload_bar, 0);
             tc_fence_after();
-            const uint32_t idesc = make_idesc(P.gdn_chunk);
-            for (int kc = 0; kc < P.Cout / 64; ++kc) {
-                const uint64_t adesc = make_desc(smem_u32(g.sA2 + (size_t)kc * kABytes));
-                const uint64_t bdesc = make_desc(smem_u32(g.sG + (size_t)kc * P.Cout * 128 + (size_t)g0 * 128));
+            const uint32_t idesc = make_idesc(gch * 16);
+            const uint32_t a2 = smem_u32(g.sA2), gm = smem_u32(g.sG) + (uint32_t)(g0 * 128);
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma(g.tmem_base + g.norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                for (int kc = 0; kc < (P.debug == 3 ? 0 : NCH / 2); ++kc) {   // debug 3: profiling, no norm MMAs
+                    const uint64_t adesc = make_desc(a2 + (uint32_t)(kc * kABytes));
+                    const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * P.Cout * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma(g.tmem_base + g.norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                }
+                tc_commit(g.gdn_bar);
             }
-            tc_commit(g.gdn_bar);
+            __syncwarp();
         }
         mbar_wait(g.gdn_bar, gdn_phase);
         gdn_phase ^= 1;
         tc_fence_after();
-        // my chunks of this group: j in [grp*per, (grp+1)*per)
-        float nrm[per][16];
+        // my chunks of this group: j in [grp*per, (grp+1)*per), two norm chunks in flight at a time (register budget)
 #pragma unroll
-        for (int jj = 0; jj < per; ++jj)
-            tmem_ld16(g.tmem_base + g.lane_addr + g.norm_col + (uint32_t)((chunk_of(grp * per + jj) << 4) - g0), nrm[jj]);
-        tmem_ld_wait();
+        for (int jb = 0; jb < per; jb += 2) {
+            float nrm[2][16];
 #pragma unroll
-        for (int jj = 0; jj < per; ++jj) {
-            const int j = grp * per + jj;
-            const int c0 = chunk_of(j) << 4;
-            float bt[16], y[16];
-            load16f(beta_s + c0, bt);
+            for (int u = 0; u < 2; ++u)
+                if (jb + u < per)
+                    tmem_ld16(g.tmem_base + g.lane_addr + g.norm_col + (uint32_t)((chunk_of(grp * per + jb + u) << 4) - g0), nrm[u]);
+            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float n = bt[i] + nrm[jj][i];
-                const float r = rsqrtf(n);
-                y[i] = (P.gdn == MMC_GDN_INVERSE) ? x[j][i] * (n * r) : x[j][i] * r;
+            for (int u = 0; u < 2; ++u) {
+                if (jb + u >= per) continue;
+                const int j = grp * per + jb + u;
+                const int c0 = chunk_of(j) << 4;
+                float bt[16];
+                load16f(beta_s + c0, bt);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float n = bt[i] + nrm[u][i];
+                    const float r = rsqrt_fast(n);
+                    x[j][i] = (P.gdn == MMC_GDN_INVERSE) ? x[j][i] * (n * r) : x[j][i] * r;
+                }
+                const float *y = x[j];
+                if (G == 1 && !P.out_f32 && !P.out2) {
+                    // stage the bf16 result in the (now idle) x^2 tile, same swizzled [pixel][channel] layout
+                    uint8_t *tile_base = g.sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)g.row * 128;
+                    const int j0 = (c0 & 63) >> 3;
+                    *reinterpret_cast<uint4 *>(tile_base + (((j0) ^ (g.row & 7)) << 4)) =
+                        make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+                    *reinterpret_cast<uint4 *>(tile_base + (((j0 + 1) ^ (g.row & 7)) << 4)) =
+                        make_uint4(pack_bf16(y[8], y[9]), pack_bf16(y[10], y[11]), pack_bf16(y[12], y[13]), pack_bf16(y[14], y[15]));
+                } else if (g.valid) {
+                    store16(P, g.pix_off + c0, y);
+                }
             }
-            if (g.valid) store16(P, g.pix_off + c0, y);
         }
         // every epilogue thread is done with the norm columns (and, after the last group, with sA2)
         tc_fence_before();
         asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    if (G == 1 && !P.out_f32 && !P.out2) {
+        // Coalesced copy-out: consecutive lanes move consecutive 16-byte chunks of one pixel, so every warp store
+        // covers whole 128-byte lines (the per-row direct stores touch 32 lines per instruction).
+        constexpr int cpp = NCH * 4;               // 16-byte chunks per pixel (C / 8): 8 or 16
+        constexpr int ppi = kEpiThreads / cpp;     // pixels covered per iteration (32 or 16, a multiple of 8)
+        const int et = threadIdx.x - 64;
+        const int j = et % cpp, p0 = et / cpp;     // this thread always moves chunk j; pixel p0 + it * ppi
+        const uint8_t *src = g.sA2 + (size_t)(j >> 3) * kABytes + (size_t)p0 * 128 + (((j & 7) ^ (p0 & 7)) << 4);
+        __nv_bfloat16 *yo = (__nv_bfloat16 *)P.y + j * 8;
+#pragma unroll
+        for (int i = 0; i < 128 / ppi; ++i) {
+            const int64_t off = g.pix_off_s[p0 + i * ppi];
+            const uint4 v = *reinterpret_cast<const uint4 *>(src + (size_t)i * ppi * 128);
+            if (off >= 0) *reinterpret_cast<uint4 *>(yo + off) = v;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile free for the next tile's x^2
+    }
 }
 
 enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_SCATTER = 2 };
 
-template <int kEpi>
+template <int kEpi, int kNCH>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -355,6 +426,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[kMaxCout];
     __shared__ __align__(16) float beta_s[256];
+    __shared__ int64_t pix_off_s[128];   // GDN epilogue: global element offset of each tile pixel (-1 = masked)
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_tile_bytes = P.Ntile * 128;
@@ -395,39 +467,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            if (kEpi == EPI_GDN) {
+        // Whole warp walks the tile / K-block loops (uniform control flow); the lane chosen by elect.sync issues.
+        if (kEpi == EPI_GDN) {
+            if (elect_one()) {
                 mbar_expect_tx(&gload_bar, (uint32_t)(P.Cout * P.Cout * 2));
                 for (int kc = 0; kc < P.Cout / 64; ++kc)
                     tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * P.Cout * 128, kc * 64, 0);
             }
-            if (P.b_resident) {
+            __syncwarp();
+        }
+        if (P.b_resident) {
+            if (elect_one()) {
                 const int nkb = P.phase_begin[1] * P.kchunks;
                 mbar_expect_tx(&bres_bar, (uint32_t)(nkb * b_tile_bytes));
                 for (int tp = 0; tp < P.phase_begin[1]; ++tp)
                     for (int kc = 0; kc < P.kchunks; ++kc)
                         tma_load_2d(&P.tmB, &bres_bar, sBres + (size_t)(tp * P.kchunks + kc) * b_tile_bytes, kc * 64, P.taps[tp].brow);
             }
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-                TileCoord t = decode_tile(P, tile);
-                const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
-                for (int tp = P.phase_begin[t.phase]; tp < P.phase_begin[t.phase + 1]; ++tp) {
-                    const Tap tap = P.taps[tp];
-                    for (int kc = 0; kc < P.kchunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t *a = smem + (size_t)stage * stage_bytes;
+            __syncwarp();
+        }
+        int stage = 0;
+        uint32_t phase = 0;
+        TileIter ti;
+        ti.init(P, blockIdx.x);
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti.advance(P)) {
+            const TileCoord t = ti.coord(P);
+            const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
+            for (int tp = P.phase_begin[t.phase]; tp < P.phase_begin[t.phase + 1]; ++tp) {
+                const Tap tap = P.taps[tp];
+                for (int kc = 0; kc < P.kchunks; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t *a = smem + (size_t)stage * stage_bytes;
+                    if (elect_one()) {
                         if (P.debug == 1 && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
                             mbar_arrive(&full_bar[stage]);
-                            if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
-                            continue;
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+                            tma_load_4d(&P.tmA, &full_bar[stage], a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
+                            if (!P.b_resident) tma_load_2d(&P.tmB, &full_bar[stage], a + kABytes, kc * 64, tap.brow + t.n0);
                         }
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                        tma_load_4d(&P.tmA, &full_bar[stage], a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
-                        if (!P.b_resident) tma_load_2d(&P.tmB, &full_bar[stage], a + kABytes, kc * 64, tap.brow + t.n0);
-                        if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
                     }
+                    __syncwarp();
+                    if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -441,8 +522,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         uint32_t phase = 0;
         int it = 0;
         if (P.b_resident) mbar_wait(&bres_bar, 0);
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-            TileCoord t = decode_tile(P, tile);
+        TileIter ti;
+        ti.init(P, blockIdx.x);
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P)) {
+            const TileCoord t = ti.coord(P);
             const int as = (P.acc_stages == 2) ? (it & 1) : 0;
             const uint32_t aphase = (P.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
             mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
@@ -480,8 +563,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const uint32_t norm_col = (uint32_t)(P.acc_stages * P.Ntile);
         uint32_t gdn_phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it) {
-            TileCoord t = decode_tile(P, tile);
+        TileIter ti;
+        ti.init(P, blockIdx.x);
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P)) {
+            const TileCoord t = ti.coord(P);
             const int as = (P.acc_stages == 2) ? (it & 1) : 0;
             const uint32_t aphase = (P.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
             const int gy = t.y0 + th, gx = t.x0 + tw;
@@ -602,11 +687,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                         }
                     }
                 } else {
-                    GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it};
+                    if (half == 0) pix_off_s[row] = valid ? pix_off : -1;   // published by the bar.sync inside epilogue_gdn
+                    GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it, pix_off_s};
                     // (chunks per thread, norm groups): C=128 -> one 128-column norm pass; C=192 -> two 96-column passes
-                    if (P.Cout == 128) epilogue_gdn<4, 1>(g, bias_s, beta_s, gdn_phase);
-                    else if (P.Cout == 192) epilogue_gdn<6, 2>(g, bias_s, beta_s, gdn_phase);
-                    else epilogue_gdn<2, 1>(g, bias_s, beta_s, gdn_phase);
+                    epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1)>(g, bias_s, beta_s, gdn_phase);
                 }
             }
             tc_fence_before();
@@ -849,16 +933,16 @@ static void pick_tile(int gh, int gw, int sx, int sy, int *TH, int *TW)
     }
 }
 
-template <int kEpi>
+template <int kEpi, int kNCH>
 static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaStream_t st, const char *name)
 {
     // dynamic shared memory available next to the kernel's static allocation (227 KB per CTA on sm_100)
     static size_t budget = 0;
     if (budget == 0) {
         cudaFuncAttributes fa;
-        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi>));
+        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi, kNCH>));
         size_t avail = 227 * 1024 - fa.sharedSizeBytes;
-        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi, kNCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
         budget = avail;
     }
     MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
@@ -873,7 +957,15 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         int v = atoi(g);
         if (v >= 1 && v < grid) grid = v;
     }
-    conv_tc_kernel<kEpi><<<grid, kTcThreads, smem, st>>>(Q);
+    {
+        int r = grid;   // step of the persistent loop, in the tile counter's radices
+        Q.st_nb = r % Q.n_blocks; r /= Q.n_blocks;
+        Q.st_tx = r % Q.tiles_x;  r /= Q.tiles_x;
+        Q.st_ty = r % Q.tiles_y;  r /= Q.tiles_y;
+        Q.st_b = r % Q.B;
+        Q.st_ph = r / Q.B;
+    }
+    conv_tc_kernel<kEpi, kNCH><<<grid, kTcThreads, smem, st>>>(Q);
     MMC_CHECK_LAUNCH(name);
     return MMC_OK;
 }
@@ -1033,9 +1125,15 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl.mode == MODE_SCATTER) return launch_tc<EPI_SCATTER>(P, fixed, stage_bytes, st, name);
-    if (d->gdn != MMC_GDN_NONE) return launch_tc<EPI_GDN>(P, fixed, stage_bytes, st, name);
-    return launch_tc<EPI_PLAIN>(P, fixed, stage_bytes, st, name);
+    if (pl.mode == MODE_SCATTER) return launch_tc<EPI_SCATTER, 0>(P, fixed, stage_bytes, st, name);
+    if (d->gdn != MMC_GDN_NONE) {
+        // one kernel per channel count (16-column chunks per epilogue thread = Cout / 32) so that each gets its own
+        // register allocation: C=128 keeps 64 activations per thread in registers, C=192 keeps 96
+        if (d->Cout == 128) return launch_tc<EPI_GDN, 4>(P, fixed, stage_bytes, st, name);
+        if (d->Cout == 192) return launch_tc<EPI_GDN, 6>(P, fixed, stage_bytes, st, name);
+        return launch_tc<EPI_GDN, 2>(P, fixed, stage_bytes, st, name);
+    }
+    return launch_tc<EPI_PLAIN, 0>(P, fixed, stage_bytes, st, name);
 }
 
 }  // extern "C"
