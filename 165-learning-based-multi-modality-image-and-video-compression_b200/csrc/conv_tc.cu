@@ -34,6 +34,7 @@ namespace mmc {
 constexpr int kTcThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAccStages = 4;
 constexpr int kMaxTaps = 32;
 constexpr int kMaxCout = 1024;
 constexpr int kABytes = 128 * 128;  // 128 pixels x 64 bf16
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-    __shared__ uint64_t tmem_full_bar[2], tmem_empty_bar[2], gdn_bar, gload_bar, bres_bar;
+    __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar, gload_bar, bres_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[kMaxCout];
     __shared__ __align__(16) float beta_s[256];
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiThreads); }
+        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiThreads); }
         mbar_init(&gdn_bar, 1);
         mbar_init(&gload_bar, 1);
         mbar_init(&bres_bar, 1);
@@ -524,10 +525,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         if (P.b_resident) mbar_wait(&bres_bar, 0);
         TileIter ti;
         ti.init(P, blockIdx.x);
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P)) {
+        int acc_i = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
             const TileCoord t = ti.coord(P);
-            const int as = (P.acc_stages == 2) ? (it & 1) : 0;
-            const uint32_t aphase = (P.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+            const int as = acc_i;                       // accumulator ring position of this tile
+            const uint32_t aphase = acc_ph;
             mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(as * P.Ntile);
@@ -565,10 +568,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         int it = 0;
         TileIter ti;
         ti.init(P, blockIdx.x);
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P)) {
+        int acc_i = 0;
+        uint32_t acc_ph = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
             const TileCoord t = ti.coord(P);
-            const int as = (P.acc_stages == 2) ? (it & 1) : 0;
-            const uint32_t aphase = (P.acc_stages == 2) ? ((it >> 1) & 1) : (it & 1);
+            const int as = acc_i;                       // accumulator ring position of this tile
+            const uint32_t aphase = acc_ph;
             const int gy = t.y0 + th, gx = t.x0 + tw;
             const bool valid = gy < P.Gh && gx < P.Gw;
             const uint32_t acc_addr = tmem_base + lane_addr + (uint32_t)(as * P.Ntile);
@@ -1077,7 +1082,9 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     P.total_tiles = (int)(tpp * P.n_phases);
     P.gdn_chunk = 0;
     if (d->gdn != MMC_GDN_NONE) P.gdn_chunk = (3 * P.Ntile <= 512) ? P.Ntile : P.Ntile / 2;
-    P.acc_stages = (2 * P.Ntile + P.gdn_chunk <= 512) ? 2 : 1;
+    P.acc_stages = (512 - P.gdn_chunk) / P.Ntile;      // as many accumulator stages as TMEM holds (epilogue slack)
+    if (P.acc_stages > kMaxAccStages) P.acc_stages = kMaxAccStages;
+    if (P.acc_stages < 1) P.acc_stages = 1;
     MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
 
     size_t fixed = 1024;  // alignment slack
