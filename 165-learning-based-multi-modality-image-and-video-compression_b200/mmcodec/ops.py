@@ -347,7 +347,7 @@ def conv_forward_direct(d: L.ConvDesc, x: Tensor, w: Tensor, bias: Optional[Tens
     """CUDA-core conv / deconv.  x is the raw buffer in the layout/dtype the descriptor names."""
     _require_cuda(x, w)
     y, y2 = _alloc_out(d, x.device)
-    with _Timed(name + "|direct"):
+    with _Timed(name + "|direct", conv_flops(d) if _profile is not None else 0.0):
         L.check(L.lib().mmc_conv_forward_direct(ctypes.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(beta_eff),
                                                 _ptr(gamma_eff), _ptr(y), _ptr(y2), _stream()))
     return (y, y2) if d.out2_bf16 else y
@@ -368,7 +368,7 @@ def conv_forward_tc(d: L.ConvDesc, x: Tensor, w_packed: Tensor, bias: Optional[T
     """Tensor-core (tcgen05) implicit-GEMM conv / deconv on NHWC bf16 input."""
     _require_cuda(x, w_packed)
     y, y2 = _alloc_out(d, x.device)
-    with _Timed(name + "|tc"):
+    with _Timed(name + "|tc", conv_flops(d) if _profile is not None else 0.0):
         L.check(L.lib().mmc_conv_forward_tc(ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(beta_eff),
                                             _ptr(gamma_bf16), _ptr(y), _ptr(y2), _stream()))
     return (y, y2) if d.out2_bf16 else y
@@ -425,20 +425,36 @@ def start_profile():
     return _profile
 
 
-def stop_profile():
-    """Returns {name: mean ms per launch} for everything recorded since start_profile()."""
+def stop_profile(with_work: bool = False):
+    """Returns {name: mean ms per launch} for everything recorded since start_profile()
+    (with_work: {name: (ms, algorithmic FLOPs per launch)})."""
     global _profile
     rec, _profile = _profile or [], None
     torch.cuda.synchronize()
-    acc = {}
-    for name, e0, e1 in rec:
+    acc, work = {}, {}
+    for name, e0, e1, flops in rec:
         acc.setdefault(name, []).append(e0.elapsed_time(e1))
+        work[name] = flops
+    if with_work:
+        return {k: (sum(v) / len(v), work[k]) for k, v in acc.items()}
     return {k: sum(v) / len(v) for k, v in acc.items()}
 
 
+def conv_flops(d: L.ConvDesc) -> float:
+    """Algorithmic FLOPs of one conv / deconv launch: 2*Cin*Cout*k*k*B*Hout*Wout for a conv,
+    2*Cin*Cout*k*k*B*Hin*Win for a transposed conv, plus 2*C*C*B*Hout*Wout when GDN / IGDN is fused."""
+    Ho, Wo = conv_out_size(d)
+    pix = d.H * d.W if d.transposed else Ho * Wo
+    f = 2.0 * d.Cin * d.Cout * d.k * d.k * d.B * pix
+    if d.gdn != L.GDN_NONE:
+        f += 2.0 * d.Cout * d.Cout * d.B * Ho * Wo
+    return f
+
+
 class _Timed:
-    def __init__(self, name):
+    def __init__(self, name, flops: float = 0.0):
         self.name = name
+        self.flops = flops
 
     def __enter__(self):
         if _profile is not None:
@@ -449,7 +465,7 @@ class _Timed:
         if _profile is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _profile.append((self.name, self.e0, e1))
+            _profile.append((self.name, self.e0, e1, self.flops))
 
 
 def launch_count() -> int:

@@ -40,9 +40,20 @@ for p in (ROOT, PKG_DIR, os.path.join(ROOT, "tests", "golden")):
 
 METRIC = "img/s (768x512 codec fwd+likelihoods)"
 UNIT = "img/s"
-ARCH, QUALITY, N_CH, M_CH = "bmshj2018-hyperprior", 4, 128, 192
-H, W = 512, 768
-WORKLOAD = "bmshj2018-hyperprior q4 eval forward, batch 64 x 768x512 RGB (BASELINE.json configs[1])"
+# name -> (zoo architecture, quality, H, W, default batch per GPU, call, description).  The default (and the only one the
+# driver runs) is configs[1]; the others are BASELINE.json's parity configs, measurable with --workload for the record.
+WORKLOADS = {
+    "hyperprior": ("bmshj2018-hyperprior", 4, 512, 768, 64, "forward",
+                   "bmshj2018-hyperprior q4 eval forward, batch 64 x 768x512 RGB (BASELINE.json configs[1])"),
+    "factorized": ("bmshj2018-factorized", 1, 512, 768, 64, "forward",
+                   "bmshj2018-factorized q1 eval forward, 768x512 RGB (BASELINE.json configs[0], batched)"),
+    "mbt-mean-symbols": ("mbt2018-mean", 6, 1088, 1920, 8, "symbols",
+                         "mbt2018-mean q6 compress() symbol/index path, 1920x1080 padded to 1088 (BASELINE.json configs[2])"),
+    "mbt-mean-compress": ("mbt2018-mean", 6, 1088, 1920, 8, "compress",
+                          "mbt2018-mean q6 compress() incl. host rANS coding, 1920x1080 padded to 1088"),
+}
+ARCH, QUALITY, H, W = "bmshj2018-hyperprior", 4, 512, 768
+WORKLOAD = WORKLOADS["hyperprior"][6]
 
 
 def shard_range(total: int, rank: int, world: int):
@@ -52,30 +63,12 @@ def shard_range(total: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def conv_flops_per_image():
-    """Algorithmic FLOPs per 768x512 image: 2*Cin*Cout*k*k*Hout*Wout per conv,
-    2*Cin*Cout*k*k*Hin*Win per deconv, 2*C*C*H*W per GDN/IGDN."""
-    N, M = N_CH, M_CH
-    layers = []  # (name, flops, min_bytes)
-    def conv(name, cin, cout, k, ho, wo, gdn=False):
-        f = 2.0 * cin * cout * k * k * ho * wo + (2.0 * cout * cout * ho * wo if gdn else 0.0)
-        layers.append((name, f))
-    conv("g_a.0", 3, N, 5, 256, 384, True); conv("g_a.2", N, N, 5, 128, 192, True)
-    conv("g_a.4", N, N, 5, 64, 96, True); conv("g_a.6", N, M, 5, 32, 48)
-    conv("h_a.0", M, N, 3, 32, 48); conv("h_a.2", N, N, 5, 16, 24); conv("h_a.4", N, N, 5, 8, 12)
-    conv("h_s.0", N, N, 5, 8, 12); conv("h_s.2", N, N, 5, 16, 24); conv("h_s.4", N, M, 3, 32, 48)   # deconv: Hin*Win
-    conv("g_s.0", M, N, 5, 32, 48); conv("g_s.2", N, N, 5, 64, 96); conv("g_s.4", N, N, 5, 128, 192)
-    conv("g_s.6", N, 3, 5, 256, 384)
-    # IGDN terms (at the deconv OUTPUT resolution)
-    layers.append(("igdn", 2.0 * N * N * (64 * 96 + 128 * 192 + 256 * 384)))
-    return dict(layers)
-
-
 def bench_config(batch: int, world: int):
     """`config` of the JSON line; identical for both arms (the reference arm runs bounded samples of it)."""
-    return {"workload": WORKLOAD, "batch_per_gpu": batch, "image": "768x512", "weights": "random init",
+    mb = batch * 3 * H * W * 4 / 1e6
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "image": f"{W}x{H}", "weights": "random init",
             "parallelism": f"batch-sharded replicas x{world}, no data-path collective",
-            "l2": "inputs larger than L2 (302 MB fp32 batch, >1.5 GB first activation), no flush needed"}
+            "l2": f"inputs larger than L2 ({mb:.0f} MB fp32 batch and GB-sized first activations), no flush needed"}
 
 
 class ClockSampler(threading.Thread):
@@ -119,14 +112,19 @@ def cpu_reference_throughput(batch: int, steps: int, warmup: int):
     net = mmcodec.build_model(ARCH, QUALITY).eval()
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
     x = torch.rand(batch, 3, H, W, generator=torch.Generator().manual_seed(1234))
+    if ARCH == "mbt2018-mean":
+        table = tp.get_scale_table()
+        fn = lambda sd_, x_: tp.mean_scale_compress_symbols(sd_, x_, table)
+    else:
+        fn = tp.FORWARD["hyperprior" if ARCH == "bmshj2018-hyperprior" else "factorized"]
     with torch.no_grad():
         for _ in range(warmup):
-            tp.hyperprior_forward(sd, x)
+            fn(sd, x)
         t0 = time.perf_counter()
         for _ in range(steps):
-            out = tp.hyperprior_forward(sd, x)
+            out = fn(sd, x)
         dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps * 1e3, cores, tp.bpp(out, batch * H * W)
+    return batch * steps / dt, dt / steps * 1e3, cores, (tp.bpp(out, batch * H * W) if "likelihoods" in out else None)
 
 
 def main():
@@ -135,11 +133,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: the workload's)")
+    ap.add_argument("--workload", default="hyperprior", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro-batch", type=int, default=8, help="images per pipelined micro-batch on the host-buffer path")
     args = ap.parse_args()
 
+    global ARCH, QUALITY, H, W, WORKLOAD
+    ARCH, QUALITY, H, W, default_batch, call, WORKLOAD = WORKLOADS[args.workload]
+    if args.batch is None:
+        args.batch = default_batch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -187,9 +190,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if call == "forward":
+        step_fn = net
+    elif call == "symbols":
+        step_fn = net.symbols_and_indexes
+    else:
+        step_fn = net.compress
+
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
-            out = net(x)
+            out = step_fn(x)
         barrier()
         ops.reset_launch_count()
         sampler = ClockSampler(local_rank)
@@ -199,30 +209,53 @@ def main():
         barrier()
         e0.record()
         for _ in range(args.steps):
-            out = net(x)
+            out = step_fn(x)
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
         launches = ops.launch_count()
-        bpp = net.bpp(out)
+        bpp = net.bpp(out) if call == "forward" else None
 
         # ---- end to end: the host-buffer API (mmcodec.HostPipeline): pinned host images in, pinned host
         #      x_hat + likelihoods out; H2D / kernels / D2H of consecutive micro-batches overlap ----------
-        pipe = mmcodec.HostPipeline(net, micro_batch=args.micro_batch)
-        res = pipe(x_host)
-        torch.cuda.synchronize()
-        for _ in range(2):
-            pipe(x_host)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(args.steps):
+        if call == "forward":
+            pipe = mmcodec.HostPipeline(net, micro_batch=args.micro_batch)
             res = pipe(x_host)
-        f1.record()
-        barrier()
-        ms_e2e = f0.elapsed_time(f1)
-        e2e_bpp = float(sum(torch.log(l).sum() for l in res["likelihoods"].values()) / (-math.log(2) * B * H * W))
-        xh_host, ly_host, lz_host = res["x_hat"], res["likelihoods"]["y"], res["likelihoods"]["z"]
+            torch.cuda.synchronize()
+            for _ in range(2):
+                pipe(x_host)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                res = pipe(x_host)
+            f1.record()
+            barrier()
+            ms_e2e = f0.elapsed_time(f1)
+            e2e_bpp = float(sum(torch.log(l).sum() for l in res["likelihoods"].values()) / (-math.log(2) * B * H * W))
+            d2h = (res["x_hat"].numel() + sum(l.numel() for l in res["likelihoods"].values())) * 4
+            e2e_api = f"mmcodec.HostPipeline(net, micro_batch={args.micro_batch})(x_pinned)"
+        else:
+            # symbol / compress path: pinned host images in, int32 symbols+indexes (or rANS byte strings) on the host out
+            x_dev = torch.empty_like(x)
+
+            def host_step():
+                x_dev.copy_(x_host, non_blocking=True)
+                o = step_fn(x_dev)
+                if call == "symbols":
+                    return {k: v.cpu() for k, v in o.items() if torch.is_tensor(v)}
+                return o
+            host_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                res = host_step()
+            torch.cuda.synchronize()
+            ms_e2e = (time.perf_counter() - t0) * 1e3
+            e2e_bpp = None
+            d2h = (sum(v.numel() * 4 for v in res.values()) if call == "symbols"
+                   else sum(len(s_) for ss in res["strings"] for s_ in ss) + 4 * B * (res["shape"][0] * res["shape"][1]) * 0)
+            e2e_api = f"net.{'symbols_and_indexes' if call == 'symbols' else 'compress'}(x_pinned.to(device)) -> host"
         if rank == 0:
             sampler.stop_flag.set()
             sampler.join(2)
@@ -230,9 +263,9 @@ def main():
         # ---- per-layer device times for the roofline (separate pass, events around each launch) ---
         prof = ops.start_profile()
         for _ in range(2):
-            net(x)
+            step_fn(x)
         torch.cuda.synchronize()
-        layer_ms = ops.stop_profile()
+        layer_prof = ops.stop_profile(with_work=True)
 
     t = torch.tensor([ms_total, ms_e2e], device=dev)
     if world > 1:
@@ -248,30 +281,30 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-    flops = conv_flops_per_image()
-    # dominant kernel = the conv launch with the largest device time in the profiled pass
+    # dominant kernel = the launch with the largest device time in the profiled pass; achieved = its algorithmic FLOPs
+    # (SURVEY.md 8d formulas, computed from the launch's descriptor in mmcodec.ops.conv_flops) / its event-timed duration
     roofline = None
-    if layer_ms:
-        name, ms = max(layer_ms.items(), key=lambda kv: kv[1])
-        key = name.split("|")[0]
-        f = flops.get(key, 0.0) + (flops["igdn"] * {"g_s.0": 64 * 96, "g_s.2": 128 * 192, "g_s.4": 256 * 384}.get(key, 0) / (64 * 96 + 128 * 192 + 256 * 384))
-        achieved = f * B / (ms * 1e-3) / 1e12
+    if layer_prof:
+        name, (ms, f) = max(layer_prof.items(), key=lambda kv: kv[1][0])
+        achieved = f / (ms * 1e-3) / 1e12
+        total_f = sum(v[1] for v in layer_prof.values())
         roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
-                    "ms_per_launch": ms, "layer_ms": {k: round(v, 4) for k, v in layer_ms.items()}}
+                    "ms_per_launch": ms, "flops_per_launch": f,
+                    "step_tflops": total_f / (ms_total / args.steps * 1e-3) / 1e12,
+                    "layer_ms": {k: round(v[0], 4) for k, v in layer_prof.items()}}
 
     value = B * world * args.steps / (ms_total * 1e-3)
     e2e_value = B * world * args.steps / (ms_e2e * 1e-3)
     h2d = x_host.numel() * 4
-    d2h = (xh_host.numel() + ly_host.numel() + lz_host.numel()) * 4
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+    metric = METRIC if args.workload == "hyperprior" else f"img/s ({W}x{H} {ARCH} {call})"
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
             "config": bench_config(B, world),
             "bpp": bpp, "gpu_launches": launches, "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps, "bpp": e2e_bpp,
-                    "api": f"mmcodec.HostPipeline(net, micro_batch={args.micro_batch})(x_pinned)"},
+                    "ms_per_step": ms_e2e / args.steps, "bpp": e2e_bpp, "api": e2e_api},
             "roofline": roofline}
     if world == 1 and not args.no_cpu_baseline:
         with contextlib.redirect_stdout(io.StringIO()):
