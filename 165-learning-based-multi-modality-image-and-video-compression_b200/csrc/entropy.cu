@@ -313,6 +313,86 @@ __global__ void __launch_bounds__(kBlock) eb_kernel(const float *__restrict__ x,
     if (kModeOp == 0 && bits) block_atomic_add(bit_acc, red, bits);
 }
 
+// ---- eval-mode fast path: likelihood table per (channel, integer symbol) ---------------------------------
+// In eval mode x_hat = rint(x - median) + median, so the likelihood is a function of (channel, symbol) only -- the
+// same observation update() uses to tabulate the CDFs (entropy_models.py:422-432).  build: one thread per entry.
+__global__ void __launch_bounds__(kBlock) eb_build_lut_kernel(mmc_eb_params p, float lik_bound, uint32_t C, int half_width,
+                                                              float *__restrict__ lut)
+{
+    const int width = 2 * half_width + 1;
+    int64_t n = (int64_t)C * width;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = (uint32_t)(i / width);
+    const int k = (int)(i - (int64_t)c * width) - half_width;
+    EbRegs r;
+    eb_load(p, c, r);
+    float l = eb_likelihood(r, __fadd_rn((float)k, r.median));
+    if (lik_bound > 0.0f) l = lower_bound_f(l, lik_bound);
+    lut[i] = l;
+}
+
+__device__ __noinline__ float eb_likelihood_slow(const mmc_eb_params &p, uint32_t c, float v, float lik_bound)
+{
+    EbRegs r;
+    eb_load(p, c, r);
+    float l = eb_likelihood(r, v);
+    return lik_bound > 0.0f ? lower_bound_f(l, lik_bound) : l;
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(kBlock) eb_lut_kernel(const float *__restrict__ x, mmc_eb_params p, const float *__restrict__ lut,
+                                                        int half_width, float lik_bound, ChanIndex ci, int64_t n,
+                                                        float *__restrict__ x_hat, __nv_bfloat16 *__restrict__ x_hat_bf16,
+                                                        float *__restrict__ lik, float *__restrict__ bits)
+{
+    __shared__ float red[32];
+    float bit_acc = 0.0f;
+    const int width = 2 * half_width + 1;
+    auto one = [&](int64_t i, float xv, float &v, float &l) {
+        const uint32_t c = ci(i);
+        const float med = __ldg(p.medians + c);
+        const float kf = rintf(__fsub_rn(xv, med));
+        v = __fadd_rn(kf, med);
+        if (fabsf(kf) <= (float)half_width) l = __ldg(lut + (int64_t)c * width + ((int)kf + half_width));
+        else l = eb_likelihood_slow(p, c, v, lik_bound);          // outside the table (also NaN): direct evaluation
+        if (bits) bit_acc -= log2f(l);
+    };
+    int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (kVec) {
+        int64_t n4 = n >> 2;
+        for (int64_t q = tid; q < n4; q += stride) {
+            float4 xv = ldg_stream(reinterpret_cast<const float4 *>(x) + q);
+            float4 v, l;
+            one(4 * q + 0, xv.x, v.x, l.x);
+            one(4 * q + 1, xv.y, v.y, l.y);
+            one(4 * q + 2, xv.z, v.z, l.z);
+            one(4 * q + 3, xv.w, v.w, l.w);
+            reinterpret_cast<float4 *>(x_hat)[q] = v;
+            reinterpret_cast<float4 *>(lik)[q] = l;
+            if (x_hat_bf16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                reinterpret_cast<uint2 *>(x_hat_bf16)[q] = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
+            }
+        }
+        for (int64_t i = (n4 << 2) + tid; i < n; i += stride) {
+            float v, l;
+            one(i, x[i], v, l);
+            x_hat[i] = v; lik[i] = l;
+            if (x_hat_bf16) x_hat_bf16[i] = __float2bfloat16_rn(v);
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += stride) {
+            float v, l;
+            one(i, x[i], v, l);
+            x_hat[i] = v; lik[i] = l;
+            if (x_hat_bf16) x_hat_bf16[i] = __float2bfloat16_rn(v);
+        }
+    }
+    if (bits) block_atomic_add(bit_acc, red, bits);
+}
+
 static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
 static int launch_eb(int op, const float *x, const float *noise, const mmc_eb_params *params, float lik_bound,
@@ -359,10 +439,32 @@ static int launch_eb(int op, const float *x, const float *noise, const mmc_eb_pa
 // -------------------------------------------------------------------------------------------
 // GaussianConditional
 // -------------------------------------------------------------------------------------------
+// erfc with fractional error < 1.2e-7 everywhere (Chebyshev fit of Numerical Recipes' erfcc: t * exp(-z^2 + P(t)),
+// t = 1 / (1 + z/2)): 10 FMAs, one MUFU.RCP and one MUFU.EX2 instead of the ~45-instruction erfcf().  The likelihood
+// is a difference of two such values of magnitude <= 1/2, so this sits inside the cancellation noise (4 ulp of 1/2)
+// that the reference's own fp32 result carries; the kernel then streams at HBM speed instead of being ALU-bound.
+__device__ __forceinline__ float erfc_fast(float x)
+{
+    const float z = fabsf(x);
+    const float t = __frcp_rn(fmaf(0.5f, z, 1.0f));
+    float p = 0.17087277f;
+    p = fmaf(p, t, -0.82215223f);
+    p = fmaf(p, t, 1.48851587f);
+    p = fmaf(p, t, -1.13520398f);
+    p = fmaf(p, t, 0.27886807f);
+    p = fmaf(p, t, -0.18628806f);
+    p = fmaf(p, t, 0.09678418f);
+    p = fmaf(p, t, 0.37409196f);
+    p = fmaf(p, t, 1.00002368f);
+    p = fmaf(p, t, -1.26551223f);
+    const float r = t * __expf(fmaf(-z, z, p));
+    return x >= 0.0f ? r : 2.0f - r;
+}
+
 __device__ __forceinline__ float std_cumulative(float t)
 {
     const float c = -0.70710678118654752440f;  // float(-(2**-0.5)), entropy_models.py:631
-    return 0.5f * erfcf(c * t);
+    return 0.5f * erfc_fast(c * t);
 }
 
 template <bool kMeans, bool kNoise>
@@ -379,9 +481,22 @@ __device__ __forceinline__ void gc_one(float xv, float sv, float mv, float nv, f
     float val = kMeans ? __fsub_rn(v, mv) : v;
     float a = fabsf(val);
     float s = lower_bound_f(sv, scale_bound);
-    float upper = std_cumulative(__fdiv_rn(0.5f - a, s));
-    float lower = std_cumulative(__fdiv_rn(-0.5f - a, s));
-    l = upper - lower;
+    const float inv_s = __frcp_rn(s);            // one reciprocal for both CDF arguments
+    if (s >= 8.0f) {
+        // Wide Gaussians: Phi(u) - Phi(l) is a difference of two numbers near 1/2 (the reference's fp32 result carries
+        // ~2.4e-7 of cancellation noise there).  Integrate the density over the bin instead:
+        //   h phi(m) [1 + h^2 (m^2 - 1)/24 + h^4 (m^4 - 6 m^2 + 3)/1920],  m = -a/s (bin centre), h = 1/s <= 1/8
+        // (truncation < 1e-6 relative for every m whose likelihood is above the 1e-9 floor).
+        const float m = -a * inv_s, m2 = m * m, h2 = inv_s * inv_s;
+        const float phi = 0.3989422804014327f * __expf(-0.5f * m2);
+        const float c2 = (m2 - 1.0f) * (1.0f / 24.0f);
+        const float c4 = fmaf(m2, m2 - 6.0f, 3.0f) * (1.0f / 1920.0f);
+        l = inv_s * phi * fmaf(h2, fmaf(h2, c4, c2), 1.0f);
+    } else {
+        float upper = std_cumulative((0.5f - a) * inv_s);
+        float lower = std_cumulative((-0.5f - a) * inv_s);
+        l = upper - lower;
+    }
     if (lik_bound > 0.0f) l = lower_bound_f(l, lik_bound);
 }
 
@@ -542,6 +657,44 @@ int mmc_eb_forward(const float *x, const float *noise, const mmc_eb_params *para
 {
     return launch_eb(0, x, noise, params, likelihood_bound, outer, C, inner, x_hat, x_hat_bf16, likelihood, bits,
                      (cudaStream_t)stream, "mmc_eb_forward");
+}
+
+int mmc_eb_build_lut(const mmc_eb_params *params, float likelihood_bound, int64_t C, int half_width, float *lut, void *stream)
+{
+    MMC_CHECK_ARG(params && lut && C >= 1 && C <= 65535 && half_width >= 0 && half_width <= 4096, "mmc_eb_build_lut: bad argument");
+    for (int k = 0; k < 5; ++k) MMC_CHECK_ARG(params->matrix[k] && params->bias[k], "mmc_eb_build_lut: NULL parameter block");
+    for (int k = 0; k < 4; ++k) MMC_CHECK_ARG(params->factor[k], "mmc_eb_build_lut: NULL factor block");
+    MMC_CHECK_ARG(params->medians, "mmc_eb_build_lut: medians is NULL");
+    int64_t n = C * (2 * half_width + 1);
+    eb_build_lut_kernel<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(*params, likelihood_bound, (uint32_t)C,
+                                                                                              half_width, lut);
+    MMC_CHECK_LAUNCH("mmc_eb_build_lut");
+    return MMC_OK;
+}
+
+int mmc_eb_forward_lut(const float *x, const mmc_eb_params *params, const float *lut, int half_width, float likelihood_bound,
+                       int64_t outer, int64_t C, int64_t inner, float *x_hat, void *x_hat_bf16, float *likelihood, float *bits,
+                       void *stream)
+{
+    const char *name = "mmc_eb_forward_lut";
+    MMC_CHECK_ARG(params && lut && half_width >= 0, "%s: bad argument", name);
+    MMC_CHECK_ARG(outer >= 0 && C >= 1 && inner >= 1 && C <= 65535 && inner < (1ll << 31), "%s: bad shape", name);
+    for (int k = 0; k < 5; ++k) MMC_CHECK_ARG(params->matrix[k] && params->bias[k], "%s: NULL parameter block", name);
+    for (int k = 0; k < 4; ++k) MMC_CHECK_ARG(params->factor[k], "%s: NULL factor block", name);
+    MMC_CHECK_ARG(params->medians, "%s: medians is NULL", name);
+    int64_t n = outer * C * inner;
+    if (n == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && x_hat && likelihood, "%s: NULL buffer", name);
+    ChanIndex ci{(uint32_t)C, (uint32_t)inner};
+    __nv_bfloat16 *xb = (__nv_bfloat16 *)x_hat_bf16;
+    bool vec = aligned16(x) && aligned16(x_hat) && aligned16(likelihood) && (!xb || (reinterpret_cast<uintptr_t>(xb) & 7u) == 0);
+    int grid = elementwise_grid((n + 3) / 4, kBlock);
+    if (vec)
+        eb_lut_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(x, *params, lut, half_width, likelihood_bound, ci, n, x_hat, xb, likelihood, bits);
+    else
+        eb_lut_kernel<false><<<grid, kBlock, 0, (cudaStream_t)stream>>>(x, *params, lut, half_width, likelihood_bound, ci, n, x_hat, xb, likelihood, bits);
+    MMC_CHECK_LAUNCH(name);
+    return MMC_OK;
 }
 
 int mmc_eb_logits_cumulative(const float *x, const mmc_eb_params *params, int64_t outer, int64_t C, int64_t inner,

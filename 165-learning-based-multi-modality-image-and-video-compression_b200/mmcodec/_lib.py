@@ -45,6 +45,8 @@ _PROTOS = {
     "mmc_build_indexes": (c_int, [c_vp, c_vp, c_int, c_f32, c_i64, c_vp, c_vp]),
     "mmc_channel_indexes": (c_int, [c_i64, c_i64, c_i64, c_vp, c_vp]),
     "mmc_eb_forward": (c_int, [c_vp, c_vp, ctypes.POINTER(EbParams), c_f32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmc_eb_build_lut": (c_int, [ctypes.POINTER(EbParams), c_f32, c_i64, c_int, c_vp, c_vp]),
+    "mmc_eb_forward_lut": (c_int, [c_vp, ctypes.POINTER(EbParams), c_vp, c_int, c_f32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mmc_eb_logits_cumulative": (c_int, [c_vp, ctypes.POINTER(EbParams), c_i64, c_i64, c_i64, c_vp, c_vp]),
     "mmc_gc_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mmc_bits": (c_int, [c_vp, c_i64, c_vp, c_vp]),

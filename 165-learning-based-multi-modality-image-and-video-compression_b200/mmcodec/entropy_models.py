@@ -203,6 +203,16 @@ class EntropyBottleneck(EntropyModel):
                                   [getattr(self, f"_factor{i}") for i in range(4)],
                                   self.quantiles[:, 0, 1])
 
+    def _eval_lut(self):
+        """Likelihood table for the eval fast path, rebuilt whenever a parameter (or its storage / device) changes."""
+        ps = [getattr(self, f"_matrix{i}") for i in range(5)] + [getattr(self, f"_bias{i}") for i in range(5)] + \
+             [getattr(self, f"_factor{i}") for i in range(4)] + [self.quantiles]
+        key = tuple((t._version, t.data_ptr()) for t in ps) + (self._lik_bound(),)
+        if getattr(self, "_lut_key", None) != key:
+            self._lut = ops.eb_build_lut(self._params(), self.channels, self._lik_bound(), self.quantiles.device)
+            self._lut_key = key
+        return self._lut
+
     # ---- once-per-model table construction (entropy_models.py:396-441) -------------------------
     def _logits_cumulative_host(self, inputs: Tensor) -> Tensor:
         logits = inputs
@@ -261,7 +271,7 @@ class EntropyBottleneck(EntropyModel):
             raise ValueError(f"expected {self.channels} channels, got {x.shape[1]}")
         with torch.no_grad():
             noise = torch.empty_like(x, dtype=torch.float32).uniform_(-0.5, 0.5) if training else None
-            return ops.eb_forward(x, self._params(), noise, self._lik_bound())
+            return ops.eb_forward(x, self._params(), noise, self._lik_bound(), lut=None if training else self._eval_lut())
 
     @staticmethod
     def _build_indexes(size, device=None):

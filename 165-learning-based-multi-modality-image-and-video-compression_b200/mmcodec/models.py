@@ -126,7 +126,8 @@ class FactorizedPrior(CompressionModel):
         y = run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32")
         y_l = _nhwc_to_logical(y)
         noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
-        y_hat, y_lik, y_hat_bf16 = ops.eb_forward(y_l, eb._params(), noise, eb._lik_bound(), want_bf16=True)
+        y_hat, y_lik, y_hat_bf16 = ops.eb_forward(y_l, eb._params(), noise, eb._lik_bound(), want_bf16=True,
+                                                  lut=None if self.training else eb._eval_lut())
         x_hat = run_layers(list(self.g_s), y_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nchw_f32")
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik}}
 
@@ -191,7 +192,8 @@ class ScaleHyperprior(CompressionModel):
         y, z = self._analysis(x)
         z_l = _nhwc_to_logical(z)
         z_noise = torch.empty_like(z_l).uniform_(-0.5, 0.5) if self.training else None
-        z_hat, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True)
+        z_hat, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True,
+                                                  lut=None if self.training else eb._eval_lut())
         scales_hat = run_layers(list(self.h_s), z_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nhwc_f32")
         y_l = _nhwc_to_logical(y)
         y_noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
@@ -296,7 +298,8 @@ class MeanScaleHyperprior(ScaleHyperprior):
         y, z = self._analysis(x)
         z_l = _nhwc_to_logical(z)
         z_noise = torch.empty_like(z_l).uniform_(-0.5, 0.5) if self.training else None
-        z_hat, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True)
+        z_hat, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True,
+                                                  lut=None if self.training else eb._eval_lut())
         scales_hat, means_hat = self._gaussian_params(z_hat_bf16.permute(0, 2, 3, 1))
         y_l = _nhwc_to_logical(y)
         y_noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None

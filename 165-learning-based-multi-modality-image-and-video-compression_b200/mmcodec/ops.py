@@ -177,10 +177,23 @@ def make_eb_params(matrices, biases, factors, medians: Optional[Tensor]):
     return p, keep
 
 
+EB_LUT_HALF_WIDTH = 64   # symbols tabulated per channel on the eval fast path: -64 .. 64
+
+
+def eb_build_lut(params, C: int, likelihood_bound: float, device) -> Tensor:
+    """[C][129] table of bound(likelihood(k + median_c)), |k| <= 64 (see mmc_eb_build_lut)."""
+    p, _keep = params
+    lut = torch.empty((C, 2 * EB_LUT_HALF_WIDTH + 1), dtype=torch.float32, device=device)
+    _require_cuda(lut)
+    L.check(L.lib().mmc_eb_build_lut(ctypes.byref(p), float(likelihood_bound), C, EB_LUT_HALF_WIDTH, _ptr(lut), _stream()))
+    return lut
+
+
 def eb_forward(x: Tensor, params, noise: Optional[Tensor] = None, likelihood_bound: float = 1e-9,
-               want_bf16: bool = False, bits: Optional[Tensor] = None):
+               want_bf16: bool = False, bits: Optional[Tensor] = None, lut: Optional[Tensor] = None):
     """EntropyBottleneck.forward on a logical (N, C, *spatial) tensor (entropy_models.py:495-540).
-    Returns (x_hat, likelihood[, x_hat_bf16]) in x's memory layout."""
+    Returns (x_hat, likelihood[, x_hat_bf16]) in x's memory layout.  With `lut` (eval mode only) the likelihood
+    comes from the per-(channel, symbol) table built by eb_build_lut."""
     _require_cuda(x, noise)
     p, _keep = params
     xv, outer, C, inner = _view_oci(x.float())
@@ -188,6 +201,11 @@ def eb_forward(x: Tensor, params, noise: Optional[Tensor] = None, likelihood_bou
     x_hat = torch.empty_like(xv)
     lik = torch.empty_like(xv)
     xb = torch.empty_like(xv, dtype=torch.bfloat16) if want_bf16 else None
+    if lut is not None and nz is None:
+        with _Timed("entropy_bottleneck|eb_lut"):
+            L.check(L.lib().mmc_eb_forward_lut(_ptr(xv), ctypes.byref(p), _ptr(lut), EB_LUT_HALF_WIDTH, float(likelihood_bound),
+                                               outer, C, inner, _ptr(x_hat), _ptr(xb), _ptr(lik), _ptr(bits), _stream()))
+        return (x_hat, lik, xb) if want_bf16 else (x_hat, lik)
     with _Timed("entropy_bottleneck|eb"):
         L.check(L.lib().mmc_eb_forward(_ptr(xv), _ptr(nz), ctypes.byref(p), float(likelihood_bound), outer, C, inner,
                                        _ptr(x_hat), _ptr(xb), _ptr(lik), _ptr(bits), _stream()))

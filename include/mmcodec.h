@@ -128,6 +128,17 @@ MMC_API int mmc_eb_forward(const float *x, const float *noise, const mmc_eb_para
                    int64_t outer, int64_t C, int64_t inner, float *x_hat, void *x_hat_bf16,
                    float *likelihood, float *bits, void *stream);
 
+/* Eval-mode fast path of EntropyBottleneck.forward.  In eval mode x_hat = rint(x - median) + median, so the likelihood
+ * depends only on (channel, integer symbol) -- the observation update() uses for the CDF tables (entropy_models.py:422-432).
+ * mmc_eb_build_lut tabulates bound(likelihood(k + median_c)) for |k| <= half_width into lut[C][2*half_width+1] (caller-owned
+ * device buffer, rebuilt when the parameters change); mmc_eb_forward_lut is mmc_eb_forward(noise = NULL) reading that table
+ * (symbols outside it are evaluated directly), which turns the SFU-bound kernel into an HBM-bound one. */
+MMC_API int mmc_eb_build_lut(const mmc_eb_params *params, float likelihood_bound, int64_t C, int half_width, float *lut,
+                             void *stream);
+MMC_API int mmc_eb_forward_lut(const float *x, const mmc_eb_params *params, const float *lut, int half_width,
+                               float likelihood_bound, int64_t outer, int64_t C, int64_t inner, float *x_hat,
+                               void *x_hat_bf16, float *likelihood, float *bits, void *stream);
+
 /* EntropyBottleneck._logits_cumulative   entropy_models.py:457-477 (used by update() and loss()) */
 MMC_API int mmc_eb_logits_cumulative(const float *x, const mmc_eb_params *params, int64_t outer, int64_t C,
                              int64_t inner, float *logits, void *stream);

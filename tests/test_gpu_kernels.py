@@ -341,3 +341,26 @@ def test_layout_round_trip():
     assert torch.equal(nhwc, x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
     assert torch.equal(ops.nhwc_bf16_to_nchw(nhwc), x.to(torch.bfloat16).float())
     assert torch.equal(ops.to_bf16(x), x.to(torch.bfloat16))
+
+
+def test_eb_eval_lut_equals_direct_evaluation(kernels_golden):
+    """Eval fast path (per-(channel, symbol) likelihood table) vs direct evaluation of the 5-layer CDF model: identical
+    x_hat and likelihoods, including symbols outside the +-64 table (direct fallback), NaN, both memory layouts."""
+    eb = _load_eb(kernels_golden)
+    rs = np.random.RandomState(4)
+    x = (rs.standard_normal((3, 8, 6, 10)) * 30).astype(np.float32)
+    x[0, :, 0, 0] = 500.0
+    x[1, :, 1, 1] = -1e4
+    x[2, 0, 0, 0] = np.nan
+    for xt in (cu(x), cu(x).to(memory_format=torch.channels_last)):
+        a_hat, a_lik = ops.eb_forward(xt, eb._params(), None, 1e-9)
+        bits = torch.zeros(1, device=dev())
+        b_hat, b_lik, b_bf = ops.eb_forward(xt, eb._params(), None, 1e-9, want_bf16=True, bits=bits, lut=eb._eval_lut())
+        assert torch.equal(a_hat.nan_to_num(7.0), b_hat.nan_to_num(7.0))
+        assert torch.equal(a_lik.nan_to_num(7.0), b_lik.nan_to_num(7.0))
+        assert torch.equal(b_bf.float().nan_to_num(7.0), b_hat.to(torch.bfloat16).float().nan_to_num(7.0))
+    # the table is rebuilt when a parameter changes
+    lut0 = eb._eval_lut().clone()
+    with torch.no_grad():
+        eb._bias0.add_(0.25)
+    assert not torch.equal(eb._eval_lut(), lut0)
