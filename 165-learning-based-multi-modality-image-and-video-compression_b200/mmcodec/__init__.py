@@ -4,16 +4,20 @@
     mmcodec.layers           GDN, conv, deconv, LowerBound, NonNegativeParametrizer
     mmcodec.entropy_models   EntropyModel, EntropyBottleneck, GaussianConditional
     mmcodec.models           CompressionModel, FactorizedPrior, ScaleHyperprior, MeanScaleHyperprior
+    mmcodec.models_mm        JointAutoregressiveHierarchicalPriors_R / _D (RGB + depth two-branch codec), ESA, MaskedConv2d
     mmcodec.ops              functional access to every entry point of include/mmcodec.h
 
 All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
 """
-from . import _lib, entropy_models, host_pipeline, layers, models, ops, transforms  # noqa: F401
+from . import _lib, entropy_models, host_pipeline, layers, models, models_mm, ops, transforms  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401
 from ._lib import MmcodecError, build  # noqa: F401
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional  # noqa: F401
 from .layers import GDN, LowerBound, NonNegativeParametrizer, conv, deconv  # noqa: F401
 from .models import (CompressionModel, FactorizedPrior, MeanScaleHyperprior, ScaleHyperprior,  # noqa: F401
                      build_model, get_scale_table)
+
+from .models_mm import (ESA, JointAutoregressiveHierarchicalPriors_D,  # noqa: F401
+                        JointAutoregressiveHierarchicalPriors_R, MaskedConv2d)
 
 __version__ = "0.1.0"

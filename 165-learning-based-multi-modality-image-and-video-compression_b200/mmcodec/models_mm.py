@@ -1,0 +1,294 @@
+"""Multi-modality (RGB + depth / thermal) two-branch codec -- host-side mirror of the fork's own models
+``JointAutoregressiveHierarchicalPriors_R`` (guide / RGB branch, exposes six hidden feature maps) and
+``JointAutoregressiveHierarchicalPriors_D`` (second-modality branch, fuses those maps through
+``eg_ext* -> tran_conv* -> ESA``), compressai/models/google.py:696-1459, with the reference's constructor arguments,
+attribute names and ``state_dict`` keys.
+
+Every conv / deconv (+GDN / IGDN / ReLU / LeakyReLU), the masked context convolution, the 1x1 entropy-parameter
+convs and the entropy stage run on the libmmcodec kernels with NHWC bf16 activations; channel concatenations are
+views-plus-one-copy on the NHWC tensors.  The ESA gate (1x1 -> 3x3 s2 p0 -> maxpool 7/3 -> 3x3 x3 -> bilinear
+upsample -> 1x1 -> sigmoid, google.py:1432-1459) is SURVEY.md section 8f row 3 and still runs on torch ops (bf16,
+channels-last, no layout copies).  ``forward`` is implemented for eval and for the training-mode forward pass
+(uniform-noise quantisation); the autoregressive ``compress`` / ``decompress`` (google.py:836-1003, a serial
+per-pixel Python loop in the reference) are out of scope and raise.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import ops
+from .entropy_models import GaussianConditional
+from .layers import GDN, Conv2d, conv, deconv
+from .models import MeanScaleHyperprior, _nhwc_to_logical
+from .transforms import TransformStack, run_layers
+
+__all__ = ["MaskedConv2d", "ESA", "Encoder1", "Decoder1", "JointAutoregressiveHierarchicalPriors_R",
+           "JointAutoregressiveHierarchicalPriors_D"]
+
+
+class MaskedConv2d(Conv2d):
+    """Masked 2-D convolution (compressai/layers/layers.py:52-78): the mask is folded into the weights, which is
+    exactly what the reference does in place before every forward (``self.weight.data *= self.mask``)."""
+
+    def __init__(self, *args: Any, mask_type: str = "A", **kwargs: Any):
+        super().__init__(*args, **kwargs)
+        if mask_type not in ("A", "B"):
+            raise ValueError(f'Invalid "mask_type" value "{mask_type}"')
+        self.register_buffer("mask", torch.ones_like(self.weight.data))
+        _, _, h, w = self.mask.size()
+        self.mask[:, :, h // 2, w // 2 + (mask_type == "B"):] = 0
+        self.mask[:, :, h // 2 + 1:] = 0
+
+    def _apply_mask(self):
+        with torch.no_grad():
+            self.weight.mul_(self.mask)   # idempotent; bumps the version so the packed copy is refreshed once
+
+    def packed_weight(self, d):
+        if getattr(self, "_masked_version", None) != (self.weight._version, self.weight.data_ptr()):
+            self._apply_mask()
+            self._masked_version = (self.weight._version, self.weight.data_ptr())
+        return super().packed_weight(d)
+
+    def f32_weight(self):
+        self._apply_mask()
+        return super().f32_weight()
+
+
+class ESA(nn.Module):
+    """Enhanced spatial attention gate (google.py:1432-1459).  Stock torch ops."""
+
+    def __init__(self, n_feats: int):
+        super().__init__()
+        f = n_feats // 4
+        self.conv1 = nn.Conv2d(n_feats, f, 1)
+        self.conv_f = nn.Conv2d(f, f, 1)
+        self.conv_max = nn.Conv2d(f, f, 3, padding=1)
+        self.conv2 = nn.Conv2d(f, f, 3, stride=2, padding=0)
+        self.conv3 = nn.Conv2d(f, f, 3, padding=1)
+        self.conv3_ = nn.Conv2d(f, f, 3, padding=1)
+        self.conv4 = nn.Conv2d(f, n_feats, 1)
+        self.sigmoid = nn.Sigmoid()
+        self.relu = nn.ReLU(inplace=True)
+
+    def forward(self, x: Tensor) -> Tensor:
+        c1_ = self.conv1(x)
+        c1 = self.conv2(c1_)
+        v_max = F.max_pool2d(c1, kernel_size=7, stride=3)
+        v_range = self.relu(self.conv_max(v_max))
+        c3 = self.relu(self.conv3(v_range))
+        c3 = self.conv3_(c3)
+        c3 = F.interpolate(c3, (x.size(2), x.size(3)), mode="bilinear", align_corners=False)
+        cf = self.conv_f(c1_)
+        c4 = self.conv4(c3 + cf)
+        return x * self.sigmoid(c4)
+
+    def forward_nhwc_bf16(self, x: Tensor) -> Tensor:
+        """x: (B, H, W, C) bf16 -> same; the torch ops see a channels-last (B, C, H, W) view, so no layout copy."""
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            y = self.forward(x.permute(0, 3, 1, 2))
+        return y.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+
+
+class Encoder1(nn.Module):
+    """google.py:696-718: g_a with its three post-GDN feature maps exposed."""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__()
+        self.g_a_conv1 = conv(3, N, kernel_size=5, stride=2)
+        self.g_a_gdn1 = GDN(N)
+        self.g_a_conv2 = conv(N, N, kernel_size=5, stride=2)
+        self.g_a_gdn2 = GDN(N)
+        self.g_a_conv3 = conv(N, N, kernel_size=5, stride=2)
+        self.g_a_gdn3 = GDN(N)
+        self.g_a_conv4 = conv(N, M, kernel_size=5, stride=2)
+
+    def forward_internal(self, x: Tensor):
+        """fp32 NCHW image -> (y fp32 NHWC, y bf16 NHWC, g1, g2, g3 bf16 NHWC)."""
+        g1 = run_layers([self.g_a_conv1, self.g_a_gdn1], x, "nchw_f32", "nhwc_bf16")
+        g2 = run_layers([self.g_a_conv2, self.g_a_gdn2], g1, "nhwc_bf16", "nhwc_bf16")
+        g3 = run_layers([self.g_a_conv3, self.g_a_gdn3], g2, "nhwc_bf16", "nhwc_bf16")
+        y, y_bf16 = run_layers([self.g_a_conv4], g3, "nhwc_bf16", "nhwc_f32", out2=2)
+        return y, y_bf16, g1, g2, g3
+
+    def forward(self, x):
+        y, _, g1, g2, g3 = self.forward_internal(x)
+        return tuple(_nhwc_to_logical(t) for t in (y, g1, g2, g3))
+
+
+class Decoder1(nn.Module):
+    """google.py:720-742"""
+
+    def __init__(self, N, M, **kwargs):
+        super().__init__()
+        self.g_s_conv1 = deconv(M, N, kernel_size=5, stride=2)
+        self.g_s_gdn1 = GDN(N, inverse=True)
+        self.g_s_conv2 = deconv(N, N, kernel_size=5, stride=2)
+        self.g_s_gdn2 = GDN(N, inverse=True)
+        self.g_s_conv3 = deconv(N, N, kernel_size=5, stride=2)
+        self.g_s_gdn3 = GDN(N, inverse=True)
+        self.g_s_conv4 = deconv(N, 3, kernel_size=5, stride=2)
+
+    def forward_internal(self, y_hat_bf16: Tensor):
+        g1 = run_layers([self.g_s_conv1, self.g_s_gdn1], y_hat_bf16, "nhwc_bf16", "nhwc_bf16")
+        g2 = run_layers([self.g_s_conv2, self.g_s_gdn2], g1, "nhwc_bf16", "nhwc_bf16")
+        g3 = run_layers([self.g_s_conv3, self.g_s_gdn3], g2, "nhwc_bf16", "nhwc_bf16")
+        x_hat = run_layers([self.g_s_conv4], g3, "nhwc_bf16", "nchw_f32")
+        return x_hat, g1, g2, g3
+
+    def forward(self, y_hat):
+        ops._require_cuda(y_hat)
+        x_hat, g1, g2, g3 = self.forward_internal(_to_nhwc_bf16(y_hat))
+        return (x_hat,) + tuple(_nhwc_to_logical(t) for t in (g1, g2, g3))
+
+
+def _to_nhwc_bf16(t: Tensor) -> Tensor:
+    """Logical (B, C, H, W) tensor of any float dtype / layout -> contiguous (B, H, W, C) bf16."""
+    ops._require_cuda(t)
+    if t.dtype == torch.bfloat16 and ops._is_channels_last(t):
+        return t.permute(0, 2, 3, 1)
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return ops.nchw_to_nhwc_bf16(t)
+    return ops.to_bf16(t.float().contiguous(memory_format=torch.channels_last)).permute(0, 2, 3, 1)
+
+
+class _ContextModelMixin:
+    """Entropy stage shared by the two branches (google.py:800-822 / 1196-1211): hyperprior + masked context conv
+    + 1x1 entropy-parameter convs -> (scales, means) -> Gaussian likelihood of y."""
+
+    def _entropy_stage(self, y: Tensor, y_bf16: Tensor):
+        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
+        M = self.M
+        z = run_layers(list(self.h_a), y_bf16, "nhwc_bf16", "nhwc_f32")
+        z_l = _nhwc_to_logical(z)
+        z_noise = torch.empty_like(z_l).uniform_(-0.5, 0.5) if self.training else None
+        _, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True,
+                                              lut=None if self.training else eb._eval_lut())
+        params = run_layers(list(self.h_s), z_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nhwc_bf16")
+        # y_hat = quantize(y, noise | dequantize) WITHOUT means (google.py:805-807): this is what the context model
+        # and the synthesis transform see, while the likelihood below is evaluated at round(y - mu) + mu
+        y_l = _nhwc_to_logical(y)
+        if self.training:
+            y_hat = ops.quantize_noise(y_l, torch.empty_like(y_l).uniform_(-0.5, 0.5))
+        else:
+            y_hat = ops.quantize_dequantize(y_l)
+        y_hat_bf16 = ops.to_bf16(y_hat).permute(0, 2, 3, 1)
+        ctx = run_layers([self.context_prediction], y_hat_bf16, "nhwc_bf16", "nhwc_bf16")
+        gp = run_layers(list(self.entropy_parameters), torch.cat((params, ctx), dim=-1), "nhwc_bf16", "nhwc_f32")
+        scales_hat, means_hat = _nhwc_to_logical(gp[..., :M]), _nhwc_to_logical(gp[..., M:])
+        y_noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
+        _, y_lik = ops.gc_forward(y_l, scales_hat, means_hat, y_noise, gc.lower_bound_scale._sync_bound(), gc._lik_bound())
+        return y_hat_bf16, y_lik, z_lik
+
+    def _init_entropy_stage(self, N, M):
+        self.h_a = TransformStack(conv(M, N, stride=1, kernel_size=3), nn.LeakyReLU(inplace=True),
+                                  conv(N, N, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                  conv(N, N, stride=2, kernel_size=5))
+        self.h_s = TransformStack(deconv(N, M, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                  deconv(M, M * 3 // 2, stride=2, kernel_size=5), nn.LeakyReLU(inplace=True),
+                                  conv(M * 3 // 2, M * 2, stride=1, kernel_size=3))
+        self.entropy_parameters = TransformStack(Conv2d(M * 12 // 3, M * 10 // 3, 1), nn.LeakyReLU(inplace=True),
+                                                 Conv2d(M * 10 // 3, M * 8 // 3, 1), nn.LeakyReLU(inplace=True),
+                                                 Conv2d(M * 8 // 3, M * 6 // 3, 1))
+        self.context_prediction = MaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
+        self.gaussian_conditional = GaussianConditional(None)
+
+    def compress(self, *a, **k):
+        raise NotImplementedError("autoregressive compress() (serial per-pixel context loop, google.py:836-876) is out of scope")
+
+    def decompress(self, *a, **k):
+        raise NotImplementedError("autoregressive decompress() (google.py:920-1003) is out of scope")
+
+
+class JointAutoregressiveHierarchicalPriors_R(_ContextModelMixin, MeanScaleHyperprior):
+    """Guide (RGB) branch, google.py:746-825.  ``forward`` also returns the six hidden maps the second branch fuses;
+    they are logical (B, N, H, W) bf16 tensors in channels-last memory (the kernels' native activation format)."""
+
+    def __init__(self, N=192, M=192, **kwargs):
+        super().__init__(N=N, M=M, **kwargs)
+        self.enc1 = Encoder1(N, M)
+        self.dec1 = Decoder1(N, M)
+        self._init_entropy_stage(N, M)
+        self.N = int(N)
+        self.M = int(M)
+        self._tag_layer_names()
+
+    def forward(self, x):
+        y, y_bf16, ga1, ga2, ga3 = self.enc1.forward_internal(x)
+        y_hat_bf16, y_lik, z_lik = self._entropy_stage(y, y_bf16)
+        x_hat, gs1, gs2, gs3 = self.dec1.forward_internal(y_hat_bf16)
+        hidden = {k: _nhwc_to_logical(v) for k, v in (("ga1", ga1), ("ga2", ga2), ("ga3", ga3),
+                                                    ("gs1", gs1), ("gs2", gs2), ("gs3", gs3))}
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "hidden": hidden}
+
+
+class JointAutoregressiveHierarchicalPriors_D(_ContextModelMixin, MeanScaleHyperprior):
+    """Second-modality (depth / thermal, 1 channel) branch with cross-modality fusion, google.py:1006-1248."""
+
+    def __init__(self, N=192, M=192, **kwargs):
+        super().__init__(N=N, M=M, **kwargs)
+        self.pic2_g_a_conv1 = conv(1, N)
+        self.pic2_g_a_gdn1 = GDN(N)
+        self.pic2_g_a_conv2 = conv(2 * N, N)
+        self.pic2_g_a_gdn2 = GDN(N)
+        self.pic2_g_a_conv3 = conv(2 * N, N)
+        self.pic2_g_a_gdn3 = GDN(N)
+        self.pic2_g_a_conv4 = conv(2 * N, M)
+        self.pic2_g_s_conv1 = deconv(M, N)
+        self.pic2_g_s_gdn1 = GDN(N, inverse=True)
+        self.pic2_g_s_conv2 = deconv(2 * N, N)
+        self.pic2_g_s_gdn2 = GDN(N, inverse=True)
+        self.pic2_g_s_conv3 = deconv(2 * N, N)
+        self.pic2_g_s_gdn3 = GDN(N, inverse=True)
+        self.pic2_g_s_conv4 = deconv(2 * N, 1)
+        for i in range(1, 7):
+            setattr(self, f"tran_conv{i}", conv(2 * N, N, stride=1))
+        self._init_entropy_stage(N, M)
+        self.N = int(N)
+        self.M = int(M)
+        for i in range(1, 7):
+            setattr(self, f"r{i}", nn.ReLU())
+        for i in range(1, 7):
+            setattr(self, f"attention{i}", ESA(N))
+        for i in range(1, 13):
+            setattr(self, f"eg_ext{i}", TransformStack(Conv2d(N, N, stride=1, kernel_size=3, padding=1), nn.ReLU(inplace=True)))
+        self._tag_layer_names()
+
+    def _fuse(self, i: int, x: Tensor, guide: Tensor) -> Tensor:
+        """eg_ext(2i-1)(x), eg_ext(2i)(guide) -> cat -> tran_conv_i -> ESA_i   (google.py:1151-1156 and five repeats)"""
+        e_own = run_layers(list(getattr(self, f"eg_ext{2 * i - 1}")), x, "nhwc_bf16", "nhwc_bf16")
+        e_guide = run_layers(list(getattr(self, f"eg_ext{2 * i}")), guide, "nhwc_bf16", "nhwc_bf16")
+        f = run_layers([getattr(self, f"tran_conv{i}")], torch.cat((e_own, e_guide), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        return getattr(self, f"attention{i}").forward_nhwc_bf16(f)
+
+    def _analysis(self, x, g):
+        """pic2_g_a with the three encoder-side fusions (google.py:1148-1194): fp32 NCHW depth map -> (y fp32, y bf16), NHWC."""
+        a = run_layers([self.pic2_g_a_conv1, self.pic2_g_a_gdn1], x, "nchw_f32", "nhwc_bf16")
+        f1 = self._fuse(1, a, g["ga1"])
+        a = run_layers([self.pic2_g_a_conv2, self.pic2_g_a_gdn2], torch.cat((a, f1), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        f2 = self._fuse(2, a, g["ga2"])
+        a = run_layers([self.pic2_g_a_conv3, self.pic2_g_a_gdn3], torch.cat((a, f2), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        f3 = self._fuse(3, a, g["ga3"])
+        return run_layers([self.pic2_g_a_conv4], torch.cat((a, f3), dim=-1), "nhwc_bf16", "nhwc_f32", out2=2)
+
+    def _synthesis(self, y_hat_bf16, g):
+        """pic2_g_s with the three decoder-side fusions (google.py:1213-1246): y_hat bf16 NHWC -> x_hat fp32 NCHW."""
+        s = run_layers([self.pic2_g_s_conv1, self.pic2_g_s_gdn1], y_hat_bf16, "nhwc_bf16", "nhwc_bf16")
+        f4 = self._fuse(4, s, g["gs1"])
+        s = run_layers([self.pic2_g_s_conv2, self.pic2_g_s_gdn2], torch.cat((s, f4), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        f5 = self._fuse(5, s, g["gs2"])
+        s = run_layers([self.pic2_g_s_conv3, self.pic2_g_s_gdn3], torch.cat((s, f5), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        f6 = self._fuse(6, s, g["gs3"])
+        return run_layers([self.pic2_g_s_conv4], torch.cat((s, f6), dim=-1), "nhwc_bf16", "nchw_f32")
+
+    def forward(self, x, hidden: Dict[str, Tensor]):
+        ops._require_cuda(x)
+        g = {k: _to_nhwc_bf16(hidden[k]) for k in ("ga1", "ga2", "ga3", "gs1", "gs2", "gs3")}
+        y, y_bf16 = self._analysis(x, g)
+        y_hat_bf16, y_lik, z_lik = self._entropy_stage(y, y_bf16)
+        x_hat = self._synthesis(y_hat_bf16, g)
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}

@@ -253,3 +253,93 @@ FORWARD = {"factorized": factorized_forward, "hyperprior": hyperprior_forward, "
 def bpp(out, num_pixels: int) -> float:
     """utils/eval_model/__main__t.py:197-200"""
     return float(sum(torch.log(l).sum() / (-math.log(2) * num_pixels) for l in out["likelihoods"].values()))
+
+
+# ---- multi-modality two-branch codec (compressai/models/google.py:696-1459) ---------------------------------
+def _context_entropy_stage(sd, y):
+    """Hyperprior + masked context model + entropy parameters, eval mode (google.py:800-822, 1196-1211)."""
+    z = _h_a(sd, y, F.leaky_relu)
+    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z)
+    params = _mean_scale_params(sd, z_hat)
+    y_hat = quantize(y, "dequantize")                                  # no means: what the context model / decoder see
+    w = sd["context_prediction.weight"] * sd["context_prediction.mask"]  # layers/layers.py:75-78
+    ctx = F.conv2d(y_hat, w, sd["context_prediction.bias"], padding=2)
+    g = torch.cat((params, ctx), dim=1)
+    for i in (0, 2, 4):
+        g = F.conv2d(g, sd[f"entropy_parameters.{i}.weight"], sd[f"entropy_parameters.{i}.bias"])
+        if i < 4:
+            g = F.leaky_relu(g)
+    scales_hat, means_hat = g.chunk(2, 1)
+    _, y_lik = gc_forward(y, scales_hat, means_hat)
+    return y_hat, y_lik, z_lik, {"z": z, "scales_hat": scales_hat, "means_hat": means_hat}
+
+
+def mm_r_forward(sd, x):
+    """JointAutoregressiveHierarchicalPriors_R.forward (google.py:800-825)."""
+    h = {}
+    a = x
+    for i in (1, 2, 3):
+        a = gdn(sd, f"enc1.g_a_gdn{i}", conv(sd, f"enc1.g_a_conv{i}", a))
+        h[f"ga{i}"] = a
+    y = conv(sd, "enc1.g_a_conv4", a)
+    y_hat, y_lik, z_lik, extra = _context_entropy_stage(sd, y)
+    s = y_hat
+    for i in (1, 2, 3):
+        s = gdn(sd, f"dec1.g_s_gdn{i}", deconv(sd, f"dec1.g_s_conv{i}", s), inverse=True)
+        h[f"gs{i}"] = s
+    x_hat = deconv(sd, "dec1.g_s_conv4", s)
+    return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "hidden": h, "y": y, "y_hat": y_hat, **extra}
+
+
+def esa(sd, name, x):
+    """ESA.forward (google.py:1445-1459)."""
+    c = lambda n, t, **k: F.conv2d(t, sd[f"{name}.{n}.weight"], sd[f"{name}.{n}.bias"], **k)
+    c1_ = c("conv1", x)
+    c1 = c("conv2", c1_, stride=2)
+    v_max = F.max_pool2d(c1, kernel_size=7, stride=3)
+    v_range = F.relu(c("conv_max", v_max, padding=1))
+    c3 = F.relu(c("conv3", v_range, padding=1))
+    c3 = c("conv3_", c3, padding=1)
+    c3 = F.interpolate(c3, (x.size(2), x.size(3)), mode="bilinear", align_corners=False)
+    cf = c("conv_f", c1_)
+    return x * torch.sigmoid(c("conv4", c3 + cf))
+
+
+def mm_fuse(sd, i, own, guide):
+    """One cross-modality fusion block: eg_ext(2i-1)(own), eg_ext(2i)(guide) -> cat -> tran_conv_i -> ESA_i
+    (google.py:1151-1156 and its five repeats)."""
+    e1 = F.relu(F.conv2d(own, sd[f"eg_ext{2 * i - 1}.0.weight"], sd[f"eg_ext{2 * i - 1}.0.bias"], padding=1))
+    e2 = F.relu(F.conv2d(guide, sd[f"eg_ext{2 * i}.0.weight"], sd[f"eg_ext{2 * i}.0.bias"], padding=1))
+    f = conv(sd, f"tran_conv{i}", torch.cat((e1, e2), dim=1), stride=1)
+    return esa(sd, f"attention{i}", f)
+
+
+def mm_d_forward(sd, x, hidden):
+    """JointAutoregressiveHierarchicalPriors_D.forward (google.py:1140-1248)."""
+    fuse = lambda i, own, guide: mm_fuse(sd, i, own, guide)
+
+    a = gdn(sd, "pic2_g_a_gdn1", conv(sd, "pic2_g_a_conv1", x))
+    f = fuse(1, a, hidden["ga1"])
+    a = gdn(sd, "pic2_g_a_gdn2", conv(sd, "pic2_g_a_conv2", torch.cat((a, f), 1)))
+    f = fuse(2, a, hidden["ga2"])
+    a = gdn(sd, "pic2_g_a_gdn3", conv(sd, "pic2_g_a_conv3", torch.cat((a, f), 1)))
+    f = fuse(3, a, hidden["ga3"])
+    y = conv(sd, "pic2_g_a_conv4", torch.cat((a, f), 1))
+    y_hat, y_lik, z_lik, extra = _context_entropy_stage(sd, y)
+    s = gdn(sd, "pic2_g_s_gdn1", deconv(sd, "pic2_g_s_conv1", y_hat), inverse=True)
+    f = fuse(4, s, hidden["gs1"])
+    s = gdn(sd, "pic2_g_s_gdn2", deconv(sd, "pic2_g_s_conv2", torch.cat((s, f), 1)), inverse=True)
+    f = fuse(5, s, hidden["gs2"])
+    s = gdn(sd, "pic2_g_s_gdn3", deconv(sd, "pic2_g_s_conv3", torch.cat((s, f), 1)), inverse=True)
+    f = fuse(6, s, hidden["gs3"])
+    x_hat = deconv(sd, "pic2_g_s_conv4", torch.cat((s, f), 1))
+    return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "y": y, "y_hat": y_hat, **extra}
+
+
+def masked_conv_mask(weight_shape, mask_type: str = "A") -> Tensor:
+    """MaskedConv2d mask buffer (compressai/layers/layers.py:64-72)."""
+    mask = torch.ones(tuple(weight_shape))
+    h, w = mask.shape[-2:]
+    mask[:, :, h // 2, w // 2 + (mask_type == "B"):] = 0
+    mask[:, :, h // 2 + 1:] = 0
+    return mask

@@ -28,7 +28,7 @@ import torch.nn as nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from weights import make_image, make_state_dict  # noqa: E402
+from weights import make_image, make_mm_state_dict, make_state_dict  # noqa: E402
 
 REF_SRC = "/root/reference/CompressAI"
 SCRATCH = os.environ.get("MMC_REF_SCRATCH", "/tmp/ref_probe")
@@ -306,6 +306,33 @@ def model_goldens(out):
         out[f"{tag}_dec_x_hat"] = t2n(d["x_hat"])
 
 
+def mm_goldens(out):
+    """Two-branch RGB + depth codec of the fork (compressai/models/google.py:746-1248), eval forward."""
+    import json
+    from compressai.models.google import (JointAutoregressiveHierarchicalPriors_D,
+                                          JointAutoregressiveHierarchicalPriors_R)
+    x = make_image(1, 128, 192, seed=1234)
+    d = make_image(1, 128, 192, seed=5, C=1)
+    out["x"], out["depth"] = x, d
+    torch.manual_seed(0)
+    net_r = quiet(JointAutoregressiveHierarchicalPriors_R, 192, 192).eval()
+    net_d = quiet(JointAutoregressiveHierarchicalPriors_D, 192, 192).eval()
+    for tag, net, seed in (("r", net_r, 0), ("d", net_d, 1)):
+        shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        load_into(net, make_mm_state_dict(shapes, seed))
+        quiet(net.update, force=True)
+        out[f"{tag}_state_dict"] = np.array(json.dumps({k: [list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()}))
+    with torch.no_grad():
+        o_r = quiet(net_r, torch.from_numpy(x))
+        o_d = quiet(net_d, torch.from_numpy(d), o_r["hidden"])
+    for tag, o in (("r", o_r), ("d", o_d)):
+        out[f"{tag}_x_hat"] = t2n(o["x_hat"])
+        for k, v in o["likelihoods"].items():
+            out[f"{tag}_lik_{k}"] = t2n(v)
+    for k, v in o_r["hidden"].items():
+        out[f"r_hidden_{k}_mean_abs"] = np.array(float(v.abs().mean()))
+
+
 def main():
     import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -315,7 +342,10 @@ def main():
     m = {}
     model_goldens(m)
     np.savez_compressed(os.path.join(HERE, "models.npz"), **m)
-    for f in ("kernels.npz", "models.npz"):
+    mm = {}
+    mm_goldens(mm)
+    np.savez_compressed(os.path.join(HERE, "models_mm.npz"), **mm)
+    for f in ("kernels.npz", "models.npz", "models_mm.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
 
 

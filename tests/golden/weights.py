@@ -111,3 +111,64 @@ def make_image(B: int, H: int, W: int, seed: int = 1234, C: int = 3):
     coarse = rs.uniform(0, 1, (B, C, (H + 7) // 8, (W + 7) // 8))
     img = np.kron(coarse, np.ones((8, 8)))[:, :, :H, :W] * 0.8 + rs.uniform(0, 0.2, (B, C, H, W))
     return img.astype(np.float32)
+
+
+def make_state_dict_like(shapes, seed: int = 0, gains=None):
+    """Deterministic values for ANY of the codec models, driven by the state_dict key names and shapes
+    (``shapes``: {key: shape}).  Conv / deconv weights ~ N(0, gain^2 / fan_in), biases ~ N(0, 0.1^2), GDN beta / gamma and
+    EntropyBottleneck parameters as in ``make_state_dict``; buffers (masks, bounds, CDF tables) are left alone.
+    ``gains`` maps a key prefix to a gain (longest prefix wins, default 1.0)."""
+    gains = gains or {}
+    rs = np.random.RandomState(seed)
+    ped = 2.0 ** -36
+    sd = {}
+
+    def gain_of(key):
+        best, g = -1, 1.0
+        for p, v in gains.items():
+            if key.startswith(p) and len(p) > best:
+                best, g = len(p), v
+        return g
+
+    done_eb = set()
+    for key in sorted(shapes):
+        shp = tuple(shapes[key])
+        leaf = key.rsplit(".", 1)[-1]
+        if leaf in ("mask", "bound", "pedestal", "target", "scale_table", "scale_bound", "_offset", "_quantized_cdf", "_cdf_length"):
+            continue
+        if leaf.startswith(("_matrix", "_bias", "_factor")) or leaf == "quantiles":
+            prefix = key.rsplit(".", 1)[0]
+            if prefix not in done_eb:
+                done_eb.add(prefix)
+                C = shapes[prefix + ".quantiles"][0]
+                _entropy_bottleneck(np.random.RandomState(seed + 17 + len(prefix)), sd, prefix, C)
+            continue
+        if leaf == "beta":
+            sd[key] = np.sqrt(rs.uniform(0.5, 2.0, shp) + ped).astype(np.float32)
+        elif leaf == "gamma":
+            C = shp[0]
+            sd[key] = np.sqrt(0.1 * np.eye(C) + np.abs(rs.standard_normal(shp)) * 0.004 + ped).astype(np.float32)
+        elif leaf == "weight" and len(shp) == 4:
+            is_deconv = "g_s" in key and "conv" in key or key.startswith("h_s.0") or key.startswith("h_s.2") or "deconv" in key
+            fan = shp[0 if is_deconv else 1] * shp[2] * shp[3]
+            if is_deconv:
+                fan /= 4.0
+            sd[key] = (rs.standard_normal(shp) * (gain_of(key) / np.sqrt(fan))).astype(np.float32)
+        elif leaf == "bias":
+            sd[key] = (rs.standard_normal(shp) * 0.1).astype(np.float32)
+    return sd
+
+
+MM_GAINS = {"enc1.g_a_conv4": 5.0, "enc1.": 3.0, "dec1.g_s_conv1": 0.12, "dec1.": 0.5, "dec1.g_s_conv4": 0.3, "h_s.4": 2.0,
+            "pic2_g_a_conv4": 5.0, "pic2_g_a": 3.0, "pic2_g_s_conv1": 0.12, "pic2_g_s": 0.5, "pic2_g_s_conv4": 0.3,
+            "tran_conv": 1.5, "eg_ext": 1.5, "context_prediction": 0.5, "entropy_parameters": 1.5}
+
+
+def make_mm_state_dict(shapes, seed: int = 0):
+    """Weights for JointAutoregressiveHierarchicalPriors_R / _D (two-branch RGB + depth codec): generic recipe plus a
+    positive offset on the scale half of the entropy-parameter head so that predicted scales cover the scale table."""
+    sd = make_state_dict_like(shapes, seed, MM_GAINS)
+    M = shapes["entropy_parameters.4.bias"][0] // 2
+    sd["entropy_parameters.4.bias"][:M] += 2.0
+    sd["entropy_parameters.4.weight"][M:] *= 0.25
+    return sd

@@ -168,3 +168,37 @@ def test_torch_port_models(models_golden, arch, N, M):
     for name in ("y_symbols", "y_indexes", "z_symbols", "z_indexes"):
         assert np.array_equal(c[name].reshape(B, -1).numpy(), g[f"{tag}_{name}"]), name
     assert c["y_symbols"].abs().max() > 5 and c["y_indexes"].unique().numel() > 20  # non-degenerate fixture
+
+
+@pytest.fixture(scope="module")
+def mm_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_mm.npz"))
+
+
+def mm_state_dict(g, tag, seed):
+    """Parameters of the two-branch codec from the key/shape contract the reference run recorded + the mask buffer."""
+    import json
+    from weights import make_mm_state_dict
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(g[f"{tag}_state_dict"])).items()}
+    sd = {k: torch.from_numpy(v) for k, v in make_mm_state_dict(shapes, seed).items()}
+    sd["context_prediction.mask"] = tp.masked_conv_mask(shapes["context_prediction.weight"], "A")
+    return sd
+
+
+def test_torch_port_multimodality(mm_golden):
+    """RGB guide branch + depth branch with cross-modality fusion (google.py:746-1248) vs the reference run."""
+    g = mm_golden
+    torch.set_num_threads(8)
+    sd_r, sd_d = mm_state_dict(g, "r", 0), mm_state_dict(g, "d", 1)
+    with torch.no_grad():
+        o_r = tp.mm_r_forward(sd_r, torch.from_numpy(g["x"]))
+        o_d = tp.mm_d_forward(sd_d, torch.from_numpy(g["depth"]), o_r["hidden"])
+    for tag, o in (("r", o_r), ("d", o_d)):
+        assert np.max(np.abs(o["x_hat"].numpy() - g[f"{tag}_x_hat"])) < 2e-4 * max(1.0, float(np.abs(g[f"{tag}_x_hat"]).max()))
+        for k, l in o["likelihoods"].items():
+            assert rel_err(l.numpy(), g[f"{tag}_lik_{k}"], 1e-9) < 1e-3, (tag, k)
+    for k, v in o_r["hidden"].items():
+        assert abs(float(v.abs().mean()) - float(g[f"r_hidden_{k}_mean_abs"])) < 1e-4 * float(g[f"r_hidden_{k}_mean_abs"])
+    # the fixture is not degenerate: y spans many symbols and scales cover the table
+    assert float(o_d["y"].abs().max()) > 5 and float(o_d["scales_hat"].max()) > 2 and float(o_d["scales_hat"].min()) < 0.5
