@@ -40,6 +40,7 @@ __device__ __forceinline__ float act_apply(float v, int act)
     case MMC_ACT_RELU: return fmaxf(v, 0.0f);
     case MMC_ACT_LEAKY_RELU: return v > 0.0f ? v : 0.01f * v;
     case MMC_ACT_ABS: return fabsf(v);
+    case MMC_ACT_QRELU8: return fminf(fmaxf(v, 0.0f), 255.0f);
     default: return v;
     }
 }
@@ -226,7 +227,7 @@ static int validate_desc(const mmc_conv_desc *d, const char *name)
     MMC_CHECK_ARG(d->out_dtype == MMC_F32 || d->out_dtype == MMC_BF16, "%s: bad out_dtype", name);
     MMC_CHECK_ARG(d->in_layout == MMC_NCHW || d->in_layout == MMC_NHWC || d->in_layout == MMC_NHWC_PAD8, "%s: bad in_layout", name);
     MMC_CHECK_ARG(d->out_layout == MMC_NCHW || d->out_layout == MMC_NHWC, "%s: bad out_layout", name);
-    MMC_CHECK_ARG(d->act >= 0 && d->act <= MMC_ACT_ABS, "%s: bad act", name);
+    MMC_CHECK_ARG(d->act >= 0 && d->act <= MMC_ACT_QRELU8, "%s: bad act", name);
     MMC_CHECK_ARG(d->gdn >= 0 && d->gdn <= MMC_GDN_INVERSE, "%s: bad gdn mode", name);
     return MMC_OK;
 }

@@ -194,6 +194,7 @@ __device__ __forceinline__ float act_tc(float v, int act)
 {
     if (act == MMC_ACT_RELU) return fmaxf(v, 0.0f);
     if (act == MMC_ACT_LEAKY_RELU) return v > 0.0f ? v : 0.01f * v;
+    if (act == MMC_ACT_QRELU8) return fminf(fmaxf(v, 0.0f), 255.0f);
     return v;
 }
 // MUFU.RSQ without the denormal fix-up sequence of rsqrtf(): the GDN norm is beta + sum(gamma x^2) >= beta_min > 0
@@ -1029,7 +1030,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     int rc = make_plan(d, pl, name);
     if (rc) return rc;
     MMC_CHECK_ARG(d->in_dtype == MMC_BF16 && (d->in_layout == MMC_NHWC || d->in_layout == MMC_NHWC_PAD8), "%s: input must be NHWC bf16", name);
-    MMC_CHECK_ARG(d->act >= 0 && d->act <= MMC_ACT_LEAKY_RELU, "%s: bad act", name);
+    MMC_CHECK_ARG((d->act >= 0 && d->act <= MMC_ACT_LEAKY_RELU) || d->act == MMC_ACT_QRELU8, "%s: bad act", name);
     MMC_CHECK_ARG(d->gdn >= 0 && d->gdn <= MMC_GDN_INVERSE, "%s: bad gdn mode", name);
     MMC_CHECK_ARG(d->out2_bf16 >= 0 && d->out2_bf16 <= 2, "%s: bad out2_bf16", name);
     MMC_CHECK_ARG(d->gdn == MMC_GDN_NONE || (beta_eff && gamma_eff_bf16), "%s: GDN needs beta/gamma", name);

@@ -16,7 +16,7 @@ MMC_OK, MMC_EINVAL, MMC_ECUDA, MMC_EUNSUPPORTED, MMC_EDOMAIN = 0, -1, -2, -3, -4
 MEANS_NONE, MEANS_FULL, MEANS_PER_CHANNEL = 0, 1, 2
 F32, BF16 = 0, 1
 NCHW, NHWC, NHWC_PAD8 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_ABS = 0, 1, 2, 3
+ACT_NONE, ACT_RELU, ACT_LEAKY_RELU, ACT_ABS, ACT_QRELU8 = 0, 1, 2, 3, 4
 GDN_NONE, GDN_FORWARD, GDN_INVERSE = 0, 1, 2
 
 c_i64, c_int, c_f32, c_vp = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p
@@ -65,6 +65,10 @@ _PROTOS = {
     "mmc_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "mmc_nhwc_f32_to_nchw_f32": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "mmc_f32_to_bf16": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "mmc_gaussian_volume_workspace": (c_int, [c_i64, c_int, c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "mmc_gaussian_volume": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_int, c_int, c_vp, ctypes.c_size_t, c_vp, c_vp]),
+    "mmc_scale_space_warp": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "mmc_add": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

@@ -153,6 +153,8 @@ def _to_nhwc_bf16(t: Tensor) -> Tensor:
         return t.permute(0, 2, 3, 1)
     if t.dtype == torch.float32 and t.is_contiguous():
         return ops.nchw_to_nhwc_bf16(t)
+    if t.dtype == torch.float32 and ops._is_channels_last(t):
+        return ops.to_bf16(t).permute(0, 2, 3, 1)
     return ops.to_bf16(t.float().contiguous(memory_format=torch.channels_last)).permute(0, 2, 3, 1)
 
 

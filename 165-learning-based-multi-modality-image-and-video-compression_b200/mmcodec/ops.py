@@ -433,6 +433,56 @@ def nhwc_bf16_to_nchw(x: Tensor) -> Tensor:
     return y
 
 
+# ---- scale-space flow (ssf2020) ----------------------------------------------------------------------
+def gaussian_volume(x: Tensor, kernel1d: Tensor, num_levels: int) -> Tensor:
+    """ScaleSpaceFlow.gaussian_volume (models/video/google.py:331-355): (N, C, H, W) fp32 -> (N, C, num_levels + 1, H, W).
+    `kernel1d` is gaussian_kernel1d(k, sigma) (any device; its host copy parametrises the blur kernel)."""
+    _require_cuda(x)
+    x = _f32c(x)
+    N, C, H, W = x.shape
+    k = np.ascontiguousarray(kernel1d.detach().cpu().numpy(), dtype=np.float32)
+    nb = ctypes.c_size_t()
+    L.check(L.lib().mmc_gaussian_volume_workspace(N * C, H, W, ctypes.byref(nb)))
+    ws = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=x.device)
+    vol = torch.empty((N, C, num_levels + 1, H, W), dtype=torch.float32, device=x.device)
+    with _Timed("gaussian_volume|scale_space"):
+        L.check(L.lib().mmc_gaussian_volume(_ptr(x), N * C, H, W, k.ctypes.data, k.size, int(num_levels), _ptr(ws), nb.value,
+                                            _ptr(vol), _stream()))
+    return vol
+
+
+def scale_space_warp(volume: Tensor, motion_info: Tensor, base_x: Tensor, base_y: Tensor, x_cur: Optional[Tensor] = None):
+    """ScaleSpaceFlow.warp_volume (models/video/google.py:357-375) -> x_pred [, x_cur - x_pred]."""
+    _require_cuda(volume, motion_info, base_x, base_y, x_cur)
+    if volume.dim() != 5:
+        raise ValueError(f"Invalid number of dimensions for volume {volume.dim()}")
+    volume, motion_info = _f32c(volume), _f32c(motion_info)
+    N, C, D, H, W = volume.shape
+    if tuple(motion_info.shape) != (N, 3, H, W):
+        raise ValueError("motion_info must be (N, 3, H, W): flow x, flow y, scale field")
+    x_pred = torch.empty((N, C, H, W), dtype=torch.float32, device=volume.device)
+    x_res = None
+    if x_cur is not None:
+        x_cur = _f32c(x_cur)
+        if x_cur.shape != x_pred.shape:
+            raise ValueError("x_cur must have the shape of the prediction")
+        x_res = torch.empty_like(x_pred)
+    with _Timed("warp_volume|scale_space"):
+        L.check(L.lib().mmc_scale_space_warp(_ptr(volume), _ptr(motion_info), _ptr(_f32c(base_x)), _ptr(_f32c(base_y)), N, C, D, H, W,
+                                             _ptr(x_cur), _ptr(x_pred), _ptr(x_res), _stream()))
+    return (x_pred, x_res) if x_cur is not None else x_pred
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    _require_cuda(a, b)
+    a, b = _f32c(a), _f32c(b)
+    if a.shape != b.shape:
+        raise ValueError("add: shape mismatch")
+    out = torch.empty_like(a)
+    L.check(L.lib().mmc_add(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream()))
+    return out
+
+
 # ---- optional per-launch device timing (bench.py roofline pass; off by default) ---------------------
 _profile = None
 

@@ -27,6 +27,14 @@ FORMATS = ("nchw_f32", "nhwc_bf16", "nhwc_f32")
 use_tensor_cores = True
 
 
+class QReLU8(nn.Module):
+    """Marker for QReLU.apply(x, bit_depth=8, beta=100) (layers/layers.py:247-277; forward = clamp(x, 0, 255)) in a fused
+    stack; used by the ssf2020 scale hyper-decoder (models/video/google.py:128-148)."""
+
+    def forward(self, x: Tensor) -> Tensor:   # stand-alone use: same kernel family, no conv in front
+        raise NotImplementedError("QReLU8 is only available fused behind a conv / deconv layer")
+
+
 @dataclass
 class Step:
     conv: nn.Module
@@ -51,6 +59,10 @@ def parse_layers(layers) -> List[Step]:
             if not steps or steps[-1].gdn is not None or abs(m.negative_slope - 0.01) > 1e-12:
                 raise NotImplementedError("only LeakyReLU(0.01) directly after a conv/deconv is fused")
             steps[-1].act = L.ACT_LEAKY_RELU
+        elif isinstance(m, QReLU8):
+            if not steps or steps[-1].gdn is not None:
+                raise NotImplementedError("QReLU must directly follow a conv/deconv layer in a fused stack")
+            steps[-1].act = L.ACT_QRELU8
         elif isinstance(m, nn.ReLU):
             if not steps or steps[-1].gdn is not None:
                 raise NotImplementedError("ReLU must directly follow a conv/deconv layer in a fused stack")

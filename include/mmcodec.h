@@ -62,7 +62,9 @@ enum mmc_act {
     MMC_ACT_NONE = 0,
     MMC_ACT_RELU = 1,       /* nn.ReLU        models/google.py:256,264 */
     MMC_ACT_LEAKY_RELU = 2, /* nn.LeakyReLU() models/google.py:365,373 (slope 0.01) */
-    MMC_ACT_ABS = 3         /* torch.abs(y)   models/google.py:283 (only for the secondary output) */
+    MMC_ACT_ABS = 3,        /* torch.abs(y)   models/google.py:283 (only for the secondary output) */
+    MMC_ACT_QRELU8 = 4      /* QReLU(bit_depth=8) forward: clamp(v, 0, 255)   layers/layers.py:268-277, used by the
+                               ssf2020 scale hyper-decoder, models/video/google.py:128-148 */
 };
 
 enum mmc_gdn_mode { MMC_GDN_NONE = 0, MMC_GDN_FORWARD = 1, MMC_GDN_INVERSE = 2 };
@@ -243,6 +245,30 @@ MMC_API int mmc_nchw_f32_to_nhwc_bf16(const float *x, int64_t B, int C, int64_t 
 MMC_API int mmc_nhwc_bf16_to_nchw_f32(const void *x, int64_t B, int C, int64_t HW, float *y, void *stream);
 MMC_API int mmc_nhwc_f32_to_nchw_f32(const float *x, int64_t B, int C, int64_t HW, float *y, void *stream);
 MMC_API int mmc_f32_to_bf16(const float *x, int64_t n, void *y, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Scale-space flow prediction of the ssf2020 video codec (HBM-bound stencil / gather kernels, planar fp32)
+ * ------------------------------------------------------------------------------------------- */
+
+/* ScaleSpaceFlow.gaussian_volume   compressai/models/video/google.py:331-355 (+ gaussian_blur / gaussian_kernel2d,
+ * compressai/models/utils.py:155-189): x [planes][H][W] -> volume [planes][num_levels + 1][H][W].  `kernel1d_host` is the
+ * HOST copy of gaussian_kernel1d(ksize, sigma) (computed by the caller exactly as the reference does; ksize odd, <= 33);
+ * H and W must be multiples of 2^(num_levels - 1).  Workspace size from mmc_gaussian_volume_workspace. */
+MMC_API int mmc_gaussian_volume_workspace(int64_t planes, int H, int W, size_t *bytes);
+MMC_API int mmc_gaussian_volume(const float *x, int64_t planes, int H, int W, const float *kernel1d_host, int ksize,
+                                int num_levels, void *workspace, size_t ws_bytes, float *volume, void *stream);
+
+/* ScaleSpaceFlow.warp_volume / forward_prediction   models/video/google.py:357-382: trilinear F.grid_sample of the
+ * volume [N][C][D][H][W] at (base grid + flow, scale_field), border padding, align_corners=False.  `motion_info` is the
+ * motion decoder's output [N][3][H][W] (flow x, flow y, scale field); base_x [W] / base_y [H] are the rows of
+ * F.affine_grid(identity, align_corners=False) (utils.py:192-195).  Writes x_pred [N][C][H][W] and, when x_res is
+ * given, the residual x_cur - x_pred (google.py:262) in the same pass. */
+MMC_API int mmc_scale_space_warp(const float *volume, const float *motion_info, const float *base_x, const float *base_y,
+                                 int64_t N, int C, int D, int H, int W, const float *x_cur, float *x_pred, float *x_res,
+                                 void *stream);
+
+/* out = a + b (x_rec = x_pred + x_res_hat, models/video/google.py:271) */
+MMC_API int mmc_add(const float *a, const float *b, int64_t n, float *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -343,3 +343,93 @@ def masked_conv_mask(weight_shape, mask_type: str = "A") -> Tensor:
     mask[:, :, h // 2, w // 2 + (mask_type == "B"):] = 0
     mask[:, :, h // 2 + 1:] = 0
     return mask
+
+
+# ---- ssf2020 video codec (compressai/models/video/google.py:55-508) --------------------------------------------
+def _ssf_stack(sd, prefix, x, transposed, n, act=F.relu):
+    """Encoder / Decoder / HyperEncoder / HyperDecoder nn.Sequential: conv at indexes 0, 2, 4[, 6] with ReLU between."""
+    op = deconv if transposed else conv
+    for i in range(n):
+        x = op(sd, f"{prefix}.{2 * i}", x)
+        if i < n - 1:
+            x = act(x)
+    return x
+
+
+def ssf_hyperprior(sd, p, y):
+    """ScaleSpaceFlow.Hyperprior.forward, eval mode (google.py:171-180)."""
+    z = _ssf_stack(sd, f"{p}.hyper_encoder", y, False, 3)
+    z_hat, z_lik = eb_forward(sd, f"{p}.entropy_bottleneck", z)
+    s = z_hat
+    for i in (1, 2, 3):
+        s = deconv(sd, f"{p}.hyper_decoder_scale.deconv{i}", s).clamp(min=0, max=255)   # QReLU fwd, layers/layers.py:277
+    means = _ssf_stack(sd, f"{p}.hyper_decoder_mean", z_hat, True, 3)
+    y_hat, y_lik = gc_forward(y, s, means)          # == quantize_ste(y - means) + means in the forward pass
+    return y_hat, {"y": y_lik, "z": z_lik}, {"z": z, "z_hat": z_hat, "scales": s, "means": means}
+
+
+def gaussian_volume(x, sigma: float, num_levels: int):
+    """google.py:331-355 with models/utils.py:155-189"""
+    k = 2 * int(math.ceil(3 * sigma)) + 1
+    khalf = (k - 1) / 2.0
+    t = torch.linspace(-khalf, khalf, steps=k, dtype=x.dtype)
+    pdf = torch.exp(-0.5 * (t / sigma).pow(2))
+    k1 = pdf / pdf.sum()
+    kernel = torch.mm(k1[:, None], k1[None, :])
+
+    def blur(v):
+        pad = k // 2
+        v = F.pad(v, (pad, pad, pad, pad), mode="replicate")
+        return F.conv2d(v, kernel.expand(v.size(1), 1, k, k), groups=v.size(1))
+
+    volume = [x.unsqueeze(2)]
+    x = blur(x)
+    volume += [x.unsqueeze(2)]
+    for i in range(1, num_levels):
+        x = F.avg_pool2d(x, kernel_size=(2, 2), stride=(2, 2))
+        x = blur(x)
+        interp = x
+        for _ in range(0, i):
+            interp = F.interpolate(interp, scale_factor=2, mode="bilinear", align_corners=False)
+        volume.append(interp.unsqueeze(2))
+    return torch.cat(volume, dim=2)
+
+
+def warp_volume(volume, flow, scale_field):
+    """google.py:357-375"""
+    N, C, _, H, W = volume.size()
+    theta = torch.eye(2, 3).unsqueeze(0).expand(N, 2, 3)
+    grid = F.affine_grid(theta, (N, C, H, W), align_corners=False)
+    update_grid = grid + flow.permute(0, 2, 3, 1).float()
+    update_scale = scale_field.permute(0, 2, 3, 1).float()
+    volume_grid = torch.cat((update_grid, update_scale), dim=-1).unsqueeze(1)
+    out = F.grid_sample(volume.float(), volume_grid, padding_mode="border", align_corners=False)
+    return out.squeeze(2)
+
+
+def ssf_forward(sd, frames, num_levels: int = 5, sigma0: float = 1.5):
+    """ScaleSpaceFlow.forward, eval mode (google.py:212-273)."""
+    trace = []
+    y = _ssf_stack(sd, "img_encoder", frames[0], False, 4)
+    y_hat, lik, ex = ssf_hyperprior(sd, "img_hyperprior", y)
+    x_ref = _ssf_stack(sd, "img_decoder", y_hat, True, 4)
+    recs, liks = [x_ref], [{"keyframe": lik}]
+    trace.append({"y": y, "y_hat": y_hat, **ex})
+    for x_cur in frames[1:]:
+        y_m = _ssf_stack(sd, "motion_encoder", torch.cat((x_cur, x_ref), dim=1), False, 4)
+        y_m_hat, lik_m, ex_m = ssf_hyperprior(sd, "motion_hyperprior", y_m)
+        motion_info = _ssf_stack(sd, "motion_decoder", y_m_hat, True, 4)
+        flow, scale_field = motion_info.chunk(2, dim=1)
+        volume = gaussian_volume(x_ref, sigma0, num_levels)
+        x_pred = warp_volume(volume, flow, scale_field)
+        x_res = x_cur - x_pred
+        y_r = _ssf_stack(sd, "res_encoder", x_res, False, 4)
+        y_r_hat, lik_r, ex_r = ssf_hyperprior(sd, "res_hyperprior", y_r)
+        x_res_hat = _ssf_stack(sd, "res_decoder", torch.cat((y_r_hat, y_m_hat), dim=1), True, 4)
+        trace.append({"x_ref": x_ref, "y_motion": y_m, "y_motion_hat": y_m_hat, "motion_info": motion_info, "volume": volume,
+                      "x_pred": x_pred, "x_res": x_res, "y_res": y_r, "y_res_hat": y_r_hat, "x_res_hat": x_res_hat,
+                      "motion": ex_m, "residual": ex_r})
+        x_ref = x_pred + x_res_hat
+        recs.append(x_ref)
+        liks.append({"motion": lik_m, "residual": lik_r})
+    return {"x_hat": recs, "likelihoods": liks, "trace": trace}

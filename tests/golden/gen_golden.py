@@ -28,7 +28,7 @@ import torch.nn as nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from weights import make_image, make_mm_state_dict, make_state_dict  # noqa: E402
+from weights import make_image, make_mm_state_dict, make_ssf_state_dict, make_state_dict  # noqa: E402
 
 REF_SRC = "/root/reference/CompressAI"
 SCRATCH = os.environ.get("MMC_REF_SCRATCH", "/tmp/ref_probe")
@@ -333,20 +333,70 @@ def mm_goldens(out):
         out[f"r_hidden_{k}_mean_abs"] = np.array(float(v.abs().mean()))
 
 
+def make_frames(n: int, H: int, W: int, seed: int = 21):
+    """A short synthetic sequence: one textured image translated by a few pixels per frame plus a little noise."""
+    base = make_image(1, H + 32, W + 32, seed=seed)[0]
+    rs = np.random.RandomState(seed + 1)
+    frames = []
+    for t in range(n):
+        dy, dx = 2 * t, 3 * t
+        f = base[:, 8 + dy: 8 + dy + H, 8 + dx: 8 + dx + W] + rs.uniform(-0.01, 0.01, (3, H, W))
+        frames.append(np.clip(f, 0, 1).astype(np.float32)[None])
+    return frames
+
+
+def ssf_goldens(out):
+    """ssf2020 video codec (compressai/models/video/google.py), eval forward on a 3-frame 128x256 sequence, plus the
+    scale-space prediction on its own (gaussian_volume / warp_volume) and the per-frame compressed sizes."""
+    import json
+    from compressai.models.video.google import ScaleSpaceFlow
+    frames = make_frames(3, 128, 256)
+    torch.manual_seed(0)
+    net = quiet(ScaleSpaceFlow).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    load_into(net, make_ssf_state_dict(shapes, 0))
+    quiet(net.update, force=True)
+    out["state_dict"] = np.array(json.dumps({k: [list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()}))
+    fr = [torch.from_numpy(f) for f in frames]
+    with torch.no_grad():
+        o = quiet(net, fr)
+        vol = net.gaussian_volume(o["x_hat"][0], net.sigma0, net.num_levels)
+        y_m = net.motion_encoder(torch.cat((fr[1], o["x_hat"][0]), dim=1))
+        y_m_hat, _ = net.motion_hyperprior(y_m)
+        motion_info = net.motion_decoder(y_m_hat)
+        x_pred = net.forward_prediction(o["x_hat"][0], motion_info)
+        strings, shapes_c = quiet(net.compress, fr)
+        dec = quiet(net.decompress, strings, shapes_c)
+    for t, f in enumerate(frames):
+        out[f"frame_{t}"] = f
+        out[f"x_hat_{t}"] = t2n(o["x_hat"][t])
+        for part, lk in o["likelihoods"][t].items():
+            for k, v in lk.items():
+                out[f"lik_{t}_{part}_{k}"] = t2n(v)
+        out[f"dec_max_abs_diff_{t}"] = np.array(float((dec[t] - o["x_hat"][t]).abs().max()))
+    out["volume_sub"] = t2n(vol[:, :, :, ::3, ::5])   # strided subsample: pins every level without storing 2.3 MB
+    out["motion_info"] = t2n(motion_info)
+    out["x_pred"] = t2n(x_pred)
+    out["bytes_keyframe"] = np.array([len(s[0]) for s in strings[0]])
+    out["bytes_inter_1"] = np.array([len(strings[1][k][i][0]) for k in ("motion", "residual") for i in range(2)])
+    flow = motion_info[:, :2]
+    print("ssf stats: flow px", float(flow[:, 0].abs().mean() * 128), float(flow[:, 0].abs().max() * 128), "scale z", float(motion_info[:, 2].min()),
+          float(motion_info[:, 2].max()), "x_hat range", float(o["x_hat"][2].min()), float(o["x_hat"][2].max()))
+    for t in range(3):
+        for part, lk in o["likelihoods"][t].items():
+            print(t, part, {k: (float(torch.log2(v).sum() / -(128 * 256)), float((v <= 1.0001e-9).float().mean())) for k, v in lk.items()})
+
+
 def main():
     import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    k = {}
-    kernel_goldens(k)
-    np.savez_compressed(os.path.join(HERE, "kernels.npz"), **k)
-    m = {}
-    model_goldens(m)
-    np.savez_compressed(os.path.join(HERE, "models.npz"), **m)
-    mm = {}
-    mm_goldens(mm)
-    np.savez_compressed(os.path.join(HERE, "models_mm.npz"), **mm)
-    for f in ("kernels.npz", "models.npz", "models_mm.npz"):
-        print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
+    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf"]
+    gens = {"kernels": kernel_goldens, "models": model_goldens, "models_mm": mm_goldens, "models_ssf": ssf_goldens}
+    for name in which:
+        d = {}
+        gens[name](d)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **d)
+        print(f"{name}.npz", os.path.getsize(os.path.join(HERE, f"{name}.npz")) // 1024, "KiB")
 
 
 if __name__ == "__main__":

@@ -149,7 +149,8 @@ def make_state_dict_like(shapes, seed: int = 0, gains=None):
             C = shp[0]
             sd[key] = np.sqrt(0.1 * np.eye(C) + np.abs(rs.standard_normal(shp)) * 0.004 + ped).astype(np.float32)
         elif leaf == "weight" and len(shp) == 4:
-            is_deconv = "g_s" in key and "conv" in key or key.startswith("h_s.0") or key.startswith("h_s.2") or "deconv" in key
+            is_deconv = ("g_s" in key and "conv" in key or key.startswith("h_s.0") or key.startswith("h_s.2") or "deconv" in key
+                         or "decoder" in key)
             fan = shp[0 if is_deconv else 1] * shp[2] * shp[3]
             if is_deconv:
                 fan /= 4.0
@@ -171,4 +172,28 @@ def make_mm_state_dict(shapes, seed: int = 0):
     M = shapes["entropy_parameters.4.bias"][0] // 2
     sd["entropy_parameters.4.bias"][:M] += 2.0
     sd["entropy_parameters.4.weight"][M:] *= 0.25
+    return sd
+
+
+SSF_GAINS = {"img_encoder.6": 15.0, "res_encoder.6": 25.0, "motion_encoder.6": 16.0,
+             "img_decoder.6": 0.1, "res_decoder.6": 0.04, "motion_decoder.6": 0.25,
+             "img_hyperprior.hyper_encoder.4": 6.0, "res_hyperprior.hyper_encoder.4": 6.0, "motion_hyperprior.hyper_encoder.4": 6.0,
+             "img_hyperprior.hyper_decoder_scale.deconv3": 4.0, "res_hyperprior.hyper_decoder_scale.deconv3": 4.0,
+             "motion_hyperprior.hyper_decoder_scale.deconv3": 4.0}
+
+
+def make_ssf_state_dict(shapes, seed: int = 0):
+    """Weights for ScaleSpaceFlow: generic recipe; gains chosen so that latents span tens of symbols, predicted scales
+    cover the scale table (a few per cent of the likelihoods on the 1e-9 floor), reconstructions stay image-like over the
+    recurrence, the decoded flow is a few pixels and the scale field covers all levels of the volume."""
+    sd = make_state_dict_like(shapes, seed, SSF_GAINS)
+    # motion decoder output = (flow x, flow y, scale field) in NORMALISED grid units: keep the flow at a few per cent of
+    # the frame and spread the scale field over about [-0.9, 0.9] (volume index 3 z + 2.5, 6 levels)
+    w = sd["motion_decoder.6.weight"]            # (Cin, 3, 5, 5)
+    w[:, :2] *= 0.03
+    w[:, 2] *= 1.2
+    sd["motion_decoder.6.bias"] = np.array([0.01, -0.015, 0.1], dtype=np.float32)
+    for hp in ("img_hyperprior", "res_hyperprior", "motion_hyperprior"):
+        sd[f"{hp}.hyper_decoder_scale.deconv3.bias"] += 3.0     # scales are QReLU outputs: keep most of them positive
+    sd["img_decoder.6.bias"] = np.full(3, 0.45, dtype=np.float32)
     return sd

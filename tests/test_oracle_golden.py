@@ -202,3 +202,38 @@ def test_torch_port_multimodality(mm_golden):
         assert abs(float(v.abs().mean()) - float(g[f"r_hidden_{k}_mean_abs"])) < 1e-4 * float(g[f"r_hidden_{k}_mean_abs"])
     # the fixture is not degenerate: y spans many symbols and scales cover the table
     assert float(o_d["y"].abs().max()) > 5 and float(o_d["scales_hat"].max()) > 2 and float(o_d["scales_hat"].min()) < 0.5
+
+
+@pytest.fixture(scope="module")
+def ssf_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_ssf.npz"))
+
+
+def ssf_state_dict(g):
+    import json
+    from weights import make_ssf_state_dict
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(g["state_dict"])).items()}
+    return {k: torch.from_numpy(v) for k, v in make_ssf_state_dict(shapes, 0).items()}
+
+
+def test_torch_port_ssf2020(ssf_golden):
+    """ScaleSpaceFlow eval forward (keyframe + 2 inter frames), gaussian_volume and warp_volume vs the reference run."""
+    g = ssf_golden
+    torch.set_num_threads(8)
+    sd = ssf_state_dict(g)
+    frames = [torch.from_numpy(g[f"frame_{t}"]) for t in range(3)]
+    with torch.no_grad():
+        o = tp.ssf_forward(sd, frames)
+    for t in range(3):
+        assert np.max(np.abs(o["x_hat"][t].numpy() - g[f"x_hat_{t}"])) < 1e-4
+        for part, lk in o["likelihoods"][t].items():
+            for k, v in lk.items():
+                assert rel_err(v.numpy(), g[f"lik_{t}_{part}_{k}"], 1e-9) < 1e-3, (t, part, k)
+        assert float(g[f"dec_max_abs_diff_{t}"]) < 1e-4     # the reference's own decompress(compress()) reproduces forward
+    T = o["trace"][1]
+    assert np.max(np.abs(T["volume"][:, :, :, ::3, ::5].numpy() - g["volume_sub"])) < 1e-5
+    assert np.max(np.abs(T["motion_info"].numpy() - g["motion_info"])) < 1e-4
+    assert np.max(np.abs(T["x_pred"].numpy() - g["x_pred"])) < 1e-4
+    mi = g["motion_info"]
+    assert np.abs(mi[:, 0]).max() * 128 > 3 and (mi[:, 2] * 3 + 2.5).min() < 0 and (mi[:, 2] * 3 + 2.5).max() > 5   # non-degenerate
