@@ -503,6 +503,8 @@ def stop_profile(with_work: bool = False):
     for name, e0, e1, flops in rec:
         acc.setdefault(name, []).append(e0.elapsed_time(e1))
         work[name] = flops
+    if with_work == "total":    # {name: (total ms, total FLOPs, launches)} over everything recorded
+        return {k: (sum(v), work[k] * len(v), len(v)) for k, v in acc.items()}
     if with_work:
         return {k: (sum(v) / len(v), work[k]) for k, v in acc.items()}
     return {k: sum(v) / len(v) for k, v in acc.items()}

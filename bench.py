@@ -52,6 +52,13 @@ WORKLOADS = {
     "mbt-mean-compress": ("mbt2018-mean", 6, 1088, 1920, 8, "compress",
                           "mbt2018-mean q6 compress() incl. host rANS coding, 1920x1080 padded to 1088"),
 }
+# workloads with their own input structure (a GOP of frames / an RGB + depth pair): measured by bench_other()
+OTHER_WORKLOADS = {
+    "ssf2020": ("ssf2020 video codec eval forward, one GOP of 8 frames 1920x1152 per GPU, frames in order "
+                "(BASELINE.json configs[4]); unit = frames"),
+    "mm-forward": ("RGB + depth two-branch codec (JointAutoregressiveHierarchicalPriors_R/_D) eval forward, 768x512 pairs "
+                   "(forward half of BASELINE.json configs[3]); unit = pairs"),
+}
 ARCH, QUALITY, H, W = "bmshj2018-hyperprior", 4, 512, 768
 WORKLOAD = WORKLOADS["hyperprior"][6]
 
@@ -127,6 +134,107 @@ def cpu_reference_throughput(batch: int, steps: int, warmup: int):
     return batch * steps / dt, dt / steps * 1e3, cores, (tp.bpp(out, batch * H * W) if "likelihoods" in out else None)
 
 
+def bench_other(args):
+    """For-the-record lines of the GOP / pair workloads (same timing rules; not the driver's headline run)."""
+    import torch
+    import torch.distributed as dist
+    import mmcodec
+    from mmcodec import ops
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"reference arm is implemented for the image workloads only, not {args.workload}"}))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    if args.workload == "ssf2020":
+        net = mmcodec.ScaleSpaceFlow().eval()
+        net.update()
+        net = net.to(dev)
+        units = args.batch or 8
+        host = [torch.rand(1, 3, 1152, 1920, generator=gen).pin_memory() for _ in range(units)]
+        step = lambda xs: net(xs)["x_hat"][-1]
+        e2e_out = lambda o: [t.cpu() for t in o["x_hat"]]
+        run = lambda xs: net(xs)
+    else:
+        net_r = mmcodec.JointAutoregressiveHierarchicalPriors_R(192, 192).eval()
+        net_d = mmcodec.JointAutoregressiveHierarchicalPriors_D(192, 192).eval()
+        for n in (net_r, net_d):
+            n.update()
+            n.to(dev)
+        units = args.batch or 8
+        host = [torch.rand(units, 3, 512, 768, generator=gen).pin_memory(), torch.rand(units, 1, 512, 768, generator=gen).pin_memory()]
+
+        def run(xs):
+            o_r = net_r(xs[0])
+            return {"r": o_r, "d": net_d(xs[1], o_r["hidden"])}
+        e2e_out = lambda o: [o["r"]["x_hat"].cpu(), o["d"]["x_hat"].cpu()]
+    xs = [t.to(dev) for t in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            run(xs)
+        barrier()
+        ops.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            run(xs)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ops.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_out(run([t.to(dev, non_blocking=True) for t in host]))
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        ops.start_profile()
+        run(xs)
+        prof = ops.stop_profile(with_work="total")
+        # launch-bound workloads: the same forward replayed as ONE CUDA graph (mmcodec.GraphedForward)
+        graphed = mmcodec.GraphedForward(run, xs)
+        graphed(xs)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            graphed(xs)
+        g1.record()
+        barrier()
+        ms_graph = g0.elapsed_time(g1)
+    t = torch.tensor([ms, ms_e2e, ms_graph], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    ms_eager, ms_e2e, ms = float(t[0]), float(t[1]), float(t[2])
+    total_f = sum(v[1] for v in prof.values())
+    kernel_ms = sum(v[0] for v in prof.values())
+    top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]
+    print(json.dumps({"metric": f"{'frames' if args.workload == 'ssf2020' else 'pairs'}/s ({args.workload})", "value": units * world * args.steps / (ms * 1e-3),
+                      "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                      "launch_mode": "one CUDA graph per step (mmcodec.GraphedForward)", "ms_per_step_eager": ms_eager / args.steps,
+                      "sum_of_kernel_ms": kernel_ms,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": OTHER_WORKLOADS[args.workload], "units_per_gpu": units, "weights": "random init"},
+                      "gpu_launches": launches,
+                      "e2e": {"value": units * world * args.steps / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
+                              "h2d_bytes_per_step": sum(t_.numel() * 4 for t_ in host), "d2h_bytes_per_step": sum(t_.numel() * 4 for t_ in host)},
+                      "roofline": {"bound": "tensor", "step_tflops": total_f / (ms / args.steps * 1e-3) / 1e12, "conv_flops_per_step": total_f,
+                                   "top_kernels_total_ms_x_launches": {k: [round(v[0], 4), v[2]] for k, v in top}}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -134,11 +242,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: the workload's)")
-    ap.add_argument("--workload", default="hyperprior", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="hyperprior", choices=sorted(WORKLOADS) + sorted(OTHER_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro-batch", type=int, default=8, help="images per pipelined micro-batch on the host-buffer path")
     args = ap.parse_args()
 
+    if args.workload in OTHER_WORKLOADS:
+        return bench_other(args)
     global ARCH, QUALITY, H, W, WORKLOAD
     ARCH, QUALITY, H, W, default_batch, call, WORKLOAD = WORKLOADS[args.workload]
     if args.batch is None:
