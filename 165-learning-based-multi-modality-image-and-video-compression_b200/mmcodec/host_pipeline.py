@@ -28,24 +28,48 @@ def _pinned_like(shape, channels_last: bool) -> Tensor:
 
 
 class HostPipeline:
-    def __init__(self, net, micro_batch: int = 16, device: Optional[torch.device] = None):
+    def __init__(self, net, micro_batch: int = 8, device: Optional[torch.device] = None, use_graphs: bool = True):
         self.net = net
         self.micro_batch = int(micro_batch)
         self.device = device or next(net.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("HostPipeline needs the model on a CUDA device (no CPU path)")
+        self.use_graphs = bool(use_graphs)
         self.s_h2d = torch.cuda.Stream(self.device)
         self.s_run = torch.cuda.Stream(self.device)
         self.s_d2h = torch.cuda.Stream(self.device)
         self._slots = None
+        self._graphs = None      # per slot: (CUDAGraph, captured output dict) -- no allocator traffic, one launch per micro-batch
         self._out: Optional[Dict[str, Tensor]] = None
 
     def _buffers(self, x_host: Tensor):
         mb = min(self.micro_batch, x_host.shape[0])
         shape = (mb,) + tuple(x_host.shape[1:])
         if self._slots is None or tuple(self._slots[0].shape) != shape:
-            self._slots = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._slots = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._graphs = None
+        if self.use_graphs and self._graphs is None:
+            graphs = []
+            with torch.cuda.stream(self.s_run), torch.no_grad():
+                self.net(self._slots[0])     # fills the per-parameter caches (packed weights, LUTs) outside the capture
+                torch.cuda.synchronize(self.device)
+                for k in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.s_run):
+                        o = self.net(self._slots[k])
+                    graphs.append((g, o))
+            torch.cuda.synchronize(self.device)
+            self._graphs = graphs
         return self._slots, mb
+
+    def _run(self, k: int, n: int):
+        """Forward of the first n images of slot k on the current (run) stream."""
+        if self.use_graphs and n == self._slots[k].shape[0]:
+            g, o = self._graphs[k]
+            g.replay()
+            return o, True
+        with torch.no_grad():
+            return self.net(self._slots[k][:n]), False       # ragged tail micro-batch: eager launches
 
     def __call__(self, x_host: Tensor, out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
         """x_host: (B, C, H, W) fp32 host tensor (pinned for asynchronous copies).  Returns / fills
@@ -60,6 +84,7 @@ class HostPipeline:
         for s in (self.s_h2d, self.s_run, self.s_d2h):
             s.wait_event(start)
         slot_free = [None, None]      # event: kernels that read slot k have finished
+        out_free = [None, None]       # event: the captured outputs of slot k have been copied to the host
         last_d2h = None
         result = out if out is not None else self._out
         if result is not None and result["x_hat"].shape[0] != B:
@@ -71,14 +96,14 @@ class HostPipeline:
             with torch.cuda.stream(self.s_h2d):
                 if slot_free[k] is not None:
                     self.s_h2d.wait_event(slot_free[k])
-                xd = slots[k][: hi - lo]
-                xd.copy_(x_host[lo:hi], non_blocking=True)
+                slots[k][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_h2d)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(ev_in)
-                with torch.no_grad():
-                    o = self.net(xd)
+                if out_free[k] is not None:
+                    self.s_run.wait_event(out_free[k])
+                o, static = self._run(k, hi - lo)
                 ev_run = torch.cuda.Event()
                 ev_run.record(self.s_run)
                 slot_free[k] = ev_run
@@ -92,12 +117,15 @@ class HostPipeline:
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(ev_run)
                 result["x_hat"][lo:hi].copy_(o["x_hat"], non_blocking=True)
-                o["x_hat"].record_stream(self.s_d2h)
                 for n, t in o["likelihoods"].items():
                     result["likelihoods"][n][lo:hi].copy_(t, non_blocking=True)
-                    t.record_stream(self.s_d2h)
+                if not static:
+                    o["x_hat"].record_stream(self.s_d2h)
+                    for t in o["likelihoods"].values():
+                        t.record_stream(self.s_d2h)
                 last_d2h = torch.cuda.Event()
                 last_d2h.record(self.s_d2h)
+                out_free[k] = last_d2h
             i += 1
         if last_d2h is not None:
             caller.wait_event(last_d2h)
