@@ -69,6 +69,8 @@ _PROTOS = {
     "mmc_gaussian_volume": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_int, c_int, c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "mmc_scale_space_warp": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "mmc_add": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "mmc_wgrad_tc": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "mmc_wgrad_finalize": (c_int, [c_vp, c_int, c_int, c_int, c_f32, c_vp, c_int, c_vp, c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

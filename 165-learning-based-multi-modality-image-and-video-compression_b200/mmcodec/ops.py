@@ -483,6 +483,26 @@ def add(a: Tensor, b: Tensor) -> Tensor:
     return out
 
 
+# ---- backward of the transforms ------------------------------------------------------------------------
+def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.0, mask: Optional[Tensor] = None,
+          name: str = "conv") -> Tensor:
+    """Weight gradient (Cs, Cl, k, k) fp32 of a conv / deconv layer from its low-resolution side S and high-resolution side
+    L, both NHWC bf16 with channel counts that are multiples of 8 (see mmc_wgrad_tc)."""
+    _require_cuda(s_nhwc, l_nhwc)
+    if s_nhwc.dtype != torch.bfloat16 or l_nhwc.dtype != torch.bfloat16:
+        raise ValueError("wgrad expects NHWC bf16 operands")
+    s_nhwc, l_nhwc = s_nhwc.contiguous(), l_nhwc.contiguous()
+    B, Hs, Ws, Cs = s_nhwc.shape
+    _, Hl, Wl, Cl = l_nhwc.shape
+    ws = torch.zeros((k * k, Cs, Cl), dtype=torch.float32, device=s_nhwc.device)
+    dw = torch.empty((Cs, Cl, k, k), dtype=torch.float32, device=s_nhwc.device)
+    with _Timed(name + "|wgrad", 2.0 * Cs * Cl * k * k * B * Hs * Ws if _profile is not None else 0.0):
+        L.check(L.lib().mmc_wgrad_tc(_ptr(s_nhwc), _ptr(l_nhwc), B, Cs, Cl, Hs, Ws, Hl, Wl, k, stride, _ptr(ws), _stream()))
+    m = _f32c(mask) if mask is not None else None
+    L.check(L.lib().mmc_wgrad_finalize(_ptr(ws), k, Cs, Cl, float(scale), _ptr(m), 0, _ptr(dw), _stream()))
+    return dw
+
+
 # ---- optional per-launch device timing (bench.py roofline pass; off by default) ---------------------
 _profile = None
 

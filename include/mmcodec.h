@@ -270,6 +270,23 @@ MMC_API int mmc_scale_space_warp(const float *volume, const float *motion_info, 
 /* out = a + b (x_rec = x_pred + x_res_hat, models/video/google.py:271) */
 MMC_API int mmc_add(const float *a, const float *b, int64_t n, float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backward of the transforms (training step, examples/train.py:239-253): weight gradient on tensor cores.
+ * The input gradient of conv() is deconv() with the same weight tensor and vice versa, i.e. mmc_conv_forward_tc with the
+ * adjoint descriptor -- no separate entry point.
+ * ------------------------------------------------------------------------------------------- */
+
+/* dW[cs][cl][ky][kx] = sum_{b,qy,qx} S[b,qy,qx,cs] * L[b,qy*stride+ky-k/2,qx*stride+kx-k/2,cl]  (fp32 accumulate),
+ * S and L NHWC bf16 with channel counts that are multiples of 8.
+ * nn.Conv2d (models/utils.py:128-135): S = grad_output, L = input; nn.ConvTranspose2d (utils.py:138-146): S = input,
+ * L = grad_output.  Also the GDN gamma gradient with k = 1 (layers/gdn.py:77-92).  Partial sums are ADDED into
+ * workspace ([k*k][Cs][Cl] fp32, zeroed by the caller); mmc_wgrad_finalize writes scale * workspace (* mask) in torch's
+ * (Cs, Cl, k, k) weight-gradient layout. */
+MMC_API int mmc_wgrad_tc(const void *s_nhwc, const void *l_nhwc, int64_t B, int Cs, int Cl, int Hs, int Ws, int Hl, int Wl,
+                         int k, int stride, float *workspace, void *stream);
+MMC_API int mmc_wgrad_finalize(const float *workspace, int k, int Cs, int Cl, float scale, const float *mask, int accumulate,
+                               float *dw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
