@@ -166,7 +166,7 @@ __device__ __forceinline__ void store16(const TcParams &P, int64_t off, const fl
         dst[0] = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
         dst[1] = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
     }
-    if (P.out2) {
+    if (P.out2 == 1 || P.out2 == 2) {
         float w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] = (P.out2 == 1) ? fabsf(v[i]) : v[i];
@@ -216,6 +216,12 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         uint32_t pk[8];
 #pragma unroll
         for (int i = 0; i < 16; ++i) x[j][i] += bs[i];
+        if (P.out2 == 3 && g.valid) {
+            // training: keep the pre-GDN activations (bf16) for the backward pass
+            uint4 *dst = reinterpret_cast<uint4 *>(P.y2 + g.pix_off + c0);
+            dst[0] = make_uint4(pack_bf16(x[j][0], x[j][1]), pack_bf16(x[j][2], x[j][3]), pack_bf16(x[j][4], x[j][5]), pack_bf16(x[j][6], x[j][7]));
+            dst[1] = make_uint4(pack_bf16(x[j][8], x[j][9]), pack_bf16(x[j][10], x[j][11]), pack_bf16(x[j][12], x[j][13]), pack_bf16(x[j][14], x[j][15]));
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(x[j][2 * i] * x[j][2 * i], x[j][2 * i + 1] * x[j][2 * i + 1]);
         uint8_t *tile_base = g.sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)g.row * 128;
@@ -891,7 +897,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     MMC_CHECK_ARG(d->in_dtype == MMC_BF16 && (d->in_layout == MMC_NHWC || d->in_layout == MMC_NHWC_PAD8), "%s: input must be NHWC bf16", name);
     MMC_CHECK_ARG((d->act >= 0 && d->act <= MMC_ACT_LEAKY_RELU) || d->act == MMC_ACT_QRELU8, "%s: bad act", name);
     MMC_CHECK_ARG(d->gdn >= 0 && d->gdn <= MMC_GDN_INVERSE, "%s: bad gdn mode", name);
-    MMC_CHECK_ARG(d->out2_bf16 >= 0 && d->out2_bf16 <= 2, "%s: bad out2_bf16", name);
+    MMC_CHECK_ARG((d->out2_bf16 >= 0 && d->out2_bf16 <= 2) || (d->out2_bf16 == 3 && d->gdn != MMC_GDN_NONE), "%s: bad out2_bf16 (3 = pre-GDN activations, needs a fused GDN)", name);
     MMC_CHECK_ARG(d->gdn == MMC_GDN_NONE || (beta_eff && gamma_eff_bf16), "%s: GDN needs beta/gamma", name);
     MMC_CHECK_ARG(!d->out2_bf16 || y2, "%s: out2_bf16 set but y2 is NULL", name);
     if (pl.mode == MODE_SCATTER) {

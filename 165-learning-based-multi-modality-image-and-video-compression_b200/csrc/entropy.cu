@@ -313,6 +313,146 @@ __global__ void __launch_bounds__(kBlock) eb_kernel(const float *__restrict__ x,
     if (kModeOp == 0 && bits) block_atomic_add(bit_acc, red, bits);
 }
 
+// ---- backward of the noise-mode likelihood (training) -------------------------------------
+// Per element: both logits forward, then each branch again keeping h_k / tanh(u_k) and back-propagating
+// delta(u_4) = +-g m sign(q) s sigma'(s logit) down to the input.  The 58 parameter gradients of the thread's channel
+// accumulate in registers; dM = dW * sigmoid(M) = dW * (1 - exp(-W)), da = dA * (1 - A^2) are applied once at the end.
+struct EbGrads {
+    float W0[3], W1[9], W2[9], W3[9], W4[3];
+    float b0[3], b1[3], b2[3], b3[3], b4;
+    float A0[3], A1[3], A2[3], A3[3];
+};
+
+__device__ __forceinline__ void eb_bwd_layer3(const float *W, const float *A, const float *h_in, const float *th, const float *dh_out,
+                                              float *dW, float *db, float *dA, float *dh_in)
+{
+    float du[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        dA[o] += dh_out[o] * th[o];
+        du[o] = dh_out[o] * fmaf(A[o], 1.0f - th[o] * th[o], 1.0f);
+        db[o] += du[o];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dW[o * 3 + j] = fmaf(du[o], h_in[j], dW[o * 3 + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dh_in[j] = W[j] * du[0] + W[3 + j] * du[1] + W[6 + j] * du[2];
+}
+
+// one branch: forward from v keeping intermediates, backward from du4; returns d(logit)/dv * du4
+__device__ __forceinline__ float eb_branch_bwd(const EbRegs &r, float v, float du4, EbGrads &G)
+{
+    float h1[3], h2[3], h3[3], h4[3], t0[3], t1[3], t2[3], t3[3];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        const float u = fmaf(r.W0[o], v, r.b0[o]);
+        t0[o] = tanhf(u);
+        h1[o] = fmaf(r.A0[o], t0[o], u);
+    }
+    auto fwd3 = [](const float *W, const float *b, const float *A, const float *hin, float *t, float *hout) {
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            float u = W[o * 3] * hin[0];
+            u = fmaf(W[o * 3 + 1], hin[1], u);
+            u = fmaf(W[o * 3 + 2], hin[2], u);
+            u += b[o];
+            t[o] = tanhf(u);
+            hout[o] = fmaf(A[o], t[o], u);
+        }
+    };
+    fwd3(r.W1, r.b1, r.A1, h1, t1, h2);
+    fwd3(r.W2, r.b2, r.A2, h2, t2, h3);
+    fwd3(r.W3, r.b3, r.A3, h3, t3, h4);
+    // layer 4 (linear)
+    float dh4[3], dh3[3], dh2[3], dh1[3];
+    G.b4 += du4;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        G.W4[j] = fmaf(du4, h4[j], G.W4[j]);
+        dh4[j] = r.W4[j] * du4;
+    }
+    eb_bwd_layer3(r.W3, r.A3, h3, t3, dh4, G.W3, G.b3, G.A3, dh3);
+    eb_bwd_layer3(r.W2, r.A2, h2, t2, dh3, G.W2, G.b2, G.A2, dh2);
+    eb_bwd_layer3(r.W1, r.A1, h1, t1, dh2, G.W1, G.b1, G.A1, dh1);
+    float dv = 0.0f;
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        G.A0[o] += dh1[o] * t0[o];
+        const float du = dh1[o] * fmaf(r.A0[o], 1.0f - t0[o] * t0[o], 1.0f);
+        G.b0[o] += du;
+        G.W0[o] = fmaf(du, v, G.W0[o]);
+        dv = fmaf(r.W0[o], du, dv);
+    }
+    return dv;
+}
+
+template <bool kChannelsLast>
+__global__ void __launch_bounds__(kBlock) eb_bwd_kernel(const float *__restrict__ x, const float *__restrict__ noise, const float *__restrict__ g,
+                                                        mmc_eb_params p, float lik_bound, int64_t outer, uint32_t C, int64_t inner,
+                                                        float *__restrict__ dx, float *__restrict__ dparams /* [C][58] */)
+{
+    EbRegs r;
+    EbGrads G;
+    float *Gf = reinterpret_cast<float *>(&G);
+#pragma unroll
+    for (int i = 0; i < 58; ++i) Gf[i] = 0.0f;
+    bool any = false;
+    auto body = [&](int64_t i) {
+        const float v = x[i] + noise[i];
+        const float lo = eb_logits(r, v - 0.5f), up = eb_logits(r, v + 0.5f);
+        const float sum = lo + up;
+        const float s = (sum > 0.0f) ? -1.0f : ((sum < 0.0f) ? 1.0f : 0.0f);
+        const float su = sigmoid_f(s * up), sl = sigmoid_f(s * lo);
+        const float q = su - sl, p_raw = fabsf(q);
+        const float gv = g[i];
+        const float gm = (lik_bound <= 0.0f || p_raw >= lik_bound || gv < 0.0f) ? gv : 0.0f;
+        const float sq = q > 0.0f ? 1.0f : (q < 0.0f ? -1.0f : 0.0f);
+        const float du_up = gm * sq * s * su * (1.0f - su);
+        const float du_lo = -gm * sq * s * sl * (1.0f - sl);
+        float d = eb_branch_bwd(r, v + 0.5f, du_up, G);
+        d += eb_branch_bwd(r, v - 0.5f, du_lo, G);
+        dx[i] = d;
+        any = true;
+    };
+    uint32_t c;
+    if (kChannelsLast) {
+        int64_t n = outer * C;
+        int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        int64_t T = (int64_t)gridDim.x * blockDim.x;  // multiple of C by construction
+        c = (uint32_t)(tid % C);
+        eb_load(p, c, r);
+        for (int64_t i = tid; i < n; i += T) body(i);
+    } else {
+        c = blockIdx.y;
+        eb_load(p, c, r);
+        int64_t per_chan = outer * inner;
+        int64_t T = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < per_chan; j += T) {
+            int64_t o = j / inner, in = j - o * inner;
+            body((o * C + c) * inner + in);
+        }
+    }
+    // chain through softplus / tanh of the raw parameters
+    const float *Wf = reinterpret_cast<const float *>(&r);       // W0..W4 (33), b0..b4 (13), A0..A3 (12): same order as EbGrads
+#pragma unroll
+    for (int i = 0; i < 33; ++i) Gf[i] *= (1.0f - expf(-Wf[i]));
+#pragma unroll
+    for (int i = 46; i < 58; ++i) Gf[i] *= (1.0f - Wf[i] * Wf[i]);
+    float *dst = dparams + (size_t)c * 58;
+    if (kChannelsLast) {
+        if (any)
+#pragma unroll
+            for (int i = 0; i < 58; ++i) atomicAdd(dst + i, Gf[i]);
+    } else {
+        // the whole block works on channel c: warp-reduce, one atomic per warp
+#pragma unroll
+        for (int i = 0; i < 58; ++i) {
+            const float sum = warp_sum(Gf[i]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(dst + i, sum);
+        }
+    }
+}
+
 // ---- eval-mode fast path: likelihood table per (channel, integer symbol) ---------------------------------
 // In eval mode x_hat = rint(x - median) + median, so the likelihood is a function of (channel, symbol) only -- the
 // same observation update() uses to tabulate the CDFs (entropy_models.py:422-432).  build: one thread per entry.
@@ -431,6 +571,35 @@ static int launch_eb(int op, const float *x, const float *noise, const mmc_eb_pa
             eb_kernel<false, 0><<<grid, kBlock, 0, st>>>(x, noise, *params, lik_bound, outer, (uint32_t)C, inner, x_hat, xb, lik, bits);
         else
             eb_kernel<false, 1><<<grid, kBlock, 0, st>>>(x, noise, *params, lik_bound, outer, (uint32_t)C, inner, x_hat, xb, lik, bits);
+    }
+    MMC_CHECK_LAUNCH(name);
+    return MMC_OK;
+}
+
+static int launch_eb_bwd(const float *x, const float *noise, const float *g, const mmc_eb_params *params, float lik_bound, int64_t outer,
+                         int64_t C, int64_t inner, float *dx, float *dparams, cudaStream_t st)
+{
+    const char *name = "mmc_eb_backward";
+    MMC_CHECK_ARG(params != nullptr, "%s: params is NULL", name);
+    MMC_CHECK_ARG(outer >= 0 && C >= 1 && inner >= 1 && C <= 65535, "%s: bad shape", name);
+    for (int k = 0; k < 5; ++k) MMC_CHECK_ARG(params->matrix[k] && params->bias[k], "%s: NULL parameter block", name);
+    for (int k = 0; k < 4; ++k) MMC_CHECK_ARG(params->factor[k], "%s: NULL factor block", name);
+    int64_t n = outer * C * inner;
+    if (n == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && noise && g && dx && dparams, "%s: NULL buffer (the backward exists for the noise-mode forward only)", name);
+    if (inner == 1) {
+        int64_t unit_blocks = C / gcd64(C, kBlock);
+        int64_t want = (n + (int64_t)kBlock * 16 - 1) / ((int64_t)kBlock * 16);     // ~16 elements per thread: few atomics
+        int64_t m = (want + unit_blocks - 1) / unit_blocks;
+        if (m < 1) m = 1;
+        eb_bwd_kernel<true><<<(int)(m * unit_blocks), kBlock, 0, st>>>(x, noise, g, *params, lik_bound, outer, (uint32_t)C, inner, dx, dparams);
+    } else {
+        int64_t per_chan = outer * inner;
+        int64_t gx = (per_chan + kBlock * 8 - 1) / (kBlock * 8);
+        int64_t cap = ((int64_t)kNumSMs * 8 + C - 1) / C;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        eb_bwd_kernel<false><<<dim3((unsigned)gx, (unsigned)C), kBlock, 0, st>>>(x, noise, g, *params, lik_bound, outer, (uint32_t)C, inner, dx, dparams);
     }
     MMC_CHECK_LAUNCH(name);
     return MMC_OK;
@@ -649,6 +818,12 @@ int mmc_channel_indexes(int64_t outer, int64_t C, int64_t inner, int32_t *out, v
         ChanIndex{(uint32_t)C, (uint32_t)inner}, n, out);
     MMC_CHECK_LAUNCH("mmc_channel_indexes");
     return MMC_OK;
+}
+
+int mmc_eb_backward(const float *x, const float *noise, const float *grad_lik, const mmc_eb_params *params, float likelihood_bound,
+                    int64_t outer, int64_t C, int64_t inner, float *dx, float *dparams, void *stream)
+{
+    return launch_eb_bwd(x, noise, grad_lik, params, likelihood_bound, outer, C, inner, dx, dparams, (cudaStream_t)stream);
 }
 
 int mmc_eb_forward(const float *x, const float *noise, const mmc_eb_params *params, float likelihood_bound,

@@ -245,7 +245,12 @@ class EntropyBottleneck(EntropyModel):
         return True
 
     def loss(self) -> Tensor:
-        """entropy_models.py:450-454 (value only; the training backward is a later row)."""
+        """entropy_models.py:450-454: gradient flows to ``quantiles`` only (the reference evaluates the cumulative with
+        stop_gradient=True on the density parameters)."""
+        if torch.is_grad_enabled() and self.quantiles.requires_grad:
+            # (C, 1, 3) values: host-side glue on 3 numbers per channel, same torch ops as the reference
+            logits = self._logits_cumulative_host(self.quantiles)
+            return torch.abs(logits - self.target).sum()
         q = self.quantiles.detach()                                  # (C, 1, 3)
         logits = ops.eb_logits_cumulative(q.permute(1, 0, 2).contiguous(), self._params())   # (1, C, 3)
         return torch.abs(logits.permute(1, 0, 2) - self.target).sum()

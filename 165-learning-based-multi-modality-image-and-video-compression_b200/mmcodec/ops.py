@@ -503,6 +503,86 @@ def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.
     return dw
 
 
+def nchw_to_nhwc8(x: Tensor) -> Tensor:
+    """fp32 NCHW tensor with <= 8 channels -> bf16 NHWC with the channels zero-padded to 8 (no spatial padding)."""
+    _require_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, 8), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().mmc_pad_nchw_to_nhwc8(_ptr(x), B, C, H, W, 0, H, W, _ptr(out), _stream()))
+    return out
+
+
+def act_bwd(grad_out: Tensor, y: Tensor, act: int) -> Tensor:
+    _require_cuda(grad_out, y)
+    g, y = grad_out.contiguous(), y.contiguous()
+    out = torch.empty_like(g)
+    L.check(L.lib().mmc_act_bwd(_ptr(g), _ptr(y), int(act), g.numel(), _ptr(out), _stream()))
+    return out
+
+
+def colsum(g: Tensor, scale: float = 1.0) -> Tensor:
+    """fp32 [C] = scale * sum over all leading dims of a (..., C) bf16 tensor (bias / beta gradients)."""
+    _require_cuda(g)
+    g = g.contiguous()
+    C = g.shape[-1]
+    out = torch.zeros(C, dtype=torch.float32, device=g.device)
+    L.check(L.lib().mmc_colsum_bf16(_ptr(g), g.numel() // C, C, float(scale), _ptr(out), _stream()))
+    return out
+
+
+def square(x: Tensor) -> Tensor:
+    _require_cuda(x)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    L.check(L.lib().mmc_square_bf16(_ptr(x), x.numel(), _ptr(out), _stream()))
+    return out
+
+
+def gdn_bwd_t(grad_out: Tensor, x: Tensor, norm: Tensor, inverse: bool) -> Tensor:
+    _require_cuda(grad_out, x, norm)
+    t = torch.empty_like(x)
+    L.check(L.lib().mmc_gdn_bwd_t(_ptr(grad_out.contiguous()), _ptr(x), _ptr(norm), int(bool(inverse)), x.numel(), _ptr(t), _stream()))
+    return t
+
+
+def gdn_bwd_dx(grad_out: Tensor, x: Tensor, norm: Tensor, u: Tensor, inverse: bool) -> Tensor:
+    _require_cuda(grad_out, x, norm, u)
+    dx = torch.empty_like(x)
+    L.check(L.lib().mmc_gdn_bwd_dx(_ptr(grad_out.contiguous()), _ptr(x), _ptr(norm), _ptr(u), int(bool(inverse)), x.numel(), _ptr(dx), _stream()))
+    return dx
+
+
+def reparam_bwd(p: Tensor, dp_eff: Tensor, bound: float) -> Tensor:
+    _require_cuda(p, dp_eff)
+    p, d = _f32c(p.detach()), _f32c(dp_eff)
+    out = torch.empty_like(p)
+    L.check(L.lib().mmc_reparam_bwd(_ptr(p), _ptr(d), float(bound), p.numel(), _ptr(out), _stream()))
+    return out
+
+
+def gc_backward(xv: Tensor, s: Tensor, m: Optional[Tensor], nz: Optional[Tensor], g: Tensor, scale_bound: float, likelihood_bound: float):
+    """Gradients of GaussianConditional.forward's likelihood; all tensors share xv's memory layout."""
+    _require_cuda(xv, s, m, nz, g)
+    dx = torch.empty_like(xv) if nz is not None else None
+    ds = torch.empty_like(xv)
+    dm = torch.empty_like(xv) if (m is not None and nz is not None) else None
+    L.check(L.lib().mmc_gc_backward(_ptr(xv), _ptr(s), _ptr(m), _ptr(nz), _ptr(g), float(scale_bound), float(likelihood_bound), xv.numel(),
+                                    _ptr(dx), _ptr(ds), _ptr(dm), _stream()))
+    return dx, ds, dm
+
+
+def eb_backward(xv: Tensor, nz: Tensor, g: Tensor, params, likelihood_bound: float, outer: int, C: int, inner: int):
+    """dx and packed parameter gradients [C][58] of EntropyBottleneck.forward (noise mode)."""
+    _require_cuda(xv, nz, g)
+    p, _keep = params
+    dx = torch.empty_like(xv)
+    dparams = torch.zeros((C, 58), dtype=torch.float32, device=xv.device)
+    L.check(L.lib().mmc_eb_backward(_ptr(xv), _ptr(nz), _ptr(g), ctypes.byref(p), float(likelihood_bound), outer, C, inner, _ptr(dx),
+                                    _ptr(dparams), _stream()))
+    return dx, dparams
+
+
 # ---- optional per-launch device timing (bench.py roofline pass; off by default) ---------------------
 _profile = None
 

@@ -88,13 +88,17 @@ def _tc_eligible(cin: int, cout: int, gdn: bool) -> bool:
     return (not gdn) or cout in (64, 128, 192)
 
 
-def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0):
+def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0, _train_dispatch: bool = True):
     """Run a conv stack.  ``x``: (B,C,H,W) fp32 for "nchw_f32", (B,H,W,C) for the NHWC formats.
     Returns the output in ``out_fmt``; "nchw_f32" results may be channels-last strided views (same
     logical shape and values as the reference's NCHW tensor).  With ``out2`` (1: |output|, 2: output)
     also returns that tensor as NHWC bf16 (the h_a input, models/google.py:283,381)."""
     assert in_fmt in FORMATS and out_fmt in FORMATS
     ops._require_cuda(x)
+    if _train_dispatch and torch.is_grad_enabled():
+        from . import autograd as AG
+        if AG.wants_grad(layers, x):
+            return AG.run_layers_train(layers, x, in_fmt, out_fmt, out2)   # same kernels, recorded for backward
     steps = parse_layers(layers)
     if not steps:
         raise ValueError("empty transform stack")

@@ -206,7 +206,8 @@ typedef struct mmc_conv_desc {
     int act;             /* mmc_act applied to (acc + bias) */
     int gdn;             /* mmc_gdn_mode applied after act; needs beta_eff / gamma_eff */
     int out2_bf16;       /* secondary NHWC bf16 output y2: 0 none, 1 = |out| (torch.abs(y) feeding h_a,
-                            models/google.py:283), 2 = out (y feeding h_a in the mean-scale model, :381) */
+                            models/google.py:283), 2 = out (y feeding h_a in the mean-scale model, :381),
+                            3 = the activations BEFORE the fused GDN / IGDN (saved for the backward pass) */
 } mmc_conv_desc;
 
 /* Output spatial size for a descriptor (conv: ceil(H/stride); deconv: H*stride). */
@@ -286,6 +287,40 @@ MMC_API int mmc_wgrad_tc(const void *s_nhwc, const void *l_nhwc, int64_t B, int 
                          int k, int stride, float *workspace, void *stream);
 MMC_API int mmc_wgrad_finalize(const float *workspace, int k, int Cs, int Cl, float scale, const float *mask, int accumulate,
                                float *dw, void *stream);
+
+/* ---- elementwise / reduction kernels of the training step (NHWC bf16 activations and gradients, n % 8 == 0) ---- */
+
+/* grad_in = grad_out * act'(y) for the fused ReLU / LeakyReLU(0.01) epilogues (models/google.py:254-269,363-377) */
+MMC_API int mmc_act_bwd(const void *grad_out, const void *y, int act, int64_t n, void *grad_in, void *stream);
+/* out[c] += scale * sum_rows g[row][c]: bias gradient of conv()/deconv(); GDN beta gradient (scale = -+1/2).
+ * out is fp32 [C] and must be initialised by the caller. */
+MMC_API int mmc_colsum_bf16(const void *g, int64_t rows, int C, float scale, float *out, void *stream);
+MMC_API int mmc_square_bf16(const void *x, int64_t n, void *out, void *stream);
+/* GDN / IGDN backward (layers/gdn.py:77-92) around two 1x1 tensor-core contractions:
+ *   norm = beta' + gamma' x^2        (mmc_conv_forward_tc, k = 1, fp32 out)
+ *   t    = g x norm^(-3/2)           (IGDN: g x norm^(-1/2))                          mmc_gdn_bwd_t
+ *   u    = gamma'^T t                (mmc_conv_forward_tc, k = 1, fp32 out)
+ *   dx   = g norm^(-1/2) - x u       (IGDN: g norm^(1/2) + x u)                       mmc_gdn_bwd_dx
+ *   dbeta' = -+1/2 colsum(t),  dgamma' = -+1/2 t^T x^2  (mmc_wgrad_tc with k = 1) */
+MMC_API int mmc_gdn_bwd_t(const void *grad_out, const void *x, const float *norm, int inverse, int64_t n, void *t, void *stream);
+MMC_API int mmc_gdn_bwd_dx(const void *grad_out, const void *x, const float *norm, const float *u, int inverse, int64_t n,
+                           void *dx, void *stream);
+/* NonNegativeParametrizer backward (ops/parametrizers.py:61-64 + ops/bound_ops.py:40-42):
+ * d = dp_eff * 2 max(p, bound); dp = d * [(p >= bound) | (d < 0)] */
+MMC_API int mmc_reparam_bwd(const float *p, const float *dp_eff, float bound, int64_t n, float *dp, void *stream);
+
+/* GaussianConditional.forward backward (entropy_models.py:692-731): gradients of the bounded likelihood w.r.t. the
+ * input (noise mode only; round() has zero gradient), the scales (through the scale LowerBound) and the means.
+ * dx / dmeans may be NULL. */
+MMC_API int mmc_gc_backward(const float *x, const float *scales, const float *means, const float *noise, const float *grad_lik,
+                            float scale_bound, float likelihood_bound, int64_t n, float *dx, float *dscales, float *dmeans,
+                            void *stream);
+/* EntropyBottleneck.forward backward, noise mode (entropy_models.py:457-540): dx and the packed parameter gradients
+ * dparams [C][58] fp32 (ADDED into; order: _matrix0..4 (3,9,9,9,3), _bias0..4 (3,3,3,3,1), _factor0..3 (3 each)),
+ * already chained through softplus / tanh of the raw parameters. */
+MMC_API int mmc_eb_backward(const float *x, const float *noise, const float *grad_lik, const mmc_eb_params *params,
+                            float likelihood_bound, int64_t outer, int64_t C, int64_t inner, float *dx, float *dparams,
+                            void *stream);
 
 #ifdef __cplusplus
 }

@@ -34,9 +34,24 @@ def deconv(sd: Dict[str, Tensor], name: str, x: Tensor, stride: int = 2) -> Tens
                               output_padding=stride - 1)
 
 
+class _LowerBoundFn(torch.autograd.Function):
+    """compressai/ops/bound_ops.py:36-56: max(x, bound) whose gradient also passes where it pushes x up towards the bound"""
+
+    @staticmethod
+    def forward(ctx, x, bound):
+        ctx.save_for_backward(x, bound)
+        return torch.max(x, bound)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, bound = ctx.saved_tensors
+        pass_through_if = (x >= bound) | (grad_output < 0)
+        return pass_through_if.type(grad_output.dtype) * grad_output, None
+
+
 def lower_bound(x: Tensor, bound: float) -> Tensor:
-    """compressai/ops/bound_ops.py:36-37"""
-    return torch.max(x, torch.tensor([bound], dtype=x.dtype))
+    """compressai/ops/bound_ops.py:36-80 (forward: torch.max(x, bound))"""
+    return _LowerBoundFn.apply(x, torch.tensor([bound], dtype=x.dtype))
 
 
 def gdn(sd: Dict[str, Tensor], name: str, x: Tensor, inverse: bool = False, beta_min: float = 1e-6) -> Tensor:
@@ -256,12 +271,16 @@ def bpp(out, num_pixels: int) -> float:
 
 
 # ---- multi-modality two-branch codec (compressai/models/google.py:696-1459) ---------------------------------
-def _context_entropy_stage(sd, y):
-    """Hyperprior + masked context model + entropy parameters, eval mode (google.py:800-822, 1196-1211)."""
+def _context_entropy_stage(sd, y, noise=None):
+    """Hyperprior + masked context model + entropy parameters (google.py:800-822, 1196-1211); eval mode, or training mode
+    when ``noise`` = {"z", "y_hat", "y"} holds the three uniform draws the reference makes."""
     z = _h_a(sd, y, F.leaky_relu)
-    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z)
+    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z, noise=None if noise is None else noise["z"])
     params = _mean_scale_params(sd, z_hat)
-    y_hat = quantize(y, "dequantize")                                  # no means: what the context model / decoder see
+    if noise is None:
+        y_hat = quantize(y, "dequantize")                              # no means: what the context model / decoder see
+    else:
+        y_hat = quantize(y, "noise", noise=noise["y_hat"])
     w = sd["context_prediction.weight"] * sd["context_prediction.mask"]  # layers/layers.py:75-78
     ctx = F.conv2d(y_hat, w, sd["context_prediction.bias"], padding=2)
     g = torch.cat((params, ctx), dim=1)
@@ -270,7 +289,7 @@ def _context_entropy_stage(sd, y):
         if i < 4:
             g = F.leaky_relu(g)
     scales_hat, means_hat = g.chunk(2, 1)
-    _, y_lik = gc_forward(y, scales_hat, means_hat)
+    _, y_lik = gc_forward(y, scales_hat, means_hat, noise=None if noise is None else noise["y"])
     return y_hat, y_lik, z_lik, {"z": z, "scales_hat": scales_hat, "means_hat": means_hat}
 
 
@@ -314,8 +333,8 @@ def mm_fuse(sd, i, own, guide):
     return esa(sd, f"attention{i}", f)
 
 
-def mm_d_forward(sd, x, hidden):
-    """JointAutoregressiveHierarchicalPriors_D.forward (google.py:1140-1248)."""
+def mm_d_forward(sd, x, hidden, noise=None):
+    """JointAutoregressiveHierarchicalPriors_D.forward (google.py:1140-1248); ``noise``: see _context_entropy_stage."""
     fuse = lambda i, own, guide: mm_fuse(sd, i, own, guide)
 
     a = gdn(sd, "pic2_g_a_gdn1", conv(sd, "pic2_g_a_conv1", x))
@@ -325,7 +344,7 @@ def mm_d_forward(sd, x, hidden):
     a = gdn(sd, "pic2_g_a_gdn3", conv(sd, "pic2_g_a_conv3", torch.cat((a, f), 1)))
     f = fuse(3, a, hidden["ga3"])
     y = conv(sd, "pic2_g_a_conv4", torch.cat((a, f), 1))
-    y_hat, y_lik, z_lik, extra = _context_entropy_stage(sd, y)
+    y_hat, y_lik, z_lik, extra = _context_entropy_stage(sd, y, noise)
     s = gdn(sd, "pic2_g_s_gdn1", deconv(sd, "pic2_g_s_conv1", y_hat), inverse=True)
     f = fuse(4, s, hidden["gs1"])
     s = gdn(sd, "pic2_g_s_gdn2", deconv(sd, "pic2_g_s_conv2", torch.cat((s, f), 1)), inverse=True)

@@ -53,3 +53,158 @@ def test_wgrad_tc(transposed, B, Cin, Cout, H, W, k, s):
     dw = ops.wgrad(x_nhwc, dy_nhwc, k, s) if transposed else ops.wgrad(dy_nhwc, x_nhwc, k, s)
     assert tuple(dw.shape) == tuple(ref.shape)
     assert rel_rms(dw, ref) < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------
+# layer-level backward through the autograd Functions vs float64 autograd of the oracle's ops
+# ---------------------------------------------------------------------------------------------------------
+from oracle import torch_port as tp  # noqa: E402
+from mmcodec import autograd as AG  # noqa: E402
+from mmcodec.layers import GDN, conv, deconv  # noqa: E402
+from mmcodec.transforms import run_layers  # noqa: E402
+
+
+def cos(a, b):
+    a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+    return float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,s,act", [
+    ("conv", 64, 128, 5, 2, "leaky"), ("deconv", 128, 64, 5, 2, "relu"), ("conv", 192, 96, 3, 1, None),
+    ("conv", 384, 192, 5, 1, None), ("conv", 96, 64, 1, 1, "leaky"), ("deconv", 192, 288, 5, 2, "leaky")])
+def test_conv_layer_backward(kind, cin, cout, k, s, act):
+    torch.manual_seed(cin + cout)
+    m = (conv if kind == "conv" else deconv)(cin, cout, kernel_size=k, stride=s).to(dev())
+    with torch.no_grad():
+        m.weight.copy_(m.weight.to(torch.bfloat16).float())       # bf16-exact weights: the comparison isolates the kernels
+        m.bias.copy_(m.bias.to(torch.bfloat16).float())
+    B, H, W = 2, 12, 20
+    x = torch.randn(B, H, W, cin, device=dev()).to(torch.bfloat16).requires_grad_(True)
+    layers = [m] + ([torch.nn.LeakyReLU()] if act == "leaky" else [torch.nn.ReLU()] if act == "relu" else [])
+    y = run_layers(layers, x, "nhwc_bf16", "nhwc_bf16")
+    assert y.requires_grad
+    gy = torch.randn_like(y.float()).to(torch.bfloat16)
+    y.backward(gy)
+    # reference
+    xr = x.detach().double().cpu().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = m.weight.detach().double().cpu().requires_grad_(True), m.bias.detach().double().cpu().requires_grad_(True)
+    if kind == "conv":
+        yr = F.conv2d(xr, wr, br, stride=s, padding=k // 2)
+    else:
+        yr = F.conv_transpose2d(xr, wr, br, stride=s, padding=k // 2, output_padding=s - 1)
+    if act:
+        yr = F.leaky_relu(yr) if act == "leaky" else F.relu(yr)
+    assert rel_rms(y.detach().float().permute(0, 3, 1, 2), yr.detach()) < 1e-2
+    yr.backward(gy.double().cpu().permute(0, 3, 1, 2))
+    assert rel_rms(x.grad.float().permute(0, 3, 1, 2), xr.grad) < 2e-2
+    assert rel_rms(m.weight.grad, wr.grad) < 2e-2 and rel_rms(m.bias.grad, br.grad) < 2e-2
+
+
+def test_edge_layers_backward():
+    """Image-edge conv (3 -> N, fp32 NCHW input, no input gradient) and reconstruction deconv (N -> 3, planar fp32 output)."""
+    torch.manual_seed(3)
+    m = conv(3, 128).to(dev())
+    d = deconv(128, 3).to(dev())
+    with torch.no_grad():
+        for p in list(m.parameters()) + list(d.parameters()):
+            p.copy_(p.to(torch.bfloat16).float())          # bf16-exact parameters: same ReLU mask on both sides
+    x = torch.rand(2, 3, 32, 48, device=dev())
+    y = run_layers([m, torch.nn.ReLU()], x, "nchw_f32", "nhwc_bf16")
+    gy = torch.randn_like(y.float()).to(torch.bfloat16)
+    y.backward(gy)
+    xr = x.double().cpu().to(torch.bfloat16).double()
+    wr, br = m.weight.detach().double().cpu().requires_grad_(True), m.bias.detach().double().cpu().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wr, br, stride=2, padding=2))
+    yr.backward(gy.double().cpu().permute(0, 3, 1, 2))
+    assert rel_rms(m.weight.grad, wr.grad) < 2e-2 and rel_rms(m.bias.grad, br.grad) < 2e-2
+    h = torch.randn(2, 8, 12, 128, device=dev()).to(torch.bfloat16).requires_grad_(True)
+    xh = run_layers([d], h, "nhwc_bf16", "nchw_f32")
+    assert tuple(xh.shape) == (2, 3, 16, 24) and xh.dtype == torch.float32
+    gx = torch.randn_like(xh)
+    xh.backward(gx)
+    hr = h.detach().double().cpu().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = d.weight.detach().double().cpu().requires_grad_(True), d.bias.detach().double().cpu().requires_grad_(True)
+    yr = F.conv_transpose2d(hr, wr, br, stride=2, padding=2, output_padding=1)
+    yr.backward(gx.double().cpu())
+    assert rel_rms(h.grad.float().permute(0, 3, 1, 2), hr.grad) < 2e-2
+    assert rel_rms(d.weight.grad, wr.grad) < 2e-2 and rel_rms(d.bias.grad, br.grad) < 2e-2
+
+
+@pytest.mark.parametrize("inverse,C", [(False, 128), (True, 192)])
+def test_conv_gdn_backward(inverse, C):
+    """Fused conv + GDN / IGDN forward (pre-GDN activations as secondary output) and its backward."""
+    torch.manual_seed(C)
+    m = (deconv if inverse else conv)(64, C).to(dev())
+    gdn = GDN(C, inverse=inverse).to(dev())
+    with torch.no_grad():
+        m.weight.mul_(3.0)
+        gdn.gamma.add_(torch.rand_like(gdn.gamma) * 0.02)
+        gdn.beta.add_(torch.rand_like(gdn.beta) * 0.5)
+    x = torch.randn(2, 10, 14, 64, device=dev()).to(torch.bfloat16).requires_grad_(True)
+    y = run_layers([m, gdn], x, "nhwc_bf16", "nhwc_bf16")
+    gy = torch.randn_like(y.float()).to(torch.bfloat16)
+    y.backward(gy)
+    sd = {"c.weight": m.weight.detach().double().cpu().requires_grad_(True), "c.bias": m.bias.detach().double().cpu().requires_grad_(True),
+          "g.beta": gdn.beta.detach().double().cpu().requires_grad_(True), "g.gamma": gdn.gamma.detach().double().cpu().requires_grad_(True)}
+    xr = x.detach().double().cpu().permute(0, 3, 1, 2).requires_grad_(True)
+    pre = (tp.deconv if inverse else tp.conv)(sd, "c", xr)
+    yr = tp.gdn(sd, "g", pre, inverse=inverse)
+    assert rel_rms(y.detach().float().permute(0, 3, 1, 2), yr.detach()) < 1e-2
+    yr.backward(gy.double().cpu().permute(0, 3, 1, 2))
+    assert rel_rms(x.grad.float().permute(0, 3, 1, 2), xr.grad) < 3e-2
+    assert rel_rms(m.weight.grad, sd["c.weight"].grad) < 3e-2 and rel_rms(m.bias.grad, sd["c.bias"].grad) < 3e-2
+    assert rel_rms(gdn.beta.grad, sd["g.beta"].grad) < 3e-2 and rel_rms(gdn.gamma.grad, sd["g.gamma"].grad) < 3e-2
+
+
+def test_gaussian_conditional_backward():
+    torch.manual_seed(5)
+    shape = (2, 16, 6, 10)
+    x = (torch.randn(shape) * 4).to(dev()).requires_grad_(True)
+    scales = torch.exp(torch.empty(shape).uniform_(np.log(0.05), np.log(30.0))).to(dev()).requires_grad_(True)
+    means = (torch.randn(shape) * 2).to(dev()).requires_grad_(True)
+    noise = torch.empty(shape).uniform_(-0.5, 0.5).to(dev())
+    _, lik = AG.gc_forward(x, scales, means, noise, 0.11, 1e-9)
+    g = torch.randn(shape, device=dev())
+    lik.backward(g)
+    xr, sr, mr = (t.detach().double().cpu().requires_grad_(True) for t in (x, scales, means))
+    _, lr = tp.gc_forward(xr, sr, mr, noise=noise.double().cpu())
+    lr.backward(g.double().cpu())
+    for mine, ref in ((x.grad, xr.grad), (scales.grad, sr.grad), (means.grad, mr.grad)):
+        assert rel_rms(mine, ref) < 1e-3
+
+
+def test_entropy_bottleneck_backward():
+    torch.manual_seed(6)
+    C = 24
+    eb = mmcodec.EntropyBottleneck(C).to(dev())
+    with torch.no_grad():
+        for i in range(5):
+            getattr(eb, f"_matrix{i}").add_(torch.randn_like(getattr(eb, f"_matrix{i}")) * 0.3)
+            if i < 4:
+                getattr(eb, f"_factor{i}").add_(torch.randn_like(getattr(eb, f"_factor{i}")) * 0.3)
+    sd = {f"eb.{k}": v.detach().double().cpu().requires_grad_(True) for k, v in eb.named_parameters()}
+    for layout in ("nchw", "channels_last"):
+        eb.zero_grad()
+        for v in sd.values():
+            v.grad = None
+        x = (torch.randn(2, C, 5, 7) * 3).to(dev())
+        if layout == "channels_last":
+            x = x.contiguous(memory_format=torch.channels_last)
+        x.requires_grad_(True)
+        noise = torch.empty(2, C, 5, 7).uniform_(-0.5, 0.5).to(dev())
+        x_hat, lik = AG.eb_forward(x, eb, noise)
+        g = torch.randn(2, C, 5, 7, device=dev())
+        (lik * g).sum().backward()
+        xr = x.detach().double().cpu().contiguous().requires_grad_(True)
+        _, lr = tp.eb_forward(sd, "eb", xr, noise=noise.double().cpu())
+        (lr * g.double().cpu()).sum().backward()
+        assert rel_rms(lik.detach(), lr.detach()) < 1e-4
+        assert rel_rms(x.grad, xr.grad) < 1e-3
+        for k, p in eb.named_parameters():
+            if k == "quantiles":
+                continue
+            assert rel_rms(p.grad, sd[f"eb.{k}"].grad) < 2e-3, (layout, k)
+    # aux loss: gradient reaches the quantiles only
+    eb.zero_grad()
+    eb.loss().backward()
+    assert eb.quantiles.grad is not None and eb._matrix0.grad is None
