@@ -6,11 +6,13 @@
     mmcodec.models           CompressionModel, FactorizedPrior, ScaleHyperprior, MeanScaleHyperprior
     mmcodec.models_mm        JointAutoregressiveHierarchicalPriors_R / _D (RGB + depth two-branch codec), ESA, MaskedConv2d
     mmcodec.models_video     ScaleSpaceFlow (ssf2020 video codec: keyframe / inter-frame forward, compress, decompress)
+    mmcodec.autograd         training path: autograd Functions over the forward / backward kernels
+    mmcodec.training         RateDistortionLoss, configure_optimizers, GradBucketReducer (NCCL), TrainStep
     mmcodec.ops              functional access to every entry point of include/mmcodec.h
 
 All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
 """
-from . import _lib, entropy_models, graphs, host_pipeline, layers, models, models_mm, models_video, ops, transforms  # noqa: F401
+from . import _lib, entropy_models, graphs, host_pipeline, layers, models, models_mm, models_video, ops, training, transforms  # noqa: F401
 from .graphs import GraphedForward  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401
 from ._lib import MmcodecError, build  # noqa: F401
@@ -22,5 +24,6 @@ from .models import (CompressionModel, FactorizedPrior, MeanScaleHyperprior, Sca
 from .models_mm import (ESA, JointAutoregressiveHierarchicalPriors_D,  # noqa: F401
                         JointAutoregressiveHierarchicalPriors_R, MaskedConv2d)
 from .models_video import ScaleSpaceFlow  # noqa: F401
+from .training import GradBucketReducer, RateDistortionLoss, TrainStep, configure_optimizers  # noqa: F401
 
 __version__ = "0.1.0"

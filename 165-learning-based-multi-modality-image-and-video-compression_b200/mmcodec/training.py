@@ -1,0 +1,159 @@
+"""Training step of the two-branch codec -- mirror of the loop body in examples/train.py (RateDistortionLoss :59-82,
+configure_optimizers :111-142, train_one_epoch_master :208-260) with data-parallel gradient averaging.
+
+One process per GPU, batch shards, replicas of the weights.  The only exchange step is the gradient all-reduce:
+``GradBucketReducer`` flattens gradients into fixed-size fp32 buckets as the backward pass produces them (post-accumulate
+hooks), launches one asynchronous NCCL all-reduce per full bucket on a side stream so that it overlaps the rest of the
+backward, and copies the averaged values back before the optimizer step.  Parameters that never receive a gradient (the
+unused g_a / g_s / h_a / h_s inherited from MeanScaleHyperprior) are left out -- consistently on every
+rank, because the graph is the same everywhere.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+from torch import Tensor
+
+__all__ = ["RateDistortionLoss", "configure_optimizers", "GradBucketReducer", "TrainStep"]
+
+
+class RateDistortionLoss(nn.Module):
+    """examples/train.py:59-82: loss = lmbda[q] * MSE + bpp."""
+
+    def __init__(self, q: int):
+        super().__init__()
+        self.mse = nn.MSELoss()
+        self.lmbda = [256, 512, 1024, 2048, 4096, 8192, 10240]
+        self.q = q
+
+    def forward(self, output, target):
+        N, _, H, W = target.size()
+        num_pixels = N * H * W
+        out = {}
+        out["bpp_loss"] = sum((torch.log(lk).sum() / (-math.log(2) * num_pixels)) for lk in output["likelihoods"].values())
+        out["mse_loss"] = self.mse(output["x_hat"], target)
+        out["loss"] = self.lmbda[self.q] * out["mse_loss"] + out["bpp_loss"]
+        return out
+
+
+def configure_optimizers(net: nn.Module, learning_rate: float = 1e-4, aux_learning_rate: float = 1e-3):
+    """examples/train.py:111-142: Adam on everything but the EntropyBottleneck quantiles, a second Adam on those."""
+    params = dict(net.named_parameters())
+    main = sorted(n for n, p in params.items() if not n.endswith(".quantiles") and p.requires_grad)
+    aux = sorted(n for n, p in params.items() if n.endswith(".quantiles") and p.requires_grad)
+    assert not set(main) & set(aux) and len(main) + len(aux) == sum(p.requires_grad for p in params.values())
+    return (torch.optim.Adam((params[n] for n in main), lr=learning_rate),
+            torch.optim.Adam((params[n] for n in aux), lr=aux_learning_rate))
+
+
+class GradBucketReducer:
+    """Bucketed, overlapped gradient averaging over a process group (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, params: Iterable[nn.Parameter], bucket_bytes: int = 32 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # reverse registration order ~ the order in which the backward pass produces gradients
+        self.params: List[nn.Parameter] = [p for p in params if p.requires_grad][::-1]
+        self.buckets: List[List[int]] = []
+        cur, size = [], 0
+        for i, p in enumerate(self.params):
+            cur.append(i)
+            size += p.numel() * 4
+            if size >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {i: b for b, idxs in enumerate(self.buckets) for i in idxs}
+        self._ready = [0] * len(self.buckets)
+        self._work: Dict[int, tuple] = {}
+        self._stream = torch.cuda.Stream() if (self.params and self.params[0].is_cuda) else None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+        self.enabled = True
+
+    def _make_hook(self, i: int):
+        def hook(_p):
+            if not self.enabled or self.world == 1:
+                return
+            b = self.bucket_of[i]
+            self._ready[b] += 1
+            if self._ready[b] == len(self.buckets[b]):
+                self._launch(b)
+        return hook
+
+    def _launch(self, b: int):
+        grads = [self.params[i].grad for i in self.buckets[b] if self.params[i].grad is not None]
+        if not grads:
+            return
+        if self._stream is not None:
+            self._stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._stream):
+                flat = torch.cat([g.reshape(-1).float() for g in grads])
+                work = dist.all_reduce(flat, group=self.group, async_op=True)
+        else:
+            flat = torch.cat([g.reshape(-1).float() for g in grads])
+            work = dist.all_reduce(flat, group=self.group, async_op=True)
+        self._work[b] = (work, flat, grads)
+
+    def finish(self):
+        """Call after backward(): reduces the buckets that never filled up (parameters without gradient), waits for all
+        collectives and writes the averaged gradients back."""
+        if self.world == 1:
+            self._ready = [0] * len(self.buckets)
+            return
+        for b in range(len(self.buckets)):
+            if b not in self._work:
+                self._launch(b)
+        for b, (work, flat, grads) in sorted(self._work.items()):
+            work.wait()
+            if self._stream is not None:
+                torch.cuda.current_stream().wait_stream(self._stream)
+            flat.div_(self.world)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        self._work.clear()
+        self._ready = [0] * len(self.buckets)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+
+
+class TrainStep:
+    """One optimisation step of the second-modality branch with a frozen guide branch (examples/train.py:216-253):
+    hidden = guide(rgb) under no_grad; out = net(x, hidden); loss.backward(); clip; Adam; aux loss; aux Adam."""
+
+    def __init__(self, net: nn.Module, guide: Optional[nn.Module], quality: int = 3, learning_rate: float = 1e-4,
+                 aux_learning_rate: float = 1e-3, clip_max_norm: float = 1.0, bucket_bytes: int = 32 << 20, group=None):
+        self.net, self.guide = net, guide
+        self.criterion = RateDistortionLoss(quality)
+        self.optimizer, self.aux_optimizer = configure_optimizers(net, learning_rate, aux_learning_rate)
+        self.clip_max_norm = clip_max_norm
+        self.reducer = GradBucketReducer(net.parameters(), bucket_bytes, group)
+
+    def __call__(self, x: Tensor, guided: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        self.net.train()
+        hidden = None
+        if self.guide is not None:
+            with torch.no_grad():
+                hidden = self.guide(guided)["hidden"]
+        self.optimizer.zero_grad(set_to_none=True)
+        self.aux_optimizer.zero_grad(set_to_none=True)
+        out_net = self.net(x, hidden) if hidden is not None else self.net(x)
+        out = self.criterion(out_net, x)
+        out["loss"].backward()
+        aux_loss = self.net.aux_loss()
+        aux_loss.backward()
+        self.reducer.finish()
+        if self.clip_max_norm > 0:
+            torch.nn.utils.clip_grad_norm_((p for g in self.optimizer.param_groups for p in g["params"]), self.clip_max_norm)
+        self.optimizer.step()
+        self.aux_optimizer.step()
+        out["aux_loss"] = aux_loss.detach()
+        return {k: v.detach() for k, v in out.items()}
