@@ -56,6 +56,9 @@ WORKLOADS = {
 OTHER_WORKLOADS = {
     "ssf2020": ("ssf2020 video codec eval forward, one GOP of 8 frames 1920x1152 per GPU, frames in order "
                 "(BASELINE.json configs[4]); unit = frames"),
+    "mm-train": ("RGB + depth two-branch codec training step (frozen RGB guide forward, depth branch forward + backward, "
+                 "bucketed NCCL gradient all-reduce overlapped with backward, grad clip, Adam + aux Adam), 768x512 pairs "
+                 "(BASELINE.json configs[3]); unit = pairs"),
     "mm-forward": ("RGB + depth two-branch codec (JointAutoregressiveHierarchicalPriors_R/_D) eval forward, 768x512 pairs "
                    "(forward half of BASELINE.json configs[3]); unit = pairs"),
 }
@@ -134,6 +137,23 @@ def cpu_reference_throughput(batch: int, steps: int, warmup: int):
     return batch * steps / dt, dt / steps * 1e3, cores, (tp.bpp(out, batch * H * W) if "likelihoods" in out else None)
 
 
+def init_nccl_quietly(dist, dev):
+    """NCCL prints its version banner on stdout when the communicator is created; keep stdout for the ONE JSON line."""
+    import torch
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        warm = torch.zeros(1, device=dev)
+        dist.all_reduce(warm)          # forces communicator creation now
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def bench_other(args):
     """For-the-record lines of the GOP / pair workloads (same timing rules; not the driver's headline run)."""
     import torch
@@ -149,7 +169,7 @@ def bench_other(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        init_nccl_quietly(dist, dev)
     torch.manual_seed(0)
     gen = torch.Generator().manual_seed(1234 + rank)
     if args.workload == "ssf2020":
@@ -161,6 +181,20 @@ def bench_other(args):
         step = lambda xs: net(xs)["x_hat"][-1]
         e2e_out = lambda o: [t.cpu() for t in o["x_hat"]]
         run = lambda xs: net(xs)
+    elif args.workload == "mm-train":
+        net_r = mmcodec.JointAutoregressiveHierarchicalPriors_R(192, 192).eval()
+        net_d = mmcodec.JointAutoregressiveHierarchicalPriors_D(192, 192)
+        for n in (net_r, net_d):
+            n.update()
+            n.to(dev)
+        units = args.batch or 4
+        host = [torch.rand(units, 3, 512, 768, generator=gen).pin_memory(), torch.rand(units, 1, 512, 768, generator=gen).pin_memory()]
+        trainer = mmcodec.TrainStep(net_d, net_r, quality=3)
+
+        def run(xs):
+            with torch.enable_grad():
+                return trainer(xs[1], xs[0])
+        e2e_out = lambda o: [o["loss"].cpu()]
     else:
         net_r = mmcodec.JointAutoregressiveHierarchicalPriors_R(192, 192).eval()
         net_d = mmcodec.JointAutoregressiveHierarchicalPriors_D(192, 192).eval()
@@ -201,17 +235,20 @@ def bench_other(args):
         ops.start_profile()
         run(xs)
         prof = ops.stop_profile(with_work="total")
-        # launch-bound workloads: the same forward replayed as ONE CUDA graph (mmcodec.GraphedForward)
-        graphed = mmcodec.GraphedForward(run, xs)
-        graphed(xs)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        for _ in range(args.steps):
+        if args.workload == "mm-train":
+            ms_graph = ms          # optimizer state and collectives: not captured, eager launches are the product path
+        else:
+            # launch-bound workloads: the same forward replayed as ONE CUDA graph (mmcodec.GraphedForward)
+            graphed = mmcodec.GraphedForward(run, xs)
             graphed(xs)
-        g1.record()
-        barrier()
-        ms_graph = g0.elapsed_time(g1)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for _ in range(args.steps):
+                graphed(xs)
+            g1.record()
+            barrier()
+            ms_graph = g0.elapsed_time(g1)
     t = torch.tensor([ms, ms_e2e, ms_graph], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -224,10 +261,11 @@ def bench_other(args):
     top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]
     print(json.dumps({"metric": f"{'frames' if args.workload == 'ssf2020' else 'pairs'}/s ({args.workload})", "value": units * world * args.steps / (ms * 1e-3),
                       "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-                      "launch_mode": "one CUDA graph per step (mmcodec.GraphedForward)", "ms_per_step_eager": ms_eager / args.steps,
+                      "launch_mode": "eager launches" if args.workload == "mm-train" else "one CUDA graph per step (mmcodec.GraphedForward)", "ms_per_step_eager": ms_eager / args.steps,
                       "sum_of_kernel_ms": kernel_ms,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                      "config": {"workload": OTHER_WORKLOADS[args.workload], "units_per_gpu": units, "weights": "random init"},
+                      "config": {"workload": OTHER_WORKLOADS[args.workload], "units_per_gpu": units, "weights": "random init",
+                                 "parallelism": f"data parallel x{world}" + (", bucketed NCCL all-reduce of fp32 gradients" if args.workload == "mm-train" else ", no collective")},
                       "gpu_launches": launches,
                       "e2e": {"value": units * world * args.steps / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
                               "h2d_bytes_per_step": sum(t_.numel() * 4 for t_ in host), "d2h_bytes_per_step": sum(t_.numel() * 4 for t_ in host)},
@@ -282,19 +320,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout when the communicator is created; keep stdout for the ONE JSON line
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            warm = torch.zeros(1, device=dev)
-            dist.all_reduce(warm)          # forces communicator creation now
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        init_nccl_quietly(dist, dev)
 
     B = args.batch
     torch.manual_seed(0)

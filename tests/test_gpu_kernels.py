@@ -285,14 +285,16 @@ def test_conv_deconv_direct_golden(kernels_golden, tag):
     w = g[f"conv_{tag}_w"]
     m = mmcodec.conv(w.shape[1], w.shape[0], kernel_size=k, stride=s)
     m.weight.data.copy_(torch.from_numpy(w)); m.bias.data.copy_(torch.from_numpy(g[f"conv_{tag}_b"]))
-    y = m.to(dev())(cu(g[f"conv_{tag}_x"]))
+    with torch.no_grad():     # outside no_grad the layer records an autograd graph (training path), as the reference's does
+        y = m.to(dev())(cu(g[f"conv_{tag}_x"]))
     assert tuple(y.shape) == g[f"conv_{tag}_y"].shape
     assert np.max(np.abs(y.cpu().numpy() - g[f"conv_{tag}_y"])) < 1e-4
     k, s = (int(v) for v in g[f"deconv_{tag}_cfg"])
     w = g[f"deconv_{tag}_w"]
     m = mmcodec.deconv(w.shape[0], w.shape[1], kernel_size=k, stride=s)
     m.weight.data.copy_(torch.from_numpy(w)); m.bias.data.copy_(torch.from_numpy(g[f"deconv_{tag}_b"]))
-    y = m.to(dev())(cu(g[f"deconv_{tag}_x"]))
+    with torch.no_grad():
+        y = m.to(dev())(cu(g[f"deconv_{tag}_x"]))
     assert tuple(y.shape) == g[f"deconv_{tag}_y"].shape
     assert np.max(np.abs(y.cpu().numpy() - g[f"deconv_{tag}_y"])) < 1e-4
 

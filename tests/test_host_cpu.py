@@ -246,3 +246,52 @@ def test_batch_sharding_world_size_2_gloo():
     [p.join(60) for p in ps]
     assert res[0][1:3] == (0, 32) and res[1][1:3] == (32, 64)
     assert res[0][3] == 64.0 and res[0][4] == 2.0
+
+
+def _reducer_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch.nn as nn
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                                    # identical replicas
+    net = nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 4), nn.Linear(4, 3))
+    unused = nn.Parameter(torch.zeros(7))                   # a parameter that never receives a gradient
+    params = list(net.parameters()) + [unused]
+    red = mmcodec.GradBucketReducer(params, bucket_bytes=64)   # tiny buckets: several collectives, one left partially filled
+    x = torch.arange(12, dtype=torch.float32).reshape(2, 6) * (rank + 1)
+    net(x).pow(2).sum().backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    red.finish()
+    q.put((rank, [g.tolist() for g in local], [p.grad.tolist() for p in net.parameters()], unused.grad is None, len(red.buckets)))
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_reducer_world_size_2_gloo():
+    """Data-parallel exchange step of the training path: bucketed all-reduce averages the gradients of both ranks."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 1000
+    ps = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    res = sorted(q.get(timeout=120) for _ in ps)
+    [p.join(60) for p in ps]
+    (_, l0, a0, u0, nb), (_, l1, a1, u1, _) = res
+    assert u0 and u1 and nb >= 3
+    for g0, g1, r0, r1 in zip(l0, l1, a0, a1):
+        want = (torch.tensor(g0) + torch.tensor(g1)) / 2
+        assert torch.allclose(torch.tensor(r0), want, rtol=1e-6, atol=1e-6) and torch.allclose(torch.tensor(r1), want, rtol=1e-6, atol=1e-6)
+
+
+def test_training_glue_on_cpu():
+    """RateDistortionLoss and configure_optimizers follow examples/train.py:59-82,111-142 (host logic, no kernels)."""
+    out = {"x_hat": torch.full((2, 1, 4, 4), 0.5), "likelihoods": {"y": torch.full((2, 3, 2, 2), 0.25), "z": torch.full((2, 3, 1, 1), 0.5)}}
+    target = torch.zeros(2, 1, 4, 4)
+    res = mmcodec.RateDistortionLoss(2)(out, target)
+    assert abs(float(res["bpp_loss"]) - (24 * 2 + 6 * 1) / 32) < 1e-6 and abs(float(res["mse_loss"]) - 0.25) < 1e-7
+    assert abs(float(res["loss"]) - (1024 * 0.25 + 54 / 32)) < 1e-4
+    net = mmcodec.FactorizedPrior(8, 8)
+    opt, aux = mmcodec.configure_optimizers(net)
+    n_main = sum(len(g["params"]) for g in opt.param_groups)
+    n_aux = sum(len(g["params"]) for g in aux.param_groups)
+    assert n_aux == 1 and n_main + n_aux == len(list(net.parameters()))
