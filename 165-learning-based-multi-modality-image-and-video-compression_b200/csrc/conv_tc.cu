@@ -72,6 +72,7 @@ struct TcParams {
     int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
     int num_stages, acc_stages;
     int debug;       // profiling aid (env MMC_TC_DEBUG): 1 = no TMA traffic after priming, 2 = no main-loop MMAs, 3 = no GDN MMAs
+    int pair;        // 1: CTA-pair kernel (cta_group::2): two adjacent tiles per MMA, each CTA holds half of the B rows
     int b_resident;  // whole packed weight matrix stays in shared memory (small layers); K blocks stream A only
     int act, gdn, out_f32, out2;
     int gdn_chunk;
@@ -194,9 +195,12 @@ struct GdnCtx {
     int64_t pix_off;
     int it;
     const int64_t *pix_off_s;   // per-pixel output offsets of this tile (-1: outside the image)
+    uint32_t ready_bar_leader;  // pair mode: cluster address of the leader's gdn_ready barrier
+    uint64_t *ready_bar;        // pair mode: the leader's own gdn_ready barrier (valid in the leader CTA)
+    uint32_t rank;              // pair mode: CTA rank in the cluster
 };
 
-template <int NCH, int G>
+template <int NCH, int G, bool kPair>
 __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_s, const float *beta_s, uint32_t &gdn_phase)
 {
     const TcParams &P = g.P;
@@ -238,6 +242,29 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         if ((threadIdx.x >> 5) == 2) {
             // first epilogue warp: uniform control flow, one elected lane issues the (compile-time unrolled) MMAs
             if (g.it == 0 && grp == 0) mbar_wait(g.gload_bar, 0);
+            if (kPair) {
+                // both CTAs' x^2 tiles (and gamma halves) must be in place before the leader issues the pair MMA
+                if (elect_one()) mbar_arrive_cluster(g.ready_bar_leader);
+                __syncwarp();
+                if (g.rank == 0) {
+                    mbar_wait(g.ready_bar, gdn_phase);
+                    tc_fence_after();
+                    const uint32_t idesc = make_idesc_m256(gch * 16);
+                    const uint32_t a2 = smem_u32(g.sA2), gm = smem_u32(g.sG);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kc = 0; kc < NCH / 2; ++kc) {
+                            const uint64_t adesc = make_desc(a2 + (uint32_t)(kc * kABytes));
+                            const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * (P.Cout / 2) * 128));   // this CTA's half of gamma's rows
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma2(g.tmem_base + g.norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                        }
+                        tc_commit2(g.gdn_bar);
+                    }
+                    __syncwarp();
+                }
+            } else {
             tc_fence_after();
             const uint32_t idesc = make_idesc(gch * 16);
             const uint32_t a2 = smem_u32(g.sA2), gm = smem_u32(g.sG) + (uint32_t)(g0 * 128);
@@ -253,6 +280,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
                 tc_commit(g.gdn_bar);
             }
             __syncwarp();
+            }
         }
         mbar_wait(g.gdn_bar, gdn_phase);
         gdn_phase ^= 1;
@@ -318,22 +346,23 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
 
 enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_SCATTER = 2 };
 
-template <int kEpi, int kNCH>
+template <int kEpi, int kNCH, bool kPair>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P)
 {
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-    __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar, gload_bar, bres_bar;
+    __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar, gload_bar, bres_bar, gdn_ready_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[kMaxCout];
     __shared__ __align__(16) float beta_s[256];
     __shared__ int64_t pix_off_s[128];   // GDN epilogue: global element offset of each tile pixel (-1 = masked)
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_tile_bytes = P.Ntile * 128;
+    const int b_tile_bytes = (kPair ? P.Ntile / 2 : P.Ntile) * 128;   // pair mode: this CTA's half of the weight rows
+    const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const int stage_bytes = kABytes + (P.b_resident ? 0 : b_tile_bytes);
     uint8_t *sG = smem + (size_t)P.num_stages * stage_bytes;       // gamma: (Cout/64) tiles of [Cout][64] bf16
-    uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * 2;               // x^2:   (Cout/64) tiles of [128][64] bf16
+    uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * (kPair ? 1 : 2);   // x^2:   (Cout/64) tiles of [128][64] bf16 (pair mode: half of gamma per CTA)
     float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
     // resident weights (b_resident): one [Ntile][64] bf16 tile per K block, after the GDN / staging region
     const size_t epi_bytes = (kEpi == EPI_GDN) ? (size_t)P.Cout * P.Cout * 2 + (size_t)(P.Cout / 64) * kABytes
@@ -344,7 +373,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpiThreads); }
+        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kPair ? 2 * kEpiThreads : kEpiThreads); }
+        mbar_init(&gdn_ready_bar, 2);
         mbar_init(&gdn_bar, 1);
         mbar_init(&gload_bar, 1);
         mbar_init(&bres_bar, 1);
@@ -354,8 +384,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         if (kEpi == EPI_GDN) prefetch_tmap(&P.tmG);
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     for (int i = threadIdx.x; i < kMaxCout; i += kTcThreads) {
         bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.0f;
@@ -363,17 +398,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();     // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    // pair mode: tiles 2j and 2j+1 go to the two CTAs of a cluster (blockIdx.x = 2 * pair + rank, gridDim.x even, the host
+    // pads tiles_per_phase to an even count; an index past the last image decodes to b == B and is masked everywhere)
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         // Whole warp walks the tile / K-block loops (uniform control flow); the lane chosen by elect.sync issues.
         if (kEpi == EPI_GDN) {
             if (elect_one()) {
-                mbar_expect_tx(&gload_bar, (uint32_t)(P.Cout * P.Cout * 2));
+                const int grows = kPair ? P.Cout / 2 : P.Cout;      // pair mode: gamma rows [rank * C/2, (rank + 1) * C/2)
+                mbar_expect_tx(&gload_bar, (uint32_t)(grows * P.Cout * 2));
                 for (int kc = 0; kc < P.Cout / 64; ++kc)
-                    tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * P.Cout * 128, kc * 64, 0);
+                    tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * grows * 128, kc * 64, (int)rank * grows);
             }
             __syncwarp();
         }
@@ -392,6 +431,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         TileIter ti;
         ti.init(P, blockIdx.x);
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti.advance(P)) {
+            if (kPair) ti.init(P, tile);
             const TileCoord t = ti.coord(P);
             const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
             for (int tp = P.phase_begin[t.phase]; tp < P.phase_begin[t.phase + 1]; ++tp) {
@@ -400,7 +440,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t *a = smem + (size_t)stage * stage_bytes;
                     if (elect_one()) {
-                        if (P.debug == 1 && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
+                        if (kPair) {
+                            // the leader's barrier collects the bytes of both CTAs; only the leader arrives on it
+                            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                            if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
+                            tma_load_4d_pair(&P.tmA, fb, a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
+                            tma_load_2d_pair(&P.tmB, fb, a + kABytes, kc * 64, tap.brow + t.n0 + (int)rank * (P.Ntile / 2));
+                        } else if (P.debug == 1 && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
                             mbar_arrive(&full_bar[stage]);
                         } else {
                             mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
@@ -413,12 +459,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && (!kPair || rank == 0)) {
+        // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
         // The whole warp walks the pipeline (uniform control flow, every lane observes the barriers); one lane chosen
         // by elect.sync issues the tcgen05.mma / tcgen05.commit instructions, fully unrolled per K block so that the
         // descriptors are plain uniform-register increments.
-        const uint32_t idesc = make_idesc(P.Ntile);
+        const uint32_t idesc = kPair ? make_idesc_m256(P.Ntile) : make_idesc(P.Ntile);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -428,6 +474,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         int acc_i = 0;
         uint32_t acc_ph = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
+            if (kPair) ti.init(P, tile);
             const TileCoord t = ti.coord(P);
             const int as = acc_i;                       // accumulator ring position of this tile
             const uint32_t aphase = acc_ph;
@@ -442,6 +489,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 const uint64_t adesc = make_desc(a_addr);
                 const uint64_t bdesc = make_desc(P.b_resident ? smem_u32(sBres + (size_t)kb * b_tile_bytes) : a_addr + kABytes);
                 if (elect_one()) {
+                    if (kPair) {
+                        tc_mma2(d_tmem, adesc, bdesc, idesc, kb != 0);
+                        tc_mma2(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                        tc_mma2(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                        tc_mma2(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                        tc_commit2(&empty_bar[stage]);                          // both CTAs' producers
+                        if (kb == nkb - 1) tc_commit2(&tmem_full_bar[as]);      // both CTAs' epilogues
+                    } else {
                     if (P.debug != 2) {
                         // K=16 per step: +32 B (= +2 in descriptor units) inside the 128-byte swizzle atom
                         tc_mma(d_tmem, adesc, bdesc, idesc, kb != 0);
@@ -451,12 +506,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     }
                     tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
                     if (kb == nkb - 1) tc_commit(&tmem_full_bar[as]);   // accumulator complete -> epilogue
+                    }
                 }
                 __syncwarp();
                 if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else {
+    } else if (warp >= 2) {
         // ===================== epilogue: 8 warps, 2 per TMEM lane quarter, each pair splits the columns ============
         const int q = warp & 3;                 // TMEM lane quarter this warp can access
         const int half = (warp - 2) >> 2;       // 0: first half of the 16-column chunks, 1: second half
@@ -470,12 +526,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         ti.init(P, blockIdx.x);
         int acc_i = 0;
         uint32_t acc_ph = 0;
+        const uint32_t empty_leader = kPair ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+        const uint32_t ready_leader = kPair ? mapa_u32(smem_u32(&gdn_ready_bar), 0) : 0u;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
+            if (kPair) ti.init(P, tile);
             const TileCoord t = ti.coord(P);
             const int as = acc_i;                       // accumulator ring position of this tile
             const uint32_t aphase = acc_ph;
             const int gy = t.y0 + th, gx = t.x0 + tw;
-            const bool valid = gy < P.Gh && gx < P.Gw;
+            const bool valid = gy < P.Gh && gx < P.Gw && t.b < P.B;
             const uint32_t acc_addr = tmem_base + lane_addr + (uint32_t)(as * P.Ntile);
 
             mbar_wait(&tmem_full_bar[as], aphase);
@@ -593,21 +652,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     }
                 } else {
                     if (half == 0) pix_off_s[row] = valid ? pix_off : -1;   // published by the bar.sync inside epilogue_gdn
-                    GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it, pix_off_s};
+                    GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it, pix_off_s,
+                             ready_leader, &gdn_ready_bar, rank};
                     // (chunks per thread, norm groups): C=128 -> one 128-column norm pass; C=192 -> two 96-column passes
-                    epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1)>(g, bias_s, beta_s, gdn_phase);
+                    epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1), kPair>(g, bias_s, beta_s, gdn_phase);
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty_bar[as]);
+            if (kPair) mbar_arrive_cluster(empty_leader + (uint32_t)(as * sizeof(uint64_t)));   // the leader's MMA issuer waits for both epilogues
+            else mbar_arrive(&tmem_empty_bar[as]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (kPair) cluster_sync_all();     // nobody leaves while the peer may still signal its barriers / read its shared memory
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
     }
 }
 
@@ -804,16 +867,16 @@ static void pick_tile(int gh, int gw, int sx, int sy, int *TH, int *TW)
     }
 }
 
-template <int kEpi, int kNCH>
+template <int kEpi, int kNCH, bool kPair = false>
 static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaStream_t st, const char *name)
 {
     // dynamic shared memory available next to the kernel's static allocation (227 KB per CTA on sm_100)
     static size_t budget = 0;
     if (budget == 0) {
         cudaFuncAttributes fa;
-        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi, kNCH>));
+        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi, kNCH, kPair>));
         size_t avail = 227 * 1024 - fa.sharedSizeBytes;
-        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi, kNCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi, kNCH, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
         budget = avail;
     }
     MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
@@ -836,7 +899,30 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         Q.st_b = r % Q.B;
         Q.st_ph = r / Q.B;
     }
-    conv_tc_kernel<kEpi, kNCH><<<grid, kTcThreads, smem, st>>>(Q);
+    if (kPair) {
+        // 2-CTA clusters: even grid, as many pairs as the device can keep resident
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
+        static int max_pairs = 0;
+        if (max_pairs == 0) {
+            cfg.gridDim = dim3(kNumSMs);
+            int n = 0;
+            MMC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<kEpi, kNCH, kPair>, &cfg));
+            max_pairs = n > 0 ? n : 1;
+        }
+        grid &= ~1;
+        if (grid > 2 * max_pairs) grid = 2 * max_pairs;
+        if (grid < 2) grid = 2;
+        cfg.gridDim = dim3(grid);
+        MMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kEpi, kNCH, kPair>, Q));
+        count_launch();
+        return MMC_OK;
+    }
+    conv_tc_kernel<kEpi, kNCH, kPair><<<grid, kTcThreads, smem, st>>>(Q);
     MMC_CHECK_LAUNCH(name);
     return MMC_OK;
 }
@@ -943,6 +1029,16 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     P.tiles_y = (P.Gh + P.step_y - 1) / P.step_y;
     P.tiles_x = (P.Gw + P.step_x - 1) / P.step_x;
     int64_t tpp = (int64_t)d->B * P.tiles_y * P.tiles_x * P.n_blocks;
+    // CTA-pair kernel (cta_group::2): the 128-channel GDN layers.  One MMA covers two adjacent tiles (M = 256) and each CTA
+    // supplies half of the weight rows, which halves the weight traffic and takes the shared-memory operand reads per MMA from
+    // 8 KB to 6 KB per SM -- the N = 128 single-CTA MMA is bound by exactly that read bandwidth (profiles/README.md).
+    const bool pair_ok = pl.mode == MODE_STD && d->gdn != MMC_GDN_NONE && d->Cout == 128 && P.n_blocks == 1 && !d->out2_bf16;
+    P.pair = (pair_ok && tpp * pl.n_phases >= 4 * kNumSMs) ? 1 : 0;
+    if (const char *g = getenv("MMC_TC_PAIR")) {   // 0: never, 2: whenever the shape allows it (tests), else the default rule
+        if (atoi(g) == 0) P.pair = 0;
+        if (atoi(g) == 2) P.pair = pair_ok ? 1 : 0;
+    }
+    if (P.pair) tpp = (tpp + 1) & ~(int64_t)1;     // even tile count per phase: a pair never straddles two phases
     MMC_CHECK_ARG(tpp * P.n_phases < (1ll << 31), "%s: too many tiles", name);
     P.tiles_per_phase = (int)tpp;
     P.total_tiles = (int)(tpp * P.n_phases);
@@ -954,14 +1050,14 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
 
     size_t fixed = 1024;  // alignment slack
-    if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (size_t)(d->Cout / 64) * kABytes;
+    if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * (P.pair ? 1 : 2) + (size_t)(d->Cout / 64) * kABytes;
     if (pl.mode == MODE_SCATTER) fixed += (((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023;
     // Small layers (image-edge conv, reconstruction deconv): keep every weight tile resident in shared memory so that
     // the K blocks stream activations only (halves the L2 -> SM traffic of those layers).
     const size_t b_total = (size_t)pl.ntaps * pl.kchunks * P.Ntile * 128;
-    P.b_resident = (P.n_blocks == 1 && P.n_phases == 1 && b_total <= 96 * 1024 && fixed + b_total + 4 * kABytes <= 200 * 1024) ? 1 : 0;
+    P.b_resident = (!P.pair && P.n_blocks == 1 && P.n_phases == 1 && b_total <= 96 * 1024 && fixed + b_total + 4 * kABytes <= 200 * 1024) ? 1 : 0;
     if (P.b_resident) fixed += b_total;
-    const size_t stage_bytes = kABytes + (P.b_resident ? 0 : (size_t)P.Ntile * 128);
+    const size_t stage_bytes = kABytes + (P.b_resident ? 0 : (size_t)(P.pair ? P.Ntile / 2 : P.Ntile) * 128);
 
     // ---- tensor maps ----
     if (pl.mode == MODE_PAD8) {
@@ -983,7 +1079,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     {
         uint64_t dims[2] = {(uint64_t)pl.wcols, (uint64_t)pl.ntaps * pl.wrows};
         uint64_t str[1] = {(uint64_t)pl.wcols * 2};
-        uint32_t box[2] = {64, (uint32_t)P.Ntile};
+        uint32_t box[2] = {64, (uint32_t)(P.pair ? P.Ntile / 2 : P.Ntile)};
         uint32_t es[2] = {1, 1};
         rc = encode_map(&P.tmB, w_packed, 2, dims, str, box, es, "weights");
         if (rc) return rc;
@@ -992,7 +1088,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         MMC_CHECK_ARG(aligned16(gamma_eff_bf16), "%s: gamma must be 16-byte aligned", name);
         uint64_t dims[2] = {(uint64_t)d->Cout, (uint64_t)d->Cout};
         uint64_t str[1] = {(uint64_t)d->Cout * 2};
-        uint32_t box[2] = {64, (uint32_t)d->Cout};
+        uint32_t box[2] = {64, (uint32_t)(P.pair ? d->Cout / 2 : d->Cout)};
         uint32_t es[2] = {1, 1};
         rc = encode_map(&P.tmG, gamma_eff_bf16, 2, dims, str, box, es, "gamma");
         if (rc) return rc;
@@ -1002,6 +1098,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     if (d->gdn != MMC_GDN_NONE) {
         // one kernel per channel count (16-column chunks per epilogue thread = Cout / 32) so that each gets its own
         // register allocation: C=128 keeps 64 activations per thread in registers, C=192 keeps 96
+        if (d->Cout == 128 && P.pair) return launch_tc<EPI_GDN, 4, true>(P, fixed, stage_bytes, st, name);
         if (d->Cout == 128) return launch_tc<EPI_GDN, 4>(P, fixed, stage_bytes, st, name);
         if (d->Cout == 192) return launch_tc<EPI_GDN, 6>(P, fixed, stage_bytes, st, name);
         return launch_tc<EPI_GDN, 2>(P, fixed, stage_bytes, st, name);

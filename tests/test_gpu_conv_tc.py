@@ -150,3 +150,40 @@ def test_conv_tc_narrow_transposed_output(cin, cout, k, h, w, B):
     err = np.abs(y - ref)
     worst = np.unravel_index(np.argmax(err), err.shape)
     assert err.max() < 2e-3 * scale, f"max err {err.max():.4g} (scale {scale:.4g}) at {worst}; frac bad {(err > 2e-3 * scale).mean():.4f}"
+
+
+@pytest.mark.parametrize("transposed,cin,h,w,B,gdn", [
+    (False, 128, 200, 312, 3, L.GDN_FORWARD),    # g_a.2 class: 100 x 156 outputs per image -> 7 x 10 tiles x 3 images (odd tile count per phase)
+    (True, 192, 50, 78, 2, L.GDN_INVERSE),       # g_s.0 class: 4 deconv phases
+])
+def test_conv_tc_cta_pair_vs_single(transposed, cin, h, w, B, gdn):
+    """CTA-pair kernel (cta_group::2, two tiles per MMA, weight / gamma rows split across the pair) against the single-CTA
+    kernel on the same data (bit-identical: same products, same accumulation order) and against the CPU oracle."""
+    import os
+    rs = np.random.RandomState(h + w)
+    cout, k, s = 128, 5, 2
+    x = bf16_round(rs.standard_normal((B, cin, h, w)).astype(np.float32))
+    fan = cin * k * k / (s * s if transposed else 1)
+    wt = bf16_round((rs.standard_normal((cin, cout, k, k) if transposed else (cout, cin, k, k)) * (2.0 / np.sqrt(fan))).astype(np.float32))
+    b = rs.standard_normal(cout).astype(np.float32)
+    gw = {}
+    _gdn(rs, gw, "g", cout)
+    beta_eff, _, gamma_bf16 = ops.gdn_reparam(torch.from_numpy(gw["g.beta"]).to(dev()), torch.from_numpy(gw["g.gamma"]).to(dev()),
+                                              oracle.gdn_beta_bound(), oracle.GDN_GAMMA_BOUND, oracle.GDN_PEDESTAL, want_bf16=True)
+    xin = torch.from_numpy(x).to(dev()).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    d = ops.conv_desc(transposed, B, h, w, cin, cout, k, s, L.BF16, L.NHWC, L.BF16, L.NHWC, gdn=gdn)
+    packed = ops.conv_pack_weights(d, torch.from_numpy(wt).to(dev()))
+    outs = {}
+    for mode in ("2", "0"):      # 2 = pair kernel whenever the shape allows it, 0 = single-CTA kernel
+        os.environ["MMC_TC_PAIR"] = mode
+        try:
+            outs[mode] = ops.conv_forward_tc(d, xin, packed, torch.from_numpy(b).to(dev()), beta_eff, gamma_bf16)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("MMC_TC_PAIR", None)
+    assert torch.equal(outs["2"], outs["0"])
+    torch.set_num_threads(8)
+    ref = (oracle.conv_transpose2d if transposed else oracle.conv2d)(x, wt, b, stride=s, act=None)
+    ref = oracle.gdn_forward(ref, gw["g.beta"], gw["g.gamma"], inverse=(gdn == L.GDN_INVERSE))
+    y = outs["2"].float().permute(0, 3, 1, 2).cpu().numpy()
+    assert np.abs(y - ref).max() < 1e-2 * float(np.abs(ref).max())
