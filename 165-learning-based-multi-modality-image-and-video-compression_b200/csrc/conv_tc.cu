@@ -32,8 +32,8 @@
 
 namespace mmc {
 
-constexpr int kTcThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
-constexpr int kEpiThreads = 256;
+// warp 0 TMA, warp 1 MMA, then 4 * kParts epilogue warps: kParts warps per TMEM lane quarter split the accumulator columns
+constexpr int tc_threads(int parts) { return 64 + 128 * parts; }
 constexpr int kMaxStages = 8;
 constexpr int kMaxAccStages = 4;
 constexpr int kMaxTaps = 32;
@@ -190,7 +190,7 @@ struct GdnCtx {
     uint8_t *sA2, *sG;
     uint64_t *gdn_bar, *gload_bar;
     uint32_t tmem_base, acc_addr, lane_addr, norm_col;
-    int row, half;
+    int row, half;   // half = which of the kParts column parts this thread owns
     bool valid;
     int64_t pix_off;
     int it;
@@ -200,12 +200,13 @@ struct GdnCtx {
     uint32_t rank;              // pair mode: CTA rank in the cluster
 };
 
-template <int NCH, int G, bool kPair>
+template <int NCH, int G, bool kPair, int kParts>
 __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_s, const float *beta_s, uint32_t &gdn_phase)
 {
     const TcParams &P = g.P;
     constexpr int per = NCH / G;               // chunks of each norm group owned by this thread (its half of the group)
-    constexpr int gch = 2 * per;               // 16-column chunks per norm group (gdn_chunk / 16)
+    constexpr int gch = kParts * per;          // 16-column chunks per norm group (gdn_chunk / 16)
+    constexpr int kEpiThreads = 128 * kParts;
     float x[NCH][16];
     // chunk id of my j-th chunk: group (j / per), position (j % per) within my half of the group
     auto chunk_of = [&](int j) { return (j / per) * gch + g.half * per + (j % per); };
@@ -235,7 +236,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
     tc_fence_before();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 #pragma unroll
     for (int grp = 0; grp < G; ++grp) {
         const int g0 = grp * gch * 16;
@@ -253,7 +254,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
                     const uint32_t a2 = smem_u32(g.sA2), gm = smem_u32(g.sG);
                     if (elect_one()) {
 #pragma unroll
-                        for (int kc = 0; kc < NCH / 2; ++kc) {
+                        for (int kc = 0; kc < NCH * kParts / 4; ++kc) {
                             const uint64_t adesc = make_desc(a2 + (uint32_t)(kc * kABytes));
                             const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * (P.Cout / 2) * 128));   // this CTA's half of gamma's rows
 #pragma unroll
@@ -270,7 +271,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
             const uint32_t a2 = smem_u32(g.sA2), gm = smem_u32(g.sG) + (uint32_t)(g0 * 128);
             if (elect_one()) {
 #pragma unroll
-                for (int kc = 0; kc < (P.debug == 3 ? 0 : NCH / 2); ++kc) {   // debug 3: profiling, no norm MMAs
+                for (int kc = 0; kc < (P.debug == 3 ? 0 : NCH * kParts / 4); ++kc) {   // debug 3: profiling, no norm MMAs
                     const uint64_t adesc = make_desc(a2 + (uint32_t)(kc * kABytes));
                     const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * P.Cout * 128));
 #pragma unroll
@@ -323,12 +324,12 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         }
         // every epilogue thread is done with the norm columns (and, after the last group, with sA2)
         tc_fence_before();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
     if (G == 1 && !P.out_f32 && !P.out2) {
         // Coalesced copy-out: consecutive lanes move consecutive 16-byte chunks of one pixel, so every warp store
         // covers whole 128-byte lines (the per-row direct stores touch 32 lines per instruction).
-        constexpr int cpp = NCH * 4;               // 16-byte chunks per pixel (C / 8): 8 or 16
+        constexpr int cpp = NCH * kParts * 2;      // 16-byte chunks per pixel (C / 8): 8 or 16
         constexpr int ppi = kEpiThreads / cpp;     // pixels covered per iteration (32 or 16, a multiple of 8)
         const int et = threadIdx.x - 64;
         const int j = et % cpp, p0 = et / cpp;     // this thread always moves chunk j; pixel p0 + it * ppi
@@ -340,15 +341,16 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
             const uint4 v = *reinterpret_cast<const uint4 *>(src + (size_t)i * ppi * 128);
             if (off >= 0) *reinterpret_cast<uint4 *>(yo + off) = v;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // staging tile free for the next tile's x^2
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // staging tile free for the next tile's x^2
     }
 }
 
 enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_SCATTER = 2 };
 
-template <int kEpi, int kNCH, bool kPair>
-__global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams P)
+template <int kEpi, int kNCH, bool kPair, int kParts>
+__global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __grid_constant__ TcParams P)
 {
+    constexpr int kEpiThreads = 128 * kParts;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
     __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar, gload_bar, bres_bar, gdn_ready_bar;
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
     }
-    for (int i = threadIdx.x; i < kMaxCout; i += kTcThreads) {
+    for (int i = threadIdx.x; i < kMaxCout; i += tc_threads(kParts)) {
         bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.0f;
         if (i < 256) beta_s[i] = (kEpi == EPI_GDN && i < P.Cout) ? P.beta[i] : 1.0f;
     }
@@ -515,7 +517,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     } else if (warp >= 2) {
         // ===================== epilogue: 8 warps, 2 per TMEM lane quarter, each pair splits the columns ============
         const int q = warp & 3;                 // TMEM lane quarter this warp can access
-        const int half = (warp - 2) >> 2;       // 0: first half of the 16-column chunks, 1: second half
+        const int half = (warp - 2) >> 2;       // column part of this warp: 0 .. kParts - 1
         const int row = q * 32 + lane;          // accumulator row == pixel of the tile
         const int th = row / P.TW, tw = row - th * P.TW;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -544,7 +546,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 // ---- GEMM + col2im: column n = (ky*k + kx)*Cout + c holds x[q] . w[:, c, ky, kx] for INPUT pixel q ----
                 {
                     const int nch = P.Ntile >> 4;
-                    const int ch_lo = half ? (nch + 1) / 2 : 0, ch_hi = half ? nch : (nch + 1) / 2;
+                    const int ch_lo = (nch * half + kParts - 1) / kParts, ch_hi = (nch * (half + 1) + kParts - 1) / kParts;
                     float *srow = sStage + (size_t)row * P.spitch;
                     for (int ch = ch_lo; ch < ch_hi; ++ch) {
                         float v[16];
@@ -558,7 +560,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 // the accumulator is drained: hand the TMEM stage back before the gather pass
                 tc_fence_before();
                 mbar_arrive(&tmem_empty_bar[as]);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 {
                     // Gather: one work item per (interior input-resolution pixel a, channel c) produces the s x s output
                     // block (s*a + p); every product S[q][(ky,kx,c)] is consumed exactly once.
@@ -621,15 +623,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                         }
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");   // staging buffer free for the next tile
+                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // staging buffer free for the next tile
                 continue;
             } else {
                 const int py = t.phase / P.out_stride, px = t.phase - py * P.out_stride;
                 const int oy = gy * P.out_stride + py, ox = gx * P.out_stride + px;
                 const int64_t pix_off = (((int64_t)t.b * P.Ho + oy) * P.Wo + ox) * P.Cout + t.n0;
                 const int nch = P.Ntile >> 4;                       // 16-column chunks in this tile
-                const int ch_lo = half ? (nch + 1) / 2 : 0;
-                const int ch_hi = half ? nch : (nch + 1) / 2;
+                const int ch_lo = (nch * half + kParts - 1) / kParts;
+                const int ch_hi = (nch * (half + 1) + kParts - 1) / kParts;
                 if (kEpi == EPI_PLAIN) {
                     // two TMEM loads in flight per wait
                     for (int ch = ch_lo; ch < ch_hi; ch += 2) {
@@ -655,7 +657,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                     GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it, pix_off_s,
                              ready_leader, &gdn_ready_bar, rank};
                     // (chunks per thread, norm groups): C=128 -> one 128-column norm pass; C=192 -> two 96-column passes
-                    epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1), kPair>(g, bias_s, beta_s, gdn_phase);
+                    epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1), kPair, kParts>(g, bias_s, beta_s, gdn_phase);
                 }
             }
             tc_fence_before();
@@ -867,16 +869,16 @@ static void pick_tile(int gh, int gw, int sx, int sy, int *TH, int *TW)
     }
 }
 
-template <int kEpi, int kNCH, bool kPair = false>
+template <int kEpi, int kNCH, bool kPair = false, int kParts = 2>
 static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaStream_t st, const char *name)
 {
     // dynamic shared memory available next to the kernel's static allocation (227 KB per CTA on sm_100)
     static size_t budget = 0;
     if (budget == 0) {
         cudaFuncAttributes fa;
-        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi, kNCH, kPair>));
+        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi, kNCH, kPair, kParts>));
         size_t avail = 227 * 1024 - fa.sharedSizeBytes;
-        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi, kNCH, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi, kNCH, kPair, kParts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
         budget = avail;
     }
     MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
@@ -906,23 +908,23 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
+        cfg.blockDim = dim3(tc_threads(kParts)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
         static int max_pairs = 0;
         if (max_pairs == 0) {
             cfg.gridDim = dim3(kNumSMs);
             int n = 0;
-            MMC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<kEpi, kNCH, kPair>, &cfg));
+            MMC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<kEpi, kNCH, kPair, kParts>, &cfg));
             max_pairs = n > 0 ? n : 1;
         }
         grid &= ~1;
         if (grid > 2 * max_pairs) grid = 2 * max_pairs;
         if (grid < 2) grid = 2;
         cfg.gridDim = dim3(grid);
-        MMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kEpi, kNCH, kPair>, Q));
+        MMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kEpi, kNCH, kPair, kParts>, Q));
         count_launch();
         return MMC_OK;
     }
-    conv_tc_kernel<kEpi, kNCH, kPair><<<grid, kTcThreads, smem, st>>>(Q);
+    conv_tc_kernel<kEpi, kNCH, kPair, kParts><<<grid, tc_threads(kParts), smem, st>>>(Q);
     MMC_CHECK_LAUNCH(name);
     return MMC_OK;
 }
@@ -1033,7 +1035,15 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     // supplies half of the weight rows, which halves the weight traffic and takes the shared-memory operand reads per MMA from
     // 8 KB to 6 KB per SM -- the N = 128 single-CTA MMA is bound by exactly that read bandwidth (profiles/README.md).
     const bool pair_ok = pl.mode == MODE_STD && d->gdn != MMC_GDN_NONE && d->Cout == 128 && P.n_blocks == 1 && !d->out2_bf16;
-    P.pair = (pair_ok && tpp * pl.n_phases >= 4 * kNumSMs) ? 1 : 0;
+    // Only where the main loop is long enough to stay the bottleneck once it runs twice as fast: with fewer than ~24 K blocks per
+    // tile (the 2x2 .. 3x3-tap phases of the transposed convolutions) the GDN epilogue (~5.8k cycles per tile) takes over and
+    // the cross-CTA hand-shake of the pair kernel only adds to it (measured: g_s.4 1.54 -> 1.66 ms, g_a.2 1.27 -> 1.07 ms).
+    int min_kb = 1 << 30;
+    for (int ph = 0; ph < pl.n_phases; ++ph) {
+        const int kb = (pl.phase_begin[ph + 1] - pl.phase_begin[ph]) * pl.kchunks;
+        if (kb < min_kb) min_kb = kb;
+    }
+    P.pair = (pair_ok && min_kb >= 24 && tpp * pl.n_phases >= 4 * kNumSMs) ? 1 : 0;
     if (const char *g = getenv("MMC_TC_PAIR")) {   // 0: never, 2: whenever the shape allows it (tests), else the default rule
         if (atoi(g) == 0) P.pair = 0;
         if (atoi(g) == 2) P.pair = pair_ok ? 1 : 0;
@@ -1098,8 +1108,14 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     if (d->gdn != MMC_GDN_NONE) {
         // one kernel per channel count (16-column chunks per epilogue thread = Cout / 32) so that each gets its own
         // register allocation: C=128 keeps 64 activations per thread in registers, C=192 keeps 96
-        if (d->Cout == 128 && P.pair) return launch_tc<EPI_GDN, 4, true>(P, fixed, stage_bytes, st, name);
-        if (d->Cout == 128) return launch_tc<EPI_GDN, 4>(P, fixed, stage_bytes, st, name);
+        // 8 epilogue warps (2 column parts); C = 192 has two 96-column norm groups
+        // (measured: 16 epilogue warps are SLOWER than 8 -- g_a.0 1.05 -> 1.39 ms -- so 8 stays the default; the 4-part
+        //  instantiation is kept behind MMC_TC_PARTS=4 for experiments)
+        const bool wide = getenv("MMC_TC_PARTS") ? atoi(getenv("MMC_TC_PARTS")) == 4 : false;
+        if (d->Cout == 128 && P.pair) return wide ? launch_tc<EPI_GDN, 2, true, 4>(P, fixed, stage_bytes, st, name)
+                                                  : launch_tc<EPI_GDN, 4, true, 2>(P, fixed, stage_bytes, st, name);
+        if (d->Cout == 128) return wide ? launch_tc<EPI_GDN, 2, false, 4>(P, fixed, stage_bytes, st, name)
+                                        : launch_tc<EPI_GDN, 4, false, 2>(P, fixed, stage_bytes, st, name);
         if (d->Cout == 192) return launch_tc<EPI_GDN, 6>(P, fixed, stage_bytes, st, name);
         return launch_tc<EPI_GDN, 2>(P, fixed, stage_bytes, st, name);
     }
