@@ -66,6 +66,13 @@ ARCH, QUALITY, H, W = "bmshj2018-hyperprior", 4, 512, 768
 WORKLOAD = WORKLOADS["hyperprior"][6]
 
 
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the default workload's largest kernels, from the
+# committed `ncu --set full` capture profiles/r01_ncu_conv_tc_full.csv (batch 64 x 768x512); equals the algorithmic bytes of these
+# layers (bf16 activations in + out, weights from L2), i.e. nothing is re-read from HBM.
+NCU_DRAM_BYTES = {"g_s.4|tc": 1.612476e9 + 1.565251e9, "g_a.2|tc": 1.612066e9 + 0.391675e9, "g_a.0|tc": 0.408368e9 + 1.556180e9,
+                  "g_s.6|tc": 1.611466e9 + 0.288178e9}
+
+
 def shard_range(total: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of `total` independent units for `rank` (no collective needed)."""
     base, rem = divmod(total, world)
@@ -437,7 +444,9 @@ def main():
         achieved = f / (ms * 1e-3) / 1e12
         total_f = sum(v[1] for v in layer_prof.values())
         roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak_tf,
+                    "traffic": NCU_DRAM_BYTES.get(name) if (args.workload == "hyperprior" and B == 64) else None,
+                    "traffic_source": "profiles/r01_ncu_conv_tc_full.csv (ncu --set full, same command, bytes per launch)", "peak_source": peak_src,
                     "ms_per_launch": ms, "flops_per_launch": f,
                     "step_tflops": total_f / (ms_total / args.steps * 1e-3) / 1e12,
                     "layer_ms": {k: round(v[0], 4) for k, v in layer_prof.items()}}
