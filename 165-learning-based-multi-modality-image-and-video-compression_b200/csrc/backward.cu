@@ -1,8 +1,8 @@
 // backward.cu -- elementwise / reduction kernels of the training step (HBM-bound), next to the tensor-core input- and
 // weight-gradient kernels (conv_tc.cu with the adjoint descriptor, wgrad_tc.cu).
 //
-// Backward of (file:line relative to /root/reference/CompressAI; formulas: SURVEY.md Appendix E, checked against float64
-// autograd of the oracle):
+// Backward of (file:line relative to /root/reference/CompressAI; formulas: SURVEY.md Appendix E, checked in tests/ against float64
+// autograd of the same ops):
 //   ReLU / LeakyReLU after conv()/deconv()        compressai/models/google.py:254-269,363-377
 //   bias of nn.Conv2d / nn.ConvTranspose2d        compressai/models/utils.py:128-146
 //   GDN / IGDN                                    compressai/layers/gdn.py:77-92
@@ -143,6 +143,21 @@ __global__ void __launch_bounds__(kBwBlock) reparam_bwd_kernel(const float *__re
     }
 }
 
+// |x| (fp32) -> bf16: the h_a input of ScaleHyperprior (models/google.py:283) on the training path; backward g * sign(x)
+__global__ void __launch_bounds__(kBwBlock) abs_bf16_kernel(const float *__restrict__ x, int64_t n, __nv_bfloat16 *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = __float2bfloat16_rn(fabsf(x[i]));
+}
+__global__ void __launch_bounds__(kBwBlock) abs_bwd_kernel(const __nv_bfloat16 *__restrict__ g, const float *__restrict__ x, int64_t n, float *__restrict__ dx)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float xv = x[i], gv = __bfloat162float(g[i]);
+        dx[i] = xv > 0.0f ? gv : (xv < 0.0f ? -gv : 0.0f);
+    }
+}
+
 __device__ __forceinline__ float phi_f(float t) { return 0.3989422804014327f * expf(-0.5f * t * t); }
 __device__ __forceinline__ float Phi_f(float t) { return 0.5f * erfcf(-0.7071067811865476f * t); }
 
@@ -246,6 +261,26 @@ int mmc_reparam_bwd(const float *p, const float *dp_eff, float bound, int64_t n,
     MMC_CHECK_ARG(p && dp_eff && dp, "mmc_reparam_bwd: NULL buffer");
     reparam_bwd_kernel<<<elementwise_grid(n, kBwBlock), kBwBlock, 0, (cudaStream_t)stream>>>(p, dp_eff, bound, n, dp);
     MMC_CHECK_LAUNCH("mmc_reparam_bwd");
+    return MMC_OK;
+}
+
+int mmc_abs_to_bf16(const float *x, int64_t n, void *out, void *stream)
+{
+    MMC_CHECK_ARG(n >= 0, "mmc_abs_to_bf16: n < 0");
+    if (n == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && out, "mmc_abs_to_bf16: NULL buffer");
+    abs_bf16_kernel<<<elementwise_grid(n, kBwBlock), kBwBlock, 0, (cudaStream_t)stream>>>(x, n, (__nv_bfloat16 *)out);
+    MMC_CHECK_LAUNCH("mmc_abs_to_bf16");
+    return MMC_OK;
+}
+
+int mmc_abs_bwd(const void *grad_out, const float *x, int64_t n, float *dx, void *stream)
+{
+    MMC_CHECK_ARG(n >= 0, "mmc_abs_bwd: n < 0");
+    if (n == 0) return MMC_OK;
+    MMC_CHECK_ARG(grad_out && x && dx, "mmc_abs_bwd: NULL buffer");
+    abs_bwd_kernel<<<elementwise_grid(n, kBwBlock), kBwBlock, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)grad_out, x, n, dx);
+    MMC_CHECK_LAUNCH("mmc_abs_bwd");
     return MMC_OK;
 }
 

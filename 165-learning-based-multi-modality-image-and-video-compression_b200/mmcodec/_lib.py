@@ -76,6 +76,8 @@ _PROTOS = {
     "mmc_gdn_bwd_t": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "mmc_gdn_bwd_dx": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "mmc_reparam_bwd": (c_int, [c_vp, c_vp, c_f32, c_i64, c_vp, c_vp]),
+    "mmc_abs_to_bf16": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "mmc_abs_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "mmc_gc_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mmc_eb_backward": (c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(EbParams), c_f32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "mmc_wgrad_finalize": (c_int, [c_vp, c_int, c_int, c_int, c_f32, c_vp, c_int, c_vp, c_vp]),

@@ -148,10 +148,10 @@ class _ConvFn(torch.autograd.Function):
         conv = ctx.conv
         g, g_planar = _grad_nhwc_bf16(gy, ctx.out_fmt, conv.out_channels)
         if ctx.act_module is not None:
-            if ctx.out_fmt != "nhwc_bf16":
-                raise NotImplementedError("activation backward is implemented for NHWC bf16 layer outputs")
+            if ctx.out_fmt == "nchw_f32":
+                raise NotImplementedError("activation backward is implemented for NHWC layer outputs")
             act = L.ACT_LEAKY_RELU if isinstance(ctx.act_module, nn.LeakyReLU) else L.ACT_RELU
-            g = ops.act_bwd(g, y, act)
+            g = ops.act_bwd(g, y if y.dtype == torch.bfloat16 else ops.to_bf16(y), act)   # only the sign of y matters
         dx, dw, db = _conv_backward(conv, x, ctx.in_fmt, g, g_planar, ctx.needs_input_grad[0])
         return dx, dw, db, None, None, None, None
 
@@ -177,8 +177,6 @@ class _ConvGdnFn(torch.autograd.Function):
 def run_layers_train(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0):
     """``transforms.run_layers`` with autograd: one Function per fused launch."""
     from .transforms import parse_layers
-    if out2 == 1:
-        raise NotImplementedError("the |y| secondary output has no training path yet (ScaleHyperprior)")
     steps = parse_layers(layers)
     if not steps:
         raise ValueError("empty transform stack")
@@ -211,9 +209,11 @@ def run_layers_train(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0
         fmt = ofmt
     if out_fmt == "nchw_f32" and fmt == "nhwc_f32":
         cur = cur.permute(0, 3, 1, 2)
-    if out2 == 2:
+    if out2:
         src = cur.permute(0, 2, 3, 1) if (out_fmt == "nchw_f32" and fmt == "nhwc_f32") else cur
-        return cur, cast_bf16(src)
+        if src.dtype != torch.float32:
+            raise NotImplementedError("the secondary output is derived from an fp32 primary output on the training path")
+        return cur, (_AbsBf16Fn.apply(src) if out2 == 1 else cast_bf16(src))
     return cur
 
 
@@ -232,6 +232,25 @@ class _CastBf16Fn(torch.autograd.Function):
 
 def cast_bf16(x: Tensor) -> Tensor:
     return _CastBf16Fn.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else ops.to_bf16(x)
+
+
+class _AbsBf16Fn(torch.autograd.Function):
+    """torch.abs(y) as the bf16 input of h_a (models/google.py:283)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        out = torch.empty_like(x, dtype=torch.bfloat16)
+        L.check(L.lib().mmc_abs_to_bf16(x.data_ptr(), x.numel(), out.data_ptr(), ops._stream()))
+        ctx.save_for_backward(x)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        L.check(L.lib().mmc_abs_bwd(g.contiguous().data_ptr(), x.data_ptr(), x.numel(), dx.data_ptr(), ops._stream()))
+        return dx
 
 
 class _AddNoiseFn(torch.autograd.Function):

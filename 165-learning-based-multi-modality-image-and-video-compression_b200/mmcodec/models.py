@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from . import autograd as AG
 from . import ops
 from .entropy_models import EntropyBottleneck, GaussianConditional
 from .layers import GDN, conv, deconv
@@ -60,6 +61,30 @@ class CompressionModel(nn.Module):
 
     def aux_loss(self):
         return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def _bottleneck(self, v: Tensor):
+        """entropy_bottleneck(v) -> (v_hat as bf16 for the next transform, likelihoods); training mode draws the uniform
+        noise with torch's generator and records the backward (``_noise_override`` lets the parity tests inject the oracle's)."""
+        eb = self.entropy_bottleneck
+        if self.training:
+            v_hat, lik = AG.eb_forward(v, eb, self._draw("z", v))
+            return AG.cast_bf16(v_hat), lik
+        _, lik, v_hat_bf16 = ops.eb_forward(v, eb._params(), None, eb._lik_bound(), want_bf16=True, lut=eb._eval_lut())
+        return v_hat_bf16, lik
+
+    def _conditional(self, y: Tensor, scales: Tensor, means):
+        """gaussian_conditional(y, scales, means) -> (y_hat as bf16, likelihoods)"""
+        gc = self.gaussian_conditional
+        bound, lb = gc.lower_bound_scale._sync_bound(), gc._lik_bound()
+        if self.training:
+            y_hat, lik = AG.gc_forward(y, scales, means, self._draw("y", y), bound, lb)
+            return AG.cast_bf16(y_hat), lik
+        _, lik, y_hat_bf16 = ops.gc_forward(y, scales, means, None, bound, lb, want_bf16=True)
+        return y_hat_bf16, lik
+
+    def _draw(self, key: str, like: Tensor) -> Tensor:
+        noise = getattr(self, "_noise_override", None) or {}
+        return noise[key].to(like.device) if key in noise else torch.empty_like(like).uniform_(-0.5, 0.5)
 
     def _tag_layer_names(self):
         """Give every conv its state_dict prefix (g_a.0, h_s.4, ...) for profiling labels."""
@@ -122,12 +147,9 @@ class FactorizedPrior(CompressionModel):
 
     def forward(self, x):
         """models/google.py:172-182"""
-        eb = self.entropy_bottleneck
         y = run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32")
         y_l = _nhwc_to_logical(y)
-        noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
-        y_hat, y_lik, y_hat_bf16 = ops.eb_forward(y_l, eb._params(), noise, eb._lik_bound(), want_bf16=True,
-                                                  lut=None if self.training else eb._eval_lut())
+        y_hat_bf16, y_lik = self._bottleneck(y_l)
         x_hat = run_layers(list(self.g_s), y_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nchw_f32")
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik}}
 
@@ -188,17 +210,10 @@ class ScaleHyperprior(CompressionModel):
 
     def forward(self, x):
         """models/google.py:281-295"""
-        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         y, z = self._analysis(x)
-        z_l = _nhwc_to_logical(z)
-        z_noise = torch.empty_like(z_l).uniform_(-0.5, 0.5) if self.training else None
-        z_hat, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True,
-                                                  lut=None if self.training else eb._eval_lut())
+        z_hat_bf16, z_lik = self._bottleneck(_nhwc_to_logical(z))
         scales_hat = run_layers(list(self.h_s), z_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nhwc_f32")
-        y_l = _nhwc_to_logical(y)
-        y_noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
-        y_hat, y_lik, y_hat_bf16 = ops.gc_forward(y_l, _nhwc_to_logical(scales_hat), None, y_noise,
-                                                  gc.lower_bound_scale._sync_bound(), gc._lik_bound(), want_bf16=True)
+        y_hat_bf16, y_lik = self._conditional(_nhwc_to_logical(y), _nhwc_to_logical(scales_hat), None)
         x_hat = run_layers(list(self.g_s), y_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nchw_f32")
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}
 
@@ -294,17 +309,10 @@ class MeanScaleHyperprior(ScaleHyperprior):
 
     def forward(self, x):
         """models/google.py:379-391"""
-        eb, gc = self.entropy_bottleneck, self.gaussian_conditional
         y, z = self._analysis(x)
-        z_l = _nhwc_to_logical(z)
-        z_noise = torch.empty_like(z_l).uniform_(-0.5, 0.5) if self.training else None
-        z_hat, z_lik, z_hat_bf16 = ops.eb_forward(z_l, eb._params(), z_noise, eb._lik_bound(), want_bf16=True,
-                                                  lut=None if self.training else eb._eval_lut())
+        z_hat_bf16, z_lik = self._bottleneck(_nhwc_to_logical(z))
         scales_hat, means_hat = self._gaussian_params(z_hat_bf16.permute(0, 2, 3, 1))
-        y_l = _nhwc_to_logical(y)
-        y_noise = torch.empty_like(y_l).uniform_(-0.5, 0.5) if self.training else None
-        y_hat, y_lik, y_hat_bf16 = ops.gc_forward(y_l, _nhwc_to_logical(scales_hat), _nhwc_to_logical(means_hat), y_noise,
-                                                  gc.lower_bound_scale._sync_bound(), gc._lik_bound(), want_bf16=True)
+        y_hat_bf16, y_lik = self._conditional(_nhwc_to_logical(y), _nhwc_to_logical(scales_hat), _nhwc_to_logical(means_hat))
         x_hat = run_layers(list(self.g_s), y_hat_bf16.permute(0, 2, 3, 1), "nhwc_bf16", "nchw_f32")
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}
 

@@ -309,6 +309,10 @@ MMC_API int mmc_gdn_bwd_dx(const void *grad_out, const void *x, const float *nor
  * d = dp_eff * 2 max(p, bound); dp = d * [(p >= bound) | (d < 0)] */
 MMC_API int mmc_reparam_bwd(const float *p, const float *dp_eff, float bound, int64_t n, float *dp, void *stream);
 
+/* torch.abs(y) feeding h_a (models/google.py:283) on the training path: out = bf16(|x|); backward dx = g * sign(x) */
+MMC_API int mmc_abs_to_bf16(const float *x, int64_t n, void *out, void *stream);
+MMC_API int mmc_abs_bwd(const void *grad_out, const float *x, int64_t n, float *dx, void *stream);
+
 /* GaussianConditional.forward backward (entropy_models.py:692-731): gradients of the bounded likelihood w.r.t. the
  * input (noise mode only; round() has zero gradient), the scales (through the scale LowerBound) and the means.
  * dx / dmeans may be NULL. */

@@ -193,15 +193,15 @@ def _h_a(sd, y, act):
     return conv(sd, "h_a.4", z)
 
 
-def hyperprior_forward(sd, x):
-    """ScaleHyperprior.forward: models/google.py:281-295"""
+def hyperprior_forward(sd, x, noise=None):
+    """ScaleHyperprior.forward: models/google.py:281-295; training mode when ``noise`` = {"z", "y"} holds the uniform draws"""
     y = _seq_g_a(sd, x)
     z = _h_a(sd, torch.abs(y), F.relu)
-    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z)
+    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z, None if noise is None else noise["z"])
     s = F.relu(deconv(sd, "h_s.0", z_hat))
     s = F.relu(deconv(sd, "h_s.2", s))
     scales_hat = F.relu(conv(sd, "h_s.4", s, stride=1))
-    y_hat, y_lik = gc_forward(y, scales_hat)
+    y_hat, y_lik = gc_forward(y, scales_hat, noise=None if noise is None else noise["y"])
     x_hat = _seq_g_s(sd, y_hat)
     return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "y": y, "z": z, "z_hat": z_hat,
             "scales_hat": scales_hat, "y_hat": y_hat}
@@ -214,14 +214,14 @@ def _mean_scale_params(sd, z_hat):
     return conv(sd, "h_s.4", s, stride=1)
 
 
-def mean_scale_forward(sd, x):
-    """MeanScaleHyperprior.forward: models/google.py:379-391"""
+def mean_scale_forward(sd, x, noise=None):
+    """MeanScaleHyperprior.forward: models/google.py:379-391; ``noise``: see hyperprior_forward"""
     y = _seq_g_a(sd, x)
     z = _h_a(sd, y, F.leaky_relu)
-    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z)
+    z_hat, z_lik = eb_forward(sd, "entropy_bottleneck", z, None if noise is None else noise["z"])
     gaussian_params = _mean_scale_params(sd, z_hat)
     scales_hat, means_hat = gaussian_params.chunk(2, 1)
-    y_hat, y_lik = gc_forward(y, scales_hat, means_hat)
+    y_hat, y_lik = gc_forward(y, scales_hat, means_hat, noise=None if noise is None else noise["y"])
     x_hat = _seq_g_s(sd, y_hat)
     return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "y": y, "z": z, "z_hat": z_hat,
             "scales_hat": scales_hat, "means_hat": means_hat, "y_hat": y_hat}

@@ -281,3 +281,45 @@ def test_mm_branch_training_step_vs_oracle():
     res = step(depth.to(dev()), x.to(dev()))
     assert all(bool(torch.isfinite(v).all()) for v in res.values())
     assert float((net_d.tran_conv1.weight.detach() - before).abs().max()) > 0
+
+
+@pytest.mark.parametrize("arch,cls,N,M", [("factorized", mmcodec.FactorizedPrior, 128, 192), ("hyperprior", mmcodec.ScaleHyperprior, 128, 192),
+                                          ("mean-scale", mmcodec.MeanScaleHyperprior, 128, 192)])
+def test_zoo_models_training_step_vs_oracle(arch, cls, N, M):
+    """CompressionModel.forward in training mode + RateDistortionLoss backward for the three zoo families vs fp32 autograd over
+    the restated reference ops with the same noise; then one TrainStep (Adam + aux Adam) through the public training API."""
+    from weights import make_image, make_state_dict
+    sd = {k: torch.from_numpy(v) for k, v in make_state_dict(arch, N, M, seed=0).items()}
+    net = cls(N, M)
+    net.update()
+    net.load_state_dict({**net.state_dict(), **sd})
+    net = net.to(dev()).train()
+    x = torch.from_numpy(make_image(2, 64, 128, seed=5))
+    gen = torch.Generator().manual_seed(3)
+    yshape, zshape = (2, M, 4, 8), (2, N, 1, 2)
+    noise = {"z": torch.empty(yshape if arch == "factorized" else zshape).uniform_(-0.5, 0.5, generator=gen),
+             "y": torch.empty(yshape).uniform_(-0.5, 0.5, generator=gen)}
+    crit = mmcodec.RateDistortionLoss(3)
+    sd_ref = {k: v.clone().requires_grad_(True) if v.is_floating_point() else v for k, v in sd.items()}
+    torch.set_num_threads(8)
+    out_ref = tp.FORWARD[arch](sd_ref, x, noise["z"]) if arch == "factorized" else tp.FORWARD[arch](sd_ref, x, noise)
+    loss_ref = crit(out_ref, x)
+    loss_ref["loss"].backward()
+    net._noise_override = noise
+    out = net(x.to(dev()))
+    loss = crit(out, x.to(dev()))
+    loss["loss"].backward()
+    assert abs(float(loss["loss"].detach()) - float(loss_ref["loss"].detach())) / float(loss_ref["loss"].detach()) < 0.03
+    stats = []
+    for name, p in net.named_parameters():
+        ref_g = sd_ref[name].grad
+        if ref_g is None or float(ref_g.norm()) < 1e-12:
+            continue
+        assert p.grad is not None, name
+        stats.append((cos(p.grad, ref_g), float(p.grad.double().norm().cpu() / ref_g.double().norm()), name))
+    print(arch, "worst:", sorted(stats)[:4])
+    assert all(c > 0.93 and 0.85 < r < 1.15 for c, r, _ in stats), sorted(stats)[:5]
+    assert len(stats) > 30
+    net._noise_override = None
+    res = mmcodec.TrainStep(net, None, quality=3)(x.to(dev()))
+    assert all(bool(torch.isfinite(v).all()) for v in res.values())
