@@ -204,6 +204,7 @@ template <int NCH, int G, bool kPair, int kParts>
 __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_s, const float *beta_s, uint32_t &gdn_phase)
 {
     const TcParams &P = g.P;
+    const bool inverse = P.gdn == MMC_GDN_INVERSE;
     constexpr int per = NCH / G;               // chunks of each norm group owned by this thread (its half of the group)
     constexpr int gch = kParts * per;          // 16-column chunks per norm group (gdn_chunk / 16)
     constexpr int kEpiThreads = 128 * kParts;
@@ -305,8 +306,9 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float n = bt[i] + nrm[u][i];
-                    const float r = rsqrt_fast(n);
-                    x[j][i] = (P.gdn == MMC_GDN_INVERSE) ? x[j][i] * (n * r) : x[j][i] * r;
+                    float f = rsqrt_fast(n);
+                    if (inverse) f *= n;          // IGDN: sqrt(n) = n * rsqrt(n)
+                    x[j][i] *= f;
                 }
                 const float *y = x[j];
                 if (G == 1 && !P.out_f32 && !P.out2) {
@@ -552,9 +554,12 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                         float v[16];
                         tmem_ld16(acc_addr + (ch << 4), v);
                         tmem_ld_wait();
-                        float4 *dst = reinterpret_cast<float4 *>(srow + (ch << 4));
+                        // scalar stores with an ODD row pitch: conflict-free here (lanes = rows) and in the gather below
+                        // (lanes = neighbouring pixels = neighbouring rows); 16-byte stores would need a pitch that is a
+                        // multiple of 4 and make the gather 4-way bank conflicted
+                        float *dst = srow + (ch << 4);
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        for (int i = 0; i < 16; ++i) dst[i] = v[i];
                     }
                 }
                 // the accumulator is drained: hand the TMEM stage back before the gather pass
@@ -1022,8 +1027,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         P.TH = 8; P.TW = 16;
         P.step_y = P.TH - pl.halo_lo - pl.halo_hi; P.step_x = P.TW - pl.halo_lo - pl.halo_hi;
         P.off_y = P.off_x = pl.halo_lo;
-        P.spitch = P.Ntile + 4;
-        if (((P.spitch / 4) & 1) == 0) P.spitch += 4;   // pitch/4 odd: conflict-free 16-byte row-strided stores
+        P.spitch = P.Ntile | 1;                          // odd pitch (floats): see the staging stores in the kernel
     } else {
         pick_tile(P.Gh, P.Gw, pl.mode == MODE_PAD8 ? 1 : P.a_sx, P.a_sy, &P.TH, &P.TW);
         P.step_y = P.TH; P.step_x = P.TW; P.off_y = P.off_x = 0;
