@@ -34,6 +34,9 @@ namespace mmc {
 
 // warp 0 TMA, warp 1 MMA, then 4 * kParts epilogue warps: kParts warps per TMEM lane quarter split the accumulator columns
 constexpr int tc_threads(int parts) { return 64 + 128 * parts; }
+// Pair kernel: the GDN norm contraction stays a per-CTA (cta_group::1) MMA on the CTA's own x^2 tile and a full copy of gamma, so the two
+// epilogues of a pair never wait for each other (a pair-wide GDN MMA needs a cross-CTA hand-shake per tile and was slower).
+constexpr bool kPairGdnShared = false;
 constexpr int kMaxStages = 8;
 constexpr int kMaxAccStages = 4;
 constexpr int kMaxTaps = 32;
@@ -244,7 +247,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         if ((threadIdx.x >> 5) == 2) {
             // first epilogue warp: uniform control flow, one elected lane issues the (compile-time unrolled) MMAs
             if (g.it == 0 && grp == 0) mbar_wait(g.gload_bar, 0);
-            if (kPair) {
+            if (kPair && kPairGdnShared) {
                 // both CTAs' x^2 tiles (and gamma halves) must be in place before the leader issues the pair MMA
                 if (elect_one()) mbar_arrive_cluster(g.ready_bar_leader);
                 __syncwarp();
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const int stage_bytes = kABytes + (P.b_resident ? 0 : b_tile_bytes);
     uint8_t *sG = smem + (size_t)P.num_stages * stage_bytes;       // gamma: (Cout/64) tiles of [Cout][64] bf16
-    uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * (kPair ? 1 : 2);   // x^2:   (Cout/64) tiles of [128][64] bf16 (pair mode: half of gamma per CTA)
+    uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * ((kPair && kPairGdnShared) ? 1 : 2);   // x^2:   (Cout/64) tiles of [128][64] bf16 (pair mode: half of gamma per CTA)
     float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
     // resident weights (b_resident): one [Ntile][64] bf16 tile per K block, after the GDN / staging region
     const size_t epi_bytes = (kEpi == EPI_GDN) ? (size_t)P.Cout * P.Cout * 2 + (size_t)(P.Cout / 64) * kABytes
@@ -413,10 +416,10 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
         // Whole warp walks the tile / K-block loops (uniform control flow); the lane chosen by elect.sync issues.
         if (kEpi == EPI_GDN) {
             if (elect_one()) {
-                const int grows = kPair ? P.Cout / 2 : P.Cout;      // pair mode: gamma rows [rank * C/2, (rank + 1) * C/2)
+                const int grows = (kPair && kPairGdnShared) ? P.Cout / 2 : P.Cout;      // shared pair GDN: gamma rows [rank * C/2, (rank + 1) * C/2)
                 mbar_expect_tx(&gload_bar, (uint32_t)(grows * P.Cout * 2));
                 for (int kc = 0; kc < P.Cout / 64; ++kc)
-                    tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * grows * 128, kc * 64, (int)rank * grows);
+                    tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * grows * 128, kc * 64, (kPair && kPairGdnShared) ? (int)rank * grows : 0);
             }
             __syncwarp();
         }
@@ -1064,7 +1067,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
 
     size_t fixed = 1024;  // alignment slack
-    if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * (P.pair ? 1 : 2) + (size_t)(d->Cout / 64) * kABytes;
+    if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * ((P.pair && kPairGdnShared) ? 1 : 2) + (size_t)(d->Cout / 64) * kABytes;
     if (pl.mode == MODE_SCATTER) fixed += (((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023;
     // Small layers (image-edge conv, reconstruction deconv): keep every weight tile resident in shared memory so that
     // the K blocks stream activations only (halves the L2 -> SM traffic of those layers).
@@ -1102,7 +1105,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         MMC_CHECK_ARG(aligned16(gamma_eff_bf16), "%s: gamma must be 16-byte aligned", name);
         uint64_t dims[2] = {(uint64_t)d->Cout, (uint64_t)d->Cout};
         uint64_t str[1] = {(uint64_t)d->Cout * 2};
-        uint32_t box[2] = {64, (uint32_t)(P.pair ? d->Cout / 2 : d->Cout)};
+        uint32_t box[2] = {64, (uint32_t)((P.pair && kPairGdnShared) ? d->Cout / 2 : d->Cout)};
         uint32_t es[2] = {1, 1};
         rc = encode_map(&P.tmG, gamma_eff_bf16, 2, dims, str, box, es, "gamma");
         if (rc) return rc;
