@@ -233,3 +233,23 @@ def test_compress_decompress_round_trip(models_golden, arch, cls, N, M):
     assert abs(mine - ref) / ref < 0.01, (mine, ref)
     # (No coded-size vs entropy-estimate check: with these synthetic weights ~20 % of the y likelihoods sit on the 1e-9
     #  floor, i.e. 30 estimated bits each, while the coder spends a few bypass nibbles on them.)
+
+
+def test_graphed_forward_replays_exactly():
+    """mmcodec.GraphedForward: the whole forward captured as one CUDA graph gives the eager results, also on new inputs."""
+    net, _ = load(mmcodec.MeanScaleHyperprior, "mean-scale", 192, 320)
+    x0 = torch.from_numpy(make_image(2, 64, 128, seed=21)).to(dev())
+    x1 = torch.from_numpy(make_image(2, 64, 128, seed=22)).to(dev())
+    g = mmcodec.GraphedForward(net, x0)
+    with torch.no_grad():
+        for x in (x0, x1, x0):
+            want = net(x)
+            got = g(x)
+            torch.cuda.synchronize()
+            assert torch.equal(got["x_hat"], want["x_hat"])
+            for k in want["likelihoods"]:
+                assert torch.equal(got["likelihoods"][k], want["likelihoods"][k])
+    with pytest.raises(ValueError):
+        g(torch.zeros(1, 3, 64, 128, device=dev()))
+    with pytest.raises(RuntimeError):
+        mmcodec.GraphedForward(net, x0.cpu())
