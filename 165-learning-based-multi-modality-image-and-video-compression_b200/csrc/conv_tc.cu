@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kPair ? 2 * kEpiThreads : kEpiThreads); }
+        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], (kPair ? 2 : 1) * (kEpiThreads / 32)); }   // one arrival per epilogue warp
         mbar_init(&gdn_ready_bar, 2);
         mbar_init(&gdn_bar, 1);
         mbar_init(&gload_bar, 1);
@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                 }
                 // the accumulator is drained: hand the TMEM stage back before the gather pass
                 tc_fence_before();
-                mbar_arrive(&tmem_empty_bar[as]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
                 {
                     // Gather: one work item per (interior input-resolution pixel a, channel c) produces the s x s output
@@ -669,8 +670,11 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                 }
             }
             tc_fence_before();
-            if (kPair) mbar_arrive_cluster(empty_leader + (uint32_t)(as * sizeof(uint64_t)));   // the leader's MMA issuer waits for both epilogues
-            else mbar_arrive(&tmem_empty_bar[as]);
+            __syncwarp();          // every lane's TMEM reads of this accumulator are complete: one arrival per warp
+            if (lane == 0) {
+                if (kPair) mbar_arrive_cluster(empty_leader + (uint32_t)(as * sizeof(uint64_t)));   // the leader's MMA issuer waits for both epilogues
+                else mbar_arrive(&tmem_empty_bar[as]);
+            }
         }
     }
 
