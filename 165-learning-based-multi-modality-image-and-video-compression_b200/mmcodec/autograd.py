@@ -92,6 +92,9 @@ def _conv_backward(conv, x_saved, in_fmt, g, g_planar, need_dx):
             dx = _run([adj], g_planar, "nchw_f32", "nhwc_bf16")
         else:
             dx = _run([adj], g[..., :cout] if g.shape[-1] != cout else g, "nhwc_bf16", "nhwc_bf16")
+        if not transposed and in_fmt != "nchw_f32" and dx.shape[1:3] != x_saved.shape[1:3]:
+            # odd input size: the adjoint deconv also produces the gradient of the (non-existent) padding row / column
+            dx = dx[:, : x_saved.shape[1], : x_saved.shape[2]].contiguous()
     return dx, dw.contiguous().to(conv.weight.dtype), dbias
 
 

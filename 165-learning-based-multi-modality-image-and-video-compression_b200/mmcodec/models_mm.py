@@ -61,38 +61,77 @@ class MaskedConv2d(Conv2d):
 
 
 class ESA(nn.Module):
-    """Enhanced spatial attention gate (google.py:1432-1459).  Stock torch ops."""
+    """Enhanced spatial attention gate (google.py:1432-1459).
+
+    Every convolution (1x1 conv1 / conv_f / conv4, 3x3 conv_max / conv3 / conv3_, and the stride-2 3x3 conv2) runs on the
+    tensor-core conv kernel with NHWC bf16 activations, forward and backward; the max-pool (7 / 3), the bilinear upsampling, the
+    add and the sigmoid gate are torch elementwise / pooling ops on the same bf16 channels-last tensors.  conv2 has padding 0,
+    which the kernel's padding-k/2 addressing expresses exactly as the padding-1 convolution of the map shifted by one pixel:
+    conv_p0(x)[o] = conv_p1(pad_top_left(x))[o + 1]."""
 
     def __init__(self, n_feats: int):
         super().__init__()
         f = n_feats // 4
-        self.conv1 = nn.Conv2d(n_feats, f, 1)
-        self.conv_f = nn.Conv2d(f, f, 1)
-        self.conv_max = nn.Conv2d(f, f, 3, padding=1)
-        self.conv2 = nn.Conv2d(f, f, 3, stride=2, padding=0)
-        self.conv3 = nn.Conv2d(f, f, 3, padding=1)
-        self.conv3_ = nn.Conv2d(f, f, 3, padding=1)
-        self.conv4 = nn.Conv2d(f, n_feats, 1)
+        self.conv1 = Conv2d(n_feats, f, 1)
+        self.conv_f = Conv2d(f, f, 1)
+        self.conv_max = Conv2d(f, f, 3, padding=1)
+        self.conv2 = Conv2d(f, f, 3, stride=2, padding=0)
+        self.conv3 = Conv2d(f, f, 3, padding=1)
+        self.conv3_ = Conv2d(f, f, 3, padding=1)
+        self.conv4 = Conv2d(f, n_feats, 1)
         self.sigmoid = nn.Sigmoid()
         self.relu = nn.ReLU(inplace=True)
 
-    def forward(self, x: Tensor) -> Tensor:
-        c1_ = self.conv1(x)
-        c1 = self.conv2(c1_)
+    def _conv2_p1(self) -> nn.Module:
+        """conv2 as a padding-1 layer sharing conv2's parameters (not a registered child: the state_dict is the reference's)."""
+        m = getattr(self, "_conv2_alias", None)
+        if m is None:
+            c = self.conv2
+            m = Conv2d(c.in_channels, c.out_channels, 3, stride=2, padding=1)
+            m._mmc_name = getattr(c, "_mmc_name", "conv2")
+            object.__setattr__(self, "_conv2_alias", m)
+        m._parameters["weight"], m._parameters["bias"] = self.conv2.weight, self.conv2.bias
+        return m
+
+    # Training keeps the gate on torch's bf16 ops: its seven small convolutions per block (42 layers in the depth branch) each cost
+    # ~5 launches in the backward pass and made the step host-bound (measured 52.3 vs 42.9 ms per 4-pair step); the kernel path
+    # below is what inference uses (19.0 -> 17.7 ms per 8 pairs).  Both are covered by the parity tests.
+    train_on_kernels = False
+
+    def _forward_torch(self, x: Tensor) -> Tensor:
+        """(B, C, H, W) channels-last view -> same, stock torch ops (google.py:1445-1459)."""
+        conv = lambda m, t: nn.Conv2d.forward(m, t)      # the reference's op, not the fused executor
+        c1_ = conv(self.conv1, x)
+        c1 = conv(self.conv2, c1_)
         v_max = F.max_pool2d(c1, kernel_size=7, stride=3)
-        v_range = self.relu(self.conv_max(v_max))
-        c3 = self.relu(self.conv3(v_range))
-        c3 = self.conv3_(c3)
+        v_range = self.relu(conv(self.conv_max, v_max))
+        c3 = self.relu(conv(self.conv3, v_range))
+        c3 = conv(self.conv3_, c3)
         c3 = F.interpolate(c3, (x.size(2), x.size(3)), mode="bilinear", align_corners=False)
-        cf = self.conv_f(c1_)
-        c4 = self.conv4(c3 + cf)
-        return x * self.sigmoid(c4)
+        cf = conv(self.conv_f, c1_)
+        return x * self.sigmoid(conv(self.conv4, c3 + cf))
 
     def forward_nhwc_bf16(self, x: Tensor) -> Tensor:
-        """x: (B, H, W, C) bf16 -> same; the torch ops see a channels-last (B, C, H, W) view, so no layout copy."""
-        with torch.autocast("cuda", dtype=torch.bfloat16):      # records an autograd graph when x requires grad
-            y = self.forward(x.permute(0, 3, 1, 2))
-        return y.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+        """x: (B, H, W, C) bf16 -> same (records an autograd graph when x or the parameters require grad)."""
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad and not self.train_on_kernels:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = self._forward_torch(x.permute(0, 3, 1, 2))
+            return y.to(torch.bfloat16).permute(0, 2, 3, 1).contiguous()
+        B, H, W, _ = x.shape
+        c1_ = run_layers([self.conv1], x, "nhwc_bf16", "nhwc_bf16")
+        ho, wo = (H - 3) // 2 + 1, (W - 3) // 2 + 1
+        c1 = run_layers([self._conv2_p1()], F.pad(c1_, (0, 0, 1, 0, 1, 0)), "nhwc_bf16", "nhwc_bf16")[:, 1:1 + ho, 1:1 + wo]
+        v_max = F.max_pool2d(c1.permute(0, 3, 1, 2), kernel_size=7, stride=3).permute(0, 2, 3, 1).contiguous()
+        c3 = run_layers([self.conv_max, self.relu, self.conv3, self.relu, self.conv3_], v_max, "nhwc_bf16", "nhwc_bf16")
+        c3 = F.interpolate(c3.permute(0, 3, 1, 2), (H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+        cf = run_layers([self.conv_f], c1_, "nhwc_bf16", "nhwc_bf16")
+        c4 = run_layers([self.conv4], (c3 + cf).contiguous(), "nhwc_bf16", "nhwc_bf16")
+        return x * torch.sigmoid(c4)
+
+    def forward(self, x: Tensor) -> Tensor:
+        """(B, C, H, W) fp32 in / out, as the reference's module."""
+        return _nhwc_to_logical(self.forward_nhwc_bf16(_to_nhwc_bf16(x))).float()
 
 
 class Encoder1(nn.Module):

@@ -213,7 +213,8 @@ def test_entropy_bottleneck_backward():
 # ---------------------------------------------------------------------------------------------------------
 # end to end: training-mode forward + backward of the second-modality branch vs the oracle's autograd (fp32 CPU)
 # ---------------------------------------------------------------------------------------------------------
-def test_mm_branch_training_step_vs_oracle():
+@pytest.mark.parametrize("esa_on_kernels", [False, True])
+def test_mm_branch_training_step_vs_oracle(esa_on_kernels):
     import json
     import os
     from weights import make_mm_state_dict
@@ -247,6 +248,7 @@ def test_mm_branch_training_step_vs_oracle():
     # ours: guide maps from the reference (so both sides see identical inputs), training mode, same noise
     net_d.train()
     net_d._noise_override = noise
+    mm.ESA.train_on_kernels = esa_on_kernels
     hidden = {k: v.to(dev()) for k, v in ref_r["hidden"].items()}
     out = net_d(depth.to(dev()), hidden)
     loss = crit(out, depth.to(dev()))
@@ -279,6 +281,7 @@ def test_mm_branch_training_step_vs_oracle():
     step = mmcodec.TrainStep(net_d, net_r.eval(), quality=3)
     before = net_d.tran_conv1.weight.detach().clone()
     res = step(depth.to(dev()), x.to(dev()))
+    mm.ESA.train_on_kernels = False
     assert all(bool(torch.isfinite(v).all()) for v in res.values())
     assert float((net_d.tran_conv1.weight.detach() - before).abs().max()) > 0
 
