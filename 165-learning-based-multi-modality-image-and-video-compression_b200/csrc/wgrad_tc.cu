@@ -259,8 +259,12 @@ int mmc_wgrad_tc(const void *s_nhwc, const void *l_nhwc, int64_t B, int Cs, int 
     MMC_CHECK_ARG(kblocks < (1ll << 31), "%s: too many K blocks", name);
     P.kblocks = (int)kblocks;
     const int tiles = k * k * P.m_tiles * P.n_tiles;
-    // split K so that the grid covers the machine about twice; every split non-empty
+    // split K so that the grid covers the machine about twice -- but every split pays 128 x Ntile fp32 atomics in its epilogue, so a
+    // split must carry enough K blocks to amortise them (measured: a 192x192 3x3 layer on 4 x 32x48 pixels took 1.6 ms with 17
+    // splits of 6 K blocks, all of it atomics); every split non-empty
     int splits = (2 * kNumSMs + tiles - 1) / tiles;
+    const int max_splits = (P.kblocks + 31) / 32;
+    if (splits > max_splits) splits = max_splits;
     if (splits > P.kblocks) splits = P.kblocks;
     if (splits < 1) splits = 1;
     P.kb_per_split = (P.kblocks + splits - 1) / splits;
