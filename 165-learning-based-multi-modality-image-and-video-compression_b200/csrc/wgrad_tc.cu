@@ -203,6 +203,27 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     }
 }
 
+// Narrow tensors (image / reconstruction gradient, <= 8 channels): gather the k x k neighbourhood of every low-resolution
+// position into one NHWC row [q][tap][8 ch], so that the weight gradient of the edge layers is ONE k = 1 GEMM with N = k*k*8
+// columns instead of k*k GEMMs with a 16-wide N tile (the MMA costs the same ~115 cycles for N = 16 as for N = 208).
+__global__ void __launch_bounds__(256) im2col8_kernel(const uint4 *__restrict__ x, int H, int W, int k, int stride, int Hs, int Ws, int64_t n,
+                                                     uint4 *__restrict__ out)
+{
+    const int kk = k * k, pad = k / 2;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const int tap = (int)(i % kk);
+        int64_t q = i / kk;
+        const int qx = (int)(q % Ws); q /= Ws;
+        const int qy = (int)(q % Hs);
+        const int64_t b = q / Hs;
+        const int iy = qy * stride + tap / k - pad, ix = qx * stride + tap % k - pad;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (b * H + iy) * (int64_t)W + ix);
+        out[i] = v;
+    }
+}
+
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float *__restrict__ ws, int taps, int Cs, int Cl, float scale,
                                                             const float *__restrict__ mask, int accumulate, float *__restrict__ dw)
 {
@@ -303,6 +324,17 @@ int mmc_wgrad_tc(const void *s_nhwc, const void *l_nhwc, int64_t B, int Cs, int 
     const int grid = P.total_items < kNumSMs ? P.total_items : kNumSMs;
     wgrad_tc_kernel<<<grid, kWgThreads, 1024 + (size_t)stages * stage_bytes, (cudaStream_t)stream>>>(P);
     MMC_CHECK_LAUNCH(name);
+    return MMC_OK;
+}
+
+int mmc_im2col8(const void *x_nhwc8, int64_t B, int H, int W, int k, int stride, int Hs, int Ws, void *out, void *stream)
+{
+    MMC_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && Hs >= 1 && Ws >= 1 && (k == 1 || k == 3 || k == 5) && (stride == 1 || stride == 2), "mmc_im2col8: bad argument");
+    if (B == 0) return MMC_OK;
+    MMC_CHECK_ARG(x_nhwc8 && out && aligned16(x_nhwc8) && aligned16(out), "mmc_im2col8: NULL or unaligned buffer");
+    const int64_t n = B * Hs * Ws * k * k;
+    im2col8_kernel<<<elementwise_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)x_nhwc8, H, W, k, stride, Hs, Ws, n, (uint4 *)out);
+    MMC_CHECK_LAUNCH("mmc_im2col8");
     return MMC_OK;
 }
 

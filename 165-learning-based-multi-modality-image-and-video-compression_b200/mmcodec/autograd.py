@@ -79,9 +79,9 @@ def _conv_backward(conv, x_saved, in_fmt, g, g_planar, need_dx):
         dbias = ops.colsum(g)[:cout].to(conv.bias.dtype)
     x_nhwc = ops.nchw_to_nhwc8(x_saved) if in_fmt == "nchw_f32" else x_saved
     if transposed:      # S = input (low resolution), L = grad_output
-        dw = ops.wgrad(x_nhwc, g, k, s, name=name)[:cin, :cout]
+        dw = (ops.wgrad_edge(x_nhwc, g, k, s, name=name) if g.shape[-1] == 8 and cout <= 8 else ops.wgrad(x_nhwc, g, k, s, name=name))[:cin, :cout]
     else:               # S = grad_output, L = input
-        dw = ops.wgrad(g, x_nhwc, k, s, name=name)[:cout, :cin]
+        dw = (ops.wgrad_edge(g, x_nhwc, k, s, name=name) if x_nhwc.shape[-1] == 8 and cin <= 8 else ops.wgrad(g, x_nhwc, k, s, name=name))[:cout, :cin]
     mask = getattr(conv, "mask", None)
     if mask is not None:
         dw = dw * mask          # MaskedConv2d: masked taps never receive gradient (their weights are re-zeroed every forward)

@@ -503,6 +503,21 @@ def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.
     return dw
 
 
+def wgrad_edge(s_nhwc: Tensor, l_nhwc8: Tensor, k: int, stride: int, name: str = "conv") -> Tensor:
+    """Weight gradient (Cs, 8, k, k) of an edge layer whose high-resolution side has <= 8 channels (padded to 8): the k x k
+    neighbourhoods are gathered into k*k*8 channels and the gradient is one k = 1 GEMM (see mmc_im2col8)."""
+    _require_cuda(s_nhwc, l_nhwc8)
+    s_nhwc, l_nhwc8 = s_nhwc.contiguous(), l_nhwc8.contiguous()
+    B, Hs, Ws, Cs = s_nhwc.shape
+    _, H, W, c8 = l_nhwc8.shape
+    if c8 != 8:
+        raise ValueError("wgrad_edge expects the narrow tensor padded to 8 channels")
+    col = torch.empty((B, Hs, Ws, k * k * 8), dtype=torch.bfloat16, device=s_nhwc.device)
+    L.check(L.lib().mmc_im2col8(_ptr(l_nhwc8), B, H, W, k, stride, Hs, Ws, _ptr(col), _stream()))
+    dw = wgrad(s_nhwc, col, 1, 1, name=name)                       # (Cs, k*k*8, 1, 1)
+    return dw.reshape(Cs, k, k, 8).permute(0, 3, 1, 2)
+
+
 def nchw_to_nhwc8(x: Tensor) -> Tensor:
     """fp32 NCHW tensor with <= 8 channels -> bf16 NHWC with the channels zero-padded to 8 (no spatial padding)."""
     _require_cuda(x)

@@ -285,6 +285,10 @@ MMC_API int mmc_add(const float *a, const float *b, int64_t n, float *out, void 
  * (Cs, Cl, k, k) weight-gradient layout. */
 MMC_API int mmc_wgrad_tc(const void *s_nhwc, const void *l_nhwc, int64_t B, int Cs, int Cl, int Hs, int Ws, int Hl, int Wl,
                          int k, int stride, float *workspace, void *stream);
+/* Edge layers (image input / reconstruction gradient with <= 8 channels): out[b][qy][qx][tap][8] = x[b][qy*stride + ky - k/2]
+ * [qx*stride + kx - k/2][0..7] (zero outside), NHWC bf16 with 8 channels in, k*k*8 channels out; the weight gradient is then one
+ * mmc_wgrad_tc call with k = 1 and Cl = k*k*8. */
+MMC_API int mmc_im2col8(const void *x_nhwc8, int64_t B, int H, int W, int k, int stride, int Hs, int Ws, void *out, void *stream);
 MMC_API int mmc_wgrad_finalize(const float *workspace, int k, int Cs, int Cl, float scale, const float *mask, int accumulate,
                                float *dw, void *stream);
 
