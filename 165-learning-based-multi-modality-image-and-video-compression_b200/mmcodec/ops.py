@@ -494,6 +494,11 @@ def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.
     s_nhwc, l_nhwc = s_nhwc.contiguous(), l_nhwc.contiguous()
     B, Hs, Ws, Cs = s_nhwc.shape
     _, Hl, Wl, Cl = l_nhwc.shape
+    if stride == 1 and mask is None and Cs % 128 != 0 and Cl % 128 == 0 and Cs <= 256 and (Hs, Ws) == (Hl, Wl):
+        # Stride 1: the two sides are interchangeable (dW[cs][cl][k] = R[cl][cs][K-1-k] with the roles swapped).  Put the side
+        # whose channel count fills the 128-row M tiles on M (tran_conv: 384 x 192 instead of a half-empty second tile of 192).
+        r = wgrad(l_nhwc, s_nhwc, k, 1, scale, None, name)
+        return r.permute(1, 0, 2, 3).flip(2, 3).contiguous()
     ws = torch.zeros((k * k, Cs, Cl), dtype=torch.float32, device=s_nhwc.device)
     dw = torch.empty((Cs, Cl, k, k), dtype=torch.float32, device=s_nhwc.device)
     with _Timed(name + "|wgrad", 2.0 * Cs * Cl * k * k * B * Hs * Ws if _profile is not None else 0.0):
