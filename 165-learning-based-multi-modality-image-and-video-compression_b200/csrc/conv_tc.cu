@@ -1045,7 +1045,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     // CTA-pair kernel (cta_group::2): the 128-channel GDN layers.  One MMA covers two adjacent tiles (M = 256) and each CTA
     // supplies half of the weight rows, which halves the weight traffic and takes the shared-memory operand reads per MMA from
     // 8 KB to 6 KB per SM -- the N = 128 single-CTA MMA is bound by exactly that read bandwidth (profiles/README.md).
-    const bool pair_ok = pl.mode == MODE_STD && d->gdn != MMC_GDN_NONE && d->Cout == 128 && P.n_blocks == 1 && !d->out2_bf16;
+    const bool pair_ok = pl.mode == MODE_STD && d->Cout == 128 && P.Ntile == 128 && P.n_blocks == 1 && !d->out2_bf16;
     // Only where the main loop is long enough to stay the bottleneck once it runs twice as fast: with fewer than ~24 K blocks per
     // tile (the 2x2 .. 3x3-tap phases of the transposed convolutions) the GDN epilogue (~5.8k cycles per tile) takes over and
     // the cross-CTA hand-shake of the pair kernel only adds to it (measured: g_s.4 1.54 -> 1.66 ms, g_a.2 1.27 -> 1.07 ms).
@@ -1054,7 +1054,11 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         const int kb = (pl.phase_begin[ph + 1] - pl.phase_begin[ph]) * pl.kchunks;
         if (kb < min_kb) min_kb = kb;
     }
-    P.pair = (pair_ok && min_kb >= 24 && tpp * pl.n_phases >= 4 * kNumSMs) ? 1 : 0;
+    // (the same threshold holds for the plain bias / activation epilogue: ssf2020's 128 -> 128 encoder layers 0.90 -> 0.73 ms per GOP
+    //  with the pair kernel, its transposed-conv decoder layers 0.92 -> 0.98 ms)
+    int need_kb = 24;
+    if (const char *g = getenv("MMC_TC_PAIR_MINKB")) need_kb = atoi(g);
+    P.pair = (pair_ok && min_kb >= need_kb && tpp * pl.n_phases >= 4 * kNumSMs) ? 1 : 0;
     if (const char *g = getenv("MMC_TC_PAIR")) {   // 0: never, 2: whenever the shape allows it (tests), else the default rule
         if (atoi(g) == 0) P.pair = 0;
         if (atoi(g) == 2) P.pair = pair_ok ? 1 : 0;
@@ -1130,6 +1134,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         if (d->Cout == 192) return launch_tc<EPI_GDN, 6>(P, fixed, stage_bytes, st, name);
         return launch_tc<EPI_GDN, 2>(P, fixed, stage_bytes, st, name);
     }
+    if (P.pair) return launch_tc<EPI_PLAIN, 0, true, 2>(P, fixed, stage_bytes, st, name);
     return launch_tc<EPI_PLAIN, 0>(P, fixed, stage_bytes, st, name);
 }
 
