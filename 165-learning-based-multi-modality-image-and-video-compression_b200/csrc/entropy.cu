@@ -737,6 +737,87 @@ __global__ void __launch_bounds__(kBlock) bits_kernel(const float *__restrict__ 
     block_atomic_add(acc, red, bits);
 }
 
+// -------------------------------------------------------------------------------------------
+// pmf_to_quantized_cdf on the device (compressai/cpp_exts/ops/ops.cpp:40-109 via entropy_models.py:206-214): one CTA per
+// table row.  Integer algorithm, bit-exact with the reference: round(pmf * 2^p) frequencies (the tail mass is the last
+// symbol), renormalised prefix sums, then every zero-frequency symbol steals one count from the cheapest donor (first index
+// among equals).  The scan over symbols is inherently sequential; the donor search and the shifts run across the CTA.
+// -------------------------------------------------------------------------------------------
+constexpr int kCdfThreads = 256;
+
+__global__ void __launch_bounds__(kCdfThreads) pmf_to_cdf_kernel(const float *__restrict__ pmf, int64_t pmf_pitch, const float *__restrict__ tail_mass,
+                                                                 const int32_t *__restrict__ pmf_length, int max_len, int precision,
+                                                                 int32_t *__restrict__ cdf_out, int32_t *__restrict__ status)
+{
+    extern __shared__ uint32_t c[];                 // [max_len + 2]
+    __shared__ unsigned long long red_key[kCdfThreads / 32];
+    __shared__ uint32_t total_s;
+    __shared__ int bad_s;
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const int n = pmf_length[row] + 1;              // symbols incl. the tail-mass symbol
+    const float scale = (float)(1u << precision);
+    if (tid == 0) { total_s = 0; bad_s = 0; c[0] = 0; }
+    __syncthreads();
+    uint32_t part = 0;
+    for (int i = tid; i < n; i += kCdfThreads) {
+        const float p = (i < n - 1) ? pmf[row * pmf_pitch + i] : tail_mass[row];
+        if (!(p >= 0.0f) || isinf(p)) bad_s = 1;
+        const uint32_t f = (uint32_t)roundf(p * scale);
+        c[i + 1] = f;
+        part += f;
+    }
+    atomicAdd(&total_s, part);
+    __syncthreads();
+    int32_t *out = cdf_out + (int64_t)row * (max_len + 2);
+    if (bad_s || total_s == 0) {
+        if (tid == 0) status[row] = MMC_EDOMAIN;
+        for (int i = tid; i < max_len + 2; i += kCdfThreads) out[i] = 0;
+        return;
+    }
+    if (tid == 0) {
+        const uint64_t one = (uint64_t)1 << precision;
+        const uint32_t total = total_s;
+        uint32_t run = 0;
+        for (int i = 0; i <= n; ++i) {
+            run += (uint32_t)((one * c[i]) / total);
+            c[i] = run;
+        }
+        c[n] = 1u << precision;
+    }
+    __syncthreads();
+    int fail = 0;
+    for (int i = 0; i < n; ++i) {
+        if (c[i] != c[i + 1]) continue;               // uniform: everybody reads the same shared values
+        // cheapest donor: smallest frequency > 1, first index among equals  ->  min over (freq << 32 | index)
+        unsigned long long best = ~0ull;
+        for (int j = tid; j < n; j += kCdfThreads) {
+            const uint32_t f = c[j + 1] - c[j];
+            if (f > 1) {
+                const unsigned long long key = ((unsigned long long)f << 32) | (uint32_t)j;
+                if (key < best) best = key;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            if (other < best) best = other;
+        }
+        if ((tid & 31) == 0) red_key[tid >> 5] = best;
+        __syncthreads();
+        best = red_key[0];
+#pragma unroll
+        for (int w = 1; w < kCdfThreads / 32; ++w)
+            if (red_key[w] < best) best = red_key[w];
+        if (best == ~0ull) { fail = 1; break; }
+        const int donor = (int)(uint32_t)best;
+        if (donor < i) { for (int j = donor + 1 + tid; j <= i; j += kCdfThreads) c[j]--; }
+        else           { for (int j = i + 1 + tid; j <= donor; j += kCdfThreads) c[j]++; }
+        __syncthreads();
+    }
+    if (tid == 0) status[row] = fail ? MMC_EDOMAIN : MMC_OK;
+    for (int i = tid; i < max_len + 2; i += kCdfThreads) out[i] = (i <= n) ? (int32_t)c[i] : 0;
+}
+
 }  // namespace mmc
 
 using namespace mmc;
@@ -817,6 +898,25 @@ int mmc_channel_indexes(int64_t outer, int64_t C, int64_t inner, int32_t *out, v
     channel_indexes_kernel<<<elementwise_grid(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
         ChanIndex{(uint32_t)C, (uint32_t)inner}, n, out);
     MMC_CHECK_LAUNCH("mmc_channel_indexes");
+    return MMC_OK;
+}
+
+int mmc_pmf_to_quantized_cdf(const float *pmf, int64_t pmf_pitch, const float *tail_mass, const int32_t *pmf_length, int rows, int max_len,
+                             int precision, int32_t *cdf, int32_t *status, void *stream)
+{
+    const char *name = "mmc_pmf_to_quantized_cdf";
+    MMC_CHECK_ARG(rows >= 0 && max_len >= 1 && precision >= 1 && precision <= 30 && pmf_pitch >= max_len, "%s: bad argument", name);
+    if (rows == 0) return MMC_OK;
+    MMC_CHECK_ARG(pmf && tail_mass && pmf_length && cdf && status, "%s: NULL buffer", name);
+    const size_t smem = (size_t)(max_len + 2) * sizeof(uint32_t);
+    MMC_UNSUPPORTED(smem > 200 * 1024, "%s: rows longer than %d symbols are not supported", name, 200 * 1024 / 4 - 2);
+    static bool attr = false;
+    if (!attr) {
+        MMC_CHECK_CUDA(cudaFuncSetAttribute(pmf_to_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    pmf_to_cdf_kernel<<<rows, kCdfThreads, smem, (cudaStream_t)stream>>>(pmf, pmf_pitch, tail_mass, pmf_length, max_len, precision, cdf, status);
+    MMC_CHECK_LAUNCH(name);
     return MMC_OK;
 }
 

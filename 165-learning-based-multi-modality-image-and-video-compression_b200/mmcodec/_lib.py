@@ -79,6 +79,7 @@ _PROTOS = {
     "mmc_abs_to_bf16": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "mmc_abs_bwd": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "mmc_gc_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_f32, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mmc_pmf_to_quantized_cdf": (c_int, [c_vp, c_i64, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "mmc_eb_backward": (c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(EbParams), c_f32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "mmc_im2col8": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "mmc_wgrad_finalize": (c_int, [c_vp, c_int, c_int, c_int, c_f32, c_vp, c_int, c_vp, c_vp]),

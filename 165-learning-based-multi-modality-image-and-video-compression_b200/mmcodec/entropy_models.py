@@ -86,7 +86,10 @@ class EntropyModel(nn.Module):
         return cls.dequantize(inputs, means)
 
     def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):
-        """entropy_models.py:206-214"""
+        """entropy_models.py:206-214 (on the device when the model lives there: one kernel for the whole table)"""
+        if pmf.is_cuda:
+            return ops.pmf_to_quantized_cdf_device(pmf[:, :max_length], tail_mass, pmf_length.to(pmf.device), max_length,
+                                                   self.entropy_coder_precision)
         cdf = torch.zeros((len(pmf_length), max_length + 2), dtype=torch.int32)
         pmf, tail_mass = pmf.detach().cpu(), tail_mass.detach().cpu()
         for i, p in enumerate(pmf):
@@ -369,7 +372,9 @@ class GaussianConditional(EntropyModel):
         pmf = upper - lower
         tail_mass = 2 * lower[:, :1]
         dev = self.scale_table.device
-        self._quantized_cdf = self._pmf_to_cdf(pmf, tail_mass, pmf_length, max_length).to(dev)
+        # the pmf itself is evaluated with the reference's CPU ops (bit-identical tables); the integer CDF construction runs on
+        # the device when the model lives there
+        self._quantized_cdf = self._pmf_to_cdf(pmf.to(dev), tail_mass.to(dev), pmf_length, max_length).to(dev)
         self._offset = (-pmf_center).to(dev)
         self._cdf_length = (pmf_length + 2).to(dev)
 

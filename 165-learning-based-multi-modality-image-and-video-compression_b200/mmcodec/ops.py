@@ -262,6 +262,22 @@ def pmf_to_quantized_cdf(pmf, precision: int = 16):
     return cdf.tolist()
 
 
+def pmf_to_quantized_cdf_device(pmf: Tensor, tail_mass: Tensor, pmf_length: Tensor, max_length: int, precision: int = 16) -> Tensor:
+    """EntropyModel._pmf_to_cdf for all rows at once on the device: int32 (rows, max_length + 2), bit-exact with the reference."""
+    _require_cuda(pmf, tail_mass, pmf_length)
+    pmf = _f32c(pmf.detach())
+    rows = pmf.shape[0]
+    tail = _f32c(tail_mass.detach().reshape(-1))
+    lens = pmf_length.detach().to(torch.int32).contiguous()
+    cdf = torch.empty((rows, max_length + 2), dtype=torch.int32, device=pmf.device)
+    status = torch.empty(rows, dtype=torch.int32, device=pmf.device)
+    L.check(L.lib().mmc_pmf_to_quantized_cdf(_ptr(pmf), pmf.shape[1], _ptr(tail), _ptr(lens), rows, int(max_length), int(precision),
+                                             _ptr(cdf), _ptr(status), _stream()))
+    if int(status.min().item()) != 0:
+        raise ValueError("Invalid `pmf`: negative, non-finite or all-zero row, or no symbol can donate frequency")
+    return cdf
+
+
 def _i32np(t):
     a = t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
     return np.ascontiguousarray(a, dtype=np.int32)

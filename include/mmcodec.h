@@ -323,6 +323,13 @@ MMC_API int mmc_abs_bwd(const void *grad_out, const float *x, int64_t n, float *
 MMC_API int mmc_gc_backward(const float *x, const float *scales, const float *means, const float *noise, const float *grad_lik,
                             float scale_bound, float likelihood_bound, int64_t n, float *dx, float *dscales, float *dmeans,
                             void *stream);
+/* EntropyModel._pmf_to_cdf (entropy_models.py:206-214) with compressai._CXX.pmf_to_quantized_cdf (cpp_exts/ops/ops.cpp:40-109)
+ * for every row of a table at once, on the device: row r codes pmf[r][0 .. pmf_length[r]) followed by tail_mass[r];
+ * cdf is int32 [rows][max_len + 2] (unused tail zero-filled), status[r] = MMC_OK or MMC_EDOMAIN (negative / non-finite / all-zero
+ * pmf, or no symbol can donate frequency).  Bit-exact with the reference's integer algorithm. */
+MMC_API int mmc_pmf_to_quantized_cdf(const float *pmf, int64_t pmf_pitch, const float *tail_mass, const int32_t *pmf_length, int rows,
+                                     int max_len, int precision, int32_t *cdf, int32_t *status, void *stream);
+
 /* EntropyBottleneck.forward backward, noise mode (entropy_models.py:457-540): dx and the packed parameter gradients
  * dparams [C][58] fp32 (ADDED into; order: _matrix0..4 (3,9,9,9,3), _bias0..4 (3,3,3,3,1), _factor0..3 (3 each)),
  * already chained through softplus / tanh of the raw parameters. */

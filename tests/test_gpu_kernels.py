@@ -366,3 +366,43 @@ def test_eb_eval_lut_equals_direct_evaluation(kernels_golden):
     with torch.no_grad():
         eb._bias0.add_(0.25)
     assert not torch.equal(eb._eval_lut(), lut0)
+
+
+def test_pmf_to_quantized_cdf_device_bit_exact(kernels_golden):
+    """Device CDF construction (one CTA per table row) vs the reference's own outputs and vs the host implementation:
+    KAT of tests/test_ops.py:104-106, the GaussianConditional table of the zoo models (64 x 3133, most symbols need a stolen
+    count), random pmfs with zeros; domain errors as in ops.cpp:46-52."""
+    g = kernels_golden
+    rs = np.random.RandomState(4)
+    rows = [np.array([0.1, 0.2, 0.0, 0.0], dtype=np.float32)] + [np.asarray(p_[:n_], dtype=np.float32) for p_, n_ in zip(g["cdf_pmfs"], g["cdf_lens"])]
+    for n in (3, 17, 200, 1500):
+        p = rs.dirichlet(np.full(n, 0.05)).astype(np.float32)
+        p[rs.rand(n) < 0.4] = 0.0
+        p[rs.randint(n)] = max(float(p.max()), 0.5)
+        rows.append(p)
+    max_len = max(len(r) for r in rows) - 1
+    pmf = np.zeros((len(rows), max_len), np.float32)
+    tail = np.zeros(len(rows), np.float32)
+    lens = np.zeros(len(rows), np.int32)
+    for i, r in enumerate(rows):
+        pmf[i, : len(r) - 1], tail[i], lens[i] = r[:-1], r[-1], len(r) - 1
+    got = ops.pmf_to_quantized_cdf_device(cu(pmf), cu(tail), torch.from_numpy(lens).to(dev()), max_len, 16).cpu().numpy()
+    for i, r in enumerate(rows):
+        want = np.array(ops.pmf_to_quantized_cdf(r, 16), dtype=np.int64)
+        assert np.array_equal(got[i, : len(want)], want), i
+        assert not got[i, len(want):].any()
+    assert np.array_equal(got[0, :5], g["cdf_kat"].astype(np.int64))                     # the reference's known-answer test
+    for i, (c_, n_) in enumerate(zip(g["cdf_cdfs"], g["cdf_lens"])):                     # the reference's own outputs
+        assert np.array_equal(got[1 + i, : n_ + 1], c_[: n_ + 1].astype(np.int64)), i
+    # the zoo's GaussianConditional tables: update() on the device reproduces the CPU model's tables bit for bit
+    gc_cpu = mmcodec.GaussianConditional(None)
+    gc_cpu.update_scale_table(mmcodec.get_scale_table())
+    gc_dev = mmcodec.GaussianConditional(None).to(dev())
+    gc_dev.update_scale_table(mmcodec.get_scale_table())
+    assert torch.equal(gc_dev._quantized_cdf.cpu(), gc_cpu._quantized_cdf) and torch.equal(gc_dev._cdf_length.cpu(), gc_cpu._cdf_length)
+    with pytest.raises(ValueError):
+        ops.pmf_to_quantized_cdf_device(cu(np.array([[0.5, -0.1]], np.float32)), cu(np.array([0.1], np.float32)),
+                                        torch.tensor([2], dtype=torch.int32, device=dev()), 2, 16)
+    with pytest.raises(ValueError):
+        ops.pmf_to_quantized_cdf_device(cu(np.zeros((1, 3), np.float32)), cu(np.zeros(1, np.float32)),
+                                        torch.tensor([3], dtype=torch.int32, device=dev()), 3, 16)
