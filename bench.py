@@ -393,12 +393,21 @@ def main():
         else:
             # symbol / compress path: pinned host images in, int32 symbols+indexes (or rANS byte strings) on the host out
             x_dev = torch.empty_like(x)
+            pinned = {}
 
             def host_step():
                 x_dev.copy_(x_host, non_blocking=True)
                 o = step_fn(x_dev)
                 if call == "symbols":
-                    return {k: v.cpu() for k, v in o.items() if torch.is_tensor(v)}
+                    res_ = {}
+                    for k, v in o.items():
+                        if torch.is_tensor(v):
+                            if k not in pinned:       # pinned int32 result buffers, allocated once (memory format of the device tensor)
+                                pinned[k] = torch.empty_like(v, device="cpu").pin_memory()
+                            pinned[k].copy_(v, non_blocking=True)
+                            res_[k] = pinned[k]
+                    torch.cuda.current_stream().synchronize()
+                    return res_
                 return o
             host_step()
             barrier()
