@@ -74,6 +74,7 @@ struct TcParams {
     int kchunks;     // K boxes per tap (ceil(Cin / 64); 1 in MODE_PAD8)
     int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
     int num_stages, acc_stages;
+    int direct_store; // GDN epilogue: 32-byte vector stores straight from registers instead of the shared-memory staged copy-out
     int debug;       // profiling aid (env MMC_TC_DEBUG): 1 = no TMA traffic after priming, 2 = no main-loop MMAs, 3 = no GDN MMAs
     int pair;        // 1: CTA-pair kernel (cta_group::2): two adjacent tiles per MMA, each CTA holds half of the B rows
     int b_resident;  // whole packed weight matrix stays in shared memory (small layers); K blocks stream A only
@@ -314,7 +315,16 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
                     x[j][i] *= f;
                 }
                 const float *y = x[j];
-                if (G == 1 && !P.out_f32 && !P.out2) {
+                if (G == 1 && !P.out_f32 && !P.out2 && P.direct_store) {
+                    // one 256-bit store per 16-channel chunk: a full 32-byte sector, no staging round trip and no extra barriers
+                    if (g.valid) {
+                        __nv_bfloat16 *dst = (__nv_bfloat16 *)P.y + g.pix_off + c0;
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst),
+                                     "r"(pack_bf16(y[0], y[1])), "r"(pack_bf16(y[2], y[3])), "r"(pack_bf16(y[4], y[5])), "r"(pack_bf16(y[6], y[7])),
+                                     "r"(pack_bf16(y[8], y[9])), "r"(pack_bf16(y[10], y[11])), "r"(pack_bf16(y[12], y[13])), "r"(pack_bf16(y[14], y[15]))
+                                     : "memory");
+                    }
+                } else if (G == 1 && !P.out_f32 && !P.out2) {
                     // stage the bf16 result in the (now idle) x^2 tile, same swizzled [pixel][channel] layout
                     uint8_t *tile_base = g.sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)g.row * 128;
                     const int j0 = (c0 & 63) >> 3;
@@ -331,7 +341,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         tc_fence_before();
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
-    if (G == 1 && !P.out_f32 && !P.out2) {
+    if (G == 1 && !P.out_f32 && !P.out2 && !P.direct_store) {
         // Coalesced copy-out: consecutive lanes move consecutive 16-byte chunks of one pixel, so every warp store
         // covers whole 128-byte lines (the per-row direct stores touch 32 lines per instruction).
         constexpr int cpp = NCH * kParts * 2;      // 16-byte chunks per pixel (C / 8): 8 or 16
@@ -901,6 +911,8 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     int grid = Q.total_tiles < kNumSMs ? Q.total_tiles : kNumSMs;
     if (const char *g = getenv("MMC_TC_DEBUG")) Q.debug = atoi(g);
+    Q.direct_store = 1;   // measured: g_a.0 1.04 -> 0.99 ms, g_s.2 0.38 -> 0.37 ms vs the staged, coalesced copy-out (MMC_TC_GDN_DIRECT=0)
+    if (const char *g = getenv("MMC_TC_GDN_DIRECT")) Q.direct_store = atoi(g);
     if (const char *g = getenv("MMC_TC_GRID")) {   // profiling aid: restrict the persistent grid (profiles/probe_grid.py)
         int v = atoi(g);
         if (v >= 1 && v < grid) grid = v;
