@@ -29,79 +29,75 @@ __global__ void __launch_bounds__(256) gaussian_blur_kernel(const float *__restr
     float *tmp = sm + span * (span + 1); // [span][kBlurTile + 1]  horizontal pass
     const int64_t plane = blockIdx.z;
     const int x0 = blockIdx.x * kBlurTile, y0 = blockIdx.y * kBlurTile;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads, no index divisions in the loops
     const float *xp = x + plane * (int64_t)H * W;
-    for (int i = threadIdx.x; i < span * span; i += blockDim.x) {
-        const int ly = i / span, lx = i - ly * span;
-        const int gy = min(max(y0 + ly - r, 0), H - 1), gx = min(max(x0 + lx - r, 0), W - 1);
-        in[ly * (span + 1) + lx] = __ldg(xp + (int64_t)gy * W + gx);
+    for (int ly = ty; ly < span; ly += 8) {
+        const float *row = xp + (int64_t)min(max(y0 + ly - r, 0), H - 1) * W;
+        for (int lx = tx; lx < span; lx += 32) in[ly * (span + 1) + lx] = __ldg(row + min(max(x0 + lx - r, 0), W - 1));
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < span * kBlurTile; i += blockDim.x) {
-        const int ly = i / kBlurTile, lx = i - ly * kBlurTile;
+    for (int ly = ty; ly < span; ly += 8) {
         float acc = 0.0f;
-        for (int t = 0; t < ksize; ++t) acc += taps.w[t] * in[ly * (span + 1) + lx + t];
-        tmp[ly * (kBlurTile + 1) + lx] = acc;
+        for (int t = 0; t < ksize; ++t) acc += taps.w[t] * in[ly * (span + 1) + tx + t];
+        tmp[ly * (kBlurTile + 1) + tx] = acc;
     }
     __syncthreads();
     float *yp = y + plane * y_plane_stride;
-    for (int i = threadIdx.x; i < kBlurTile * kBlurTile; i += blockDim.x) {
-        const int ly = i / kBlurTile, lx = i - ly * kBlurTile;
-        const int gy = y0 + ly, gx = x0 + lx;
-        if (gy >= H || gx >= W) continue;
-        float acc = 0.0f;
-        for (int t = 0; t < ksize; ++t) acc += taps.w[t] * tmp[(ly + t) * (kBlurTile + 1) + lx];
-        yp[(int64_t)gy * W + gx] = acc;
+    const int gx = x0 + tx;
+    if (gx < W) {
+        for (int ly = ty; ly < kBlurTile; ly += 8) {
+            const int gy = y0 + ly;
+            if (gy >= H) break;
+            float acc = 0.0f;
+            for (int t = 0; t < ksize; ++t) acc += taps.w[t] * tmp[(ly + t) * (kBlurTile + 1) + tx];
+            yp[(int64_t)gy * W + gx] = acc;
+        }
     }
 }
 
-// F.avg_pool2d(x, 2, 2) on [planes][H][W] (H, W even) -> [planes][H/2][W/2]
-__global__ void __launch_bounds__(256) avg_pool2_kernel(const float *__restrict__ x, int64_t x_plane_stride, int64_t planes, int H, int W,
-                                                       float *__restrict__ y)
+// F.avg_pool2d(x, 2, 2) on [planes][H][W] (H, W even) -> [planes][H/2][W/2].  grid = (ceil(Wo / 256), Ho, planes): no index divisions.
+__global__ void __launch_bounds__(256) avg_pool2_kernel(const float *__restrict__ x, int64_t x_plane_stride, int H, int W, float *__restrict__ y)
 {
     const int Ho = H / 2, Wo = W / 2;
-    const int64_t n = planes * Ho * Wo, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int ox = (int)(i % Wo);
-        const int64_t r = i / Wo;
-        const int oy = (int)(r % Ho);
-        const int64_t p = r / Ho;
-        const float *xp = x + p * x_plane_stride + (int64_t)(2 * oy) * W + 2 * ox;
-        const float2 a = *reinterpret_cast<const float2 *>(xp);
-        const float2 b = *reinterpret_cast<const float2 *>(xp + W);
-        y[i] = (a.x + a.y + b.x + b.y) * 0.25f;
-    }
+    const int ox = blockIdx.x * 256 + threadIdx.x, oy = blockIdx.y;
+    if (ox >= Wo) return;
+    const int64_t p = blockIdx.z;
+    const float *xp = x + p * x_plane_stride + (int64_t)(2 * oy) * W + 2 * ox;
+    const float2 a = *reinterpret_cast<const float2 *>(xp);
+    const float2 b = *reinterpret_cast<const float2 *>(xp + W);
+    y[(p * Ho + oy) * (int64_t)Wo + ox] = (a.x + a.y + b.x + b.y) * 0.25f;
 }
 
-// F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False): src = (dst + 0.5) / 2 - 0.5 clamped at 0
-__global__ void __launch_bounds__(256) upsample2x_kernel(const float *__restrict__ x, int64_t planes, int H, int W,
-                                                        float *__restrict__ y, int64_t y_plane_stride)
+// F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False): src = (dst + 0.5) / 2 - 0.5 clamped at 0.
+// grid = (ceil(W / 128), 2H, planes); each thread produces the two outputs 2*ix, 2*ix + 1 of one output row (one 8-byte store).
+__global__ void __launch_bounds__(128) upsample2x_kernel(const float *__restrict__ x, int H, int W, float *__restrict__ y, int64_t y_plane_stride)
 {
-    const int Ho = 2 * H, Wo = 2 * W;
-    const int64_t n = planes * Ho * Wo, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int ox = (int)(i % Wo);
-        const int64_t r = i / Wo;
-        const int oy = (int)(r % Ho);
-        const int64_t p = r / Ho;
-        const float sy = fmaxf(0.5f * (oy + 0.5f) - 0.5f, 0.0f), sx = fmaxf(0.5f * (ox + 0.5f) - 0.5f, 0.0f);
-        const int y0 = (int)sy, x0 = (int)sx;
-        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
-        const float ly = sy - y0, lx = sx - x0, hy = 1.0f - ly, hx = 1.0f - lx;
-        const float *xp = x + p * (int64_t)H * W;
-        const float v = hy * (hx * __ldg(xp + (int64_t)y0 * W + x0) + lx * __ldg(xp + (int64_t)y0 * W + x1)) +
-                        ly * (hx * __ldg(xp + (int64_t)y1 * W + x0) + lx * __ldg(xp + (int64_t)y1 * W + x1));
-        y[p * y_plane_stride + (int64_t)oy * Wo + ox] = v;
-    }
+    const int ix = blockIdx.x * 128 + threadIdx.x, oy = blockIdx.y;
+    if (ix >= W) return;
+    const int64_t p = blockIdx.z;
+    const float sy = fmaxf(0.5f * (oy + 0.5f) - 0.5f, 0.0f);
+    const int y0 = (int)sy, y1 = min(y0 + 1, H - 1);
+    const float ly = sy - y0, hy = 1.0f - ly;
+    const float *r0 = x + (p * H + y0) * (int64_t)W, *r1 = x + (p * H + y1) * (int64_t)W;
+    const int xm = max(ix - 1, 0), xp = min(ix + 1, W - 1);
+    const float a0 = __ldg(r0 + xm), b0 = __ldg(r0 + ix), c0 = __ldg(r0 + xp);
+    const float a1 = __ldg(r1 + xm), b1 = __ldg(r1 + ix), c1 = __ldg(r1 + xp);
+    // output 2*ix: src = ix - 0.25 -> x0 = ix - 1 (lambda 0.75) except at the left border (src clamped to 0: x0 = 0, lambda 0);
+    // output 2*ix + 1: src = ix + 0.25 -> x0 = ix (lambda 0.25), x1 = min(ix + 1, W - 1)
+    float e, o;
+    if (ix == 0) e = hy * (1.0f * b0 + 0.0f * c0) + ly * (1.0f * b1 + 0.0f * c1);
+    else         e = hy * (0.25f * a0 + 0.75f * b0) + ly * (0.25f * a1 + 0.75f * b1);
+    o = hy * (0.75f * b0 + 0.25f * c0) + ly * (0.75f * b1 + 0.25f * c1);
+    *reinterpret_cast<float2 *>(y + p * y_plane_stride + (int64_t)oy * (2 * W) + 2 * ix) = make_float2(e, o);
 }
 
-__global__ void __launch_bounds__(256) copy_planes_kernel(const float *__restrict__ x, int64_t planes, int64_t hw, float *__restrict__ y,
-                                                         int64_t y_plane_stride)
+// plane copy into the volume; grid = (ceil(hw / 1024), planes), float4 per thread (hw % 4 == 0)
+__global__ void __launch_bounds__(256) copy_planes_kernel(const float4 *__restrict__ x, int64_t hw4, float4 *__restrict__ y, int64_t y_plane_stride4)
 {
-    const int64_t n = planes * hw, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const int64_t p = i / hw;
-        y[p * y_plane_stride + (i - p * hw)] = __ldg(x + i);
-    }
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= hw4) return;
+    const int64_t p = blockIdx.y;
+    y[p * y_plane_stride4 + i] = ldg_stream(x + p * hw4 + i);
 }
 
 // grid_sampler_unnormalize + clip_coordinates (border padding, align_corners=False), no FMA contraction so that the
@@ -112,43 +108,41 @@ __device__ __forceinline__ float source_index(float coord, int size)
     return fminf((float)(size - 1), fmaxf(v, 0.0f));
 }
 
-// One thread per output pixel; the 8 corner weights are shared by the C channels.
-__global__ void __launch_bounds__(256) scale_space_warp_kernel(const float *__restrict__ volume, const float *__restrict__ motion,
+// One thread per output pixel (grid = (ceil(W / 128), H, N)); the 8 corner weights are shared by the C channels.
+__global__ void __launch_bounds__(128) scale_space_warp_kernel(const float *__restrict__ volume, const float *__restrict__ motion,
                                                               const float *__restrict__ base_x, const float *__restrict__ base_y,
-                                                              int64_t N, int C, int D, int H, int W, const float *__restrict__ x_cur,
+                                                              int C, int D, int H, int W, const float *__restrict__ x_cur,
                                                               float *__restrict__ x_pred, float *__restrict__ x_res)
 {
-    const int64_t hw = (int64_t)H * W, n_pix = N * hw, stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += stride) {
-        const int64_t n = i / hw, p = i - n * hw;
-        const int h = (int)(p / W), w = (int)(p - (int64_t)h * W);
-        const float *m = motion + n * 3 * hw + p;
-        const float gx = __fadd_rn(__ldg(base_x + w), __ldg(m)), gy = __fadd_rn(__ldg(base_y + h), __ldg(m + hw)), gz = __ldg(m + 2 * hw);
-        const float ix = source_index(gx, W), iy = source_index(gy, H), iz = source_index(gz, D);
-        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
-        const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
-        const float wx1 = ix - fx, wy1 = iy - fy, wz1 = iz - fz;                 // weights of the +1 corners
-        const float wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy, wz0 = (fz + 1.0f) - iz;
-        const bool x1ok = x0 + 1 < W, y1ok = y0 + 1 < H, z1ok = z0 + 1 < D;      // x0, y0, z0 are in range after clipping
-        const float *vb = volume + n * C * D * hw;
-        for (int c = 0; c < C; ++c) {
-            const float *v0 = vb + ((int64_t)c * D + z0) * hw + (int64_t)y0 * W + x0;
-            const float *v1 = v0 + hw;
-            float acc = 0.0f;
-            acc += __ldg(v0) * (wx0 * wy0 * wz0);
-            if (x1ok) acc += __ldg(v0 + 1) * (wx1 * wy0 * wz0);
-            if (y1ok) acc += __ldg(v0 + W) * (wx0 * wy1 * wz0);
-            if (x1ok && y1ok) acc += __ldg(v0 + W + 1) * (wx1 * wy1 * wz0);
-            if (z1ok) {
-                acc += __ldg(v1) * (wx0 * wy0 * wz1);
-                if (x1ok) acc += __ldg(v1 + 1) * (wx1 * wy0 * wz1);
-                if (y1ok) acc += __ldg(v1 + W) * (wx0 * wy1 * wz1);
-                if (x1ok && y1ok) acc += __ldg(v1 + W + 1) * (wx1 * wy1 * wz1);
-            }
-            const int64_t o = (n * C + c) * hw + p;
-            x_pred[o] = acc;
-            if (x_res) x_res[o] = __ldg(x_cur + o) - acc;
+    const int w = blockIdx.x * 128 + threadIdx.x, h = blockIdx.y;
+    if (w >= W) return;
+    const int64_t n = blockIdx.z, hw = (int64_t)H * W, p = (int64_t)h * W + w;
+    const float *m = motion + n * 3 * hw + p;
+    const float gx = __fadd_rn(__ldg(base_x + w), __ldg(m)), gy = __fadd_rn(__ldg(base_y + h), __ldg(m + hw)), gz = __ldg(m + 2 * hw);
+    const float ix = source_index(gx, W), iy = source_index(gy, H), iz = source_index(gz, D);
+    const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const float wx1 = ix - fx, wy1 = iy - fy, wz1 = iz - fz;                 // weights of the +1 corners
+    const float wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy, wz0 = (fz + 1.0f) - iz;
+    const bool x1ok = x0 + 1 < W, y1ok = y0 + 1 < H, z1ok = z0 + 1 < D;      // x0, y0, z0 are in range after clipping
+    const float *vb = volume + n * C * D * hw;
+    for (int c = 0; c < C; ++c) {
+        const float *v0 = vb + ((int64_t)c * D + z0) * hw + (int64_t)y0 * W + x0;
+        const float *v1 = v0 + hw;
+        float acc = 0.0f;
+        acc += __ldg(v0) * (wx0 * wy0 * wz0);
+        if (x1ok) acc += __ldg(v0 + 1) * (wx1 * wy0 * wz0);
+        if (y1ok) acc += __ldg(v0 + W) * (wx0 * wy1 * wz0);
+        if (x1ok && y1ok) acc += __ldg(v0 + W + 1) * (wx1 * wy1 * wz0);
+        if (z1ok) {
+            acc += __ldg(v1) * (wx0 * wy0 * wz1);
+            if (x1ok) acc += __ldg(v1 + 1) * (wx1 * wy0 * wz1);
+            if (y1ok) acc += __ldg(v1 + W) * (wx0 * wy1 * wz1);
+            if (x1ok && y1ok) acc += __ldg(v1 + W + 1) * (wx1 * wy1 * wz1);
         }
+        const int64_t o = (n * C + c) * hw + p;
+        x_pred[o] = acc;
+        if (x_res) x_res[o] = __ldg(x_cur + o) - acc;
     }
 }
 
@@ -209,7 +203,8 @@ int mmc_gaussian_volume(const float *x, int64_t planes, int H, int W, const floa
         return MMC_OK;
     };
     // level 0: the frame itself; level 1: its blur
-    copy_planes_kernel<<<elementwise_grid(planes * hw, 256), 256, 0, st>>>(x, planes, hw, volume, vstride);
+    MMC_CHECK_ARG(hw % 4 == 0 && aligned16(x) && aligned16(volume), "%s: H * W must be a multiple of 4 and the buffers 16-byte aligned", name);
+    copy_planes_kernel<<<dim3((unsigned)((hw / 4 + 255) / 256), (unsigned)planes), 256, 0, st>>>((const float4 *)x, hw / 4, (float4 *)volume, vstride / 4);
     MMC_CHECK_LAUNCH(name);
     int rc = blur(x, H, W, volume + hw, vstride);
     if (rc) return rc;
@@ -221,7 +216,7 @@ int mmc_gaussian_volume(const float *x, int64_t planes, int H, int W, const floa
     int64_t prev_stride = vstride;
     int h = H, w = W;
     for (int lvl = 2; lvl <= num_levels; ++lvl) {
-        avg_pool2_kernel<<<elementwise_grid(planes * (int64_t)(h / 2) * (w / 2), 256), 256, 0, st>>>(prev, prev_stride, planes, h, w, pooled);
+        avg_pool2_kernel<<<dim3((unsigned)((w / 2 + 255) / 256), (unsigned)(h / 2), (unsigned)planes), 256, 0, st>>>(prev, prev_stride, h, w, pooled);
         MMC_CHECK_LAUNCH(name);
         h /= 2; w /= 2;
         rc = blur(pooled, h, w, blurred, (int64_t)h * w);
@@ -232,8 +227,8 @@ int mmc_gaussian_volume(const float *x, int64_t planes, int H, int W, const floa
         for (int u = 0; u < lvl - 1; ++u) {
             const bool last = (u == lvl - 2);
             float *dst = last ? volume + (int64_t)lvl * hw : up[u & 1];
-            upsample2x_kernel<<<elementwise_grid(planes * (int64_t)uh * uw * 4, 256), 256, 0, st>>>(src, planes, uh, uw, dst,
-                                                                                                    last ? vstride : (int64_t)uh * uw * 4);
+            upsample2x_kernel<<<dim3((unsigned)((uw + 127) / 128), (unsigned)(2 * uh), (unsigned)planes), 128, 0, st>>>(src, uh, uw, dst,
+                                                                                                                  last ? vstride : (int64_t)uh * uw * 4);
             MMC_CHECK_LAUNCH(name);
             src = dst; uh *= 2; uw *= 2;
         }
@@ -249,8 +244,9 @@ int mmc_scale_space_warp(const float *volume, const float *motion_info, const fl
     if (N == 0) return MMC_OK;
     MMC_CHECK_ARG(volume && motion_info && base_x && base_y && x_pred, "%s: NULL buffer", name);
     MMC_CHECK_ARG(!x_res || x_cur, "%s: x_res requested without x_cur", name);
-    scale_space_warp_kernel<<<elementwise_grid(N * (int64_t)H * W, 256), 256, 0, (cudaStream_t)stream>>>(volume, motion_info, base_x, base_y, N, C, D,
-                                                                                                     H, W, x_cur, x_pred, x_res);
+    MMC_CHECK_ARG(N <= 65535 && H <= 65535, "%s: N and H must be <= 65535", name);
+    scale_space_warp_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)H, (unsigned)N), 128, 0, (cudaStream_t)stream>>>(volume, motion_info, base_x, base_y,
+                                                                                                                      C, D, H, W, x_cur, x_pred, x_res);
     MMC_CHECK_LAUNCH(name);
     return MMC_OK;
 }
