@@ -837,40 +837,37 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
 
 // NCHW fp32 image -> zero-padded NHWC bf16 with 8 channels per pixel ([B][Hp][Wp][8], 16 B per pixel).
 // One thread converts 4 horizontally adjacent pixels: up to 8 independent plane loads in flight, 64 B stored.
-__global__ void __launch_bounds__(256) pad8_kernel(const float *__restrict__ x, int C, int H, int W, int pad, int Hp, int Wp,
-                                                  int64_t nquads, uint4 *__restrict__ out)
+__global__ void __launch_bounds__(128) pad8_kernel(const float *__restrict__ x, int C, int H, int W, int pad, int Hp, int Wp,
+                                                  uint4 *__restrict__ out)
 {
-    const int qpr = (Wp + 3) >> 2;   // quads per padded row
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
-        const int qx = (int)(i % qpr);
-        int64_t r = i / qpr;
-        const int py = (int)(r % Hp);
-        const int64_t b = r / Hp;
-        const int iy = py - pad;
-        float v[4][8];
+    // grid = (ceil(quads per row / 128), Hp, B): no index divisions
+    const int qx = blockIdx.x * 128 + threadIdx.x;
+    if (qx * 4 >= Wp) return;
+    const int py = blockIdx.y;
+    const int64_t b = blockIdx.z;
+    const int iy = py - pad;
+    float v[4][8];
 #pragma unroll
-        for (int p = 0; p < 4; ++p)
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) v[p][c] = 0.0f;
-        if (iy >= 0 && iy < H) {
-            const float *row = x + (b * C * H + iy) * (int64_t)W;
+        for (int c = 0; c < 8; ++c) v[p][c] = 0.0f;
+    if (iy >= 0 && iy < H) {
+        const float *row = x + (b * C * H + iy) * (int64_t)W;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c >= C) break;
+        for (int c = 0; c < 8; ++c) {
+            if (c >= C) break;
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int ix = qx * 4 + p - pad;
-                    if (ix >= 0 && ix < W) v[p][c] = __ldg(row + (int64_t)c * H * W + ix);
-                }
+            for (int p = 0; p < 4; ++p) {
+                const int ix = qx * 4 + p - pad;
+                if (ix >= 0 && ix < W) v[p][c] = __ldg(row + (int64_t)c * H * W + ix);
             }
         }
-        uint4 *dst = out + (b * Hp + py) * (int64_t)Wp + qx * 4;
-#pragma unroll
-        for (int p = 0; p < 4; ++p)
-            if (qx * 4 + p < Wp)
-                dst[p] = make_uint4(pack_bf16(v[p][0], v[p][1]), pack_bf16(v[p][2], v[p][3]), pack_bf16(v[p][4], v[p][5]), pack_bf16(v[p][6], v[p][7]));
     }
+    uint4 *dst = out + (b * Hp + py) * (int64_t)Wp + qx * 4;
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+        if (qx * 4 + p < Wp)
+            dst[p] = make_uint4(pack_bf16(v[p][0], v[p][1]), pack_bf16(v[p][2], v[p][3]), pack_bf16(v[p][4], v[p][5]), pack_bf16(v[p][6], v[p][7]));
 }
 
 static int pick_ntile(int cout)
@@ -975,8 +972,9 @@ int mmc_pad_nchw_to_nhwc8(const float *x, int64_t B, int C, int H, int W, int pa
                   "mmc_pad_nchw_to_nhwc8: bad shape");
     if (B == 0) return MMC_OK;
     MMC_CHECK_ARG(x && out && aligned16(out), "mmc_pad_nchw_to_nhwc8: NULL or unaligned buffer");
-    int64_t nquads = B * Hp * ((Wp + 3) / 4);
-    pad8_kernel<<<elementwise_grid(nquads, 256, 16), 256, 0, (cudaStream_t)stream>>>(x, C, H, W, pad, Hp, Wp, nquads, (uint4 *)out);
+    MMC_CHECK_ARG(B <= 65535 && Hp <= 65535, "mmc_pad_nchw_to_nhwc8: B and the padded height must be <= 65535");
+    const int qpr = (Wp + 3) / 4;
+    pad8_kernel<<<dim3((unsigned)((qpr + 127) / 128), (unsigned)Hp, (unsigned)B), 128, 0, (cudaStream_t)stream>>>(x, C, H, W, pad, Hp, Wp, (uint4 *)out);
     MMC_CHECK_LAUNCH("mmc_pad_nchw_to_nhwc8");
     return MMC_OK;
 }
