@@ -383,14 +383,14 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
     float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
     // resident weights (b_resident): one [Ntile][64] bf16 tile per K block, after the GDN / staging region
     const size_t epi_bytes = (kEpi == EPI_GDN) ? (size_t)P.Cout * P.Cout * 2 + (size_t)(P.Cout / 64) * kABytes
-                           : (kEpi == EPI_SCATTER) ? (((size_t)128 * P.spitch * sizeof(float) + 1023) & ~(size_t)1023) : 0;
+                           : (kEpi == EPI_SCATTER) ? 2 * (((size_t)128 * P.spitch * sizeof(float) + 1023) & ~(size_t)1023) : 0;
     uint8_t *sBres = sG + epi_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], (kPair ? 2 : 1) * (kEpiThreads / 32)); }   // one arrival per epilogue warp
+        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpi == EPI_SCATTER ? 4 : (kPair ? 2 : 1) * (kEpiThreads / 32)); }   // one arrival per epilogue warp (col2im: per team of 4)
         mbar_init(&gdn_ready_bar, 2);
         mbar_init(&gdn_bar, 1);
         mbar_init(&gload_bar, 1);
@@ -547,6 +547,10 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
         const uint32_t ready_leader = kPair ? mapa_u32(smem_u32(&gdn_ready_bar), 0) : 0u;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
             if (kPair) ti.init(P, tile);
+            // col2im epilogue: two independent teams of 4 warps (one warp per TMEM lane quarter) take alternate tiles, each with its
+            // own staging buffer and named barrier, so that one team's TMEM / shared-memory latencies overlap the other's work.
+            // acc_stages is even there, hence every accumulator stage (and its barriers) always belongs to the same team.
+            if (kEpi == EPI_SCATTER && (it & 1) != half) continue;
             const TileCoord t = ti.coord(P);
             const int as = acc_i;                       // accumulator ring position of this tile
             const uint32_t aphase = acc_ph;
@@ -559,11 +563,11 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
 
             if (kEpi == EPI_SCATTER) {
                 // ---- GEMM + col2im: column n = (ky*k + kx)*Cout + c holds x[q] . w[:, c, ky, kx] for INPUT pixel q ----
+                float *stage = sStage + (size_t)half * ((((size_t)128 * P.spitch * sizeof(float) + 1023) & ~(size_t)1023) / sizeof(float));
                 {
                     const int nch = P.Ntile >> 4;
-                    const int ch_lo = (nch * half + kParts - 1) / kParts, ch_hi = (nch * (half + 1) + kParts - 1) / kParts;
-                    float *srow = sStage + (size_t)row * P.spitch;
-                    for (int ch = ch_lo; ch < ch_hi; ++ch) {
+                    float *srow = stage + (size_t)row * P.spitch;
+                    for (int ch = 0; ch < nch; ++ch) {
                         float v[16];
                         tmem_ld16(acc_addr + (ch << 4), v);
                         tmem_ld_wait();
@@ -579,7 +583,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
                 {
                     // Gather: one work item per (interior input-resolution pixel a, channel c) produces the s x s output
                     // block (s*a + p); every product S[q][(ky,kx,c)] is consumed exactly once.
@@ -587,7 +591,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                     const int ih = P.TH - P.halo_lo - P.halo_hi, iw = P.TW - P.halo_lo - P.halo_hi;   // interior (input res)
                     const int items = ih * iw * P.Cout;
                     float *yo = (float *)P.y;
-                    for (int e = threadIdx.x - 64; e < items; e += kEpiThreads) {
+                    for (int e = (threadIdx.x - 64) & 127; e < items; e += 128) {
                         const int ax = e % iw;
                         const int r2 = e / iw;
                         const int ay = r2 % ih;
@@ -598,7 +602,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                         if (k == 5 && s == 2) {
                             // pad = 2: ky has the parity of oy; input row = a + (py + 2 - ky) / 2  (all compile-time)
                             float o00 = b0, o01 = b0, o10 = b0, o11 = b0;
-                            const float *base = sStage + (size_t)((P.halo_lo + ay) * P.TW + (P.halo_lo + ax)) * P.spitch + c;
+                            const float *base = stage + (size_t)((P.halo_lo + ay) * P.TW + (P.halo_lo + ax)) * P.spitch + c;
 #pragma unroll
                             for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
@@ -634,7 +638,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                                         for (int kx = (ox + P.pad) % s; kx < k; kx += s) {
                                             const int ixl = (ox + P.pad - kx) / s - t.x0;
                                             if (ixl < 0 || ixl >= P.TW) continue;
-                                            acc += sStage[(size_t)(iyl * P.TW + ixl) * P.spitch + (ky * k + kx) * P.Cout + c];
+                                            acc += stage[(size_t)(iyl * P.TW + ixl) * P.spitch + (ky * k + kx) * P.Cout + c];
                                         }
                                     }
                                     yo[(((int64_t)t.b * P.Cout + c) * P.Ho + oy) * P.Wo + ox] = act_tc(acc, P.act);
@@ -642,7 +646,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                         }
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // staging buffer free for the next tile
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");   // this team's staging buffer is free for its next tile
                 continue;
             } else {
                 const int py = t.phase / P.out_stride, px = t.phase - py * P.out_stride;
@@ -1082,11 +1086,15 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     P.acc_stages = (512 - P.gdn_chunk) / P.Ntile;      // as many accumulator stages as TMEM holds (epilogue slack)
     if (P.acc_stages > kMaxAccStages) P.acc_stages = kMaxAccStages;
     if (P.acc_stages < 1) P.acc_stages = 1;
+    if (pl.mode == MODE_SCATTER) {
+        P.acc_stages &= ~1;    // the two col2im epilogue teams own alternate accumulator stages
+        MMC_UNSUPPORTED(P.acc_stages < 2, "%s: the reconstruction kernel needs two accumulator stages (N tile %d)", name, P.Ntile);
+    }
     MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
 
     size_t fixed = 1024;  // alignment slack
     if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * ((P.pair && kPairGdnShared) ? 1 : 2) + (size_t)(d->Cout / 64) * kABytes;
-    if (pl.mode == MODE_SCATTER) fixed += (((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023;
+    if (pl.mode == MODE_SCATTER) fixed += 2 * ((((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023);   // one staging buffer per epilogue team
     // Small layers (image-edge conv, reconstruction deconv): keep every weight tile resident in shared memory so that
     // the K blocks stream activations only (halves the L2 -> SM traffic of those layers).
     const size_t b_total = (size_t)pl.ntaps * pl.kchunks * P.Ntile * 128;
