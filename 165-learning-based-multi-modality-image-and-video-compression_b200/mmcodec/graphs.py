@@ -5,6 +5,9 @@ of microseconds of device work) are bound by host-side launch cost, not by the k
 once under ``torch.cuda.graph`` -- every libmmcodec launch (tensor maps included: they are kernel parameters) is recorded
 on the capturing stream -- and replays it with one ``cudaGraphLaunch`` per call.  Inputs are copied into the captured
 input buffers; outputs are the captured output tensors (overwritten by the next call).
+
+The graph reads the packed weights, GDN re-parametrisations and likelihood tables that existed at capture time.  Pass the modules
+whose parameters matter as ``modules=`` and the graph is re-captured automatically after any in-place parameter update.
 """
 from __future__ import annotations
 
@@ -17,7 +20,19 @@ __all__ = ["GraphedForward"]
 
 
 class GraphedForward:
-    def __init__(self, fn: Callable[..., Any], *example_inputs: Any, warmup: int = 2):
+    def __init__(self, fn: Callable[..., Any], *example_inputs: Any, warmup: int = 2, modules=None):
+        if modules is None and isinstance(fn, torch.nn.Module):
+            modules = [fn]
+        self._modules = list(modules or [])
+        self._warmup = warmup
+        self._capture(fn, example_inputs)
+
+    def _signature(self):
+        return tuple(p._version for m in self._modules for p in m.parameters()) + tuple(m.training for m in self._modules)
+
+    def _capture(self, fn, example_inputs):
+        warmup = self._warmup
+        self._sig = self._signature()
         flat, self._spec = pytree.tree_flatten(example_inputs)
         for t in flat:
             if torch.is_tensor(t) and not t.is_cuda:
@@ -37,6 +52,8 @@ class GraphedForward:
             self._static_out = fn(*args)
 
     def __call__(self, *inputs: Any) -> Any:
+        if self._modules and self._signature() != self._sig:
+            self._capture(self._fn, inputs)        # parameters changed since the capture: the cached packs / tables are stale
         flat, spec = pytree.tree_flatten(inputs)
         if spec != self._spec:
             raise ValueError("GraphedForward: input structure differs from the captured one")

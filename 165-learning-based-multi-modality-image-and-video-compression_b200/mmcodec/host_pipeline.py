@@ -45,6 +45,11 @@ class HostPipeline:
     def _buffers(self, x_host: Tensor):
         mb = min(self.micro_batch, x_host.shape[0])
         shape = (mb,) + tuple(x_host.shape[1:])
+        # the captured graphs read the packed weights / tables that existed at capture time: re-capture after any parameter update
+        sig = tuple(p._version for p in self.net.parameters()) + (self.net.training,)
+        if sig != getattr(self, "_param_sig", None):
+            self._graphs = None
+            self._param_sig = sig
         if self._slots is None or tuple(self._slots[0].shape) != shape:
             self._slots = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
             self._graphs = None

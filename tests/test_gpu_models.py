@@ -253,3 +253,22 @@ def test_graphed_forward_replays_exactly():
         g(torch.zeros(1, 3, 64, 128, device=dev()))
     with pytest.raises(RuntimeError):
         mmcodec.GraphedForward(net, x0.cpu())
+
+
+def test_graphs_follow_parameter_updates():
+    """Captured graphs hold the packed weights of capture time: both wrappers re-capture after an in-place parameter update."""
+    net, _ = load(mmcodec.ScaleHyperprior, "hyperprior", 128, 192)
+    x = torch.from_numpy(make_image(2, 64, 128, seed=31))
+    g = mmcodec.GraphedForward(net, x.to(dev()))
+    pipe = mmcodec.HostPipeline(net, micro_batch=2)
+    pipe(x.pin_memory())
+    with torch.no_grad():
+        net.g_s[6].weight.mul_(1.5)
+        net.g_s[6].bias.add_(0.25)
+        want = net(x.to(dev()))
+        got = g(x.to(dev()))
+        torch.cuda.synchronize()
+        assert torch.equal(got["x_hat"], want["x_hat"])
+        out = pipe(x.pin_memory())
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(out["x_hat"], want["x_hat"].cpu())
