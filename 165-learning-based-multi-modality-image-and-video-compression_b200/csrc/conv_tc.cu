@@ -15,15 +15,17 @@
 //     correlation over the taps of matching parity (3x3 / 3x2 / 2x3 / 2x2 for k=5), so no zero
 //     insertion and no wasted MACs.
 //   * B operand: weights pre-packed [tap][Cout][Cin] bf16, one 2-D TMA box {64, Ntile} per K block.
-//   * tcgen05.mma (cta_group::1, M=128, N=Ntile, K=16) issued by one thread, fp32 accumulators in
-//     TMEM, double buffered so the epilogue of tile i overlaps the main loop of tile i+1.
-//   * Epilogue (4 warps, one accumulator row = one pixel per thread): tcgen05.ld -> bias -> act ->
-//     [GDN] -> bf16 / fp32 NHWC stores.  GDN is a second tensor-core contraction: the epilogue
-//     squares the activations into a swizzled bf16 tile in shared memory, one thread issues
-//     D2[128 x C] = X2[128 x C] * gamma^T with gamma resident in shared memory, and the result is
-//     combined as x * rsqrt(beta + D2) (sqrt for IGDN).
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
-// Persistent grid: one CTA per SM, tiles strided across CTAs.
+//   * tcgen05.mma (M=128, N=Ntile, K=16) issued by one elected thread, fp32 accumulators in TMEM in a ring of 2-4 stages so
+//     that the epilogue of tile i overlaps the main loops of the next tiles.  CTA-pair variant (kPair): a 2-CTA cluster takes two
+//     adjacent tiles, one cta_group::2 MMA (M=256) spans both SMs and each CTA supplies half of the weight rows.
+//   * Epilogue (8 warps, two per TMEM lane quarter, one accumulator row = one pixel per thread): tcgen05.ld -> bias -> act ->
+//     [GDN] -> bf16 / fp32 NHWC stores.  GDN is a second tensor-core contraction: the epilogue squares the activations into a
+//     swizzled bf16 tile in shared memory, one thread issues D2[128 x C] = X2[128 x C] * gamma^T with gamma resident in
+//     shared memory, and the result is combined as x * rsqrt(beta + D2) (sqrt for IGDN).
+//   * Image-edge layers (Cin <= 8, MODE_PAD8) and the reconstruction layer (Cout <= 4, MODE_SCATTER: GEMM + col2im with two
+//     independent epilogue teams) are described at their plan / epilogue code below.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-9 = epilogue.
+// Persistent grid: one CTA per SM (pairs: one cluster per SM pair), tiles strided across CTAs.
 #include <cuda.h>
 #include <stdlib.h>
 
