@@ -146,6 +146,30 @@ __global__ void __launch_bounds__(128) scale_space_warp_kernel(const float *__re
     }
 }
 
+// rgb2ycbcr / ycbcr2rgb, ITU-R BT.709 (compressai/transforms/functional.py:26-66), planar [N][3][HW] fp32; the operation order
+// (and the absence of FMA contraction) follows the reference's expression so that results agree to the last bit or two
+__global__ void __launch_bounds__(256) color_kernel(const float *__restrict__ x, int64_t hw, int to_ycbcr, float *__restrict__ y)
+{
+    const float Kr = 0.2126f, Kg = 0.7152f, Kb = 0.0722f;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= hw) return;
+    const int64_t base = (int64_t)blockIdx.y * 3 * hw + i;
+    const float a = x[base], b = x[base + hw], c = x[base + 2 * hw];
+    float o0, o1, o2;
+    if (to_ycbcr) {
+        const float yy = __fadd_rn(__fadd_rn(__fmul_rn(Kr, a), __fmul_rn(Kg, b)), __fmul_rn(Kb, c));
+        o0 = yy;
+        o1 = __fadd_rn(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(c, yy)), (float)(1.0 - 0.0722)), 0.5f);
+        o2 = __fadd_rn(__fdiv_rn(__fmul_rn(0.5f, __fsub_rn(a, yy)), (float)(1.0 - 0.2126)), 0.5f);
+    } else {
+        const float r = __fadd_rn(a, __fmul_rn((float)(2.0 - 2.0 * 0.2126), __fsub_rn(c, 0.5f)));
+        const float bb = __fadd_rn(a, __fmul_rn((float)(2.0 - 2.0 * 0.0722), __fsub_rn(b, 0.5f)));
+        const float g = __fdiv_rn(__fsub_rn(__fsub_rn(a, __fmul_rn(Kr, r)), __fmul_rn(Kb, bb)), Kg);
+        o0 = r; o1 = g; o2 = bb;
+    }
+    y[base] = o0; y[base + hw] = o1; y[base + 2 * hw] = o2;
+}
+
 __global__ void __launch_bounds__(256) add_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b, int64_t n4, float4 *__restrict__ out,
                                                  const float *at, const float *bt, float *ot, int tail)
 {
@@ -248,6 +272,38 @@ int mmc_scale_space_warp(const float *volume, const float *motion_info, const fl
     scale_space_warp_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)H, (unsigned)N), 128, 0, (cudaStream_t)stream>>>(volume, motion_info, base_x, base_y,
                                                                                                                       C, D, H, W, x_cur, x_pred, x_res);
     MMC_CHECK_LAUNCH(name);
+    return MMC_OK;
+}
+
+int mmc_color_convert(const float *x, int64_t N, int64_t HW, int to_ycbcr, float *y, void *stream)
+{
+    MMC_CHECK_ARG(N >= 0 && HW >= 0 && N <= 65535, "mmc_color_convert: bad shape");
+    if (N * HW == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && y, "mmc_color_convert: NULL buffer");
+    color_kernel<<<dim3((unsigned)((HW + 255) / 256), (unsigned)N), 256, 0, (cudaStream_t)stream>>>(x, HW, to_ycbcr, y);
+    MMC_CHECK_LAUNCH("mmc_color_convert");
+    return MMC_OK;
+}
+
+int mmc_avg_pool2(const float *x, int64_t x_plane_stride, int64_t planes, int H, int W, float *y, void *stream)
+{
+    MMC_CHECK_ARG(planes >= 0 && planes <= 65535 && H >= 2 && W >= 2 && H / 2 <= 65535 && x_plane_stride >= (int64_t)H * W && W % 2 == 0,
+                  "mmc_avg_pool2: bad shape (W must be even)");
+    if (planes == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && y && (reinterpret_cast<uintptr_t>(x) & 7) == 0 && x_plane_stride % 2 == 0, "mmc_avg_pool2: NULL or unaligned buffer");
+    avg_pool2_kernel<<<dim3((unsigned)((W / 2 + 255) / 256), (unsigned)(H / 2), (unsigned)planes), 256, 0, (cudaStream_t)stream>>>(x, x_plane_stride, H, W, y);
+    MMC_CHECK_LAUNCH("mmc_avg_pool2");
+    return MMC_OK;
+}
+
+int mmc_upsample2x_bilinear(const float *x, int64_t planes, int H, int W, float *y, int64_t y_plane_stride, void *stream)
+{
+    MMC_CHECK_ARG(planes >= 0 && planes <= 65535 && H >= 1 && W >= 1 && 2 * H <= 65535 && y_plane_stride >= 4ll * H * W && y_plane_stride % 2 == 0,
+                  "mmc_upsample2x_bilinear: bad shape");
+    if (planes == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && y && (reinterpret_cast<uintptr_t>(y) & 7) == 0, "mmc_upsample2x_bilinear: NULL or unaligned buffer");
+    upsample2x_kernel<<<dim3((unsigned)((W + 127) / 128), (unsigned)(2 * H), (unsigned)planes), 128, 0, (cudaStream_t)stream>>>(x, H, W, y, y_plane_stride);
+    MMC_CHECK_LAUNCH("mmc_upsample2x_bilinear");
     return MMC_OK;
 }
 

@@ -8,11 +8,12 @@
     mmcodec.models_video     ScaleSpaceFlow (ssf2020 video codec: keyframe / inter-frame forward, compress, decompress)
     mmcodec.autograd         training path: autograd Functions over the forward / backward kernels
     mmcodec.training         RateDistortionLoss, configure_optimizers, GradBucketReducer (NCCL), TrainStep
+    mmcodec.transforms_functional   rgb2ycbcr, ycbcr2rgb, yuv_444_to_420, yuv_420_to_444 (compressai.transforms.functional)
     mmcodec.ops              functional access to every entry point of include/mmcodec.h
 
 All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
 """
-from . import _lib, entropy_models, graphs, host_pipeline, layers, models, models_mm, models_video, ops, training, transforms  # noqa: F401
+from . import _lib, entropy_models, graphs, host_pipeline, layers, models, models_mm, models_video, ops, training, transforms, transforms_functional  # noqa: F401
 from .graphs import GraphedForward  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401
 from ._lib import MmcodecError, build  # noqa: F401

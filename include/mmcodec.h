@@ -268,6 +268,15 @@ MMC_API int mmc_scale_space_warp(const float *volume, const float *motion_info, 
                                  int64_t N, int C, int D, int H, int W, const float *x_cur, float *x_pred, float *x_res,
                                  void *stream);
 
+/* Colour transforms of the video pipeline (compressai/transforms/functional.py:26-137), planar fp32:
+ *   mmc_color_convert: rgb2ycbcr (to_ycbcr = 1) / ycbcr2rgb (0), ITU-R BT.709, x and y [N][3][HW];
+ *   mmc_avg_pool2: F.avg_pool2d(x, 2, 2) per plane (yuv_444_to_420 chroma), input planes x_plane_stride apart;
+ *   mmc_upsample2x_bilinear: F.interpolate(scale_factor=2, mode="bilinear", align_corners=False) per plane
+ *   (yuv_420_to_444 chroma; also a step of the Gaussian volume), output planes y_plane_stride apart. */
+MMC_API int mmc_color_convert(const float *x, int64_t N, int64_t HW, int to_ycbcr, float *y, void *stream);
+MMC_API int mmc_avg_pool2(const float *x, int64_t x_plane_stride, int64_t planes, int H, int W, float *y, void *stream);
+MMC_API int mmc_upsample2x_bilinear(const float *x, int64_t planes, int H, int W, float *y, int64_t y_plane_stride, void *stream);
+
 /* out = a + b (x_rec = x_pred + x_res_hat, models/video/google.py:271) */
 MMC_API int mmc_add(const float *a, const float *b, int64_t n, float *out, void *stream);
 

@@ -452,3 +452,33 @@ def ssf_forward(sd, frames, num_levels: int = 5, sigma0: float = 1.5):
         recs.append(x_ref)
         liks.append({"motion": lik_m, "residual": lik_r})
     return {"x_hat": recs, "likelihoods": liks, "trace": trace}
+
+
+# ---- colour transforms (compressai/transforms/functional.py:26-137) ---------------------------------------------
+def rgb2ycbcr(rgb):
+    r, g, b = rgb.chunk(3, -3)
+    Kr, Kg, Kb = 0.2126, 0.7152, 0.0722
+    y = Kr * r + Kg * g + Kb * b
+    cb = 0.5 * (b - y) / (1 - Kb) + 0.5
+    cr = 0.5 * (r - y) / (1 - Kr) + 0.5
+    return torch.cat((y, cb, cr), dim=-3)
+
+
+def ycbcr2rgb(ycbcr):
+    y, cb, cr = ycbcr.chunk(3, -3)
+    Kr, Kg, Kb = 0.2126, 0.7152, 0.0722
+    r = y + (2 - 2 * Kr) * (cr - 0.5)
+    b = y + (2 - 2 * Kb) * (cb - 0.5)
+    g = (y - Kr * r - Kb * b) / Kg
+    return torch.cat((r, g, b), dim=-3)
+
+
+def yuv_444_to_420(yuv):
+    y, u, v = yuv.chunk(3, 1)
+    return y, F.avg_pool2d(u, kernel_size=2, stride=2), F.avg_pool2d(v, kernel_size=2, stride=2)
+
+
+def yuv_420_to_444(yuv):
+    y, u, v = yuv
+    up = lambda t: F.interpolate(t, scale_factor=2, mode="bilinear", align_corners=False)
+    return torch.cat((y, up(u), up(v)), dim=1)

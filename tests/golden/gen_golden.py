@@ -387,11 +387,22 @@ def ssf_goldens(out):
             print(t, part, {k: (float(torch.log2(v).sum() / -(128 * 256)), float((v <= 1.0001e-9).float().mean())) for k, v in lk.items()})
 
 
+def color_goldens(out):
+    """compressai.transforms.functional on a random frame (the reference's own functions)."""
+    from compressai.transforms.functional import rgb2ycbcr, ycbcr2rgb, yuv_420_to_444, yuv_444_to_420
+    rgb = torch.from_numpy(make_image(2, 36, 52, seed=77))
+    ycc = rgb2ycbcr(rgb)
+    y, u, v = yuv_444_to_420(ycc)
+    out["rgb"], out["ycbcr"], out["rgb_back"] = t2n(rgb), t2n(ycc), t2n(ycbcr2rgb(ycc))
+    out["u420"], out["v420"] = t2n(u), t2n(v)
+    out["yuv444"] = t2n(yuv_420_to_444((y, u, v)))
+
+
 def main():
     import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf"]
-    gens = {"kernels": kernel_goldens, "models": model_goldens, "models_mm": mm_goldens, "models_ssf": ssf_goldens}
+    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color"]
+    gens = {"kernels": kernel_goldens, "models": model_goldens, "models_mm": mm_goldens, "models_ssf": ssf_goldens, "color": color_goldens}
     for name in which:
         d = {}
         gens[name](d)

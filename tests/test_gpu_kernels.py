@@ -406,3 +406,27 @@ def test_pmf_to_quantized_cdf_device_bit_exact(kernels_golden):
     with pytest.raises(ValueError):
         ops.pmf_to_quantized_cdf_device(cu(np.zeros((1, 3), np.float32)), cu(np.zeros(1, np.float32)),
                                         torch.tensor([3], dtype=torch.int32, device=dev()), 3, 16)
+
+
+def test_colour_transforms_vs_reference_golden():
+    """mmcodec.transforms_functional (compressai/transforms/functional.py:26-137) vs the reference's own outputs; fp32, 1e-6."""
+    import os
+    from mmcodec import transforms_functional as TF
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "color.npz"))
+    rgb = cu(g["rgb"])
+    ycc = TF.rgb2ycbcr(rgb)
+    assert np.abs(ycc.cpu().numpy() - g["ycbcr"]).max() < 1e-6
+    assert np.abs(TF.ycbcr2rgb(cu(g["ycbcr"])).cpu().numpy() - g["rgb_back"]).max() < 1e-6
+    y, u, v = TF.yuv_444_to_420(cu(g["ycbcr"]))
+    assert np.abs(u.cpu().numpy() - g["u420"]).max() < 1e-6 and np.abs(v.cpu().numpy() - g["v420"]).max() < 1e-6
+    assert np.array_equal(y.cpu().numpy(), g["ycbcr"][:, :1])
+    back = TF.yuv_420_to_444((y, cu(g["u420"]), cu(g["v420"])))
+    assert np.abs(back.cpu().numpy() - g["yuv444"]).max() < 1e-6
+    t3 = TF.yuv_420_to_444((y, cu(g["u420"]), cu(g["v420"])), return_tuple=True)
+    assert len(t3) == 3 and tuple(t3[1].shape) == tuple(y.shape)
+    with pytest.raises(ValueError):
+        TF.rgb2ycbcr(torch.zeros(2, 4, 8, 8, device=dev()))
+    with pytest.raises(ValueError):
+        TF.yuv_444_to_420(cu(g["ycbcr"]), mode="nearest")
+    with pytest.raises(NotImplementedError):
+        TF.yuv_420_to_444((y, u, v), mode="bicubic")

@@ -237,3 +237,15 @@ def test_torch_port_ssf2020(ssf_golden):
     assert np.max(np.abs(T["x_pred"].numpy() - g["x_pred"])) < 1e-4
     mi = g["motion_info"]
     assert np.abs(mi[:, 0]).max() * 128 > 3 and (mi[:, 2] * 3 + 2.5).min() < 0 and (mi[:, 2] * 3 + 2.5).max() > 5   # non-degenerate
+
+
+def test_torch_port_colour_transforms():
+    """rgb2ycbcr / ycbcr2rgb / yuv_444_to_420 / yuv_420_to_444 vs the reference's own functions (tests/golden/color.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "color.npz"))
+    rgb = torch.from_numpy(g["rgb"])
+    ycc = tp.rgb2ycbcr(rgb)
+    assert np.array_equal(ycc.numpy(), g["ycbcr"]) and np.array_equal(tp.ycbcr2rgb(ycc).numpy(), g["rgb_back"])
+    y, u, v = tp.yuv_444_to_420(ycc)
+    assert np.array_equal(u.numpy(), g["u420"]) and np.array_equal(v.numpy(), g["v420"])
+    assert np.array_equal(tp.yuv_420_to_444((y, u, v)).numpy(), g["yuv444"])
