@@ -28,7 +28,7 @@ from .layers import GDN, Conv2d, conv, deconv
 from .models import MeanScaleHyperprior, _nhwc_to_logical
 from .transforms import TransformStack, run_layers
 
-__all__ = ["MaskedConv2d", "ESA", "Encoder1", "Decoder1", "JointAutoregressiveHierarchicalPriors_R",
+__all__ = ["MaskedConv2d", "ESA", "Encoder1", "Decoder1", "JointAutoregressiveHierarchicalPriors_R", "Guided_compresser",
            "JointAutoregressiveHierarchicalPriors_D"]
 
 
@@ -137,9 +137,9 @@ class ESA(nn.Module):
 class Encoder1(nn.Module):
     """google.py:696-718: g_a with its three post-GDN feature maps exposed."""
 
-    def __init__(self, N, M, **kwargs):
+    def __init__(self, N, M, channel=3, first_stride=2, **kwargs):
         super().__init__()
-        self.g_a_conv1 = conv(3, N, kernel_size=5, stride=2)
+        self.g_a_conv1 = conv(channel, N, kernel_size=5, stride=first_stride)
         self.g_a_gdn1 = GDN(N)
         self.g_a_conv2 = conv(N, N, kernel_size=5, stride=2)
         self.g_a_gdn2 = GDN(N)
@@ -163,7 +163,7 @@ class Encoder1(nn.Module):
 class Decoder1(nn.Module):
     """google.py:720-742"""
 
-    def __init__(self, N, M, **kwargs):
+    def __init__(self, N, M, channel=3, first_stride=2, **kwargs):
         super().__init__()
         self.g_s_conv1 = deconv(M, N, kernel_size=5, stride=2)
         self.g_s_gdn1 = GDN(N, inverse=True)
@@ -171,7 +171,7 @@ class Decoder1(nn.Module):
         self.g_s_gdn2 = GDN(N, inverse=True)
         self.g_s_conv3 = deconv(N, N, kernel_size=5, stride=2)
         self.g_s_gdn3 = GDN(N, inverse=True)
-        self.g_s_conv4 = deconv(N, 3, kernel_size=5, stride=2)
+        self.g_s_conv4 = deconv(N, channel, kernel_size=5, stride=first_stride)
 
     def forward_internal(self, y_hat_bf16: Tensor):
         g1 = run_layers([self.g_s_conv1, self.g_s_gdn1], y_hat_bf16, "nhwc_bf16", "nhwc_bf16")
@@ -254,10 +254,11 @@ class JointAutoregressiveHierarchicalPriors_R(_ContextModelMixin, MeanScaleHyper
     """Guide (RGB) branch, google.py:746-825.  ``forward`` also returns the six hidden maps the second branch fuses;
     they are logical (B, N, H, W) bf16 tensors in channels-last memory (the kernels' native activation format)."""
 
-    def __init__(self, N=192, M=192, **kwargs):
+    def __init__(self, N=192, M=192, channel=3, first_stride=2, **kwargs):
         super().__init__(N=N, M=M, **kwargs)
-        self.enc1 = Encoder1(N, M)
-        self.dec1 = Decoder1(N, M)
+        self.first_stride = first_stride
+        self.enc1 = Encoder1(N, M, channel, first_stride)
+        self.dec1 = Decoder1(N, M, channel, first_stride)
         self._init_entropy_stage(N, M)
         self.N = int(N)
         self.M = int(M)
@@ -270,6 +271,19 @@ class JointAutoregressiveHierarchicalPriors_R(_ContextModelMixin, MeanScaleHyper
         hidden = {k: _nhwc_to_logical(v) for k, v in (("ga1", ga1), ("ga2", ga2), ("ga3", ga3),
                                                     ("gs1", gs1), ("gs2", gs2), ("gs3", gs3))}
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "hidden": hidden}
+
+
+class Guided_compresser(JointAutoregressiveHierarchicalPriors_R):
+    """The guide-modality codec of the RGB-T reproduction (compressai/models/master.py:1167-1300): the same network as
+    ``JointAutoregressiveHierarchicalPriors_R`` with a configurable input channel count (default 1: thermal / depth) and
+    first-layer stride; same sub-module names, ``state_dict`` keys and ``forward`` result (incl. the six hidden maps)."""
+
+    def __init__(self, N=192, M=192, channel=1, first_stride=2, **kwargs):
+        super().__init__(N=N, M=M, channel=channel, first_stride=first_stride, **kwargs)
+
+    @property
+    def downsampling_factor(self) -> int:
+        return 2 ** (4 + 2)
 
 
 class JointAutoregressiveHierarchicalPriors_D(_ContextModelMixin, MeanScaleHyperprior):

@@ -387,6 +387,27 @@ def ssf_goldens(out):
             print(t, part, {k: (float(torch.log2(v).sum() / -(128 * 256)), float((v <= 1.0001e-9).float().mean())) for k, v in lk.items()})
 
 
+def guided_goldens(out):
+    """Guided_compresser (compressai/models/master.py:1215-1300), the RGB-T reproduction's guide codec: 1-channel input,
+    eval forward incl. the hidden maps' statistics, on the two-branch weight recipe."""
+    import json
+    from compressai.models.master import Guided_compresser
+    d = make_image(1, 128, 192, seed=5, C=1)
+    torch.manual_seed(0)
+    net = quiet(Guided_compresser, channel=1).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    load_into(net, make_mm_state_dict(shapes, 2))
+    quiet(net.update, force=True)
+    out["state_dict"] = np.array(json.dumps({k: [list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()}))
+    with torch.no_grad():
+        o = quiet(net, torch.from_numpy(d))
+    out["x"], out["x_hat"] = d, t2n(o["x_hat"])
+    for k, v in o["likelihoods"].items():
+        out[f"lik_{k}"] = t2n(v)
+    for k, v in o["hidden"].items():
+        out[f"hidden_{k}"] = t2n(v[:, ::8, ::2, ::2])      # strided subsample of every hidden map
+
+
 def color_goldens(out):
     """compressai.transforms.functional on a random frame (the reference's own functions)."""
     from compressai.transforms.functional import rgb2ycbcr, ycbcr2rgb, yuv_420_to_444, yuv_444_to_420
@@ -401,8 +422,9 @@ def color_goldens(out):
 def main():
     import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color"]
-    gens = {"kernels": kernel_goldens, "models": model_goldens, "models_mm": mm_goldens, "models_ssf": ssf_goldens, "color": color_goldens}
+    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color", "models_guided"]
+    gens = {"kernels": kernel_goldens, "models": model_goldens, "models_mm": mm_goldens, "models_ssf": ssf_goldens, "color": color_goldens,
+            "models_guided": guided_goldens}
     for name in which:
         d = {}
         gens[name](d)

@@ -140,3 +140,26 @@ def test_masked_conv_and_errors(setup):
         net_r.compress(torch.zeros(1, 3, 64, 64, device=dev()))
     with pytest.raises(RuntimeError):
         net_d(torch.zeros(1, 1, 64, 64), {})
+
+
+def test_guided_compresser_vs_reference_golden():
+    """Guided_compresser (compressai/models/master.py:1215-1300): 1-channel guide codec of the RGB-T reproduction."""
+    import os
+    gg = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_guided.npz"))
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(gg["state_dict"])).items()}
+    sd = {k: torch.from_numpy(v) for k, v in make_mm_state_dict(shapes, 2).items()}
+    net = mmcodec.Guided_compresser(channel=1).eval()
+    net.update()
+    net.load_state_dict({**net.state_dict(), **sd})
+    net.update(force=True)
+    net = net.to(dev())
+    x = torch.from_numpy(gg["x"]).to(dev())
+    with torch.no_grad():
+        o = net(x)
+    assert set(o) == {"x_hat", "likelihoods", "hidden"} and tuple(o["x_hat"].shape) == gg["x_hat"].shape
+    npix = x.shape[0] * x.shape[2] * x.shape[3]
+    ref_bpp = sum(oracle.bits(gg[f"lik_{k}"]) for k in o["likelihoods"]) / npix
+    assert abs(bpp_of(o["likelihoods"], npix) - ref_bpp) / ref_bpp < 0.05
+    for k in ("ga1", "ga2", "ga3"):      # encoder-side hidden maps do not pass through a quantiser: stage-wise tolerance
+        assert rel_rms(o["hidden"][k].float()[:, ::8, ::2, ::2], torch.from_numpy(gg[f"hidden_{k}"])) < 1e-2, k
+    assert rel_rms(o["x_hat"].float(), torch.from_numpy(gg["x_hat"])) < 0.15

@@ -249,3 +249,23 @@ def test_torch_port_colour_transforms():
     y, u, v = tp.yuv_444_to_420(ycc)
     assert np.array_equal(u.numpy(), g["u420"]) and np.array_equal(v.numpy(), g["v420"])
     assert np.array_equal(tp.yuv_420_to_444((y, u, v)).numpy(), g["yuv444"])
+
+
+def test_torch_port_guided_compresser():
+    """Guided_compresser (master.py:1215-1300) = the _R network on a 1-channel input: the port reproduces the reference run."""
+    import json
+    import os
+    from weights import make_mm_state_dict
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_guided.npz"))
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(g["state_dict"])).items()}
+    sd = {k: torch.from_numpy(v) for k, v in make_mm_state_dict(shapes, 2).items()}
+    sd["context_prediction.mask"] = tp.masked_conv_mask(shapes["context_prediction.weight"], "A")
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        o = tp.mm_r_forward(sd, torch.from_numpy(g["x"]))
+    assert np.max(np.abs(o["x_hat"].numpy() - g["x_hat"])) < 2e-4 * max(1.0, float(np.abs(g["x_hat"]).max()))
+    for k, l in o["likelihoods"].items():
+        assert rel_err(l.numpy(), g[f"lik_{k}"], 1e-9) < 1e-3, k
+    for k, v in o["hidden"].items():
+        ref = g[f"hidden_{k}"]
+        assert np.max(np.abs(v[:, ::8, ::2, ::2].numpy() - ref)) < 1e-4 * max(1.0, float(np.abs(ref).max())), k
