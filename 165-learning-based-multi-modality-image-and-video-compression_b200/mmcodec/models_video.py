@@ -195,6 +195,9 @@ class ScaleSpaceFlow(nn.Module):
     def forward(self, frames):
         if not isinstance(frames, List):
             raise RuntimeError(f"Invalid number of frames: {len(frames)}.")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("ScaleSpaceFlow has no backward path yet (QReLU, Gaussian-volume and warp adjoints): "
+                                      "call it under torch.no_grad()")
         reconstructions, frames_likelihoods = [], []
         x_hat, likelihoods = self.forward_keyframe(frames[0])
         reconstructions.append(x_hat)

@@ -131,6 +131,8 @@ def test_forward_vs_reference_golden(g, setup):
         assert rel_rms(out["x_hat"][t].float(), torch.from_numpy(g[f"x_hat_{t}"])) < 0.05
     with pytest.raises(RuntimeError):
         net(frames[0].to(dev()))
+    with pytest.raises(NotImplementedError):          # no backward path: fails loudly instead of silently detaching
+        net([f.to(dev()) for f in frames])
 
 
 def test_compress_decompress_round_trip(g, setup):
