@@ -38,7 +38,6 @@ namespace mmc {
 constexpr int tc_threads(int parts) { return 64 + 128 * parts; }
 // Pair kernel: the GDN norm contraction stays a per-CTA (cta_group::1) MMA on the CTA's own x^2 tile and a full copy of gamma, so the two
 // epilogues of a pair never wait for each other (a pair-wide GDN MMA needs a cross-CTA hand-shake per tile and was slower).
-constexpr bool kPairGdnShared = false;
 constexpr int kMaxStages = 8;
 constexpr int kMaxAccStages = 4;
 constexpr int kMaxTaps = 32;
@@ -183,6 +182,38 @@ __device__ __forceinline__ void store16(const TcParams &P, int64_t off, const fl
     }
 }
 
+// Constant operands that put the bias (and the GDN beta') into the accumulators through the tensor core instead of per-element
+// shared-memory loads and adds in the epilogue (measured: the 32 LDS.128 + 128 FADD per thread and tile cost 13 % of g_s.4):
+//   A "ones" tile [128 rows][K = 16]: columns 0 and 1 are 1.0;  B tile [rows][K = 16]: column 0 = bf16(v), column 1 = bf16(v - hi),
+// so that one extra K = 16 MMA adds v (to ~2^-17 relative) to every accumulator row.  K-major, NO swizzle: 8-row x 16-byte core
+// matrices, the two K halves 128 B apart (LBO), 8-row groups 256 B apart (SBO).
+constexpr int kConstRowsMax = 192;
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t saddr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;    // leading byte offset: second K half
+    d |= (uint64_t)(256 >> 4) << 32;    // stride byte offset: next 8 rows
+    d |= (uint64_t)1 << 46;
+    return d;                           // layout type 0: no swizzle
+}
+__device__ __forceinline__ void fill_const_tile(uint8_t *tile, int rows, const float *v, bool ones)
+{
+    // one thread per row: zero the row's 2 x 16 bytes, then set K columns 0 / 1
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+        uint8_t *row = tile + (r >> 3) * 256 + (r & 7) * 16;
+        float hi_f = 1.0f, lo_f = 1.0f;
+        if (!ones) {
+            const float val = v ? v[r] : 0.0f;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(val);
+            hi_f = __bfloat162float(hi);
+            lo_f = val - hi_f;
+        }
+        *reinterpret_cast<uint4 *>(row) = make_uint4(pack_bf16(hi_f, lo_f), 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(row + 128) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Fused GDN / IGDN epilogue (compressai/layers/gdn.py:77-92) for one 128-pixel x C-channel tile.
 // Each of the 256 epilogue threads owns one pixel row and NCH 16-column chunks (C/2 channels); the
@@ -201,9 +232,8 @@ struct GdnCtx {
     int64_t pix_off;
     int it;
     const int64_t *pix_off_s;   // per-pixel output offsets of this tile (-1: outside the image)
-    uint32_t ready_bar_leader;  // pair mode: cluster address of the leader's gdn_ready barrier
-    uint64_t *ready_bar;        // pair mode: the leader's own gdn_ready barrier (valid in the leader CTA)
     uint32_t rank;              // pair mode: CTA rank in the cluster
+    uint32_t ones, beta_tile;   // shared-memory addresses of the constant operands (see fill_const_tiles)
 };
 
 template <int NCH, int G, bool kPair, int kParts>
@@ -223,11 +253,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
         const int c0 = chunk_of(j) << 4;
-        float bs[16];
-        load16f(bias_s + c0, bs);
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) x[j][i] += bs[i];
+        uint32_t pk[8];      // (the bias is already in the accumulator: see the constant-operand MMAs below)
         if (P.out2 == 3 && g.valid) {
             // training: keep the pre-GDN activations (bf16) for the backward pass
             uint4 *dst = reinterpret_cast<uint4 *>(P.y2 + g.pix_off + c0);
@@ -250,29 +276,6 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         if ((threadIdx.x >> 5) == 2) {
             // first epilogue warp: uniform control flow, one elected lane issues the (compile-time unrolled) MMAs
             if (g.it == 0 && grp == 0) mbar_wait(g.gload_bar, 0);
-            if (kPair && kPairGdnShared) {
-                // both CTAs' x^2 tiles (and gamma halves) must be in place before the leader issues the pair MMA
-                if (elect_one()) mbar_arrive_cluster(g.ready_bar_leader);
-                __syncwarp();
-                if (g.rank == 0) {
-                    mbar_wait(g.ready_bar, gdn_phase);
-                    tc_fence_after();
-                    const uint32_t idesc = make_idesc_m256(gch * 16);
-                    const uint32_t a2 = smem_u32(g.sA2), gm = smem_u32(g.sG);
-                    if (elect_one()) {
-#pragma unroll
-                        for (int kc = 0; kc < NCH * kParts / 4; ++kc) {
-                            const uint64_t adesc = make_desc(a2 + (uint32_t)(kc * kABytes));
-                            const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * (P.Cout / 2) * 128));   // this CTA's half of gamma's rows
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                tc_mma2(g.tmem_base + g.norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
-                        }
-                        tc_commit2(g.gdn_bar);
-                    }
-                    __syncwarp();
-                }
-            } else {
             tc_fence_after();
             const uint32_t idesc = make_idesc(gch * 16);
             const uint32_t a2 = smem_u32(g.sA2), gm = smem_u32(g.sG) + (uint32_t)(g0 * 128);
@@ -285,10 +288,11 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
                     for (int k = 0; k < 4; ++k)
                         tc_mma(g.tmem_base + g.norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
                 }
+                // + 1 * beta': one K = 16 step against the constant operands (ones x [beta_hi, beta_lo, 0...])
+                tc_mma(g.tmem_base + g.norm_col, make_desc_ns(g.ones), make_desc_ns(g.beta_tile + (uint32_t)((g0 >> 3) * 256)), idesc, 1);
                 tc_commit(g.gdn_bar);
             }
             __syncwarp();
-            }
         }
         mbar_wait(g.gdn_bar, gdn_phase);
         gdn_phase ^= 1;
@@ -307,11 +311,9 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
                 if (jb + u >= per) continue;
                 const int j = grp * per + jb + u;
                 const int c0 = chunk_of(j) << 4;
-                float bt[16];
-                load16f(beta_s + c0, bt);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float n = bt[i] + nrm[u][i];
+                    const float n = nrm[u][i];          // beta' + gamma' x^2: beta' entered through the constant-operand MMA
                     float f = rsqrt_fast(n);
                     if (inverse) f *= n;          // IGDN: sqrt(n) = n * rsqrt(n)
                     x[j][i] *= f;
@@ -370,18 +372,20 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
     constexpr int kEpiThreads = 128 * kParts;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-    __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar, gload_bar, bres_bar, gdn_ready_bar;
+    __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar, gload_bar, bres_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[kMaxCout];
     __shared__ __align__(16) float beta_s[256];
     __shared__ int64_t pix_off_s[128];   // GDN epilogue: global element offset of each tile pixel (-1 = masked)
+    __shared__ __align__(128) uint8_t s_const[kEpi == EPI_GDN ? 4096 + 2 * (kConstRowsMax / 8) * 256 : 16];   // ones | bias | beta tiles
+    uint8_t *s_ones = s_const, *s_biasB = s_const + (kEpi == EPI_GDN ? 4096 : 0), *s_betaB = s_const + (kEpi == EPI_GDN ? 4096 + (kConstRowsMax / 8) * 256 : 0);
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int b_tile_bytes = (kPair ? P.Ntile / 2 : P.Ntile) * 128;   // pair mode: this CTA's half of the weight rows
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const int stage_bytes = kABytes + (P.b_resident ? 0 : b_tile_bytes);
     uint8_t *sG = smem + (size_t)P.num_stages * stage_bytes;       // gamma: (Cout/64) tiles of [Cout][64] bf16
-    uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * ((kPair && kPairGdnShared) ? 1 : 2);   // x^2:   (Cout/64) tiles of [128][64] bf16 (pair mode: half of gamma per CTA)
+    uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * 2;   // x^2:   (Cout/64) tiles of [128][64] bf16
     float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
     // resident weights (b_resident): one [Ntile][64] bf16 tile per K block, after the GDN / staging region
     const size_t epi_bytes = (kEpi == EPI_GDN) ? (size_t)P.Cout * P.Cout * 2 + (size_t)(P.Cout / 64) * kABytes
@@ -393,7 +397,6 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpi == EPI_SCATTER ? 4 : (kPair ? 2 : 1) * (kEpiThreads / 32)); }   // one arrival per epilogue warp (col2im: per team of 4)
-        mbar_init(&gdn_ready_bar, 2);
         mbar_init(&gdn_bar, 1);
         mbar_init(&gload_bar, 1);
         mbar_init(&bres_bar, 1);
@@ -410,6 +413,14 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
+    }
+    if (kEpi == EPI_GDN) {
+        // pair mode: this CTA supplies weight (and bias) rows [rank * Ntile / 2, (rank + 1) * Ntile / 2) of the main-loop B operand
+        const int brows = kPair ? P.Ntile / 2 : P.Ntile;
+        fill_const_tile(s_ones, 128, nullptr, true);
+        fill_const_tile(s_biasB, brows, P.bias ? P.bias + (kPair ? (int)rank * brows : 0) : nullptr, false);
+        fill_const_tile(s_betaB, P.Cout, P.beta, false);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     for (int i = threadIdx.x; i < kMaxCout; i += tc_threads(kParts)) {
         bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.0f;
@@ -428,10 +439,10 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
         // Whole warp walks the tile / K-block loops (uniform control flow); the lane chosen by elect.sync issues.
         if (kEpi == EPI_GDN) {
             if (elect_one()) {
-                const int grows = (kPair && kPairGdnShared) ? P.Cout / 2 : P.Cout;      // shared pair GDN: gamma rows [rank * C/2, (rank + 1) * C/2)
+                const int grows = P.Cout;
                 mbar_expect_tx(&gload_bar, (uint32_t)(grows * P.Cout * 2));
                 for (int kc = 0; kc < P.Cout / 64; ++kc)
-                    tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * grows * 128, kc * 64, (kPair && kPairGdnShared) ? (int)rank * grows : 0);
+                    tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * grows * 128, kc * 64, 0);
             }
             __syncwarp();
         }
@@ -514,7 +525,10 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                         tc_mma2(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
                         tc_mma2(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
                         tc_commit2(&empty_bar[stage]);                          // both CTAs' producers
-                        if (kb == nkb - 1) tc_commit2(&tmem_full_bar[as]);      // both CTAs' epilogues
+                        if (kb == nkb - 1) {
+                            if (kEpi == EPI_GDN) tc_mma2(d_tmem, make_desc_ns(smem_u32(s_ones)), make_desc_ns(smem_u32(s_biasB)), idesc, 1);   // + bias
+                            tc_commit2(&tmem_full_bar[as]);      // both CTAs' epilogues
+                        }
                     } else {
                     if (P.debug != 2) {
                         // K=16 per step: +32 B (= +2 in descriptor units) inside the 128-byte swizzle atom
@@ -524,7 +538,10 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                         if (P.ksteps == 4) tc_mma(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
                     }
                     tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
-                    if (kb == nkb - 1) tc_commit(&tmem_full_bar[as]);   // accumulator complete -> epilogue
+                    if (kb == nkb - 1) {
+                        if (kEpi == EPI_GDN) tc_mma(d_tmem, make_desc_ns(smem_u32(s_ones)), make_desc_ns(smem_u32(s_biasB)), idesc, 1);   // + bias
+                        tc_commit(&tmem_full_bar[as]);   // accumulator complete -> epilogue
+                    }
                     }
                 }
                 __syncwarp();
@@ -546,7 +563,6 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
         int acc_i = 0;
         uint32_t acc_ph = 0;
         const uint32_t empty_leader = kPair ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
-        const uint32_t ready_leader = kPair ? mapa_u32(smem_u32(&gdn_ready_bar), 0) : 0u;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
             if (kPair) ti.init(P, tile);
             // col2im epilogue: two independent teams of 4 warps (one warp per TMEM lane quarter) take alternate tiles, each with its
@@ -680,7 +696,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                 } else {
                     if (half == 0) pix_off_s[row] = valid ? pix_off : -1;   // published by the bar.sync inside epilogue_gdn
                     GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it, pix_off_s,
-                             ready_leader, &gdn_ready_bar, rank};
+                             rank, smem_u32(s_ones), smem_u32(s_betaB)};
                     // (chunks per thread, norm groups): C=128 -> one 128-column norm pass; C=192 -> two 96-column passes
                     epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1), kPair, kParts>(g, bias_s, beta_s, gdn_phase);
                 }
@@ -1095,7 +1111,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
 
     size_t fixed = 1024;  // alignment slack
-    if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * ((P.pair && kPairGdnShared) ? 1 : 2) + (size_t)(d->Cout / 64) * kABytes;
+    if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (size_t)(d->Cout / 64) * kABytes;
     if (pl.mode == MODE_SCATTER) fixed += 2 * ((((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023);   // one staging buffer per epilogue team
     // Small layers (image-edge conv, reconstruction deconv): keep every weight tile resident in shared memory so that
     // the K blocks stream activations only (halves the L2 -> SM traffic of those layers).
@@ -1133,7 +1149,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         MMC_CHECK_ARG(aligned16(gamma_eff_bf16), "%s: gamma must be 16-byte aligned", name);
         uint64_t dims[2] = {(uint64_t)d->Cout, (uint64_t)d->Cout};
         uint64_t str[1] = {(uint64_t)d->Cout * 2};
-        uint32_t box[2] = {64, (uint32_t)((P.pair && kPairGdnShared) ? d->Cout / 2 : d->Cout)};
+        uint32_t box[2] = {64, (uint32_t)d->Cout};
         uint32_t es[2] = {1, 1};
         rc = encode_map(&P.tmG, gamma_eff_bf16, 2, dims, str, box, es, "gamma");
         if (rc) return rc;
