@@ -104,6 +104,12 @@ __device__ __forceinline__ float rsqrt_fast(float v)
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
 }
+__device__ __forceinline__ float sqrt_fast(float v)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b)
 {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -315,9 +321,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float n = nrm[u][i];          // beta' + gamma' x^2: beta' entered through the constant-operand MMA
-                    float f = rsqrt_fast(n);
-                    if (inverse) f *= n;          // IGDN: sqrt(n) = n * rsqrt(n)
-                    x[j][i] *= f;
+                    x[j][i] *= inverse ? sqrt_fast(n) : rsqrt_fast(n);   // one MUFU either way
                 }
                 const float *y = x[j];
                 if (G == 1 && !P.out_f32 && !P.out2 && P.direct_store) {
