@@ -163,3 +163,30 @@ def test_guided_compresser_vs_reference_golden():
     for k in ("ga1", "ga2", "ga3"):      # encoder-side hidden maps do not pass through a quantiser: stage-wise tolerance
         assert rel_rms(o["hidden"][k].float()[:, ::8, ::2, ::2], torch.from_numpy(gg[f"hidden_{k}"])) < 1e-2, k
     assert rel_rms(o["x_hat"].float(), torch.from_numpy(gg["x_hat"])) < 0.15
+
+
+def test_full_size_properties_768x512():
+    """BASELINE size (768x512 RGB + depth pair, random-init weights): shapes, likelihood ranges, finite outputs, batch
+    independence (images are independent units: a batch of two equals two batches of one)."""
+    torch.manual_seed(0)
+    net_r = mm.JointAutoregressiveHierarchicalPriors_R(192, 192).eval()
+    net_d = mm.JointAutoregressiveHierarchicalPriors_D(192, 192).eval()
+    for n in (net_r, net_d):
+        n.update()
+        n.to(dev())
+    gen = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 512, 768, generator=gen).to(dev())
+    d = torch.rand(2, 1, 512, 768, generator=gen).to(dev())
+    with torch.no_grad():
+        o_r = net_r(x)
+        o_d = net_d(d, o_r["hidden"])
+        o_r0 = net_r(x[:1])
+        o_d0 = net_d(d[:1], o_r0["hidden"])
+    assert tuple(o_d["x_hat"].shape) == (2, 1, 512, 768) and tuple(o_r["x_hat"].shape) == (2, 3, 512, 768)
+    assert tuple(o_r["hidden"]["ga1"].shape) == (2, 192, 256, 384) and tuple(o_r["hidden"]["gs3"].shape) == (2, 192, 256, 384)
+    assert tuple(o_d["likelihoods"]["y"].shape) == (2, 192, 32, 48) and tuple(o_d["likelihoods"]["z"].shape) == (2, 192, 8, 12)
+    for o in (o_r, o_d):
+        assert bool(torch.isfinite(o["x_hat"]).all())
+        for lk in o["likelihoods"].values():
+            assert float(lk.min()) >= 1e-9 * 0.999 and float(lk.max()) <= 1 + 1e-6
+    assert torch.equal(o_d0["x_hat"], o_d["x_hat"][:1]) and torch.equal(o_d0["likelihoods"]["y"], o_d["likelihoods"]["y"][:1])

@@ -151,3 +151,31 @@ def test_compress_decompress_round_trip(g, setup):
     assert abs(mine_key - int(g["bytes_keyframe"].sum())) / int(g["bytes_keyframe"].sum()) < 0.03
     mine_inter = sum(len(strings[1][k][i][0]) for k in ("motion", "residual") for i in range(2))
     assert abs(mine_inter - int(g["bytes_inter_1"].sum())) / int(g["bytes_inter_1"].sum()) < 0.05
+
+
+def test_full_size_properties_1080p():
+    """BASELINE size (1920x1152, random-init weights): size-independent properties -- likelihoods in [1e-9, 1], finite
+    reconstructions of the input shape, the decoder reproduces the encoder's reconstruction loop exactly, and the graph-replayed
+    forward equals the eager one."""
+    torch.manual_seed(0)
+    net = mmcodec.ScaleSpaceFlow().eval()
+    net.update()
+    net = net.to(dev())
+    gen = torch.Generator().manual_seed(5)
+    frames = [torch.rand(1, 3, 1152, 1920, generator=gen).to(dev()) for _ in range(2)]
+    with torch.no_grad():
+        out = net(frames)
+        strings, shapes = net.compress(frames)
+        dec = net.decompress(strings, shapes)
+        graphed = mmcodec.GraphedForward(lambda fs: net(fs), frames)
+        out_g = graphed(frames)
+        torch.cuda.synchronize()
+    for t in range(2):
+        assert tuple(out["x_hat"][t].shape) == (1, 3, 1152, 1920) and bool(torch.isfinite(out["x_hat"][t]).all())
+        for part in out["likelihoods"][t].values():
+            for lk in part.values():
+                assert float(lk.min()) >= 1e-9 * 0.999 and float(lk.max()) <= 1 + 1e-6
+        assert float((dec[t] - out["x_hat"][t]).abs().max()) < 1e-5
+        assert torch.equal(out_g["x_hat"][t], out["x_hat"][t])
+    assert tuple(out["likelihoods"][1]["motion"]["y"].shape) == (1, 192, 72, 120)
+    assert tuple(out["likelihoods"][1]["residual"]["z"].shape) == (1, 192, 9, 15)
