@@ -75,6 +75,7 @@ struct TcParams {
     int kchunks;     // K boxes per tap (ceil(Cin / 64); 1 in MODE_PAD8)
     int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
     int num_stages, acc_stages;
+    int a_tmem;       // GDN: the x^2 operand of the norm contraction lives in TMEM (A-from-TMEM MMA), not in shared memory
     int bias_mma;     // the bias enters the accumulator through a constant-operand MMA (one N block per tile), not in the epilogue
     int direct_store; // GDN epilogue: 32-byte vector stores straight from registers instead of the shared-memory staged copy-out
     int debug;       // profiling aid (env MMC_TC_DEBUG): 1 = no TMA traffic after priming, 2 = no main-loop MMAs, 3 = no GDN MMAs
@@ -103,6 +104,17 @@ __device__ __forceinline__ float rsqrt_fast(float v)
     float r;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
     return r;
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T: A rows = TMEM lanes, K elements packed two per 32-bit column
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 __device__ __forceinline__ float sqrt_fast(float v)
 {
@@ -241,6 +253,9 @@ struct GdnCtx {
     const int64_t *pix_off_s;   // per-pixel output offsets of this tile (-1: outside the image)
     uint32_t rank;              // pair mode: CTA rank in the cluster
     uint32_t ones, beta_tile;   // shared-memory addresses of the constant operands (see fill_const_tiles)
+    uint32_t a_col;             // TMEM column of the x^2 operand (a_tmem mode)
+    uint64_t *empty_bar;        // this tile's accumulator-release barrier (pair mode: the leader's, as a cluster address)
+    uint32_t empty_leader;
 };
 
 template <int NCH, int G, bool kPair, int kParts>
@@ -269,13 +284,26 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(x[j][2 * i] * x[j][2 * i], x[j][2 * i + 1] * x[j][2 * i + 1]);
-        uint8_t *tile_base = g.sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)g.row * 128;
-        const int j0 = (c0 & 63) >> 3;   // 16-byte chunk index inside the 128-byte row
-        *reinterpret_cast<uint4 *>(tile_base + (((j0) ^ (g.row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4 *>(tile_base + (((j0 + 1) ^ (g.row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (P.a_tmem) {
+            // A operand in TMEM: row = lane, K element k in 32-bit column k / 2 (two bf16 per column)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(g.tmem_base + g.lane_addr + g.a_col + (uint32_t)(c0 >> 1)),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+        } else {
+            uint8_t *tile_base = g.sA2 + (size_t)(c0 >> 6) * kABytes + (size_t)g.row * 128;
+            const int j0 = (c0 & 63) >> 3;   // 16-byte chunk index inside the 128-byte row
+            *reinterpret_cast<uint4 *>(tile_base + (((j0) ^ (g.row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *reinterpret_cast<uint4 *>(tile_base + (((j0 + 1) ^ (g.row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+    if (P.a_tmem) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+    // x is in registers (and x^2 staged): the conv accumulator can go back to the MMA warp already
     tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        if (kPair) mbar_arrive_cluster(g.empty_leader);
+        else mbar_arrive(g.empty_bar);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 #pragma unroll
     for (int grp = 0; grp < G; ++grp) {
@@ -292,8 +320,10 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
                     const uint64_t adesc = make_desc(a2 + (uint32_t)(kc * kABytes));
                     const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * P.Cout * 128));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma(g.tmem_base + g.norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                    for (int k = 0; k < 4; ++k) {
+                        if (P.a_tmem) tc_mma_ts(g.tmem_base + g.norm_col, g.tmem_base + g.a_col + (uint32_t)((kc * 4 + k) * 8), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                        else tc_mma(g.tmem_base + g.norm_col, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+                    }
                 }
                 // + 1 * beta': one K = 16 step against the constant operands (ones x [beta_hi, beta_lo, 0...])
                 tc_mma(g.tmem_base + g.norm_col, make_desc_ns(g.ones), make_desc_ns(g.beta_tile + (uint32_t)((g0 >> 3) * 256)), idesc, 1);
@@ -394,7 +424,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
     uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * 2;   // x^2:   (Cout/64) tiles of [128][64] bf16
     float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
     // resident weights (b_resident): one [Ntile][64] bf16 tile per K block, after the GDN / staging region
-    const size_t epi_bytes = (kEpi == EPI_GDN) ? (size_t)P.Cout * P.Cout * 2 + (size_t)(P.Cout / 64) * kABytes
+    const size_t epi_bytes = (kEpi == EPI_GDN) ? (size_t)P.Cout * P.Cout * 2 + (P.a_tmem ? 0 : (size_t)(P.Cout / 64) * kABytes)
                            : (kEpi == EPI_SCATTER) ? 2 * (((size_t)128 * P.spitch * sizeof(float) + 1023) & ~(size_t)1023) : 0;
     uint8_t *sBres = sG + epi_bytes;
 
@@ -715,14 +745,15 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                 } else {
                     if (half == 0) pix_off_s[row] = valid ? pix_off : -1;   // published by the bar.sync inside epilogue_gdn
                     GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it, pix_off_s,
-                             rank, smem_u32(s_ones), smem_u32(s_betaB)};
+                             rank, smem_u32(s_ones), smem_u32(s_betaB), norm_col + (uint32_t)P.gdn_chunk, &tmem_empty_bar[as],
+                             kPair ? empty_leader + (uint32_t)(as * sizeof(uint64_t)) : 0u};
                     // (chunks per thread, norm groups): C=128 -> one 128-column norm pass; C=192 -> two 96-column passes
                     epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1), kPair, kParts>(g, bias_s, beta_s, gdn_phase);
                 }
             }
             tc_fence_before();
             __syncwarp();          // every lane's TMEM reads of this accumulator are complete: one arrival per warp
-            if (lane == 0) {
+            if (lane == 0 && kEpi != EPI_GDN) {      // (the GDN epilogue releases the accumulator right after its first pass)
                 if (kPair) mbar_arrive_cluster(empty_leader + (uint32_t)(as * sizeof(uint64_t)));   // the leader's MMA issuer waits for both epilogues
                 else mbar_arrive(&tmem_empty_bar[as]);
             }
@@ -951,6 +982,7 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
     if (const char *g = getenv("MMC_TC_DEBUG")) Q.debug = atoi(g);
     Q.direct_store = 1;   // measured: g_a.0 1.04 -> 0.99 ms, g_s.2 0.38 -> 0.37 ms vs the staged, coalesced copy-out (MMC_TC_GDN_DIRECT=0)
     if (const char *g = getenv("MMC_TC_GDN_DIRECT")) Q.direct_store = atoi(g);
+    if (Q.a_tmem) Q.direct_store = 1;    // no shared-memory x^2 tile to stage the copy-out in
     if (const char *g = getenv("MMC_TC_GRID")) {   // profiling aid: restrict the persistent grid (profiles/probe_grid.py)
         int v = atoi(g);
         if (v >= 1 && v < grid) grid = v;
@@ -1123,17 +1155,21 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     P.bias_mma = (d->gdn != MMC_GDN_NONE) ? 1 : 0;
     P.gdn_chunk = 0;
     if (d->gdn != MMC_GDN_NONE) P.gdn_chunk = (3 * P.Ntile <= 512) ? P.Ntile : P.Ntile / 2;
-    P.acc_stages = (512 - P.gdn_chunk) / P.Ntile;      // as many accumulator stages as TMEM holds (epilogue slack)
+    // GDN with C <= 128: the x^2 operand of the norm contraction goes through TMEM (C / 2 columns), which frees its shared-memory
+    // tile for one more pipeline stage and removes its write + read from the shared-memory port
+    P.a_tmem = (d->gdn != MMC_GDN_NONE && d->Cout <= 128) ? 1 : 0;
+    if (const char *g = getenv("MMC_TC_ATMEM")) P.a_tmem = P.a_tmem && atoi(g) != 0;
+    P.acc_stages = (512 - P.gdn_chunk - (P.a_tmem ? d->Cout / 2 : 0)) / P.Ntile;      // as many accumulator stages as TMEM holds
     if (P.acc_stages > kMaxAccStages) P.acc_stages = kMaxAccStages;
     if (P.acc_stages < 1) P.acc_stages = 1;
     if (pl.mode == MODE_SCATTER) {
         P.acc_stages &= ~1;    // the two col2im epilogue teams own alternate accumulator stages
         MMC_UNSUPPORTED(P.acc_stages < 2, "%s: the reconstruction kernel needs two accumulator stages (N tile %d)", name, P.Ntile);
     }
-    MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
+    MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk + (P.a_tmem ? d->Cout / 2 : 0) > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
 
     size_t fixed = 1024;  // alignment slack
-    if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (size_t)(d->Cout / 64) * kABytes;
+    if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (P.a_tmem ? 0 : (size_t)(d->Cout / 64) * kABytes);
     if (pl.mode == MODE_SCATTER) fixed += 2 * ((((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023);   // one staging buffer per epilogue team
     // Small layers (image-edge conv, reconstruction deconv): keep every weight tile resident in shared memory so that
     // the K blocks stream activations only (halves the L2 -> SM traffic of those layers).
