@@ -32,6 +32,8 @@ CASES = [
     (False, 128, 192, 5, 2, 16, 24, L.ACT_NONE, L.GDN_NONE, 1),     # g_a.6 class (N=192)
     (False, 192, 320, 5, 2, 34, 60, L.ACT_NONE, L.GDN_NONE, 1),     # mbt2018-mean g_a.6: two N blocks, ragged 17x30 output
     (False, 192, 192, 5, 2, 20, 28, L.ACT_NONE, L.GDN_FORWARD, 1),  # C=192 GDN (two 96-column norm chunks)
+    (False, 64, 64, 5, 2, 20, 28, L.ACT_NONE, L.GDN_FORWARD, 2),    # C=64 GDN (x^2 operand through TMEM, 32 columns)
+    (True, 64, 64, 3, 1, 9, 11, L.ACT_NONE, L.GDN_INVERSE, 1),      # C=64 IGDN on a stride-1 transposed conv
     (False, 128, 128, 5, 2, 17, 23, L.ACT_LEAKY_RELU, L.GDN_NONE, 2),   # odd input size
     (True, 192, 128, 5, 2, 8, 12, L.ACT_NONE, L.GDN_INVERSE, 2),    # g_s.0 class: 4-phase deconv + IGDN
     (True, 128, 128, 5, 2, 16, 24, L.ACT_RELU, L.GDN_NONE, 1),      # h_s class
