@@ -58,7 +58,7 @@ enum TcMode {
 };
 
 struct TcParams {
-    CUtensorMap tmA, tmB, tmG;
+    CUtensorMap tmA, tmB, tmG, tmA2;   // tmA2: second activation source (channels Cin1 .. Cin-1), see mmc_conv_forward_tc2
     Tap taps[kMaxTaps];
     int phase_begin[5];  // taps of phase p are [phase_begin[p], phase_begin[p+1])
     int n_phases;
@@ -73,6 +73,7 @@ struct TcParams {
     int spitch;                          // MODE_SCATTER: fp32 staging row pitch (floats)
     int Cout, Ntile, n_blocks;
     int kchunks;     // K boxes per tap (ceil(Cin / 64); 1 in MODE_PAD8)
+    int kchunks1;    // K boxes that come from the first activation source (== kchunks with a single source)
     int ksteps;      // K=16 MMA steps per K box (4; 3 for a 5-wide kernel row in MODE_PAD8)
     int num_stages, acc_stages;
     int a_tmem;       // GDN: the x^2 operand of the norm contraction lives in TMEM (A-from-TMEM MMA), not in shared memory
@@ -510,13 +511,15 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                             // the leader's barrier collects the bytes of both CTAs; only the leader arrives on it
                             const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
                             if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
-                            tma_load_4d_pair(&P.tmA, fb, a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
+                            if (kc < P.kchunks1) tma_load_4d_pair(&P.tmA, fb, a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
+                            else tma_load_4d_pair(&P.tmA2, fb, a, (kc - P.kchunks1) * 64, cx + tap.dx, cy + tap.dy, t.b);
                             tma_load_2d_pair(&P.tmB, fb, a + kABytes, kc * 64, tap.brow + t.n0 + (int)rank * (P.Ntile / 2));
                         } else if (P.debug == 1 && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
                             mbar_arrive(&full_bar[stage]);
                         } else {
                             mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                            tma_load_4d(&P.tmA, &full_bar[stage], a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
+                            if (kc < P.kchunks1) tma_load_4d(&P.tmA, &full_bar[stage], a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
+                            else tma_load_4d(&P.tmA2, &full_bar[stage], a, (kc - P.kchunks1) * 64, cx + tap.dx, cy + tap.dy, t.b);
                             if (!P.b_resident) tma_load_2d(&P.tmB, &full_bar[stage], a + kABytes, kc * 64, tap.brow + t.n0);
                         }
                     }
@@ -1070,10 +1073,27 @@ int mmc_conv_pack_weights(const mmc_conv_desc *d, const float *w, void *w_packed
     return MMC_OK;
 }
 
+static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const void *x2, int cin1, const void *w_packed, const float *bias,
+                                const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream, const char *name);
+
 int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_packed, const float *bias,
                         const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream)
 {
-    const char *name = "mmc_conv_forward_tc";
+    return conv_forward_tc_impl(d, x, nullptr, d ? d->Cin : 0, w_packed, bias, beta_eff, gamma_eff_bf16, y, y2, stream, "mmc_conv_forward_tc");
+}
+
+int mmc_conv_forward_tc2(const mmc_conv_desc *d, const void *x1, int cin1, const void *x2, const void *w_packed, const float *bias,
+                         const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream)
+{
+    MMC_CHECK_ARG(d && x2 && cin1 > 0 && cin1 < d->Cin, "mmc_conv_forward_tc2: needs two sources with 0 < cin1 < Cin");
+    MMC_UNSUPPORTED(cin1 % 64 != 0 || (d->Cin - cin1) % 8 != 0 || d->in_layout != MMC_NHWC,
+                    "mmc_conv_forward_tc2: the first source must have a multiple of 64 channels, the second a multiple of 8 (NHWC bf16)");
+    return conv_forward_tc_impl(d, x1, x2, cin1, w_packed, bias, beta_eff, gamma_eff_bf16, y, y2, stream, "mmc_conv_forward_tc2");
+}
+
+static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const void *x2, int cin1, const void *w_packed, const float *bias,
+                                const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream, const char *name)
+{
     Plan pl;
     int rc = make_plan(d, pl, name);
     if (rc) return rc;
@@ -1093,6 +1113,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     }
     if (d->B == 0) return MMC_OK;
     MMC_CHECK_ARG(x && w_packed && y, "%s: NULL buffer", name);
+    MMC_CHECK_ARG(!x2 || (aligned16(x2) && pl.mode != MODE_PAD8), "%s: second source must be 16-byte aligned NHWC", name);
     MMC_CHECK_ARG(aligned16(x) && aligned16(w_packed) && aligned16(y) && (!y2 || aligned16(y2)), "%s: buffers must be 16-byte aligned", name);
 
     TcParams P;
@@ -1100,6 +1121,7 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
     P.mode = pl.mode;
     P.Ho = pl.Ho; P.Wo = pl.Wo; P.B = d->B; P.Cout = d->Cout;
     P.kchunks = pl.kchunks; P.ksteps = pl.ksteps;
+    P.kchunks1 = x2 ? cin1 / 64 : pl.kchunks;
     P.act = d->act; P.gdn = d->gdn; P.out_f32 = (d->out_dtype == MMC_F32); P.out2 = d->out2_bf16;
     P.bias = bias; P.beta = beta_eff; P.y = y; P.y2 = (__nv_bfloat16 *)y2;
     P.n_phases = pl.n_phases; P.a_sx = pl.a_sx; P.a_sy = pl.a_sy; P.out_stride = pl.out_stride; P.Gh = pl.Gh; P.Gw = pl.Gw;
@@ -1188,11 +1210,19 @@ int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_pac
         uint32_t es[4] = {1, 1, (uint32_t)P.a_sy, 1};
         rc = encode_map(&P.tmA, x, 4, dims, str, box, es, "padded image");
     } else {
-        uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
-        uint64_t str[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+        // one tensor map per activation source: the K loop takes its 64-channel boxes from the first source, then from the second
+        // (the concatenation of two feature maps along the channels is never materialised)
+        const int c1 = x2 ? cin1 : d->Cin, c2 = d->Cin - c1;
+        uint64_t dims[4] = {(uint64_t)c1, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+        uint64_t str[3] = {(uint64_t)c1 * 2, (uint64_t)d->W * c1 * 2, (uint64_t)d->H * d->W * c1 * 2};
         uint32_t box[4] = {64, (uint32_t)(P.TW * P.a_sx), (uint32_t)(P.TH * P.a_sy), 1};
         uint32_t es[4] = {1, (uint32_t)P.a_sx, (uint32_t)P.a_sy, 1};
         rc = encode_map(&P.tmA, x, 4, dims, str, box, es, "activations");
+        if (!rc && x2) {
+            uint64_t dims2[4] = {(uint64_t)c2, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+            uint64_t str2[3] = {(uint64_t)c2 * 2, (uint64_t)d->W * c2 * 2, (uint64_t)d->H * d->W * c2 * 2};
+            rc = encode_map(&P.tmA2, x2, 4, dims2, str2, box, es, "activations (second source)");
+        }
     }
     if (rc) return rc;
     {

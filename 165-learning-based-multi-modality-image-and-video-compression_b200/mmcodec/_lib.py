@@ -59,6 +59,7 @@ _PROTOS = {
     "mmc_conv_pack_weights": (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, ctypes.POINTER(ctypes.c_size_t), c_vp]),
     "mmc_conv_forward_direct": (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mmc_conv_forward_tc": (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mmc_conv_forward_tc2": (c_int, [ctypes.POINTER(ConvDesc), c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mmc_conv_pad8_size": (c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "mmc_pad_nchw_to_nhwc8": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "mmc_nchw_f32_to_nhwc_bf16": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),

@@ -224,7 +224,7 @@ class _ContextModelMixin:
             y_hat = ops.quantize_dequantize(y_l)
         y_hat_bf16 = AG.cast_bf16(y_hat).permute(0, 2, 3, 1)
         ctx = run_layers([self.context_prediction], y_hat_bf16, "nhwc_bf16", "nhwc_bf16")
-        gp = run_layers(list(self.entropy_parameters), torch.cat((params, ctx), dim=-1), "nhwc_bf16", "nhwc_f32")
+        gp = run_layers(list(self.entropy_parameters), (params, ctx), "nhwc_bf16", "nhwc_f32")
         scales_hat, means_hat = _nhwc_to_logical(gp[..., :M]), _nhwc_to_logical(gp[..., M:])
         y_noise = draw("y", y_l) if self.training else None
         _, y_lik = AG.gc_forward(y_l, scales_hat, means_hat, y_noise, gc.lower_bound_scale._sync_bound(), gc._lik_bound())
@@ -322,28 +322,28 @@ class JointAutoregressiveHierarchicalPriors_D(_ContextModelMixin, MeanScaleHyper
         """eg_ext(2i-1)(x), eg_ext(2i)(guide) -> cat -> tran_conv_i -> ESA_i   (google.py:1151-1156 and five repeats)"""
         e_own = run_layers(list(getattr(self, f"eg_ext{2 * i - 1}")), x, "nhwc_bf16", "nhwc_bf16")
         e_guide = run_layers(list(getattr(self, f"eg_ext{2 * i}")), guide, "nhwc_bf16", "nhwc_bf16")
-        f = run_layers([getattr(self, f"tran_conv{i}")], torch.cat((e_own, e_guide), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        f = run_layers([getattr(self, f"tran_conv{i}")], (e_own, e_guide), "nhwc_bf16", "nhwc_bf16")
         return getattr(self, f"attention{i}").forward_nhwc_bf16(f)
 
     def _analysis(self, x, g):
         """pic2_g_a with the three encoder-side fusions (google.py:1148-1194): fp32 NCHW depth map -> (y fp32, y bf16), NHWC."""
         a = run_layers([self.pic2_g_a_conv1, self.pic2_g_a_gdn1], x, "nchw_f32", "nhwc_bf16")
         f1 = self._fuse(1, a, g["ga1"])
-        a = run_layers([self.pic2_g_a_conv2, self.pic2_g_a_gdn2], torch.cat((a, f1), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        a = run_layers([self.pic2_g_a_conv2, self.pic2_g_a_gdn2], (a, f1), "nhwc_bf16", "nhwc_bf16")
         f2 = self._fuse(2, a, g["ga2"])
-        a = run_layers([self.pic2_g_a_conv3, self.pic2_g_a_gdn3], torch.cat((a, f2), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        a = run_layers([self.pic2_g_a_conv3, self.pic2_g_a_gdn3], (a, f2), "nhwc_bf16", "nhwc_bf16")
         f3 = self._fuse(3, a, g["ga3"])
-        return run_layers([self.pic2_g_a_conv4], torch.cat((a, f3), dim=-1), "nhwc_bf16", "nhwc_f32", out2=2)
+        return run_layers([self.pic2_g_a_conv4], (a, f3), "nhwc_bf16", "nhwc_f32", out2=2)
 
     def _synthesis(self, y_hat_bf16, g):
         """pic2_g_s with the three decoder-side fusions (google.py:1213-1246): y_hat bf16 NHWC -> x_hat fp32 NCHW."""
         s = run_layers([self.pic2_g_s_conv1, self.pic2_g_s_gdn1], y_hat_bf16, "nhwc_bf16", "nhwc_bf16")
         f4 = self._fuse(4, s, g["gs1"])
-        s = run_layers([self.pic2_g_s_conv2, self.pic2_g_s_gdn2], torch.cat((s, f4), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        s = run_layers([self.pic2_g_s_conv2, self.pic2_g_s_gdn2], (s, f4), "nhwc_bf16", "nhwc_bf16")
         f5 = self._fuse(5, s, g["gs2"])
-        s = run_layers([self.pic2_g_s_conv3, self.pic2_g_s_gdn3], torch.cat((s, f5), dim=-1), "nhwc_bf16", "nhwc_bf16")
+        s = run_layers([self.pic2_g_s_conv3, self.pic2_g_s_gdn3], (s, f5), "nhwc_bf16", "nhwc_bf16")
         f6 = self._fuse(6, s, g["gs3"])
-        return run_layers([self.pic2_g_s_conv4], torch.cat((s, f6), dim=-1), "nhwc_bf16", "nchw_f32")
+        return run_layers([self.pic2_g_s_conv4], (s, f6), "nhwc_bf16", "nchw_f32")
 
     def forward(self, x, hidden: Dict[str, Tensor]):
         ops._require_cuda(x)

@@ -402,7 +402,16 @@ def conv_pack_weights(d: L.ConvDesc, w: Tensor) -> Tensor:
 
 def conv_forward_tc(d: L.ConvDesc, x: Tensor, w_packed: Tensor, bias: Optional[Tensor], beta_eff=None,
                     gamma_bf16=None, name: str = "conv"):
-    """Tensor-core (tcgen05) implicit-GEMM conv / deconv on NHWC bf16 input."""
+    """Tensor-core (tcgen05) implicit-GEMM conv / deconv on NHWC bf16 input.  ``x`` may be a pair (x1, x2) of NHWC tensors whose
+    channels are concatenated by the kernel's K loop (no torch.cat copy)."""
+    if isinstance(x, (tuple, list)):
+        x1, x2 = x
+        _require_cuda(x1, x2, w_packed)
+        y, y2 = _alloc_out(d, x1.device)
+        with _Timed(name + "|tc", conv_flops(d) if _profile is not None else 0.0):
+            L.check(L.lib().mmc_conv_forward_tc2(ctypes.byref(d), _ptr(x1), int(x1.shape[-1]), _ptr(x2), _ptr(w_packed), _ptr(bias),
+                                                 _ptr(beta_eff), _ptr(gamma_bf16), _ptr(y), _ptr(y2), _stream()))
+        return (y, y2) if d.out2_bf16 else y
     _require_cuda(x, w_packed)
     y, y2 = _alloc_out(d, x.device)
     with _Timed(name + "|tc", conv_flops(d) if _profile is not None else 0.0):

@@ -94,8 +94,23 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0, _tra
     logical shape and values as the reference's NCHW tensor).  With ``out2`` (1: |output|, 2: output)
     also returns that tensor as NHWC bf16 (the h_a input, models/google.py:283,381)."""
     assert in_fmt in FORMATS and out_fmt in FORMATS
+    pair = None
+    if isinstance(x, (tuple, list)):
+        # two NHWC bf16 feature maps whose channel concatenation feeds the first layer (google.py:1153 ...): the tensor-core kernel
+        # reads both sources in its K loop; anything else (training, odd channel counts) concatenates first
+        x1, x2 = x
+        ops._require_cuda(x1, x2)
+        first = next((m for m in layers if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d))), None)
+        fusable = (in_fmt == "nhwc_bf16" and use_tensor_cores and first is not None and x1.shape[-1] % 64 == 0 and x2.shape[-1] % 8 == 0
+                   and x1.shape[:3] == x2.shape[:3] and first.out_channels % 16 == 0
+                   and not (torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad or any(p.requires_grad for p in first.parameters()))))
+        if fusable:
+            pair = (x1.contiguous(), x2.contiguous())
+            x = pair[0]
+        else:
+            x = torch.cat((x1, x2), dim=-1)
     ops._require_cuda(x)
-    if _train_dispatch and torch.is_grad_enabled():
+    if _train_dispatch and torch.is_grad_enabled() and pair is None:
         from . import autograd as AG
         if AG.wants_grad(layers, x):
             return AG.run_layers_train(layers, x, in_fmt, out_fmt, out2)   # same kernels, recorded for backward
@@ -121,6 +136,8 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0, _tra
                 B, C, H, W = cur.shape
             else:
                 B, H, W, C = cur.shape
+            if i == 0 and pair is not None:
+                C += pair[1].shape[-1]
             if C != cin:
                 raise ValueError(f"expected {cin} input channels, got {C}")
             stride, k = c.stride[0], c.kernel_size[0]
@@ -161,7 +178,8 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0, _tra
                 bias = bias.float()
             name = getattr(c, "_mmc_name", "conv")
             if tc:
-                out = ops.conv_forward_tc(d, cur, c.packed_weight(d), bias, beta_eff, gamma_bf16, name=name)
+                src = pair if (i == 0 and pair is not None) else cur
+                out = ops.conv_forward_tc(d, src, c.packed_weight(d), bias, beta_eff, gamma_bf16, name=name)
             else:
                 out = ops.conv_forward_direct(d, cur, c.f32_weight(), bias, beta_eff, gamma_eff, name=name)
             if d.out2_bf16:

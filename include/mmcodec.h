@@ -234,6 +234,14 @@ MMC_API int mmc_conv_forward_direct(const mmc_conv_desc *d, const void *x, const
 MMC_API int mmc_conv_forward_tc(const mmc_conv_desc *d, const void *x, const void *w_packed, const float *bias,
                         const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2, void *stream);
 
+/* The same with the input channels coming from TWO NHWC bf16 tensors (channels [0, cin1) from x1, [cin1, Cin) from x2): the
+ * torch.cat of two feature maps in front of a convolution (compressai/models/google.py:1153,1161,... `tran_conv*`,
+ * `pic2_g_a_conv2..4`, `pic2_g_s_conv2..4`, `entropy_parameters`) is never materialised -- the K loop takes its channel boxes
+ * from the first tensor map, then from the second.  cin1 % 64 == 0, (Cin - cin1) % 8 == 0; weights packed for the full Cin. */
+MMC_API int mmc_conv_forward_tc2(const mmc_conv_desc *d, const void *x1, int cin1, const void *x2, const void *w_packed,
+                                 const float *bias, const float *beta_eff, const void *gamma_eff_bf16, void *y, void *y2,
+                                 void *stream);
+
 /* Staging for image-edge convolutions on the tensor cores (Cin <= 8): the fp32 NCHW image is copied once
  * into a zero-padded 8-channel NHWC bf16 buffer [B][Hp][Wp][8]; the conv then reads each 5x5 (3x3) window row
  * as one 128-byte TMA box.  mmc_conv_pad8_size gives (Hp, Wp) for a descriptor with in_layout NHWC_PAD8. */

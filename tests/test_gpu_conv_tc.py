@@ -189,3 +189,27 @@ def test_conv_tc_cta_pair_vs_single(transposed, cin, h, w, B, gdn):
     ref = oracle.gdn_forward(ref, gw["g.beta"], gw["g.gamma"], inverse=(gdn == L.GDN_INVERSE))
     y = outs["2"].float().permute(0, 3, 1, 2).cpu().numpy()
     assert np.abs(y - ref).max() < 1e-2 * float(np.abs(ref).max())
+
+
+@pytest.mark.parametrize("kind,c1,c2,cout,k,s,gdn", [
+    ("conv", 192, 192, 192, 5, 1, L.GDN_NONE),       # tran_conv: eg_ext(own) ++ eg_ext(guide)
+    ("conv", 192, 192, 192, 5, 2, L.GDN_FORWARD),    # pic2_g_a_conv2 + GDN on (a ++ fused)
+    ("deconv", 192, 192, 192, 5, 2, L.GDN_INVERSE),  # pic2_g_s_conv2 + IGDN
+    ("deconv", 192, 192, 1, 5, 2, L.GDN_NONE),       # pic2_g_s_conv4: reconstruction layer (GEMM + col2im)
+    ("conv", 384, 384, 640, 1, 1, L.GDN_NONE),       # entropy_parameters.0 on (params ++ ctx)
+    ("conv", 64, 40, 48, 3, 1, L.GDN_NONE),          # ragged second source
+])
+def test_two_source_conv_equals_concatenation(kind, c1, c2, cout, k, s, gdn):
+    """mmc_conv_forward_tc2: channels from two NHWC tensors, bit-identical to the convolution of their torch.cat."""
+    from mmcodec.layers import GDN, conv, deconv
+    from mmcodec.transforms import run_layers
+    torch.manual_seed(c1 + cout)
+    m = (conv if kind == "conv" else deconv)(c1 + c2, cout, kernel_size=k, stride=s).to(dev())
+    layers = [m] + ([GDN(cout, inverse=(gdn == L.GDN_INVERSE)).to(dev())] if gdn != L.GDN_NONE else [])
+    x1 = torch.randn(2, 12, 20, c1, device=dev()).to(torch.bfloat16)
+    x2 = torch.randn(2, 12, 20, c2, device=dev()).to(torch.bfloat16)
+    out_fmt = "nchw_f32" if cout <= 4 else "nhwc_bf16"
+    with torch.no_grad():
+        want = run_layers(layers, torch.cat((x1, x2), dim=-1), "nhwc_bf16", out_fmt)
+        got = run_layers(layers, (x1, x2), "nhwc_bf16", out_fmt)
+    assert torch.equal(got, want)
