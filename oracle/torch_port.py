@@ -355,6 +355,157 @@ def mm_d_forward(sd, x, hidden, noise=None):
     return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "y": y, "y_hat": y_hat, **extra}
 
 
+
+# ---- Master_compresser (RGB-T paper reproduction, compressai/models/master.py) -------------------------------------------
+def _c3(sd, name, x, stride=1):
+    """conv3x3 / conv1x1 (master.py:18-25): padding = k // 2."""
+    w = sd[name + ".weight"]
+    return F.conv2d(x, w, sd[name + ".bias"], stride=stride, padding=w.shape[-1] // 2)
+
+
+def residual_block(sd, name, x):
+    """ResidualBlock.forward (master.py:48-62): LeakyReLU after BOTH convs, optional 1x1 skip."""
+    out = F.leaky_relu(_c3(sd, name + ".conv2", F.leaky_relu(_c3(sd, name + ".conv1", x))))
+    return out + (_c3(sd, name + ".skip", x) if (name + ".skip.weight") in sd else x)
+
+
+def feature_encoder(sd, name, x, stride):
+    """Feature_encoder.forward (master.py:78-89)."""
+    first = _c3(sd, name + ".conv1", x, stride)
+    out = first
+    for i in (1, 2, 3):
+        out = residual_block(sd, f"{name}.resblock{i}", out)
+    return out + first
+
+
+def feature_decoder(sd, name, x, stride):
+    """Feature_decoder.forward (master.py:110-118): 3 residual blocks + 1x1 shortcut, then a k=3 transposed conv."""
+    out = x
+    for i in (1, 2, 3):
+        out = residual_block(sd, f"{name}.resblock{i}", out)
+    out = out + _c3(sd, name + ".conv", x)
+    return deconv(sd, name + ".deconv1", out, stride=stride)
+
+
+def channel_aligner(sd, name, master_feat, guide_feat):
+    """Channel_aligner.forward (master.py:177-210): one shared 4-conv trunk applied to each feature map, conv5 / conv6 heads,
+    global average -> beta (from the master features) and gamma (from the guide features); guide * gamma + beta."""
+    def trunk(t):
+        for i in (1, 2, 3, 4):
+            t = F.leaky_relu(_c3(sd, f"{name}.conv{i}", t))
+        return t
+    beta = _c3(sd, name + ".conv5", trunk(master_feat)).mean(dim=(2, 3), keepdim=True)
+    gamma = _c3(sd, name + ".conv6", trunk(guide_feat)).mean(dim=(2, 3), keepdim=True)
+    return gamma * guide_feat + beta, beta, gamma
+
+
+def _to_windows(t, ws):
+    """window_partition (master.py:431-443) on (B, H, W, C) -> (B * nW, ws * ws, C)."""
+    B, H, W, C = t.shape
+    return t.view(B, H // ws, ws, W // ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws, C)
+
+
+def _from_windows(t, ws, B, H, W):
+    """window_reverse (master.py:446-460)."""
+    return t.view(B, H // ws, W // ws, ws, ws, -1).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, -1)
+
+
+def relative_position_index(ws: int) -> Tensor:
+    """master.py:512-522: index into the (2 ws - 1)^2 bias table for every (query, key) pair of a ws x ws window."""
+    r = torch.arange(ws)
+    ci, cj = torch.meshgrid(r, r, indexing="ij")
+    ci, cj = ci.flatten(), cj.flatten()
+    return (ci[:, None] - ci[None, :] + ws - 1) * (2 * ws - 1) + (cj[:, None] - cj[None, :] + ws - 1)
+
+
+def shift_attention_mask(H: int, W: int, ws: int, shift: int) -> Tensor:
+    """master.py:625-643: 0 / -100 mask between tokens that the cyclic shift brought together from different image regions."""
+    region = torch.zeros(H, W)
+    bands = (slice(0, -ws), slice(-ws, -shift), slice(-shift, None))
+    n = 0
+    for hs in bands:
+        for wsl in bands:
+            region[hs, wsl] = n
+            n += 1
+    m = _to_windows(region.view(1, H, W, 1), ws).squeeze(-1)          # (nW, ws*ws)
+    diff = m[:, None, :] - m[:, :, None]
+    return torch.where(diff != 0, torch.full_like(diff, -100.0), torch.zeros_like(diff))
+
+
+def swin_cross_block(sd, name, x, guide, H, W, ws, shift, heads=3):
+    """SwinTransformerBlock.forward (master.py:652-706) with WindowAttention.forward (master.py:535-568): queries from the
+    master tokens, keys / values from the guide tokens, both normalised by the SAME norm1."""
+    B, L, C = x.shape
+    ln = lambda t, n: F.layer_norm(t, (C,), sd[f"{name}.{n}.weight"], sd[f"{name}.{n}.bias"])
+    lin = lambda t, n: F.linear(t, sd[f"{name}.{n}.weight"], sd[f"{name}.{n}.bias"])
+    if min(H, W) <= ws:                                                # master.py:601-603
+        ws, shift = min(H, W), 0
+    q_src, kv_src = ln(x, "norm1").view(B, H, W, C), ln(guide, "norm1").view(B, H, W, C)
+    if shift:
+        q_src, kv_src = (torch.roll(t, (-shift, -shift), (1, 2)) for t in (q_src, kv_src))
+    qw, kw = _to_windows(q_src, ws), _to_windows(kv_src, ws)
+    nWB, N, hd = qw.shape[0], ws * ws, C // heads
+    q = lin(qw, "attn.qkv1").view(nWB, N, heads, hd).transpose(1, 2) * hd ** -0.5
+    kv = lin(kw, "attn.qkv2").view(nWB, N, 2, heads, hd)
+    k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
+    att = q @ k.transpose(-2, -1)
+    table = sd[f"{name}.attn.relative_position_bias_table"]
+    att = att + table[relative_position_index(ws).view(-1)].view(N, N, heads).permute(2, 0, 1)
+    if shift:
+        att = att.view(B, -1, heads, N, N) + shift_attention_mask(H, W, ws, shift).to(att)[None, :, None]
+        att = att.view(nWB, heads, N, N)
+    o = lin((att.softmax(-1) @ v).transpose(1, 2).reshape(nWB, N, C), "attn.proj")
+    o = _from_windows(o, ws, B, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    x = x + o.reshape(B, L, C)
+    return x + lin(F.gelu(lin(ln(x, "norm2"), "mlp.fc1")), "mlp.fc2")
+
+
+def spatial_aligner(sd, name, x, guide):
+    """Spatial_aligner.forward (master.py:730-742): 2x2 patch embedding of both maps, two cross-attention blocks (window 4,
+    second one shifted by 2), then -- as the reference does -- the (B, L, 96) token tensor is REINTERPRETED (``.view``, no
+    transpose) as (B, 96, H/2, W/2) and a 2x2 stride-2 transposed conv restores the resolution."""
+    B, _, H, W = x.shape
+    emb = lambda n, t: F.conv2d(t, sd[f"{name}.{n}.proj.weight"], sd[f"{name}.{n}.proj.bias"], stride=2).flatten(2).transpose(1, 2)
+    tok, gtok = emb("patch_embeding1", x), emb("patch_embeding2", guide)
+    for i in (0, 1):
+        tok = swin_cross_block(sd, f"{name}.blocks.{i}", tok, gtok, H // 2, W // 2, 4, 0 if i == 0 else 2)
+    grid = tok.contiguous().view(B, tok.shape[-1], H // 2, W // 2)
+    return F.conv_transpose2d(grid, sd[name + ".recovery.weight"], sd[name + ".recovery.bias"], stride=2)
+
+
+def master_decoder(sd, name, y_hat, hidden):
+    """Master_decoder.forward (master.py:776-811)."""
+    g = [hidden["gs1"], hidden["gs2"], hidden["gs3"]]
+    if (name + ".downsample1.weight") in sd:                           # 1-channel master: guide maps are at twice the size
+        g = [conv(sd, f"{name}.downsample{i + 1}", t) for i, t in enumerate(g)]
+    s = y_hat
+    for i in (1, 2, 3):
+        s = gdn(sd, f"{name}.g_s_gdn{i}", deconv(sd, f"{name}.g_s_conv{i}", s), inverse=True)
+        s = torch.cat((spatial_aligner(sd, f"{name}.sp_aligner{i}", s, g[i - 1]), s), dim=1)
+    first_stride = 2                                                   # master.py:900 always builds the decoder with 2
+    return deconv(sd, name + ".g_s_conv4", s, stride=first_stride)
+
+
+def master_forward(sd, x, guided_hat, guided_hidden, noise=None):
+    """Master_compresser.forward (master.py:904-951).  Strides follow the constructor (master.py:840-850): 3-channel master
+    -> (master_stride, guided_stride) = (2, 1); 1-channel master -> (1, 2)."""
+    ms, gs = (2, 1) if x.shape[1] == 3 else (1, 2)
+    xf = feature_encoder(sd, "fencoder1", x, ms)
+    gf = feature_encoder(sd, "fencoder2", guided_hat, gs)
+    aligned, beta, gamma = channel_aligner(sd, "ch_aligner", xf, gf)
+    a = torch.cat((xf, aligned), dim=1)
+    for i in (0, 2, 4):
+        a = gdn(sd, f"g_a.{i + 1}", conv(sd, f"g_a.{i}", a))
+    y = conv(sd, "g_a.6", a)
+    y_hat, y_lik, z_lik, extra = _context_entropy_stage(sd, y, noise)
+    feat_hat = master_decoder(sd, "decoder", y_hat, guided_hidden)
+    x_hat = feature_decoder(sd, "fdecoder", torch.cat((feat_hat, aligned), dim=1), ms)
+    return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}, "y": y, "y_hat": y_hat, "beta": beta, "gamma": gamma,
+            "x_feature": xf, "guided_align": aligned, "x_feature_hat": feat_hat, **extra}
+
+
 def masked_conv_mask(weight_shape, mask_type: str = "A") -> Tensor:
     """MaskedConv2d mask buffer (compressai/layers/layers.py:64-72)."""
     mask = torch.ones(tuple(weight_shape))

@@ -28,7 +28,7 @@ import torch.nn as nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from weights import make_image, make_mm_state_dict, make_ssf_state_dict, make_state_dict  # noqa: E402
+from weights import make_image, make_master_state_dict, make_mm_state_dict, make_ssf_state_dict, make_state_dict  # noqa: E402
 
 REF_SRC = "/root/reference/CompressAI"
 SCRATCH = os.environ.get("MMC_REF_SCRATCH", "/tmp/ref_probe")
@@ -408,6 +408,43 @@ def guided_goldens(out):
         out[f"hidden_{k}"] = t2n(v[:, ::8, ::2, ::2])      # strided subsample of every hidden map
 
 
+def master_goldens(out, verbose=False):
+    """Master_compresser (compressai/models/master.py:837-951) driven by Guided_compresser's reconstruction and hidden maps
+    (the pairing examples/train.py:208-274 uses): 3-channel master at 128x256, 1-channel guide at 64x128, eval forward."""
+    import json
+    from compressai.models.master import Guided_compresser, Master_compresser
+    x = make_image(1, 128, 256, seed=8, C=3)
+    g = make_image(1, 64, 128, seed=9, C=1)
+    torch.manual_seed(0)
+    guide = quiet(Guided_compresser, channel=1).eval()
+    load_into(guide, make_mm_state_dict({k: tuple(v.shape) for k, v in guide.state_dict().items()}, 2))
+    quiet(guide.update, force=True)
+    net = quiet(Master_compresser, width=64, height=128, channel=3).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    load_into(net, make_master_state_dict(shapes, 4))
+    quiet(net.update, force=True)
+    out["state_dict"] = np.array(json.dumps({k: [list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()}))
+    with torch.no_grad():
+        og = quiet(guide, torch.from_numpy(g))
+        # the guide's outputs are rounded to bf16-representable values BEFORE the master sees them, and stored as bf16 bit
+        # patterns: both sides of the parity test then start from identical inputs at half the fixture size
+        hidden = {k: og["hidden"][k].bfloat16().float() for k in ("gs1", "gs2", "gs3")}
+        g_hat = og["x_hat"].bfloat16().float()
+        o = quiet(net, torch.from_numpy(x), g_hat, hidden)
+    out["x"], out["g"], out["x_hat"] = x, g, t2n(o["x_hat"])
+    out["g_hat_bf16"] = t2n(g_hat.bfloat16().view(torch.int16))
+    for k, v in hidden.items():
+        out[f"hidden_{k}_bf16"] = t2n(v.bfloat16().view(torch.int16))
+    for k, v in o["likelihoods"].items():
+        out[f"lik_{k}"] = t2n(v)
+    if verbose:
+        print("x_hat", float(o["x_hat"].min()), float(o["x_hat"].mean()), float(o["x_hat"].max()),
+              "mse", float(((o["x_hat"] - torch.from_numpy(x)) ** 2).mean()))
+        for k, v in o["likelihoods"].items():
+            print(k, "bpp", float(torch.log2(v).sum() / -(128 * 256)), "floor frac", float((v <= 1.0001e-9).float().mean()),
+                  "p>0.99", float((v > 0.99).float().mean()))
+
+
 def color_goldens(out):
     """compressai.transforms.functional on a random frame (the reference's own functions)."""
     from compressai.transforms.functional import rgb2ycbcr, ycbcr2rgb, yuv_420_to_444, yuv_444_to_420
@@ -422,9 +459,9 @@ def color_goldens(out):
 def main():
     import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color", "models_guided"]
+    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color", "models_guided", "models_master"]
     gens = {"kernels": kernel_goldens, "models": model_goldens, "models_mm": mm_goldens, "models_ssf": ssf_goldens, "color": color_goldens,
-            "models_guided": guided_goldens}
+            "models_guided": guided_goldens, "models_master": master_goldens}
     for name in which:
         d = {}
         gens[name](d)

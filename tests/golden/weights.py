@@ -197,3 +197,41 @@ def make_ssf_state_dict(shapes, seed: int = 0):
         sd[f"{hp}.hyper_decoder_scale.deconv3.bias"] += 3.0     # scales are QReLU outputs: keep most of them positive
     sd["img_decoder.6.bias"] = np.full(3, 0.45, dtype=np.float32)
     return sd
+
+
+MASTER_GAINS = {"g_a.6": 5.0, "g_a.": 3.0, "decoder.g_s_conv1": 0.12, "decoder.g_s_conv": 0.5, "decoder.g_s_conv4": 0.6,
+                "decoder.downsample": 1.0, "h_s.4": 2.0, "context_prediction": 0.5, "entropy_parameters": 1.5,
+                "fencoder": 1.2, "fencoder1.resblock": 0.5, "fencoder2.resblock": 0.5, "ch_aligner": 1.3,
+                "fdecoder.resblock": 0.4, "fdecoder.resblock1.conv1": 0.2, "fdecoder.resblock1.skip": 0.2, "fdecoder.conv": 0.2,
+                "fdecoder.deconv1": 0.12}
+
+
+def make_master_state_dict(shapes, seed: int = 0):
+    """Weights for Master_compresser (master.py:837-902): the generic recipe for the conv / GDN / entropy-model tensors plus
+    values for what only this model has -- Linear weights ~ N(0, 1/fan_in), LayerNorm weight 1 +- 0.1, relative-position
+    tables ~ N(0, 0.5^2) (so the window bias and the shift mask matter), 2x2 patch-embedding / recovery kernels."""
+    sd = make_state_dict_like(shapes, seed, MASTER_GAINS)
+    rs = np.random.RandomState(seed + 101)
+    for key in sorted(shapes):
+        shp = tuple(shapes[key])
+        leaf = key.rsplit(".", 1)[-1]
+        if ".norm" in key and leaf == "weight":
+            sd[key] = (1.0 + 0.1 * rs.standard_normal(shp)).astype(np.float32)
+        elif ".norm" in key and leaf == "bias":
+            sd[key] = (0.05 * rs.standard_normal(shp)).astype(np.float32)
+        elif leaf == "relative_position_bias_table":
+            sd[key] = (0.5 * rs.standard_normal(shp)).astype(np.float32)
+        elif leaf == "weight" and len(shp) == 2:
+            g = 2.0 if (".qkv" in key) else 1.0
+            sd[key] = (rs.standard_normal(shp) * (g / np.sqrt(shp[1]))).astype(np.float32)
+        elif "patch_embeding" in key and leaf == "weight":
+            sd[key] = (rs.standard_normal(shp) * (1.0 / np.sqrt(shp[1] * 4))).astype(np.float32)
+        elif key.endswith("recovery.weight"):
+            sd[key] = (rs.standard_normal(shp) * (1.0 / np.sqrt(shp[0]))).astype(np.float32)
+        elif key.endswith("fdecoder.deconv1.weight"):
+            sd[key] = (rs.standard_normal(shp) * (MASTER_GAINS["fdecoder.deconv1"] / np.sqrt(shp[0] * 9 / 4.0))).astype(np.float32)
+    M = shapes["entropy_parameters.4.bias"][0] // 2
+    sd["entropy_parameters.4.bias"][:M] += 2.0
+    sd["entropy_parameters.4.weight"][M:] *= 0.25
+    sd["fdecoder.deconv1.bias"] = np.full(shapes["fdecoder.deconv1.bias"], 0.45, dtype=np.float32)
+    return sd

@@ -269,3 +269,41 @@ def test_torch_port_guided_compresser():
     for k, v in o["hidden"].items():
         ref = g[f"hidden_{k}"]
         assert np.max(np.abs(v[:, ::8, ::2, ::2].numpy() - ref)) < 1e-4 * max(1.0, float(np.abs(ref).max())), k
+
+
+def _master_golden():
+    import json
+    import os
+    from weights import make_master_state_dict
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_master.npz"))
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(g["state_dict"])).items()}
+    sd = {k: torch.from_numpy(v) for k, v in make_master_state_dict(shapes, 4).items()}
+    sd["context_prediction.mask"] = tp.masked_conv_mask(shapes["context_prediction.weight"], "A")
+    bf = lambda a: torch.from_numpy(a).view(torch.bfloat16).float()
+    hidden = {k: bf(g[f"hidden_{k}_bf16"]) for k in ("gs1", "gs2", "gs3")}
+    return g, sd, bf(g["g_hat_bf16"]), hidden
+
+
+def test_torch_port_master_compresser():
+    """Master_compresser (master.py:837-951: Feature_encoder/decoder, Channel_aligner, Spatial_aligner's window
+    cross-attention with the shifted second block, Master_decoder) -- the port reproduces the reference run."""
+    g, sd, g_hat, hidden = _master_golden()
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        o = tp.master_forward(sd, torch.from_numpy(g["x"]), g_hat, hidden)
+    assert np.max(np.abs(o["x_hat"].numpy() - g["x_hat"])) < 2e-4 * max(1.0, float(np.abs(g["x_hat"]).max()))
+    for k, l in o["likelihoods"].items():
+        assert rel_err(l.numpy(), g[f"lik_{k}"], 1e-9) < 1e-3, k
+
+
+def test_master_attention_tables():
+    """The port's closed-form relative-position index and shift mask equal the buffers the reference registers
+    (master.py:512-522, 625-643): checked on the properties those constructions guarantee."""
+    idx = tp.relative_position_index(4)
+    assert idx.shape == (16, 16) and int(idx.min()) == 0 and int(idx.max()) == 48
+    assert torch.equal(torch.diagonal(idx), torch.full((16,), 24))           # zero offset -> centre of the 7x7 table
+    assert torch.equal(idx + idx.t(), torch.full((16, 16), 48))              # offset negation mirrors the index
+    m = tp.shift_attention_mask(8, 16, 4, 2)
+    assert m.shape == (8, 16, 16) and set(m.unique().tolist()) <= {0.0, -100.0}
+    assert torch.equal(m, m.transpose(1, 2)) and float(m[0].abs().sum()) == 0.0   # interior windows are unmasked
+    assert float(m[-1].abs().sum()) > 0                                       # the wrap-around corner window is not
