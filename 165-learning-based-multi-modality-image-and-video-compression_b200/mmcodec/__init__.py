@@ -5,6 +5,7 @@
     mmcodec.entropy_models   EntropyModel, EntropyBottleneck, GaussianConditional
     mmcodec.models           CompressionModel, FactorizedPrior, ScaleHyperprior, MeanScaleHyperprior
     mmcodec.models_mm        JointAutoregressiveHierarchicalPriors_R / _D (RGB + depth two-branch codec), ESA, MaskedConv2d
+    mmcodec.models_master    Master_compresser (RGB-T reproduction: feature codecs, channel aligner, window cross-attention decoder)
     mmcodec.models_video     ScaleSpaceFlow (ssf2020 video codec: keyframe / inter-frame forward, compress, decompress)
     mmcodec.autograd         training path: autograd Functions over the forward / backward kernels
     mmcodec.training         RateDistortionLoss, configure_optimizers, GradBucketReducer (NCCL), TrainStep
@@ -13,7 +14,7 @@
 
 All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
 """
-from . import _lib, entropy_models, graphs, host_pipeline, layers, models, models_mm, models_video, ops, training, transforms, transforms_functional  # noqa: F401
+from . import _lib, entropy_models, graphs, host_pipeline, layers, models, models_master, models_mm, models_video, ops, training, transforms, transforms_functional  # noqa: F401
 from .graphs import GraphedForward  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401
 from ._lib import MmcodecError, build  # noqa: F401
@@ -24,6 +25,7 @@ from .models import (CompressionModel, FactorizedPrior, MeanScaleHyperprior, Sca
 
 from .models_mm import (ESA, Guided_compresser, JointAutoregressiveHierarchicalPriors_D,  # noqa: F401
                         JointAutoregressiveHierarchicalPriors_R, MaskedConv2d)
+from .models_master import Master_compresser  # noqa: F401
 from .models_video import ScaleSpaceFlow  # noqa: F401
 from .training import GradBucketReducer, RateDistortionLoss, TrainStep, configure_optimizers  # noqa: F401
 

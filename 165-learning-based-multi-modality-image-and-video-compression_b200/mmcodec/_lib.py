@@ -70,6 +70,12 @@ _PROTOS = {
     "mmc_gaussian_volume": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_int, c_int, c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "mmc_scale_space_warp": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     "mmc_add": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "mmc_layernorm_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_vp]),
+    "mmc_gelu_bf16": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "mmc_channel_mean_workspace": (c_int, [c_int, c_i64, c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "mmc_channel_mean": (c_int, [c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp]),
+    "mmc_channel_affine_bf16": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp]),
+    "mmc_window_attention": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp]),
     "mmc_color_convert": (c_int, [c_vp, c_i64, c_i64, c_int, c_vp, c_vp]),
     "mmc_avg_pool2": (c_int, [c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_vp]),
     "mmc_upsample2x_bilinear": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_i64, c_vp]),

@@ -511,6 +511,83 @@ def add(a: Tensor, b: Tensor) -> Tensor:
     return out
 
 
+# ---- token-side kernels of the window cross-attention (master.py:484-742) -------------------------------------
+def _bf16c(t: Tensor) -> Tensor:
+    if t.dtype != torch.bfloat16:
+        raise TypeError("expected a bf16 tensor")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def layernorm_bf16(x: Tensor, weight: Tensor, bias: Tensor, eps: float = 1e-5, delta: Optional[Tensor] = None, want_sum: bool = False):
+    """LayerNorm over the last dimension of a bf16 tensor; with ``delta`` computes LayerNorm(x + delta) and, with ``want_sum``,
+    also returns the bf16 sum (the updated residual stream): (sum, normed)."""
+    _require_cuda(x, weight, bias)
+    x = _bf16c(x)
+    C = x.shape[-1]
+    if delta is not None:
+        delta = _bf16c(delta)
+        if delta.shape != x.shape:
+            raise ValueError("layernorm_bf16: delta shape mismatch")
+    y = torch.empty_like(x)
+    s = torch.empty_like(x) if (want_sum and delta is not None) else None
+    with _Timed("layernorm|attn"):
+        L.check(L.lib().mmc_layernorm_bf16(_ptr(x), _ptr(delta), _ptr(_f32c(weight.detach())), _ptr(_f32c(bias.detach())), x.numel() // C, C,
+                                           float(eps), _ptr(s), _ptr(y), _stream()))
+    return (s, y) if want_sum else y
+
+
+def gelu_bf16(x: Tensor) -> Tensor:
+    _require_cuda(x)
+    x = _bf16c(x)
+    y = torch.empty_like(x)
+    with _Timed("gelu|attn"):
+        L.check(L.lib().mmc_gelu_bf16(_ptr(x), x.numel(), _ptr(y), _stream()))
+    return y
+
+
+def window_attention(q: Tensor, kv: Tensor, bias_table: Tensor, window: int, shift: int, heads: int, scale: float) -> Tensor:
+    """Windowed multi-head cross-attention on (B, H, W, C) bf16 token grids (see mmc_window_attention)."""
+    _require_cuda(q, kv, bias_table)
+    q, kv = _bf16c(q), _bf16c(kv)
+    B, H, W, C = q.shape
+    if kv.shape != (B, H, W, 2 * C) or C % heads:
+        raise ValueError("window_attention: kv must be (B, H, W, 2C) and C a multiple of heads")
+    if tuple(bias_table.shape) != ((2 * window - 1) ** 2, heads):
+        raise ValueError("window_attention: bias table must be ((2 ws - 1)^2, heads)")
+    out = torch.empty_like(q)
+    with _Timed("window_attention|attn"):
+        L.check(L.lib().mmc_window_attention(_ptr(q), _ptr(kv), _ptr(_f32c(bias_table.detach())), B, H, W, heads, C // heads, window, shift,
+                                             float(scale), _ptr(out), _stream()))
+    return out
+
+
+def channel_mean(x: Tensor) -> Tensor:
+    """(B, H, W, C) fp32 NHWC -> (B, C) spatial mean (AdaptiveAvgPool2d(1)); per-sample result independent of the batch size."""
+    _require_cuda(x)
+    x = _f32c(x)
+    B, H, W, C = x.shape
+    out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    nbytes = ctypes.c_size_t()
+    L.check(L.lib().mmc_channel_mean_workspace(B, H * W, C, ctypes.byref(nbytes)))
+    ws = torch.empty(max(1, nbytes.value), dtype=torch.uint8, device=x.device)
+    with _Timed("channel_mean|attn"):
+        L.check(L.lib().mmc_channel_mean(_ptr(x), B, H * W, C, _ptr(ws), _ptr(out), _stream()))
+    return out
+
+
+def channel_affine_bf16(x: Tensor, gamma: Tensor, beta: Tensor) -> Tensor:
+    """y = gamma[b, c] * x + beta[b, c] on a (B, H, W, C) bf16 map, gamma / beta (B, C) fp32."""
+    _require_cuda(x, gamma, beta)
+    x = _bf16c(x)
+    B, H, W, C = x.shape
+    if tuple(gamma.shape) != (B, C) or tuple(beta.shape) != (B, C):
+        raise ValueError("channel_affine_bf16: gamma / beta must be (B, C)")
+    y = torch.empty_like(x)
+    with _Timed("channel_affine|attn"):
+        L.check(L.lib().mmc_channel_affine_bf16(_ptr(x), _ptr(_f32c(gamma)), _ptr(_f32c(beta)), B, H * W, C, _ptr(y), _stream()))
+    return y
+
+
 # ---- backward of the transforms ------------------------------------------------------------------------
 def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.0, mask: Optional[Tensor] = None,
           name: str = "conv") -> Tensor:

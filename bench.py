@@ -61,6 +61,8 @@ OTHER_WORKLOADS = {
                  "(BASELINE.json configs[3]); unit = pairs"),
     "mm-forward": ("RGB + depth two-branch codec (JointAutoregressiveHierarchicalPriors_R/_D) eval forward, 768x512 pairs "
                    "(forward half of BASELINE.json configs[3]); unit = pairs"),
+    "master-forward": ("RGB-T reproduction (Guided_compresser on the 1x256x384 guide + Master_compresser on the 3x512x768 master: feature "
+                       "codecs, channel aligner, three window cross-attention stages) eval forward; unit = pairs"),
 }
 ARCH, QUALITY, H, W = "bmshj2018-hyperprior", 4, 512, 768
 WORKLOAD = WORKLOADS["hyperprior"][6]
@@ -202,6 +204,19 @@ def bench_other(args):
             with torch.enable_grad():
                 return trainer(xs[1], xs[0])
         e2e_out = lambda o: [o["loss"].cpu()]
+    elif args.workload == "master-forward":
+        guide = mmcodec.Guided_compresser(channel=1).eval()
+        master = mmcodec.Master_compresser(width=256, height=384, channel=3).eval()
+        for n in (guide, master):
+            n.update()
+            n.to(dev)
+        units = args.batch or 8
+        host = [torch.rand(units, 3, 512, 768, generator=gen).pin_memory(), torch.rand(units, 1, 256, 384, generator=gen).pin_memory()]
+
+        def run(xs):
+            og = guide(xs[1])
+            return {"g": og, "m": master(xs[0], og["x_hat"], og["hidden"])}
+        e2e_out = lambda o: [o["g"]["x_hat"].cpu(), o["m"]["x_hat"].cpu()]
     else:
         net_r = mmcodec.JointAutoregressiveHierarchicalPriors_R(192, 192).eval()
         net_d = mmcodec.JointAutoregressiveHierarchicalPriors_D(192, 192).eval()

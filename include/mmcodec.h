@@ -289,6 +289,31 @@ MMC_API int mmc_upsample2x_bilinear(const float *x, int64_t planes, int H, int W
 MMC_API int mmc_add(const float *a, const float *b, int64_t n, float *out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Token-side kernels of Spatial_aligner's window cross-attention (compressai/models/master.py:484-742).  The block's
+ * Linear layers are per-token and run as 1x1 mmc_conv_forward_tc calls on the (B, H, W, C) bf16 token grid; these are the rest.
+ *
+ * mmc_layernorm_bf16: y = LayerNorm(x [+ delta]) over the last dimension (nn.LayerNorm(dim), master.py:606,613; biased
+ *   variance, fp32 statistics, fp32 affine).  With `delta` the residual add in front of the norm is fused (master.py:699) and,
+ *   if `sum_out` is given, the bf16 sum is written too.  rows x C bf16 in / out, C <= 256.
+ * mmc_gelu_bf16: nn.GELU() (erf form, master.py:464) on n bf16 values (n even).
+ * mmc_window_attention: softmax(scale * Q K^T + relative-position bias [+ shift mask]) V inside ws x ws windows of the token
+ *   grid cyclically shifted by `shift` (WindowAttention.forward master.py:535-568 inside SwinTransformerBlock.forward
+ *   master.py:652-697: roll, window_partition, attention, window_reverse, roll back -- all as index arithmetic).
+ *   q: (B, H, W, heads*head_dim) bf16; kv: (B, H, W, 2*heads*head_dim) bf16, keys then values (qkv2's output layout);
+ *   bias_table: ((2 ws - 1)^2, heads) fp32 = relative_position_bias_table; out like q.  head_dim must be 32, ws <= 4. */
+/* Channel_aligner tail (master.py:193-210): out[b][c] = mean over the HW positions of an fp32 NHWC map (AdaptiveAvgPool2d(1);
+ * two passes over row splits, fixed summation order per sample, independent of B; `workspace` of
+ * mmc_channel_mean_workspace bytes), and y = gamma[b][c] * x + beta[b][c] on a bf16 NHWC map. */
+MMC_API int mmc_channel_mean_workspace(int B, int64_t HW, int C, size_t *bytes);
+MMC_API int mmc_channel_mean(const float *x, int B, int64_t HW, int C, void *workspace, float *out, void *stream);
+MMC_API int mmc_channel_affine_bf16(const void *x, const float *gamma, const float *beta, int B, int64_t HW, int C, void *y, void *stream);
+MMC_API int mmc_layernorm_bf16(const void *x, const void *delta, const float *weight, const float *bias, int64_t rows, int C, float eps,
+                               void *sum_out, void *y, void *stream);
+MMC_API int mmc_gelu_bf16(const void *x, int64_t n, void *y, void *stream);
+MMC_API int mmc_window_attention(const void *q, const void *kv, const float *bias_table, int B, int H, int W, int heads, int head_dim,
+                                 int window, int shift, float scale, void *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Backward of the transforms (training step, examples/train.py:239-253): weight gradient on tensor cores.
  * The input gradient of conv() is deconv() with the same weight tensor and vice versa, i.e. mmc_conv_forward_tc with the
  * adjoint descriptor -- no separate entry point.
