@@ -27,6 +27,6 @@ from .models_mm import (ESA, Guided_compresser, JointAutoregressiveHierarchicalP
                         JointAutoregressiveHierarchicalPriors_R, MaskedConv2d)
 from .models_master import Master_compresser  # noqa: F401
 from .models_video import ScaleSpaceFlow  # noqa: F401
-from .training import GradBucketReducer, RateDistortionLoss, TrainStep, configure_optimizers  # noqa: F401
+from .training import GradBucketReducer, GraphedTrainStep, RateDistortionLoss, TrainStep, configure_optimizers  # noqa: F401
 
 __version__ = "0.1.0"

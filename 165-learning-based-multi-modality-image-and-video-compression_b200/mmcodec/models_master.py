@@ -449,6 +449,8 @@ class Master_compresser(_ContextModelMixin, MeanScaleHyperprior):
     """master.py:837-951.  ``width`` / ``height`` are the first / second spatial size of the GUIDE image (= half the 3-channel
     master image); ``channel`` is the master image's channel count (3: RGB master + 1-channel guide, 1: the reverse)."""
 
+    forward_takes_guide_image = True      # TrainStep: net(x, guided, hidden) as in examples/train.py:224
+
     def __init__(self, width=256, height=256, channel=3, N=192, M=192) -> None:
         super().__init__(M, M)
         master_chl, guided_chl, master_stride, guided_stride = (3, 1, 2, 1) if channel != 1 else (1, 3, 1, 2)

@@ -7,8 +7,9 @@ attribute names and ``state_dict`` keys.
 Every conv / deconv (+GDN / IGDN / ReLU / LeakyReLU), the masked context convolution, the 1x1 entropy-parameter
 convs and the entropy stage run on the libmmcodec kernels with NHWC bf16 activations; channel concatenations are
 views-plus-one-copy on the NHWC tensors.  The ESA gate (1x1 -> 3x3 s2 p0 -> maxpool 7/3 -> 3x3 x3 -> bilinear
-upsample -> 1x1 -> sigmoid, google.py:1432-1459) is SURVEY.md section 8f row 3 and still runs on torch ops (bf16,
-channels-last, no layout copies).  ``forward`` is implemented for eval and for the training-mode forward pass
+upsample -> 1x1 -> sigmoid, google.py:1432-1459) runs entirely in libmmcodec in inference (convs on
+the tensor-core kernel, pool / upsample+add / gate in csrc/esa.cu); under autograd it runs on torch ops (bf16, channels-last).
+``forward`` is implemented for eval and for the training-mode forward pass
 (uniform-noise quantisation); the autoregressive ``compress`` / ``decompress`` (google.py:836-1003, a serial
 per-pixel Python loop in the reference) are out of scope and raise.
 """
@@ -64,8 +65,9 @@ class ESA(nn.Module):
     """Enhanced spatial attention gate (google.py:1432-1459).
 
     Every convolution (1x1 conv1 / conv_f / conv4, 3x3 conv_max / conv3 / conv3_, and the stride-2 3x3 conv2) runs on the
-    tensor-core conv kernel with NHWC bf16 activations, forward and backward; the max-pool (7 / 3), the bilinear upsampling, the
-    add and the sigmoid gate are torch elementwise / pooling ops on the same bf16 channels-last tensors.  conv2 has padding 0,
+    tensor-core conv kernel with NHWC bf16 activations, forward and backward; in inference the max-pool (7 / 3), the bilinear
+    upsampling fused with the add, and the sigmoid gate are single libmmcodec passes (csrc/esa.cu); under autograd they are torch
+    elementwise / pooling ops on the same bf16 channels-last tensors.  conv2 has padding 0,
     which the kernel's padding-k/2 addressing expresses exactly as the padding-1 convolution of the map shifted by one pixel:
     conv_p0(x)[o] = conv_p1(pad_top_left(x))[o + 1]."""
 
@@ -122,12 +124,19 @@ class ESA(nn.Module):
         c1_ = run_layers([self.conv1], x, "nhwc_bf16", "nhwc_bf16")
         ho, wo = (H - 3) // 2 + 1, (W - 3) // 2 + 1
         c1 = run_layers([self._conv2_p1()], F.pad(c1_, (0, 0, 1, 0, 1, 0)), "nhwc_bf16", "nhwc_bf16")[:, 1:1 + ho, 1:1 + wo]
-        v_max = F.max_pool2d(c1.permute(0, 3, 1, 2), kernel_size=7, stride=3).permute(0, 2, 3, 1).contiguous()
+        if needs_grad:
+            v_max = F.max_pool2d(c1.permute(0, 3, 1, 2), kernel_size=7, stride=3).permute(0, 2, 3, 1).contiguous()
+            c3 = run_layers([self.conv_max, self.relu, self.conv3, self.relu, self.conv3_], v_max, "nhwc_bf16", "nhwc_bf16")
+            c3 = F.interpolate(c3.permute(0, 3, 1, 2), (H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+            cf = run_layers([self.conv_f], c1_, "nhwc_bf16", "nhwc_bf16")
+            c4 = run_layers([self.conv4], (c3 + cf).contiguous(), "nhwc_bf16", "nhwc_bf16")
+            return x * torch.sigmoid(c4)
+        # inference: pool, upsample + add and the gate are single libmmcodec passes (csrc/esa.cu)
+        v_max = ops.maxpool_nhwc_bf16(c1, 7, 3)
         c3 = run_layers([self.conv_max, self.relu, self.conv3, self.relu, self.conv3_], v_max, "nhwc_bf16", "nhwc_bf16")
-        c3 = F.interpolate(c3.permute(0, 3, 1, 2), (H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
         cf = run_layers([self.conv_f], c1_, "nhwc_bf16", "nhwc_bf16")
-        c4 = run_layers([self.conv4], (c3 + cf).contiguous(), "nhwc_bf16", "nhwc_bf16")
-        return x * torch.sigmoid(c4)
+        c4 = run_layers([self.conv4], ops.upsample_bilinear_add_bf16(c3, cf), "nhwc_bf16", "nhwc_bf16")
+        return ops.sigmoid_gate_bf16(x, c4)
 
     def forward(self, x: Tensor) -> Tensor:
         """(B, C, H, W) fp32 in / out, as the reference's module."""

@@ -588,6 +588,43 @@ def channel_affine_bf16(x: Tensor, gamma: Tensor, beta: Tensor) -> Tensor:
     return y
 
 
+# ---- non-convolution steps of the ESA gate (google.py:1445-1459) ------------------------------------------------
+def maxpool_nhwc_bf16(x: Tensor, k: int, stride: int) -> Tensor:
+    _require_cuda(x)
+    x = _bf16c(x)
+    B, H, W, C = x.shape
+    if H < k or W < k:
+        raise ValueError(f"max-pool window {k} does not fit the {H}x{W} map")
+    y = torch.empty((B, (H - k) // stride + 1, (W - k) // stride + 1, C), dtype=torch.bfloat16, device=x.device)
+    with _Timed("maxpool|esa"):
+        L.check(L.lib().mmc_maxpool_nhwc_bf16(_ptr(x), B, H, W, C, k, stride, _ptr(y), _stream()))
+    return y
+
+
+def upsample_bilinear_add_bf16(small: Tensor, add: Tensor) -> Tensor:
+    """F.interpolate(small, add's size, mode="bilinear", align_corners=False) + add, NHWC bf16."""
+    _require_cuda(small, add)
+    small, add = _bf16c(small), _bf16c(add)
+    B, hs, ws, C = small.shape
+    if add.shape[0] != B or add.shape[3] != C:
+        raise ValueError("upsample_bilinear_add_bf16: batch / channel mismatch")
+    y = torch.empty_like(add)
+    with _Timed("upsample_add|esa"):
+        L.check(L.lib().mmc_upsample_bilinear_add_bf16(_ptr(small), B, hs, ws, C, _ptr(add), add.shape[1], add.shape[2], _ptr(y), _stream()))
+    return y
+
+
+def sigmoid_gate_bf16(x: Tensor, gate: Tensor) -> Tensor:
+    _require_cuda(x, gate)
+    x, gate = _bf16c(x), _bf16c(gate)
+    if x.shape != gate.shape:
+        raise ValueError("sigmoid_gate_bf16: shape mismatch")
+    y = torch.empty_like(x)
+    with _Timed("sigmoid_gate|esa"):
+        L.check(L.lib().mmc_sigmoid_gate_bf16(_ptr(x), _ptr(gate), x.numel(), _ptr(y), _stream()))
+    return y
+
+
 # ---- backward of the transforms ------------------------------------------------------------------------
 def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.0, mask: Optional[Tensor] = None,
           name: str = "conv") -> Tensor:

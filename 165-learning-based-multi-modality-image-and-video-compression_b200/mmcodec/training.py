@@ -18,7 +18,7 @@ import torch.distributed as dist
 import torch.nn as nn
 from torch import Tensor
 
-__all__ = ["RateDistortionLoss", "configure_optimizers", "GradBucketReducer", "TrainStep"]
+__all__ = ["RateDistortionLoss", "configure_optimizers", "GradBucketReducer", "TrainStep", "GraphedTrainStep"]
 
 
 class RateDistortionLoss(nn.Module):
@@ -40,14 +40,16 @@ class RateDistortionLoss(nn.Module):
         return out
 
 
-def configure_optimizers(net: nn.Module, learning_rate: float = 1e-4, aux_learning_rate: float = 1e-3):
-    """examples/train.py:111-142: Adam on everything but the EntropyBottleneck quantiles, a second Adam on those."""
+def configure_optimizers(net: nn.Module, learning_rate: float = 1e-4, aux_learning_rate: float = 1e-3, capturable: bool = False):
+    """examples/train.py:111-142: Adam on everything but the EntropyBottleneck quantiles, a second Adam on those.
+    ``capturable``: keep the step counters on the device so that ``step()`` can be recorded in a CUDA graph."""
     params = dict(net.named_parameters())
     main = sorted(n for n, p in params.items() if not n.endswith(".quantiles") and p.requires_grad)
     aux = sorted(n for n, p in params.items() if n.endswith(".quantiles") and p.requires_grad)
     assert not set(main) & set(aux) and len(main) + len(aux) == sum(p.requires_grad for p in params.values())
-    return (torch.optim.Adam((params[n] for n in main), lr=learning_rate),
-            torch.optim.Adam((params[n] for n in aux), lr=aux_learning_rate))
+    extra = {"capturable": True} if capturable else {}
+    return (torch.optim.Adam((params[n] for n in main), lr=learning_rate, **extra),
+            torch.optim.Adam((params[n] for n in aux), lr=aux_learning_rate, **extra))
 
 
 class GradBucketReducer:
@@ -127,13 +129,16 @@ class GradBucketReducer:
 
 class TrainStep:
     """One optimisation step of the second-modality branch with a frozen guide branch (examples/train.py:216-253):
-    hidden = guide(rgb) under no_grad; out = net(x, hidden); loss.backward(); clip; Adam; aux loss; aux Adam."""
+    hidden = guide(rgb) under no_grad; out = net(x, hidden); loss.backward(); clip; Adam; aux loss; aux Adam.
+    A net whose ``forward_takes_guide_image`` is set (Master_compresser) is called as net(x, guided, hidden), the pairing of
+    train_one_epoch_master (examples/train.py:208-233)."""
 
     def __init__(self, net: nn.Module, guide: Optional[nn.Module], quality: int = 3, learning_rate: float = 1e-4,
-                 aux_learning_rate: float = 1e-3, clip_max_norm: float = 1.0, bucket_bytes: int = 32 << 20, group=None):
+                 aux_learning_rate: float = 1e-3, clip_max_norm: float = 1.0, bucket_bytes: int = 32 << 20, group=None,
+                 capturable: bool = False):
         self.net, self.guide = net, guide
         self.criterion = RateDistortionLoss(quality)
-        self.optimizer, self.aux_optimizer = configure_optimizers(net, learning_rate, aux_learning_rate)
+        self.optimizer, self.aux_optimizer = configure_optimizers(net, learning_rate, aux_learning_rate, capturable)
         self.clip_max_norm = clip_max_norm
         self.reducer = GradBucketReducer(net.parameters(), bucket_bytes, group)
 
@@ -145,7 +150,10 @@ class TrainStep:
                 hidden = self.guide(guided)["hidden"]
         self.optimizer.zero_grad(set_to_none=True)
         self.aux_optimizer.zero_grad(set_to_none=True)
-        out_net = self.net(x, hidden) if hidden is not None else self.net(x)
+        if hidden is not None and getattr(self.net, "forward_takes_guide_image", False):
+            out_net = self.net(x, guided, hidden)
+        else:
+            out_net = self.net(x, hidden) if hidden is not None else self.net(x)
         out = self.criterion(out_net, x)
         out["loss"].backward()
         aux_loss = self.net.aux_loss()
@@ -157,3 +165,53 @@ class TrainStep:
         self.aux_optimizer.step()
         out["aux_loss"] = aux_loss.detach()
         return {k: v.detach() for k, v in out.items()}
+
+
+class GraphedTrainStep:
+    """``TrainStep`` replayed as ONE CUDA graph.
+
+    The training step of the fusion models is a few hundred small launches (forward, dgrad / wgrad per layer, the attention
+    blocks' elementwise ops, bucket flattening, clipping, two Adam updates): on a B200 the device finishes them faster than
+    Python can issue them.  The first ``warmup`` calls run eagerly (real optimisation steps; they also fill every per-shape
+    cache); the next call records one whole step -- guide forward, forward, loss, backward, NCCL bucket all-reduces on the side
+    stream, clipping, both Adam updates (``capturable=True``) -- under ``torch.cuda.graph`` and every call from then on copies
+    its batch into the captured input buffers and launches the graph.  Everything that depends on the parameters (bf16 weight
+    packs, GDN re-parametrisations) is recomputed INSIDE the graph, because the optimizer step of the previous replay changed
+    them; after each replay the parameters' version counters are bumped so that caches used by later eager calls are rebuilt.
+
+    Inputs must keep their shape and dtype.  The returned tensors are the captured outputs (overwritten by the next call)."""
+
+    def __init__(self, net: nn.Module, guide: Optional[nn.Module], warmup: int = 3, **kwargs):
+        self.step = TrainStep(net, guide, capturable=True, **kwargs)
+        self.warmup = max(1, warmup)
+        self.calls = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def _copy_in(self, x: Tensor, guided: Optional[Tensor]):
+        for dst, src in ((self._x, x), (self._g, guided)):
+            if dst is None:
+                continue
+            if src is None or dst.shape != src.shape or dst.dtype != src.dtype:
+                raise ValueError("GraphedTrainStep: input shape / dtype differs from the captured one")
+            dst.copy_(src, non_blocking=True)
+
+    def __call__(self, x: Tensor, guided: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        if not x.is_cuda:
+            raise RuntimeError("GraphedTrainStep captures CUDA work only (there is no CPU path)")
+        self.calls += 1
+        if self.graph is None and self.calls <= self.warmup:
+            with torch.enable_grad():
+                return self.step(x, guided)
+        if self.graph is None:
+            self._x, self._g = x.clone(), (guided.clone() if guided is not None else None)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph), torch.enable_grad():
+                self._out = self.step(self._x, self._g)
+        else:
+            self._copy_in(x, guided)
+        self.graph.replay()
+        for p in self.step.net.parameters():
+            if p.grad is not None:
+                torch.autograd.graph.increment_version(p)
+        return self._out

@@ -61,6 +61,9 @@ OTHER_WORKLOADS = {
                  "(BASELINE.json configs[3]); unit = pairs"),
     "mm-forward": ("RGB + depth two-branch codec (JointAutoregressiveHierarchicalPriors_R/_D) eval forward, 768x512 pairs "
                    "(forward half of BASELINE.json configs[3]); unit = pairs"),
+    "master-train": ("RGB-T reproduction training step (frozen Guided_compresser forward on the 1x256x384 guide, Master_compresser forward + "
+                     "backward on the 3x512x768 master, bucketed NCCL gradient all-reduce, grad clip, Adam + aux Adam; examples/train.py:208-233); "
+                     "unit = pairs"),
     "master-forward": ("RGB-T reproduction (Guided_compresser on the 1x256x384 guide + Master_compresser on the 3x512x768 master: feature "
                        "codecs, channel aligner, three window cross-attention stages) eval forward; unit = pairs"),
 }
@@ -204,6 +207,20 @@ def bench_other(args):
             with torch.enable_grad():
                 return trainer(xs[1], xs[0])
         e2e_out = lambda o: [o["loss"].cpu()]
+    elif args.workload == "master-train":
+        guide = mmcodec.Guided_compresser(channel=1).eval()
+        master = mmcodec.Master_compresser(width=256, height=384, channel=3)
+        for n in (guide, master):
+            n.update()
+            n.to(dev)
+        units = args.batch or 4
+        host = [torch.rand(units, 3, 512, 768, generator=gen).pin_memory(), torch.rand(units, 1, 256, 384, generator=gen).pin_memory()]
+        trainer = mmcodec.TrainStep(master, guide, quality=3)
+
+        def run(xs):
+            with torch.enable_grad():
+                return trainer(xs[0], xs[1])
+        e2e_out = lambda o: [o["loss"].cpu()]
     elif args.workload == "master-forward":
         guide = mmcodec.Guided_compresser(channel=1).eval()
         master = mmcodec.Master_compresser(width=256, height=384, channel=3).eval()
@@ -257,8 +274,27 @@ def bench_other(args):
         ops.start_profile()
         run(xs)
         prof = ops.stop_profile(with_work="total")
-        if args.workload == "mm-train":
-            ms_graph = ms          # optimizer state and collectives: not captured, eager launches are the product path
+        graph_error = None
+        if args.workload in ("mm-train", "master-train"):
+            # the whole optimisation step (forward, backward, bucket all-reduces, clip, Adam x2) replayed as ONE CUDA graph
+            ms_graph = ms
+            try:
+                trainer.reducer.remove()
+                g_net, g_guide = trainer.net, trainer.guide
+                graphed = mmcodec.GraphedTrainStep(g_net, g_guide, warmup=2, quality=3)
+                run_g = (lambda xs: graphed(xs[1], xs[0])) if args.workload == "mm-train" else (lambda xs: graphed(xs[0], xs[1]))
+                for _ in range(4):
+                    run_g(xs)
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(args.steps):
+                    run_g(xs)
+                g1.record()
+                barrier()
+                ms_graph = g0.elapsed_time(g1)
+            except Exception as e:   # keep the eager number, say why
+                graph_error = f"{type(e).__name__}: {e}"[:300]
         else:
             # launch-bound workloads: the same forward replayed as ONE CUDA graph (mmcodec.GraphedForward)
             graphed = mmcodec.GraphedForward(run, xs)
@@ -283,11 +319,11 @@ def bench_other(args):
     top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]
     print(json.dumps({"metric": f"{'frames' if args.workload == 'ssf2020' else 'pairs'}/s ({args.workload})", "value": units * world * args.steps / (ms * 1e-3),
                       "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-                      "launch_mode": "eager launches" if args.workload == "mm-train" else "one CUDA graph per step (mmcodec.GraphedForward)", "ms_per_step_eager": ms_eager / args.steps,
+                      "launch_mode": ("eager launches (graph capture failed: " + graph_error + ")") if graph_error else ("one CUDA graph per optimisation step (mmcodec.GraphedTrainStep)" if args.workload in ("mm-train", "master-train") else "one CUDA graph per step (mmcodec.GraphedForward)"), "ms_per_step_eager": ms_eager / args.steps,
                       "sum_of_kernel_ms": kernel_ms,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                       "config": {"workload": OTHER_WORKLOADS[args.workload], "units_per_gpu": units, "weights": "random init",
-                                 "parallelism": f"data parallel x{world}" + (", bucketed NCCL all-reduce of fp32 gradients" if args.workload == "mm-train" else ", no collective")},
+                                 "parallelism": f"data parallel x{world}" + (", bucketed NCCL all-reduce of fp32 gradients" if args.workload in ("mm-train", "master-train") else ", no collective")},
                       "gpu_launches": launches,
                       "e2e": {"value": units * world * args.steps / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
                               "h2d_bytes_per_step": sum(t_.numel() * 4 for t_ in host), "d2h_bytes_per_step": sum(t_.numel() * 4 for t_ in host)},

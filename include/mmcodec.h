@@ -301,6 +301,15 @@ MMC_API int mmc_add(const float *a, const float *b, int64_t n, float *out, void 
  *   master.py:652-697: roll, window_partition, attention, window_reverse, roll back -- all as index arithmetic).
  *   q: (B, H, W, heads*head_dim) bf16; kv: (B, H, W, 2*heads*head_dim) bf16, keys then values (qkv2's output layout);
  *   bias_table: ((2 ws - 1)^2, heads) fp32 = relative_position_bias_table; out like q.  head_dim must be 32, ws <= 4. */
+/* ---------------------------------------------------------------------------------------------
+ * Non-convolution steps of the ESA gate (ESA.forward, models/google.py:1445-1459) on NHWC bf16 maps.
+ * mmc_maxpool_nhwc_bf16: F.max_pool2d(kernel_size=k, stride=stride), no padding; y is (B, (H-k)/stride+1, (W-k)/stride+1, C).
+ * mmc_upsample_bilinear_add_bf16: F.interpolate(small, (H, W), mode="bilinear", align_corners=False) + add  (c3 + cf).
+ * mmc_sigmoid_gate_bf16: y = x * sigmoid(gate)  (the `x * m` of google.py:1458-1459), n elements. */
+MMC_API int mmc_maxpool_nhwc_bf16(const void *x, int B, int H, int W, int C, int k, int stride, void *y, void *stream);
+MMC_API int mmc_upsample_bilinear_add_bf16(const void *small, int B, int hs, int ws, int C, const void *add, int H, int W, void *y, void *stream);
+MMC_API int mmc_sigmoid_gate_bf16(const void *x, const void *gate, int64_t n, void *y, void *stream);
+
 /* Channel_aligner tail (master.py:193-210): out[b][c] = mean over the HW positions of an fp32 NHWC map (AdaptiveAvgPool2d(1);
  * two passes over row splits, fixed summation order per sample, independent of B; `workspace` of
  * mmc_channel_mean_workspace bytes), and y = gamma[b][c] * x + beta[b][c] on a bf16 NHWC map. */

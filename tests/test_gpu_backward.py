@@ -1,5 +1,7 @@
 """GPU parity tests of the backward (training) kernels against torch CPU autograd of the oracle's ops in float64.
 Operands are rounded to bf16 first, so the comparison isolates accumulation order: rel-RMS <= 2e-3."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -326,3 +328,59 @@ def test_zoo_models_training_step_vs_oracle(arch, cls, N, M):
     net._noise_override = None
     res = mmcodec.TrainStep(net, None, quality=3)(x.to(dev()))
     assert all(bool(torch.isfinite(v).all()) for v in res.values())
+
+
+@pytest.mark.parametrize("family", ["mean-scale", "master"])
+def test_graphed_train_step_matches_eager(family):
+    """mmcodec.GraphedTrainStep (whole optimisation step as one CUDA graph, parameter-dependent caches rebuilt inside the graph)
+    follows the eager TrainStep: same initial weights, same batches, same noise draws -> same loss trajectory and parameters
+    (up to the fp32 summation order of the split-K weight-gradient atomics), and the loss goes down."""
+    import copy
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(21)
+    if family == "mean-scale":
+        net_a = mmcodec.MeanScaleHyperprior(128, 192)
+        guide = None
+        xs = [torch.rand(2, 3, 128, 192, generator=gen).to(dev()) for _ in range(3)]
+        gs = [None] * 3
+        noise = {"y": torch.rand(2, 192, 8, 12, generator=gen) - 0.5, "z": torch.rand(2, 128, 2, 3, generator=gen) - 0.5}
+        watch = ["g_a.0.weight", "g_s.6.weight", "h_s.2.bias", "g_a.1.gamma"]
+    else:
+        net_a = mmcodec.Master_compresser(width=64, height=128, channel=3)
+        guide = mmcodec.Guided_compresser(channel=1).eval()
+        guide.update()
+        guide.to(dev())
+        xs = [torch.rand(1, 3, 128, 256, generator=gen).to(dev()) for _ in range(3)]
+        gs = [torch.rand(1, 1, 64, 128, generator=gen).to(dev()) for _ in range(3)]
+        noise = {"z": torch.rand(1, 192, 1, 2, generator=gen) - 0.5, "y_hat": torch.rand(1, 192, 4, 8, generator=gen) - 0.5,
+                 "y": torch.rand(1, 192, 4, 8, generator=gen) - 0.5}
+        watch = ["fencoder1.conv1.weight", "decoder.sp_aligner2.blocks.1.attn.qkv2.weight", "ch_aligner.conv3.weight", "g_a.1.gamma"]
+    net_a.update()
+    net_a.to(dev())
+    net_b = copy.deepcopy(net_a)
+    noise = {k: v.to(dev()) for k, v in noise.items()}     # device-resident: a host-to-device copy cannot be captured
+    for n in (net_a, net_b):
+        n._noise_override = noise
+    eager = mmcodec.TrainStep(net_a, guide, quality=3)
+    graphed = mmcodec.GraphedTrainStep(net_b, guide, warmup=2, quality=3)
+    la, lb = [], []
+    for i in range(9):                                  # calls 1-2 eager warm-up, call 3 captures, calls 4-9 replay
+        x, g_ = xs[i % 3], gs[i % 3]
+        la.append(float(eager(x, g_)["loss"]))
+        lb.append(float(graphed(x, g_)["loss"]))
+    assert graphed.graph is not None and graphed.calls == 9
+    assert all(math.isfinite(v) for v in la + lb)
+    assert all(abs(a - b) / abs(a) < 2e-2 for a, b in zip(la, lb)), (la, lb)
+    assert lb[-1] < lb[0] and lb[-2] < lb[1] and lb[-3] < lb[2]     # same batch three rounds later: the steps did optimise
+    pa, pb = dict(net_a.named_parameters()), dict(net_b.named_parameters())
+    for name in watch:
+        d = float((pa[name].detach() - pb[name].detach()).abs().max())
+        step_size = 9 * 1e-4                               # Adam moves a weight by at most ~lr per step
+        assert d < 0.25 * step_size, (name, d)
+    # eager inference after graphed training sees the CURRENT weights (version counters were bumped after every replay)
+    net_b.eval()
+    net_a.eval()
+    with torch.no_grad():
+        oa = net_a(xs[0], gs[0], guide(gs[0])["hidden"]) if guide is not None else net_a(xs[0])
+        ob = net_b(xs[0], gs[0], guide(gs[0])["hidden"]) if guide is not None else net_b(xs[0])
+    assert float((oa["x_hat"].float() - ob["x_hat"].float()).abs().max()) < 0.05 * float(oa["x_hat"].float().abs().max()) + 1e-3

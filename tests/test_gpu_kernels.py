@@ -430,3 +430,35 @@ def test_colour_transforms_vs_reference_golden():
         TF.yuv_444_to_420(cu(g["ycbcr"]), mode="nearest")
     with pytest.raises(NotImplementedError):
         TF.yuv_420_to_444((y, u, v), mode="bicubic")
+
+
+def test_esa_glue_kernels_vs_torch():
+    """csrc/esa.cu against the torch ops of ESA.forward (google.py:1449-1459) on the same bf16 maps: max_pool2d(7, 3) is exact;
+    bilinear upsample + add and the sigmoid gate are computed in fp32 and rounded once."""
+    import torch.nn.functional as F
+    from mmcodec import ops
+    gen = torch.Generator().manual_seed(12)
+    dev = torch.device("cuda", 0)
+    for (B, H, W, C) in ((2, 31, 47, 48), (1, 7, 7, 2), (3, 64, 96, 48)):
+        x = torch.randn(B, H, W, C, generator=gen).to(dev).bfloat16()
+        ref = F.max_pool2d(x.permute(0, 3, 1, 2).float(), kernel_size=7, stride=3).permute(0, 2, 3, 1)
+        out = ops.maxpool_nhwc_bf16(x, 7, 3)
+        assert tuple(out.shape) == tuple(ref.shape) and torch.equal(out.float(), ref)
+    xs = torch.randn(1, 9, 9, 4, generator=gen).to(dev).bfloat16()
+    xs[0, 3, 3, 1] = float("nan")
+    assert bool(torch.isnan(ops.maxpool_nhwc_bf16(xs, 7, 3)[0, 0, 0, 1])) and not bool(torch.isnan(ops.maxpool_nhwc_bf16(xs, 7, 3)[0, 0, 0, 0]))
+    with pytest.raises((ValueError, mmcodec.MmcodecError)):
+        ops.maxpool_nhwc_bf16(torch.zeros(1, 5, 9, 4, device=dev, dtype=torch.bfloat16), 7, 3)
+    for (B, hs, ws, H, W, C) in ((2, 5, 8, 64, 96, 48), (1, 1, 1, 16, 16, 48), (1, 13, 20, 128, 192, 48), (1, 4, 4, 9, 11, 6)):
+        small = torch.randn(B, hs, ws, C, generator=gen).to(dev).bfloat16()
+        add = torch.randn(B, H, W, C, generator=gen).to(dev).bfloat16()
+        ref = F.interpolate(small.permute(0, 3, 1, 2).float(), (H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1) + add.float()
+        out = ops.upsample_bilinear_add_bf16(small, add)
+        assert float((out.float() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max()) + 1e-6
+    x = (3 * torch.randn(2, 17, 19, 192, generator=gen)).to(dev).bfloat16()
+    g = (4 * torch.randn(2, 17, 19, 192, generator=gen)).to(dev).bfloat16()
+    ref = x.float() * torch.sigmoid(g.float())
+    out = ops.sigmoid_gate_bf16(x, g)
+    assert float((out.float() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max())
+    xt, gt = x.flatten()[:13].contiguous(), g.flatten()[:13].contiguous()            # ragged tail (n % 8 != 0)
+    assert float((ops.sigmoid_gate_bf16(xt, gt).float() - xt.float() * torch.sigmoid(gt.float())).abs().max()) <= 2 ** -8 * float(ref.abs().max())

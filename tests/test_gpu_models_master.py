@@ -293,6 +293,31 @@ def test_training_step_gradients(g, setup):
         net.zero_grad(set_to_none=True)
 
 
+def test_train_step_api_with_guide_codec():
+    """mmcodec.TrainStep on the (master, guide) pair: net(x, guided, hidden) with hidden from the frozen guide codec
+    (examples/train.py:208-233); one step changes the attention and conv parameters and keeps everything finite."""
+    torch.manual_seed(0)
+    guide = mmcodec.Guided_compresser(channel=1).eval()
+    master = mmcodec.Master_compresser(width=64, height=128, channel=3)
+    for n in (guide, master):
+        n.update()
+        n.to(dev())
+    gen = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 3, 128, 256, generator=gen).to(dev())
+    t = torch.rand(2, 1, 64, 128, generator=gen).to(dev())
+    step = mmcodec.TrainStep(master, guide, quality=3)
+    watch = {n: p.detach().clone() for n, p in master.named_parameters()
+             if n in ("decoder.sp_aligner2.blocks.1.attn.qkv2.weight", "ch_aligner.conv3.weight", "fdecoder.deconv1.weight",
+                      "decoder.sp_aligner1.blocks.0.attn.relative_position_bias_table", "entropy_bottleneck.quantiles")}
+    assert len(watch) == 5
+    res = step(x, t)
+    assert all(bool(torch.isfinite(v).all()) for v in res.values())
+    params = dict(master.named_parameters())
+    for n, before in watch.items():
+        assert float((params[n].detach() - before).abs().max()) > 0, n
+    assert all(bool(torch.isfinite(p).all()) for p in master.parameters())
+
+
 def test_full_size_properties_768x512():
     """BASELINE-size pair (3 x 512 x 768 master, 1 x 256 x 384 guide through Guided_compresser): shapes, finite outputs,
     likelihood ranges, batch independence."""
