@@ -122,6 +122,23 @@ class GradBucketReducer:
         self._work.clear()
         self._ready = [0] * len(self.buckets)
 
+    def reduce_now(self):
+        """Average every existing gradient across the group, bucket by bucket, on the current stream (no overlap; used when the
+        backward pass ran inside a CUDA graph and the hooks did not launch anything)."""
+        if self.world == 1:
+            return
+        for idxs in self.buckets:
+            grads = [self.params[i].grad for i in idxs if self.params[i].grad is not None]
+            if not grads:
+                continue
+            flat = torch.cat([g.reshape(-1).float() for g in grads])
+            dist.all_reduce(flat, group=self.group)
+            flat.div_(self.world)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+
     def remove(self):
         for h in self._hooks:
             h.remove()
@@ -142,7 +159,9 @@ class TrainStep:
         self.clip_max_norm = clip_max_norm
         self.reducer = GradBucketReducer(net.parameters(), bucket_bytes, group)
 
-    def __call__(self, x: Tensor, guided: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    def forward_backward(self, x: Tensor, guided: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """Guide forward (no grad), forward, rate-distortion loss backward, aux loss backward; gradients are left in ``.grad``
+        (bucket all-reduces are launched by the hooks as the gradients appear, unless the reducer is disabled)."""
         self.net.train()
         hidden = None
         if self.guide is not None:
@@ -158,13 +177,21 @@ class TrainStep:
         out["loss"].backward()
         aux_loss = self.net.aux_loss()
         aux_loss.backward()
-        self.reducer.finish()
+        out["aux_loss"] = aux_loss.detach()
+        return {k: v.detach() for k, v in out.items()}
+
+    def update(self) -> None:
+        """Gradient clipping (main parameters) and the two Adam steps."""
         if self.clip_max_norm > 0:
             torch.nn.utils.clip_grad_norm_((p for g in self.optimizer.param_groups for p in g["params"]), self.clip_max_norm)
         self.optimizer.step()
         self.aux_optimizer.step()
-        out["aux_loss"] = aux_loss.detach()
-        return {k: v.detach() for k, v in out.items()}
+
+    def __call__(self, x: Tensor, guided: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        out = self.forward_backward(x, guided)
+        self.reducer.finish()
+        self.update()
+        return out
 
 
 class GraphedTrainStep:
@@ -175,7 +202,9 @@ class GraphedTrainStep:
     Python can issue them.  The first ``warmup`` calls run eagerly (real optimisation steps; they also fill every per-shape
     cache); the next call records one whole step -- guide forward, forward, loss, backward, NCCL bucket all-reduces on the side
     stream, clipping, both Adam updates (``capturable=True``) -- under ``torch.cuda.graph`` and every call from then on copies
-    its batch into the captured input buffers and launches the graph.  Everything that depends on the parameters (bf16 weight
+    its batch into the captured input buffers and launches the graph.  With more than one rank the collectives stay outside:
+    graph 1 = forward + backward into static gradient buffers, then the bucketed NCCL all-reduce (eager, current stream), then
+    graph 2 = clipping + both Adam updates.  Everything that depends on the parameters (bf16 weight
     packs, GDN re-parametrisations) is recomputed INSIDE the graph, because the optimizer step of the previous replay changed
     them; after each replay the parameters' version counters are bumped so that caches used by later eager calls are rebuilt.
 
@@ -206,12 +235,33 @@ class GraphedTrainStep:
             self._x, self._g = x.clone(), (guided.clone() if guided is not None else None)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph), torch.enable_grad():
-                self._out = self.step(self._x, self._g)
+            if self.step.reducer.world == 1:
+                with torch.cuda.graph(self.graph), torch.enable_grad():
+                    self._out = self.step(self._x, self._g)
+            else:
+                # data parallel: the collectives stay OUTSIDE the graphs (graph 1: forward + backward into static gradient
+                # buffers; eager bucketed NCCL all-reduce; graph 2: clip + Adam x2)
+                self.step.reducer.enabled = False
+                with torch.cuda.graph(self.graph), torch.enable_grad():
+                    self._out = self.step.forward_backward(self._x, self._g)
+                self.graph.replay()                      # capture does not execute: materialise the gradients once
+                self.step.reducer.reduce_now()
+                self.update_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.update_graph):
+                    self.step.update()
+                self.update_graph.replay()
+                self._bump_versions()
+                return self._out
         else:
             self._copy_in(x, guided)
         self.graph.replay()
+        if self.step.reducer.world > 1:
+            self.step.reducer.reduce_now()
+            self.update_graph.replay()
+        self._bump_versions()
+        return self._out
+
+    def _bump_versions(self):
         for p in self.step.net.parameters():
             if p.grad is not None:
                 torch.autograd.graph.increment_version(p)
-        return self._out

@@ -319,7 +319,7 @@ def bench_other(args):
     top = sorted(prof.items(), key=lambda kv: -kv[1][0])[:14]
     print(json.dumps({"metric": f"{'frames' if args.workload == 'ssf2020' else 'pairs'}/s ({args.workload})", "value": units * world * args.steps / (ms * 1e-3),
                       "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-                      "launch_mode": ("eager launches (graph capture failed: " + graph_error + ")") if graph_error else ("one CUDA graph per optimisation step (mmcodec.GraphedTrainStep)" if args.workload in ("mm-train", "master-train") else "one CUDA graph per step (mmcodec.GraphedForward)"), "ms_per_step_eager": ms_eager / args.steps,
+                      "launch_mode": ("eager launches (graph capture failed: " + graph_error + ")") if graph_error else (("one CUDA graph per optimisation step (mmcodec.GraphedTrainStep)" if world == 1 else "mmcodec.GraphedTrainStep: graph 1 = forward + backward, eager bucketed NCCL all-reduce, graph 2 = clip + Adam x2") if args.workload in ("mm-train", "master-train") else "one CUDA graph per step (mmcodec.GraphedForward)"), "ms_per_step_eager": ms_eager / args.steps,
                       "sum_of_kernel_ms": kernel_ms,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                       "config": {"workload": OTHER_WORKLOADS[args.workload], "units_per_gpu": units, "weights": "random init",

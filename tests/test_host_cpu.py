@@ -262,7 +262,15 @@ def _reducer_worker(rank, world, port, q):
     net(x).pow(2).sum().backward()
     local = [p.grad.clone() for p in net.parameters()]
     red.finish()
-    q.put((rank, [g.tolist() for g in local], [p.grad.tolist() for p in net.parameters()], unused.grad is None, len(red.buckets)))
+    first = [p.grad.tolist() for p in net.parameters()]
+    # second mode (GraphedTrainStep with several ranks): hooks disabled during backward, one explicit reduction afterwards
+    red.enabled = False
+    net.zero_grad(set_to_none=True)
+    net(x + 1.0).pow(2).sum().backward()
+    local2 = [p.grad.clone() for p in net.parameters()]
+    red.reduce_now()
+    q.put((rank, [g.tolist() for g in local], first, unused.grad is None, len(red.buckets),
+           [g.tolist() for g in local2], [p.grad.tolist() for p in net.parameters()]))
     dist.destroy_process_group()
 
 
@@ -276,11 +284,12 @@ def test_grad_bucket_reducer_world_size_2_gloo():
     [p.start() for p in ps]
     res = sorted(q.get(timeout=120) for _ in ps)
     [p.join(60) for p in ps]
-    (_, l0, a0, u0, nb), (_, l1, a1, u1, _) = res
+    (_, l0, a0, u0, nb, m0, b0), (_, l1, a1, u1, _, m1, b1) = res
     assert u0 and u1 and nb >= 3
-    for g0, g1, r0, r1 in zip(l0, l1, a0, a1):
-        want = (torch.tensor(g0) + torch.tensor(g1)) / 2
-        assert torch.allclose(torch.tensor(r0), want, rtol=1e-6, atol=1e-6) and torch.allclose(torch.tensor(r1), want, rtol=1e-6, atol=1e-6)
+    for loc0, loc1, red0, red1 in ((l0, l1, a0, a1), (m0, m1, b0, b1)):      # hook-driven buckets, then reduce_now()
+        for g0, g1, r0, r1 in zip(loc0, loc1, red0, red1):
+            want = (torch.tensor(g0) + torch.tensor(g1)) / 2
+            assert torch.allclose(torch.tensor(r0), want, rtol=1e-6, atol=1e-6) and torch.allclose(torch.tensor(r1), want, rtol=1e-6, atol=1e-6)
 
 
 def test_training_glue_on_cpu():
