@@ -57,7 +57,16 @@ __global__ void __launch_bounds__(kBwBlock) colsum_kernel(const uint4 *__restric
     const int tc = threadIdx.x % C8, tr = threadIdx.x / C8, rpb = kBwBlock / C8;   // C8 <= 256
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (tr < rpb) {
-        for (int64_t r = (int64_t)blockIdx.x * rpb + tr; r < rows; r += (int64_t)gridDim.x * rpb) {
+        const int64_t step = (int64_t)gridDim.x * rpb;
+        int64_t r = (int64_t)blockIdx.x * rpb + tr;
+        for (; r + 3 * step < rows; r += 4 * step) {      // four independent 16-byte loads in flight per thread
+            const uint4 q0 = g[r * C8 + tc], q1 = g[(r + step) * C8 + tc], q2 = g[(r + 2 * step) * C8 + tc], q3 = g[(r + 3 * step) * C8 + tc];
+            float v0[8], v1[8], v2[8], v3[8];
+            unpack8(q0, v0); unpack8(q1, v1); unpack8(q2, v2); unpack8(q3, v3);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += (v0[k] + v1[k]) + (v2[k] + v3[k]);
+        }
+        for (; r < rows; r += step) {
             float v[8];
             unpack8(g[r * C8 + tc], v);
 #pragma unroll

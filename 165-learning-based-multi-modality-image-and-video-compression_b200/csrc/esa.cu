@@ -62,6 +62,41 @@ __global__ void __launch_bounds__(256) upsample_add_kernel(const __nv_bfloat162 
     }
 }
 
+// 8 channels (one 16-byte vector) per thread: used whenever C % 8 == 0
+__global__ void __launch_bounds__(256) upsample_add_v8_kernel(const uint4 *__restrict__ small, const uint4 *__restrict__ add, int hs, int ws, int H, int W,
+                                                              int C8, float sy, float sx, int64_t n, uint4 *__restrict__ y)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C8);
+        int64_t t = i / C8;
+        const int ox = (int)(t % W); t /= W;
+        const int oy = (int)(t % H);
+        const int64_t b = t / H;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(oy, sy, hs, &y0, &y1, &ly);
+        bilinear_src(ox, sx, ws, &x0, &x1, &lx);
+        const uint4 *base = small + b * hs * ws * C8 + c;
+        const uint4 q00 = base[((int64_t)y0 * ws + x0) * C8], q01 = base[((int64_t)y0 * ws + x1) * C8];
+        const uint4 q10 = base[((int64_t)y1 * ws + x0) * C8], q11 = base[((int64_t)y1 * ws + x1) * C8];
+        const uint4 qa = add[i];
+        uint4 o;
+        const __nv_bfloat162 *p00 = reinterpret_cast<const __nv_bfloat162 *>(&q00), *p01 = reinterpret_cast<const __nv_bfloat162 *>(&q01);
+        const __nv_bfloat162 *p10 = reinterpret_cast<const __nv_bfloat162 *>(&q10), *p11 = reinterpret_cast<const __nv_bfloat162 *>(&q11);
+        const __nv_bfloat162 *pa = reinterpret_cast<const __nv_bfloat162 *>(&qa);
+        __nv_bfloat162 *po = reinterpret_cast<__nv_bfloat162 *>(&o);
+        const float hy = 1.0f - ly, hx = 1.0f - lx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 v00 = __bfloat1622float2(p00[j]), v01 = __bfloat1622float2(p01[j]), v10 = __bfloat1622float2(p10[j]), v11 = __bfloat1622float2(p11[j]);
+            const float2 a = __bfloat1622float2(pa[j]);
+            po[j] = __floats2bfloat162_rn(hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x) + a.x,
+                                          hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y) + a.y);
+        }
+        y[i] = o;
+    }
+}
+
 __global__ void __launch_bounds__(256) sigmoid_gate_kernel(const uint4 *__restrict__ x, const uint4 *__restrict__ g, int64_t n8, uint4 *__restrict__ y)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -109,6 +144,13 @@ int mmc_upsample_bilinear_add_bf16(const void *small, int B, int hs, int ws, int
     const int64_t n = (int64_t)B * H * W * (C / 2);
     if (n == 0) return MMC_OK;
     MMC_CHECK_ARG(small && add && y, "mmc_upsample_bilinear_add_bf16: NULL buffer");
+    if (C % 8 == 0 && aligned16(small) && aligned16(add) && aligned16(y)) {
+        const int64_t n8 = (int64_t)B * H * W * (C / 8);
+        upsample_add_v8_kernel<<<elementwise_grid(n8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)small, (const uint4 *)add, hs, ws, H, W, C / 8,
+                                                                                          (float)hs / (float)H, (float)ws / (float)W, n8, (uint4 *)y);
+        MMC_CHECK_LAUNCH("mmc_upsample_bilinear_add_bf16");
+        return MMC_OK;
+    }
     upsample_add_kernel<<<elementwise_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat162 *)small, (const __nv_bfloat162 *)add, hs, ws, H, W,
                                                                                    C / 2, (float)hs / (float)H, (float)ws / (float)W, n, (__nv_bfloat162 *)y);
     MMC_CHECK_LAUNCH("mmc_upsample_bilinear_add_bf16");

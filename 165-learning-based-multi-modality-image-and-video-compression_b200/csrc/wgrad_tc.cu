@@ -283,6 +283,10 @@ int mmc_wgrad_tc(const void *s_nhwc, const void *l_nhwc, int64_t B, int Cs, int 
     // split K so that the grid covers the machine about twice -- but every split pays 128 x Ntile fp32 atomics in its epilogue, so a
     // split must carry enough K blocks to amortise them (measured: a 192x192 3x3 layer on 4 x 32x48 pixels took 1.6 ms with 17
     // splits of 6 K blocks, all of it atomics); every split non-empty
+    // (Tried: choosing the split count that minimises rounds x K blocks per item -- fewer, longer items in one or two full rounds.
+    // Measured SLOWER, tran_conv1 1.56 -> 2.16 ms: the kernel is bound by L2 bandwidth, not by the per-SM pipeline -- every tap and
+    // every M tile re-reads its operand patches, 21 GB through L2 for a 256x256 3x3 layer at 16 x 256x384 in 0.96 ms -- and more,
+    // shorter items spread those reads better.  The lever is operand reuse across taps, not the schedule.)
     int splits = (2 * kNumSMs + tiles - 1) / tiles;
     const int max_splits = (P.kblocks + 31) / 32;
     if (splits > max_splits) splits = max_splits;

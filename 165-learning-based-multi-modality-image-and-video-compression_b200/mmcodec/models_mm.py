@@ -15,6 +15,7 @@ per-pixel Python loop in the reference) are out of scope and raise.
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict
 
 import torch
@@ -98,7 +99,7 @@ class ESA(nn.Module):
     # Training keeps the gate on torch's bf16 ops: its seven small convolutions per block (42 layers in the depth branch) each cost
     # ~5 launches in the backward pass and made the step host-bound (measured 52.3 vs 42.9 ms per 4-pair step); the kernel path
     # below is what inference uses (19.0 -> 17.7 ms per 8 pairs).  Both are covered by the parity tests.
-    train_on_kernels = False
+    train_on_kernels = os.environ.get("MMC_ESA_TRAIN_KERNELS", "0") == "1"
 
     def _forward_torch(self, x: Tensor) -> Tensor:
         """(B, C, H, W) channels-last view -> same, stock torch ops (google.py:1445-1459)."""
