@@ -23,7 +23,7 @@ from .layers import GDN, LowerBound, NonNegativeParametrizer, conv, deconv  # no
 from .models import (CompressionModel, FactorizedPrior, MeanScaleHyperprior, ScaleHyperprior,  # noqa: F401
                      build_model, get_scale_table)
 
-from .models_mm import (ESA, Guided_compresser, JointAutoregressiveHierarchicalPriors_D,  # noqa: F401
+from .models_mm import (ESA, Guided_compresser, JointAutoregressiveHierarchicalPriors, JointAutoregressiveHierarchicalPriors_D,  # noqa: F401
                         JointAutoregressiveHierarchicalPriors_R, MaskedConv2d)
 from .models_master import Master_compresser  # noqa: F401
 from .models_video import ScaleSpaceFlow  # noqa: F401

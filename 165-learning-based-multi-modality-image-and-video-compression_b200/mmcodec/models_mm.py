@@ -30,7 +30,7 @@ from .layers import GDN, Conv2d, conv, deconv
 from .models import MeanScaleHyperprior, _nhwc_to_logical
 from .transforms import TransformStack, run_layers
 
-__all__ = ["MaskedConv2d", "ESA", "Encoder1", "Decoder1", "JointAutoregressiveHierarchicalPriors_R", "Guided_compresser",
+__all__ = ["MaskedConv2d", "ESA", "Encoder1", "Decoder1", "JointAutoregressiveHierarchicalPriors", "JointAutoregressiveHierarchicalPriors_R", "Guided_compresser",
            "JointAutoregressiveHierarchicalPriors_D"]
 
 
@@ -260,6 +260,41 @@ class _ContextModelMixin:
         raise NotImplementedError("autoregressive decompress() (google.py:920-1003) is out of scope")
 
 
+class JointAutoregressiveHierarchicalPriors(_ContextModelMixin, MeanScaleHyperprior):
+    """The zoo's mbt2018 model (google.py:421-520): stock g_a / g_s around the hyperprior + masked-context entropy stage.
+    ``forward`` (eval and training) runs on the kernels; the serial autoregressive coder (google.py:565-692) is out of scope."""
+
+    def __init__(self, N=192, M=192, channel=3, **kwargs):
+        super().__init__(N=N, M=M, **kwargs)
+        self.g_a = TransformStack(conv(channel, N, kernel_size=5, stride=2), GDN(N), conv(N, N, kernel_size=5, stride=2), GDN(N),
+                                  conv(N, N, kernel_size=5, stride=2), GDN(N), conv(N, M, kernel_size=5, stride=2))
+        self.g_s = TransformStack(deconv(M, N, kernel_size=5, stride=2), GDN(N, inverse=True), deconv(N, N, kernel_size=5, stride=2),
+                                  GDN(N, inverse=True), deconv(N, N, kernel_size=5, stride=2), GDN(N, inverse=True),
+                                  deconv(N, channel, kernel_size=5, stride=2))
+        self._init_entropy_stage(N, M)
+        self.N, self.M = int(N), int(M)
+        self._tag_layer_names()
+
+    @property
+    def downsampling_factor(self) -> int:
+        return 2 ** (4 + 2)
+
+    def forward(self, x):
+        y, y_bf16 = run_layers(list(self.g_a), x, "nchw_f32", "nhwc_f32", out2=2)
+        y_hat_bf16, y_lik, z_lik = self._entropy_stage(y, y_bf16)
+        x_hat = run_layers(list(self.g_s), y_hat_bf16, "nhwc_bf16", "nchw_f32")
+        return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}
+
+    @classmethod
+    def from_state_dict(cls, state_dict, channel=3):
+        """google.py:522-529"""
+        N = state_dict["g_a.0.weight"].size(0)
+        M = state_dict["g_a.6.weight"].size(0)
+        net = cls(N, M, channel)
+        net.load_state_dict(state_dict)
+        return net
+
+
 class JointAutoregressiveHierarchicalPriors_R(_ContextModelMixin, MeanScaleHyperprior):
     """Guide (RGB) branch, google.py:746-825.  ``forward`` also returns the six hidden maps the second branch fuses;
     they are logical (B, N, H, W) bf16 tensors in channels-last memory (the kernels' native activation format)."""
@@ -362,3 +397,10 @@ class JointAutoregressiveHierarchicalPriors_D(_ContextModelMixin, MeanScaleHyper
         y_hat_bf16, y_lik, z_lik = self._entropy_stage(y, y_bf16)
         x_hat = self._synthesis(y_hat_bf16, g)
         return {"x_hat": x_hat, "likelihoods": {"y": y_lik, "z": z_lik}}
+
+
+# zoo registration (compressai/zoo/image.py:56,220-229): build_model("mbt2018", q)
+from . import models as _models  # noqa: E402
+
+_models.MODELS["mbt2018"] = JointAutoregressiveHierarchicalPriors
+_models.CFGS["mbt2018"] = {q: ((192, 192) if q <= 4 else (192, 320)) for q in range(1, 9)}

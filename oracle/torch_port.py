@@ -293,6 +293,14 @@ def _context_entropy_stage(sd, y, noise=None):
     return y_hat, y_lik, z_lik, {"z": z, "scales_hat": scales_hat, "means_hat": means_hat}
 
 
+def mbt2018_forward(sd, x, noise=None):
+    """JointAutoregressiveHierarchicalPriors.forward (the zoo's mbt2018, google.py:499-520): stock g_a / g_s around the
+    context-model entropy stage."""
+    y = _seq_g_a(sd, x)
+    y_hat, y_lik, z_lik, extra = _context_entropy_stage(sd, y, noise)
+    return {"x_hat": _seq_g_s(sd, y_hat), "likelihoods": {"y": y_lik, "z": z_lik}, "y": y, "y_hat": y_hat, **extra}
+
+
 def mm_r_forward(sd, x):
     """JointAutoregressiveHierarchicalPriors_R.forward (google.py:800-825)."""
     h = {}

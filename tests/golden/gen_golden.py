@@ -28,7 +28,7 @@ import torch.nn as nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from weights import make_image, make_master_state_dict, make_mm_state_dict, make_ssf_state_dict, make_state_dict  # noqa: E402
+from weights import make_image, make_master_state_dict, make_mbt2018_state_dict, make_mm_state_dict, make_ssf_state_dict, make_state_dict  # noqa: E402
 
 REF_SRC = "/root/reference/CompressAI"
 SCRATCH = os.environ.get("MMC_REF_SCRATCH", "/tmp/ref_probe")
@@ -445,6 +445,26 @@ def master_goldens(out, verbose=False):
                   "p>0.99", float((v > 0.99).float().mean()))
 
 
+def mbt2018_goldens(out):
+    """The zoo's JointAutoregressiveHierarchicalPriors (mbt2018, compressai/models/google.py:421-520): eval forward."""
+    import json
+    from compressai.models import JointAutoregressiveHierarchicalPriors
+    d = make_image(1, 128, 192, seed=6)
+    torch.manual_seed(0)
+    net = quiet(JointAutoregressiveHierarchicalPriors, 192, 192).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    load_into(net, make_mbt2018_state_dict(shapes, 3))
+    quiet(net.update, force=True)
+    out["state_dict"] = np.array(json.dumps({k: [list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()}))
+    with torch.no_grad():
+        o = quiet(net, torch.from_numpy(d))
+    out["x"], out["x_hat"] = d, t2n(o["x_hat"])
+    for k, v in o["likelihoods"].items():
+        out[f"lik_{k}"] = t2n(v)
+    print("mbt2018 bpp", {k: float(torch.log2(v).sum() / -(128 * 192)) for k, v in o["likelihoods"].items()},
+          "floor", float((o["likelihoods"]["y"] <= 1.0001e-9).float().mean()), "x_hat", float(o["x_hat"].min()), float(o["x_hat"].max()))
+
+
 def color_goldens(out):
     """compressai.transforms.functional on a random frame (the reference's own functions)."""
     from compressai.transforms.functional import rgb2ycbcr, ycbcr2rgb, yuv_420_to_444, yuv_444_to_420
@@ -459,9 +479,9 @@ def color_goldens(out):
 def main():
     import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color", "models_guided", "models_master"]
+    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color", "models_guided", "models_master", "models_mbt2018"]
     gens = {"kernels": kernel_goldens, "models": model_goldens, "models_mm": mm_goldens, "models_ssf": ssf_goldens, "color": color_goldens,
-            "models_guided": guided_goldens, "models_master": master_goldens}
+            "models_guided": guided_goldens, "models_master": master_goldens, "models_mbt2018": mbt2018_goldens}
     for name in which:
         d = {}
         gens[name](d)

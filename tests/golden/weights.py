@@ -235,3 +235,16 @@ def make_master_state_dict(shapes, seed: int = 0):
     sd["entropy_parameters.4.weight"][M:] *= 0.25
     sd["fdecoder.deconv1.bias"] = np.full(shapes["fdecoder.deconv1.bias"], 0.45, dtype=np.float32)
     return sd
+
+
+MBT2018_GAINS = {"g_a.6": 3.0, "g_a.": 3.0, "g_s.0": 0.12, "g_s.": 0.5, "g_s.6": 0.3, "h_s.4": 2.0, "context_prediction": 0.5,
+                 "entropy_parameters": 1.5}
+
+
+def make_mbt2018_state_dict(shapes, seed: int = 0):
+    """Weights for the zoo's JointAutoregressiveHierarchicalPriors (mbt2018): the two-branch recipe on the stock g_a / g_s names."""
+    sd = make_state_dict_like(shapes, seed, MBT2018_GAINS)
+    M = shapes["entropy_parameters.4.bias"][0] // 2
+    sd["entropy_parameters.4.bias"][:M] += 2.0
+    sd["entropy_parameters.4.weight"][M:] *= 0.25
+    return sd

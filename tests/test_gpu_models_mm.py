@@ -190,3 +190,65 @@ def test_full_size_properties_768x512():
         for lk in o["likelihoods"].values():
             assert float(lk.min()) >= 1e-9 * 0.999 and float(lk.max()) <= 1 + 1e-6
     assert torch.equal(o_d0["x_hat"], o_d["x_hat"][:1]) and torch.equal(o_d0["likelihoods"]["y"], o_d["likelihoods"]["y"][:1])
+
+
+def test_mbt2018_vs_reference_golden_and_training():
+    """The zoo's JointAutoregressiveHierarchicalPriors (mbt2018, google.py:421-520) through build_model: state_dict keys, eval
+    forward vs the reference's run (stage-wise against the oracle on the reference's latents), training-mode gradients vs the
+    oracle's autograd on the same noise, q >= 5 configuration (M = 320: entropy_parameters widths that are not multiples of 16)."""
+    import os
+    from weights import make_mbt2018_state_dict
+    gg = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_mbt2018.npz"))
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(gg["state_dict"])).items()}
+    sd = {k: torch.from_numpy(v) for k, v in make_mbt2018_state_dict(shapes, 3).items()}
+    net = mmcodec.build_model("mbt2018", 3).eval()
+    assert isinstance(net, mm.JointAutoregressiveHierarchicalPriors) and set(net.state_dict()) == set(shapes)
+    net.update()
+    net.load_state_dict({**net.state_dict(), **sd})
+    net.update(force=True)
+    net = net.to(dev())
+    sd["context_prediction.mask"] = tp.masked_conv_mask(shapes["context_prediction.weight"], "A")
+    x = torch.from_numpy(gg["x"])
+    with torch.no_grad():
+        o = net(x.to(dev()))
+        ref = tp.mbt2018_forward(sd, x)
+        x_hat_same_latent = net.g_s(ref["y_hat"].to(dev()))
+    npix = x.shape[0] * x.shape[2] * x.shape[3]
+    ref_bpp = sum(oracle.bits(gg[f"lik_{k}"]) for k in o["likelihoods"]) / npix
+    assert abs(bpp_of(o["likelihoods"], npix) - ref_bpp) / ref_bpp < 0.05
+    assert rel_rms(x_hat_same_latent.float(), ref["x_hat"]) < 1e-2
+    assert rel_rms(o["x_hat"].float(), torch.from_numpy(gg["x_hat"])) < 0.15
+    with pytest.raises(NotImplementedError):
+        net.compress(x.to(dev()))
+    # training-mode forward / backward on the same noise draws
+    gen = torch.Generator().manual_seed(2)
+    noise = {"z": torch.rand(1, 192, 2, 3, generator=gen) - 0.5, "y_hat": torch.rand(1, 192, 8, 12, generator=gen) - 0.5,
+             "y": torch.rand(1, 192, 8, 12, generator=gen) - 0.5}
+    net.train()
+    net._noise_override = noise
+    crit = mmcodec.RateDistortionLoss(3)
+    loss = crit(net(x.to(dev())), x.to(dev()))
+    loss["loss"].backward()
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("mask", "bound", "pedestal")) else v) for k, v in sd.items()}
+    ro = tp.mbt2018_forward(sdg, x, noise=noise)
+    r_loss = crit(ro, x)
+    r_loss["loss"].backward()
+    assert abs(float(loss["loss"]) - float(r_loss["loss"])) / float(r_loss["loss"]) < 3e-2
+    checked = 0
+    for name, p in net.named_parameters():
+        rg = sdg[name].grad if name in sdg else None
+        if rg is None or p.dim() < 2 or float(rg.norm()) < 1e-12:
+            continue
+        assert p.grad is not None, name
+        c = float(torch.nn.functional.cosine_similarity(p.grad.flatten().double().cpu(), rg.flatten().double(), dim=0))
+        assert c > 0.93, (name, c)
+        checked += 1
+    assert checked >= 20
+    net._noise_override = None
+    # the high-quality configuration
+    big = mmcodec.build_model("mbt2018", 6).eval()
+    big.update()
+    big = big.to(dev())
+    with torch.no_grad():
+        ob = big(torch.rand(1, 3, 64, 128, generator=gen).to(dev()))
+    assert tuple(ob["likelihoods"]["y"].shape) == (1, 320, 4, 8) and torch.isfinite(ob["x_hat"]).all()

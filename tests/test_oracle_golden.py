@@ -307,3 +307,20 @@ def test_master_attention_tables():
     assert m.shape == (8, 16, 16) and set(m.unique().tolist()) <= {0.0, -100.0}
     assert torch.equal(m, m.transpose(1, 2)) and float(m[0].abs().sum()) == 0.0   # interior windows are unmasked
     assert float(m[-1].abs().sum()) > 0                                       # the wrap-around corner window is not
+
+
+def test_torch_port_mbt2018():
+    """The zoo's JointAutoregressiveHierarchicalPriors (google.py:421-520): the port reproduces the reference run."""
+    import json
+    import os
+    from weights import make_mbt2018_state_dict
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_mbt2018.npz"))
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(g["state_dict"])).items()}
+    sd = {k: torch.from_numpy(v) for k, v in make_mbt2018_state_dict(shapes, 3).items()}
+    sd["context_prediction.mask"] = tp.masked_conv_mask(shapes["context_prediction.weight"], "A")
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        o = tp.mbt2018_forward(sd, torch.from_numpy(g["x"]))
+    assert np.max(np.abs(o["x_hat"].numpy() - g["x_hat"])) < 2e-4 * max(1.0, float(np.abs(g["x_hat"]).max()))
+    for k, l in o["likelihoods"].items():
+        assert rel_err(l.numpy(), g[f"lik_{k}"], 1e-9) < 1e-3, k
