@@ -191,7 +191,7 @@ def bench_other(args):
         units = args.batch or 8
         host = [torch.rand(1, 3, 1152, 1920, generator=gen).pin_memory() for _ in range(units)]
         step = lambda xs: net(xs)["x_hat"][-1]
-        e2e_out = lambda o: [t.cpu() for t in o["x_hat"]]
+        e2e_out = lambda o: list(o["x_hat"])
         run = lambda xs: net(xs)
     elif args.workload == "mm-train":
         net_r = mmcodec.JointAutoregressiveHierarchicalPriors_R(192, 192).eval()
@@ -206,7 +206,7 @@ def bench_other(args):
         def run(xs):
             with torch.enable_grad():
                 return trainer(xs[1], xs[0])
-        e2e_out = lambda o: [o["loss"].cpu()]
+        e2e_out = lambda o: [o["loss"]]
     elif args.workload == "master-train":
         guide = mmcodec.Guided_compresser(channel=1).eval()
         master = mmcodec.Master_compresser(width=256, height=384, channel=3)
@@ -220,7 +220,7 @@ def bench_other(args):
         def run(xs):
             with torch.enable_grad():
                 return trainer(xs[0], xs[1])
-        e2e_out = lambda o: [o["loss"].cpu()]
+        e2e_out = lambda o: [o["loss"]]
     elif args.workload == "master-forward":
         guide = mmcodec.Guided_compresser(channel=1).eval()
         master = mmcodec.Master_compresser(width=256, height=384, channel=3).eval()
@@ -233,7 +233,7 @@ def bench_other(args):
         def run(xs):
             og = guide(xs[1])
             return {"g": og, "m": master(xs[0], og["x_hat"], og["hidden"])}
-        e2e_out = lambda o: [o["g"]["x_hat"].cpu(), o["m"]["x_hat"].cpu()]
+        e2e_out = lambda o: [o["g"]["x_hat"], o["m"]["x_hat"]]
     else:
         net_r = mmcodec.JointAutoregressiveHierarchicalPriors_R(192, 192).eval()
         net_d = mmcodec.JointAutoregressiveHierarchicalPriors_D(192, 192).eval()
@@ -246,7 +246,7 @@ def bench_other(args):
         def run(xs):
             o_r = net_r(xs[0])
             return {"r": o_r, "d": net_d(xs[1], o_r["hidden"])}
-        e2e_out = lambda o: [o["r"]["x_hat"].cpu(), o["d"]["x_hat"].cpu()]
+        e2e_out = lambda o: [o["r"]["x_hat"], o["d"]["x_hat"]]
     xs = [t.to(dev) for t in host]
 
     def barrier():
@@ -266,9 +266,18 @@ def bench_other(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = ops.launch_count()
+        # results land in pinned host buffers (same memory layout as the device tensors), as a serving loop would keep them
+        pinned_out = [torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, pin_memory=True) for t in e2e_out(run(xs))]
+        def e2e_step():
+            outs = e2e_out(run([t.to(dev, non_blocking=True) for t in host]))
+            for dst, src in zip(pinned_out, outs):
+                dst.copy_(src, non_blocking=True)
+        for _ in range(2):          # untimed: lets the caching allocator settle on the e2e allocation pattern (fresh input tensors per step)
+            e2e_step()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            e2e_out(run([t.to(dev, non_blocking=True) for t in host]))
+            e2e_step()
         torch.cuda.synchronize()
         ms_e2e = (time.perf_counter() - t0) * 1e3
         ops.start_profile()
@@ -326,7 +335,7 @@ def bench_other(args):
                                  "parallelism": f"data parallel x{world}" + (", bucketed NCCL all-reduce of fp32 gradients" if args.workload in ("mm-train", "master-train") else ", no collective")},
                       "gpu_launches": launches,
                       "e2e": {"value": units * world * args.steps / (ms_e2e * 1e-3), "unit": "img/s", "ms_per_step": ms_e2e / args.steps,
-                              "h2d_bytes_per_step": sum(t_.numel() * 4 for t_ in host), "d2h_bytes_per_step": sum(t_.numel() * 4 for t_ in host)},
+                              "h2d_bytes_per_step": sum(t_.numel() * 4 for t_ in host), "d2h_bytes_per_step": sum(t_.numel() * t_.element_size() for t_ in pinned_out)},
                       "roofline": {"bound": "tensor", "step_tflops": total_f / (ms / args.steps * 1e-3) / 1e12, "conv_flops_per_step": total_f,
                                    "top_kernels_total_ms_x_launches": {k: [round(v[0], 4), v[2]] for k, v in top}}}))
 
