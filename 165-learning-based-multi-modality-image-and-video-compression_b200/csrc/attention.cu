@@ -196,6 +196,143 @@ __global__ void __launch_bounds__(256) channel_affine_kernel(const __nv_bfloat16
     }
 }
 
+// 8 channels per thread (C % 8 == 0, 16-byte aligned buffers)
+__global__ void __launch_bounds__(256) channel_affine_v8_kernel(const uint4 *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                                int64_t HW, int C8, int64_t n8, uint4 *__restrict__ y)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % C8);
+        const int64_t b = i / (HW * C8);
+        const float4 *g = reinterpret_cast<const float4 *>(gamma + (b * C8 + c8) * 8), *bt = reinterpret_cast<const float4 *>(beta + (b * C8 + c8) * 8);
+        const float4 g0 = g[0], g1 = g[1], b0 = bt[0], b1 = bt[1];
+        const uint4 q = x[i];
+        const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&q);
+        const float2 v0 = __bfloat1622float2(p[0]), v1 = __bfloat1622float2(p[1]), v2 = __bfloat1622float2(p[2]), v3 = __bfloat1622float2(p[3]);
+        uint4 o;
+        __nv_bfloat162 *po = reinterpret_cast<__nv_bfloat162 *>(&o);
+        po[0] = __floats2bfloat162_rn(fmaf(g0.x, v0.x, b0.x), fmaf(g0.y, v0.y, b0.y));
+        po[1] = __floats2bfloat162_rn(fmaf(g0.z, v1.x, b0.z), fmaf(g0.w, v1.y, b0.w));
+        po[2] = __floats2bfloat162_rn(fmaf(g1.x, v2.x, b1.x), fmaf(g1.y, v2.y, b1.y));
+        po[3] = __floats2bfloat162_rn(fmaf(g1.z, v3.x, b1.z), fmaf(g1.w, v3.y, b1.w));
+        y[i] = o;
+    }
+}
+
+// ---- spatial mean of a 3x3 / stride-1 / padding-1 convolution WITHOUT computing the convolution -------------------------------
+// Channel_aligner only uses conv5 / conv6 through AdaptiveAvgPool2d(1) (master.py:193-194,205-206).  The mean over output positions
+// of sum_tap W[tap] . t[p + tap] is, by linearity, sum_tap W[tap] . S_tap / HW with S_tap = the sum of t over the positions tap can
+// reach = total - excluded border row - excluded border column + their corner.  So one pass over t (9 channel vectors per sample:
+// total, first / last row, first / last column, four corners) and a 9 x C x O matrix-vector product replace two 256 -> 64 convolutions
+// on the full-resolution map and their 2 x 200 MB fp32 outputs.  Fixed summation orders throughout (batch-independent results).
+__global__ void __launch_bounds__(256) border_total_partial_kernel(const uint4 *__restrict__ t, int64_t HW, int C8, int splits, float *__restrict__ part)
+{
+    __shared__ float red[8][32][9];
+    const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c8 = blockIdx.x * 32 + lane, b = blockIdx.y, sp = blockIdx.z;
+    const int64_t per = (HW + splits - 1) / splits, r0 = sp * per, r1 = (r0 + per < HW) ? r0 + per : HW;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c8 < C8) {
+        const uint4 *src = t + (int64_t)b * HW * C8 + c8;
+        int64_t r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {          // four independent 16-byte loads in flight per thread
+            const uint4 q4[4] = {src[r * C8], src[(r + 8) * C8], src[(r + 16) * C8], src[(r + 24) * C8]};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&q4[u]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float2 v = __bfloat1622float2(p[j]); acc[2 * j] += v.x; acc[2 * j + 1] += v.y; }
+            }
+        }
+        for (; r < r1; r += 8) {
+            const uint4 q = src[r * C8];
+            const __nv_bfloat162 *p = reinterpret_cast<const __nv_bfloat162 *>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const float2 v = __bfloat1622float2(p[j]); acc[2 * j] += v.x; acc[2 * j + 1] += v.y; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[ty][lane][k] = acc[k];
+    __syncthreads();
+    if (ty == 0 && c8 < C8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float s = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += red[i][lane][k];
+            part[((int64_t)b * splits + sp) * (C8 * 8) + c8 * 8 + k] = s;
+        }
+    }
+}
+
+// sums[b][0..8][c]: total, row 0, row H-1, column 0, column W-1, corners (0,0) (0,W-1) (H-1,0) (H-1,W-1)
+// edges: one CTA per (32-channel group, sample, edge), 8 position lanes, fixed-order reduction
+__global__ void __launch_bounds__(256) border_edges_kernel(const __nv_bfloat16 *__restrict__ t, int H, int W, int C, float *__restrict__ sums)
+{
+    __shared__ float red[8][33];
+    const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane, b = blockIdx.y, e = blockIdx.z;
+    const int len = (e < 2) ? W : H;
+    const int64_t first = (e == 1) ? (int64_t)(H - 1) * W : (e == 3 ? W - 1 : 0), step = (e < 2) ? 1 : W;
+    const __nv_bfloat16 *img = t + (int64_t)b * H * W * C + c;
+    float s = 0.0f;
+    if (c < C)
+        for (int i = ty; i < len; i += 8) s += __bfloat162float(img[(first + (int64_t)i * step) * C]);
+    red[ty][lane] = s;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+        float v = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v += red[i][lane];
+        sums[((int64_t)b * 9 + 1 + e) * C + c] = v;
+    }
+}
+
+// totals (sum of the row splits) and the four corner pixels; one thread per (b, c)
+__global__ void __launch_bounds__(256) border_sums_kernel(const __nv_bfloat16 *__restrict__ t, const float *__restrict__ part, int H, int W, int C,
+                                                          int splits, int64_t n, float *__restrict__ sums)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t b = i / C;
+    const int c = (int)(i % C);
+    const __nv_bfloat16 *img = t + b * H * W * C + c;
+    float total = 0.0f;
+    for (int sp = 0; sp < splits; ++sp) total += part[(b * splits + sp) * C + c];
+    float *o = sums + b * 9 * C + c;
+    o[0] = total;
+    o[5 * C] = __bfloat162float(img[0]);
+    o[6 * C] = __bfloat162float(img[(int64_t)(W - 1) * C]);
+    o[7 * C] = __bfloat162float(img[(int64_t)(H - 1) * W * C]);
+    o[8 * C] = __bfloat162float(img[((int64_t)(H - 1) * W + W - 1) * C]);
+}
+
+// out[b][o] = bias[o] + (1 / HW) sum_{c, ky, kx} w[o][c][ky][kx] * S(ky - 1, kx - 1)[b][c]; one warp per (b, o), lanes over c
+__global__ void __launch_bounds__(256) conv3x3_mean_kernel(const float *__restrict__ sums, const float *__restrict__ w, const float *__restrict__ bias,
+                                                           int C, int O, float inv_hw, int64_t n, float *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= n) return;
+    const int64_t b = item / O;
+    const int o = (int)(item % O);
+    const float *s = sums + b * 9 * C;
+    float acc = 0.0f;
+    for (int c = lane; c < C; c += 32) {
+        const float T = s[c], r0 = s[C + c], rl = s[2 * C + c], c0 = s[3 * C + c], cl = s[4 * C + c];
+        const float k00 = s[5 * C + c], k0l = s[6 * C + c], kl0 = s[7 * C + c], kll = s[8 * C + c];
+        const float *wk = w + ((int64_t)o * C + c) * 9;
+        // tap offset -1 cannot reach the LAST row / column of t, offset +1 cannot reach the FIRST
+        const float rex[3] = {rl, 0.0f, r0}, cex[3] = {cl, 0.0f, c0};
+        const float cor[3][3] = {{kll, 0.0f, kl0}, {0.0f, 0.0f, 0.0f}, {k0l, 0.0f, k00}};
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) acc = fmaf(wk[ky * 3 + kx], T - rex[ky] - cex[kx] + cor[ky][kx], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[item] = (bias ? bias[o] : 0.0f) + acc * inv_hw;
+}
+
 }  // namespace mmc
 
 using namespace mmc;
@@ -272,8 +409,42 @@ int mmc_channel_affine_bf16(const void *x, const float *gamma, const float *beta
     if (B == 0) return MMC_OK;
     MMC_CHECK_ARG(x && gamma && beta && y, "mmc_channel_affine_bf16: NULL buffer");
     const int64_t n = (int64_t)B * HW * C;
+    if (C % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta)) {
+        channel_affine_v8_kernel<<<elementwise_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const uint4 *)x, gamma, beta, HW, C / 8, n / 8, (uint4 *)y);
+        MMC_CHECK_LAUNCH("mmc_channel_affine_bf16");
+        return MMC_OK;
+    }
     channel_affine_kernel<<<elementwise_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, gamma, beta, HW, C, n, (__nv_bfloat16 *)y);
     MMC_CHECK_LAUNCH("mmc_channel_affine_bf16");
+    return MMC_OK;
+}
+
+int mmc_conv3x3_mean_workspace(int B, int H, int W, int C, size_t *bytes)
+{
+    MMC_CHECK_ARG(B >= 0 && H >= 1 && W >= 1 && C >= 1 && bytes, "mmc_conv3x3_mean_workspace: bad argument");
+    *bytes = ((size_t)B * channel_mean_splits((int64_t)H * W) * C + (size_t)B * 9 * C) * sizeof(float);
+    return MMC_OK;
+}
+
+int mmc_conv3x3_mean(const void *t, int B, int H, int W, int C, const float *weight, const float *bias, int O, void *workspace, float *out, void *stream)
+{
+    MMC_CHECK_ARG(B >= 0 && B <= 65535 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && O >= 1, "mmc_conv3x3_mean: bad shape (C must be a multiple of 8)");
+    if (B == 0) return MMC_OK;
+    MMC_CHECK_ARG(t && weight && workspace && out && aligned16(t), "mmc_conv3x3_mean: NULL or unaligned buffer");
+    const int64_t HW = (int64_t)H * W;
+    const int splits = channel_mean_splits(HW);
+    float *part = (float *)workspace, *sums = part + (size_t)B * splits * C;
+    cudaStream_t st = (cudaStream_t)stream;
+    border_total_partial_kernel<<<dim3((C / 8 + 31) / 32, B, splits), 256, 0, st>>>((const uint4 *)t, HW, C / 8, splits, part);
+    MMC_CHECK_LAUNCH("mmc_conv3x3_mean");
+    const int64_t n = (int64_t)B * C;
+    border_sums_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16 *)t, part, H, W, C, splits, n, sums);
+    MMC_CHECK_LAUNCH("mmc_conv3x3_mean");
+    border_edges_kernel<<<dim3((C + 31) / 32, B, 4), 256, 0, st>>>((const __nv_bfloat16 *)t, H, W, C, sums);
+    MMC_CHECK_LAUNCH("mmc_conv3x3_mean");
+    const int64_t items = (int64_t)B * O;
+    conv3x3_mean_kernel<<<(unsigned)((items + 7) / 8), 256, 0, st>>>(sums, weight, bias, C, O, 1.0f / (float)HW, items, out);
+    MMC_CHECK_LAUNCH("mmc_conv3x3_mean");
     return MMC_OK;
 }
 

@@ -625,6 +625,25 @@ def sigmoid_gate_bf16(x: Tensor, gate: Tensor) -> Tensor:
     return y
 
 
+def conv3x3_mean(t: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """Spatial mean of conv3x3(t) (stride 1, padding 1) per sample and output channel, computed from border-corrected channel sums
+    of ``t`` instead of the convolution (see mmc_conv3x3_mean).  t: (B, H, W, C) bf16 NHWC; weight (O, C, 3, 3); returns (B, O) fp32."""
+    _require_cuda(t, weight)
+    t = _bf16c(t)
+    B, H, W, C = t.shape
+    O = weight.shape[0]
+    if tuple(weight.shape) != (O, C, 3, 3):
+        raise ValueError("conv3x3_mean: weight must be (O, C, 3, 3)")
+    nbytes = ctypes.c_size_t()
+    L.check(L.lib().mmc_conv3x3_mean_workspace(B, H, W, C, ctypes.byref(nbytes)))
+    ws = torch.empty(max(1, nbytes.value), dtype=torch.uint8, device=t.device)
+    out = torch.empty((B, O), dtype=torch.float32, device=t.device)
+    with _Timed("conv3x3_mean|attn"):
+        L.check(L.lib().mmc_conv3x3_mean(_ptr(t), B, H, W, C, _ptr(_f32c(weight.detach())), _ptr(_f32c(bias.detach())) if bias is not None else None,
+                                         O, _ptr(ws), _ptr(out), _stream()))
+    return out
+
+
 # ---- backward of the transforms ------------------------------------------------------------------------
 def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.0, mask: Optional[Tensor] = None,
           name: str = "conv") -> Tensor:

@@ -316,6 +316,13 @@ MMC_API int mmc_sigmoid_gate_bf16(const void *x, const void *gate, int64_t n, vo
 MMC_API int mmc_channel_mean_workspace(int B, int64_t HW, int C, size_t *bytes);
 MMC_API int mmc_channel_mean(const float *x, int B, int64_t HW, int C, void *workspace, float *out, void *stream);
 MMC_API int mmc_channel_affine_bf16(const void *x, const float *gamma, const float *beta, int B, int64_t HW, int C, void *y, void *stream);
+/* mean over all output positions of conv3x3(t) (stride 1, padding 1, weight (O, C, 3, 3) fp32, optional bias) WITHOUT computing the
+ * convolution: by linearity it is a 9 x C x O contraction of border-corrected channel sums of t (one pass over t).  Replaces
+ * `avgpool(conv5(out4))` / `avgpool(conv6(out9))` of Channel_aligner.forward (master.py:193-194, 205-206).  t: (B, H, W, C) bf16 NHWC,
+ * C % 8 == 0; out: (B, O) fp32; workspace of mmc_conv3x3_mean_workspace bytes.  Batch-independent summation order. */
+MMC_API int mmc_conv3x3_mean_workspace(int B, int H, int W, int C, size_t *bytes);
+MMC_API int mmc_conv3x3_mean(const void *t, int B, int H, int W, int C, const float *weight, const float *bias, int O, void *workspace,
+                             float *out, void *stream);
 MMC_API int mmc_layernorm_bf16(const void *x, const void *delta, const float *weight, const float *bias, int64_t rows, int C, float eps,
                                void *sum_out, void *y, void *stream);
 MMC_API int mmc_gelu_bf16(const void *x, int64_t n, void *y, void *stream);

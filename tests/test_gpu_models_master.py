@@ -99,6 +99,10 @@ def test_channel_mean_and_affine_kernels():
     ref = (gm[:, None, None, :] * f.float() + bt[:, None, None, :])
     out = ops.channel_affine_bf16(f, gm, bt)
     assert float((out.float() - ref).abs().max()) <= 2 ** -8 * float(ref.abs().max())
+    fr = torch.randn(2, 5, 7, 12, generator=gen).to(dev()).bfloat16()         # C % 8 != 0: scalar path
+    gr, br = torch.randn(2, 12, generator=gen).to(dev()), torch.randn(2, 12, generator=gen).to(dev())
+    rr = gr[:, None, None, :] * fr.float() + br[:, None, None, :]
+    assert float((ops.channel_affine_bf16(fr, gr, br).float() - rr).abs().max()) <= 2 ** -8 * float(rr.abs().max())
     xr = torch.randn(2, 5, 7, 40, generator=gen).to(dev())                    # ragged channel count
     assert float((ops.channel_mean(xr) - xr.mean(dim=(1, 2))).abs().max()) < 1e-6
 
@@ -134,6 +138,35 @@ def test_window_attention_kernel_vs_fp32_reference(H, W, ws, shift):
 
 
 # ---- stages vs the oracle on the reference's tensors -----------------------------------------------------------------------
+def test_conv3x3_mean_by_linearity_vs_convolution(setup):
+    """mmc_conv3x3_mean (mean over positions of a padding-1 3x3 convolution from border-corrected channel sums) against the
+    convolution itself in fp64, incl. degenerate maps (one row / one column / one pixel) and batch independence; then the two
+    Channel_aligner head evaluations (by linearity / by running conv5, conv6 and averaging) against each other."""
+    gen = torch.Generator().manual_seed(31)
+    for (B, H, W, C, O) in ((3, 20, 28, 64, 24), (2, 1, 5, 16, 8), (2, 4, 1, 8, 3), (1, 1, 1, 8, 5), (2, 33, 17, 256, 64)):
+        t = torch.randn(B, H, W, C, generator=gen).bfloat16()
+        w = torch.randn(O, C, 3, 3, generator=gen) / (3 * C ** 0.5)
+        b = torch.randn(O, generator=gen)
+        ref = F.conv2d(t.double().permute(0, 3, 1, 2), w.double(), b.double(), padding=1).mean(dim=(2, 3))
+        out = ops.conv3x3_mean(t.to(dev()), w.to(dev()), b.to(dev()))
+        assert float((out.double().cpu() - ref).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max())), (B, H, W, C, O)
+        assert torch.equal(ops.conv3x3_mean(t[B - 1:].to(dev()), w.to(dev()), b.to(dev())), out[B - 1:])
+        nob = ops.conv3x3_mean(t.to(dev()), w.to(dev()), None)
+        assert float((nob.double().cpu() - (ref - b.double())).abs().max()) < 1e-5 * max(1.0, float(ref.abs().max()))
+    net, _, ref_out, _, _ = setup
+    al = net.ch_aligner
+    gf = torch.randn(2, 64, 24, 40, generator=gen).to(dev())
+    xf = torch.randn(2, 64, 24, 40, generator=gen).to(dev())
+    with torch.no_grad():
+        a1, b1, g1 = al(xf, gf)
+        al.heads_by_linearity = False
+        try:
+            a2, b2, g2 = al(xf, gf)
+        finally:
+            al.heads_by_linearity = True
+    assert rel_rms(b1, b2) < 1e-2 and rel_rms(g1, g2) < 1e-2 and rel_rms(a1.float(), a2.float()) < 1e-2
+
+
 def test_state_dict_keys_and_shapes(g):
     ref = {k: tuple(v[0]) for k, v in json.loads(str(g["state_dict"])).items()}
     net = mmcodec.Master_compresser(width=64, height=128, channel=3)
