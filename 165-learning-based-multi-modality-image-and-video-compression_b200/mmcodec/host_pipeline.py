@@ -9,6 +9,11 @@ CUDA streams (PCIe is full duplex, the copy engines are independent of the SMs).
 independent, so the results are bit-identical to one big forward.  On return the caller's current
 stream is ordered after every copy: ``torch.cuda.current_stream().synchronize()`` (or an event
 recorded on it) makes the host buffers valid.
+
+``outputs="metrics"`` keeps what that evaluation loop keeps of a forward (``inference_entropy_estimation``,
+__main__t.py:151-173): per-image bpp and MSE (PSNR = -10 log10 MSE), reduced on the device by ``mmc_image_bits`` /
+``mmc_image_sse`` inside the same CUDA graph, so the device->host traffic is 8 bytes per image instead of the reconstruction
+and the likelihood tensors and the pipeline is bound by the host->device copy of the images alone.
 """
 from __future__ import annotations
 
@@ -28,7 +33,10 @@ def _pinned_like(shape, channels_last: bool) -> Tensor:
 
 
 class HostPipeline:
-    def __init__(self, net, micro_batch: int = 8, device: Optional[torch.device] = None, use_graphs: bool = True):
+    def __init__(self, net, micro_batch: int = 8, device: Optional[torch.device] = None, use_graphs: bool = True, outputs: str = "full"):
+        if outputs not in ("full", "metrics"):
+            raise ValueError('outputs must be "full" (x_hat + likelihoods) or "metrics" (per-image bpp and mse)')
+        self.outputs = outputs
         self.net = net
         self.micro_batch = int(micro_batch)
         self.device = device or next(net.parameters()).device
@@ -56,16 +64,28 @@ class HostPipeline:
         if self.use_graphs and self._graphs is None:
             graphs = []
             with torch.cuda.stream(self.s_run), torch.no_grad():
-                self.net(self._slots[0])     # fills the per-parameter caches (packed weights, LUTs) outside the capture
+                self._forward(self._slots[0])     # fills the per-parameter caches (packed weights, LUTs) outside the capture
                 torch.cuda.synchronize(self.device)
                 for k in range(2):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=self.s_run):
-                        o = self.net(self._slots[k])
+                        o = self._forward(self._slots[k])
                     graphs.append((g, o))
             torch.cuda.synchronize(self.device)
             self._graphs = graphs
         return self._slots, mb
+
+    def _forward(self, x: Tensor):
+        o = self.net(x)
+        if self.outputs == "full":
+            return o
+        from . import ops
+        n = x.shape[0]
+        m = torch.zeros((2, n), dtype=torch.float32, device=x.device)        # row 0: bpp, row 1: mse
+        for lk in o["likelihoods"].values():
+            ops.image_bits(lk, m[0], 1.0 / (x.shape[2] * x.shape[3]))
+        ops.image_mse(x, o["x_hat"], m[1])
+        return {"metrics": m}
 
     def _run(self, k: int, n: int):
         """Forward of the first n images of slot k on the current (run) stream."""
@@ -74,11 +94,12 @@ class HostPipeline:
             g.replay()
             return o, True
         with torch.no_grad():
-            return self.net(self._slots[k][:n]), False       # ragged tail micro-batch: eager launches
+            return self._forward(self._slots[k][:n]), False       # ragged tail micro-batch: eager launches
 
     def __call__(self, x_host: Tensor, out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
         """x_host: (B, C, H, W) fp32 host tensor (pinned for asynchronous copies).  Returns / fills
-        {"x_hat": (B,C,H,W), "likelihoods": {name: (B,C',H',W')}} pinned host tensors."""
+        {"x_hat": (B,C,H,W), "likelihoods": {name: (B,C',H',W')}} pinned host tensors, or, with outputs="metrics",
+        {"bpp": (B,), "mse": (B,)} pinned host tensors."""
         if x_host.is_cuda:
             raise ValueError("HostPipeline takes host tensors; call the model directly for device tensors")
         B = x_host.shape[0]
@@ -92,7 +113,7 @@ class HostPipeline:
         out_free = [None, None]       # event: the captured outputs of slot k have been copied to the host
         last_d2h = None
         result = out if out is not None else self._out
-        if result is not None and result["x_hat"].shape[0] != B:
+        if result is not None and next(iter(result.values())).shape[0] != B:
             result = None
         i = 0
         for lo in range(0, B, mb):
@@ -112,6 +133,22 @@ class HostPipeline:
                 ev_run = torch.cuda.Event()
                 ev_run.record(self.s_run)
                 slot_free[k] = ev_run
+            if self.outputs == "metrics":
+                if result is None:
+                    result = {"bpp": torch.empty(B, dtype=torch.float32).pin_memory(), "mse": torch.empty(B, dtype=torch.float32).pin_memory()}
+                    if out is None:
+                        self._out = result
+                with torch.cuda.stream(self.s_d2h):
+                    self.s_d2h.wait_event(ev_run)
+                    result["bpp"][lo:hi].copy_(o["metrics"][0], non_blocking=True)
+                    result["mse"][lo:hi].copy_(o["metrics"][1], non_blocking=True)
+                    if not static:
+                        o["metrics"].record_stream(self.s_d2h)
+                    last_d2h = torch.cuda.Event()
+                    last_d2h.record(self.s_d2h)
+                    out_free[k] = last_d2h
+                i += 1
+                continue
             if result is None:
                 # first call: allocate pinned result buffers with the device tensors' memory formats
                 result = {"x_hat": _pinned_like((B,) + tuple(o["x_hat"].shape[1:]), False),

@@ -644,6 +644,34 @@ def conv3x3_mean(t: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
     return out
 
 
+# ---- per-image metrics of a forward pass (eval_model/__main__t.py:151-173) ---------------------------------------
+def _sample_contiguous(t: Tensor) -> Tensor:
+    t = t if t.dtype == torch.float32 else t.float()
+    return t if (t.is_contiguous() or _is_channels_last(t)) else t.contiguous()
+
+
+def image_bits(likelihood: Tensor, accum: Tensor, scale: float) -> Tensor:
+    """accum[b] += scale * -sum(log2(likelihood[b])); ``accum``: zero-initialised (B,) fp32."""
+    _require_cuda(likelihood, accum)
+    lk = _sample_contiguous(likelihood)
+    B = lk.shape[0]
+    L.check(L.lib().mmc_image_bits(_ptr(lk), B, lk.numel() // max(B, 1), float(scale), _ptr(accum), _stream()))
+    return accum
+
+
+def image_mse(a: Tensor, b: Tensor, accum: Tensor) -> Tensor:
+    """accum[i] += mean((a[i] - b[i])^2); a, b: same shape and memory format."""
+    _require_cuda(a, b, accum)
+    a, b = _sample_contiguous(a), _sample_contiguous(b)
+    if a.shape != b.shape or a.stride() != b.stride():
+        b = b.contiguous()
+        a = a.contiguous()
+    B = a.shape[0]
+    n = a.numel() // max(B, 1)
+    L.check(L.lib().mmc_image_sse(_ptr(a), _ptr(b), B, n, 1.0 / max(n, 1), _ptr(accum), _stream()))
+    return accum
+
+
 # ---- backward of the transforms ------------------------------------------------------------------------
 def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.0, mask: Optional[Tensor] = None,
           name: str = "conv") -> Tensor:

@@ -302,6 +302,15 @@ MMC_API int mmc_add(const float *a, const float *b, int64_t n, float *out, void 
  *   q: (B, H, W, heads*head_dim) bf16; kv: (B, H, W, 2*heads*head_dim) bf16, keys then values (qkv2's output layout);
  *   bias_table: ((2 ws - 1)^2, heads) fp32 = relative_position_bias_table; out like q.  head_dim must be 32, ws <= 4. */
 /* ---------------------------------------------------------------------------------------------
+ * Per-image rate / distortion of a forward pass, reduced on the device -- the numbers the reference's evaluation loop keeps
+ * (compressai/utils/eval_model/__main__t.py:151-173).  out[b] += scale * (-sum over image b of log2(likelihood)), resp.
+ * out[b] += scale * sum over image b of (a - b)^2; image b is the b-th block of n_per_image consecutive floats (any memory format
+ * in which a sample is contiguous).  `out` must be zeroed by the caller (several likelihood tensors accumulate into it):
+ * bpp = mmc_image_bits(..., scale = 1 / pixels), mse = mmc_image_sse(..., scale = 1 / n_per_image). */
+MMC_API int mmc_image_bits(const float *likelihood, int B, int64_t n_per_image, float scale, float *out, void *stream);
+MMC_API int mmc_image_sse(const float *a, const float *b, int B, int64_t n_per_image, float scale, float *out, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Non-convolution steps of the ESA gate (ESA.forward, models/google.py:1445-1459) on NHWC bf16 maps.
  * mmc_maxpool_nhwc_bf16: F.max_pool2d(kernel_size=k, stride=stride), no padding; y is (B, (H-k)/stride+1, (W-k)/stride+1, C).
  * mmc_upsample_bilinear_add_bf16: F.interpolate(small, (H, W), mode="bilinear", align_corners=False) + add  (c3 + cf).

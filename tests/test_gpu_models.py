@@ -211,6 +211,39 @@ def test_host_pipeline_matches_device_forward():
         pipe(x.to(dev()))
 
 
+def test_host_pipeline_metrics_mode():
+    """outputs="metrics": per-image bpp and MSE reduced on the device (mmc_image_bits / mmc_image_sse inside the micro-batch
+    graphs) equal the values computed on the host from the full outputs (eval_model/__main__t.py:151-173), incl. the ragged
+    tail micro-batch; the stand-alone kernels against torch on odd sizes and channels-last likelihoods."""
+    import math
+    from mmcodec import ops
+    net, _ = load(mmcodec.ScaleHyperprior, "hyperprior", 128, 192)
+    x = torch.from_numpy(make_image(5, 64, 128, seed=12))
+    with torch.no_grad():
+        ref = net(x.to(dev()))
+    bpp_ref = sum(torch.log(l.double()).flatten(1).sum(1) for l in ref["likelihoods"].values()).cpu() / (-math.log(2) * 64 * 128)
+    mse_ref = ((ref["x_hat"].double().cpu() - x.double()) ** 2).flatten(1).mean(1)
+    pipe = mmcodec.HostPipeline(net, micro_batch=2, outputs="metrics")
+    for _ in range(2):
+        out = pipe(x.pin_memory())
+        torch.cuda.current_stream().synchronize()
+        assert set(out) == {"bpp", "mse"} and tuple(out["bpp"].shape) == (5,)
+        assert float(((out["bpp"].double() - bpp_ref).abs() / bpp_ref).max()) < 1e-4
+        assert float(((out["mse"].double() - mse_ref).abs() / mse_ref).max()) < 1e-4
+    with pytest.raises(ValueError):
+        mmcodec.HostPipeline(net, outputs="everything")
+    gen = torch.Generator().manual_seed(3)
+    lk = (torch.rand(3, 7, 5, 9, generator=gen) * 0.9 + 0.05).to(dev())
+    for t in (lk, lk.contiguous(memory_format=torch.channels_last)):
+        acc = torch.zeros(3, device=dev())
+        ops.image_bits(t, acc, 0.5)
+        want = -0.5 * torch.log2(lk.double()).flatten(1).sum(1)
+        assert float(((acc.double() - want).abs() / want.abs()).max()) < 1e-5
+    a, b = torch.randn(2, 3, 11, 13, generator=gen).to(dev()), torch.randn(2, 3, 11, 13, generator=gen).to(dev())
+    acc = ops.image_mse(a, b, torch.zeros(2, device=dev()))
+    assert float((acc.double() - ((a.double() - b.double()) ** 2).flatten(1).mean(1)).abs().max()) < 1e-5
+
+
 @pytest.mark.parametrize("arch,cls,N,M", ARCHS)
 def test_compress_decompress_round_trip(models_golden, arch, cls, N, M):
     """CompressionModel.compress / decompress (models/google.py:196-205,324-344,393-416): the rANS streams decode to
