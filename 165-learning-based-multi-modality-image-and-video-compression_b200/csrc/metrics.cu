@@ -62,6 +62,20 @@ __global__ void __launch_bounds__(256) image_sse_kernel(const float *__restrict_
     if (threadIdx.x == 0) atomicAdd(out + blockIdx.y, t * scale);
 }
 
+// 8-bit image samples -> fp32 in [0, 1]: torchvision's ToTensor (`img.to(float32).div(255)`, the reference's loader,
+// eval_model/__main__t.py:94-101) moved behind the host->device copy, so that the copy carries one byte per sample instead of four.
+__global__ void __launch_bounds__(256) u8_to_f32_kernel(const uint8_t *__restrict__ x, int64_t n, float *__restrict__ y)
+{
+    const int64_t n4 = n / 4, step = (int64_t)gridDim.x * blockDim.x;
+    const uchar4 *x4 = reinterpret_cast<const uchar4 *>(x);
+    float4 *y4 = reinterpret_cast<float4 *>(y);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const uchar4 v = x4[i];
+        y4[i] = make_float4(__fdiv_rn((float)v.x, 255.0f), __fdiv_rn((float)v.y, 255.0f), __fdiv_rn((float)v.z, 255.0f), __fdiv_rn((float)v.w, 255.0f));
+    }
+    for (int64_t i = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) y[i] = __fdiv_rn((float)x[i], 255.0f);
+}
+
 static int chunks_for(int B, int64_t n)
 {
     int64_t want = (n / 4 + 255) / 256 / 8;                 // ~8 float4 per thread
@@ -93,6 +107,16 @@ int mmc_image_sse(const float *a, const float *b, int B, int64_t n_per_image, fl
     MMC_CHECK_ARG(a && b && out, "mmc_image_sse: NULL buffer");
     image_sse_kernel<<<dim3(chunks_for(B, n_per_image), B), 256, 0, (cudaStream_t)stream>>>(a, b, n_per_image, scale, out);
     MMC_CHECK_LAUNCH("mmc_image_sse");
+    return MMC_OK;
+}
+
+int mmc_u8_to_f32(const void *x, int64_t n, float *y, void *stream)
+{
+    MMC_CHECK_ARG(n >= 0, "mmc_u8_to_f32: n < 0");
+    if (n == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && y && (reinterpret_cast<uintptr_t>(x) & 3u) == 0 && aligned16(y), "mmc_u8_to_f32: NULL or unaligned buffer");
+    u8_to_f32_kernel<<<elementwise_grid(n / 4 > 0 ? n / 4 : 1, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t *)x, n, y);
+    MMC_CHECK_LAUNCH("mmc_u8_to_f32");
     return MMC_OK;
 }
 

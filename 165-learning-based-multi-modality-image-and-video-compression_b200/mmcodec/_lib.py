@@ -73,6 +73,7 @@ _PROTOS = {
     "mmc_layernorm_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_vp]),
     "mmc_gelu_bf16": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "mmc_image_bits": (c_int, [c_vp, c_int, c_i64, c_f32, c_vp, c_vp]),
+    "mmc_u8_to_f32": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "mmc_image_sse": (c_int, [c_vp, c_vp, c_int, c_i64, c_f32, c_vp, c_vp]),
     "mmc_conv3x3_mean_workspace": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "mmc_conv3x3_mean": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp]),

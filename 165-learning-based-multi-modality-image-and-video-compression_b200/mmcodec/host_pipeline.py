@@ -47,6 +47,7 @@ class HostPipeline:
         self.s_run = torch.cuda.Stream(self.device)
         self.s_d2h = torch.cuda.Stream(self.device)
         self._slots = None
+        self._u8_slots = None
         self._graphs = None      # per slot: (CUDAGraph, captured output dict) -- no allocator traffic, one launch per micro-batch
         self._out: Optional[Dict[str, Tensor]] = None
 
@@ -60,7 +61,11 @@ class HostPipeline:
             self._param_sig = sig
         if self._slots is None or tuple(self._slots[0].shape) != shape:
             self._slots = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._u8_slots = None
             self._graphs = None
+        if x_host.dtype == torch.uint8 and self._u8_slots is None:
+            # 8-bit images (as decoded from PNG): the copy carries one byte per sample, ToTensor's /255 runs on the device
+            self._u8_slots = [torch.zeros(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
         if self.use_graphs and self._graphs is None:
             graphs = []
             with torch.cuda.stream(self.s_run), torch.no_grad():
@@ -97,11 +102,16 @@ class HostPipeline:
             return self._forward(self._slots[k][:n]), False       # ragged tail micro-batch: eager launches
 
     def __call__(self, x_host: Tensor, out: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
-        """x_host: (B, C, H, W) fp32 host tensor (pinned for asynchronous copies).  Returns / fills
+        """x_host: (B, C, H, W) fp32 host tensor (pinned for asynchronous copies), or uint8 (8-bit samples, converted on the
+        device exactly as torchvision's ToTensor does on the host).  Returns / fills
         {"x_hat": (B,C,H,W), "likelihoods": {name: (B,C',H',W')}} pinned host tensors, or, with outputs="metrics",
         {"bpp": (B,), "mse": (B,)} pinned host tensors."""
         if x_host.is_cuda:
             raise ValueError("HostPipeline takes host tensors; call the model directly for device tensors")
+        if x_host.dtype not in (torch.float32, torch.uint8):
+            raise TypeError("HostPipeline takes fp32 images in [0, 1] or uint8 images (converted as ToTensor does: / 255)")
+        from . import ops
+        as_u8 = x_host.dtype == torch.uint8
         B = x_host.shape[0]
         slots, mb = self._buffers(x_host)
         caller = torch.cuda.current_stream(self.device)
@@ -122,13 +132,15 @@ class HostPipeline:
             with torch.cuda.stream(self.s_h2d):
                 if slot_free[k] is not None:
                     self.s_h2d.wait_event(slot_free[k])
-                slots[k][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                (self._u8_slots if as_u8 else slots)[k][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_h2d)
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(ev_in)
                 if out_free[k] is not None:
                     self.s_run.wait_event(out_free[k])
+                if as_u8:
+                    ops.u8_to_f32(self._u8_slots[k][: hi - lo], out=slots[k][: hi - lo])
                 o, static = self._run(k, hi - lo)
                 ev_run = torch.cuda.Event()
                 ev_run.record(self.s_run)

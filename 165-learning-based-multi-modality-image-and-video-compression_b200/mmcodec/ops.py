@@ -672,6 +672,19 @@ def image_mse(a: Tensor, b: Tensor, accum: Tensor) -> Tensor:
     return accum
 
 
+def u8_to_f32(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """uint8 image samples -> fp32 / 255 (ToTensor), into ``out`` if given (contiguous fp32 of the same shape)."""
+    _require_cuda(x)
+    if x.dtype != torch.uint8 or not x.is_contiguous():
+        raise TypeError("u8_to_f32: expected a contiguous uint8 tensor")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.shape != x.shape:
+        raise TypeError("u8_to_f32: out must be a contiguous fp32 tensor of the same shape")
+    L.check(L.lib().mmc_u8_to_f32(_ptr(x), x.numel(), _ptr(out), _stream()))
+    return out
+
+
 # ---- backward of the transforms ------------------------------------------------------------------------
 def wgrad(s_nhwc: Tensor, l_nhwc: Tensor, k: int, stride: int, scale: float = 1.0, mask: Optional[Tensor] = None,
           name: str = "conv") -> Tensor:

@@ -435,18 +435,19 @@ def main():
         #      micro-batches overlap.  Headline e2e = what the reference's evaluation loop keeps of a forward (per-image bpp and
         #      MSE -> PSNR, eval_model/__main__t.py:151-173), reduced on the device inside the same CUDA graph and read back
         #      (8 bytes per image); `e2e_full_outputs` = the same call returning x_hat + likelihoods to pinned host memory. ----
-        e2e_full = None
+        e2e_full = e2e_u8 = None
         if call == "forward":
-            def time_pipe(pipe):
-                pipe(x_host)
+            def time_pipe(pipe, x_in=None):
+                x_in = x_host if x_in is None else x_in
+                pipe(x_in)
                 torch.cuda.synchronize()
                 for _ in range(2):
-                    pipe(x_host)
+                    pipe(x_in)
                 barrier()
                 f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 f0.record()
                 for _ in range(args.steps):
-                    r_ = pipe(x_host)
+                    r_ = pipe(x_in)
                 f1.record()
                 barrier()
                 return f0.elapsed_time(f1), r_
@@ -463,6 +464,12 @@ def main():
                 raise SystemExit(f"metrics-mode e2e disagrees with the full-output e2e: bpp {e2e_bpp} vs {full_bpp}, mse {e2e_mse} vs {full_mse}")
             d2h = (res["bpp"].numel() + res["mse"].numel()) * 4
             e2e_api = f'mmcodec.HostPipeline(net, micro_batch={args.micro_batch}, outputs="metrics")(x_pinned) -> per-image bpp, mse'
+            # for the record (NOT the headline: different input data): the same call fed with 8-bit images, as an image loader
+            # decodes them -- one byte per sample over PCIe, ToTensor's /255 on the device
+            x_u8 = (x_host * 255).round().to(torch.uint8).pin_memory()
+            ms_u8, res_u8 = time_pipe(mmcodec.HostPipeline(net, micro_batch=args.micro_batch, outputs="metrics"), x_u8)
+            e2e_u8 = {"ms_per_step": ms_u8 / args.steps, "h2d_bytes_per_step": x_u8.numel(), "d2h_bytes_per_step": d2h,
+                      "bpp": float(res_u8["bpp"].mean()), "input": "uint8 host images (synthetic images rounded to 8 bits), converted on the device"}
         else:
             # symbol / compress path: pinned host images in, int32 symbols+indexes (or rANS byte strings) on the host out
             x_dev = torch.empty_like(x)
@@ -504,12 +511,14 @@ def main():
         torch.cuda.synchronize()
         layer_prof = ops.stop_profile(with_work=True)
 
-    t = torch.tensor([ms_total, ms_e2e, e2e_full["ms_per_step"] if e2e_full else 0.0], device=dev)
+    t = torch.tensor([ms_total, ms_e2e, e2e_full["ms_per_step"] if e2e_full else 0.0, e2e_u8["ms_per_step"] if e2e_u8 else 0.0], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = float(t[0]), float(t[1])
     if e2e_full:
         e2e_full["ms_per_step"] = float(t[2])
+    if e2e_u8:
+        e2e_u8["ms_per_step"] = float(t[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -551,6 +560,10 @@ def main():
         e2e_full["value"] = B * world / (e2e_full["ms_per_step"] * 1e-3)
         e2e_full["unit"] = UNIT
         line["e2e_full_outputs"] = e2e_full
+    if e2e_u8:
+        e2e_u8["value"] = B * world / (e2e_u8["ms_per_step"] * 1e-3)
+        e2e_u8["unit"] = UNIT
+        line["e2e_uint8_input"] = e2e_u8
     if world == 1 and not args.no_cpu_baseline:
         with contextlib.redirect_stdout(io.StringIO()):
             v, ms, cores, cpu_bpp = cpu_reference_throughput(2, 3, 1)

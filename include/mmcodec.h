@@ -307,6 +307,9 @@ MMC_API int mmc_add(const float *a, const float *b, int64_t n, float *out, void 
  * out[b] += scale * sum over image b of (a - b)^2; image b is the b-th block of n_per_image consecutive floats (any memory format
  * in which a sample is contiguous).  `out` must be zeroed by the caller (several likelihood tensors accumulate into it):
  * bpp = mmc_image_bits(..., scale = 1 / pixels), mse = mmc_image_sse(..., scale = 1 / n_per_image). */
+/* y = x / 255 for 8-bit image samples (torchvision ToTensor, the reference's image loader eval_model/__main__t.py:94-101), bit-exact
+ * with `img.to(torch.float32).div(255)`: lets the host->device copy carry the decoded 8-bit image instead of its fp32 expansion. */
+MMC_API int mmc_u8_to_f32(const void *x, int64_t n, float *y, void *stream);
 MMC_API int mmc_image_bits(const float *likelihood, int B, int64_t n_per_image, float scale, float *out, void *stream);
 MMC_API int mmc_image_sse(const float *a, const float *b, int B, int64_t n_per_image, float scale, float *out, void *stream);
 

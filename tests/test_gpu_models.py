@@ -232,6 +232,18 @@ def test_host_pipeline_metrics_mode():
         assert float(((out["mse"].double() - mse_ref).abs() / mse_ref).max()) < 1e-4
     with pytest.raises(ValueError):
         mmcodec.HostPipeline(net, outputs="everything")
+    # 8-bit host images: the device-side /255 is bit-exact with ToTensor's, so both input formats give identical results
+    x8 = (x * 255).round().to(torch.uint8)
+    xf = x8.to(torch.float32).div(255)
+    assert torch.equal(ops.u8_to_f32(x8.to(dev())).cpu(), xf)
+    full = mmcodec.HostPipeline(net, micro_batch=2)
+    o8 = {k: (v.clone() if torch.is_tensor(v) else {n: t.clone() for n, t in v.items()}) for k, v in full(x8.pin_memory()).items()}
+    torch.cuda.synchronize()
+    of = full(xf.pin_memory())
+    torch.cuda.synchronize()
+    assert torch.equal(o8["x_hat"], of["x_hat"]) and all(torch.equal(o8["likelihoods"][n], of["likelihoods"][n]) for n in of["likelihoods"])
+    with pytest.raises(TypeError):
+        full(x.double().pin_memory())
     gen = torch.Generator().manual_seed(3)
     lk = (torch.rand(3, 7, 5, 9, generator=gen) * 0.9 + 0.05).to(dev())
     for t in (lk, lk.contiguous(memory_format=torch.channels_last)):
