@@ -205,13 +205,34 @@ class PatchEmbed(nn.Module):
         w = self.proj.weight
         return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
 
+    def _as_3x3(self) -> nn.Module:
+        """The 2x2 stride-2 projection as a 3x3 stride-2 padding-1 layer whose first kernel row and column are zero
+        (out[i] = w[1] x[2i] + w[2] x[2i+1]): the tensor-core conv reads the NHWC map in place, no space-to-depth copy.
+        Not a registered child (the state_dict is the reference's); refreshed when ``proj`` changes."""
+        m = getattr(self, "_alias3", None)
+        if m is None or m.weight.device != self.proj.weight.device:
+            m = conv(self.in_chans, self.embed_dim, kernel_size=3, stride=2).to(self.proj.weight.device)
+            m.requires_grad_(False)
+            m._mmc_name = getattr(self.proj, "_mmc_name", "patch_embed")
+            object.__setattr__(self, "_alias3", m)
+        key = (self.proj.weight._version, self.proj.weight.data_ptr(), self.proj.bias._version)
+        if getattr(self, "_alias3_key", None) != key:
+            with torch.no_grad():
+                m.weight.copy_(F.pad(self.proj.weight.detach(), (1, 0, 1, 0)))
+                m.bias.copy_(self.proj.bias.detach())
+            self._alias3_key = key
+        return m
+
     def forward_grid(self, x: Tensor) -> Tensor:
         """NHWC bf16 map -> (B, H/p, W/p, E) bf16 token grid."""
         B, H, W, C = x.shape
         self._check(H, W)
         p, q = self.patch_size
+        on_kernels = attention_on_kernels and not torch.is_grad_enabled()
+        if on_kernels and (p, q) == (2, 2) and H % 2 == 0 and W % 2 == 0 and self.norm is None:
+            return run_layers([self._as_3x3()], x, "nhwc_bf16", "nhwc_bf16")
         patches = x.reshape(B, H // p, p, W // q, q, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H // p, W // q, p * q * C)
-        if attention_on_kernels and not torch.is_grad_enabled():
+        if on_kernels:
             d = ops.conv_desc(False, B, H // p, W // q, p * q * C, self.embed_dim, 1, 1, L.BF16, L.NHWC, L.BF16, L.NHWC)
             key = (self.proj.weight._version, self.proj.weight.data_ptr())
             if getattr(self, "_pack_key", None) != key:
@@ -376,23 +397,30 @@ class Spatial_aligner(nn.Module):
         self.recovery = nn.ConvTranspose2d(96, out_channel, kernel_size=2, stride=2)
 
     def _recover(self, tok: Tensor, B: int, H: int, W: int) -> Tensor:
-        """(B, h, w, 96) token grid -> NHWC bf16 (B, H, W, out): the reference's reinterpretation, then the 2x2 s2 deconv as a
-        per-pixel matrix product followed by depth-to-space."""
+        """(B, h, w, 96) token grid -> NHWC bf16 (B, H, W, out): the reference's reinterpretation, then the 2x2 s2 deconv (on the
+        transposed-conv kernel in inference; as a per-pixel matrix product followed by depth-to-space under autograd)."""
         E, h, w = self.embed_dim, H // 2, W // 2
         grid = tok.reshape(B, E, h * w).transpose(1, 2).reshape(B, h, w, E)    # memory reinterpreted as NCHW, then made NHWC
         wt = self.recovery.weight                                                 # (E, O, 2, 2)
         O = wt.shape[1]
         if attention_on_kernels and not torch.is_grad_enabled():
-            d = ops.conv_desc(False, B, h, w, E, 4 * O, 1, 1, L.BF16, L.NHWC, L.BF16, L.NHWC)
+            # the 2x2 stride-2 transposed conv as a 3x3 stride-2 one with kernel row / column 0 zero (out[2i + d] = x[i] w[1 + d]):
+            # the transposed-conv kernel writes the full-resolution NHWC map directly, no depth-to-space copy
+            m = getattr(self, "_recovery3", None)
+            if m is None or m.weight.device != wt.device:
+                m = deconv(E, O, kernel_size=3, stride=2).to(wt.device)
+                m.requires_grad_(False)
+                m._mmc_name = getattr(self.recovery, "_mmc_name", "recovery")
+                object.__setattr__(self, "_recovery3", m)
             key = (wt._version, wt.data_ptr(), self.recovery.bias._version)
-            if getattr(self, "_pack_key", None) != key:
-                mat = wt.detach().permute(2, 3, 1, 0).reshape(4 * O, E, 1, 1).contiguous()
-                self._pack = (ops.conv_pack_weights(d, mat), self.recovery.bias.detach().float().repeat(4).contiguous())
-                self._pack_key = key
-            out = ops.conv_forward_tc(d, grid.contiguous(), self._pack[0], self._pack[1], name=getattr(self.recovery, "_mmc_name", "recovery"))
-        else:
-            mat = wt.permute(2, 3, 1, 0).reshape(4 * O, E)
-            out = F.linear(grid, mat.to(grid.dtype), self.recovery.bias.repeat(4).to(grid.dtype))
+            if getattr(self, "_recovery3_key", None) != key:
+                with torch.no_grad():
+                    m.weight.copy_(F.pad(wt.detach(), (1, 0, 1, 0)))
+                    m.bias.copy_(self.recovery.bias.detach())
+                self._recovery3_key = key
+            return run_layers([m], grid.contiguous(), "nhwc_bf16", "nhwc_bf16")
+        mat = wt.permute(2, 3, 1, 0).reshape(4 * O, E)
+        out = F.linear(grid, mat.to(grid.dtype), self.recovery.bias.repeat(4).to(grid.dtype))
         return out.reshape(B, h, w, 2, 2, O).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, O)
 
     def forward_nhwc(self, x: Tensor, guided: Tensor) -> Tensor:
