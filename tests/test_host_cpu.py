@@ -304,3 +304,34 @@ def test_training_glue_on_cpu():
     n_main = sum(len(g["params"]) for g in opt.param_groups)
     n_aux = sum(len(g["params"]) for g in aux.param_groups)
     assert n_aux == 1 and n_main + n_aux == len(list(net.parameters()))
+
+
+def test_fusion_model_mirrors_state_dict_contract_on_cpu():
+    """Host-side mirrors of the fork's own models are constructible without a GPU and expose exactly the reference's state_dict
+    (keys; shapes except the data-dependent CDF buffers) -- compared with the lists the golden generators recorded from the
+    reference itself: Master_compresser (master.py:837-902), Guided_compresser (:1215-1268), mbt2018 (google.py:421-497)."""
+    from oracle import torch_port as tp
+    golden = os.path.join(ROOT, "tests", "golden")
+    data_dependent = ("_offset", "_quantized_cdf", "_cdf_length", "scale_table")
+    cases = (("models_master.npz", lambda: mmcodec.Master_compresser(width=64, height=128, channel=3)),
+             ("models_guided.npz", lambda: mmcodec.Guided_compresser(channel=1)),
+             ("models_mbt2018.npz", lambda: mmcodec.build_model("mbt2018", 3)))
+    for fname, make in cases:
+        ref = {k: tuple(v[0]) for k, v in json.loads(str(np.load(os.path.join(golden, fname))["state_dict"])).items()}
+        net = make()
+        mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        assert set(mine) == set(ref), (fname, sorted(set(mine) ^ set(ref))[:5])
+        assert all(mine[k] == ref[k] for k in ref if not k.endswith(data_dependent)), fname
+    # the attention buffers the reference registers (master.py:512-522, 625-643) equal the restatement's closed forms
+    net = mmcodec.Master_compresser(width=64, height=128, channel=3)
+    blk = net.decoder.sp_aligner3.blocks[1]                      # tokens 16 x 32, window 4, shift 2
+    assert blk.shift_size == 2 and torch.equal(blk.attn.relative_position_index, tp.relative_position_index(4))
+    assert torch.equal(blk.attn_mask, tp.shift_attention_mask(16, 32, 4, 2))
+    assert net.decoder.sp_aligner1.blocks[1].shift_size == 0      # 4 x 8 tokens: min(resolution) <= window -> no shift (master.py:601-603)
+    assert "attn_mask" not in dict(net.decoder.sp_aligner1.blocks[1].named_buffers())
+    one = mmcodec.Master_compresser(width=64, height=64, channel=1)   # 1-channel master: extra downsample convs, swapped strides
+    assert {"decoder.downsample1.weight", "decoder.downsample3.bias"} <= set(one.state_dict())
+    assert one.fencoder1.conv1.stride == (1, 1) and one.fencoder2.conv1.stride == (2, 2) and one.fdecoder.deconv1.stride == (1, 1)
+    # and there is no CPU execution path
+    with pytest.raises((RuntimeError, mmcodec.MmcodecError)):
+        net.eval()(torch.zeros(1, 3, 128, 256), torch.zeros(1, 1, 64, 128), {k: torch.zeros(1, 192, 8 * 2 ** i, 16 * 2 ** i) for i, k in enumerate(("gs1", "gs2", "gs3"))})
