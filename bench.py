@@ -166,6 +166,45 @@ def init_nccl_quietly(dist, dev):
         os.close(saved)
 
 
+def reference_pair_forward(args, world):
+    """Reference arm of the pair workloads: the reference's own CPU execution path (stock torch ops, restated in oracle/torch_port.py
+    and pinned to the reference's outputs by tests/golden) on all host threads, ONE pair per step (a bounded sample of the workload)."""
+    import torch
+    import mmcodec
+    from oracle import torch_port as tp
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(1234)
+    as_sd = lambda net: {k: v.detach().float() for k, v in net.state_dict().items()}
+    if args.workload == "mm-forward":
+        sd_r, sd_d = as_sd(mmcodec.JointAutoregressiveHierarchicalPriors_R(192, 192)), as_sd(mmcodec.JointAutoregressiveHierarchicalPriors_D(192, 192))
+        x, d = torch.rand(1, 3, 512, 768, generator=gen), torch.rand(1, 1, 512, 768, generator=gen)
+        step = lambda: tp.mm_d_forward(sd_d, d, tp.mm_r_forward(sd_r, x)["hidden"])
+    else:
+        sd_g, sd_m = as_sd(mmcodec.Guided_compresser(channel=1)), as_sd(mmcodec.Master_compresser(width=256, height=384, channel=3))
+        x, t = torch.rand(1, 3, 512, 768, generator=gen), torch.rand(1, 1, 256, 384, generator=gen)
+
+        def step():
+            og = tp.mm_r_forward(sd_g, t)
+            return tp.master_forward(sd_m, x, og["x_hat"], og["hidden"])
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 1))):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps)):
+            step()
+        dt = time.perf_counter() - t0
+    steps = max(1, args.steps)
+    v = steps / dt
+    return {"impl": "reference", "metric": f"pairs/s ({args.workload})", "value": v, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": OTHER_WORKLOADS[args.workload], "units_per_gpu": 1, "weights": "random init", "parallelism": f"one process, {cores} host threads"},
+            "cpu_baseline": {"value": v, "unit": "img/s", "cores": cores, "kind": "port", "sample": f"{steps} steps of ONE pair (same models / resolution), torch CPU ops on {cores} threads"},
+            "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def bench_other(args):
     """For-the-record lines of the GOP / pair workloads (same timing rules; not the driver's headline run)."""
     import torch
@@ -176,7 +215,10 @@ def bench_other(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable": f"reference arm is implemented for the image workloads only, not {args.workload}"}))
+            if args.workload in ("mm-forward", "master-forward"):
+                print(json.dumps(reference_pair_forward(args, world)))
+            else:
+                print(json.dumps({"impl": "reference", "unavailable": f"reference arm is implemented for the forward workloads only, not {args.workload}"}))
         return
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
