@@ -1,10 +1,14 @@
-// attention.cu -- the token-side kernels of Spatial_aligner (compressai/models/master.py:484-742): LayerNorm (optionally
-// fused with the residual add in front of it), GELU, and the windowed multi-head cross-attention itself.
+// attention.cu -- the kernels of the RGB-T master codec that are not convolutions (compressai/models/master.py):
+//   * token side of Spatial_aligner (master.py:484-742): LayerNorm (optionally fused with the residual add in front of it), GELU, and
+//     the windowed multi-head cross-attention itself;
+//   * Channel_aligner tail (master.py:193-210): global average of a head (two-pass, fixed order), the same average obtained by
+//     linearity from border-corrected channel sums of the trunk output (mmc_conv3x3_mean: no convolution at all), and the
+//     per-sample affine gamma * guide + beta.
 //
-// The Linear layers of the block are per-token, so they run as 1x1 tensor-core convolutions on the un-shifted, un-partitioned
-// (B, H, W, C) token grid; this file holds what is left.  All three kernels are HBM-bound at a few bytes per element and the
-// token grids are small (<= 128 x 192 tokens of 96 channels for a 512 x 768 master image), so the design goal is one pass over
-// the data with coalesced 64-byte head slices, not arithmetic throughput.
+// The Linear layers of the attention block are per-token, so they run as 1x1 tensor-core convolutions on the un-shifted,
+// un-partitioned (B, H, W, C) token grid; this file holds what is left.  Everything here is HBM / L2-bound at a few bytes per element
+// and the token grids are small (<= 128 x 192 tokens of 96 channels per 512 x 768 master image), so the design goal is one pass over
+// the data with coalesced vector accesses, not arithmetic throughput.
 //
 //   window_attention_kernel: one warp per (window, head).  The cyclic shift (torch.roll by -shift, master.py:664-668), the
 //   window partition (master.py:431-443) and their inverses are index arithmetic on the loads / stores; the relative-position

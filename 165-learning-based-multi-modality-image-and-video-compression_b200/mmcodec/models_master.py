@@ -18,7 +18,7 @@ stay on the kernels through mmcodec.autograd.  ``compress`` / ``decompress`` (se
 """
 from __future__ import annotations
 
-from typing import Dict, Tuple
+from typing import Dict
 
 import torch
 import torch.nn as nn
@@ -27,7 +27,7 @@ from torch import Tensor
 
 from . import _lib as L
 from . import ops
-from .layers import GDN, Conv2d, ConvTranspose2d, conv, deconv
+from .layers import GDN, conv, deconv
 from .models import MeanScaleHyperprior, _nhwc_to_logical
 from .models_mm import _ContextModelMixin, _to_nhwc_bf16
 from .transforms import TransformStack, run_layers
