@@ -28,7 +28,7 @@ import torch.nn as nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from weights import make_image, make_master_state_dict, make_mbt2018_state_dict, make_mm_state_dict, make_ssf_state_dict, make_state_dict  # noqa: E402
+from weights import make_image, make_master1_inputs, make_master_state_dict, make_mbt2018_state_dict, make_mm_state_dict, make_ssf_state_dict, make_state_dict  # noqa: E402
 
 REF_SRC = "/root/reference/CompressAI"
 SCRATCH = os.environ.get("MMC_REF_SCRATCH", "/tmp/ref_probe")
@@ -465,6 +465,27 @@ def mbt2018_goldens(out):
           "floor", float((o["likelihoods"]["y"] <= 1.0001e-9).float().mean()), "x_hat", float(o["x_hat"].min()), float(o["x_hat"].max()))
 
 
+def master1_goldens(out):
+    """Master_compresser(channel=1) (master.py:840-850: 1-channel master at stride 1, 3-channel guide at stride 2, guide maps
+    brought to the decoder's resolutions by decoder.downsample1-3, master.py:765-768,783-786): eval forward on seeded inputs."""
+    import json
+    from compressai.models.master import Master_compresser
+    x, g_hat, hidden = make_master1_inputs(10)
+    torch.manual_seed(0)
+    net = quiet(Master_compresser, width=64, height=64, channel=1).eval()
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    load_into(net, make_master_state_dict(shapes, 5))
+    quiet(net.update, force=True)
+    out["state_dict"] = np.array(json.dumps({k: [list(v.shape), str(v.dtype)] for k, v in net.state_dict().items()}))
+    with torch.no_grad():
+        o = quiet(net, torch.from_numpy(x), torch.from_numpy(g_hat), {k: torch.from_numpy(v) for k, v in hidden.items()})
+    out["x_hat"] = t2n(o["x_hat"])
+    for k, v in o["likelihoods"].items():
+        out[f"lik_{k}"] = t2n(v)
+    print("master1 x_hat", float(o["x_hat"].min()), float(o["x_hat"].max()),
+          {k: float(torch.log2(v).sum() / -(64 * 64)) for k, v in o["likelihoods"].items()})
+
+
 def color_goldens(out):
     """compressai.transforms.functional on a random frame (the reference's own functions)."""
     from compressai.transforms.functional import rgb2ycbcr, ycbcr2rgb, yuv_420_to_444, yuv_444_to_420
@@ -479,9 +500,9 @@ def color_goldens(out):
 def main():
     import_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
-    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color", "models_guided", "models_master", "models_mbt2018"]
+    which = sys.argv[1:] or ["kernels", "models", "models_mm", "models_ssf", "color", "models_guided", "models_master", "models_mbt2018", "models_master1"]
     gens = {"kernels": kernel_goldens, "models": model_goldens, "models_mm": mm_goldens, "models_ssf": ssf_goldens, "color": color_goldens,
-            "models_guided": guided_goldens, "models_master": master_goldens, "models_mbt2018": mbt2018_goldens}
+            "models_guided": guided_goldens, "models_master": master_goldens, "models_mbt2018": mbt2018_goldens, "models_master1": master1_goldens}
     for name in which:
         d = {}
         gens[name](d)

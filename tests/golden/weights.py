@@ -248,3 +248,16 @@ def make_mbt2018_state_dict(shapes, seed: int = 0):
     sd["entropy_parameters.4.bias"][:M] += 2.0
     sd["entropy_parameters.4.weight"][M:] *= 0.25
     return sd
+
+
+def make_master1_inputs(seed: int = 10):
+    """Inputs of the 1-channel-master golden (regenerated from the seed on both sides, not stored): 1 x 64 x 64 master image,
+    3 x 128 x 128 decoded guide, and guide hidden maps gs1..gs3 at twice the master decoder's resolutions (bf16-representable)."""
+    rs = np.random.RandomState(seed)
+    x = make_image(1, 64, 64, seed=seed + 1, C=1)
+    g_hat = make_image(1, 128, 128, seed=seed + 2, C=3)
+    hidden = {}
+    for k, r in (("gs1", 16), ("gs2", 32), ("gs3", 64)):
+        v = (rs.standard_normal((1, 192, r, r)) * 0.5).astype(np.float32)
+        hidden[k] = (v.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)      # truncate to bf16-representable values
+    return x, g_hat, hidden

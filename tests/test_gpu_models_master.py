@@ -279,6 +279,28 @@ def test_one_channel_master_variant():
     assert rel_rms(o["x_hat"].float(), ref["x_hat"]) < 0.1
 
 
+def test_one_channel_master_vs_reference_golden():
+    """Master_compresser(channel=1) against the reference's own run (tests/golden/models_master1.npz, seeded inputs)."""
+    from weights import make_master1_inputs
+    g1 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_master1.npz"))
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(g1["state_dict"])).items()}
+    sd = {k: torch.from_numpy(v) for k, v in make_master_state_dict(shapes, 5).items()}
+    net = mmcodec.Master_compresser(width=64, height=64, channel=1).eval()
+    assert set(net.state_dict()) == set(shapes)
+    net.update()
+    net.load_state_dict({**net.state_dict(), **sd})
+    net.update(force=True)
+    net = net.to(dev())
+    x, g_hat, hidden = make_master1_inputs(10)
+    with torch.no_grad():
+        o = net(torch.from_numpy(x).to(dev()), torch.from_numpy(g_hat).to(dev()), {k: torch.from_numpy(v).to(dev()) for k, v in hidden.items()})
+    assert tuple(o["x_hat"].shape) == g1["x_hat"].shape
+    npix = 64 * 64
+    ref_bpp = sum(oracle.bits(g1[f"lik_{k}"]) for k in o["likelihoods"]) / npix
+    assert abs(bpp_of(o["likelihoods"], npix) - ref_bpp) / ref_bpp < 0.05
+    assert rel_rms(o["x_hat"].float(), torch.from_numpy(g1["x_hat"])) < 0.15
+
+
 def test_training_step_gradients(g, setup):
     """Training-mode forward + backward (examples/train.py:208-274: master loss = lambda * MSE + bpp): every parameter
     on the forward path receives a finite gradient; the unused inherited ``g_s`` does not; the

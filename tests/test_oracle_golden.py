@@ -324,3 +324,23 @@ def test_torch_port_mbt2018():
     assert np.max(np.abs(o["x_hat"].numpy() - g["x_hat"])) < 2e-4 * max(1.0, float(np.abs(g["x_hat"]).max()))
     for k, l in o["likelihoods"].items():
         assert rel_err(l.numpy(), g[f"lik_{k}"], 1e-9) < 1e-3, k
+
+
+def test_torch_port_master_compresser_one_channel_variant():
+    """Master_compresser(channel=1) (swapped strides, decoder.downsample1-3): the port reproduces the reference run on seeded inputs."""
+    import json
+    import os
+    from weights import make_master1_inputs, make_master_state_dict
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "models_master1.npz"))
+    shapes = {k: tuple(v[0]) for k, v in json.loads(str(g["state_dict"])).items()}
+    assert "decoder.downsample2.weight" in shapes and shapes["fencoder1.conv1.weight"][1] == 1 and shapes["fencoder2.conv1.weight"][1] == 3
+    sd = {k: torch.from_numpy(v) for k, v in make_master_state_dict(shapes, 5).items()}
+    sd["context_prediction.mask"] = tp.masked_conv_mask(shapes["context_prediction.weight"], "A")
+    x, g_hat, hidden = make_master1_inputs(10)
+    torch.set_num_threads(8)
+    with torch.no_grad():
+        o = tp.master_forward(sd, torch.from_numpy(x), torch.from_numpy(g_hat), {k: torch.from_numpy(v) for k, v in hidden.items()})
+    assert o["x_hat"].shape == g["x_hat"].shape
+    assert np.max(np.abs(o["x_hat"].numpy() - g["x_hat"])) < 2e-4 * max(1.0, float(np.abs(g["x_hat"]).max()))
+    for k, l in o["likelihoods"].items():
+        assert rel_err(l.numpy(), g[f"lik_{k}"], 1e-9) < 1e-3, k
