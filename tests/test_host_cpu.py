@@ -335,3 +335,21 @@ def test_fusion_model_mirrors_state_dict_contract_on_cpu():
     # and there is no CPU execution path
     with pytest.raises((RuntimeError, mmcodec.MmcodecError)):
         net.eval()(torch.zeros(1, 3, 128, 256), torch.zeros(1, 1, 64, 128), {k: torch.zeros(1, 192, 8 * 2 ** i, 16 * 2 ** i) for i, k in enumerate(("gs1", "gs2", "gs3"))})
+
+
+def test_bench_reference_arm_of_the_pair_workloads():
+    """bench.py --impl reference for the RGB-T pair workload: runs the CPU port (no GPU, no /root/reference), prints ONE JSON line
+    with the contract's keys; the training workloads report `unavailable` and exit 0."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "master-forward", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "img/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "master-train"],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "unavailable" in json.loads(r.stdout.strip().splitlines()[-1])
