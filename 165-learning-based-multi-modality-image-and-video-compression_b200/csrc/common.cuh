@@ -1,6 +1,7 @@
 // common.cuh -- shared helpers for libmmcodec (sm_100a only).
 #pragma once
 
+#include <atomic>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -50,6 +51,21 @@ void count_launch(int n = 1);
             return MMC_ECUDA;                                                           \
         }                                                                               \
     } while (0)
+
+// Per-device launch state (cudaFuncSetAttribute and occupancy queries apply to the CURRENT device only, so anything cached
+// about them is keyed by cudaGetDevice(); plain process-wide statics would leave every device but the first unconfigured).
+// Values are idempotent (every thread computes the same number), so relaxed atomics are all the synchronisation needed.
+constexpr int kMaxDevices = 64;
+template <typename T>
+struct PerDevice {
+    std::atomic<T> v[kMaxDevices];
+    std::atomic<T> &cur()
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) d = 0;
+        return v[d];
+    }
+};
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

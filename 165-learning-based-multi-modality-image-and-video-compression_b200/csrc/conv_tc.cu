@@ -967,13 +967,15 @@ template <int kEpi, int kNCH, bool kPair = false, int kParts = 2>
 static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaStream_t st, const char *name)
 {
     // dynamic shared memory available next to the kernel's static allocation (227 KB per CTA on sm_100)
-    static size_t budget = 0;
+    static PerDevice<size_t> budget_dev;   // one slot per device and per template instantiation
+    size_t budget = budget_dev.cur().load(std::memory_order_relaxed);
     if (budget == 0) {
         cudaFuncAttributes fa;
         MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi, kNCH, kPair, kParts>));
         size_t avail = 227 * 1024 - fa.sharedSizeBytes;
         MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi, kNCH, kPair, kParts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
         budget = avail;
+        budget_dev.cur().store(avail, std::memory_order_relaxed);
     }
     MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
     int stages = (int)((budget - fixed) / stage_bytes);
@@ -1006,12 +1008,14 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.blockDim = dim3(tc_threads(kParts)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
-        static int max_pairs = 0;
+        static PerDevice<int> max_pairs_dev;
+        int max_pairs = max_pairs_dev.cur().load(std::memory_order_relaxed);
         if (max_pairs == 0) {
             cfg.gridDim = dim3(kNumSMs);
             int n = 0;
             MMC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<kEpi, kNCH, kPair, kParts>, &cfg));
             max_pairs = n > 0 ? n : 1;
+            max_pairs_dev.cur().store(max_pairs, std::memory_order_relaxed);
         }
         grid &= ~1;
         if (grid > 2 * max_pairs) grid = 2 * max_pairs;

@@ -910,10 +910,10 @@ int mmc_pmf_to_quantized_cdf(const float *pmf, int64_t pmf_pitch, const float *t
     MMC_CHECK_ARG(pmf && tail_mass && pmf_length && cdf && status, "%s: NULL buffer", name);
     const size_t smem = (size_t)(max_len + 2) * sizeof(uint32_t);
     MMC_UNSUPPORTED(smem > 200 * 1024, "%s: rows longer than %d symbols are not supported", name, 200 * 1024 / 4 - 2);
-    static bool attr = false;
-    if (!attr) {
+    static PerDevice<int> attr_dev;
+    if (!attr_dev.cur().load(std::memory_order_relaxed)) {
         MMC_CHECK_CUDA(cudaFuncSetAttribute(pmf_to_cdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
+        attr_dev.cur().store(1, std::memory_order_relaxed);
     }
     pmf_to_cdf_kernel<<<rows, kCdfThreads, smem, (cudaStream_t)stream>>>(pmf, pmf_pitch, tail_mass, pmf_length, max_len, precision, cdf, status);
     MMC_CHECK_LAUNCH(name);

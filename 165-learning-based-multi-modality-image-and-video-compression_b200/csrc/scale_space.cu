@@ -215,10 +215,10 @@ int mmc_gaussian_volume(const float *x, int64_t planes, int H, int W, const floa
     const int64_t hw = (int64_t)H * W, vstride = (int64_t)D * hw;
     const int span = kBlurTile + 2 * (ksize / 2);
     const size_t blur_smem = ((size_t)span * (span + 1) + (size_t)span * (kBlurTile + 1)) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDevice<int> attr_dev;
+    if (!attr_dev.cur().load(std::memory_order_relaxed)) {
         MMC_CHECK_CUDA(cudaFuncSetAttribute(gaussian_blur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
+        attr_dev.cur().store(1, std::memory_order_relaxed);
     }
     auto blur = [&](const float *src, int h, int w, float *dst, int64_t dst_stride) -> int {
         dim3 grid((unsigned)((w + kBlurTile - 1) / kBlurTile), (unsigned)((h + kBlurTile - 1) / kBlurTile), (unsigned)planes);

@@ -311,13 +311,15 @@ int mmc_wgrad_tc(const void *s_nhwc, const void *l_nhwc, int64_t B, int Cs, int 
         int rc = encode_map(&P.tmL, l_nhwc, 4, dims, str, box, es, "wgrad L");
         if (rc) return rc;
     }
-    static size_t budget = 0;
+    static PerDevice<size_t> budget_dev;
+    size_t budget = budget_dev.cur().load(std::memory_order_relaxed);
     if (budget == 0) {
         cudaFuncAttributes fa;
         MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, wgrad_tc_kernel));
         size_t avail = 227 * 1024 - fa.sharedSizeBytes;
         MMC_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
         budget = avail;
+        budget_dev.cur().store(avail, std::memory_order_relaxed);
     }
     const size_t stage_bytes = (size_t)(2 + P.n_atoms) * kAtomBytes;
     int stages = (int)((budget - 1024) / stage_bytes);

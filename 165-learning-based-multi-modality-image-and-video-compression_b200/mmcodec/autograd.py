@@ -20,7 +20,7 @@ from torch import Tensor
 from . import _lib as L
 from . import ops
 
-__all__ = ["run_layers_train", "eb_forward", "gc_forward", "cast_bf16", "add_noise", "wants_grad"]
+__all__ = ["run_layers_train", "eb_forward", "gc_forward", "gdn_forward", "cast_bf16", "add_noise", "wants_grad"]
 
 
 def wants_grad(layers, x: Tensor) -> bool:
@@ -175,6 +175,37 @@ class _ConvGdnFn(torch.autograd.Function):
         g_pre, dbeta, dgamma = _gdn_backward(ctx.gdn, x_pre, gy.contiguous())
         dx, dw, db = _conv_backward(ctx.conv, x, ctx.in_fmt, g_pre, None, ctx.needs_input_grad[0])
         return dx, dw, db, dbeta.to(ctx.gdn.beta.dtype), dgamma.to(ctx.gdn.gamma.dtype), None, None, None
+
+
+class _GdnFn(torch.autograd.Function):
+    """Stand-alone GDN / IGDN module call (compressai/layers/gdn.py:77-92) on a logical (B, C, H, W) fp32 tensor: forward on the
+    fp32 kernel, backward through the same tensor-core contractions as the fused conv + GDN layers (bf16 operands)."""
+
+    @staticmethod
+    def forward(ctx, x, beta, gamma, gdn):
+        beta_eff, gamma_eff, _ = gdn.effective_params()
+        y = ops.gdn_forward(x, beta_eff, gamma_eff, gdn.inverse)
+        ctx.gdn = gdn
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        gdn = ctx.gdn
+        x_pre = ops.nchw_to_nhwc_bf16(x.float().contiguous())
+        g = ops.nchw_to_nhwc_bf16(gy.float().contiguous())
+        dx, dbeta, dgamma = _gdn_backward(gdn, x_pre, g)
+        return dx.permute(0, 3, 1, 2).float(), dbeta.to(gdn.beta.dtype), dgamma.to(gdn.gamma.dtype), None
+
+
+def gdn_forward(gdn, x: Tensor) -> Tensor:
+    """GDN.forward with autograd when the input or the module's parameters need it."""
+    if torch.is_grad_enabled() and (x.requires_grad or gdn.beta.requires_grad or gdn.gamma.requires_grad):
+        return _GdnFn.apply(x, gdn.beta, gdn.gamma, gdn)
+    beta_eff, gamma_eff, _ = gdn.effective_params()
+    with torch.no_grad():
+        return ops.gdn_forward(x, beta_eff, gamma_eff, gdn.inverse)
 
 
 def run_layers_train(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0):

@@ -277,9 +277,17 @@ class EntropyBottleneck(EntropyModel):
             raise ValueError("EntropyBottleneck expects (N, C, ...) inputs")
         if x.shape[1] != self.channels:
             raise ValueError(f"expected {self.channels} channels, got {x.shape[1]}")
+        if training:
+            # differentiable like the reference's module (rate gradient to the caller's transforms and to the density
+            # parameters): recorded by mmcodec.autograd._EbFn when autograd is on and anything requires grad
+            from . import autograd as AG
+            with torch.no_grad():
+                noise = torch.empty_like(x, dtype=torch.float32).uniform_(-0.5, 0.5)
+            return AG.eb_forward(x, self, noise)
+        # eval mode ("dequantize"): round() has a zero gradient, so nothing flows to the input in the reference either; the
+        # density parameters are not trained in eval mode -- no graph is recorded
         with torch.no_grad():
-            noise = torch.empty_like(x, dtype=torch.float32).uniform_(-0.5, 0.5) if training else None
-            return ops.eb_forward(x, self._params(), noise, self._lik_bound(), lut=None if training else self._eval_lut())
+            return ops.eb_forward(x, self._params(), None, self._lik_bound(), lut=self._eval_lut())
 
     @staticmethod
     def _build_indexes(size, device=None):
@@ -391,9 +399,12 @@ class GaussianConditional(EntropyModel):
             training = self.training
         if inputs.shape != scales.shape:
             raise ValueError("`inputs` and `scales` should have the same size.")
+        from . import autograd as AG
         with torch.no_grad():
             noise = torch.empty_like(inputs, dtype=torch.float32).uniform_(-0.5, 0.5) if training else None
-            return ops.gc_forward(inputs, scales, means, noise, self.lower_bound_scale._sync_bound(), self._lik_bound())
+        # differentiable like the reference's module: mmcodec.autograd._GcFn records the call when autograd is on and inputs /
+        # scales / means require grad (noise mode: gradients to all three; eval mode: to the scales only, round() has none)
+        return AG.gc_forward(inputs, scales, means, noise, self.lower_bound_scale._sync_bound(), self._lik_bound())
 
     def build_indexes(self, scales: Tensor) -> Tensor:
         """entropy_models.py:735-740, one kernel instead of 63 x 3 launches."""

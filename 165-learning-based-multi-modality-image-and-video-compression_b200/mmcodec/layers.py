@@ -113,9 +113,10 @@ class GDN(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         if x.dim() != 4:
             raise ValueError("GDN expects a 4-D (B, C, H, W) tensor")  # `_, C, _, _ = x.size()` in gdn.py:78
-        beta_eff, gamma_eff, _ = self.effective_params()
-        with torch.no_grad():
-            return ops.gdn_forward(x, beta_eff, gamma_eff, self.inverse)
+        # differentiable like the reference's module: with autograd on and a parameter or the input requiring grad the call is
+        # recorded (mmcodec.autograd._GdnFn); otherwise it is the plain forward kernel
+        from . import autograd as AG
+        return AG.gdn_forward(self, x)
 
 
 class _PackedWeightMixin:

@@ -17,10 +17,21 @@ Tensor = torch.Tensor
 
 
 def _require_cuda(*tensors) -> None:
+    """Every kernel is enqueued on the CURRENT device's current stream (see _stream): a tensor that lives on another device
+    would be read through a foreign pointer on the wrong stream, so it is rejected here instead (use torch.cuda.device(...)
+    or torch.cuda.set_device around the call, as for any stream-ordered CUDA library)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("mmcodec runs on CUDA tensors only (B200 / sm_100a); got a CPU tensor. "
                                "There is no CPU fallback.")
+        if cur is None:
+            cur = torch._C._cuda_getDevice()
+        if t.device.index != cur:
+            raise RuntimeError(f"mmcodec: tensor on cuda:{t.device.index} but the current device is cuda:{cur}; "
+                               "wrap the call in torch.cuda.device(tensor.device)")
 
 
 def _ptr(t: Optional[Tensor]):

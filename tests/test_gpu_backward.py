@@ -212,6 +212,76 @@ def test_entropy_bottleneck_backward():
     assert eb.quantiles.grad is not None and eb._matrix0.grad is None
 
 
+def test_module_forwards_are_differentiable_like_the_reference():
+    """EntropyBottleneck / GaussianConditional / GDN module calls made the way the reference's training code makes
+    them (``self.entropy_bottleneck(z)`` inside a custom model, entropy_models.py:495-540,715-731, layers/gdn.py:77-92) carry
+    a graph: rate gradients reach the caller's tensors and the modules' parameters, and match the oracle's autograd."""
+    torch.manual_seed(11)
+    C = 128
+    d = dev()
+    # --- EntropyBottleneck(z) in training mode -------------------------------------------------------------------
+    eb = mmcodec.EntropyBottleneck(C).to(d).train()
+    z = (torch.randn(2, C, 4, 6) * 3).to(d).requires_grad_(True)
+    torch.manual_seed(12)
+    z_hat, lik = eb(z)
+    assert lik.grad_fn is not None and z_hat.grad_fn is not None
+    noise = (z_hat - z).detach()                                   # the draw the module made
+    assert float(noise.abs().max()) <= 0.5
+    torch.log(lik).sum().backward()
+    sd = {f"eb.{k}": v.detach().double().cpu().requires_grad_(True) for k, v in eb.named_parameters()}
+    zr = z.detach().double().cpu().requires_grad_(True)
+    _, lr = tp.eb_forward(sd, "eb", zr, noise=noise.double().cpu())
+    torch.log(lr).sum().backward()
+    assert rel_rms(z.grad, zr.grad) < 2e-3
+    assert eb._matrix0.grad is not None and rel_rms(eb._matrix0.grad, sd["eb._matrix0"].grad) < 5e-3
+    # eval mode: values only (round() has no gradient in the reference either)
+    eb.eval()
+    z_hat_e, lik_e = eb(z)
+    assert z_hat_e.grad_fn is None and lik_e.grad_fn is None
+    # --- GaussianConditional(y, scales, means) -------------------------------------------------------------------
+    gc = mmcodec.GaussianConditional(None).to(d).train()
+    shape = (2, 16, 6, 10)
+    y = (torch.randn(shape) * 4).to(d).requires_grad_(True)
+    scales = torch.exp(torch.empty(shape).uniform_(np.log(0.05), np.log(30.0))).to(d).requires_grad_(True)
+    means = (torch.randn(shape) * 2).to(d).requires_grad_(True)
+    y_hat, lk = gc(y, scales, means)
+    nz = (y_hat - y).detach()
+    torch.log(lk).sum().backward()
+    yr, sr, mr = (t.detach().double().cpu().requires_grad_(True) for t in (y, scales, means))
+    _, lr = tp.gc_forward(yr, sr, mr, noise=nz.double().cpu())
+    torch.log(lr).sum().backward()
+    for mine, ref in ((y.grad, yr.grad), (scales.grad, sr.grad), (means.grad, mr.grad)):
+        assert mine is not None and rel_rms(mine, ref) < 2e-3
+    gc.eval()                                                       # eval mode: the gradient reaches the scales only
+    s2 = scales.detach().clone().requires_grad_(True)
+    _, lk = gc(y.detach(), s2, means.detach())
+    torch.log(lk).sum().backward()
+    sr2 = s2.detach().double().cpu().requires_grad_(True)
+    _, lr = tp.gc_forward(y.detach().double().cpu(), sr2, means.detach().double().cpu())
+    torch.log(lr).sum().backward()
+    assert rel_rms(s2.grad, sr2.grad) < 2e-3
+    # --- stand-alone GDN module ------------------------------------------------------------------------------------
+    for inverse in (False, True):
+        gdn = GDN(C, inverse=inverse).to(d)
+        with torch.no_grad():
+            gdn.gamma.add_(torch.rand_like(gdn.gamma) * 0.02)
+            gdn.beta.add_(torch.rand_like(gdn.beta) * 0.5)
+        x = torch.randn(2, C, 10, 12, device=d).to(torch.bfloat16).float().requires_grad_(True)
+        out = gdn(x)
+        assert out.grad_fn is not None
+        gy = torch.randn_like(out).to(torch.bfloat16).float()
+        out.backward(gy)
+        sdg = {"g.beta": gdn.beta.detach().double().cpu().requires_grad_(True), "g.gamma": gdn.gamma.detach().double().cpu().requires_grad_(True)}
+        xr = x.detach().double().cpu().requires_grad_(True)
+        yr = tp.gdn(sdg, "g", xr, inverse=inverse)
+        assert rel_rms(out.detach(), yr.detach()) < 1e-4
+        yr.backward(gy.double().cpu())
+        assert rel_rms(x.grad, xr.grad) < 3e-2
+        assert rel_rms(gdn.beta.grad, sdg["g.beta"].grad) < 3e-2 and rel_rms(gdn.gamma.grad, sdg["g.gamma"].grad) < 3e-2
+        with torch.no_grad():
+            assert gdn(x).grad_fn is None
+
+
 # ---------------------------------------------------------------------------------------------------------
 # end to end: training-mode forward + backward of the second-modality branch vs the oracle's autograd (fp32 CPU)
 # ---------------------------------------------------------------------------------------------------------

@@ -253,14 +253,17 @@ def test_gdn_golden(kernels_golden):
         m.gamma.data.copy_(torch.from_numpy(g["gdn_gamma"]))
         m = m.to(dev())
         y = m(x)
-        assert rel_err(y.cpu().numpy(), g[key], 1.0) < 1e-5
-        ycl = m(x.to(memory_format=torch.channels_last))
+        assert y.grad_fn is not None          # differentiable module call, as in the reference (parameters require grad)
+        assert rel_err(y.detach().cpu().numpy(), g[key], 1.0) < 1e-5
+        with torch.no_grad():
+            ycl = m(x.to(memory_format=torch.channels_last))
         assert rel_err(ycl.cpu().numpy(), g[key], 1.0) < 1e-5
     # closed form at init: y = x / sqrt(1 + 0.1 x^2) (tests/test_layers.py:145-146,158-159)
     xx = cu(g["gdn_x"])
-    y0 = mmcodec.GDN(16).to(dev())(xx)
+    with torch.no_grad():
+        y0 = mmcodec.GDN(16).to(dev())(xx)
     assert torch.allclose(y0, xx / torch.sqrt(1 + 0.1 * xx ** 2), atol=1e-5)
-    y1 = mmcodec.GDN(16, inverse=True).to(dev())(xx)
+    y1 = mmcodec.GDN(16, inverse=True).to(dev())(xx).detach()
     assert torch.allclose(y1, xx * torch.sqrt(1 + 0.1 * xx ** 2), atol=1e-5)
 
 
@@ -273,7 +276,7 @@ def test_gdn_wide_vs_oracle():
     m = mmcodec.GDN(C)
     m.beta.data.copy_(torch.from_numpy(w["g.beta"]))
     m.gamma.data.copy_(torch.from_numpy(w["g.gamma"]))
-    y = m.to(dev())(cu(x)).cpu().numpy()
+    y = m.to(dev())(cu(x)).detach().cpu().numpy()
     assert rel_err(y, oracle.gdn_forward(x, w["g.beta"], w["g.gamma"]), 1e-2) < 1e-4
 
 
