@@ -78,6 +78,7 @@ struct TcParams {
     int num_stages, acc_stages;
     int a_tmem;       // GDN: the x^2 operand of the norm contraction lives in TMEM (A-from-TMEM MMA), not in shared memory
     int bias_mma;     // the bias enters the accumulator through a constant-operand MMA (one N block per tile), not in the epilogue
+    int late_release; // GDN epilogue: the accumulator stage is handed back by the thread that issues the norm MMAs, after issuing them
     int direct_store; // GDN epilogue: 32-byte vector stores straight from registers instead of the shared-memory staged copy-out
     int debug;       // profiling aid (env MMC_TC_DEBUG): 1 = no TMA traffic after priming, 2 = no main-loop MMAs, 3 = no GDN MMAs
     int pair;        // 1: CTA-pair kernel (cta_group::2): two adjacent tiles per MMA, each CTA holds half of the B rows
@@ -298,10 +299,14 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
     }
     if (P.a_tmem) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
-    // x is in registers (and x^2 staged): the conv accumulator can go back to the MMA warp already
+    // x is in registers (and x^2 staged): the conv accumulator can go back to the MMA warp -- but only AFTER the norm MMAs below
+    // have been issued (P.late_release).  The tensor pipe executes in issue order: handing the accumulator back first (one arrival
+    // per warp, right here) lets the MMA warp queue the whole main loop of the tile after next in front of this tile's norm
+    // contraction, which then waits for all of it -- the epilogue and the main loop ran back to back instead of overlapped
+    // (round-2 finding: g_s.4 8.3k cycles per tile = 6.1k main loop + 2.3k epilogue).
     tc_fence_before();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
+    if (!P.late_release && (threadIdx.x & 31) == 0) {
         if (kPair) mbar_arrive_cluster(g.empty_leader);
         else mbar_arrive(g.empty_bar);
     }
@@ -329,6 +334,12 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
                 // + 1 * beta': one K = 16 step against the constant operands (ones x [beta_hi, beta_lo, 0...])
                 tc_mma(g.tmem_base + g.norm_col, make_desc_ns(g.ones), make_desc_ns(g.beta_tile + (uint32_t)((g0 >> 3) * 256)), idesc, 1);
                 tc_commit(g.gdn_bar);
+                if (P.late_release && grp == 0) {
+                    // every epilogue thread finished reading the accumulator before the bar.sync above; the norm MMAs are queued:
+                    // now the main loop of the tile after next may follow them into the pipe (barrier count: see the kernel prologue)
+                    if (kPair) mbar_arrive_cluster(g.empty_leader);
+                    else mbar_arrive(g.empty_bar);
+                }
             }
             __syncwarp();
         }
@@ -433,7 +444,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpi == EPI_SCATTER ? 4 : (kPair ? 2 : 1) * (kEpiThreads / 32)); }   // one arrival per epilogue warp (col2im: per team of 4)
+        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpi == EPI_SCATTER ? 4 : (kPair ? 2 : 1) * ((kEpi == EPI_GDN && P.late_release) ? 1 : kEpiThreads / 32)); }   // one arrival per epilogue warp (col2im: per team of 4)
         mbar_init(&gdn_bar, 1);
         mbar_init(&gload_bar, 1);
         mbar_init(&bres_bar, 1);
@@ -988,6 +999,8 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
     Q.direct_store = 1;   // measured: g_a.0 1.04 -> 0.99 ms, g_s.2 0.38 -> 0.37 ms vs the staged, coalesced copy-out (MMC_TC_GDN_DIRECT=0)
     if (const char *g = getenv("MMC_TC_GDN_DIRECT")) Q.direct_store = atoi(g);
     if (Q.a_tmem) Q.direct_store = 1;    // no shared-memory x^2 tile to stage the copy-out in
+    Q.late_release = 1;
+    if (const char *g = getenv("MMC_TC_LATE_RELEASE")) Q.late_release = atoi(g) != 0;   // 0: round-1 behaviour (measurement aid)
     if (const char *g = getenv("MMC_TC_GRID")) {   // profiling aid: restrict the persistent grid (profiles/probe_grid.py)
         int v = atoi(g);
         if (v >= 1 && v < grid) grid = v;

@@ -612,10 +612,18 @@ static int launch_eb_bwd(const float *x, const float *noise, const float *g, con
 // t = 1 / (1 + z/2)): 10 FMAs, one MUFU.RCP and one MUFU.EX2 instead of the ~45-instruction erfcf().  The likelihood
 // is a difference of two such values of magnitude <= 1/2, so this sits inside the cancellation noise (4 ulp of 1/2)
 // that the reference's own fp32 result carries; the kernel then streams at HBM speed instead of being ALU-bound.
+// MUFU.RCP alone (1 ulp): __frcp_rn() adds a Newton step and a CALL to a denormal slow path, which made the likelihood kernel
+// ALU-bound; every use below feeds an approximation whose own error is larger (operands are >= 0.11 resp. >= 1)
+__device__ __forceinline__ float rcp_fast(float v)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
 __device__ __forceinline__ float erfc_fast(float x)
 {
     const float z = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.5f, z, 1.0f));
+    const float t = rcp_fast(fmaf(0.5f, z, 1.0f));
     float p = 0.17087277f;
     p = fmaf(p, t, -0.82215223f);
     p = fmaf(p, t, 1.48851587f);
@@ -650,7 +658,7 @@ __device__ __forceinline__ void gc_one(float xv, float sv, float mv, float nv, f
     float val = kMeans ? __fsub_rn(v, mv) : v;
     float a = fabsf(val);
     float s = lower_bound_f(sv, scale_bound);
-    const float inv_s = __frcp_rn(s);            // one reciprocal for both CDF arguments
+    const float inv_s = rcp_fast(s);             // one reciprocal (MUFU) for both CDF arguments
     if (s >= 8.0f) {
         // Wide Gaussians: Phi(u) - Phi(l) is a difference of two numbers near 1/2 (the reference's fp32 result carries
         // ~2.4e-7 of cancellation noise there).  Integrate the density over the bin instead:
@@ -686,7 +694,7 @@ __global__ void __launch_bounds__(kBlock) gc_kernel(const float *__restrict__ x,
         x_hat[i] = v;
         if (x_hat_bf16) x_hat_bf16[i] = __float2bfloat16_rn(v);
         lik[i] = l;
-        if (bits) bit_acc -= log2f(l);
+        if (bits) bit_acc -= __log2f(l);
     };
     if (kVec) {
         int64_t n4 = n >> 2;
@@ -708,7 +716,7 @@ __global__ void __launch_bounds__(kBlock) gc_kernel(const float *__restrict__ x,
                 uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&lo), *reinterpret_cast<uint32_t *>(&hi));
                 reinterpret_cast<uint2 *>(x_hat_bf16)[q] = pk;
             }
-            if (bits) bit_acc -= (log2f(l.x) + log2f(l.y)) + (log2f(l.z) + log2f(l.w));
+            if (bits) bit_acc -= (__log2f(l.x) + __log2f(l.y)) + (__log2f(l.z) + __log2f(l.w));
         }
         for (int64_t i = (n4 << 2) + tid; i < n; i += stride) scalar(i);
     } else {

@@ -7,6 +7,8 @@
 // images of a batch on parallel host threads.
 #include <algorithm>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -81,27 +83,153 @@ static int validate(const int32_t *indexes, int64_t n, const CdfTable &T, const 
     return MMC_OK;
 }
 
-// Encodes one stream; returns its 32-bit words (front = first word of the stream).
-static void encode_one(const int32_t *symbols, const int32_t *indexes, int64_t n, const CdfTable &T, std::vector<uint32_t> &words)
+// ---- fast path: reciprocal-multiply encoder --------------------------------------------------------------------------
+// The serial dependency of rANS encoding is x -> x / freq.  The reference divides (rans64.h Rans64EncPut); with one
+// precomputed entry per (CDF row, value) the quotient is an exact multiply-high + shift (Granlund-Montgomery, the
+// RansEncSymbol idea of ryg_rans): for 2 <= freq <= 2^16 and x < freq * 2^47 <= 2^63,
+//     floor(x / freq) == mulhi64(x, ceil(2^(63 + s) / freq)) >> (s - 1),   s = ceil(log2 freq)
+// (checked exhaustively over freq with edge and random x in tests/test_host_cpu.py via mmc_rans_selftest).  freq == 1
+// uses rcp = 2^64 - 1 (mulhi gives x - 1) and a bias of 2^16 - 1, as ryg does.  The stream is byte-identical.
+typedef unsigned __int128 u128;
+struct EncEntry {
+    uint64_t rcp;
+    uint32_t bias;        // start (+ 2^16 - 1 when freq == 1)
+    uint32_t freq_shift;  // freq in bits 0..19, shift in bits 24..31
+};
+static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((u128)a * b) >> 64); }
+
+static inline EncEntry make_entry(uint32_t start, uint32_t freq)
 {
-    // upper bound on emitted words: one per token (each put renormalises at most once) + 2 for the flush
-    size_t ntok = 0;
-    Token tmp[16];
-    for (int64_t i = 0; i < n; ++i) {
-        const int32_t max_value = T.sizes[indexes[i]] - 2;
-        const int32_t v = symbols[i] - T.offsets[indexes[i]];
-        ntok += (v < 0 || v >= max_value) ? 12 : 1;
+    EncEntry e;
+    if (freq < 2) {
+        e.rcp = ~0ull; e.bias = start + (1u << kPrecision) - 1; e.freq_shift = freq;
+    } else {
+        uint32_t shift = 0;
+        while (freq > (1u << shift)) ++shift;
+        e.rcp = (uint64_t)((((u128)1 << (shift + 63)) + freq - 1) / freq);
+        e.bias = start;
+        e.freq_shift = freq | ((shift - 1) << 24);
     }
-    std::vector<uint32_t> buf(ntok + 2);
-    uint32_t *end = buf.data() + buf.size(), *ptr = end;
+    return e;
+}
+
+// Encoder tables derived from one set of CDFs; cached by content hash (the Python side passes freshly copied tables on
+// every call, and building ~100k reciprocals costs a few ms).
+struct EncTable {
+    uint64_t hash = 0;
+    std::vector<EncEntry> entries;       // [row base + value]
+    std::vector<uint32_t> row_base;
+    std::vector<int32_t> max_value, offset;
+    bool ok = true;
+};
+
+static uint64_t hash_words(const int32_t *p, size_t n, uint64_t h)
+{
+    for (size_t i = 0; i < n; ++i) { h ^= (uint32_t)p[i]; h *= 0x100000001b3ull; h ^= h >> 29; }
+    return h;
+}
+
+static std::shared_ptr<const EncTable> get_enc_table(const CdfTable &T)
+{
+    static std::mutex mu;
+    static std::vector<std::shared_ptr<const EncTable>> cache;
+    uint64_t h = 0xcbf29ce484222325ull ^ ((uint64_t)T.n_cdfs << 32) ^ (uint64_t)T.stride;
+    h = hash_words(T.sizes, T.n_cdfs, h);
+    h = hash_words(T.offsets, T.n_cdfs, h);
+    for (int i = 0; i < T.n_cdfs; ++i) h = hash_words(T.cdfs + (size_t)i * T.stride, (size_t)T.sizes[i], h);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto &t : cache) if (t->hash == h) return t;
+    }
+    auto t = std::make_shared<EncTable>();
+    t->hash = h;
+    t->row_base.resize(T.n_cdfs); t->max_value.resize(T.n_cdfs); t->offset.resize(T.n_cdfs);
+    size_t total = 0;
+    for (int i = 0; i < T.n_cdfs; ++i) { t->row_base[i] = (uint32_t)total; total += (size_t)T.sizes[i] - 1; }
+    t->entries.resize(total);
+    for (int i = 0; i < T.n_cdfs; ++i) {
+        const int32_t *cdf = T.cdfs + (size_t)i * T.stride;
+        t->max_value[i] = T.sizes[i] - 2;
+        t->offset[i] = T.offsets[i];
+        for (int v = 0; v + 1 < T.sizes[i]; ++v) {
+            const int64_t freq = (int64_t)cdf[v + 1] - cdf[v];
+            if (freq < 1 || freq > (1 << kPrecision) || cdf[v] < 0) { t->ok = false; t->entries[t->row_base[i] + v] = make_entry(0, 1); continue; }
+            t->entries[t->row_base[i] + v] = make_entry((uint32_t)cdf[v], (uint32_t)freq);
+        }
+    }
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() >= 16) cache.erase(cache.begin());
+    cache.push_back(t);
+    return t;
+}
+
+// Output words are produced back to front.  Every coded unit emits at most one word, so n + slack words always hold the
+// regular symbols; the (rare) bypass symbols check the remaining room and grow the buffer when they need to.
+struct BackBuffer {
+    std::unique_ptr<uint32_t[]> buf;     // uninitialised: only the words actually produced are ever read
+    size_t cap;
+    uint32_t *ptr, *end;
+    explicit BackBuffer(size_t words) : buf(new uint32_t[words]), cap(words) { end = buf.get() + cap; ptr = end; }
+    void ensure(size_t words)
+    {
+        if ((size_t)(ptr - buf.get()) >= words) return;
+        const size_t used = end - ptr, bigger = cap * 2 + words;
+        std::unique_ptr<uint32_t[]> nb(new uint32_t[bigger]);
+        memcpy(nb.get() + bigger - used, ptr, used * sizeof(uint32_t));
+        buf.swap(nb);
+        cap = bigger;
+        end = buf.get() + cap;
+        ptr = end - used;
+    }
+    size_t bytes() const { return (size_t)(end - ptr) * sizeof(uint32_t); }
+};
+
+// Encodes one stream back to front into `out`; returns false on an index outside the table.
+static bool encode_one(const int32_t *symbols, const int32_t *indexes, int64_t n, const CdfTable &T, const EncTable &E, BackBuffer &out)
+{
     uint64_t x = kRansL;
+    Token tmp[16];
+    const EncEntry *entries = E.entries.data();
+    const uint32_t *row_base = E.row_base.data();
+    const int32_t *max_value = E.max_value.data(), *offset = E.offset.data();
+    const uint32_t n_cdfs = (uint32_t)T.n_cdfs;
+    uint32_t *ptr = out.ptr;                          // at least 64 words of slack below the n regular words
+    constexpr int64_t kAhead = 12;                    // table entries are fetched a few symbols ahead of the serial state chain
     for (int64_t i = n - 1; i >= 0; --i) {          // rANS is LIFO: code the last symbol first
-        const int nt = tokens_of(symbols[i], indexes[i], T, tmp);
-        for (int t = nt - 1; t >= 0; --t) put(x, ptr, tmp[t]);
+        if (i >= kAhead) {
+            const uint32_t pi = (uint32_t)indexes[i - kAhead];
+            if (pi < n_cdfs) {
+                const int32_t pv = symbols[i - kAhead] - offset[pi];
+                if ((uint32_t)pv < (uint32_t)max_value[pi]) __builtin_prefetch(entries + row_base[pi] + (uint32_t)pv);
+            }
+        }
+        const uint32_t idx = (uint32_t)indexes[i];
+        if (idx >= n_cdfs) return false;
+        const int32_t v = symbols[i] - offset[idx];
+        if ((uint32_t)v < (uint32_t)max_value[idx]) {
+            const EncEntry e = entries[row_base[idx] + (uint32_t)v];
+            const uint32_t freq = e.freq_shift & 0xFFFFFu, shift = e.freq_shift >> 24;
+            // renormalise without a data-dependent branch: the word is always stored, the pointer moves only when x >= x_max
+            // (x_max = ((L >> 16) << 32) * freq)
+            const bool r = x >= ((uint64_t)freq << (31 - kPrecision + 32));
+            ptr[-1] = (uint32_t)x;
+            ptr -= r;
+            x = r ? (x >> 32) : x;
+            const uint64_t q = mulhi64(x, e.rcp) >> shift;
+            x += e.bias + q * ((1u << kPrecision) - freq);              // (q << 16) + (x - q * freq) + start
+        } else {
+            // escape symbol + bypass nibbles (rans_interface.cpp:117-171): rare, keeps the division-based path
+            out.ptr = ptr;
+            out.ensure(16 + 64);
+            ptr = out.ptr;
+            const int nt = tokens_of(symbols[i], indexes[i], T, tmp);
+            for (int t = nt - 1; t >= 0; --t) put(x, ptr, tmp[t]);
+        }
     }
     *--ptr = (uint32_t)(x >> 32);                    // Rans64EncFlush: low word first in the stream
     *--ptr = (uint32_t)x;
-    words.assign(ptr, end);
+    out.ptr = ptr;
+    return true;
 }
 
 static inline uint32_t get_bits(uint64_t &x, const uint32_t *&ptr, const uint32_t *end, uint32_t nbits, bool &ok)
@@ -183,21 +311,51 @@ int mmc_rans_encode_batch_host(const int32_t *symbols, const int32_t *indexes, i
     if (batch == 0) return MMC_OK;
     MMC_CHECK_ARG(symbols && indexes, "%s: NULL buffer", name);
     CdfTable T{cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets};
-    int rc = validate(indexes, (int64_t)batch * n, T, name);
+    int rc = validate(indexes, 0, T, name);          // the table; the indexes are range-checked inside the coding loop
     if (rc) return rc;
-    std::vector<std::vector<uint32_t>> streams(batch);
-    parallel_for(batch, [&](int b) { encode_one(symbols + (size_t)b * n, indexes + (size_t)b * n, n, T, streams[b]); });
+    std::shared_ptr<const EncTable> E = get_enc_table(T);
+    MMC_CHECK_ARG(E->ok, "%s: CDF rows must be strictly increasing with steps of at most 2^%d", name, kPrecision);
+    std::vector<std::unique_ptr<BackBuffer>> streams(batch);
+    std::vector<int> good(batch, 1);
+    parallel_for(batch, [&](int b) {
+        streams[b].reset(new BackBuffer((size_t)n + 128));
+        good[b] = encode_one(symbols + (size_t)b * n, indexes + (size_t)b * n, n, T, *E, *streams[b]) ? 1 : 0;
+    });
+    for (int b = 0; b < batch; ++b)
+        MMC_CHECK_ARG(good[b], "%s: stream %d has an index outside [0, %d)", name, b, n_cdfs);
     bool fits = out != nullptr;
     for (int b = 0; b < batch; ++b) {
-        nbytes[b] = streams[b].size() * sizeof(uint32_t);
+        nbytes[b] = streams[b]->bytes();
         fits = fits && nbytes[b] <= cap_per_stream;
     }
     if (!fits) {
         set_error("%s: output capacity %zu bytes per stream is too small (sizes returned in nbytes)", name, cap_per_stream);
         return MMC_EINVAL;
     }
-    for (int b = 0; b < batch; ++b) memcpy(out + (size_t)b * cap_per_stream, streams[b].data(), nbytes[b]);
+    for (int b = 0; b < batch; ++b) memcpy(out + (size_t)b * cap_per_stream, streams[b]->ptr, nbytes[b]);
     return MMC_OK;
+}
+
+// Exhaustive-over-freq check of the reciprocal quotient against the division it replaces (CPU test hook).
+int64_t mmc_rans_selftest(void)
+{
+    int64_t bad = 0;
+    uint64_t r = 0x9E3779B97F4A7C15ull;
+    for (uint32_t freq = 1; freq <= (1u << kPrecision); ++freq) {
+        const EncEntry e = make_entry(0, freq);
+        const uint64_t x_max = (uint64_t)freq << 47;
+        const uint64_t edge[8] = {1, freq, freq + 1ull, x_max - 1, x_max - freq, x_max / 2, kRansL, kRansL + freq - 1};
+        for (int k = 0; k < 24; ++k) {
+            r ^= r << 13; r ^= r >> 7; r ^= r << 17;
+            const uint64_t x = k < 8 ? edge[k] : r % x_max;
+            if (x == 0 || x >= x_max) continue;
+            const uint64_t q = mulhi64(x, e.rcp) >> (e.freq_shift >> 24);
+            const uint64_t got = x + e.bias + q * ((1u << kPrecision) - freq);
+            const uint64_t want = ((x / freq) << kPrecision) + (x % freq);
+            bad += got != want;
+        }
+    }
+    return bad;
 }
 
 int mmc_rans_decode_batch_host(const uint8_t *streams, const size_t *stream_offsets, const size_t *nbytes, const int32_t *indexes,

@@ -52,6 +52,7 @@ _PROTOS = {
     "mmc_bits": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "mmc_pmf_to_quantized_cdf_host": (c_int, [c_vp, c_int, c_int, c_vp]),
     "mmc_rans_encode_batch_host": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "mmc_rans_selftest": (c_i64, []),
     "mmc_rans_decode_batch_host": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "mmc_gdn_reparam": (c_int, [c_vp, c_vp, c_int, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "mmc_gdn_forward": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_i64, c_int, c_vp, c_vp]),

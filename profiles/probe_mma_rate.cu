@@ -12,6 +12,12 @@
 #define CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // layout: 0 none, 2 = 128B swizzle, 4 = 64B, 6 = 32B (sm_100 descriptor encoding, bits 61-63)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout)
@@ -73,7 +79,10 @@ __global__ void __launch_bounds__(128, 1) probe(Cfg c, long long *cycles)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_s;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        // the whole warp walks the loop (uniform control flow, uniform registers); the lane chosen by elect.sync issues -- the issue
+        // scheme of conv_tc.cu.  (A first version issued from `if (threadIdx.x == 0)`: every tcgen05.mma then paid ~125 cycles of
+        // R2UR / predication overhead and the probe measured its own issue loop.)
         const uint32_t idesc = make_idesc(c.n);
         const uint32_t base = smem_u32(smem);
         long long t0 = clock64();
@@ -81,25 +90,151 @@ __global__ void __launch_bounds__(128, 1) probe(Cfg c, long long *cycles)
         for (int it = 0; it < c.iters; ++it) {
             const uint32_t a_addr = base + slot * slot_bytes, b_addr = a_addr + c.a_bytes;
             const uint64_t ad = make_desc(a_addr, c.lbo, c.sbo, c.layout), bd = make_desc(b_addr, c.lbo, c.sbo, c.layout);
-            // alternate between two accumulators (A-from-TMEM: the operand sits in columns 448..479)
             const uint32_t d = tmem + (uint32_t)(c.a_tmem ? (c.n <= 192 ? (it & 1) * c.n : 0) : (it & 1) * 256);
+            const uint32_t a_t = tmem + (uint32_t)(448 + (it & 1) * 32);     // two A buffers of 32 columns each
+            const uint32_t acc = it > 1;
+            if (elect_one()) {
+                if (c.layout == 2) {
+                    // sw128: K steps are +32 B inside the swizzle atom for both operands (immediate offsets)
+                    if (c.a_tmem == 0) {
+                        mma_ss(d, ad, bd, idesc, acc); mma_ss(d, ad + 2, bd + 2, idesc, 1); mma_ss(d, ad + 4, bd + 4, idesc, 1); mma_ss(d, ad + 6, bd + 6, idesc, 1);
+                    } else if (c.a_tmem == 1) {
+                        mma_ts(d, a_t, bd, idesc, acc); mma_ts(d, a_t + 8, bd + 2, idesc, 1); mma_ts(d, a_t + 16, bd + 4, idesc, 1); mma_ts(d, a_t + 24, bd + 6, idesc, 1);
+                    } else if (c.a_tmem == 2) {
+                        cp_128x256b(a_t, ad); cp_128x256b(a_t + 8, ad + 2); cp_128x256b(a_t + 16, ad + 4); cp_128x256b(a_t + 24, ad + 6);
+                        mma_ts(d, a_t, bd, idesc, acc); mma_ts(d, a_t + 8, bd + 2, idesc, 1); mma_ts(d, a_t + 16, bd + 4, idesc, 1); mma_ts(d, a_t + 24, bd + 6, idesc, 1);
+                    } else {
+                        cp_128x256b(a_t, ad); cp_128x256b(a_t + 8, ad + 2); cp_128x256b(a_t + 16, ad + 4); cp_128x256b(a_t + 24, ad + 6);
+                    }
+                } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t a_t = tmem + (uint32_t)(448 + ((it & 1) * 4 + k) * 8);     // two A buffers of 32 columns each
-                if (c.a_tmem >= 2) cp_128x256b(a_t, ad + (uint64_t)(c.a_off[k] >> 4));
-                if (c.a_tmem == 1 || c.a_tmem == 2) mma_ts(d, a_t, bd + (uint64_t)(c.b_off[k] >> 4), idesc, (it > 1) | k);
-                else if (c.a_tmem == 0) mma_ss(d, ad + (uint64_t)(c.a_off[k] >> 4), bd + (uint64_t)(c.b_off[k] >> 4), idesc, (it > 1) | k);
+                    for (int k = 0; k < 4; ++k) {
+                        if (c.a_tmem >= 2) cp_128x256b(a_t + k * 8, ad + (uint64_t)(c.a_off[k] >> 4));
+                        if (c.a_tmem == 1 || c.a_tmem == 2) mma_ts(d, a_t + k * 8, bd + (uint64_t)(c.b_off[k] >> 4), idesc, acc | k);
+                        else if (c.a_tmem == 0) mma_ss(d, ad + (uint64_t)(c.a_off[k] >> 4), bd + (uint64_t)(c.b_off[k] >> 4), idesc, acc | k);
+                    }
+                }
             }
+            __syncwarp();
             if (++slot == c.nslots) slot = 0;
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        if (elect_one()) {
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        }
+        __syncwarp();
         asm volatile("{\n\t.reg .pred P1;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t@P1 bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
         long long t1 = clock64();
-        cycles[blockIdx.x] = t1 - t0;
+        if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+// Issue-loop variants for the SS sw128 case (is ~94 cycles per N <= 128 MMA the tensor core or the issuing warp?):
+//   kVariant 0: one elect.sync per 4 K steps, descriptors rebuilt per slot (the loop of `probe`, i.e. conv_tc.cu's shape)
+//   kVariant 1: one elect.sync per kUnroll slots (4 * kUnroll MMAs), descriptors precomputed before the loop
+//   kVariant 2: a single elected thread runs the whole loop (elect.sync once), descriptors precomputed
+template <int kVariant, int kUnroll>
+__global__ void __launch_bounds__(128, 1) probe_issue(int n, int iters, long long *cycles)
+{
+    extern __shared__ uint8_t raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_s;
+    uint8_t *smem = (uint8_t *)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+    const int slot_bytes = 128 * 128 + 256 * 128;      // A tile + room for a 256-row B tile
+    for (int i = threadIdx.x; i < kUnroll * slot_bytes / 16; i += blockDim.x) ((uint4 *)smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_s)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_s;
+    if (threadIdx.x < 32) {
+        const uint32_t idesc = make_idesc(n);
+        const uint32_t base = smem_u32(smem);
+        uint64_t ad[kUnroll], bd[kUnroll];
+#pragma unroll
+        for (int s = 0; s < kUnroll; ++s) {
+            ad[s] = make_desc(base + s * slot_bytes, 16, 1024, 2);
+            bd[s] = make_desc(base + s * slot_bytes + 128 * 128, 16, 1024, 2);
+        }
+        long long t0 = clock64();
+        if (kVariant == 2) {
+            if (elect_one()) {
+                for (int it = 0; it < iters; it += kUnroll) {
+#pragma unroll
+                    for (int s = 0; s < kUnroll; ++s) {
+                        const uint32_t d = tmem + (uint32_t)((s & 1) * 256);
+                        mma_ss(d, ad[s], bd[s], idesc, it > 1); mma_ss(d, ad[s] + 2, bd[s] + 2, idesc, 1);
+                        mma_ss(d, ad[s] + 4, bd[s] + 4, idesc, 1); mma_ss(d, ad[s] + 6, bd[s] + 6, idesc, 1);
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            }
+            __syncwarp();
+        } else {
+            for (int it = 0; it < iters; it += kUnroll) {
+                if (kVariant == 1) {
+                    if (elect_one()) {
+#pragma unroll
+                        for (int s = 0; s < kUnroll; ++s) {
+                            const uint32_t d = tmem + (uint32_t)((s & 1) * 256);
+                            mma_ss(d, ad[s], bd[s], idesc, it > 1); mma_ss(d, ad[s] + 2, bd[s] + 2, idesc, 1);
+                            mma_ss(d, ad[s] + 4, bd[s] + 4, idesc, 1); mma_ss(d, ad[s] + 6, bd[s] + 6, idesc, 1);
+                        }
+                    }
+                    __syncwarp();
+                } else {
+#pragma unroll
+                    for (int s = 0; s < kUnroll; ++s) {
+                        const uint32_t d = tmem + (uint32_t)((s & 1) * 256);
+                        if (elect_one()) {
+                            mma_ss(d, ad[s], bd[s], idesc, it > 1); mma_ss(d, ad[s] + 2, bd[s] + 2, idesc, 1);
+                            mma_ss(d, ad[s] + 4, bd[s] + 4, idesc, 1); mma_ss(d, ad[s] + 6, bd[s] + 6, idesc, 1);
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            if (elect_one()) {
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            }
+            __syncwarp();
+        }
+        asm volatile("{\n\t.reg .pred P1;\n\tW3:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t@P1 bra D3;\n\tbra W3;\n\tD3:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
+        long long t1 = clock64();
+        if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+}
+
+template <int kVariant, int kUnroll>
+static void run_issue(int sms, long long *d_cycles, long long *h)
+{
+    CHECK(cudaFuncSetAttribute(probe_issue<kVariant, kUnroll>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int n : {64, 128, 256}) {
+        const int iters = 1998 / kUnroll * kUnroll;
+        const size_t smem = (size_t)kUnroll * (128 * 128 + 256 * 128) + 1024;
+        probe_issue<kVariant, kUnroll><<<sms, 128, smem>>>(n, iters, d_cycles);
+        CHECK(cudaDeviceSynchronize());
+        probe_issue<kVariant, kUnroll><<<sms, 128, smem>>>(n, iters, d_cycles);
+        CHECK(cudaDeviceSynchronize());
+        CHECK(cudaMemcpy(h, d_cycles, sms * sizeof(long long), cudaMemcpyDeviceToHost));
+        double avg = 0;
+        for (int i = 0; i < sms; ++i) avg += (double)h[i];
+        avg /= sms;
+        printf("issue variant %d unroll %d  N %3d: %6.1f cycles per MMA (ideal %d)\n", kVariant, kUnroll, n, avg / (iters * 4.0), n / 2);
+    }
 }
 
 // Does tcgen05.cp.128x256b of a SWIZZLE_128B K-major tile land in the layout the A-from-TMEM MMA expects (row = lane, K element k in
@@ -178,10 +313,15 @@ int main()
     CHECK(cudaMalloc(&d_cycles, sms * sizeof(long long)));
     long long *h = (long long *)malloc(sms * sizeof(long long));
     const char *lname[] = {"none", "", "sw128", "", "sw64", "", "sw32"};
+    run_issue<0, 3>(sms, d_cycles, h);
+    run_issue<1, 3>(sms, d_cycles, h);
+    run_issue<2, 3>(sms, d_cycles, h);
+    run_issue<1, 1>(sms, d_cycles, h);
+    run_issue<2, 1>(sms, d_cycles, h);
     printf("layout a_src N grid cycles_per_mma ideal(N/2) us_total\n");
     for (int grid : {sms}) {
         for (int a_tmem = 0; a_tmem < 4; ++a_tmem) {
-            for (int layout : {2, 0}) {
+            for (int layout : {2}) {
                 for (int n : {64, 128, 192, 256}) {
                     Cfg c;
                     c.n = n; c.layout = layout; c.a_tmem = a_tmem; c.iters = 2000; c.nslots = 3;

@@ -220,6 +220,25 @@ def test_rans_bypass_and_errors():
         ops.rans_decode([s[:8] for s in strings], idx, *tabs)               # truncated stream
 
 
+def test_rans_fast_path_exact_and_mixed_streams():
+    """The encoder's multiply-by-reciprocal state update equals the reference's division for every frequency, and long streams
+    that mix regular symbols with escape / bypass symbols (buffer growth path) round-trip."""
+    from mmcodec import _lib, ops
+    assert _lib.lib().mmc_rans_selftest() == 0
+    gc = mmcodec.GaussianConditional(None)
+    gc.update_scale_table(mmcodec.models.get_scale_table())
+    tabs = (gc._quantized_cdf, gc._cdf_length, gc._offset)
+    g = torch.Generator().manual_seed(7)
+    n = 200000
+    idx = torch.randint(0, 64, (2, n), generator=g, dtype=torch.int32)
+    scale = torch.tensor(mmcodec.models.get_scale_table())[idx.long()]
+    sym = torch.round(torch.randn(2, n, generator=g) * scale).to(torch.int32)
+    sym[1, ::3] = torch.randint(-5000, 5000, (len(sym[1, ::3]),), generator=g, dtype=torch.int32)   # every third symbol escapes
+    strings = ops.rans_encode(sym, idx, *tabs)
+    assert torch.equal(ops.rans_decode(strings, idx, *tabs), sym)
+    assert len(strings[1]) > len(strings[0])
+
+
 def _shard_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
