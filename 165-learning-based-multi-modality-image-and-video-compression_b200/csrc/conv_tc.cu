@@ -35,7 +35,8 @@
 namespace mmc {
 
 // warp 0 TMA, warp 1 MMA, then 4 * kParts epilogue warps: kParts warps per TMEM lane quarter split the accumulator columns
-constexpr int tc_threads(int parts) { return 64 + 128 * parts; }
+// kTeams = 2 (GDN epilogue, C <= 128): two such groups of epilogue warps work on alternate tiles, see epilogue_gdn
+constexpr int tc_threads(int parts, int teams = 1) { return 64 + 128 * parts * teams; }
 // Pair kernel: the GDN norm contraction stays a per-CTA (cta_group::1) MMA on the CTA's own x^2 tile and a full copy of gamma, so the two
 // epilogues of a pair never wait for each other (a pair-wide GDN MMA needs a cross-CTA hand-shake per tile and was slower).
 constexpr int kMaxStages = 8;
@@ -258,9 +259,11 @@ struct GdnCtx {
     uint32_t a_col;             // TMEM column of the x^2 operand (a_tmem mode)
     uint64_t *empty_bar;        // this tile's accumulator-release barrier (pair mode: the leader's, as a cluster address)
     uint32_t empty_leader;
+    uint32_t bar_id;            // named barrier of this epilogue team (1 + team)
+    bool first_warp;            // the team's first warp issues the norm MMAs
 };
 
-template <int NCH, int G, bool kPair, int kParts>
+template <int NCH, int G, bool kPair, int kParts, int kTeams>
 __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_s, const float *beta_s, uint32_t &gdn_phase)
 {
     const TcParams &P = g.P;
@@ -306,16 +309,16 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
     // (round-2 finding: g_s.4 8.3k cycles per tile = 6.1k main loop + 2.3k epilogue).
     tc_fence_before();
     __syncwarp();
-    if (!P.late_release && (threadIdx.x & 31) == 0) {
+    if (kTeams == 1 && !P.late_release && (threadIdx.x & 31) == 0) {
         if (kPair) mbar_arrive_cluster(g.empty_leader);
         else mbar_arrive(g.empty_bar);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "n"(kEpiThreads) : "memory");
 #pragma unroll
     for (int grp = 0; grp < G; ++grp) {
         const int g0 = grp * gch * 16;
-        if ((threadIdx.x >> 5) == 2) {
-            // first epilogue warp: uniform control flow, one elected lane issues the (compile-time unrolled) MMAs
+        if (g.first_warp) {
+            // first warp of the team: uniform control flow, one elected lane issues the (compile-time unrolled) MMAs
             if (g.it == 0 && grp == 0) mbar_wait(g.gload_bar, 0);
             tc_fence_after();
             const uint32_t idesc = make_idesc(gch * 16);
@@ -334,7 +337,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
                 // + 1 * beta': one K = 16 step against the constant operands (ones x [beta_hi, beta_lo, 0...])
                 tc_mma(g.tmem_base + g.norm_col, make_desc_ns(g.ones), make_desc_ns(g.beta_tile + (uint32_t)((g0 >> 3) * 256)), idesc, 1);
                 tc_commit(g.gdn_bar);
-                if (P.late_release && grp == 0) {
+                if (kTeams == 1 && P.late_release && grp == 0) {
                     // every epilogue thread finished reading the accumulator before the bar.sync above; the norm MMAs are queued:
                     // now the main loop of the tile after next may follow them into the pipe (barrier count: see the kernel prologue)
                     if (kPair) mbar_arrive_cluster(g.empty_leader);
@@ -390,7 +393,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         }
         // every epilogue thread is done with the norm columns (and, after the last group, with sA2)
         tc_fence_before();
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "n"(kEpiThreads) : "memory");
     }
     if (G == 1 && !P.out_f32 && !P.out2 && !P.direct_store) {
         // Coalesced copy-out: consecutive lanes move consecutive 16-byte chunks of one pixel, so every warp store
@@ -407,19 +410,116 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
             const uint4 v = *reinterpret_cast<const uint4 *>(src + (size_t)i * ppi * 128);
             if (off >= 0) *reinterpret_cast<uint4 *>(yo + off) = v;
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");   // staging tile free for the next tile's x^2
+        asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "n"(kEpiThreads) : "memory");   // staging tile free for the next tile's x^2
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-team GDN / IGDN epilogue (single-CTA kernel, C in {64, 128}).  With one team the epilogue is a serial chain per tile -- TMEM
+// load of x (64 B / clk: 1024 cycles for 128 x 128 fp32), square, stage, barrier, norm-MMA round trip through the busy tensor pipe,
+// TMEM load of the norm (another 1024), MUFU, stores: 4.5-6.3k cycles -- and it, not the MMAs, bounded g_a.0 and g_s.* (ncu r02:
+// 35 % / 61 % tensor-pipe active).  Here two teams of FOUR warps take alternate tiles so that one team's TMEM reads overlap the
+// other's MMA wait / MUFU / stores.  One thread owns a whole pixel row: x (C fp32 values) stays in registers between the passes
+// (a second TMEM read of x was measured slower than the single team -- TMEM read bandwidth is the scarce resource; 8-warp teams
+// would need 18 warps = 96 registers per thread, not enough for 64 + working set).  TMEM: the x^2 operand goes through TMEM as
+// before (C / 2 columns per team) and the norm is written IN PLACE over the tile's accumulator stage, which therefore returns to
+// the MMA warp only at the end of the epilogue; three stages (one being filled, one per team): 3 C + 2 C / 2 = 512 for C = 128.
+// Same arithmetic as epilogue_gdn (bf16 x^2 operand, fp32 accumulate, beta through the constant-operand MMA): bit-identical.
+// ---------------------------------------------------------------------------------------------
+template <int NCH>     // 16-column chunks per thread = C / 16
+__device__ __forceinline__ void epilogue_gdn_rows(const GdnCtx &g, uint32_t &gdn_phase)
+{
+    const TcParams &P = g.P;
+    const bool inverse = P.gdn == MMC_GDN_INVERSE;
+    constexpr int kTeamThreads = 128;
+    float x[NCH][16];
+    // ---- pass 1: x -> registers, x^2 -> this team's TMEM operand block ----
+#pragma unroll
+    for (int j = 0; j < NCH; j += 2) {
+        tmem_ld16(g.acc_addr + (uint32_t)(j << 4), x[j]);
+        tmem_ld16(g.acc_addr + (uint32_t)((j + 1) << 4), x[j + 1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c0 = (j + u) << 4;
+            const float *xv = x[j + u];
+            if (P.out2 == 3 && g.valid) {
+                // training: keep the pre-GDN activations (bf16) for the backward pass
+                uint4 *dst = reinterpret_cast<uint4 *>(P.y2 + g.pix_off + c0);
+                dst[0] = make_uint4(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]), pack_bf16(xv[4], xv[5]), pack_bf16(xv[6], xv[7]));
+                dst[1] = make_uint4(pack_bf16(xv[8], xv[9]), pack_bf16(xv[10], xv[11]), pack_bf16(xv[12], xv[13]), pack_bf16(xv[14], xv[15]));
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16(xv[2 * i] * xv[2 * i], xv[2 * i + 1] * xv[2 * i + 1]);
+            // A operand in TMEM: row = lane, K element k in 32-bit column k / 2 (two bf16 per column)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(g.tmem_base + g.lane_addr + g.a_col + (uint32_t)(c0 >> 1)),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+        }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    tc_fence_before();
+    asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "n"(kTeamThreads) : "memory");
+    if (g.first_warp) {
+        // the whole team has read the accumulator: the norm may overwrite it
+        if (g.it == 0) mbar_wait(g.gload_bar, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(NCH * 16);
+        const uint32_t gm = smem_u32(g.sG);
+        if (elect_one()) {
+#pragma unroll
+            for (int kc = 0; kc < (P.debug == 3 ? 0 : NCH / 4); ++kc) {   // debug 3: profiling, no norm MMAs
+                const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * P.Cout * 128));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma_ts(g.tmem_base + g.norm_col, g.tmem_base + g.a_col + (uint32_t)((kc * 4 + k) * 8), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+            }
+            // + 1 * beta': one K = 16 step against the constant operands (ones x [beta_hi, beta_lo, 0...])
+            tc_mma(g.tmem_base + g.norm_col, make_desc_ns(g.ones), make_desc_ns(g.beta_tile), idesc, 1);
+            tc_commit(g.gdn_bar);
+        }
+        __syncwarp();
+    }
+    mbar_wait(g.gdn_bar, gdn_phase);
+    gdn_phase ^= 1;
+    tc_fence_after();
+    // ---- pass 2: y = x * rsqrt(beta' + gamma' x^2)  (IGDN: * sqrt), one MUFU per value, 256-bit stores ----
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int c0 = j << 4;
+        float nrm[16];
+        tmem_ld16(g.tmem_base + g.lane_addr + g.norm_col + (uint32_t)c0, nrm);
+        tmem_ld_wait();
+        float *y = x[j];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) y[i] *= inverse ? sqrt_fast(nrm[i]) : rsqrt_fast(nrm[i]);
+        if (g.valid) {
+            if (!P.out_f32 && !(P.out2 == 1 || P.out2 == 2)) {
+                __nv_bfloat16 *dst = (__nv_bfloat16 *)P.y + g.pix_off + c0;
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst),
+                             "r"(pack_bf16(y[0], y[1])), "r"(pack_bf16(y[2], y[3])), "r"(pack_bf16(y[4], y[5])), "r"(pack_bf16(y[6], y[7])),
+                             "r"(pack_bf16(y[8], y[9])), "r"(pack_bf16(y[10], y[11])), "r"(pack_bf16(y[12], y[13])), "r"(pack_bf16(y[14], y[15]))
+                             : "memory");
+            } else {
+                store16(P, g.pix_off + c0, y);
+            }
+        }
+    }
+    // the norm (and with it the accumulator stage) has been consumed by every thread of the team
+    tc_fence_before();
+    asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "n"(kTeamThreads) : "memory");
+    if (g.first_warp && (threadIdx.x & 31) == 0) mbar_arrive(g.empty_bar);
 }
 
 enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_SCATTER = 2 };
 
-template <int kEpi, int kNCH, bool kPair, int kParts>
-__global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __grid_constant__ TcParams P)
+template <int kEpi, int kNCH, bool kPair, int kParts, int kTeams>
+__global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(const __grid_constant__ TcParams P)
 {
-    constexpr int kEpiThreads = 128 * kParts;
+    constexpr int kEpiThreads = 128 * kParts;     // threads of ONE epilogue team
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-    __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar, gload_bar, bres_bar;
+    __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar[2], gload_bar, bres_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[kMaxCout];
     __shared__ __align__(16) float beta_s[256];
@@ -444,8 +544,9 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpi == EPI_SCATTER ? 4 : (kPair ? 2 : 1) * ((kEpi == EPI_GDN && P.late_release) ? 1 : kEpiThreads / 32)); }   // one arrival per epilogue warp (col2im: per team of 4)
-        mbar_init(&gdn_bar, 1);
+        for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpi == EPI_SCATTER ? 4 : (kPair ? 2 : 1) * ((kEpi == EPI_GDN && (P.late_release || kTeams == 2)) ? 1 : kEpiThreads / 32)); }   // one arrival per epilogue warp (col2im: per team of 4)
+        mbar_init(&gdn_bar[0], 1);
+        mbar_init(&gdn_bar[1], 1);
         mbar_init(&gload_bar, 1);
         mbar_init(&bres_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -470,7 +571,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
         if (kEpi == EPI_GDN) fill_const_tile(s_betaB, P.Cout, P.beta, false);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < kMaxCout; i += tc_threads(kParts)) {
+    for (int i = threadIdx.x; i < kMaxCout; i += tc_threads(kParts, kTeams)) {
         bias_s[i] = (P.bias && i < P.Cout) ? P.bias[i] : 0.0f;
         if (i < 256) beta_s[i] = (kEpi == EPI_GDN && i < P.Cout) ? P.beta[i] : 1.0f;
     }
@@ -484,130 +585,136 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        // Whole warp walks the tile / K-block loops (uniform control flow); the lane chosen by elect.sync issues.
-        if (kEpi == EPI_GDN) {
-            if (elect_one()) {
+        // ONE elected thread runs the whole loop (round 2: with the entire warp walking the K-block loop and an elect.sync per
+        // block, the per-block bookkeeping -- pointer re-derivation, R2UR chains, divergence barriers -- cost more than the four
+        // MMAs it feeds; see profiles/r02_probe_mma_rate_v4.txt).  Stage and barrier addresses are running 32-bit values.
+        if (elect_one()) {
+            if (kEpi == EPI_GDN) {
                 const int grows = P.Cout;
                 mbar_expect_tx(&gload_bar, (uint32_t)(grows * P.Cout * 2));
                 for (int kc = 0; kc < P.Cout / 64; ++kc)
                     tma_load_2d(&P.tmG, &gload_bar, sG + (size_t)kc * grows * 128, kc * 64, 0);
             }
-            __syncwarp();
-        }
-        if (P.b_resident) {
-            if (elect_one()) {
+            if (P.b_resident) {
                 const int nkb = P.phase_begin[1] * P.kchunks;
                 mbar_expect_tx(&bres_bar, (uint32_t)(nkb * b_tile_bytes));
                 for (int tp = 0; tp < P.phase_begin[1]; ++tp)
                     for (int kc = 0; kc < P.kchunks; ++kc)
                         tma_load_2d(&P.tmB, &bres_bar, sBres + (size_t)(tp * P.kchunks + kc) * b_tile_bytes, kc * 64, P.taps[tp].brow);
             }
-            __syncwarp();
-        }
-        int stage = 0;
-        uint32_t phase = 0;
-        TileIter ti;
-        ti.init(P, blockIdx.x);
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti.advance(P)) {
-            if (kPair) ti.init(P, tile);
-            const TileCoord t = ti.coord(P);
-            const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
-            for (int tp = P.phase_begin[t.phase]; tp < P.phase_begin[t.phase + 1]; ++tp) {
-                const Tap tap = P.taps[tp];
-                for (int kc = 0; kc < P.kchunks; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t *a = smem + (size_t)stage * stage_bytes;
-                    if (elect_one()) {
+            const uint32_t smem0 = smem_u32(smem), full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+            const uint32_t full0_leader = kPair ? mapa_u32(full0, 0) : 0u;   // pair: the leader's barrier collects both CTAs' bytes
+            const uint32_t sbytes = (uint32_t)stage_bytes, nst = (uint32_t)P.num_stages;
+            const int kchunks = P.kchunks, kchunks1 = P.kchunks1, half_n = P.Ntile / 2;
+            const bool resident = P.b_resident != 0, dbg_no_tma = P.debug == 1;
+            uint32_t stage = 0, phase = 0, a_s = smem0;
+            TileIter ti;
+            ti.init(P, blockIdx.x);
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti.advance(P)) {
+                if (kPair) ti.init(P, tile);
+                const TileCoord t = ti.coord(P);
+                const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
+                const int tp_end = P.phase_begin[t.phase + 1];
+                for (int tp = P.phase_begin[t.phase]; tp < tp_end; ++tp) {
+                    const Tap tap = P.taps[tp];
+                    const int ax = cx + tap.dx, ay = cy + tap.dy, brow = tap.brow + t.n0 + (kPair ? (int)rank * half_n : 0);
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        mbar_wait_a(empty0 + stage * 8, phase ^ 1);
                         if (kPair) {
-                            // the leader's barrier collects the bytes of both CTAs; only the leader arrives on it
-                            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
-                            if (rank == 0) mbar_expect_tx(&full_bar[stage], (uint32_t)(2 * stage_bytes));
-                            if (kc < P.kchunks1) tma_load_4d_pair(&P.tmA, fb, a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
-                            else tma_load_4d_pair(&P.tmA2, fb, a, (kc - P.kchunks1) * 64, cx + tap.dx, cy + tap.dy, t.b);
-                            tma_load_2d_pair(&P.tmB, fb, a + kABytes, kc * 64, tap.brow + t.n0 + (int)rank * (P.Ntile / 2));
-                        } else if (P.debug == 1 && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
-                            mbar_arrive(&full_bar[stage]);
+                            const uint32_t fb = full0_leader + stage * 8;
+                            if (rank == 0) mbar_expect_tx_a(full0 + stage * 8, 2 * sbytes);   // only the leader arrives on it
+                            if (kc < kchunks1) tma_load_4d_pair_a(&P.tmA, fb, a_s, kc * 64, ax, ay, t.b);
+                            else tma_load_4d_pair_a(&P.tmA2, fb, a_s, (kc - kchunks1) * 64, ax, ay, t.b);
+                            tma_load_2d_pair_a(&P.tmB, fb, a_s + kABytes, kc * 64, brow);
+                        } else if (dbg_no_tma && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
+                            mbar_arrive_a(full0 + stage * 8);
                         } else {
-                            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-                            if (kc < P.kchunks1) tma_load_4d(&P.tmA, &full_bar[stage], a, kc * 64, cx + tap.dx, cy + tap.dy, t.b);
-                            else tma_load_4d(&P.tmA2, &full_bar[stage], a, (kc - P.kchunks1) * 64, cx + tap.dx, cy + tap.dy, t.b);
-                            if (!P.b_resident) tma_load_2d(&P.tmB, &full_bar[stage], a + kABytes, kc * 64, tap.brow + t.n0);
+                            const uint32_t fb = full0 + stage * 8;
+                            mbar_expect_tx_a(fb, sbytes);
+                            if (kc < kchunks1) tma_load_4d_a(&P.tmA, fb, a_s, kc * 64, ax, ay, t.b);
+                            else tma_load_4d_a(&P.tmA2, fb, a_s, (kc - kchunks1) * 64, ax, ay, t.b);
+                            if (!resident) tma_load_2d_a(&P.tmB, fb, a_s + kABytes, kc * 64, brow);
                         }
+                        ++stage; a_s += sbytes;
+                        if (stage == nst) { stage = 0; a_s = smem0; phase ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1 && (!kPair || rank == 0)) {
         // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
-        // The whole warp walks the pipeline (uniform control flow, every lane observes the barriers); one lane chosen
-        // by elect.sync issues the tcgen05.mma / tcgen05.commit instructions, fully unrolled per K block so that the
-        // descriptors are plain uniform-register increments.
-        const uint32_t idesc = kPair ? make_idesc_m256(P.Ntile) : make_idesc(P.Ntile);
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
-        if (P.b_resident) mbar_wait(&bres_bar, 0);
-        TileIter ti;
-        ti.init(P, blockIdx.x);
-        int acc_i = 0;
-        uint32_t acc_ph = 0;
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
-            if (kPair) ti.init(P, tile);
-            const TileCoord t = ti.coord(P);
-            const int as = acc_i;                       // accumulator ring position of this tile
-            const uint32_t aphase = acc_ph;
-            mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * P.Ntile);
-            const int nkb = (P.phase_begin[t.phase + 1] - P.phase_begin[t.phase]) * P.kchunks;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+        // ONE elected thread: wait for the stage, four tcgen05.mma whose descriptors are the stage-0 descriptors plus a running
+        // 16-byte-unit offset, commit.  Measured (profiles/r02_probe_mma_rate_v4.txt): a lean loop sustains the tensor core's
+        // 64 cycles per N = 128 MMA; the round-1 loop took ~122 cycles per MMA whatever N <= 128 -- it was issue-bound.
+        if (elect_one()) {
+            const uint32_t idesc = kPair ? make_idesc_m256(P.Ntile) : make_idesc(P.Ntile);
+            const uint64_t adesc0 = make_desc(smem_u32(smem));
+            const uint64_t bres0 = make_desc(smem_u32(sBres));
+            const uint64_t ones_desc = make_desc_ns(smem_u32(s_ones)), biasb_desc = make_desc_ns(smem_u32(s_biasB));
+            const uint32_t step16 = (uint32_t)(stage_bytes >> 4), bres_step16 = (uint32_t)(b_tile_bytes >> 4), nst = (uint32_t)P.num_stages;
+            const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+            const uint32_t tfull0 = smem_u32(&tmem_full_bar[0]), tempty0 = smem_u32(&tmem_empty_bar[0]);
+            const bool resident = P.b_resident != 0, four = P.ksteps == 4, no_mma = P.debug == 2;
+            const int kchunks = P.kchunks, ntile = P.Ntile, acc_stages = P.acc_stages;
+            uint32_t stage = 0, phase = 0, off16 = 0;
+            if (resident) mbar_wait(&bres_bar, 0);
+            int tphase = 0, next_phase_tile = P.tiles_per_phase;   // tiles are phase-major: the phase changes every tiles_per_phase tiles
+            uint32_t acc_i = 0, acc_ph = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+                while (tile >= next_phase_tile) { ++tphase; next_phase_tile += P.tiles_per_phase; }
+                const int nkb = (P.phase_begin[tphase + 1] - P.phase_begin[tphase]) * kchunks;
+                mbar_wait_a(tempty0 + acc_i * 8, acc_ph ^ 1);
                 tc_fence_after();
-                const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint64_t adesc = make_desc(a_addr);
-                const uint64_t bdesc = make_desc(P.b_resident ? smem_u32(sBres + (size_t)kb * b_tile_bytes) : a_addr + kABytes);
-                if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + acc_i * (uint32_t)ntile;
+                uint64_t bres = bres0;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait_a(full0 + stage * 8, phase);
+                    tc_fence_after();
+                    const uint64_t adesc = adesc0 + off16;
+                    const uint64_t bdesc = resident ? bres : adesc + (uint64_t)(kABytes >> 4);
                     if (kPair) {
                         tc_mma2(d_tmem, adesc, bdesc, idesc, kb != 0);
                         tc_mma2(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
                         tc_mma2(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
                         tc_mma2(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
-                        tc_commit2(&empty_bar[stage]);                          // both CTAs' producers
-                        if (kb == nkb - 1) {
-                            if (kEpi == EPI_GDN) tc_mma2(d_tmem, make_desc_ns(smem_u32(s_ones)), make_desc_ns(smem_u32(s_biasB)), idesc, 1);   // + bias
-                            tc_commit2(&tmem_full_bar[as]);      // both CTAs' epilogues
-                        }
+                        tc_commit2_a(empty0 + stage * 8);                          // both CTAs' producers
                     } else {
-                    if (P.debug != 2) {
-                        // K=16 per step: +32 B (= +2 in descriptor units) inside the 128-byte swizzle atom
-                        tc_mma(d_tmem, adesc, bdesc, idesc, kb != 0);
-                        tc_mma(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
-                        tc_mma(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
-                        if (P.ksteps == 4) tc_mma(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                        if (!no_mma) {
+                            // K=16 per step: +32 B (= +2 in descriptor units) inside the 128-byte swizzle atom
+                            tc_mma(d_tmem, adesc, bdesc, idesc, kb != 0);
+                            tc_mma(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                            tc_mma(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                            if (four) tc_mma(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                        }
+                        tc_commit_a(empty0 + stage * 8);   // frees the smem slot once these MMAs have read it
                     }
-                    tc_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
-                    if (kb == nkb - 1) {
-                        if (kEpi == EPI_GDN) tc_mma(d_tmem, make_desc_ns(smem_u32(s_ones)), make_desc_ns(smem_u32(s_biasB)), idesc, 1);   // + bias
-                        tc_commit(&tmem_full_bar[as]);   // accumulator complete -> epilogue
-                    }
-                    }
+                    bres += bres_step16;
+                    ++stage; off16 += step16;
+                    if (stage == nst) { stage = 0; off16 = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == P.num_stages) { stage = 0; phase ^= 1; }
+                if (kPair) {
+                    if (kEpi == EPI_GDN) tc_mma2(d_tmem, ones_desc, biasb_desc, idesc, 1);   // + bias
+                    tc_commit2_a(tfull0 + acc_i * 8);      // both CTAs' epilogues
+                } else {
+                    if (kEpi == EPI_GDN) tc_mma(d_tmem, ones_desc, biasb_desc, idesc, 1);    // + bias
+                    tc_commit_a(tfull0 + acc_i * 8);       // accumulator complete -> epilogue
+                }
+                if (++acc_i == (uint32_t)acc_stages) { acc_i = 0; acc_ph ^= 1; }
             }
         }
+        __syncwarp();
     } else if (warp >= 2) {
         // ===================== epilogue: 8 warps, 2 per TMEM lane quarter, each pair splits the columns ============
         const int q = warp & 3;                 // TMEM lane quarter this warp can access
-        const int half = (warp - 2) >> 2;       // column part of this warp: 0 .. kParts - 1
+        const int team = (warp - 2) / (4 * kParts);                 // kTeams == 2: which of the two epilogue teams
+        const int half = ((warp - 2) % (4 * kParts)) >> 2;          // column part of this warp: 0 .. kParts - 1
         const int row = q * 32 + lane;          // accumulator row == pixel of the tile
         const int th = row / P.TW, tw = row - th * P.TW;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t norm_col = (uint32_t)(P.acc_stages * P.Ntile);
         uint32_t gdn_phase = 0;
-        int it = 0;
+            int it = 0;
         TileIter ti;
         ti.init(P, blockIdx.x);
         int acc_i = 0;
@@ -619,6 +726,7 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
             // own staging buffer and named barrier, so that one team's TMEM / shared-memory latencies overlap the other's work.
             // acc_stages is even there, hence every accumulator stage (and its barriers) always belongs to the same team.
             if (kEpi == EPI_SCATTER && (it & 1) != half) continue;
+            if (kTeams == 2 && (it & 1) != team) continue;             // GDN teams: alternate tiles
             const TileCoord t = ti.coord(P);
             const int as = acc_i;                       // accumulator ring position of this tile
             const uint32_t aphase = acc_ph;
@@ -757,12 +865,18 @@ __global__ void __launch_bounds__(tc_threads(kParts), 1) conv_tc_kernel(const __
                         }
                     }
                 } else {
-                    if (half == 0) pix_off_s[row] = valid ? pix_off : -1;   // published by the bar.sync inside epilogue_gdn
-                    GdnCtx g{P, sA2, sG, &gdn_bar, &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off, it, pix_off_s,
+                    if (kTeams == 1 && half == 0) pix_off_s[row] = valid ? pix_off : -1;   // published by the bar.sync inside epilogue_gdn
+                    GdnCtx g{P, sA2, sG, &gdn_bar[team], &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off,
+                             kTeams == 2 ? (it >> 1) : it, pix_off_s,
                              rank, smem_u32(s_ones), smem_u32(s_betaB), norm_col + (uint32_t)P.gdn_chunk, &tmem_empty_bar[as],
-                             kPair ? empty_leader + (uint32_t)(as * sizeof(uint64_t)) : 0u};
-                    // (chunks per thread, norm groups): C=128 -> one 128-column norm pass; C=192 -> two 96-column passes
-                    epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1), kPair, kParts>(g, bias_s, beta_s, gdn_phase);
+                             kPair ? empty_leader + (uint32_t)(as * sizeof(uint64_t)) : 0u, (uint32_t)(1 + team), ((warp - 2) % (4 * kParts)) == 0};
+                    if constexpr (kTeams == 2) {
+                        // norm in place over this tile's accumulator stage; the x^2 operand block of the team sits behind the stages
+                        g.norm_col = (uint32_t)(as * P.Ntile);
+                        g.a_col = norm_col + (uint32_t)(team * (P.Cout / 2));     // norm_col here = acc_stages * Ntile
+                        epilogue_gdn_rows<(kNCH > 0 ? kNCH : 4)>(g, gdn_phase);
+                    } else
+                    epilogue_gdn<(kNCH > 0 ? kNCH : 2), (kNCH == 6 ? 2 : 1), kPair, kParts, kTeams>(g, bias_s, beta_s, gdn_phase);
                 }
             }
             tc_fence_before();
@@ -974,7 +1088,7 @@ static void pick_tile(int gh, int gw, int sx, int sy, int *TH, int *TW)
     }
 }
 
-template <int kEpi, int kNCH, bool kPair = false, int kParts = 2>
+template <int kEpi, int kNCH, bool kPair = false, int kParts = 2, int kTeams = 1>
 static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaStream_t st, const char *name)
 {
     // dynamic shared memory available next to the kernel's static allocation (227 KB per CTA on sm_100)
@@ -982,9 +1096,9 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
     size_t budget = budget_dev.cur().load(std::memory_order_relaxed);
     if (budget == 0) {
         cudaFuncAttributes fa;
-        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi, kNCH, kPair, kParts>));
+        MMC_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams>));
         size_t avail = 227 * 1024 - fa.sharedSizeBytes;
-        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi, kNCH, kPair, kParts>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
+        MMC_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)avail));
         budget = avail;
         budget_dev.cur().store(avail, std::memory_order_relaxed);
     }
@@ -1020,13 +1134,13 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.blockDim = dim3(tc_threads(kParts)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
+        cfg.blockDim = dim3(tc_threads(kParts, kTeams)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
         static PerDevice<int> max_pairs_dev;
         int max_pairs = max_pairs_dev.cur().load(std::memory_order_relaxed);
         if (max_pairs == 0) {
             cfg.gridDim = dim3(kNumSMs);
             int n = 0;
-            MMC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<kEpi, kNCH, kPair, kParts>, &cfg));
+            MMC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams>, &cfg));
             max_pairs = n > 0 ? n : 1;
             max_pairs_dev.cur().store(max_pairs, std::memory_order_relaxed);
         }
@@ -1034,11 +1148,11 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         if (grid > 2 * max_pairs) grid = 2 * max_pairs;
         if (grid < 2) grid = 2;
         cfg.gridDim = dim3(grid);
-        MMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kEpi, kNCH, kPair, kParts>, Q));
+        MMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams>, Q));
         count_launch();
         return MMC_OK;
     }
-    conv_tc_kernel<kEpi, kNCH, kPair, kParts><<<grid, tc_threads(kParts), smem, st>>>(Q);
+    conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams><<<grid, tc_threads(kParts, kTeams), smem, st>>>(Q);
     MMC_CHECK_LAUNCH(name);
     return MMC_OK;
 }
@@ -1201,11 +1315,17 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
     P.acc_stages = (512 - P.gdn_chunk - (P.a_tmem ? d->Cout / 2 : 0)) / P.Ntile;      // as many accumulator stages as TMEM holds
     if (P.acc_stages > kMaxAccStages) P.acc_stages = kMaxAccStages;
     if (P.acc_stages < 1) P.acc_stages = 1;
+    // Two GDN epilogue teams (single-CTA kernel, C in {64, 128}; see epilogue_gdn_teams): x^2 through ONE shared-memory tile, the
+    // norm in two halves into a team-private scratch block, three accumulator stages: 3 C + 2 C / 2 <= 512 TMEM columns.
+    bool teams = d->gdn != MMC_GDN_NONE && !P.pair && (d->Cout == 64 || d->Cout == 128) && P.Ntile == d->Cout;
+    if (const char *g = getenv("MMC_TC_TEAMS")) teams = teams && atoi(g) != 1;      // 1: single team (round-1 epilogue, measurement aid)
+    if (teams) { P.acc_stages = 3; P.a_tmem = 1; P.gdn_chunk = 0; }
     if (pl.mode == MODE_SCATTER) {
         P.acc_stages &= ~1;    // the two col2im epilogue teams own alternate accumulator stages
         MMC_UNSUPPORTED(P.acc_stages < 2, "%s: the reconstruction kernel needs two accumulator stages (N tile %d)", name, P.Ntile);
     }
-    MMC_UNSUPPORTED(P.acc_stages * P.Ntile + P.gdn_chunk + (P.a_tmem ? d->Cout / 2 : 0) > 512 || (P.gdn_chunk % 16) != 0, "%s: TMEM budget exceeded", name);
+    MMC_UNSUPPORTED((teams ? 3 * P.Ntile + d->Cout : P.acc_stages * P.Ntile + P.gdn_chunk + (P.a_tmem ? d->Cout / 2 : 0)) > 512 || (P.gdn_chunk % 16) != 0,
+                    "%s: TMEM budget exceeded", name);
 
     size_t fixed = 1024;  // alignment slack
     if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (P.a_tmem ? 0 : (size_t)(d->Cout / 64) * kABytes);
@@ -1213,7 +1333,7 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
     // Small layers (image-edge conv, reconstruction deconv): keep every weight tile resident in shared memory so that
     // the K blocks stream activations only (halves the L2 -> SM traffic of those layers).
     const size_t b_total = (size_t)pl.ntaps * pl.kchunks * P.Ntile * 128;
-    P.b_resident = (!P.pair && P.n_blocks == 1 && P.n_phases == 1 && b_total <= 96 * 1024 && fixed + b_total + 4 * kABytes <= 200 * 1024) ? 1 : 0;
+    P.b_resident = (!P.pair && P.n_blocks == 1 && P.n_phases == 1 && b_total <= 96 * 1024 && fixed + b_total + 3 * kABytes <= 204 * 1024) ? 1 : 0;
     if (P.b_resident) fixed += b_total;
     const size_t stage_bytes = kABytes + (P.b_resident ? 0 : (size_t)(P.pair ? P.Ntile / 2 : P.Ntile) * 128);
 
@@ -1270,9 +1390,11 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
         const bool wide = getenv("MMC_TC_PARTS") ? atoi(getenv("MMC_TC_PARTS")) == 4 : false;
         if (d->Cout == 128 && P.pair) return wide ? launch_tc<EPI_GDN, 2, true, 4>(P, fixed, stage_bytes, st, name)
                                                   : launch_tc<EPI_GDN, 4, true, 2>(P, fixed, stage_bytes, st, name);
+        if (d->Cout == 128 && teams) return launch_tc<EPI_GDN, 8, false, 1, 2>(P, fixed, stage_bytes, st, name);
         if (d->Cout == 128) return wide ? launch_tc<EPI_GDN, 2, false, 4>(P, fixed, stage_bytes, st, name)
                                         : launch_tc<EPI_GDN, 4, false, 2>(P, fixed, stage_bytes, st, name);
         if (d->Cout == 192) return launch_tc<EPI_GDN, 6>(P, fixed, stage_bytes, st, name);
+        if (teams) return launch_tc<EPI_GDN, 4, false, 1, 2>(P, fixed, stage_bytes, st, name);
         return launch_tc<EPI_GDN, 2>(P, fixed, stage_bytes, st, name);
     }
     if (P.pair) return launch_tc<EPI_PLAIN, 0, true, 2>(P, fixed, stage_bytes, st, name);
