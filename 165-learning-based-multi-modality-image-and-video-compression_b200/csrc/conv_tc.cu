@@ -36,7 +36,10 @@ namespace mmc {
 
 // warp 0 TMA, warp 1 MMA, then 4 * kParts epilogue warps: kParts warps per TMEM lane quarter split the accumulator columns
 // kTeams = 2 (GDN epilogue, C <= 128): two such groups of epilogue warps work on alternate tiles, see epilogue_gdn
-constexpr int tc_threads(int parts, int teams = 1) { return 64 + 128 * parts * teams; }
+// Service warps: 0 = TMA producer (A patches in grouped mode), 1 = MMA issuer, 2 = weight-tile producer and 3 = second MMA issuer
+// (both grouped mode only); the epilogue warps follow.
+constexpr int kSvcWarps = 4;
+constexpr int tc_threads(int parts, int teams = 1) { return 32 * kSvcWarps + 128 * parts * teams; }
 // Pair kernel: the GDN norm contraction stays a per-CTA (cta_group::1) MMA on the CTA's own x^2 tile and a full copy of gamma, so the two
 // epilogues of a pair never wait for each other (a pair-wide GDN MMA needs a cross-CTA hand-shake per tile and was slower).
 constexpr int kMaxStages = 8;
@@ -58,10 +61,30 @@ enum TcMode {
                       // into output pixels through shared memory (no tap loop, every activation is read once)
 };
 
+// Tap group (MODE_STD, P.grouped): taps whose A tiles are row shifts of ONE patch.  The patch -- (TH + ntaps - 1) tile rows of TW = 8
+// pixels, 64 channels, i.e. one 1024-byte swizzle atom per tile row -- is loaded once per 64-channel chunk; tap j reads it from row
+// j on: a whole-atom offset of the UMMA descriptor, so the K-major SWIZZLE_128B layout stays intact.  Taps of a transposed
+// convolution phase with the same dx, resp. taps of a strided convolution with the same kx and ky of the same parity (the rows of
+// the patch are then every stride-th input row: TMA element strides), form a group.  Round 2: the per-SM L2 -> SM ingest
+// (64 B / clk) bounded every large layer (32 KB of operands per 256 cycles of MMA); grouping cuts the A traffic 2-2.5x.
+constexpr int kMaxGroups = 16;
+struct Group {
+    int16_t ox, oy;      // patch origin relative to the tile origin (A-grid units)
+    uint8_t ntaps;       // taps reading this patch, at tile-row offsets 0 .. ntaps - 1
+    uint8_t tap0;        // first entry of this group in gbrow[]
+};
+
 struct TcParams {
     CUtensorMap tmA, tmB, tmG, tmA2;   // tmA2: second activation source (channels Cin1 .. Cin-1), see mmc_conv_forward_tc2
     Tap taps[kMaxTaps];
     int phase_begin[5];  // taps of phase p are [phase_begin[p], phase_begin[p+1])
+    Group groups[kMaxGroups];
+    int32_t gbrow[kMaxTaps];   // first weight row of every grouped tap, group-major
+    int group_begin[5];  // groups of phase p are [group_begin[p], group_begin[p+1])
+    int grouped;         // 1: A-patch ring + B ring (producer / issuer loops below); 0: one (A tile, B tile) stage per K block
+    int a_stage_bytes;   // grouped: bytes of one A patch (patch rows * 1024)
+    int nA, nB;          // grouped: ring depths (per issuer)
+    int issuers;         // grouped: 1 or 2 MMA-issuing threads (warps 1 and 3), each with its own A / B rings
     int n_phases;
     int mode;
     int a_sx, a_sy;  // A-box start = tile origin * (a_sx, a_sy) + tap offset
@@ -400,7 +423,7 @@ __device__ __forceinline__ void epilogue_gdn(const GdnCtx &g, const float *bias_
         // covers whole 128-byte lines (the per-row direct stores touch 32 lines per instruction).
         constexpr int cpp = NCH * kParts * 2;      // 16-byte chunks per pixel (C / 8): 8 or 16
         constexpr int ppi = kEpiThreads / cpp;     // pixels covered per iteration (32 or 16, a multiple of 8)
-        const int et = threadIdx.x - 64;
+        const int et = threadIdx.x - 32 * kSvcWarps;
         const int j = et % cpp, p0 = et / cpp;     // this thread always moves chunk j; pixel p0 + it * ppi
         const uint8_t *src = g.sA2 + (size_t)(j >> 3) * kABytes + (size_t)p0 * 128 + (((j & 7) ^ (p0 & 7)) << 4);
         __nv_bfloat16 *yo = (__nv_bfloat16 *)P.y + j * 8;
@@ -519,6 +542,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
     constexpr int kEpiThreads = 128 * kParts;     // threads of ONE epilogue team
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+    __shared__ uint64_t bfull_bar[kMaxStages], bempty_bar[kMaxStages];   // grouped mode: the weight-tile ring (full_bar / empty_bar: A patches)
     __shared__ uint64_t tmem_full_bar[kMaxAccStages], tmem_empty_bar[kMaxAccStages], gdn_bar[2], gload_bar, bres_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_s[kMaxCout];
@@ -532,7 +556,9 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
     const int b_tile_bytes = (kPair ? P.Ntile / 2 : P.Ntile) * 128;   // pair mode: this CTA's half of the weight rows
     const uint32_t rank = kPair ? cluster_ctarank() : 0u;
     const int stage_bytes = kABytes + (P.b_resident ? 0 : b_tile_bytes);
-    uint8_t *sG = smem + (size_t)P.num_stages * stage_bytes;       // gamma: (Cout/64) tiles of [Cout][64] bf16
+    // grouped: [nA A patches][nB weight tiles] instead of num_stages (A tile, B tile) pairs
+    const size_t ring_bytes = P.grouped ? (size_t)P.issuers * ((size_t)P.nA * P.a_stage_bytes + (size_t)P.nB * b_tile_bytes) : (size_t)P.num_stages * stage_bytes;
+    uint8_t *sG = smem + ring_bytes;       // gamma: (Cout/64) tiles of [Cout][64] bf16
     uint8_t *sA2 = sG + (size_t)P.Cout * P.Cout * 2;   // x^2:   (Cout/64) tiles of [128][64] bf16
     float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
     // resident weights (b_resident): one [Ntile][64] bf16 tile per K block, after the GDN / staging region
@@ -543,7 +569,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.num_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&bfull_bar[s], 1); mbar_init(&bempty_bar[s], 1); }
         for (int s = 0; s < kMaxAccStages; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], kEpi == EPI_SCATTER ? 4 : (kPair ? 2 : 1) * ((kEpi == EPI_GDN && (P.late_release || kTeams == 2)) ? 1 : kEpiThreads / 32)); }   // one arrival per epilogue warp (col2im: per team of 4)
         mbar_init(&gdn_bar[0], 1);
         mbar_init(&gdn_bar[1], 1);
@@ -610,6 +636,47 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             uint32_t stage = 0, phase = 0, a_s = smem0;
             TileIter ti;
             ti.init(P, blockIdx.x);
+            if (P.grouped) {
+                // ---- grouped: this warp streams the A patches, one per (group, chunk); warp 2 streams the weight tiles.  Even and odd
+                //      tiles (the two MMA issuers) have their OWN rings of nA patches: a barrier has one phase bit, so every ring needs
+                //      a single consumer that observes each of its phases ----
+                const uint32_t abytes = (uint32_t)P.a_stage_bytes, nA = (uint32_t)P.nA;
+                uint32_t st[2] = {0, 0}, ph[2] = {0, 0};
+                uint32_t r = 0;
+                const uint32_t rtoggle = P.issuers == 2 ? 1u : 0u;
+                for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti.advance(P), r ^= rtoggle) {
+                    if (kPair) ti.init(P, tile);
+                    const TileCoord t = ti.coord(P);
+                    const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
+                    const int g_end = P.group_begin[t.phase + 1];
+                    uint32_t stage_r = st[r], phase_r = ph[r];
+                    for (int gi = P.group_begin[t.phase]; gi < g_end; ++gi) {
+                        const Group G = P.groups[gi];
+                        const int ax = cx + G.ox, ay = cy + G.oy;
+                        for (int kc = 0; kc < kchunks; ++kc) {
+                            const bool live = !(dbg_no_tma && (phase_r != 0 || tile >= (int)(blockIdx.x + 2 * gridDim.x)));
+                            const uint32_t slot = r * nA + stage_r;
+                            const uint32_t dst = smem0 + slot * abytes;
+                            mbar_wait_a(empty0 + slot * 8, phase_r ^ 1);
+                            if (!live) {
+                                if (!kPair || rank == 0) mbar_arrive_a(full0 + slot * 8);
+                            } else if (kPair) {
+                                const uint32_t fb = full0_leader + slot * 8;
+                                if (rank == 0) mbar_expect_tx_a(full0 + slot * 8, 2 * abytes);
+                                if (kc < kchunks1) tma_load_4d_pair_a(&P.tmA, fb, dst, kc * 64, ax, ay, t.b);
+                                else tma_load_4d_pair_a(&P.tmA2, fb, dst, (kc - kchunks1) * 64, ax, ay, t.b);
+                            } else {
+                                const uint32_t fb = full0 + slot * 8;
+                                mbar_expect_tx_a(fb, abytes);
+                                if (kc < kchunks1) tma_load_4d_a(&P.tmA, fb, dst, kc * 64, ax, ay, t.b);
+                                else tma_load_4d_a(&P.tmA2, fb, dst, (kc - kchunks1) * 64, ax, ay, t.b);
+                            }
+                            if (++stage_r == nA) { stage_r = 0; phase_r ^= 1; }
+                        }
+                    }
+                    st[r] = stage_r; ph[r] = phase_r;
+                }
+            } else
             for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti.advance(P)) {
                 if (kPair) ti.init(P, tile);
                 const TileCoord t = ti.coord(P);
@@ -628,6 +695,12 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                             tma_load_2d_pair_a(&P.tmB, fb, a_s + kABytes, kc * 64, brow);
                         } else if (dbg_no_tma && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
                             mbar_arrive_a(full0 + stage * 8);
+                        } else if (P.debug >= 4 && (phase != 0 || tile != (int)blockIdx.x)) {
+                            // profiling: 4 = no A loads after priming, 5 = no B loads (which operand stream bounds the layer?)
+                            const uint32_t fb = full0 + stage * 8;
+                            mbar_expect_tx_a(fb, P.debug == 4 ? sbytes - kABytes : (uint32_t)kABytes);
+                            if (P.debug == 5) tma_load_4d_a(&P.tmA, fb, a_s, kc * 64, ax, ay, t.b);
+                            else tma_load_2d_a(&P.tmB, fb, a_s + kABytes, kc * 64, brow);
                         } else {
                             const uint32_t fb = full0 + stage * 8;
                             mbar_expect_tx_a(fb, sbytes);
@@ -642,8 +715,59 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             }
         }
         __syncwarp();
-    } else if (warp == 1 && (!kPair || rank == 0)) {
+    } else if (warp == 2) {
+        // ===================== weight-tile producer (grouped mode) =====================
+        // Its own thread: with one producer thread for both operand streams and one MMA-issuing thread, each spent ~500 cycles
+        // per tap on ring bookkeeping (ncu r02 source view: the epilogue warps starved on tmem_full while those two threads were
+        // busy executing, not waiting) -- twice the 256 cycles the four MMAs of a tap take.
+        if (P.grouped && elect_one()) {
+            const uint32_t smem0 = smem_u32(smem);
+            const uint32_t bfull0 = smem_u32(&bfull_bar[0]), bempty0 = smem_u32(&bempty_bar[0]);
+            const uint32_t bfull0_leader = kPair ? mapa_u32(bfull0, 0) : 0u;
+            const uint32_t bbytes = (uint32_t)b_tile_bytes, nB = (uint32_t)P.nB, b_s0 = smem0 + (uint32_t)P.issuers * (uint32_t)P.nA * (uint32_t)P.a_stage_bytes;
+            const int kchunks = P.kchunks, half_n = P.Ntile / 2;
+            const bool dbg_no_tma = P.debug == 1;
+            uint32_t st[2] = {0, 0}, ph[2] = {0, 0};
+            uint32_t r = 0;
+            int tphase = 0, next_phase_tile = P.tiles_per_phase;
+            const uint32_t rtoggle = P.issuers == 2 ? 1u : 0u;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, r ^= rtoggle) {
+                while (tile >= next_phase_tile) { ++tphase; next_phase_tile += P.tiles_per_phase; }
+                int n0 = 0;
+                if (P.n_blocks > 1) n0 = ((tile - tphase * P.tiles_per_phase) % P.n_blocks) * P.Ntile;
+                const int brow_off = n0 + (kPair ? (int)rank * half_n : 0);
+                const int g_end = P.group_begin[tphase + 1];
+                uint32_t bi = st[r], bphase = ph[r];
+                for (int gi = P.group_begin[tphase]; gi < g_end; ++gi) {
+                    const int ntaps = P.groups[gi].ntaps, tap0 = P.groups[gi].tap0;
+                    for (int kc = 0; kc < kchunks; ++kc) {
+                        for (int j = 0; j < ntaps; ++j) {
+                            const int brow = P.gbrow[tap0 + j] + brow_off;
+                            const bool live = !(dbg_no_tma && (bphase != 0 || tile >= (int)(blockIdx.x + 2 * gridDim.x)));
+                            const uint32_t slot = r * nB + bi;
+                            const uint32_t dst = b_s0 + slot * bbytes;
+                            mbar_wait_a(bempty0 + slot * 8, bphase ^ 1);
+                            if (!live) {
+                                if (!kPair || rank == 0) mbar_arrive_a(bfull0 + slot * 8);
+                            } else if (kPair) {
+                                if (rank == 0) mbar_expect_tx_a(bfull0 + slot * 8, 2 * bbytes);
+                                tma_load_2d_pair_a(&P.tmB, bfull0_leader + slot * 8, dst, kc * 64, brow);
+                            } else {
+                                mbar_expect_tx_a(bfull0 + slot * 8, bbytes);
+                                tma_load_2d_a(&P.tmB, bfull0 + slot * 8, dst, kc * 64, brow);
+                            }
+                            if (++bi == nB) { bi = 0; bphase ^= 1; }
+                        }
+                    }
+                }
+                st[r] = bi; ph[r] = bphase;
+            }
+        }
+        __syncwarp();
+    } else if ((warp == 1 || (warp == 3 && P.grouped && P.issuers == 2)) && (!kPair || rank == 0)) {
         // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
+        // grouped mode: TWO issuing threads (warps 1 and 3) take alternate tiles -- different accumulator stages, so no ordering
+        // between them is needed; each skips the ring slots of the other's tiles.
         // ONE elected thread: wait for the stage, four tcgen05.mma whose descriptors are the stage-0 descriptors plus a running
         // 16-byte-unit offset, commit.  Measured (profiles/r02_probe_mma_rate_v4.txt): a lean loop sustains the tensor core's
         // 64 cycles per N = 128 MMA; the round-1 loop took ~122 cycles per MMA whatever N <= 128 -- it was issue-bound.
@@ -658,16 +782,74 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             const bool resident = P.b_resident != 0, four = P.ksteps == 4, no_mma = P.debug == 2;
             const int kchunks = P.kchunks, ntile = P.Ntile, acc_stages = P.acc_stages;
             uint32_t stage = 0, phase = 0, off16 = 0;
+            // grouped mode: A patches in full_bar / empty_bar's ring, weight tiles in their own ring behind it
+            const uint32_t g_nA = (uint32_t)P.nA, g_nB = (uint32_t)P.nB, g_astep16 = (uint32_t)(P.a_stage_bytes >> 4), g_bstep16 = (uint32_t)(b_tile_bytes >> 4);
+            const uint32_t g_bfull0 = smem_u32(&bfull_bar[0]) + ((P.grouped && warp == 3) ? (uint32_t)P.nB * 8 : 0u);
+            const uint32_t g_bempty0 = smem_u32(&bempty_bar[0]) + ((P.grouped && warp == 3) ? (uint32_t)P.nB * 8 : 0u);
+            // this issuer's rings: A patches [ring][nA], then weight tiles [ring][nB]; barrier slots likewise
+            const uint32_t g_ring = (P.grouped && warp == 3) ? 1u : 0u;
+            const uint64_t g_adesc0 = make_desc(smem_u32(smem) + g_ring * g_nA * (uint32_t)P.a_stage_bytes);
+            const uint64_t g_bdesc0 = make_desc(smem_u32(smem) + (uint32_t)P.issuers * g_nA * (uint32_t)P.a_stage_bytes + g_ring * g_nB * (uint32_t)b_tile_bytes);
+            const uint32_t g_full0 = smem_u32(&full_bar[0]) + g_ring * g_nA * 8, g_empty0 = smem_u32(&empty_bar[0]) + g_ring * g_nA * 8;
+            uint32_t g_bi = 0, g_bphase = 0, g_boff16 = 0;
             if (resident) mbar_wait(&bres_bar, 0);
             int tphase = 0, next_phase_tile = P.tiles_per_phase;   // tiles are phase-major: the phase changes every tiles_per_phase tiles
             uint32_t acc_i = 0, acc_ph = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+            const uint32_t my_parity = warp == 3 ? 1u : 0u;
+            uint32_t it_par = 0;
+            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, it_par ^= 1) {
                 while (tile >= next_phase_tile) { ++tphase; next_phase_tile += P.tiles_per_phase; }
                 const int nkb = (P.phase_begin[tphase + 1] - P.phase_begin[tphase]) * kchunks;
+                if (P.grouped && P.issuers == 2 && it_par != my_parity) {
+                    // the other issuer's tile (it has its own operand rings): only the accumulator ring is shared
+                    if (++acc_i == (uint32_t)acc_stages) { acc_i = 0; acc_ph ^= 1; }
+                    continue;
+                }
                 mbar_wait_a(tempty0 + acc_i * 8, acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc_i * (uint32_t)ntile;
                 uint64_t bres = bres0;
+                if (P.grouped) {
+                    // ---- grouped: tap j of a group reads the group's A patch from tile row j on (one 1024-byte swizzle atom per row) ----
+                    uint32_t first = 0;
+                    const int g_end = P.group_begin[tphase + 1];
+                    for (int gi = P.group_begin[tphase]; gi < g_end; ++gi) {
+                        const int ntaps = P.groups[gi].ntaps;
+                        for (int kc = 0; kc < kchunks; ++kc) {
+                            mbar_wait_a(g_full0 + stage * 8, phase);
+                            tc_fence_after();
+                            uint64_t adesc = g_adesc0 + off16;
+                            for (int j = 0; j < ntaps; ++j) {
+                                mbar_wait_a(g_bfull0 + g_bi * 8, g_bphase);
+                                tc_fence_after();
+                                const uint64_t bdesc = g_bdesc0 + g_boff16;
+                                if (kPair) {
+                                    tc_mma2(d_tmem, adesc, bdesc, idesc, first);
+                                    tc_mma2(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                                    tc_mma2(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                                    tc_mma2(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                                    tc_commit2_a(g_bempty0 + g_bi * 8);
+                                } else {
+                                    if (!no_mma) {
+                                        tc_mma(d_tmem, adesc, bdesc, idesc, first);
+                                        tc_mma(d_tmem, adesc + 2, bdesc + 2, idesc, 1);
+                                        tc_mma(d_tmem, adesc + 4, bdesc + 4, idesc, 1);
+                                        tc_mma(d_tmem, adesc + 6, bdesc + 6, idesc, 1);
+                                    }
+                                    tc_commit_a(g_bempty0 + g_bi * 8);
+                                }
+                                first = 1;
+                                adesc += 64;                                    // next tile row of the patch: + 1024 B
+                                ++g_bi; g_boff16 += g_bstep16;
+                                if (g_bi == g_nB) { g_bi = 0; g_boff16 = 0; g_bphase ^= 1; }
+                            }
+                            if (kPair) tc_commit2_a(g_empty0 + stage * 8);        // the patch is free once its last tap's MMAs have read it
+                            else tc_commit_a(g_empty0 + stage * 8);
+                            ++stage; off16 += g_astep16;
+                            if (stage == g_nA) { stage = 0; off16 = 0; phase ^= 1; }
+                        }
+                    }
+                } else
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait_a(full0 + stage * 8, phase);
                     tc_fence_after();
@@ -704,11 +886,11 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             }
         }
         __syncwarp();
-    } else if (warp >= 2) {
+    } else if (warp >= kSvcWarps) {
         // ===================== epilogue: 8 warps, 2 per TMEM lane quarter, each pair splits the columns ============
         const int q = warp & 3;                 // TMEM lane quarter this warp can access
-        const int team = (warp - 2) / (4 * kParts);                 // kTeams == 2: which of the two epilogue teams
-        const int half = ((warp - 2) % (4 * kParts)) >> 2;          // column part of this warp: 0 .. kParts - 1
+        const int team = (warp - kSvcWarps) / (4 * kParts);                 // kTeams == 2: which of the two epilogue teams
+        const int half = ((warp - kSvcWarps) % (4 * kParts)) >> 2;          // column part of this warp: 0 .. kParts - 1
         const int row = q * 32 + lane;          // accumulator row == pixel of the tile
         const int th = row / P.TW, tw = row - th * P.TW;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
@@ -767,7 +949,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                     const int ih = P.TH - P.halo_lo - P.halo_hi, iw = P.TW - P.halo_lo - P.halo_hi;   // interior (input res)
                     const int items = ih * iw * P.Cout;
                     float *yo = (float *)P.y;
-                    for (int e = (threadIdx.x - 64) & 127; e < items; e += 128) {
+                    for (int e = (threadIdx.x - 32 * kSvcWarps) & 127; e < items; e += 128) {
                         const int ax = e % iw;
                         const int r2 = e / iw;
                         const int ay = r2 % ih;
@@ -869,7 +1051,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                     GdnCtx g{P, sA2, sG, &gdn_bar[team], &gload_bar, tmem_base, acc_addr, lane_addr, norm_col, row, half, valid, pix_off,
                              kTeams == 2 ? (it >> 1) : it, pix_off_s,
                              rank, smem_u32(s_ones), smem_u32(s_betaB), norm_col + (uint32_t)P.gdn_chunk, &tmem_empty_bar[as],
-                             kPair ? empty_leader + (uint32_t)(as * sizeof(uint64_t)) : 0u, (uint32_t)(1 + team), ((warp - 2) % (4 * kParts)) == 0};
+                             kPair ? empty_leader + (uint32_t)(as * sizeof(uint64_t)) : 0u, (uint32_t)(1 + team), ((warp - kSvcWarps) % (4 * kParts)) == 0};
                     if constexpr (kTeams == 2) {
                         // norm in place over this tile's accumulator stage; the x^2 operand block of the team sits behind the stages
                         g.norm_col = (uint32_t)(as * P.Ntile);
@@ -1102,12 +1284,20 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         budget = avail;
         budget_dev.cur().store(avail, std::memory_order_relaxed);
     }
-    MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
-    int stages = (int)((budget - fixed) / stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
     TcParams Q = P;
-    Q.num_stages = stages;
-    const size_t smem = fixed + (size_t)stages * stage_bytes;
+    size_t smem;
+    if (P.grouped) {
+        const size_t bbytes = stage_bytes - kABytes;
+        smem = fixed + (size_t)P.issuers * ((size_t)P.nA * P.a_stage_bytes + (size_t)P.nB * bbytes);
+        MMC_UNSUPPORTED(smem > budget, "%s: shared memory budget exceeded (grouped rings)", name);
+        Q.num_stages = P.nA;
+    } else {
+        MMC_UNSUPPORTED(fixed + 2 * stage_bytes > budget, "%s: shared memory budget exceeded", name);
+        int stages = (int)((budget - fixed) / stage_bytes);
+        if (stages > kMaxStages) stages = kMaxStages;
+        Q.num_stages = stages;
+        smem = fixed + (size_t)stages * stage_bytes;
+    }
     int grid = Q.total_tiles < kNumSMs ? Q.total_tiles : kNumSMs;
     if (const char *g = getenv("MMC_TC_DEBUG")) Q.debug = atoi(g);
     Q.direct_store = 1;   // measured: g_a.0 1.04 -> 0.99 ms, g_s.2 0.38 -> 0.37 ms vs the staged, coalesced copy-out (MMC_TC_GDN_DIRECT=0)
@@ -1273,6 +1463,54 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
         P.spitch = P.Ntile | 1;                          // odd pitch (floats): see the staging stores in the kernel
     } else {
         pick_tile(P.Gh, P.Gw, pl.mode == MODE_PAD8 ? 1 : P.a_sx, P.a_sy, &P.TH, &P.TW);
+        // Tap groups (see struct Group): taps with the same x offset whose y offsets differ by multiples of the A-grid stride
+        // read row shifts of one patch.  Needs tiles of 16 rows x 8 pixels (one swizzle atom per tile row).
+        bool want_grouped = pl.mode == MODE_STD && pl.ntaps > 1;
+        if (const char *g = getenv("MMC_TC_GROUPED")) want_grouped = want_grouped && atoi(g) != 0;
+        if (want_grouped) {
+            int ng = 0, nt = 0, max_taps = 1;
+            bool ok = true;
+            for (int ph = 0; ph < pl.n_phases && ok; ++ph) {
+                P.group_begin[ph] = ng;
+                bool used[kMaxTaps] = {false};
+                for (int t0 = pl.phase_begin[ph]; t0 < pl.phase_begin[ph + 1] && ok; ++t0) {
+                    if (used[t0]) continue;
+                    // collect the taps of this phase with t0's dx and dy == t0's dy (mod a_sy), in ascending dy
+                    int members[kMaxTaps], nm = 0;
+                    for (int t = pl.phase_begin[ph]; t < pl.phase_begin[ph + 1]; ++t) {
+                        if (used[t] || pl.taps[t].dx != pl.taps[t0].dx) continue;
+                        if (((pl.taps[t].dy - pl.taps[t0].dy) % P.a_sy) != 0) continue;
+                        members[nm++] = t;
+                    }
+                    for (int a = 0; a < nm; ++a)
+                        for (int b2 = a + 1; b2 < nm; ++b2)
+                            if (pl.taps[members[b2]].dy < pl.taps[members[a]].dy) { int tmp = members[a]; members[a] = members[b2]; members[b2] = tmp; }
+                    // split where consecutive members are not exactly one A-grid row apart
+                    int a = 0;
+                    while (a < nm && ok) {
+                        int b2 = a + 1;
+                        while (b2 < nm && pl.taps[members[b2]].dy - pl.taps[members[b2 - 1]].dy == P.a_sy) ++b2;
+                        if (ng >= kMaxGroups) { ok = false; break; }
+                        P.groups[ng].ox = pl.taps[members[a]].dx;
+                        P.groups[ng].oy = pl.taps[members[a]].dy;
+                        P.groups[ng].ntaps = (uint8_t)(b2 - a);
+                        P.groups[ng].tap0 = (uint8_t)nt;
+                        for (int m = a; m < b2; ++m) { P.gbrow[nt++] = pl.taps[members[m]].brow; used[members[m]] = true; }
+                        if (b2 - a > max_taps) max_taps = b2 - a;
+                        ++ng;
+                        a = b2;
+                    }
+                }
+            }
+            P.group_begin[pl.n_phases] = ng;
+            if (ok && nt == pl.ntaps) {
+                P.grouped = 1;
+                P.TH = 16; P.TW = 8;
+                P.a_stage_bytes = (P.TH + max_taps - 1) * P.TW * 128;
+                if ((P.TH + max_taps - 1) * P.a_sy > 256) P.grouped = 0;     // TMA box limit
+            }
+            if (!P.grouped) pick_tile(P.Gh, P.Gw, P.a_sx, P.a_sy, &P.TH, &P.TW);
+        }
         P.step_y = P.TH; P.step_x = P.TW; P.off_y = P.off_x = 0;
     }
     P.tiles_y = (P.Gh + P.step_y - 1) / P.step_y;
@@ -1336,6 +1574,26 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
     P.b_resident = (!P.pair && P.n_blocks == 1 && P.n_phases == 1 && b_total <= 96 * 1024 && fixed + b_total + 3 * kABytes <= 204 * 1024) ? 1 : 0;
     if (P.b_resident) fixed += b_total;
     const size_t stage_bytes = kABytes + (P.b_resident ? 0 : (size_t)(P.pair ? P.Ntile / 2 : P.Ntile) * 128);
+    if (P.grouped) {
+        // ring depths from a conservative dynamic shared-memory budget (227 KB minus the largest static footprint of the kernels);
+        // launch_tc re-checks against the real one
+        const size_t avail = (size_t)206 * 1024 - fixed, bbytes = (size_t)(P.pair ? P.Ntile / 2 : P.Ntile) * 128;
+        // rings per issuer: nA patches and nB weight tiles.  Default ONE issuer: two issuers (MMC_TC_ISSUERS=2) halve the ring depth
+        // each one sees, and the operand stream is latency-bound (measured: g_a.2 1.03 -> 1.15 ms, g_s.4 1.36 -> 1.43 ms)
+        int issuers = 1;
+        if (const char *g = getenv("MMC_TC_ISSUERS")) issuers = atoi(g) == 2 ? 2 : 1;
+        int nA = issuers == 2 ? 2 : 3;
+        if (avail < (size_t)issuers * ((size_t)nA * P.a_stage_bytes + 3 * bbytes)) nA = 2;
+        int nB = (P.b_resident || avail < (size_t)issuers * nA * P.a_stage_bytes) ? 0 : (int)((avail - (size_t)issuers * nA * P.a_stage_bytes) / (issuers * bbytes));
+        if (nB > kMaxStages / issuers) nB = kMaxStages / issuers;
+        P.issuers = issuers;
+        if (P.b_resident || nB < 2) {
+            // does not fit (or resident weights): fall back to one (A tile, B tile) stage per K block -- the tile shape stays valid
+            P.grouped = 0;
+        } else {
+            P.nA = nA; P.nB = nB;
+        }
+    }
 
     // ---- tensor maps ----
     if (pl.mode == MODE_PAD8) {
@@ -1352,7 +1610,9 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
         const int c1 = x2 ? cin1 : d->Cin, c2 = d->Cin - c1;
         uint64_t dims[4] = {(uint64_t)c1, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
         uint64_t str[3] = {(uint64_t)c1 * 2, (uint64_t)d->W * c1 * 2, (uint64_t)d->H * d->W * c1 * 2};
-        uint32_t box[4] = {64, (uint32_t)(P.TW * P.a_sx), (uint32_t)(P.TH * P.a_sy), 1};
+        // grouped: the box is the whole patch (tile rows + the rows the other taps of a group reach)
+        const int box_rows = P.grouped ? P.a_stage_bytes / (P.TW * 128) : P.TH;
+        uint32_t box[4] = {64, (uint32_t)(P.TW * P.a_sx), (uint32_t)(box_rows * P.a_sy), 1};
         uint32_t es[4] = {1, (uint32_t)P.a_sx, (uint32_t)P.a_sy, 1};
         rc = encode_map(&P.tmA, x, 4, dims, str, box, es, "activations");
         if (!rc && x2) {

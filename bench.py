@@ -72,10 +72,13 @@ WORKLOAD = WORKLOADS["hyperprior"][6]
 
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the default workload's largest kernels, from the
-# committed `ncu --set full` capture profiles/r01_ncu_conv_tc_full.csv (batch 64 x 768x512); equals the algorithmic bytes of these
-# layers (bf16 activations in + out, weights from L2), i.e. nothing is re-read from HBM.
-NCU_DRAM_BYTES = {"g_s.4|tc": 1.612476e9 + 1.565251e9, "g_a.2|tc": 1.612066e9 + 0.391675e9, "g_a.0|tc": 0.408368e9 + 1.556180e9,
-                  "g_s.6|tc": 1.611466e9 + 0.288178e9}
+# committed `ncu --set full` capture profiles/r02_ncu_conv_tc_full.csv (batch 64 x 768x512).  NOT equal to the algorithmic bytes
+# for the transposed convolutions: their four output phases each stream the input once (tiles are phase-major), so g_s.4 reads
+# 1.61 GB for a 0.40 GB input (algorithmic: 0.40 + 1.57 GB = 1.97 GB, measured 3.18 GB = 1.6x); the strided convolutions and the
+# edge layers read their input once.
+NCU_DRAM_BYTES = {"g_s.4|tc": 1.611681e9 + 1.569827e9, "g_a.2|tc": 1.613883e9 + 0.390282e9, "g_a.0|tc": 0.408379e9 + 1.557423e9,
+                  "g_s.6|tc": 1.621646e9 + 0.289706e9, "g_s.2|tc": 0.401357e9 + 0.361804e9}
+NCU_SOURCE = "profiles/r02_ncu_conv_tc_full.csv (ncu --set full, profiles/_fwd_once.py, bytes per launch)"
 
 
 def shard_range(total: int, rank: int, world: int):
@@ -123,12 +126,12 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None, "reasons": reasons}
 
 
-def cpu_reference_throughput(batch: int, steps: int, warmup: int):
-    """Reference CPU path (oracle/torch_port.py) on all host cores; returns (img/s, ms_per_step, cores)."""
+def cpu_reference_throughput(batch: int, steps: int, warmup: int, threads: int = 0):
+    """Reference CPU path (oracle/torch_port.py) on `threads` host threads (0 = all cores); returns (img/s, ms_per_step, cores)."""
     import torch
     from oracle import torch_port as tp
     import mmcodec
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     net = mmcodec.build_model(ARCH, QUALITY).eval()
@@ -581,7 +584,7 @@ def main():
         roofline = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf,
                     "traffic": NCU_DRAM_BYTES.get(name) if (args.workload == "hyperprior" and B == 64) else None,
-                    "traffic_source": "profiles/r01_ncu_conv_tc_full.csv (ncu --set full, same command, bytes per launch)", "peak_source": peak_src,
+                    "traffic_source": NCU_SOURCE, "peak_source": peak_src,
                     "ms_per_launch": ms, "flops_per_launch": f,
                     "step_tflops": total_f / (ms_total / args.steps * 1e-3) / 1e12,
                     "layer_ms": {k: round(v[0], 4) for k, v in layer_prof.items()}}
@@ -612,6 +615,28 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"3 steps of 2 images (same model/resolution) on {cores} host threads, torch CPU ops",
                                 "bpp": cpu_bpp}
+        # the reference's own evaluation setting is ONE thread (utils/eval_model/__main__t.py:61 torch.set_num_threads(1))
+        with contextlib.redirect_stdout(io.StringIO()):
+            v1, ms1, _, _ = cpu_reference_throughput(1, 2, 1, threads=1)
+        line["cpu_baseline_1thread"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": "2 steps of 1 image, torch CPU ops, torch.set_num_threads(1) as in eval_model/__main__t.py:61"}
+        if args.workload == "hyperprior":
+            # the reference's GPU execution path: the same op sequence on stock PyTorch (cuDNN / ATen) on THIS B200 -- fp32 NCHW as
+            # the reference runs it, TF32 allowed, and bf16 autocast + channels_last, its fastest stock configuration
+            # (profiles/probe_torch_cuda.py: torch.nn.functional only, random weights; no kernel of this repository involved)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "profiles"))
+                import probe_torch_cuda
+                tg = probe_torch_cuda.measure(B, steps=5, dev=dev)
+                best = min(tg["fp32_nchw_ms"], tg["tf32_nchw_ms"], tg["bf16_autocast_channels_last_ms"])
+                line["torch_gpu_baseline"] = {
+                    "unit": UNIT, "batch": B,
+                    "fp32_nchw": B / tg["fp32_nchw_ms"] * 1e3, "tf32_nchw": B / tg["tf32_nchw_ms"] * 1e3,
+                    "bf16_autocast_channels_last": B / tg["bf16_autocast_channels_last_ms"] * 1e3,
+                    "value": B / best * 1e3, "speedup_device_resident": (ms_total / args.steps) and best / (ms_total / args.steps),
+                    "what": "stock torch 2.11 ops (cuDNN convolutions, ATen elementwise) on the same GPU, device-resident batch, 5 timed steps after 3 warm-ups"}
+            except Exception as e:  # the record must not take the headline line down
+                line["torch_gpu_baseline"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

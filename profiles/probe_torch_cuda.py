@@ -6,23 +6,28 @@ import math, sys, time
 import torch
 import torch.nn.functional as F
 
-dev = torch.device("cuda", 0)
-N, M, B, H, W = 128, 192, int(sys.argv[1]) if len(sys.argv) > 1 else 64, 512, 768
-g = torch.Generator(device="cpu").manual_seed(0)
-def w(*s): return (torch.randn(*s, generator=g) / math.sqrt(s[1] * s[2] * s[3])).to(dev)
-P = {}
-for i, (ci, co) in enumerate([(3, N), (N, N), (N, N), (N, M)]):
-    P[f"ga{i}"] = (w(co, ci, 5, 5), torch.zeros(co, device=dev))
-for i, (ci, co) in enumerate([(M, N), (N, N), (N, N), (N, 3)]):
-    P[f"gs{i}"] = (w(ci, co, 5, 5), torch.zeros(co, device=dev))
-for i in range(3):
-    P[f"gdn_a{i}"] = (torch.ones(N, device=dev), 0.1 * torch.eye(N, device=dev).reshape(N, N, 1, 1))
-    P[f"gdn_s{i}"] = (torch.ones(N, device=dev), 0.1 * torch.eye(N, device=dev).reshape(N, N, 1, 1))
-P["ha0"] = (w(N, M, 3, 3), torch.zeros(N, device=dev)); P["ha1"] = (w(N, N, 5, 5), torch.zeros(N, device=dev)); P["ha2"] = (w(N, N, 5, 5), torch.zeros(N, device=dev))
-P["hs0"] = (w(N, N, 5, 5), torch.zeros(N, device=dev)); P["hs1"] = (w(N, N, 5, 5), torch.zeros(N, device=dev)); P["hs2"] = (w(M, N, 3, 3), torch.zeros(M, device=dev))
-eb_m = [torch.randn(N, 3, 1, device=dev), torch.randn(N, 3, 3, device=dev), torch.randn(N, 3, 3, device=dev), torch.randn(N, 3, 3, device=dev), torch.randn(N, 1, 3, device=dev)]
-eb_b = [torch.randn(N, 3, 1, device=dev) for _ in range(4)] + [torch.randn(N, 1, 1, device=dev)]
-eb_f = [torch.randn(N, 3, 1, device=dev) for _ in range(4)]
+N, M, H, W = 128, 192, 512, 768
+P, eb_m, eb_b, eb_f = {}, [], [], []
+
+
+def build(dev):
+    """random weights of the architecture (no checkpoint, no repo code)"""
+    g = torch.Generator(device="cpu").manual_seed(0)
+    def w(*s): return (torch.randn(*s, generator=g) / math.sqrt(s[1] * s[2] * s[3])).to(dev)
+    P.clear()
+    for i, (ci, co) in enumerate([(3, N), (N, N), (N, N), (N, M)]):
+        P[f"ga{i}"] = (w(co, ci, 5, 5), torch.zeros(co, device=dev))
+    for i, (ci, co) in enumerate([(M, N), (N, N), (N, N), (N, 3)]):
+        P[f"gs{i}"] = (w(ci, co, 5, 5), torch.zeros(co, device=dev))
+    for i in range(3):
+        P[f"gdn_a{i}"] = (torch.ones(N, device=dev), 0.1 * torch.eye(N, device=dev).reshape(N, N, 1, 1))
+        P[f"gdn_s{i}"] = (torch.ones(N, device=dev), 0.1 * torch.eye(N, device=dev).reshape(N, N, 1, 1))
+    P["ha0"] = (w(N, M, 3, 3), torch.zeros(N, device=dev)); P["ha1"] = (w(N, N, 5, 5), torch.zeros(N, device=dev)); P["ha2"] = (w(N, N, 5, 5), torch.zeros(N, device=dev))
+    P["hs0"] = (w(N, N, 5, 5), torch.zeros(N, device=dev)); P["hs1"] = (w(N, N, 5, 5), torch.zeros(N, device=dev)); P["hs2"] = (w(M, N, 3, 3), torch.zeros(M, device=dev))
+    eb_m[:] = [torch.randn(N, 3, 1, device=dev), torch.randn(N, 3, 3, device=dev), torch.randn(N, 3, 3, device=dev), torch.randn(N, 3, 3, device=dev), torch.randn(N, 1, 3, device=dev)]
+    eb_b[:] = [torch.randn(N, 3, 1, device=dev) for _ in range(4)] + [torch.randn(N, 1, 1, device=dev)]
+    eb_f[:] = [torch.randn(N, 3, 1, device=dev) for _ in range(4)]
+
 
 def gdn(x, p, inverse=False):
     beta, gamma = p
@@ -75,18 +80,35 @@ def timeit(fn, x, n=5):
         e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
-torch.backends.cudnn.benchmark = True
-x = torch.rand(B, 3, H, W, device=dev)
-ms = timeit(forward, x)
-print(f"torch fp32 NCHW (TF32 off): {ms:.2f} ms per {B} images = {B / ms * 1e3:.0f} img/s")
-torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
-ms = timeit(forward, x)
-print(f"torch fp32 NCHW (TF32 on):  {ms:.2f} ms per {B} images = {B / ms * 1e3:.0f} img/s")
-xcl = x.contiguous(memory_format=torch.channels_last)
-def fwd_bf16(t):
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        return forward(t)
-for k in P:
-    if P[k][0].dim() == 4: P[k] = (P[k][0].contiguous(memory_format=torch.channels_last), P[k][1])
-ms = timeit(fwd_bf16, xcl)
-print(f"torch bf16 autocast channels_last: {ms:.2f} ms per {B} images = {B / ms * 1e3:.0f} img/s")
+def measure(B=64, steps=5, dev=None):
+    """ms per batch of B images for the three stock configurations; restores the TF32 switches it touches"""
+    dev = dev or torch.device("cuda", torch.cuda.current_device())
+    build(dev)
+    saved = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    out = {"batch": B, "steps": steps}
+    try:
+        torch.backends.cudnn.benchmark = True
+        torch.backends.cuda.matmul.allow_tf32 = False; torch.backends.cudnn.allow_tf32 = False
+        x = torch.rand(B, 3, H, W, device=dev)
+        out["fp32_nchw_ms"] = timeit(forward, x, steps)
+        torch.backends.cuda.matmul.allow_tf32 = True; torch.backends.cudnn.allow_tf32 = True
+        out["tf32_nchw_ms"] = timeit(forward, x, steps)
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        def fwd_bf16(t):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return forward(t)
+        for k in P:
+            if P[k][0].dim() == 4: P[k] = (P[k][0].contiguous(memory_format=torch.channels_last), P[k][1])
+        out["bf16_autocast_channels_last_ms"] = timeit(fwd_bf16, xcl, steps)
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+        P.clear()
+        torch.cuda.empty_cache()
+    return out
+
+
+if __name__ == "__main__":
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    r = measure(B)
+    for k in ("fp32_nchw_ms", "tf32_nchw_ms", "bf16_autocast_channels_last_ms"):
+        print(f"torch {k[:-3]}: {r[k]:.2f} ms per {B} images = {B / r[k] * 1e3:.0f} img/s")
