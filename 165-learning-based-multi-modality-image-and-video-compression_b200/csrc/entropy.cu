@@ -142,34 +142,57 @@ __global__ void __launch_bounds__(kBlock) channel_indexes_kernel(ChanIndex ci, i
 
 // build_indexes: the sorted table sits in shared memory; idx = (L-1) - #{k < L-1 : s <= t_k}.
 // The table is sorted ascending (validated by the reference constructor, entropy_models.py:599),
-// so the count equals (L-1) - lower_bound position: a branch-free binary search.  NaN compares
-// false everywhere -> L-1, as in the reference.
+// so the count equals the lower_bound position of s in the first L-1 entries (a log2 guess corrected against the table, see
+// below).  NaN compares false everywhere -> L-1, as in the reference.
 template <bool kVec>
 __global__ void __launch_bounds__(kBlock) build_indexes_kernel(const float *__restrict__ scales,
                                                                const float *__restrict__ table, int levels,
                                                                float bound, int64_t n, int32_t *__restrict__ out)
 {
-    __shared__ float tab[256];
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) tab[k] = (k < levels - 1) ? table[k] : __int_as_float(0x7f800000);
+    // One copy of the table per shared-memory bank (entry k of lane l at word 32 k + l): the eight probes of the search are
+    // data-dependent, and with a single copy the 32 lanes of a warp hit random banks (~4-way conflicts: the kernel ran at 39 % of
+    // the HBM peak, LDS-bound); with a private bank per lane every probe is one conflict-free wavefront.
+    __shared__ float tab[256 * 32];
+    const int nrep = (levels - 1 > 0 ? levels - 1 : 0);
+    for (int k = threadIdx.x; k < nrep * 32; k += blockDim.x) tab[k] = table[k >> 5];
     __syncthreads();
     const int L1 = levels - 1;
+    const int lane = threadIdx.x & 31;
+    // The reference's table is geometric (exp(linspace(log lo, log hi, L)), models/google.py:32-34), so log2(s) lands within one
+    // entry of the answer; the exact position is then fixed up against the TABLE ITSELF (never recomputed: bit-exact for any
+    // sorted table, a non-geometric one just walks further).  ~15 instructions per element instead of an 8-probe binary
+    // search (~55: the kernel was issue-bound at 39 % of the HBM peak).
+    float l0 = 0.0f, inv = 0.0f;
+    if (L1 >= 2 && table[0] > 0.0f && table[L1 - 1] > table[0]) {
+        l0 = __log2f(table[0]);
+        inv = (float)(L1 - 1) / (__log2f(table[L1 - 1]) - l0);
+    }
     auto one = [&](float sv) -> int32_t {
         float s = lower_bound_f(sv, bound);
         if (s != s) return L1;
         // first position p in [0, L1] with tab[p] >= s  (count of entries < s)
-        int lo = 0;
-#pragma unroll
-        for (int step = 128; step > 0; step >>= 1) {
-            int probe = lo + step;
-            if (probe <= L1 && tab[probe - 1] < s) lo = probe;
-        }
-        return lo;
+        int p = __float2int_ru((__log2f(s) - l0) * inv);
+        p = min(max(p, 0), L1);
+        while (p > 0 && !(tab[((p - 1) << 5) + lane] < s)) --p;
+        while (p < L1 && tab[(p << 5) + lane] < s) ++p;
+        return p;
     };
     int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     if (kVec) {
+        // four independent 16-byte loads in flight per thread before the (dependent, ~250-cycle) searches start: with one load per
+        // iteration the kernel was latency-bound (28 KB in flight per SM)
         int64_t n4 = n >> 2;
-        for (int64_t v = tid; v < n4; v += stride) {
+        int64_t v = tid;
+        for (; v + 3 * stride < n4; v += 4 * stride) {
+            float4 s[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s[u] = ldg_stream(reinterpret_cast<const float4 *>(scales) + v + u * stride);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                reinterpret_cast<int4 *>(out)[v + u * stride] = make_int4(one(s[u].x), one(s[u].y), one(s[u].z), one(s[u].w));
+        }
+        for (; v < n4; v += stride) {
             float4 s = ldg_stream(reinterpret_cast<const float4 *>(scales) + v);
             int4 o = make_int4(one(s.x), one(s.y), one(s.z), one(s.w));
             reinterpret_cast<int4 *>(out)[v] = o;
@@ -887,7 +910,7 @@ int mmc_build_indexes(const float *scales, const float *table, int levels, float
     MMC_CHECK_ARG(n >= 0, "mmc_build_indexes: n < 0");
     if (n == 0) return MMC_OK;
     MMC_CHECK_ARG(scales && table && out, "mmc_build_indexes: NULL buffer");
-    int grid = elementwise_grid((n + 3) / 4, kBlock);
+    int grid = elementwise_grid((n + 15) / 16, kBlock);      // 4 float4 per thread and iteration
     if (aligned16(scales) && aligned16(out))
         build_indexes_kernel<true><<<grid, kBlock, 0, (cudaStream_t)stream>>>(scales, table, levels, bound, n, out);
     else

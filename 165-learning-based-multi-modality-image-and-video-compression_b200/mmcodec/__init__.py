@@ -14,9 +14,10 @@
 
 All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
 """
-from . import _lib, entropy_models, graphs, host_pipeline, layers, models, models_master, models_mm, models_video, ops, training, transforms, transforms_functional  # noqa: F401
+from . import _lib, compress_pipeline, entropy_models, graphs, host_pipeline, layers, models, models_master, models_mm, models_video, ops, training, transforms, transforms_functional  # noqa: F401
 from .graphs import GraphedForward  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401
+from .compress_pipeline import CompressPipeline  # noqa: F401
 from ._lib import MmcodecError, build  # noqa: F401
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional  # noqa: F401
 from .layers import GDN, LowerBound, NonNegativeParametrizer, conv, deconv  # noqa: F401

@@ -69,7 +69,10 @@ class CompressionModel(nn.Module):
         if self.training:
             v_hat, lik = AG.eb_forward(v, eb, self._draw("z", v))
             return AG.cast_bf16(v_hat), lik
-        _, lik, v_hat_bf16 = ops.eb_forward(v, eb._params(), None, eb._lik_bound(), want_bf16=True, lut=eb._eval_lut())
+        self.begin_forward()                    # the bottleneck is the first entropy stage of every zoo forward: new sum
+        acc = self._bits_accumulator(v)
+        _, lik, v_hat_bf16 = ops.eb_forward(v, eb._params(), None, eb._lik_bound(), want_bf16=True, lut=eb._eval_lut(), bits=acc)
+        lik._mmc_bits_total = acc
         return v_hat_bf16, lik
 
     def _conditional(self, y: Tensor, scales: Tensor, means):
@@ -79,8 +82,23 @@ class CompressionModel(nn.Module):
         if self.training:
             y_hat, lik = AG.gc_forward(y, scales, means, self._draw("y", y), bound, lb)
             return AG.cast_bf16(y_hat), lik
-        _, lik, y_hat_bf16 = ops.gc_forward(y, scales, means, None, bound, lb, want_bf16=True)
+        acc = self._bits_accumulator(y)
+        _, lik, y_hat_bf16 = ops.gc_forward(y, scales, means, None, bound, lb, want_bf16=True, bits=acc)
+        lik._mmc_bits_total = acc
         return y_hat_bf16, lik
+
+    def _bits_accumulator(self, like: Tensor) -> Tensor:
+        """Eval forward: -sum(log2 likelihood) of ALL likelihood tensors of one forward accumulates into one fp32 scalar inside the
+        entropy kernels (warp-shuffle + one atomic per CTA) and travels with the returned tensors as ``_mmc_bits_total``;
+        ``bpp(out)`` then needs no second pass over them.  ``_bottleneck`` (the first entropy stage of a forward) starts a new sum."""
+        acc = getattr(self, "_bits_acc", None)
+        if acc is None or acc.device != like.device:
+            acc = torch.zeros(1, dtype=torch.float32, device=like.device)
+            object.__setattr__(self, "_bits_acc", acc)
+        return acc
+
+    def begin_forward(self):
+        object.__setattr__(self, "_bits_acc", None)
 
     def _draw(self, key: str, like: Tensor) -> Tensor:
         noise = getattr(self, "_noise_override", None) or {}
@@ -112,9 +130,14 @@ class CompressionModel(nn.Module):
     def bpp(out, num_pixels=None) -> float:
         """sum over likelihood tensors of log(l).sum() / (-ln2 * pixels)
         (compressai/utils/eval_model/__main__t.py:197-200), reduced on the device."""
-        acc = None
-        for lk in out["likelihoods"].values():
-            acc = ops.bits(lk, acc)
+        liks = list(out["likelihoods"].values())
+        fused = [getattr(lk, "_mmc_bits_total", None) for lk in liks]
+        if liks and fused[0] is not None and all(f is fused[0] for f in fused):
+            acc = fused[0]                      # summed inside the entropy kernels of the forward that produced `out`
+        else:
+            acc = None
+            for lk in liks:
+                acc = ops.bits(lk, acc)
         if num_pixels is None:
             x = out["x_hat"]
             num_pixels = x.size(0) * x.size(2) * x.size(3)

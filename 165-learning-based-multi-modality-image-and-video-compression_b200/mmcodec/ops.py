@@ -95,7 +95,8 @@ def quantize_symbols(x: Tensor, means: Optional[Tensor] = None) -> Tensor:
         xv, outer, C, inner = _view_oci(x)
     mode, m = _means_arg(xv, means, C)
     out = torch.empty_like(xv, dtype=torch.int32)
-    L.check(L.lib().mmc_quantize_symbols(_ptr(xv), _ptr(m), mode, outer, C, inner, _ptr(out), _stream()))
+    with _Timed("quantize_symbols|entropy", xv.numel() * (8.0 + (4.0 if mode == L.MEANS_FULL else 0.0))):
+        L.check(L.lib().mmc_quantize_symbols(_ptr(xv), _ptr(m), mode, outer, C, inner, _ptr(out), _stream()))
     return out
 
 
@@ -132,7 +133,8 @@ def dequantize(symbols: Tensor, means: Optional[Tensor] = None) -> Tensor:
         sv, outer, C, inner = _view_oci(s)
     mode, m = _means_arg(sv, means, C)
     out = torch.empty_like(sv, dtype=torch.float32)
-    L.check(L.lib().mmc_dequantize(_ptr(sv), _ptr(m), mode, outer, C, inner, _ptr(out), _stream()))
+    with _Timed("dequantize|entropy", sv.numel() * (8.0 + (4.0 if mode == L.MEANS_FULL else 0.0))):
+        L.check(L.lib().mmc_dequantize(_ptr(sv), _ptr(m), mode, outer, C, inner, _ptr(out), _stream()))
     return out
 
 
@@ -160,7 +162,8 @@ def build_indexes(scales: Tensor, scale_table: Tensor, bound: float) -> Tensor:
         s = s.contiguous()
     table = _f32c(scale_table)
     out = torch.empty_like(s, dtype=torch.int32)
-    L.check(L.lib().mmc_build_indexes(_ptr(s), _ptr(table), table.numel(), float(bound), s.numel(), _ptr(out), _stream()))
+    with _Timed("build_indexes|entropy", s.numel() * 8.0):
+        L.check(L.lib().mmc_build_indexes(_ptr(s), _ptr(table), table.numel(), float(bound), s.numel(), _ptr(out), _stream()))
     return out
 
 
@@ -171,7 +174,8 @@ def channel_indexes(size, device) -> Tensor:
     _require_cuda(out)
     C = size[1]
     inner = int(np.prod(size[2:])) if len(size) > 2 else 1
-    L.check(L.lib().mmc_channel_indexes(size[0], C, inner, _ptr(out), _stream()))
+    with _Timed("channel_indexes|entropy", out.numel() * 4.0):
+        L.check(L.lib().mmc_channel_indexes(size[0], C, inner, _ptr(out), _stream()))
     return out
 
 
@@ -215,11 +219,11 @@ def eb_forward(x: Tensor, params, noise: Optional[Tensor] = None, likelihood_bou
     lik = torch.empty_like(xv)
     xb = torch.empty_like(xv, dtype=torch.bfloat16) if want_bf16 else None
     if lut is not None and nz is None:
-        with _Timed("entropy_bottleneck|eb_lut"):
+        with _Timed("entropy_bottleneck|eb_lut", xv.numel() * (12.0 + (2.0 if want_bf16 else 0.0))):
             L.check(L.lib().mmc_eb_forward_lut(_ptr(xv), ctypes.byref(p), _ptr(lut), EB_LUT_HALF_WIDTH, float(likelihood_bound),
                                                outer, C, inner, _ptr(x_hat), _ptr(xb), _ptr(lik), _ptr(bits), _stream()))
         return (x_hat, lik, xb) if want_bf16 else (x_hat, lik)
-    with _Timed("entropy_bottleneck|eb"):
+    with _Timed("entropy_bottleneck|eb", xv.numel() * (12.0 + (4.0 if nz is not None else 0.0) + (2.0 if want_bf16 else 0.0))):
         L.check(L.lib().mmc_eb_forward(_ptr(xv), _ptr(nz), ctypes.byref(p), float(likelihood_bound), outer, C, inner,
                                        _ptr(x_hat), _ptr(xb), _ptr(lik), _ptr(bits), _stream()))
     return (x_hat, lik, xb) if want_bf16 else (x_hat, lik)
@@ -249,7 +253,7 @@ def gc_forward(x: Tensor, scales: Tensor, means: Optional[Tensor] = None, noise:
     x_hat = torch.empty_like(xv)
     lik = torch.empty_like(xv)
     xb = torch.empty_like(xv, dtype=torch.bfloat16) if want_bf16 else None
-    with _Timed("gaussian_conditional|gc"):
+    with _Timed("gaussian_conditional|gc", xv.numel() * (16.0 + (4.0 if m is not None else 0.0) + (4.0 if nz is not None else 0.0) + (2.0 if want_bf16 else 0.0))):
         L.check(L.lib().mmc_gc_forward(_ptr(xv), _ptr(s), _ptr(m), _ptr(nz), float(scale_bound), float(likelihood_bound),
                                        xv.numel(), _ptr(x_hat), _ptr(xb), _ptr(lik), _ptr(bits), _stream()))
     return (x_hat, lik, xb) if want_bf16 else (x_hat, lik)
@@ -296,13 +300,42 @@ def _i32np(t):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+_host_stage = __import__("threading").local()
+
+
+def _stage_i32(tensors):
+    """int32 host arrays in LOGICAL (N, C, ...) order for the coder.  CUDA tensors are put in that order on the device (the
+    symbol / index tensors are channels-last there; transposing 21 MB per image batch on the host cost more than coding it),
+    copied asynchronously into cached pinned buffers and waited for once."""
+    cache = getattr(_host_stage, "bufs", None)
+    if cache is None:
+        cache = _host_stage.bufs = {}
+    out, pending = [], False
+    for slot, t in enumerate(tensors):
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            t = t.detach()
+            t = (t if t.dtype == torch.int32 else t.int()).contiguous()
+            buf = cache.get(slot)
+            if buf is None or buf.numel() < t.numel():
+                buf = cache[slot] = torch.empty(max(t.numel(), 1), dtype=torch.int32).pin_memory()
+            view = buf[: t.numel()].view(t.shape)
+            view.copy_(t, non_blocking=True)
+            out.append(view)
+            pending = True
+        else:
+            out.append(t)
+    if pending:
+        torch.cuda.current_stream().synchronize()
+    return [_i32np(t) for t in out]
+
+
 def rans_encode(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_lengths: Tensor, offsets: Tensor):
     """compressai.ans.RansEncoder.encode_with_indexes for every image of a batch (rans_interface.cpp:108-213);
     symbols / indexes are (B, ...) int32 tensors (any device), returns a list of B byte strings."""
-    sym, idx = _i32np(symbols), _i32np(indexes)
+    sym, idx = _stage_i32((symbols, indexes))
     B = sym.shape[0]
     n = sym[0].size if B else 0
-    tab, lens, offs = _i32np(cdf), _i32np(cdf_lengths).reshape(-1), _i32np(offsets).reshape(-1)
+    tab, lens, offs = _coder_tables_host(cdf, cdf_lengths, offsets)
     nbytes = np.zeros(max(B, 1), dtype=np.uint64)
     cap = 4 * n + 64
     for _ in range(2):
@@ -317,13 +350,29 @@ def rans_encode(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_lengths: Tens
     return [out[b, : int(nbytes[b])].tobytes() for b in range(B)]
 
 
+_tables_host_cache = {}
+
+
+def _coder_tables_host(cdf: Tensor, cdf_lengths: Tensor, offsets: Tensor):
+    """Host int32 copies of the CDF tables, cached per (storage, version): three small device->host copies per call otherwise."""
+    if not isinstance(cdf, torch.Tensor):
+        return _i32np(cdf), _i32np(cdf_lengths).reshape(-1), _i32np(offsets).reshape(-1)
+    key = (cdf.data_ptr(), cdf._version, cdf_lengths.data_ptr(), cdf_lengths._version, offsets.data_ptr(), offsets._version, tuple(cdf.shape))
+    hit = _tables_host_cache.get(key)
+    if hit is None:
+        if len(_tables_host_cache) > 32:
+            _tables_host_cache.clear()
+        hit = _tables_host_cache[key] = (_i32np(cdf), _i32np(cdf_lengths).reshape(-1), _i32np(offsets).reshape(-1))
+    return hit
+
+
 def rans_decode(strings, indexes: Tensor, cdf: Tensor, cdf_lengths: Tensor, offsets: Tensor) -> Tensor:
     """compressai.ans.RansDecoder.decode_with_indexes for a batch (rans_interface.cpp:215-284); returns int32 symbols
     shaped like `indexes`, on `indexes`' device."""
-    idx = _i32np(indexes)
+    (idx,) = _stage_i32((indexes,))
     B = idx.shape[0]
     n = idx[0].size if B else 0
-    tab, lens, offs = _i32np(cdf), _i32np(cdf_lengths).reshape(-1), _i32np(offsets).reshape(-1)
+    tab, lens, offs = _coder_tables_host(cdf, cdf_lengths, offsets)
     blob = np.frombuffer(b"".join(strings), dtype=np.uint8) if strings else np.zeros(0, np.uint8)
     blob = np.ascontiguousarray(blob)
     sizes = np.array([len(s) for s in strings], dtype=np.uint64)
@@ -439,7 +488,7 @@ def pad_to_nhwc8(x: Tensor, d: L.ConvDesc) -> Tensor:
     hp, wp = ctypes.c_int(), ctypes.c_int()
     L.check(L.lib().mmc_conv_pad8_size(ctypes.byref(d), ctypes.byref(hp), ctypes.byref(wp)))
     out = torch.empty((B, hp.value, wp.value, 8), dtype=torch.bfloat16, device=x.device)
-    with _Timed("pad8|layout"):
+    with _Timed("pad8|layout", float(B) * (C * H * W * 4.0 + hp.value * wp.value * 16.0)):
         L.check(L.lib().mmc_pad_nchw_to_nhwc8(_ptr(x), B, C, H, W, d.k // 2, hp.value, wp.value, _ptr(out), _stream()))
     return out
 
@@ -835,12 +884,16 @@ def stop_profile(with_work: bool = False):
     acc, work = {}, {}
     for name, e0, e1, flops in rec:
         acc.setdefault(name, []).append(e0.elapsed_time(e1))
-        work[name] = flops
-    if with_work == "total":    # {name: (total ms, total FLOPs, launches)} over everything recorded
-        return {k: (sum(v), work[k] * len(v), len(v)) for k, v in acc.items()}
+        work[name] = work.get(name, 0.0) + flops
+    if with_work == "total":    # {name: (total ms, total work, launches)} over everything recorded
+        return {k: (sum(v), work[k], len(v)) for k, v in acc.items()}
     if with_work:
-        return {k: (sum(v) / len(v), work[k]) for k, v in acc.items()}
+        return {k: (sum(v) / len(v), work[k] / len(v)) for k, v in acc.items()}
     return {k: sum(v) / len(v) for k, v in acc.items()}
+
+
+# profile entries whose `work` is algorithmic BYTES (HBM-bound kernels), not FLOPs
+HBM_KERNEL_SUFFIXES = ("|entropy", "|gc", "|eb", "|eb_lut", "|layout")
 
 
 def conv_flops(d: L.ConvDesc) -> float:

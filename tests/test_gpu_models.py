@@ -280,6 +280,45 @@ def test_compress_decompress_round_trip(models_golden, arch, cls, N, M):
     #  floor, i.e. 30 estimated bits each, while the coder spends a few bypass nibbles on them.)
 
 
+def test_forward_bpp_from_fused_accumulator():
+    """Eval forward sums -log2(likelihood) inside the entropy kernels; bpp(out) uses that sum and equals the separate reduction pass
+    (taken on clones, which do not carry the accumulator), also on the second forward of the same module and under graph replay."""
+    net, _ = load(mmcodec.ScaleHyperprior, "hyperprior", 128, 192)
+    npix = 2 * 64 * 128
+    for seed in (50, 51):
+        x = torch.from_numpy(make_image(2, 64, 128, seed=seed)).to(dev())
+        with torch.no_grad():
+            out = net(x)
+        assert getattr(out["likelihoods"]["y"], "_mmc_bits_total", None) is out["likelihoods"]["z"]._mmc_bits_total
+        fused = net.bpp(out, npix)
+        plain = net.bpp({"x_hat": out["x_hat"], "likelihoods": {k: v.clone() for k, v in out["likelihoods"].items()}}, npix)
+        assert abs(fused - plain) / plain < 1e-5, (fused, plain)
+    g = mmcodec.GraphedForward(net, x)
+    for _ in range(2):
+        o = g(x)
+        torch.cuda.synchronize()
+        assert abs(net.bpp(o, npix) - plain) / plain < 1e-5
+
+
+def test_compress_pipeline_matches_compress():
+    """mmcodec.CompressPipeline (host coding of batch i overlapped with the GPU stage of batch i + 1): byte-identical to compress()."""
+    net, _ = load(mmcodec.MeanScaleHyperprior, "mean-scale", 192, 320)
+    xs = [torch.from_numpy(make_image(3, 64, 128, seed=40 + i)).to(dev()) for i in range(4)]
+    with torch.no_grad():
+        want = [net.compress(x) for x in xs]
+    pipe = mmcodec.CompressPipeline(net, depth=2)
+    got = [f.result() for f in [pipe.submit(x) for x in xs]]
+    pipe.close()
+    for w, g in zip(want, got):
+        assert g["strings"] == w["strings"] and tuple(g["shape"]) == tuple(w["shape"])
+    fnet, _ = load(mmcodec.FactorizedPrior, "factorized", 128, 192)
+    with torch.no_grad():
+        w = fnet.compress(xs[0])
+    fp = mmcodec.CompressPipeline(fnet)
+    assert fp.submit(xs[0]).result()["strings"] == w["strings"]
+    fp.close()
+
+
 def test_graphed_forward_replays_exactly():
     """mmcodec.GraphedForward: the whole forward captured as one CUDA graph gives the eager results, also on new inputs."""
     net, _ = load(mmcodec.MeanScaleHyperprior, "mean-scale", 192, 320)
