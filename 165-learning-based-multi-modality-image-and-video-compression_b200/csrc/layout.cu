@@ -45,6 +45,33 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __float2bfloat16_rn(x[i]);
 }
 
+// fp32 precision mode (mmcodec.precision("fp32")): x = hi + lo + O(2^-17 x) with hi = bf16(x), lo = bf16(x - hi).  One pixel row of C
+// fp32 channels becomes 3 C bf16 channels [hi | lo | hi]; against weights laid out [w_hi | w_hi | w_lo] along the input channels
+// the ordinary bf16 tensor-core convolution then accumulates x_hi w_hi + x_lo w_hi + x_hi w_lo in fp32: every term of the product
+// down to 2^-16 relative (~1e-5 on a layer output, against 4e-3 for plain bf16 operands and ~4e-4 for a single TF32 pass).
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float *__restrict__ x, int64_t pixels, int C, __nv_bfloat16 *__restrict__ y)
+{
+    const int cq = C >> 2;                                  // float4 groups per pixel
+    const int64_t n = pixels * cq;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t p = i / cq;
+        const int q = (int)(i - p * cq);
+        const float4 v = ldg_stream(reinterpret_cast<const float4 *>(x) + i);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hi[k] = __float2bfloat16_rn(f[k]);
+            lo[k] = __float2bfloat16_rn(f[k] - __bfloat162float(hi[k]));
+        }
+        __nv_bfloat16 *row = y + p * 3 * C + q * 4;
+        *reinterpret_cast<uint2 *>(row) = *reinterpret_cast<const uint2 *>(hi);
+        *reinterpret_cast<uint2 *>(row + C) = *reinterpret_cast<const uint2 *>(lo);
+        *reinterpret_cast<uint2 *>(row + 2 * C) = *reinterpret_cast<const uint2 *>(hi);
+    }
+}
+
 template <typename TIn, typename TOut>
 static int launch_transpose(const TIn *x, int64_t B, int C, int64_t HW, bool to_nhwc, TOut *y, cudaStream_t st, const char *name)
 {
@@ -76,6 +103,16 @@ int mmc_nhwc_bf16_to_nchw_f32(const void *x, int64_t B, int C, int64_t HW, float
 int mmc_nhwc_f32_to_nchw_f32(const float *x, int64_t B, int C, int64_t HW, float *y, void *stream)
 {
     return launch_transpose<float, float>(x, B, C, HW, false, y, (cudaStream_t)stream, "mmc_nhwc_f32_to_nchw_f32");
+}
+
+int mmc_split_f32_bf16x3(const float *x, int64_t pixels, int C, void *y, void *stream)
+{
+    MMC_CHECK_ARG(pixels >= 0 && C >= 4 && C % 4 == 0, "mmc_split_f32_bf16x3: C must be a positive multiple of 4");
+    if (pixels == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && y && aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 7u) == 0, "mmc_split_f32_bf16x3: NULL or unaligned buffer");
+    split_bf16x3_kernel<<<elementwise_grid(pixels * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(x, pixels, C, (__nv_bfloat16 *)y);
+    MMC_CHECK_LAUNCH("mmc_split_f32_bf16x3");
+    return MMC_OK;
 }
 
 int mmc_f32_to_bf16(const float *x, int64_t n, void *y, void *stream)

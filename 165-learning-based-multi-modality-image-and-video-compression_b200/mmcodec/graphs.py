@@ -19,6 +19,19 @@ from torch.utils import _pytree as pytree
 __all__ = ["GraphedForward"]
 
 
+def module_signature(modules):
+    """What a captured graph of these modules bakes in: version AND storage of every parameter and buffer (an optimizer step bumps
+    the version; ``net.to(...)``, ``p.data = ...`` or ``load_state_dict(assign=True)`` change the storage without touching it; the
+    scale table, the LowerBound bounds and the MaskedConv mask are buffers) plus the training flags.  The same key the per-module
+    caches (packed weights, LUTs, GDN re-parametrisation) use."""
+    sig = []
+    for m in modules:
+        for t in list(m.parameters()) + list(m.buffers()):
+            sig.append((t._version, t.data_ptr()))
+        sig.append(m.training)
+    return tuple(sig)
+
+
 class GraphedForward:
     def __init__(self, fn: Callable[..., Any], *example_inputs: Any, warmup: int = 2, modules=None):
         if modules is None and isinstance(fn, torch.nn.Module):
@@ -28,7 +41,7 @@ class GraphedForward:
         self._capture(fn, example_inputs)
 
     def _signature(self):
-        return tuple(p._version for m in self._modules for p in m.parameters()) + tuple(m.training for m in self._modules)
+        return module_signature(self._modules)
 
     def _capture(self, fn, example_inputs):
         warmup = self._warmup

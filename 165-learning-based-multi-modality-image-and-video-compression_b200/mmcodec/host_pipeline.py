@@ -62,7 +62,8 @@ class HostPipeline:
         mb = min(self.micro_batch, x_host.shape[0])
         shape = (mb,) + tuple(x_host.shape[1:])
         # the captured graphs read the packed weights / tables that existed at capture time: re-capture after any parameter update
-        sig = tuple(p._version for p in self.net.parameters()) + (self.net.training,)
+        from .graphs import module_signature
+        sig = module_signature([self.net])        # parameter AND buffer versions + storages (not just parameter versions)
         if sig != getattr(self, "_param_sig", None):
             self._graphs = None
             self._param_sig = sig

@@ -19,7 +19,7 @@ from . import autograd as AG
 from . import ops
 from .entropy_models import EntropyBottleneck, GaussianConditional
 from .layers import GDN, conv, deconv
-from .transforms import TransformStack, run_layers
+from .transforms import TransformStack, current_precision, run_layers
 
 __all__ = ["CompressionModel", "FactorizedPrior", "ScaleHyperprior", "MeanScaleHyperprior", "get_scale_table",
            "SCALES_MIN", "SCALES_MAX", "SCALES_LEVELS", "MODELS", "CFGS", "build_model"]
@@ -71,9 +71,10 @@ class CompressionModel(nn.Module):
             return AG.cast_bf16(v_hat), lik
         self.begin_forward()                    # the bottleneck is the first entropy stage of every zoo forward: new sum
         acc = self._bits_accumulator(v)
-        _, lik, v_hat_bf16 = ops.eb_forward(v, eb._params(), None, eb._lik_bound(), want_bf16=True, lut=eb._eval_lut(), bits=acc)
+        v_hat, lik, v_hat_bf16 = ops.eb_forward(v, eb._params(), None, eb._lik_bound(), want_bf16=True, lut=eb._eval_lut(), bits=acc)
         lik._mmc_bits_total = acc
-        return v_hat_bf16, lik
+        # precision("fp32"): the next transform takes the fp32 values (medians are not integers: bf16 would round them)
+        return (v_hat if current_precision() == "fp32" else v_hat_bf16), lik
 
     def _conditional(self, y: Tensor, scales: Tensor, means):
         """gaussian_conditional(y, scales, means) -> (y_hat as bf16, likelihoods)"""
@@ -83,9 +84,9 @@ class CompressionModel(nn.Module):
             y_hat, lik = AG.gc_forward(y, scales, means, self._draw("y", y), bound, lb)
             return AG.cast_bf16(y_hat), lik
         acc = self._bits_accumulator(y)
-        _, lik, y_hat_bf16 = ops.gc_forward(y, scales, means, None, bound, lb, want_bf16=True, bits=acc)
+        y_hat, lik, y_hat_bf16 = ops.gc_forward(y, scales, means, None, bound, lb, want_bf16=True, bits=acc)
         lik._mmc_bits_total = acc
-        return y_hat_bf16, lik
+        return (y_hat if current_precision() == "fp32" else y_hat_bf16), lik
 
     def _bits_accumulator(self, like: Tensor) -> Tensor:
         """Eval forward: -sum(log2 likelihood) of ALL likelihood tensors of one forward accumulates into one fp32 scalar inside the
@@ -144,6 +145,14 @@ class CompressionModel(nn.Module):
         return float(acc.item()) / num_pixels
 
 
+def _stack_input(t: Tensor) -> Tensor:
+    """logical (B, C, H, W) fp32 tensor -> the (B, H, W, C) input of the next transform stack: bf16 on the fast path, the fp32
+    values themselves under precision("fp32")"""
+    if current_precision() == "fp32":
+        return t.float().permute(0, 2, 3, 1).contiguous()
+    return ops.to_bf16(t).permute(0, 2, 3, 1).contiguous()
+
+
 def _g_a(N, M, channel):
     return TransformStack(conv(channel, N), GDN(N), conv(N, N), GDN(N), conv(N, N), GDN(N), conv(N, M))
 
@@ -200,7 +209,7 @@ class FactorizedPrior(CompressionModel):
         """models/google.py:201-205"""
         assert isinstance(strings, list) and len(strings) == 1
         y_hat = self.entropy_bottleneck.decompress(strings[0], shape)
-        x_hat = run_layers(list(self.g_s), ops.to_bf16(y_hat).permute(0, 2, 3, 1).contiguous(), "nhwc_bf16", "nchw_f32")
+        x_hat = run_layers(list(self.g_s), _stack_input(y_hat), "nhwc_bf16", "nchw_f32")
         return {"x_hat": x_hat.clamp_(0, 1)}
 
 
@@ -275,7 +284,7 @@ class ScaleHyperprior(CompressionModel):
         gc = self.gaussian_conditional
         y, z = self._analysis(x)
         z_symbols, z_indexes, z_hat = self._z_path(z)
-        z_hat_bf16 = ops.to_bf16(z_hat).permute(0, 2, 3, 1)
+        z_hat_bf16 = _stack_input(z_hat)
         scales_hat = _nhwc_to_logical(run_layers(list(self.h_s), z_hat_bf16, "nhwc_bf16", "nhwc_f32"))
         y_indexes = gc.build_indexes(scales_hat)
         y_symbols, y_indexes = gc.symbols_and_indexes(_nhwc_to_logical(y), y_indexes)
@@ -293,7 +302,7 @@ class ScaleHyperprior(CompressionModel):
         return {"strings": [y_strings, z_strings], "shape": c["shape"]}
 
     def _synthesis_from(self, y_hat):
-        x_hat = run_layers(list(self.g_s), ops.to_bf16(y_hat).permute(0, 2, 3, 1).contiguous(), "nhwc_bf16", "nchw_f32")
+        x_hat = run_layers(list(self.g_s), _stack_input(y_hat), "nhwc_bf16", "nchw_f32")
         return {"x_hat": x_hat.clamp_(0, 1)}
 
     def decompress(self, strings, shape):
@@ -301,7 +310,7 @@ class ScaleHyperprior(CompressionModel):
         assert isinstance(strings, list) and len(strings) == 2
         gc = self.gaussian_conditional
         z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
-        z_hat_bf16 = ops.to_bf16(z_hat).permute(0, 2, 3, 1).contiguous()
+        z_hat_bf16 = _stack_input(z_hat)
         scales_hat = _nhwc_to_logical(run_layers(list(self.h_s), z_hat_bf16, "nhwc_bf16", "nhwc_f32"))
         indexes = gc.build_indexes(scales_hat)
         y_hat = gc.decompress(strings[0], indexes, z_hat.dtype)
@@ -344,7 +353,7 @@ class MeanScaleHyperprior(ScaleHyperprior):
         gc = self.gaussian_conditional
         y, z = self._analysis(x)
         z_symbols, z_indexes, z_hat = self._z_path(z)
-        scales_hat, means_hat = self._gaussian_params(ops.to_bf16(z_hat).permute(0, 2, 3, 1))
+        scales_hat, means_hat = self._gaussian_params(_stack_input(z_hat))
         y_indexes = gc.build_indexes(_nhwc_to_logical(scales_hat))
         y_symbols, y_indexes = gc.symbols_and_indexes(_nhwc_to_logical(y), y_indexes, means=_nhwc_to_logical(means_hat))
         return {"y_symbols": y_symbols, "y_indexes": y_indexes, "z_symbols": z_symbols, "z_indexes": z_indexes,
@@ -355,7 +364,7 @@ class MeanScaleHyperprior(ScaleHyperprior):
         assert isinstance(strings, list) and len(strings) == 2
         gc = self.gaussian_conditional
         z_hat = self.entropy_bottleneck.decompress(strings[1], shape)
-        scales_hat, means_hat = self._gaussian_params(ops.to_bf16(z_hat).permute(0, 2, 3, 1).contiguous())
+        scales_hat, means_hat = self._gaussian_params(_stack_input(z_hat))
         scales_hat, means_hat = _nhwc_to_logical(scales_hat), _nhwc_to_logical(means_hat)
         indexes = gc.build_indexes(scales_hat)
         y_hat = gc.decompress(strings[0], indexes, means=means_hat)

@@ -513,6 +513,17 @@ def to_bf16(x: Tensor) -> Tensor:
     return y
 
 
+def split_bf16x3(x_nhwc: Tensor) -> Tensor:
+    """(B, H, W, C) fp32 -> (B, H, W, 3C) bf16 [hi | lo | hi] (fp32 precision mode, see mmc_split_f32_bf16x3)."""
+    _require_cuda(x_nhwc)
+    x = _f32c(x_nhwc)
+    B, H, W, C = x.shape
+    y = torch.empty((B, H, W, 3 * C), dtype=torch.bfloat16, device=x.device)
+    with _Timed("split_bf16x3|layout", x.numel() * 10.0):
+        L.check(L.lib().mmc_split_f32_bf16x3(_ptr(x), B * H * W, C, _ptr(y), _stream()))
+    return y
+
+
 def nhwc_bf16_to_nchw(x: Tensor) -> Tensor:
     _require_cuda(x)
     B, H, W, C = x.shape

@@ -26,6 +26,43 @@ FORMATS = ("nchw_f32", "nhwc_bf16", "nhwc_f32")
 # Set by mmcodec.config; tests flip it to cross-check the two kernels against each other.
 use_tensor_cores = True
 
+# Arithmetic of the transform stacks (BASELINE.json north_star: "bf16/tf32 with fp32 accumulate ... 1e-2 relative in bf16, 1e-4 in
+# fp32"): "bf16" = bf16 operands, fp32 accumulate, fused GDN (the fast path); "fp32" = every layer evaluated to ~1e-5 relative on
+# the SAME bf16 tensor-core kernel through a three-term operand split (see _run_layers_fp32), fp32 activations between layers,
+# fp32 GDN.  Inference only.
+_precision = "bf16"
+
+
+class precision:
+    """``with mmcodec.precision("fp32"): out = net(x)`` -- context manager (also usable as ``mmcodec.precision.set("fp32")``)."""
+
+    MODES = ("bf16", "fp32")
+
+    def __init__(self, mode: str):
+        if mode not in self.MODES:
+            raise ValueError(f'precision must be one of {self.MODES}, got "{mode}"')
+        self.mode = mode
+
+    def __enter__(self):
+        global _precision
+        self.prev, _precision = _precision, self.mode
+        return self
+
+    def __exit__(self, *a):
+        global _precision
+        _precision = self.prev
+
+    @classmethod
+    def set(cls, mode: str):
+        global _precision
+        if mode not in cls.MODES:
+            raise ValueError(f'precision must be one of {cls.MODES}, got "{mode}"')
+        _precision = mode
+
+
+def current_precision() -> str:
+    return _precision
+
 
 class QReLU8(nn.Module):
     """Marker for QReLU.apply(x, bit_depth=8, beta=100) (layers/layers.py:247-277; forward = clamp(x, 0, 255)) in a fused
@@ -112,11 +149,17 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0, _tra
     ops._require_cuda(x)
     if _train_dispatch and torch.is_grad_enabled() and pair is None:
         from . import autograd as AG
+        if AG.wants_grad(layers, x) and _precision == "fp32":
+            raise NotImplementedError('mmcodec.precision("fp32") is an inference mode; the training path computes in bf16 / fp32-accumulate')
         if AG.wants_grad(layers, x):
             return AG.run_layers_train(layers, x, in_fmt, out_fmt, out2)   # same kernels, recorded for backward
     steps = parse_layers(layers)
     if not steps:
         raise ValueError("empty transform stack")
+    if _precision == "fp32":
+        if pair is not None:
+            x = torch.cat((pair[0].float(), pair[1].float()), dim=-1)
+        return _run_layers_fp32(steps, x, in_fmt, out_fmt, out2)
     with torch.no_grad():
         cur, fmt = x, in_fmt
         if fmt == "nchw_f32":
@@ -187,6 +230,93 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0, _tra
             cur, fmt = out, ofmt
         if out_fmt == "nchw_f32" and fmt == "nhwc_f32":
             cur = cur.permute(0, 3, 1, 2)   # logical NCHW, channels-last memory
+        return (cur, y2) if out2 else cur
+
+
+def _fp32_shadow(conv: nn.Module) -> nn.Module:
+    """The layer with its input channels tripled and the weights laid out [w_hi | w_hi | w_lo] (w_hi = bf16(w), w_lo = bf16(w - w_hi)):
+    against activations split [x_hi | x_lo | x_hi] (ops.split_bf16x3) the bf16 tensor-core kernel accumulates
+    x_hi w_hi + x_lo w_hi + x_hi w_lo in fp32.  Derived data, rebuilt when the weight's version or storage changes."""
+    from .layers import Conv2d, ConvTranspose2d
+    key = (conv.weight._version, conv.weight.data_ptr())
+    cached = getattr(conv, "_mmc_fp32_shadow", None)
+    if cached is None or cached[0] != key:
+        w = conv.weight.detach().float()
+        hi = w.bfloat16().float()
+        lo = (w - hi).bfloat16().float()
+        k, s = conv.kernel_size[0], conv.stride[0]
+        with torch.device("meta"):
+            if isinstance(conv, nn.ConvTranspose2d):
+                m = ConvTranspose2d(3 * conv.in_channels, conv.out_channels, kernel_size=k, stride=s, padding=k // 2, output_padding=s - 1, bias=False)
+            else:
+                m = Conv2d(3 * conv.in_channels, conv.out_channels, kernel_size=k, stride=s, padding=k // 2, bias=False)
+        cat_dim = 0 if isinstance(conv, nn.ConvTranspose2d) else 1          # the input-channel dimension of the weight tensor
+        m._parameters["weight"] = nn.Parameter(torch.cat([hi, hi, lo], dim=cat_dim).contiguous(), requires_grad=False)
+        m._mmc_name = getattr(conv, "_mmc_name", "conv") + ".x3"
+        cached = (key, m)
+        object.__setattr__(conv, "_mmc_fp32_shadow", cached)    # not a registered child: no state_dict entry
+    return cached[1]
+
+
+def _run_layers_fp32(steps: List[Step], x: Tensor, in_fmt: str, out_fmt: str, out2: int):
+    """precision("fp32"): the stack with fp32 activations between layers (NHWC), each tensor-core-eligible conv / deconv as ONE bf16
+    tensor-core launch over three-term split operands (fp32 accumulate, bias and ReLU / LeakyReLU fused, fp32 out), GDN / IGDN
+    on the fp32 kernel (csrc/gdn.cu), the image-edge convolution (3 input channels) on the fp32 CUDA-core kernel with its GDN
+    fused.  Inputs may be fp32 whatever ``in_fmt`` says (the models hand fp32 latents on in this mode).  Outputs are fp32:
+    "nchw_f32" as in the fast path, "nhwc_f32" AND "nhwc_bf16" as (B, H, W, C) fp32; ``out2`` likewise fp32."""
+    with torch.no_grad():
+        cur = x.float()
+        nchw = in_fmt == "nchw_f32"
+        if nchw and cur.dim() != 4:
+            raise ValueError("expected a 4-D (B, C, H, W) input")
+        if nchw and ops._is_channels_last(cur):
+            cur, nchw = cur.permute(0, 2, 3, 1), False
+        cur = cur.contiguous()
+        for i, s in enumerate(steps):
+            last = i == len(steps) - 1
+            c = s.conv
+            cin, cout, stride, k = c.in_channels, c.out_channels, c.stride[0], c.kernel_size[0]
+            if nchw:
+                B, C, H, W = cur.shape
+            else:
+                B, H, W, C = cur.shape
+            if C != cin:
+                raise ValueError(f"expected {cin} input channels, got {C}")
+            bias = c.bias.detach().float() if c.bias is not None else None
+            name = getattr(c, "_mmc_name", "conv")
+            beta_eff = gamma_eff = None
+            if s.gdn is not None:
+                beta_eff, gamma_eff, _ = s.gdn.effective_params()
+            narrow = s.transposed and cout <= 4 and stride == 2 and last and out_fmt == "nchw_f32" and not out2
+            tc = use_tensor_cores and cin % 4 == 0 and _tc_eligible(3 * cin, cout, False) or \
+                (use_tensor_cores and narrow and cin % 8 == 0 and cin >= 32)
+            if tc:
+                if nchw:
+                    cur, nchw = cur.permute(0, 2, 3, 1).contiguous(), False
+                x3 = ops.split_bf16x3(cur)
+                sh = _fp32_shadow(c)
+                d3 = ops.conv_desc(s.transposed, B, H, W, 3 * cin, cout, k, stride, L.BF16, L.NHWC, L.F32, L.NCHW if narrow else L.NHWC,
+                                   act=s.act, gdn=L.GDN_NONE, out2=0)
+                cur = ops.conv_forward_tc(d3, x3, sh.packed_weight(d3), bias, None, None, name=name + ".x3")
+                nchw = narrow
+                if s.gdn is not None:
+                    cur = ops.gdn_forward(cur.permute(0, 3, 1, 2), beta_eff, gamma_eff, s.gdn.inverse).permute(0, 2, 3, 1)
+            else:
+                # image-edge / odd shapes: the fp32 CUDA-core kernel (GDN fused in fp32 when it fits)
+                planar_out = last and out_fmt == "nchw_f32" and cout <= 4
+                d = ops.conv_desc(s.transposed, B, H, W, cin, cout, k, stride, L.F32, L.NCHW if nchw else L.NHWC, L.F32,
+                                  L.NCHW if planar_out else L.NHWC, act=s.act,
+                                  gdn=(L.GDN_NONE if s.gdn is None else (L.GDN_INVERSE if s.gdn.inverse else L.GDN_FORWARD)), out2=0)
+                cur = ops.conv_forward_direct(d, cur, c.f32_weight(), bias, beta_eff, gamma_eff, name=name)
+                nchw = planar_out
+        y2 = None
+        if out2:
+            src = cur.permute(0, 2, 3, 1) if nchw else cur
+            y2 = torch.abs(src) if out2 == 1 else src
+        if out_fmt == "nchw_f32" and not nchw:
+            cur = cur.permute(0, 3, 1, 2)        # logical NCHW, channels-last memory (as on the fast path)
+        elif out_fmt != "nchw_f32" and nchw:
+            cur = cur.permute(0, 2, 3, 1).contiguous()
         return (cur, y2) if out2 else cur
 
 

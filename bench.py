@@ -459,6 +459,8 @@ def main():
     ap.add_argument("--workload", default="hyperprior", choices=sorted(WORKLOADS) + sorted(OTHER_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro-batch", type=int, default=8, help="images per pipelined micro-batch on the host-buffer path")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help='arithmetic of the transform stacks: bf16 operands (default) or mmcodec.precision("fp32") (three-term bf16 split, ~1e-5)')
     args = ap.parse_args()
 
     if args.workload in OTHER_WORKLOADS:
@@ -499,6 +501,7 @@ def main():
         init_nccl_quietly(dist, dev)
 
     numa = bind_to_gpu_numa_node(local_rank)
+    mmcodec.precision.set(args.precision)
     B = args.batch
     torch.manual_seed(0)
     net = mmcodec.build_model(ARCH, QUALITY).eval()
@@ -696,7 +699,8 @@ def main():
     metric = METRIC if args.workload == "hyperprior" else f"img/s ({W}x{H} {ARCH} {call})"
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16" if args.precision == "bf16" else "fp32 (bf16 x3 operand split on the bf16 tensor cores, fp32 accumulate and activations)",
+            "data": "synthetic",
             "config": bench_config(B, world),
             "bpp": bpp, "gpu_launches": launches, "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
