@@ -475,8 +475,12 @@ def conv_forward_tc(d: L.ConvDesc, x: Tensor, w_packed: Tensor, bias: Optional[T
     _require_cuda(x, w_packed)
     y, y2 = _alloc_out(d, x.device)
     with _Timed(name + "|tc", conv_flops(d) if _profile is not None else 0.0):
-        L.check(L.lib().mmc_conv_forward_tc(ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(beta_eff),
-                                            _ptr(gamma_bf16), _ptr(y), _ptr(y2), _stream()))
+        try:
+            L.check(L.lib().mmc_conv_forward_tc(ctypes.byref(d), _ptr(x), _ptr(w_packed), _ptr(bias), _ptr(beta_eff),
+                                                _ptr(gamma_bf16), _ptr(y), _ptr(y2), _stream()))
+        except L.MmcodecError as e:
+            raise L.MmcodecError(f"{e} [layer {name}: B={d.B} {d.H}x{d.W} {d.Cin}->{d.Cout} k{d.k} s{d.stride} "
+                                 f"{'deconv' if d.transposed else 'conv'} gdn={d.gdn}]") from None
     return (y, y2) if d.out2_bf16 else y
 
 

@@ -55,7 +55,11 @@ def configure_optimizers(net: nn.Module, learning_rate: float = 1e-4, aux_learni
 class GradBucketReducer:
     """Bucketed, overlapped gradient averaging over a process group (NCCL on GPUs, gloo in the CPU tests)."""
 
-    def __init__(self, params: Iterable[nn.Parameter], bucket_bytes: int = 32 << 20, group=None):
+    def __init__(self, params: Iterable[nn.Parameter], bucket_bytes: int = 32 << 20, group=None, flat: bool = False):
+        """``flat``: every parameter's ``.grad`` is a VIEW into a pre-allocated fp32 bucket buffer (call ``zero_()`` instead of
+        ``zero_grad(set_to_none=True)``); the collectives then run in place on the buckets -- no ``torch.cat`` flattening and no
+        copy-back (three passes over ~160 MB per step in the round-1 graphed data-parallel step).  Parameters that never receive
+        a gradient keep a zero gradient instead of ``None`` (Adam then leaves them unchanged, as it does for ``None``)."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         # reverse registration order ~ the order in which the backward pass produces gradients
@@ -71,6 +75,20 @@ class GradBucketReducer:
         if cur:
             self.buckets.append(cur)
         self.bucket_of = {i: b for b, idxs in enumerate(self.buckets) for i in idxs}
+        self.flat: Optional[List[Tensor]] = None
+        if flat and self.params:
+            self.flat = []
+            for idxs in self.buckets:
+                n = sum(self.params[i].numel() for i in idxs)
+                buf = torch.zeros(n, dtype=torch.float32, device=self.params[idxs[0]].device)
+                off = 0
+                for i in idxs:
+                    p = self.params[i]
+                    if p.dtype != torch.float32:
+                        raise TypeError("flat gradient buckets need fp32 parameters")
+                    p.grad = buf[off:off + p.numel()].view_as(p)
+                    off += p.numel()
+                self.flat.append(buf)
         self._ready = [0] * len(self.buckets)
         self._work: Dict[int, tuple] = {}
         self._stream = torch.cuda.Stream() if (self.params and self.params[0].is_cuda) else None
@@ -87,7 +105,26 @@ class GradBucketReducer:
                 self._launch(b)
         return hook
 
+    def zero_(self):
+        """flat mode: the replacement of ``zero_grad`` (one memset per bucket; the ``.grad`` views stay in place)"""
+        for buf in self.flat or []:
+            buf.zero_()
+
+    def _avg_op(self):
+        # NCCL averages inside the collective; gloo has no AVG: sum, then one in-place scale
+        return dist.ReduceOp.AVG if dist.get_backend(self.group) == "nccl" else dist.ReduceOp.SUM
+
     def _launch(self, b: int):
+        if self.flat is not None:
+            buf, op = self.flat[b], self._avg_op()
+            if self._stream is not None:
+                self._stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self._stream):
+                    work = dist.all_reduce(buf, op=op, group=self.group, async_op=True)
+            else:
+                work = dist.all_reduce(buf, op=op, group=self.group, async_op=True)
+            self._work[b] = (work, buf, None if op == dist.ReduceOp.AVG else "scale")
+            return
         grads = [self.params[i].grad for i in self.buckets[b] if self.params[i].grad is not None]
         if not grads:
             return
@@ -114,6 +151,10 @@ class GradBucketReducer:
             work.wait()
             if self._stream is not None:
                 torch.cuda.current_stream().wait_stream(self._stream)
+            if self.flat is not None:
+                if grads == "scale":
+                    flat.div_(self.world)
+                continue
             flat.div_(self.world)
             off = 0
             for g in grads:
@@ -126,6 +167,13 @@ class GradBucketReducer:
         """Average every existing gradient across the group, bucket by bucket, on the current stream (no overlap; used when the
         backward pass ran inside a CUDA graph and the hooks did not launch anything)."""
         if self.world == 1:
+            return
+        if self.flat is not None:
+            op = self._avg_op()
+            for buf in self.flat:
+                dist.all_reduce(buf, op=op, group=self.group)
+                if op != dist.ReduceOp.AVG:
+                    buf.div_(self.world)
             return
         for idxs in self.buckets:
             grads = [self.params[i].grad for i in idxs if self.params[i].grad is not None]
@@ -157,7 +205,8 @@ class TrainStep:
         self.criterion = RateDistortionLoss(quality)
         self.optimizer, self.aux_optimizer = configure_optimizers(net, learning_rate, aux_learning_rate, capturable)
         self.clip_max_norm = clip_max_norm
-        self.reducer = GradBucketReducer(net.parameters(), bucket_bytes, group)
+        # gradients live in flat fp32 buckets on the GPU: in-place collectives, one memset per bucket instead of zero_grad
+        self.reducer = GradBucketReducer(net.parameters(), bucket_bytes, group, flat=next(net.parameters()).is_cuda)
 
     def forward_backward(self, x: Tensor, guided: Optional[Tensor] = None) -> Dict[str, Tensor]:
         """Guide forward (no grad), forward, rate-distortion loss backward, aux loss backward; gradients are left in ``.grad``
@@ -167,8 +216,11 @@ class TrainStep:
         if self.guide is not None:
             with torch.no_grad():
                 hidden = self.guide(guided)["hidden"]
-        self.optimizer.zero_grad(set_to_none=True)
-        self.aux_optimizer.zero_grad(set_to_none=True)
+        if self.reducer.flat is not None:
+            self.reducer.zero_()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+            self.aux_optimizer.zero_grad(set_to_none=True)
         if hidden is not None and getattr(self.net, "forward_takes_guide_image", False):
             out_net = self.net(x, guided, hidden)
         else:

@@ -216,6 +216,54 @@ def copy_ceilings(x_host, dev, barrier, reps: int = 3):
     return res
 
 
+def train_step_record(dev, world, dist, steps: int = 5):
+    """Sub-record of the default line so that the driver's 1..8-GPU scaling run also exercises the ONE exchange step of the path
+    (BASELINE.json configs[3]): RGB + depth two-branch codec, 4 pairs of 768x512 per GPU, frozen guide forward, depth-branch
+    forward + backward, bucketed NCCL all-reduce of the fp32 gradients (in place on flat buckets), clip, Adam x2
+    (mmcodec.GraphedTrainStep).  Every rank runs it; device-timed, MAX over ranks."""
+    import torch
+    import mmcodec
+    torch.manual_seed(0)
+    net_r = mmcodec.JointAutoregressiveHierarchicalPriors_R(192, 192).eval()
+    net_d = mmcodec.JointAutoregressiveHierarchicalPriors_D(192, 192)
+    for n in (net_r, net_d):
+        n.update()
+        n.to(dev)
+    units = 4
+    gen = torch.Generator().manual_seed(99 + int(os.environ.get("RANK", "0")))
+    rgb = torch.rand(units, 3, 512, 768, generator=gen).to(dev)
+    depth = torch.rand(units, 1, 512, 768, generator=gen).to(dev)
+    step = mmcodec.GraphedTrainStep(net_d, net_r, warmup=2, quality=3)
+    for _ in range(4):                      # two eager optimisation steps, the capture, one replay
+        out = step(depth, rgb)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = step(depth, rgb)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    red = step.step.reducer
+    grad_bytes = sum(b.numel() * 4 for b in (red.flat or []))
+    loss = float(out["loss"])
+    del step, net_r, net_d
+    torch.cuda.empty_cache()
+    return {"metric": "pairs/s (RGB + depth 768x512 training step)", "value": units * world / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+            "steps": steps, "pairs_per_gpu": units, "scaling": "weak", "loss": loss,
+            "all_reduce_bytes_per_step": grad_bytes if world > 1 else 0, "buckets": len(red.buckets),
+            "exchange": (f"NCCL all-reduce (AVG) of {len(red.buckets)} flat fp32 gradient buckets over {world} ranks, between the forward+backward "
+                         f"graph and the clip+Adam graph") if world > 1 else "none (one rank)",
+            "api": "mmcodec.GraphedTrainStep(net_d, net_r)(depth, rgb)"}
+
+
 def init_nccl_quietly(dist, dev):
     """NCCL prints its version banner on stdout when the communicator is created; keep stdout for the ONE JSON line."""
     import torch
@@ -459,6 +507,7 @@ def main():
     ap.add_argument("--workload", default="hyperprior", choices=sorted(WORKLOADS) + sorted(OTHER_WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro-batch", type=int, default=8, help="images per pipelined micro-batch on the host-buffer path")
+    ap.add_argument("--no-train-record", action="store_true", help="skip the training-step sub-record of the default line")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help='arithmetic of the transform stacks: bf16 operands (default) or mmcodec.precision("fp32") (three-term bf16 split, ~1e-5)')
     args = ap.parse_args()
@@ -645,6 +694,14 @@ def main():
         torch.cuda.synchronize()
         layer_prof = ops.stop_profile(with_work=True)
 
+    train_rec = None
+    if args.workload == "hyperprior" and args.precision == "bf16" and not args.no_train_record:
+        del out
+        torch.cuda.empty_cache()
+        try:
+            train_rec = train_step_record(dev, world, dist)
+        except Exception as e:       # the headline line must survive
+            train_rec = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     t = torch.tensor([ms_total, ms_e2e, e2e_full["ms_per_step"] if e2e_full else 0.0, e2e_u8["ms_per_step"] if e2e_u8 else 0.0], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -706,6 +763,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps, "bpp": e2e_bpp, "api": e2e_api},
             "roofline": roofline}
+    if os.environ.get("MMC_BENCH_RETRIED"):
+        line["retried_after_fault"] = os.environ["MMC_BENCH_RETRIED"]
+    if train_rec is not None:
+        line["train_step"] = train_rec
     if ceil is not None:
         # the e2e legs as fractions of the measured pure-copy ceilings: metrics mode is bound by the input copy alone, the
         # full-output call by both directions at once
@@ -762,5 +823,24 @@ def main():
         dist.destroy_process_group()
 
 
+def _main_with_one_retry():
+    """Single-process runs: a sticky CUDA fault (seen in ~3 of ~70 fresh-process runs of round 2 as an "illegal memory access" in the
+    first forward of the synthesis stack on some boxes, not reproducible on others) kills the context, so the
+    whole measurement is re-executed ONCE in a fresh process and the line carries "retried_after_fault".  Multi-rank runs are
+    left to the launcher."""
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or os.environ.get("MMC_BENCH_RETRIED"):
+        return main()
+    try:
+        return main()
+    except Exception as e:
+        msg = f"{type(e).__name__}: {e}"
+        if "illegal memory access" not in msg and "CUDA error" not in msg:
+            raise
+        sys.stderr.write(f"bench.py: CUDA fault in the first attempt ({msg[:200]}); re-executing once\n")
+        sys.stderr.flush()
+        os.environ["MMC_BENCH_RETRIED"] = msg[:200]
+        os.execv(sys.executable, [sys.executable] + sys.argv)
+
+
 if __name__ == "__main__":
-    main()
+    _main_with_one_retry()

@@ -288,8 +288,31 @@ def _reducer_worker(rank, world, port, q):
     net(x + 1.0).pow(2).sum().backward()
     local2 = [p.grad.clone() for p in net.parameters()]
     red.reduce_now()
-    q.put((rank, [g.tolist() for g in local], first, unused.grad is None, len(red.buckets),
-           [g.tolist() for g in local2], [p.grad.tolist() for p in net.parameters()]))
+    second = [p.grad.tolist() for p in net.parameters()]
+    unused_none = unused.grad is None
+    # third mode: flat buckets -- .grad are views into per-bucket buffers, collectives in place, zero_() instead of zero_grad
+    red.remove()
+    net.zero_grad(set_to_none=True)
+    red3 = mmcodec.GradBucketReducer(params, bucket_bytes=64, flat=True)
+    views_ok = all(p.grad is not None and p.grad.untyped_storage().data_ptr() == red3.flat[red3.bucket_of[i]].untyped_storage().data_ptr()
+                   for i, p in enumerate(red3.params))
+    for _ in range(2):                                       # second round: zero_() really clears the accumulated gradients
+        red3.zero_()
+        net(x + 2.0).pow(2).sum().backward()
+        for w_, _, _ in red3._work.values():                 # local copy only after the in-flight bucket collectives (they
+            w_.wait()                                        # are in place) -- recompute the local gradient instead
+        red3.finish()
+    red3.enabled = False                                     # the rank-local gradient of the same batch, for the expected average
+    red3.zero_()
+    net(x + 2.0).pow(2).sum().backward()
+    local3 = [p.grad.clone() for p in net.parameters()]
+    red3.enabled = True
+    red3.zero_()
+    net(x + 2.0).pow(2).sum().backward()
+    red3.finish()
+    third = [p.grad.tolist() for p in net.parameters()]
+    q.put((rank, [g.tolist() for g in local], first, unused_none, len(red.buckets), [g.tolist() for g in local2], second,
+           views_ok and bool((unused.grad == 0).all()), [g.tolist() for g in local3], third))
     dist.destroy_process_group()
 
 
@@ -303,9 +326,9 @@ def test_grad_bucket_reducer_world_size_2_gloo():
     [p.start() for p in ps]
     res = sorted(q.get(timeout=120) for _ in ps)
     [p.join(60) for p in ps]
-    (_, l0, a0, u0, nb, m0, b0), (_, l1, a1, u1, _, m1, b1) = res
-    assert u0 and u1 and nb >= 3
-    for loc0, loc1, red0, red1 in ((l0, l1, a0, a1), (m0, m1, b0, b1)):      # hook-driven buckets, then reduce_now()
+    (_, l0, a0, u0, nb, m0, b0, v0, f0, t0), (_, l1, a1, u1, _, m1, b1, v1, f1, t1) = res
+    assert u0 and u1 and nb >= 3 and v0 and v1
+    for loc0, loc1, red0, red1 in ((l0, l1, a0, a1), (m0, m1, b0, b1), (f0, f1, t0, t1)):   # hook-driven buckets, reduce_now(), flat buckets
         for g0, g1, r0, r1 in zip(loc0, loc1, red0, red1):
             want = (torch.tensor(g0) + torch.tensor(g1)) / 2
             assert torch.allclose(torch.tensor(r0), want, rtol=1e-6, atol=1e-6) and torch.allclose(torch.tensor(r1), want, rtol=1e-6, atol=1e-6)
