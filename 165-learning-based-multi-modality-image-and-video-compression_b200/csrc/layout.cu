@@ -4,6 +4,22 @@
 
 namespace mmc {
 
+// y = x * rsqrt(norm) (GDN) or x * sqrt(norm) (IGDN) on fp32 maps: the elementwise half of the fp32-mode GDN, whose norm
+// contraction runs on the tensor cores (three-term split, see split_bf16x3_kernel)
+__global__ void __launch_bounds__(256) gdn_apply_kernel(const float *__restrict__ x, const float *__restrict__ norm, int inverse, int64_t n4,
+                                                        float *__restrict__ y)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 a = ldg_stream(reinterpret_cast<const float4 *>(x) + i);
+        const float4 b = ldg_stream(reinterpret_cast<const float4 *>(norm) + i);
+        float4 o;
+        if (inverse) o = make_float4(a.x * sqrtf(b.x), a.y * sqrtf(b.y), a.z * sqrtf(b.z), a.w * sqrtf(b.w));
+        else o = make_float4(a.x * rsqrtf(b.x), a.y * rsqrtf(b.y), a.z * rsqrtf(b.z), a.w * rsqrtf(b.w));
+        reinterpret_cast<float4 *>(y)[i] = o;
+    }
+}
+
 // [B][C][HW] -> [B][HW][C] through a 32x33 shared tile; both sides coalesced.
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) transpose_c_hw_kernel(const TIn *__restrict__ x, int C, int64_t HW, bool to_nhwc,
@@ -49,6 +65,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float *__restric
 // fp32 channels becomes 3 C bf16 channels [hi | lo | hi]; against weights laid out [w_hi | w_hi | w_lo] along the input channels
 // the ordinary bf16 tensor-core convolution then accumulates x_hi w_hi + x_lo w_hi + x_hi w_lo in fp32: every term of the product
 // down to 2^-16 relative (~1e-5 on a layer output, against 4e-3 for plain bf16 operands and ~4e-4 for a single TF32 pass).
+template <bool kSquare>
 __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float *__restrict__ x, int64_t pixels, int C, __nv_bfloat16 *__restrict__ y)
 {
     const int cq = C >> 2;                                  // float4 groups per pixel
@@ -58,7 +75,8 @@ __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float *__restri
         const int64_t p = i / cq;
         const int q = (int)(i - p * cq);
         const float4 v = ldg_stream(reinterpret_cast<const float4 *>(x) + i);
-        const float f[4] = {v.x, v.y, v.z, v.w};
+        // kSquare: the operand of the GDN norm contraction, x^2 (fp32 mode of layers/gdn.py:77-92)
+        const float f[4] = {kSquare ? v.x * v.x : v.x, kSquare ? v.y * v.y : v.y, kSquare ? v.z * v.z : v.z, kSquare ? v.w * v.w : v.w};
         __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -105,13 +123,25 @@ int mmc_nhwc_f32_to_nchw_f32(const float *x, int64_t B, int C, int64_t HW, float
     return launch_transpose<float, float>(x, B, C, HW, false, y, (cudaStream_t)stream, "mmc_nhwc_f32_to_nchw_f32");
 }
 
-int mmc_split_f32_bf16x3(const float *x, int64_t pixels, int C, void *y, void *stream)
+int mmc_split_f32_bf16x3(const float *x, int64_t pixels, int C, int square, void *y, void *stream)
 {
     MMC_CHECK_ARG(pixels >= 0 && C >= 4 && C % 4 == 0, "mmc_split_f32_bf16x3: C must be a positive multiple of 4");
     if (pixels == 0) return MMC_OK;
     MMC_CHECK_ARG(x && y && aligned16(x) && (reinterpret_cast<uintptr_t>(y) & 7u) == 0, "mmc_split_f32_bf16x3: NULL or unaligned buffer");
-    split_bf16x3_kernel<<<elementwise_grid(pixels * (C >> 2), 256), 256, 0, (cudaStream_t)stream>>>(x, pixels, C, (__nv_bfloat16 *)y);
+    const int grid = elementwise_grid(pixels * (C >> 2), 256);
+    if (square) split_bf16x3_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, pixels, C, (__nv_bfloat16 *)y);
+    else split_bf16x3_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, pixels, C, (__nv_bfloat16 *)y);
     MMC_CHECK_LAUNCH("mmc_split_f32_bf16x3");
+    return MMC_OK;
+}
+
+int mmc_gdn_apply_f32(const float *x, const float *norm, int inverse, int64_t n, float *y, void *stream)
+{
+    MMC_CHECK_ARG(n >= 0 && n % 4 == 0, "mmc_gdn_apply_f32: n must be a non-negative multiple of 4");
+    if (n == 0) return MMC_OK;
+    MMC_CHECK_ARG(x && norm && y && aligned16(x) && aligned16(norm) && aligned16(y), "mmc_gdn_apply_f32: NULL or unaligned buffer");
+    gdn_apply_kernel<<<elementwise_grid(n >> 2, 256), 256, 0, (cudaStream_t)stream>>>(x, norm, inverse, n >> 2, y);
+    MMC_CHECK_LAUNCH("mmc_gdn_apply_f32");
     return MMC_OK;
 }
 

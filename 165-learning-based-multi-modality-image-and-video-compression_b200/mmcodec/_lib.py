@@ -67,7 +67,8 @@ _PROTOS = {
     "mmc_nhwc_bf16_to_nchw_f32": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "mmc_nhwc_f32_to_nchw_f32": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "mmc_f32_to_bf16": (c_int, [c_vp, c_i64, c_vp, c_vp]),
-    "mmc_split_f32_bf16x3": (c_int, [c_vp, c_i64, c_int, c_vp, c_vp]),
+    "mmc_split_f32_bf16x3": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_vp]),
+    "mmc_gdn_apply_f32": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "mmc_gaussian_volume_workspace": (c_int, [c_i64, c_int, c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "mmc_gaussian_volume": (c_int, [c_vp, c_i64, c_int, c_int, c_vp, c_int, c_int, c_vp, ctypes.c_size_t, c_vp, c_vp]),
     "mmc_scale_space_warp": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),

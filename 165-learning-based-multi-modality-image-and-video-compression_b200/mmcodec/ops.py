@@ -517,14 +517,24 @@ def to_bf16(x: Tensor) -> Tensor:
     return y
 
 
-def split_bf16x3(x_nhwc: Tensor) -> Tensor:
-    """(B, H, W, C) fp32 -> (B, H, W, 3C) bf16 [hi | lo | hi] (fp32 precision mode, see mmc_split_f32_bf16x3)."""
+def split_bf16x3(x_nhwc: Tensor, square: bool = False) -> Tensor:
+    """(B, H, W, C) fp32 -> (B, H, W, 3C) bf16 [hi | lo | hi] of x (or of x^2) (fp32 precision mode, see mmc_split_f32_bf16x3)."""
     _require_cuda(x_nhwc)
     x = _f32c(x_nhwc)
     B, H, W, C = x.shape
     y = torch.empty((B, H, W, 3 * C), dtype=torch.bfloat16, device=x.device)
     with _Timed("split_bf16x3|layout", x.numel() * 10.0):
-        L.check(L.lib().mmc_split_f32_bf16x3(_ptr(x), B * H * W, C, _ptr(y), _stream()))
+        L.check(L.lib().mmc_split_f32_bf16x3(_ptr(x), B * H * W, C, int(bool(square)), _ptr(y), _stream()))
+    return y
+
+
+def gdn_apply_f32(x: Tensor, norm: Tensor, inverse: bool) -> Tensor:
+    """y = x * rsqrt(norm) (inverse: x * sqrt(norm)) on fp32 tensors of identical layout (fp32-mode GDN, see mmc_gdn_apply_f32)."""
+    _require_cuda(x, norm)
+    x, norm = _f32c(x), _f32c(norm)
+    y = torch.empty_like(x)
+    with _Timed("gdn_apply|layout", x.numel() * 12.0):
+        L.check(L.lib().mmc_gdn_apply_f32(_ptr(x), _ptr(norm), int(bool(inverse)), x.numel(), _ptr(y), _stream()))
     return y
 
 

@@ -258,6 +258,75 @@ def _fp32_shadow(conv: nn.Module) -> nn.Module:
     return cached[1]
 
 
+def _fp32_gdn(gdn: nn.Module, x_nhwc: Tensor) -> Tensor:
+    """GDN / IGDN on an fp32 NHWC map (layers/gdn.py:77-92): norm = beta + gamma x^2 as a 1x1 tensor-core convolution over the
+    three-term split of x^2 (weights [g_hi | g_hi | g_lo], bias beta), then y = x * rsqrt(norm) (IGDN: * sqrt) elementwise."""
+    from .layers import Conv2d
+    beta_eff, gamma_eff, _ = gdn.effective_params()
+    key = (beta_eff.data_ptr(), gamma_eff.data_ptr(), gdn._cache_key)
+    cached = getattr(gdn, "_mmc_fp32_norm", None)
+    if cached is None or cached[0] != key:
+        C = beta_eff.numel()
+        g = gamma_eff.detach().float().reshape(C, C, 1, 1)
+        hi = g.bfloat16().float()
+        lo = (g - hi).bfloat16().float()
+        with torch.device("meta"):
+            m = Conv2d(3 * C, C, kernel_size=1, stride=1, padding=0, bias=True)
+        m._parameters["weight"] = nn.Parameter(torch.cat([hi, hi, lo], dim=1).contiguous(), requires_grad=False)
+        m._parameters["bias"] = nn.Parameter(beta_eff.detach().float().clone(), requires_grad=False)
+        m._mmc_name = "gdn.norm.x3"
+        cached = (key, m)
+        object.__setattr__(gdn, "_mmc_fp32_norm", cached)
+    m = cached[1]
+    B, H, W, C = x_nhwc.shape
+    if not _tc_eligible(3 * C, C, False):
+        return ops.gdn_forward(x_nhwc.permute(0, 3, 1, 2), beta_eff, gamma_eff, gdn.inverse).permute(0, 2, 3, 1)   # fp32 CUDA-core kernel
+    x2 = ops.split_bf16x3(x_nhwc, square=True)
+    d = ops.conv_desc(False, B, H, W, 3 * C, C, 1, 1, L.BF16, L.NHWC, L.F32, L.NHWC)
+    norm = ops.conv_forward_tc(d, x2, m.packed_weight(d), m.bias.detach(), None, None, name="gdn.norm.x3")
+    return ops.gdn_apply_f32(x_nhwc, norm, gdn.inverse)
+
+
+def _fp32_edge_conv(conv: nn.Module, x_nchw: Tensor, act: int, name: str) -> Tensor:
+    """Image-edge convolution (Cin <= 4) in fp32 mode on the tensor-core image-edge kernel: the three product terms need 3 Cin > 8
+    staged channels, so they are two launches -- [x_hi | x_lo] against [w_hi | w_hi] (+ bias) and x_hi against w_lo -- summed in
+    fp32.  (The fp32 CUDA-core kernel took 124 ms for the 64 x 768x512 batch; this takes ~1.5 ms.)  Returns NHWC fp32."""
+    from .layers import Conv2d
+    cin, cout, k, stride = conv.in_channels, conv.out_channels, conv.kernel_size[0], conv.stride[0]
+    key = (conv.weight._version, conv.weight.data_ptr())
+    cached = getattr(conv, "_mmc_fp32_edge", None)
+    if cached is None or cached[0] != key:
+        w = conv.weight.detach().float()
+        hi = w.bfloat16().float()
+        lo = (w - hi).bfloat16().float()
+        with torch.device("meta"):
+            ma = Conv2d(2 * cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False)
+            mb = Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False)
+        ma._parameters["weight"] = nn.Parameter(torch.cat([hi, hi], dim=1).contiguous(), requires_grad=False)
+        mb._parameters["weight"] = nn.Parameter(lo.contiguous(), requires_grad=False)
+        ma._mmc_name, mb._mmc_name = name + ".x2", name + ".lo"
+        cached = (key, ma, mb)
+        object.__setattr__(conv, "_mmc_fp32_edge", cached)
+    _, ma, mb = cached
+    B, C, H, W = x_nchw.shape
+    x_hi = x_nchw.bfloat16().float()
+    x6 = torch.cat([x_hi, (x_nchw - x_hi).bfloat16().float()], dim=1).contiguous()
+    bias = conv.bias.detach().float() if conv.bias is not None else None
+    outs = []
+    for m, xin, b in ((ma, x6, bias), (mb, x_hi.contiguous(), None)):
+        ci = xin.shape[1]
+        d = ops.conv_desc(False, B, H, W, ci, cout, k, stride, L.BF16, L.NHWC_PAD8, L.F32, L.NHWC)
+        outs.append(ops.conv_forward_tc(d, ops.pad_to_nhwc8(xin, d), m.packed_weight(d), b, None, None, name=m._mmc_name))
+    out = outs[0].add_(outs[1])
+    if act == L.ACT_RELU:
+        out = torch.relu_(out)
+    elif act == L.ACT_LEAKY_RELU:
+        out = torch.nn.functional.leaky_relu_(out, 0.01)
+    elif act == L.ACT_QRELU8:
+        out = out.clamp_(0, 255)
+    return out
+
+
 def _run_layers_fp32(steps: List[Step], x: Tensor, in_fmt: str, out_fmt: str, out2: int):
     """precision("fp32"): the stack with fp32 activations between layers (NHWC), each tensor-core-eligible conv / deconv as ONE bf16
     tensor-core launch over three-term split operands (fp32 accumulate, bias and ReLU / LeakyReLU fused, fp32 out), GDN / IGDN
@@ -300,7 +369,11 @@ def _run_layers_fp32(steps: List[Step], x: Tensor, in_fmt: str, out_fmt: str, ou
                 cur = ops.conv_forward_tc(d3, x3, sh.packed_weight(d3), bias, None, None, name=name + ".x3")
                 nchw = narrow
                 if s.gdn is not None:
-                    cur = ops.gdn_forward(cur.permute(0, 3, 1, 2), beta_eff, gamma_eff, s.gdn.inverse).permute(0, 2, 3, 1)
+                    cur = _fp32_gdn(s.gdn, cur)
+            elif (use_tensor_cores and nchw and not s.transposed and cin <= 4 and cout % 16 == 0 and cout <= 1024 and k in (3, 5)):
+                cur, nchw = _fp32_edge_conv(c, cur, s.act, name), False
+                if s.gdn is not None:
+                    cur = _fp32_gdn(s.gdn, cur)
             else:
                 # image-edge / odd shapes: the fp32 CUDA-core kernel (GDN fused in fp32 when it fits)
                 planar_out = last and out_fmt == "nchw_f32" and cout <= 4

@@ -261,8 +261,12 @@ MMC_API int mmc_nhwc_f32_to_nchw_f32(const float *x, int64_t B, int C, int64_t H
 MMC_API int mmc_f32_to_bf16(const float *x, int64_t n, void *y, void *stream);
 /* fp32 precision mode: [pixels][C] fp32 -> [pixels][3 C] bf16 = [hi | lo | hi] with hi = bf16(x), lo = bf16(x - hi).  Convolved
  * (mmc_conv_forward_tc) with weights whose input channels are laid out [w_hi | w_hi | w_lo] this evaluates the fp32 layer
- * (compressai/models/utils.py:128-146 on fp32 tensors) to ~1e-5 relative on the bf16 tensor cores.  C % 4 == 0. */
-MMC_API int mmc_split_f32_bf16x3(const float *x, int64_t pixels, int C, void *y, void *stream);
+ * (compressai/models/utils.py:128-146 on fp32 tensors) to ~1e-5 relative on the bf16 tensor cores.  C % 4 == 0;
+ * square != 0 splits x^2 instead (the operand of the GDN norm contraction). */
+MMC_API int mmc_split_f32_bf16x3(const float *x, int64_t pixels, int C, int square, void *y, void *stream);
+/* fp32-mode GDN / IGDN, elementwise half (layers/gdn.py:88-92): y = x * rsqrt(norm) (inverse: x * sqrt(norm)); norm = beta + gamma x^2
+ * comes from a 1x1 mmc_conv_forward_tc over mmc_split_f32_bf16x3(x, square = 1).  n % 4 == 0. */
+MMC_API int mmc_gdn_apply_f32(const float *x, const float *norm, int inverse, int64_t n, float *y, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Scale-space flow prediction of the ssf2020 video codec (HBM-bound stencil / gather kernels, planar fp32)
