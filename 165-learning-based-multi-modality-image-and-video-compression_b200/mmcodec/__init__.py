@@ -15,6 +15,7 @@
 All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
 """
 from . import _lib, compress_pipeline, entropy_models, graphs, host_pipeline, layers, models, models_master, models_mm, models_video, ops, training, transforms, transforms_functional  # noqa: F401
+from .accelerate import accelerate  # noqa: F401
 from .graphs import GraphedForward  # noqa: F401
 from .transforms import precision  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401

@@ -191,6 +191,54 @@ def test_conv_tc_cta_pair_vs_single(transposed, cin, h, w, B, gdn):
     assert np.abs(y - ref).max() < 1e-2 * float(np.abs(ref).max())
 
 
+@pytest.mark.parametrize("transposed,cin,cout,k,s,gdn,h,w", [
+    (True, 128, 128, 5, 2, L.GDN_INVERSE, 20, 28),    # g_s.2 / g_s.4 class: four phases, 3 / 2 / 3 / 2 groups, teams epilogue
+    (True, 192, 128, 5, 2, L.GDN_INVERSE, 9, 13),     # g_s.0 class: three K chunks, ragged tiles
+    (False, 128, 128, 5, 2, L.GDN_FORWARD, 40, 56),   # g_a.2 class: strided conv, parity groups (pair kernel when forced)
+    (False, 192, 128, 3, 1, L.GDN_NONE, 17, 24),      # h_a.0 class: 3x3 stride 1, plain epilogue
+    (False, 64, 64, 5, 1, L.GDN_FORWARD, 24, 24),     # C = 64 teams, five-tap groups (20-row patches)
+])
+def test_opt_in_main_loop_and_epilogue_variants(transposed, cin, cout, k, s, gdn, h, w):
+    """The opt-in round-2 paths -- tap groups (MMC_TC_GROUPED=1: one A patch per group and chunk) and the two-team GDN epilogue
+    (MMC_TC_TEAMS=2: norm in place, x in registers) -- against the default kernel path and the oracle.  Teams are bit-identical
+    to the single-team epilogue; groups change only the fp32 accumulation order of the taps."""
+    import os
+    rs = np.random.RandomState(cin + cout + k)
+    B = 3
+    x = bf16_round(rs.standard_normal((B, cin, h, w)).astype(np.float32))
+    fan = cin * k * k / (s * s if transposed else 1)
+    wt = bf16_round((rs.standard_normal((cin, cout, k, k) if transposed else (cout, cin, k, k)) * (2.0 / np.sqrt(fan))).astype(np.float32))
+    b = rs.standard_normal(cout).astype(np.float32)
+    gw = {}
+    _gdn(rs, gw, "g", cout)
+    beta_eff = gamma_bf16 = None
+    if gdn != L.GDN_NONE:
+        beta_eff, _, gamma_bf16 = ops.gdn_reparam(torch.from_numpy(gw["g.beta"]).to(dev()), torch.from_numpy(gw["g.gamma"]).to(dev()),
+                                                  oracle.gdn_beta_bound(), oracle.GDN_GAMMA_BOUND, oracle.GDN_PEDESTAL, want_bf16=True)
+    xin = torch.from_numpy(x).to(dev()).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    d = ops.conv_desc(transposed, B, h, w, cin, cout, k, s, L.BF16, L.NHWC, L.BF16, L.NHWC, gdn=gdn)
+    packed = ops.conv_pack_weights(d, torch.from_numpy(wt).to(dev()))
+    outs = {}
+    for name, env in (("default", {}), ("teams", {"MMC_TC_TEAMS": "2"}), ("grouped", {"MMC_TC_GROUPED": "1"}),
+                      ("both", {"MMC_TC_GROUPED": "1", "MMC_TC_TEAMS": "2"}), ("both+pair", {"MMC_TC_GROUPED": "1", "MMC_TC_TEAMS": "2", "MMC_TC_PAIR": "2"})):
+        os.environ.update(env)
+        try:
+            outs[name] = ops.conv_forward_tc(d, xin, packed, torch.from_numpy(b).to(dev()), beta_eff, gamma_bf16).float()
+            torch.cuda.synchronize()
+        finally:
+            for k_ in env:
+                os.environ.pop(k_, None)
+    assert torch.equal(outs["teams"], outs["default"])
+    ref = (oracle.conv_transpose2d if transposed else oracle.conv2d)(x, wt, b, stride=s, act=None)
+    if gdn != L.GDN_NONE:
+        ref = oracle.gdn_forward(ref, gw["g.beta"], gw["g.gamma"], inverse=(gdn == L.GDN_INVERSE))
+    for name, y in outs.items():
+        yy = y.permute(0, 3, 1, 2).cpu().numpy()
+        assert np.abs(yy - ref).max() < 1e-2 * float(np.abs(ref).max()), name
+    assert float((outs["grouped"] - outs["default"]).abs().max()) <= 2e-2 * float(outs["default"].abs().max())
+    assert torch.equal(outs["both"], outs["grouped"])
+
+
 @pytest.mark.parametrize("kind,c1,c2,cout,k,s,gdn", [
     ("conv", 192, 192, 192, 5, 1, L.GDN_NONE),       # tran_conv: eg_ext(own) ++ eg_ext(guide)
     ("conv", 192, 192, 192, 5, 2, L.GDN_FORWARD),    # pic2_g_a_conv2 + GDN on (a ++ fused)
