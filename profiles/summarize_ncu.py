@@ -10,7 +10,8 @@ KEEP = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__regis
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__inst_executed.sum", "launch__shared_mem_per_block_dynamic"]
+        "smsp__inst_executed.sum", "launch__shared_mem_per_block_dynamic", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed"]
 
 def summarize(rep, dst):
     hdr, units, rows = raw(rep)
@@ -42,6 +43,12 @@ def launches(src, dst):
             w.writerow([k, n, f"{us:.1f}", f"{100 * us / tot:.2f}"])
 
 if __name__ == "__main__":
-    summarize("gpurun_out/r01_conv_tc.ncu-rep", "profiles/r01_ncu_conv_tc_full.csv")
-    summarize("gpurun_out/r01_entropy.ncu-rep", "profiles/r01_ncu_entropy_full.csv")
-    launches("gpurun_out/r01_launches.csv", "profiles/r01_ncu_launch_shares.csv")
+    import os
+    rnd = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    for rep, dst in ((f"gpurun_out/{rnd}_conv_tc_default.ncu-rep", f"profiles/{rnd}_ncu_conv_tc_full.csv"),
+                     (f"gpurun_out/{rnd}_entropy.ncu-rep", f"profiles/{rnd}_ncu_entropy_full.csv"),
+                     (f"gpurun_out/{rnd}_entropy_cfg2.ncu-rep", f"profiles/{rnd}_ncu_entropy_cfg2_full.csv")):
+        if os.path.exists(rep):
+            summarize(rep, dst)
+    if os.path.exists(f"gpurun_out/{rnd}_launches.csv"):
+        launches(f"gpurun_out/{rnd}_launches.csv", f"profiles/{rnd}_ncu_launch_shares.csv")
