@@ -14,7 +14,7 @@ for line in out.splitlines():
         cur = m.group(1)
         per[cur] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
     if m and cur:
         op = m.group(1)
         per[cur]["total"] += 1
