@@ -30,6 +30,22 @@ def dev():
     return torch.device("cuda", 0)
 
 
+# gates at 2x the measured values (round 2, B200, profiles/r02_parity_fullsize_measured.jsonl): x_hat rel-RMS through the quantiser
+# 0.010 / 0.010 / 0.020; symbol / index disagreement y 2.2 % / 25 %, z 0.8 % / 0 (the round-1 gates 0.1 and 0.70 were far
+# from the measured values)
+X_HAT_REL_RMS = {"factorized": 0.021, "hyperprior": 0.021, "mean-scale": 0.04}
+MIN_AGREE = {"y_symbols": 0.955, "y_indexes": 0.50, "z_symbols": 0.983, "z_indexes": 0.999}
+
+
+def _record(test, **values):
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_measured.jsonl"), "a") as f:
+            f.write(json.dumps({"test": test, **values}) + "\n")
+
+
 def load(cls, arch, N, M):
     sd = {k: torch.from_numpy(v) for k, v in make_state_dict(arch, N, M, seed=0).items()}
     net = cls(N, M).eval()
@@ -66,7 +82,8 @@ def test_forward_vs_reference_golden(models_golden, arch, cls, N, M):
     assert abs(bpp - ref_bpp) / ref_bpp < 5e-3, (bpp, ref_bpp)
     # reconstruction: bf16 transforms + chaotic rounding -> compare at the PSNR level
     xh, rxh = out["x_hat"].float().cpu(), torch.from_numpy(g[f"{tag}_x_hat"])
-    assert rel_rms(xh, rxh) < 0.1
+    _record("forward_vs_golden", arch=arch, x_hat_rel_rms=rel_rms(xh, rxh), bpp_rel=abs(bpp - ref_bpp) / ref_bpp)
+    assert rel_rms(xh, rxh) < X_HAT_REL_RMS[arch]
 
 
 @pytest.mark.parametrize("arch,cls,N,M", ARCHS)
@@ -140,8 +157,10 @@ def test_symbols_and_indexes_end_to_end(models_golden, arch, cls, N, M):
         mine, ref = c[name].cpu().numpy().reshape(B, -1), g[f"{tag}_{name}"]
         assert mine.shape == ref.shape
         agree = float((mine == ref).mean())
-        # SURVEY.md 8d probe: bf16 transforms flip ~3 % of y symbols and ~15 % of indexes (every error passes through round())
-        assert agree > (0.999 if name == "z_indexes" else 0.70), (name, agree)
+        _record("symbols_end_to_end", arch=arch, name=name, agree=agree)
+        # SURVEY.md 8d probe: bf16 transforms flip a few % of y symbols and ~15-30 % of indexes (every error passes through
+        # round()); the gates are set at twice the measured disagreement (profiles/r02_parity_fullsize_measured.jsonl)
+        assert agree > MIN_AGREE[name], (name, agree)
     assert tuple(c["shape"]) == tuple(g[f"{tag}_shape"])
 
 
