@@ -104,6 +104,13 @@ _PROTOS = {
     "mmc_eb_backward": (c_int, [c_vp, c_vp, c_vp, ctypes.POINTER(EbParams), c_f32, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "mmc_im2col8": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "mmc_wgrad_finalize": (c_int, [c_vp, c_int, c_int, c_int, c_f32, c_vp, c_int, c_vp, c_vp]),
+    "mmc_maxpool_nhwc_bf16_idx": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    "mmc_maxpool_nhwc_bf16_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "mmc_upsample_bilinear_bwd_bf16": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    "mmc_sigmoid_gate_bwd_bf16": (c_int, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "mmc_gelu_bwd_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "mmc_layernorm_bwd_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
+    "mmc_window_attention_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOS)

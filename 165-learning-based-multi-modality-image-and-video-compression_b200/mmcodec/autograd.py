@@ -20,7 +20,8 @@ from torch import Tensor
 from . import _lib as L
 from . import ops
 
-__all__ = ["run_layers_train", "eb_forward", "gc_forward", "gdn_forward", "cast_bf16", "add_noise", "wants_grad"]
+__all__ = ["run_layers_train", "eb_forward", "gc_forward", "gdn_forward", "cast_bf16", "add_noise", "wants_grad", "maxpool_nhwc",
+           "upsample_add", "sigmoid_gate", "layernorm", "gelu", "window_attention", "conv_alias"]
 
 
 def wants_grad(layers, x: Tensor) -> bool:
@@ -177,6 +178,103 @@ class _ConvGdnFn(torch.autograd.Function):
         return dx, dw, db, dbeta.to(ctx.gdn.beta.dtype), dgamma.to(ctx.gdn.gamma.dtype), None, None, None
 
 
+def _adjoint_part(conv: nn.Module, lo: int, hi: int) -> nn.Module:
+    """Adjoint of ``conv`` restricted to input channels [lo, hi): the input-gradient operator of ONE source of a two-source layer
+    (its weight is the matching slice of ``conv.weight``, so no gradient for the other source's channels is computed or split off)."""
+    from .layers import Conv2d, ConvTranspose2d
+    parts = conv.__dict__.setdefault("_mmc_adjoint_parts", {})
+    adj = parts.get((lo, hi))
+    k, s = conv.kernel_size[0], conv.stride[0]
+    transposed = isinstance(conv, nn.ConvTranspose2d)
+    if adj is None:
+        if transposed:
+            adj = Conv2d(conv.out_channels, hi - lo, kernel_size=k, stride=s, padding=k // 2, bias=False)
+        else:
+            adj = ConvTranspose2d(conv.out_channels, hi - lo, kernel_size=k, stride=s, padding=k // 2, output_padding=s - 1, bias=False)
+        adj._mmc_name = getattr(conv, "_mmc_name", "conv") + f".dgrad[{lo}:{hi}]"
+        parts[(lo, hi)] = adj
+    w = conv.weight.detach()
+    adj._parameters["weight"] = w[lo:hi] if transposed else w[:, lo:hi]     # a view: shares the version counter, own data_ptr
+    return adj
+
+
+def _conv_backward2(conv, x1, x2, g, g_planar, need1, need2):
+    """(dx1, dx2, dweight, dbias) of a conv / deconv layer whose input is the channel concatenation of the NHWC bf16 maps x1 and x2
+    (google.py:1153 and its repeats), which is never materialised: the weight gradient is computed per source and joined along
+    the input-channel axis (a parameter-sized copy), each input gradient by the adjoint layer of that source's weight slice."""
+    transposed = isinstance(conv, nn.ConvTranspose2d)
+    k, s = conv.kernel_size[0], conv.stride[0]
+    c1, cout = x1.shape[-1], conv.out_channels
+    name = getattr(conv, "_mmc_name", "conv")
+    dbias = ops.colsum(g)[:cout].to(conv.bias.dtype) if conv.bias is not None else None
+    if transposed:      # S = input (low resolution), L = grad_output: (cin, cout, k, k)
+        edge = g.shape[-1] == 8 and cout <= 8
+        dw = torch.cat([(ops.wgrad_edge(xi, g, k, s, name=name) if edge else ops.wgrad(xi, g, k, s, name=name))[:, :cout] for xi in (x1, x2)], dim=0)
+    else:               # S = grad_output, L = input: (cout, cin, k, k)
+        dw = torch.cat([ops.wgrad(g, x1, k, s, name=name), ops.wgrad(g, x2, k, s, name=name)], dim=1)
+    mask = getattr(conv, "mask", None)
+    if mask is not None:
+        dw = dw * mask
+    dxs = []
+    for need, x_saved, (lo, hi) in ((need1, x1, (0, c1)), (need2, x2, (c1, conv.in_channels))):
+        dx = None
+        if need:
+            adj = _adjoint_part(conv, lo, hi)
+            if g_planar is not None:
+                dx = _run([adj], g_planar, "nchw_f32", "nhwc_bf16")
+            else:
+                dx = _run([adj], g[..., :cout] if g.shape[-1] != cout else g, "nhwc_bf16", "nhwc_bf16")
+            if not transposed and dx.shape[1:3] != x_saved.shape[1:3]:
+                dx = dx[:, : x_saved.shape[1], : x_saved.shape[2]].contiguous()
+        dxs.append(dx)
+    return dxs[0], dxs[1], dw.contiguous().to(conv.weight.dtype), dbias
+
+
+class _Conv2Fn(torch.autograd.Function):
+    """Two-source conv()/deconv() + bias (+ ReLU / LeakyReLU): the K loop of the forward kernel reads both maps
+    (mmc_conv_forward_tc2), the backward pass never builds the concatenation either."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias, conv, act_module, out_fmt):
+        layers = [conv] + ([act_module] if act_module is not None else [])
+        y = _run(layers, (x1, x2), "nhwc_bf16", out_fmt)
+        ctx.conv, ctx.act_module, ctx.out_fmt = conv, act_module, out_fmt
+        ctx.save_for_backward(x1, x2, y if act_module is not None else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x1, x2, y = ctx.saved_tensors
+        conv = ctx.conv
+        g, g_planar = _grad_nhwc_bf16(gy, ctx.out_fmt, conv.out_channels)
+        if ctx.act_module is not None:
+            if ctx.out_fmt == "nchw_f32":
+                raise NotImplementedError("activation backward is implemented for NHWC layer outputs")
+            act = L.ACT_LEAKY_RELU if isinstance(ctx.act_module, nn.LeakyReLU) else L.ACT_RELU
+            g = ops.act_bwd(g, y if y.dtype == torch.bfloat16 else ops.to_bf16(y), act)
+        dx1, dx2, dw, db = _conv_backward2(conv, x1, x2, g, g_planar, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dx1, dx2, dw, db, None, None, None
+
+
+class _ConvGdn2Fn(torch.autograd.Function):
+    """Two-source conv()/deconv() + bias + GDN / IGDN in one forward launch (pic2_g_a_conv2..4 / pic2_g_s_conv2..3 with their
+    GDN layers, google.py:1160-1246)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias, beta, gamma, conv, gdn):
+        y, x_pre = _run([conv, gdn], (x1, x2), "nhwc_bf16", "nhwc_bf16", out2=3)
+        ctx.conv, ctx.gdn = conv, gdn
+        ctx.save_for_backward(x1, x2, x_pre)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x1, x2, x_pre = ctx.saved_tensors
+        g_pre, dbeta, dgamma = _gdn_backward(ctx.gdn, x_pre, gy.contiguous())
+        dx1, dx2, dw, db = _conv_backward2(ctx.conv, x1, x2, g_pre, None, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dx1, dx2, dw, db, dbeta.to(ctx.gdn.beta.dtype), dgamma.to(ctx.gdn.gamma.dtype), None, None
+
+
 class _GdnFn(torch.autograd.Function):
     """Stand-alone GDN / IGDN module call (compressai/layers/gdn.py:77-92) on a logical (B, C, H, W) fp32 tensor: forward on the
     fp32 kernel, backward through the same tensor-core contractions as the fused conv + GDN layers (bf16 operands)."""
@@ -216,6 +314,13 @@ def run_layers_train(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0
         raise ValueError("empty transform stack")
     if in_fmt == "nchw_f32" and steps[0].conv.in_channels > 8:
         raise NotImplementedError("training path takes NHWC bf16 activations (or an image with <= 8 channels)")
+    pair = None
+    if isinstance(x, (tuple, list)):
+        # two NHWC bf16 sources feeding the first layer: neither pass materialises their concatenation
+        if in_fmt != "nhwc_bf16":
+            raise NotImplementedError("two-source layers take NHWC bf16 maps")
+        pair = (x[0].contiguous(), x[1].contiguous())
+        x = pair[0]
     cur, fmt = x, in_fmt
     for i, s in enumerate(steps):
         last = i == len(steps) - 1
@@ -230,7 +335,10 @@ def run_layers_train(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0
         if s.gdn is not None:
             if ofmt != "nhwc_bf16":
                 raise NotImplementedError("conv + GDN layers write NHWC bf16 on the training path")
-            cur = _ConvGdnFn.apply(cur, c.weight, c.bias, s.gdn.beta, s.gdn.gamma, c, s.gdn, fmt)
+            if i == 0 and pair is not None:
+                cur = _ConvGdn2Fn.apply(pair[0], pair[1], c.weight, c.bias, s.gdn.beta, s.gdn.gamma, c, s.gdn)
+            else:
+                cur = _ConvGdnFn.apply(cur, c.weight, c.bias, s.gdn.beta, s.gdn.gamma, c, s.gdn, fmt)
         else:
             act_module = None
             if s.act == L.ACT_RELU:
@@ -239,7 +347,10 @@ def run_layers_train(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0
                 act_module = nn.LeakyReLU()
             elif s.act != L.ACT_NONE:
                 raise NotImplementedError("this activation has no backward kernel yet")
-            cur = _ConvFn.apply(cur, c.weight, c.bias, c, act_module, fmt, ofmt)
+            if i == 0 and pair is not None:
+                cur = _Conv2Fn.apply(pair[0], pair[1], c.weight, c.bias, c, act_module, ofmt)
+            else:
+                cur = _ConvFn.apply(cur, c.weight, c.bias, c, act_module, fmt, ofmt)
         fmt = ofmt
     if out_fmt == "nchw_f32" and fmt == "nhwc_f32":
         cur = cur.permute(0, 3, 1, 2)
@@ -386,3 +497,155 @@ def eb_forward(x, eb, noise):
     if needs:
         return _EbFn.apply(x, noise, eb, *params)
     return ops.eb_forward(x, eb._params(), noise, eb._lik_bound())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# non-convolution steps of the fusion layers (csrc/esa.cu, csrc/attention.cu forward; csrc/fusion_bwd.cu backward)
+# ---------------------------------------------------------------------------------------------------------
+class _MaxPoolFn(torch.autograd.Function):
+    """F.max_pool2d(kernel_size=k, stride=s) on an NHWC bf16 map (ESA, google.py:1448); the arg-max map is the saved state."""
+
+    @staticmethod
+    def forward(ctx, x, k, stride):
+        y, idx = ops.maxpool_nhwc_bf16_idx(x, k, stride)
+        ctx.save_for_backward(idx)
+        ctx.geom = (tuple(x.shape), k, stride)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (idx,) = ctx.saved_tensors
+        shape, k, stride = ctx.geom
+        return ops.maxpool_nhwc_bf16_bwd(gy.contiguous(), idx, shape, k, stride), None, None
+
+
+class _UpsampleAddFn(torch.autograd.Function):
+    """F.interpolate(small, size of add, "bilinear") + add (google.py:1453-1455)."""
+
+    @staticmethod
+    def forward(ctx, small, add):
+        ctx.small_hw = (small.shape[1], small.shape[2])
+        return ops.upsample_bilinear_add_bf16(small, add)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        d_small = ops.upsample_bilinear_bwd_bf16(g, *ctx.small_hw) if ctx.needs_input_grad[0] else None
+        return d_small, (g if ctx.needs_input_grad[1] else None)
+
+
+class _SigmoidGateFn(torch.autograd.Function):
+    """x * sigmoid(c) (google.py:1456-1459)."""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.save_for_backward(x, c)
+        return ops.sigmoid_gate_bf16(x, c)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, c = ctx.saved_tensors
+        return ops.sigmoid_gate_bwd_bf16(g.contiguous(), x, c)
+
+
+def maxpool_nhwc(x: Tensor, k: int, stride: int) -> Tensor:
+    return _MaxPoolFn.apply(x, k, stride) if (torch.is_grad_enabled() and x.requires_grad) else ops.maxpool_nhwc_bf16(x, k, stride)
+
+
+def upsample_add(small: Tensor, add: Tensor) -> Tensor:
+    if torch.is_grad_enabled() and (small.requires_grad or add.requires_grad):
+        return _UpsampleAddFn.apply(small, add)
+    return ops.upsample_bilinear_add_bf16(small, add)
+
+
+def sigmoid_gate(x: Tensor, c: Tensor) -> Tensor:
+    if torch.is_grad_enabled() and (x.requires_grad or c.requires_grad):
+        return _SigmoidGateFn.apply(x, c)
+    return ops.sigmoid_gate_bf16(x, c)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the channels of a bf16 token grid, optionally of x + delta (the residual add of master.py:699 fused in
+    front of norm2); with ``delta`` the outputs are (sum, normed), the sum being the updated residual stream."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, delta):
+        ctx.eps, ctx.fused = float(eps), delta is not None
+        if delta is not None:
+            s, y = ops.layernorm_bf16(x, weight, bias, eps, delta=delta, want_sum=True)
+            ctx.save_for_backward(s, weight)
+            return s, y
+        y = ops.layernorm_bf16(x, weight, bias, eps)
+        ctx.save_for_backward(x if x.is_contiguous() else x.contiguous(), weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, *grads):
+        v, weight = ctx.saved_tensors
+        if ctx.fused:
+            g_sum, g = grads
+        else:
+            g_sum, g = None, grads[0]
+        if g is None:
+            g = torch.zeros_like(v)
+        dv, dw, db = ops.layernorm_bwd_bf16(g.contiguous(), v, weight, ctx.eps, g_sum=g_sum.contiguous() if g_sum is not None else None)
+        return dv, dw.to(weight.dtype), db.to(weight.dtype), None, (dv if ctx.fused else None)
+
+
+def layernorm(x: Tensor, norm: nn.LayerNorm, delta: Optional[Tensor] = None):
+    """LayerNorm(x [+ delta]) on the kernels with autograd; returns normed, or (sum, normed) when ``delta`` is given."""
+    needs = torch.is_grad_enabled() and (x.requires_grad or norm.weight.requires_grad or (delta is not None and delta.requires_grad))
+    if needs:
+        return _LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps, delta)
+    if delta is not None:
+        return ops.layernorm_bf16(x, norm.weight, norm.bias, norm.eps, delta=delta, want_sum=True)
+    return ops.layernorm_bf16(x, norm.weight, norm.bias, norm.eps)
+
+
+class _GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.gelu_bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_bwd_bf16(g.contiguous(), x)
+
+
+def gelu(x: Tensor) -> Tensor:
+    return _GeluFn.apply(x) if (torch.is_grad_enabled() and x.requires_grad) else ops.gelu_bf16(x)
+
+
+class _WindowAttnFn(torch.autograd.Function):
+    """WindowAttention core (master.py:535-568) with the roll / window partition of SwinTransformerBlock.forward (master.py:652-697)
+    as index arithmetic; backward recomputes the probabilities (nothing but q and kv is saved)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, table, window, shift, heads, scale):
+        ctx.save_for_backward(q, kv, table)
+        ctx.cfg = (window, shift, heads, scale)
+        return ops.window_attention(q, kv, table, window, shift, heads, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        q, kv, table = ctx.saved_tensors
+        dq, dkv, dtable = ops.window_attention_bwd(q, kv, table, g.contiguous(), *ctx.cfg)
+        return dq, dkv, dtable.to(table.dtype), None, None, None, None
+
+
+def window_attention(q: Tensor, kv: Tensor, table: Tensor, window: int, shift: int, heads: int, scale: float) -> Tensor:
+    if torch.is_grad_enabled() and (q.requires_grad or kv.requires_grad or table.requires_grad):
+        return _WindowAttnFn.apply(q, kv, table, window, shift, heads, scale)
+    return ops.window_attention(q, kv, table, window, shift, heads, scale)
+
+
+def conv_alias(x: Tensor, weight4d: Tensor, bias: Optional[Tensor], alias: nn.Module, act_module=None, out_fmt: str = "nhwc_bf16") -> Tensor:
+    """One conv layer on an NHWC bf16 map whose weight is a differentiable function of some other parameter (a Linear weight viewed as
+    1x1 kernels, a 2x2 patch projection zero-padded to 3x3): ``alias`` is the layer the kernels see (its ``weight`` holds the same
+    values as ``weight4d``), gradients flow to ``weight4d`` / ``bias``."""
+    if torch.is_grad_enabled() and (x.requires_grad or weight4d.requires_grad or (bias is not None and bias.requires_grad)):
+        return _ConvFn.apply(x, weight4d, bias, alias, act_module, "nhwc_bf16", out_fmt)
+    layers = [alias] + ([act_module] if act_module is not None else [])
+    return _run(layers, x, "nhwc_bf16", out_fmt)

@@ -13,8 +13,8 @@ Every conv / deconv (+GDN / IGDN / LeakyReLU), the entropy stage and -- in infer
 attention blocks (1x1 tensor-core convs on the token grid: LayerNorm, Linear and GELU are per-token, so they commute with the
 cyclic shift and the window partition), the LayerNorms and the window attention itself (``mmc_window_attention``: shift,
 partition, QK^T + relative-position bias + shift mask, softmax, PV and the inverse permutation in one kernel) run in
-libmmcodec.  Under autograd the attention blocks run on torch ops in bf16 autocast (same tensors, differentiable); the convs
-stay on the kernels through mmcodec.autograd.  ``compress`` / ``decompress`` (serial per-pixel context loop) are out of scope.
+libmmcodec.  Under autograd the same kernels run, each step recorded with its backward kernel (mmcodec.autograd, csrc/fusion_bwd.cu);
+``attention_train_on_kernels = False`` restores the torch-op training path (bf16 autocast) the tests compare against.  ``compress`` / ``decompress`` (serial per-pixel context loop) are out of scope.
 """
 from __future__ import annotations
 
@@ -26,8 +26,10 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from . import _lib as L
+from . import autograd as AG
 from . import ops
-from .layers import GDN, conv, deconv
+from . import transforms as T
+from .layers import GDN, Conv2d, conv, deconv
 from .models import MeanScaleHyperprior, _nhwc_to_logical
 from .models_mm import _ContextModelMixin, _to_nhwc_bf16
 from .transforms import TransformStack, run_layers
@@ -35,8 +37,14 @@ from .transforms import TransformStack, run_layers
 __all__ = ["ResidualBlock", "Feature_encoder", "Feature_decoder", "Channel_aligner", "PatchEmbed", "Mlp", "WindowAttention",
            "SwinTransformerBlock", "Spatial_aligner", "Master_decoder", "Master_compresser"]
 
-# Inference runs the attention blocks on the libmmcodec kernels; tests flip this to cross-check against the torch-op path.
+# The attention blocks run on the libmmcodec kernels; tests flip this to cross-check against the torch-op path.
 attention_on_kernels = True
+# ... under autograd too (backward kernels in csrc/fusion_bwd.cu); False = the round-1 training path (torch ops in bf16 autocast)
+attention_train_on_kernels = True
+
+
+def _attn_kernels() -> bool:
+    return attention_on_kernels and (attention_train_on_kernels or not torch.is_grad_enabled())
 
 
 def _conv3x3(cin, cout, stride=1):
@@ -48,8 +56,9 @@ def _conv1x1(cin, cout):
 
 
 def _cat_if_training(x):
-    """A (x1, x2) channel pair stays a pair for the two-source kernels; under autograd it is concatenated once."""
-    if isinstance(x, (tuple, list)) and torch.is_grad_enabled():
+    """A (x1, x2) channel pair stays a pair for the two-source kernels (forward and, with ``transforms.two_source_train``,
+    backward); otherwise it is concatenated once under autograd."""
+    if isinstance(x, (tuple, list)) and torch.is_grad_enabled() and not T.two_source_train:
         return torch.cat(tuple(x), dim=-1)
     return x
 
@@ -172,8 +181,24 @@ class Channel_aligner(nn.Module):
 class _TokenLinear(nn.Linear):
     """nn.Linear (same parameters / keys) that can also run as a 1x1 tensor-core conv over a (B, H, W, C) token grid."""
 
+    def _alias(self) -> nn.Module:
+        """The same layer as a 1x1 Conv2d over the token grid (not a registered child; its parameters are views of this module's)."""
+        m = getattr(self, "_alias1", None)
+        if m is None:
+            m = Conv2d(self.in_features, self.out_features, 1, bias=self.bias is not None)
+            m._mmc_name = getattr(self, "_mmc_name", "linear")
+            object.__setattr__(self, "_alias1", m)
+        m._parameters["weight"] = self.weight.detach().view(self.out_features, self.in_features, 1, 1)
+        m._parameters["bias"] = self.bias.detach() if self.bias is not None else None
+        return m
+
     def on_grid(self, x: Tensor, act: int = L.ACT_NONE, out_f32: bool = False) -> Tensor:
         B, H, W, C = x.shape
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            # recorded for backward: dgrad / wgrad of the 1x1 layer on the tensor-core kernels, gradients land on weight / bias
+            if act != L.ACT_NONE or out_f32:
+                raise NotImplementedError("_TokenLinear.on_grid: the training path has no fused activation / fp32 output")
+            return AG.conv_alias(x, self.weight.view(self.out_features, C, 1, 1), self.bias, self._alias())
         d = ops.conv_desc(False, B, H, W, C, self.out_features, 1, 1, L.BF16, L.NHWC, L.F32 if out_f32 else L.BF16, L.NHWC, act=act)
         key = (self.weight._version, self.weight.data_ptr())
         if getattr(self, "_pack_key", None) != key:
@@ -228,11 +253,15 @@ class PatchEmbed(nn.Module):
         B, H, W, C = x.shape
         self._check(H, W)
         p, q = self.patch_size
-        on_kernels = attention_on_kernels and not torch.is_grad_enabled()
+        on_kernels = _attn_kernels()
         if on_kernels and (p, q) == (2, 2) and H % 2 == 0 and W % 2 == 0 and self.norm is None:
-            return run_layers([self._as_3x3()], x, "nhwc_bf16", "nhwc_bf16")
+            m = self._as_3x3()
+            if torch.is_grad_enabled() and (x.requires_grad or self.proj.weight.requires_grad):
+                # the zero-padded 3x3 kernel as a differentiable function of proj.weight: the gradient of the padding is dropped by F.pad
+                return AG.conv_alias(x, F.pad(self.proj.weight, (1, 0, 1, 0)), self.proj.bias, m)
+            return run_layers([m], x, "nhwc_bf16", "nhwc_bf16")
         patches = x.reshape(B, H // p, p, W // q, q, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H // p, W // q, p * q * C)
-        if on_kernels:
+        if on_kernels and not torch.is_grad_enabled():
             d = ops.conv_desc(False, B, H // p, W // q, p * q * C, self.embed_dim, 1, 1, L.BF16, L.NHWC, L.BF16, L.NHWC)
             key = (self.proj.weight._version, self.proj.weight.data_ptr())
             if getattr(self, "_pack_key", None) != key:
@@ -352,14 +381,14 @@ class SwinTransformerBlock(nn.Module):
         self.fused_window_process = fused_window_process
 
     def forward_grid(self, x: Tensor, guided: Tensor) -> Tensor:
-        """(B, H, W, C) bf16 token grids -> (B, H, W, C) bf16, all on the libmmcodec kernels (inference)."""
+        """(B, H, W, C) bf16 token grids -> (B, H, W, C) bf16, all on the libmmcodec kernels; with autograd on, every step is
+        recorded with its backward kernel (mmcodec.autograd: LayerNorm, the 1x1 Linear layers, window attention, GELU)."""
         a = self.attn
-        eps1, eps2 = self.norm1.eps, self.norm2.eps
-        q = a.qkv1.on_grid(ops.layernorm_bf16(x, self.norm1.weight, self.norm1.bias, eps1))
-        kv = a.qkv2.on_grid(ops.layernorm_bf16(guided, self.norm1.weight, self.norm1.bias, eps1))
-        ctx = ops.window_attention(q, kv, a.relative_position_bias_table, self.window_size, self.shift_size, a.num_heads, a.scale)
-        x, normed = ops.layernorm_bf16(x, self.norm2.weight, self.norm2.bias, eps2, delta=a.proj.on_grid(ctx), want_sum=True)
-        return x + self.mlp.fc2.on_grid(ops.gelu_bf16(self.mlp.fc1.on_grid(normed)))
+        q = a.qkv1.on_grid(AG.layernorm(x, self.norm1))
+        kv = a.qkv2.on_grid(AG.layernorm(guided, self.norm1))
+        ctx = AG.window_attention(q, kv, a.relative_position_bias_table, self.window_size, self.shift_size, a.num_heads, a.scale)
+        x, normed = AG.layernorm(x, self.norm2, delta=a.proj.on_grid(ctx))
+        return x + self.mlp.fc2.on_grid(AG.gelu(self.mlp.fc1.on_grid(normed)))
 
     def forward(self, x: Tensor, guided: Tensor) -> Tensor:
         """(B, L, C) tokens, torch ops (differentiable)."""
@@ -403,7 +432,7 @@ class Spatial_aligner(nn.Module):
         grid = tok.reshape(B, E, h * w).transpose(1, 2).reshape(B, h, w, E)    # memory reinterpreted as NCHW, then made NHWC
         wt = self.recovery.weight                                                 # (E, O, 2, 2)
         O = wt.shape[1]
-        if attention_on_kernels and not torch.is_grad_enabled():
+        if _attn_kernels():
             # the 2x2 stride-2 transposed conv as a 3x3 stride-2 one with kernel row / column 0 zero (out[2i + d] = x[i] w[1 + d]):
             # the transposed-conv kernel writes the full-resolution NHWC map directly, no depth-to-space copy
             m = getattr(self, "_recovery3", None)
@@ -418,6 +447,8 @@ class Spatial_aligner(nn.Module):
                     m.weight.copy_(F.pad(wt.detach(), (1, 0, 1, 0)))
                     m.bias.copy_(self.recovery.bias.detach())
                 self._recovery3_key = key
+            if torch.is_grad_enabled() and (grid.requires_grad or wt.requires_grad):
+                return AG.conv_alias(grid.contiguous(), F.pad(wt, (1, 0, 1, 0)), self.recovery.bias, m)
             return run_layers([m], grid.contiguous(), "nhwc_bf16", "nhwc_bf16")
         mat = wt.permute(2, 3, 1, 0).reshape(4 * O, E)
         out = F.linear(grid, mat.to(grid.dtype), self.recovery.bias.repeat(4).to(grid.dtype))
@@ -426,7 +457,7 @@ class Spatial_aligner(nn.Module):
     def forward_nhwc(self, x: Tensor, guided: Tensor) -> Tensor:
         B, H, W, _ = x.shape
         tok, gtok = self.patch_embeding1.forward_grid(x), self.patch_embeding2.forward_grid(guided)
-        if attention_on_kernels and not torch.is_grad_enabled():
+        if _attn_kernels():
             for blk in self.blocks:
                 tok = blk.forward_grid(tok, gtok)
         else:

@@ -66,9 +66,9 @@ class ESA(nn.Module):
     """Enhanced spatial attention gate (google.py:1432-1459).
 
     Every convolution (1x1 conv1 / conv_f / conv4, 3x3 conv_max / conv3 / conv3_, and the stride-2 3x3 conv2) runs on the
-    tensor-core conv kernel with NHWC bf16 activations, forward and backward; in inference the max-pool (7 / 3), the bilinear
-    upsampling fused with the add, and the sigmoid gate are single libmmcodec passes (csrc/esa.cu); under autograd they are torch
-    elementwise / pooling ops on the same bf16 channels-last tensors.  conv2 has padding 0,
+    tensor-core conv kernel with NHWC bf16 activations, forward and backward; the max-pool (7 / 3), the bilinear upsampling fused
+    with the add, and the sigmoid gate are single libmmcodec passes (csrc/esa.cu), with their adjoints in csrc/fusion_bwd.cu when
+    the gate trains on the kernels (``train_on_kernels``; otherwise the whole gate runs on torch's bf16 ops).  conv2 has padding 0,
     which the kernel's padding-k/2 addressing expresses exactly as the padding-1 convolution of the map shifted by one pixel:
     conv_p0(x)[o] = conv_p1(pad_top_left(x))[o + 1]."""
 
@@ -126,12 +126,13 @@ class ESA(nn.Module):
         ho, wo = (H - 3) // 2 + 1, (W - 3) // 2 + 1
         c1 = run_layers([self._conv2_p1()], F.pad(c1_, (0, 0, 1, 0, 1, 0)), "nhwc_bf16", "nhwc_bf16")[:, 1:1 + ho, 1:1 + wo]
         if needs_grad:
-            v_max = F.max_pool2d(c1.permute(0, 3, 1, 2), kernel_size=7, stride=3).permute(0, 2, 3, 1).contiguous()
+            # training on the kernels: the same pool / upsample + add / gate passes as inference, recorded with their adjoints
+            # (csrc/fusion_bwd.cu: arg-max gather, bilinear adjoint, gate backward)
+            v_max = AG.maxpool_nhwc(c1.contiguous(), 7, 3)
             c3 = run_layers([self.conv_max, self.relu, self.conv3, self.relu, self.conv3_], v_max, "nhwc_bf16", "nhwc_bf16")
-            c3 = F.interpolate(c3.permute(0, 3, 1, 2), (H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
             cf = run_layers([self.conv_f], c1_, "nhwc_bf16", "nhwc_bf16")
-            c4 = run_layers([self.conv4], (c3 + cf).contiguous(), "nhwc_bf16", "nhwc_bf16")
-            return x * torch.sigmoid(c4)
+            c4 = run_layers([self.conv4], AG.upsample_add(c3, cf), "nhwc_bf16", "nhwc_bf16")
+            return AG.sigmoid_gate(x, c4)
         # inference: pool, upsample + add and the gate are single libmmcodec passes (csrc/esa.cu)
         v_max = ops.maxpool_nhwc_bf16(c1, 7, 3)
         c3 = run_layers([self.conv_max, self.relu, self.conv3, self.relu, self.conv3_], v_max, "nhwc_bf16", "nhwc_bf16")

@@ -710,6 +710,98 @@ def sigmoid_gate_bf16(x: Tensor, gate: Tensor) -> Tensor:
     return y
 
 
+# ---- backward passes of the fusion layers' non-convolution steps (csrc/fusion_bwd.cu) ---------------------------------
+def maxpool_nhwc_bf16_idx(x: Tensor, k: int, stride: int):
+    """Max-pool that also returns the arg-max map (uint8, window-local index) for ``maxpool_nhwc_bf16_bwd``."""
+    _require_cuda(x)
+    x = _bf16c(x)
+    B, H, W, C = x.shape
+    if H < k or W < k:
+        raise ValueError(f"max-pool window {k} does not fit the {H}x{W} map")
+    shape = (B, (H - k) // stride + 1, (W - k) // stride + 1, C)
+    y = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    idx = torch.empty(shape, dtype=torch.uint8, device=x.device)
+    with _Timed("maxpool|esa"):
+        L.check(L.lib().mmc_maxpool_nhwc_bf16_idx(_ptr(x), B, H, W, C, k, stride, _ptr(y), _ptr(idx), _stream()))
+    return y, idx
+
+
+def maxpool_nhwc_bf16_bwd(gy: Tensor, idx: Tensor, in_shape, k: int, stride: int) -> Tensor:
+    _require_cuda(gy, idx)
+    gy = _bf16c(gy)
+    B, H, W, C = in_shape
+    if tuple(gy.shape) != tuple(idx.shape) or idx.dtype != torch.uint8:
+        raise ValueError("maxpool_nhwc_bf16_bwd: gy / idx mismatch")
+    dx = torch.empty((B, H, W, C), dtype=torch.bfloat16, device=gy.device)
+    with _Timed("maxpool_bwd|esa"):
+        L.check(L.lib().mmc_maxpool_nhwc_bf16_bwd(_ptr(gy), _ptr(idx.contiguous()), B, H, W, C, k, stride, _ptr(dx), _stream()))
+    return dx
+
+
+def upsample_bilinear_bwd_bf16(g: Tensor, hs: int, ws: int) -> Tensor:
+    """Adjoint of the bilinear upsampling (hs, ws) -> g's size: (B, H, W, C) bf16 -> (B, hs, ws, C) bf16."""
+    _require_cuda(g)
+    g = _bf16c(g)
+    B, H, W, C = g.shape
+    out = torch.empty((B, hs, ws, C), dtype=torch.bfloat16, device=g.device)
+    with _Timed("upsample_bwd|esa"):
+        L.check(L.lib().mmc_upsample_bilinear_bwd_bf16(_ptr(g), B, H, W, C, hs, ws, _ptr(out), _stream()))
+    return out
+
+
+def sigmoid_gate_bwd_bf16(g: Tensor, x: Tensor, gate: Tensor):
+    """(dx, dgate) of y = x * sigmoid(gate)."""
+    _require_cuda(g, x, gate)
+    g, x, gate = _bf16c(g), _bf16c(x), _bf16c(gate)
+    if not (g.shape == x.shape == gate.shape):
+        raise ValueError("sigmoid_gate_bwd_bf16: shape mismatch")
+    dx, dgate = torch.empty_like(x), torch.empty_like(x)
+    with _Timed("sigmoid_gate_bwd|esa"):
+        L.check(L.lib().mmc_sigmoid_gate_bwd_bf16(_ptr(g), _ptr(x), _ptr(gate), x.numel(), _ptr(dx), _ptr(dgate), _stream()))
+    return dx, dgate
+
+
+def gelu_bwd_bf16(g: Tensor, x: Tensor) -> Tensor:
+    _require_cuda(g, x)
+    g, x = _bf16c(g), _bf16c(x)
+    dx = torch.empty_like(x)
+    with _Timed("gelu_bwd|attn"):
+        L.check(L.lib().mmc_gelu_bwd_bf16(_ptr(g), _ptr(x), x.numel(), _ptr(dx), _stream()))
+    return dx
+
+
+def layernorm_bwd_bf16(g: Tensor, v: Tensor, weight: Tensor, eps: float = 1e-5, g_sum: Optional[Tensor] = None):
+    """(dv bf16, dweight fp32 [C], dbias fp32 [C]) of y = LayerNorm(v); ``g_sum`` is added to dv (residual-stream gradient)."""
+    _require_cuda(g, v, weight)
+    g, v = _bf16c(g), _bf16c(v)
+    C = v.shape[-1]
+    if g.shape != v.shape or (g_sum is not None and g_sum.shape != v.shape):
+        raise ValueError("layernorm_bwd_bf16: shape mismatch")
+    if g_sum is not None:
+        g_sum = _bf16c(g_sum)
+    dv = torch.empty_like(v)
+    dwb = torch.zeros((2, C), dtype=torch.float32, device=v.device)
+    with _Timed("layernorm_bwd|attn"):
+        L.check(L.lib().mmc_layernorm_bwd_bf16(_ptr(g), _ptr(v), _ptr(g_sum), _ptr(_f32c(weight.detach())), v.numel() // C, C, float(eps),
+                                               _ptr(dv), _ptr(dwb[0]), _ptr(dwb[1]), _stream()))
+    return dv, dwb[0], dwb[1]
+
+
+def window_attention_bwd(q: Tensor, kv: Tensor, bias_table: Tensor, dout: Tensor, window: int, shift: int, heads: int, scale: float):
+    """(dq, dkv, dtable) of ``window_attention``."""
+    _require_cuda(q, kv, bias_table, dout)
+    q, kv, dout = _bf16c(q), _bf16c(kv), _bf16c(dout)
+    B, H, W, C = q.shape
+    if kv.shape != (B, H, W, 2 * C) or dout.shape != q.shape or C % heads:
+        raise ValueError("window_attention_bwd: shape mismatch")
+    dq, dkv = torch.empty_like(q), torch.empty_like(kv)
+    dtable = torch.zeros(((2 * window - 1) ** 2, heads), dtype=torch.float32, device=q.device)
+    with _Timed("window_attention_bwd|attn"):
+        L.check(L.lib().mmc_window_attention_bwd(_ptr(q), _ptr(kv), _ptr(_f32c(bias_table.detach())), _ptr(dout), B, H, W, heads, C // heads,
+                                                 window, shift, float(scale), _ptr(dq), _ptr(dkv), _ptr(dtable), _stream()))
+    return dq, dkv, dtable
+
+
 def conv3x3_mean(t: Tensor, weight: Tensor, bias: Optional[Tensor]) -> Tensor:
     """Spatial mean of conv3x3(t) (stride 1, padding 1) per sample and output channel, computed from border-corrected channel sums
     of ``t`` instead of the convolution (see mmc_conv3x3_mean).  t: (B, H, W, C) bf16 NHWC; weight (O, C, 3, 3); returns (B, O) fp32."""

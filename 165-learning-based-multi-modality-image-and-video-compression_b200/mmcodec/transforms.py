@@ -26,6 +26,10 @@ FORMATS = ("nchw_f32", "nhwc_bf16", "nhwc_f32")
 # Set by mmcodec.config; tests flip it to cross-check the two kernels against each other.
 use_tensor_cores = True
 
+# Two-source layers (cat([a, b]) -> conv, google.py:1153 ...) under autograd: True = the two-source kernel forward and per-source
+# gradients backward (no concatenated tensor in either pass); False = torch.cat first (the round-1 training path; tests compare both).
+two_source_train = True
+
 # Arithmetic of the transform stacks (BASELINE.json north_star: "bf16/tf32 with fp32 accumulate ... 1e-2 relative in bf16, 1e-4 in
 # fp32"): "bf16" = bf16 operands, fp32 accumulate, fused GDN (the fast path); "fp32" = every layer evaluated to ~1e-5 relative on
 # the SAME bf16 tensor-core kernel through a three-term operand split (see _run_layers_fp32), fp32 activations between layers,
@@ -138,10 +142,15 @@ def run_layers(layers, x: Tensor, in_fmt: str, out_fmt: str, out2: int = 0, _tra
         x1, x2 = x
         ops._require_cuda(x1, x2)
         first = next((m for m in layers if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d))), None)
+        narrow_out = first is not None and isinstance(first, nn.ConvTranspose2d) and first.out_channels <= 4 and out_fmt == "nchw_f32"
         fusable = (in_fmt == "nhwc_bf16" and use_tensor_cores and first is not None and x1.shape[-1] % 64 == 0 and x2.shape[-1] % 8 == 0
-                   and x1.shape[:3] == x2.shape[:3] and first.out_channels % 16 == 0
-                   and not (torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad or any(p.requires_grad for p in first.parameters()))))
-        if fusable:
+                   and x1.shape[:3] == x2.shape[:3] and (first.out_channels % 16 == 0 or narrow_out))
+        wants = torch.is_grad_enabled() and (x1.requires_grad or x2.requires_grad or (first is not None and any(p.requires_grad for p in first.parameters())))
+        if fusable and wants and _train_dispatch and _precision != "fp32" and two_source_train:
+            # training: the same two-source kernel forward, per-source weight / input gradients backward (no concatenation either way)
+            from . import autograd as AG
+            return AG.run_layers_train(layers, (x1, x2), in_fmt, out_fmt, out2)
+        if fusable and not wants:
             pair = (x1.contiguous(), x2.contiguous())
             x = pair[0]
         else:

@@ -420,6 +420,37 @@ MMC_API int mmc_eb_backward(const float *x, const float *noise, const float *gra
                             float likelihood_bound, int64_t outer, int64_t C, int64_t inner, float *dx, float *dparams,
                             void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Backward passes of the non-convolution steps of the fusion layers (csrc/fusion_bwd.cu), so that the training step of the
+ * RGB + depth / RGB-T models (examples/train.py:208-260) keeps every activation-sized pass on these kernels.  Activations and
+ * their gradients are NHWC bf16; every adjoint is a gather with fp32 accumulation (no atomics on activations).
+ *
+ * ESA gate (ESA.forward, models/google.py:1445-1459):
+ * mmc_maxpool_nhwc_bf16_idx: mmc_maxpool_nhwc_bf16 that also records the arg-max of every window as the window-local index
+ *   ky * k + kx in a uint8 map shaped like y (first maximum in scan order, NaN takes over: the rule of F.max_pool2d); k <= 15.
+ * mmc_maxpool_nhwc_bf16_bwd: dx[b][iy][ix][c] = sum of gy over the windows whose arg-max is (iy, ix).
+ * mmc_upsample_bilinear_bwd_bf16: adjoint of F.interpolate(small, (H, W), "bilinear", align_corners=False): g is (B, H, W, C),
+ *   dsmall (B, hs, ws, C); C % 8 == 0.  (`c3 + cf` passes g unchanged to cf.)
+ * mmc_sigmoid_gate_bwd_bf16: y = x * sigmoid(gate): dx = g * s, dgate = g * x * s * (1 - s); n % 8 == 0.
+ *
+ * Token side of Spatial_aligner (models/master.py:463-568, 572-706):
+ * mmc_gelu_bwd_bf16: dx = g * (Phi(x) + x phi(x)) for nn.GELU() (erf form); n even.
+ * mmc_layernorm_bwd_bf16: v = the rows that were normalised (x, or the bf16 sum x + delta written by mmc_layernorm_bf16);
+ *   dv = LayerNorm backward of g [+ g_sum, the gradient reaching v through the residual stream; may be NULL];
+ *   dweight[C] += sum_rows g * xhat, dbias[C] += sum_rows g (fp32, ADDED into: the caller zeroes or accumulates).  C <= 256.
+ * mmc_window_attention_bwd: gradients of mmc_window_attention w.r.t. q (dq like q), kv (dkv like kv) and the relative-position
+ *   bias table (dtable ((2 ws - 1)^2, heads) fp32, ADDED into).  Same layout rules and limits as the forward call. */
+MMC_API int mmc_maxpool_nhwc_bf16_idx(const void *x, int B, int H, int W, int C, int k, int stride, void *y, void *idx, void *stream);
+MMC_API int mmc_maxpool_nhwc_bf16_bwd(const void *gy, const void *idx, int B, int H, int W, int C, int k, int stride, void *dx, void *stream);
+MMC_API int mmc_upsample_bilinear_bwd_bf16(const void *g, int B, int H, int W, int C, int hs, int ws, void *dsmall, void *stream);
+MMC_API int mmc_sigmoid_gate_bwd_bf16(const void *g, const void *x, const void *gate, int64_t n, void *dx, void *dgate, void *stream);
+MMC_API int mmc_gelu_bwd_bf16(const void *g, const void *x, int64_t n, void *dx, void *stream);
+MMC_API int mmc_layernorm_bwd_bf16(const void *g, const void *v, const void *g_sum, const float *weight, int64_t rows, int C, float eps,
+                                   void *dv, float *dweight, float *dbias, void *stream);
+MMC_API int mmc_window_attention_bwd(const void *q, const void *kv, const float *bias_table, const void *dout, int B, int H, int W,
+                                     int heads, int head_dim, int window, int shift, float scale, void *dq, void *dkv, float *dtable,
+                                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

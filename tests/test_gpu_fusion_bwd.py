@@ -1,0 +1,331 @@
+"""GPU tests of the fusion layers' backward kernels (csrc/fusion_bwd.cu) and of the training paths built on them
+(cat-free ``tran_conv`` / two-source layers under autograd, the ESA gate, the window cross-attention).
+
+Every kernel is compared with torch autograd of the SAME function evaluated in fp32 / fp64 on the bf16-rounded inputs (the op the
+reference executes: F.max_pool2d, F.interpolate, sigmoid gate, nn.LayerNorm, nn.GELU, WindowAttention.forward); tolerances are
+the bf16 output rounding (2^-8 relative) plus accumulation slack, written at each assert.  Module-level tests compare the
+kernel training path with the torch-op training path of the same module on the same weights and inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import torch_port as tp
+
+pytestmark = pytest.mark.gpu
+
+import mmcodec  # noqa: E402
+from mmcodec import autograd as AG  # noqa: E402
+from mmcodec import models_master as mst  # noqa: E402
+from mmcodec import ops  # noqa: E402
+from mmcodec import transforms as T  # noqa: E402
+from mmcodec.layers import GDN, conv, deconv  # noqa: E402
+from mmcodec.models_mm import ESA  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rel_max(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rel_rms(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float(torch.sqrt(((a - b) ** 2).mean() / (b ** 2).mean().clamp_min(1e-30)))
+
+
+BF16_EPS = 2.0 ** -8
+
+
+# ---- ESA glue -------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,C", [(2, 31, 47, 48), (1, 7, 7, 8), (1, 64, 95, 32), (3, 10, 9, 6)])
+def test_maxpool_argmax_and_adjoint(B, H, W, C):
+    gen = torch.Generator().manual_seed(H * W + C)
+    # few distinct values -> many ties inside the 7x7 windows: the arg-max rule (first maximum in scan order) matters
+    x = (torch.randint(-6, 7, (B, H, W, C), generator=gen).float() / 4).bfloat16().to(dev())
+    y, idx = ops.maxpool_nhwc_bf16_idx(x, 7, 3)
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    yr = F.max_pool2d(xr, kernel_size=7, stride=3)
+    assert torch.equal(y.float(), yr.detach().permute(0, 2, 3, 1))
+    assert torch.equal(y, ops.maxpool_nhwc_bf16(x, 7, 3))
+    gy = torch.randn(y.shape, generator=gen).bfloat16().to(dev())
+    yr.backward(gy.float().permute(0, 3, 1, 2))
+    dx = ops.maxpool_nhwc_bf16_bwd(gy, idx, x.shape, 7, 3)
+    ref = xr.grad.permute(0, 2, 3, 1)
+    # up to 9 bf16 gradients summed in fp32, rounded once
+    assert float((dx.float() - ref).abs().max()) <= BF16_EPS * float(ref.abs().max()) + 1e-6
+    # autograd wrapper
+    xa = x.clone().requires_grad_(True)
+    AG.maxpool_nhwc(xa, 7, 3).backward(gy)
+    assert torch.equal(xa.grad, dx)
+    with pytest.raises(ValueError):
+        ops.maxpool_nhwc_bf16_idx(x[:, :5], 7, 3)
+
+
+@pytest.mark.parametrize("B,hs,ws,H,W,C", [(2, 9, 14, 31, 47, 48), (1, 1, 1, 5, 6, 8), (1, 41, 62, 127, 191, 48), (2, 3, 5, 3, 5, 16), (1, 6, 4, 7, 9, 8)])
+def test_bilinear_upsample_adjoint(B, hs, ws, H, W, C):
+    gen = torch.Generator().manual_seed(hs * 100 + W)
+    small = torch.randn(B, hs, ws, C, generator=gen).bfloat16().to(dev())
+    add = torch.randn(B, H, W, C, generator=gen).bfloat16().to(dev())
+    g = torch.randn(B, H, W, C, generator=gen).bfloat16().to(dev())
+    sr = small.double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    up = F.interpolate(sr, (H, W), mode="bilinear", align_corners=False)
+    up.backward(g.double().permute(0, 3, 1, 2))
+    ref = sr.grad.permute(0, 2, 3, 1)
+    d = ops.upsample_bilinear_bwd_bf16(g, hs, ws)
+    # fp32 interpolation weights vs fp64 ones + one bf16 rounding of a sum of up to ~(2 H / hs)^2 terms
+    assert float((d.double() - ref).abs().max()) <= 1.5 * BF16_EPS * float(ref.abs().max()) + 1e-5
+    # the adjoint identity <up(s), g> == <s, up^T(g)> ties the backward kernel to the forward kernel itself
+    zero = torch.zeros_like(add)
+    lhs = float((ops.upsample_bilinear_add_bf16(small, zero).double() * g.double()).sum())
+    rhs = float((small.double() * d.double()).sum())
+    scale = float((small.double().abs().sum() * g.double().abs().max()))
+    assert abs(lhs - rhs) <= 4 * BF16_EPS * scale / max(1, hs * ws) ** 0.5 + 1e-3
+    # autograd wrapper: gradient of `add` is g itself
+    s2, a2 = small.clone().requires_grad_(True), add.clone().requires_grad_(True)
+    AG.upsample_add(s2, a2).backward(g)
+    assert torch.equal(a2.grad, g) and torch.equal(s2.grad, d)
+
+
+def test_sigmoid_gate_and_gelu_backward():
+    gen = torch.Generator().manual_seed(5)
+    x = (2 * torch.randn(3, 17, 9, 64, generator=gen)).bfloat16().to(dev())
+    c = (3 * torch.randn(3, 17, 9, 64, generator=gen)).bfloat16().to(dev())
+    g = torch.randn(3, 17, 9, 64, generator=gen).bfloat16().to(dev())
+    xr, cr = x.double().requires_grad_(True), c.double().requires_grad_(True)
+    (xr * torch.sigmoid(cr)).backward(g.double())
+    dx, dc = ops.sigmoid_gate_bwd_bf16(g, x, c)
+    assert float((dx.double() - xr.grad).abs().max()) <= 1.5 * BF16_EPS * float(xr.grad.abs().max())
+    assert float((dc.double() - cr.grad).abs().max()) <= 1.5 * BF16_EPS * float(cr.grad.abs().max())
+    x2, c2 = x.clone().requires_grad_(True), c.clone().requires_grad_(True)
+    AG.sigmoid_gate(x2, c2).backward(g)
+    assert torch.equal(x2.grad, dx) and torch.equal(c2.grad, dc)
+    # GELU (erf form)
+    hr = x.double().requires_grad_(True)
+    F.gelu(hr).backward(g.double())
+    dh = ops.gelu_bwd_bf16(g, x)
+    assert float((dh.double() - hr.grad).abs().max()) <= 1.5 * BF16_EPS * float(hr.grad.abs().max())
+    with pytest.raises((ValueError, NotImplementedError)):
+        ops.sigmoid_gate_bwd_bf16(g.reshape(-1)[:12], x.reshape(-1)[:12], c.reshape(-1)[:12])
+
+
+@pytest.mark.parametrize("rows,C,fused", [(300, 96, False), (300, 96, True), (17, 40, True), (1, 256, False), (5000, 96, True)])
+def test_layernorm_backward(rows, C, fused):
+    gen = torch.Generator().manual_seed(rows + C)
+    x = torch.randn(rows, C, generator=gen).bfloat16().to(dev())
+    delta = torch.randn(rows, C, generator=gen).bfloat16().to(dev()) if fused else None
+    w = (1 + 0.3 * torch.randn(C, generator=gen)).to(dev())
+    b = (0.2 * torch.randn(C, generator=gen)).to(dev())
+    g = torch.randn(rows, C, generator=gen).bfloat16().to(dev())
+    gs = torch.randn(rows, C, generator=gen).bfloat16().to(dev()) if fused else None
+    norm = torch.nn.LayerNorm(C).to(dev())
+    with torch.no_grad():
+        norm.weight.copy_(w)
+        norm.bias.copy_(b)
+    xa = x.clone().requires_grad_(True)
+    da = delta.clone().requires_grad_(True) if fused else None
+    out = AG.layernorm(xa, norm, delta=da)
+    if fused:
+        s, y = out
+        torch.autograd.backward([s, y], [gs, g])
+        v = s.detach()
+    else:
+        out.backward(g)
+        v = x
+    # reference: fp64 LayerNorm of the SAME normalised rows v (the fused add rounds the sum to bf16, as the unfused op would)
+    vr = v.double().requires_grad_(True)
+    wr, br = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    yr = F.layer_norm(vr, (C,), wr, br, norm.eps)
+    yr.backward(g.double())
+    ref_dv = vr.grad + (gs.double() if fused else 0)
+    tol = 1.5 * BF16_EPS * float(ref_dv.abs().max())
+    assert float((xa.grad.double() - ref_dv).abs().max()) <= tol
+    if fused:
+        assert torch.equal(da.grad, xa.grad)
+    assert rel_max(norm.weight.grad, wr.grad) < 1e-4 and rel_max(norm.bias.grad, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("H,W,ws,shift", [(8, 16, 4, 0), (8, 16, 4, 2), (12, 12, 4, 3), (2, 6, 2, 1), (4, 8, 4, 0)])
+def test_window_attention_backward_vs_fp64_autograd(H, W, ws, shift):
+    gen = torch.Generator().manual_seed(H * 100 + W + shift)
+    B, heads, C = 2, 3, 96
+    q = torch.randn(B, H, W, C, generator=gen).bfloat16()
+    kv = torch.randn(B, H, W, 2 * C, generator=gen).bfloat16()
+    table = 0.5 * torch.randn((2 * ws - 1) ** 2, heads, generator=gen)
+    dout = torch.randn(B, H, W, C, generator=gen).bfloat16()
+    scale = (C // heads) ** -0.5
+    qa, kva = q.to(dev()).requires_grad_(True), kv.to(dev()).requires_grad_(True)
+    ta = table.to(dev()).requires_grad_(True)
+    AG.window_attention(qa, kva, ta, ws, shift, heads, scale).backward(dout.to(dev()))
+    # fp64 reference: roll -> partition -> attention -> reverse -> roll back (the oracle's helpers)
+    qr, kvr, tr = q.double().requires_grad_(True), kv.double().requires_grad_(True), table.double().requires_grad_(True)
+    qf, kf, vf = qr, kvr[..., :C], kvr[..., C:]
+    if shift:
+        qf, kf, vf = (torch.roll(t, (-shift, -shift), (1, 2)) for t in (qf, kf, vf))
+    N = ws * ws
+    split = lambda t: tp._to_windows(t, ws).reshape(-1, N, heads, C // heads).transpose(1, 2)
+    att = (split(qf) * scale) @ split(kf).transpose(-2, -1)
+    att = att + tr[tp.relative_position_index(ws).view(-1)].view(N, N, heads).permute(2, 0, 1)
+    if shift:
+        att = (att.view(B, -1, heads, N, N) + tp.shift_attention_mask(H, W, ws, shift).double()[None, :, None]).view(-1, heads, N, N)
+    o = (att.softmax(-1) @ split(vf)).transpose(1, 2).reshape(-1, N, C)
+    o = tp._from_windows(o, ws, B, H, W)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    o.backward(dout.double())
+    for name, got, ref in (("dq", qa.grad, qr.grad), ("dkv", kva.grad, kvr.grad)):
+        assert float((got.double().cpu() - ref).abs().max()) <= 2 * BF16_EPS * float(ref.abs().max()) + 1e-4, name
+    assert rel_max(ta.grad, tr.grad) < 1e-3            # fp32 sums of fp32 terms, __expf softmax
+
+
+# ---- two-source layers under autograd ---------------------------------------------------------------------------------------
+def _two_source_case(layer, gdn, out_fmt, c1, c2, hw, gen):
+    x1 = torch.randn(2, hw[0], hw[1], c1, generator=gen).bfloat16().to(dev())
+    x2 = torch.randn(2, hw[0], hw[1], c2, generator=gen).bfloat16().to(dev())
+    layers = [layer] + ([gdn] if gdn is not None else [])
+    res = {}
+    for mode in (True, False):
+        T.two_source_train = mode
+        try:
+            a, b = x1.clone().requires_grad_(True), x2.clone().requires_grad_(True)
+            for m in layers:
+                m.zero_grad(set_to_none=True)
+            y = T.run_layers(layers, (a, b), "nhwc_bf16", out_fmt)
+            w = torch.linspace(-1, 1, y.numel(), device=dev()).reshape(y.shape).to(y.dtype)
+            (y.float() * w.float()).sum().backward()
+            res[mode] = (y.detach().float(), a.grad.float(), b.grad.float(), [p.grad.clone() for m in layers for p in m.parameters()])
+        finally:
+            T.two_source_train = True
+    (y1, a1, b1, p1), (y0, a0, b0, p0) = res[True], res[False]
+    assert y1.shape == y0.shape and rel_rms(y1, y0) < 1e-6                 # same kernel arithmetic (K order is the same)
+    assert rel_rms(a1, a0) < 1e-6 and rel_rms(b1, b0) < 1e-6              # dgrad per weight slice == slice of the joint dgrad
+    for g1, g0 in zip(p1, p0):
+        assert g1.shape == g0.shape
+        assert rel_rms(g1, g0) < 2e-3, (g1.shape, rel_rms(g1, g0))        # split-K partial sums land in a different order
+
+
+def test_two_source_layers_train_without_concatenation():
+    gen = torch.Generator().manual_seed(11)
+    torch.manual_seed(3)
+    _two_source_case(conv(256, 128, stride=1).to(dev()), None, "nhwc_bf16", 128, 128, (24, 40), gen)                 # tran_conv
+    _two_source_case(conv(256, 128).to(dev()), GDN(128).to(dev()), "nhwc_bf16", 128, 128, (24, 40), gen)           # pic2_g_a_conv2 + GDN
+    _two_source_case(deconv(256, 128).to(dev()), GDN(128, inverse=True).to(dev()), "nhwc_bf16", 128, 128, (12, 20), gen)
+    _two_source_case(conv(192, 64, kernel_size=3, stride=1).to(dev()), None, "nhwc_bf16", 128, 64, (16, 24), gen)  # Feature_decoder pair
+    _two_source_case(conv(256, 192).to(dev()), None, "nhwc_f32", 128, 128, (23, 39), gen)                           # odd size, fp32 out
+    _two_source_case(deconv(256, 1).to(dev()), None, "nchw_f32", 128, 128, (12, 20), gen)                          # pic2_g_s_conv4
+
+
+def test_two_source_narrow_deconv_forward_matches_concatenation():
+    """The reconstruction layer of the depth branch (deconv(2N, 1), google.py:1246) fed by a pair: the GEMM + col2im kernel
+    reading two sources equals the same kernel on the concatenated map."""
+    gen = torch.Generator().manual_seed(12)
+    torch.manual_seed(4)
+    layer = deconv(256, 1).to(dev())
+    x1 = torch.randn(2, 20, 28, 128, generator=gen).bfloat16().to(dev())
+    x2 = torch.randn(2, 20, 28, 128, generator=gen).bfloat16().to(dev())
+    with torch.no_grad():
+        y_pair = T.run_layers([layer], (x1, x2), "nhwc_bf16", "nchw_f32")
+        y_cat = T.run_layers([layer], torch.cat((x1, x2), -1), "nhwc_bf16", "nchw_f32")
+    assert torch.equal(y_pair, y_cat)
+
+
+# ---- modules: kernel training path vs torch-op training path ------------------------------------------------------------------
+def test_esa_gate_trains_on_kernels():
+    torch.manual_seed(7)
+    gate = ESA(128).to(dev())
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 48, 72, 128, generator=gen).bfloat16().to(dev())
+    w = torch.randn(2, 48, 72, 128, generator=gen).to(dev())
+    res = {}
+    for on in (True, False):
+        gate.train_on_kernels = on
+        gate.zero_grad(set_to_none=True)
+        xa = x.clone().requires_grad_(True)
+        y = gate.forward_nhwc_bf16(xa)
+        (y.float() * w).sum().backward()
+        res[on] = (y.detach().float(), xa.grad.float(), {n: p.grad.clone() for n, p in gate.named_parameters()})
+    gate.train_on_kernels = False
+    (y1, d1, p1), (y0, d0, p0) = res[True], res[False]
+    # bf16 activations through 7 convolutions on two different back ends (tcgen05 kernels vs cuDNN autocast)
+    assert rel_rms(y1, y0) < 1e-2 and rel_rms(d1, d0) < 3e-2
+    for n in p0:
+        assert p1[n] is not None and torch.isfinite(p1[n]).all(), n
+        cos = float(F.cosine_similarity(p1[n].flatten().double(), p0[n].flatten().double(), dim=0))
+        assert cos > 0.98, (n, cos)
+
+
+def test_swin_block_trains_on_kernels():
+    torch.manual_seed(9)
+    H, W, C = 8, 12, 96
+    for shift in (0, 2):
+        blk = mst.SwinTransformerBlock(dim=C, input_resolution=(H, W), num_heads=3, window_size=4, shift_size=shift).to(dev())
+        with torch.no_grad():
+            blk.attn.relative_position_bias_table.mul_(20)          # make the bias matter
+        gen = torch.Generator().manual_seed(10 + shift)
+        x = torch.randn(2, H, W, C, generator=gen).bfloat16().to(dev())
+        gd = torch.randn(2, H, W, C, generator=gen).bfloat16().to(dev())
+        w = torch.randn(2, H, W, C, generator=gen).to(dev())
+        # kernels
+        xa, ga = x.clone().requires_grad_(True), gd.clone().requires_grad_(True)
+        y1 = blk.forward_grid(xa, ga)
+        (y1.float() * w).sum().backward()
+        p1 = {n: p.grad.clone() for n, p in blk.named_parameters()}
+        d1 = (xa.grad.float(), ga.grad.float())
+        blk.zero_grad(set_to_none=True)
+        # torch ops in fp32 on the same bf16 inputs (the reference's SwinTransformerBlock.forward, master.py:652-706)
+        xb, gb = x.float().requires_grad_(True), gd.float().requires_grad_(True)
+        y0 = blk(xb.reshape(2, H * W, C), gb.reshape(2, H * W, C)).reshape(2, H, W, C)
+        (y0 * w).sum().backward()
+        assert rel_rms(y1.float(), y0.detach()) < 1e-2
+        assert rel_rms(d1[0], xb.grad) < 3e-2 and rel_rms(d1[1], gb.grad) < 3e-2
+        for n, p in blk.named_parameters():
+            assert p1[n] is not None, n
+            cos = float(F.cosine_similarity(p1[n].flatten().double(), p.grad.flatten().double(), dim=0))
+            assert cos > 0.99, (n, shift, cos)
+        blk.zero_grad(set_to_none=True)
+
+
+def test_master_training_paths_agree():
+    """One forward + backward of Master_compresser with the attention blocks / two-source layers on the kernels vs the round-1
+    training path (torch ops in bf16 autocast, concatenation): same loss to 1e-2, parameter gradients aligned."""
+    torch.manual_seed(0)
+    guide = mmcodec.Guided_compresser(channel=1).eval()
+    master = mmcodec.Master_compresser(width=64, height=128, channel=3)
+    for n in (guide, master):
+        n.update()
+        n.to(dev())
+    master.train()
+    gen = torch.Generator().manual_seed(4)
+    x = torch.rand(2, 3, 128, 256, generator=gen).to(dev())
+    t = torch.rand(2, 1, 64, 128, generator=gen).to(dev())
+    with torch.no_grad():
+        og = guide(t)
+    crit = mmcodec.RateDistortionLoss(3)
+    res = {}
+    for on in (True, False):
+        mst.attention_train_on_kernels = on
+        T.two_source_train = on
+        try:
+            master.zero_grad(set_to_none=True)
+            torch.manual_seed(123)                       # same quantisation noise draws
+            out = crit(master(x, t, og["hidden"]), x)
+            out["loss"].backward()
+            res[on] = (float(out["loss"].detach()), {n: p.grad.clone() for n, p in master.named_parameters() if p.grad is not None})
+        finally:
+            mst.attention_train_on_kernels = True
+            T.two_source_train = True
+    (l1, p1), (l0, p0) = res[True], res[False]
+    assert math.isfinite(l1) and abs(l1 - l0) / abs(l0) < 1e-2
+    assert set(p1) == set(p0)
+    low = []
+    for n in p0:
+        assert torch.isfinite(p1[n]).all(), n
+        if p0[n].dim() >= 2 and float(p0[n].abs().max()) > 0:
+            cos = float(F.cosine_similarity(p1[n].flatten().double(), p0[n].flatten().double(), dim=0))
+            if cos < 0.9:
+                low.append((n, round(cos, 3)))
+    assert not low, low
