@@ -1,0 +1,324 @@
+// rans_device.cu -- range-ANS coder ON THE DEVICE ("GPU/parallel rANS").
+//
+// The reference codes one image as ONE serial rANS stream (compressai/cpp_exts/rans/rans_interface.cpp:108-200: 64-bit state,
+// 32-bit words) -- a dependency chain over every symbol of the image that no device can shorten, which is why csrc/rans.cu keeps it
+// on host threads for byte-identical streams.  This file is the other half of that row: a container of our own ("lane container",
+// magic "MMCL") in which the symbols of an image are dealt round-robin onto S independent rANS lanes, so that the symbols never
+// leave the GPU and compress() stops being bound by the host coder.  Same probability model as the reference coder: the model's
+// 16-bit quantised CDF tables (entropy_models.py:206-214), symbol -> CDF row through the same `indexes`, the same escape scheme
+// for values outside a row's range (4-bit bypass nibbles: rans_interface.cpp:117-171, restated in csrc/rans.cu tokens_of), so the
+// rate is the reference's plus the lane headers.  Streams of the two containers are NOT interchangeable; the host coder stays
+// the default and the reference-compatible one.
+//
+// Container (little endian), one per image and latent tensor:
+//   u32 magic "MMCL" | u32 n symbols | u32 S lanes | u32 0 | u32 state[S] | u32 words[S] | u16 payload[sum(words)] | pad to 4 bytes
+// Symbol i (logical order) is position i / S of lane i % S.  A lane is a classic word-renormalised rANS (32-bit state x in
+// [2^16, 2^32), 16-bit words): the encoder walks its tokens LAST to first with, per token (start, freq) against 2^bits,
+//       if (x >= ((2^16 >> bits) << 16) * freq) { emit low 16 bits of x; x >>= 16; }       x = ((x / freq) << bits) + x % freq + start
+// starting from x = 2^16; state[l] is the final x, payload words are stored in the order the decoder reads them (reverse of
+// emission).  The decoder starts from state[l] and per token does  slot = x & (2^bits - 1);  x = freq * (x >> bits) + slot - start;
+// if (x < 2^16) x = (x << 16) | next word.  A CPU restatement of exactly this text is oracle/lane_rans.py (tests compare bytes).
+//
+// Kernels: lanes are threads (32 lanes per warp read symbols / indexes coalesced); the per-lane chain is serial, so the loads of a
+// chunk of 32 steps (symbol, index -> CDF entry) are issued ahead of the chain and only the state arithmetic stays on it.
+//   pass 1  rans_lane_encode<false>: final state and word count of every lane        (no stores)
+//   scan    rans_lane_header:        lane offsets, header, total size, capacity check  (one CTA per image)
+//   pass 2  rans_lane_encode<true>:  the same chain again, words written in place
+#include "common.cuh"
+
+namespace mmc {
+
+constexpr int kLanePrecision = 16;
+constexpr int kLaneBypassBits = 4;
+constexpr uint32_t kLaneMaxBypass = (1u << kLaneBypassBits) - 1;
+constexpr uint32_t kLaneL = 1u << 16;
+constexpr uint32_t kLaneMagic = 0x4C434D4Du;   // "MMCL"
+constexpr int kLaneChunk = 32;
+constexpr int kMaxLanes = 1024;
+
+enum LaneStatus { LANE_OK = 0, LANE_BAD_INDEX = 1, LANE_BAD_CDF = 2, LANE_CAPACITY = 4, LANE_BAD_STREAM = 8 };
+
+struct LaneTables {
+    const int32_t *cdfs;
+    int n_cdfs, stride;
+    const int32_t *sizes, *offsets;
+};
+
+template <bool kWrite>
+__device__ __forceinline__ void lane_put(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t start, uint32_t freq, uint32_t bits)
+{
+    const uint64_t x_max = (uint64_t)((kLaneL >> bits) << 16) * freq;
+    if ((uint64_t)x >= x_max) {
+        if (kWrite) *--ptr = (uint16_t)(x & 0xffffu);
+        ++count;
+        x >>= 16;
+    }
+    const uint32_t q = x / freq;
+    x = (q << bits) + (x - q * freq) + start;
+}
+
+// all tokens of an escaped symbol, last token first (the forward order is: main token, count nibbles, raw nibbles)
+template <bool kWrite>
+__device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t raw, uint32_t start, uint32_t freq)
+{
+    int n_bypass = 0;
+    while (n_bypass < 8 && (raw >> (n_bypass * kLaneBypassBits)) != 0) ++n_bypass;
+    for (int j = n_bypass - 1; j >= 0; --j) lane_put<kWrite>(x, ptr, count, (raw >> (j * kLaneBypassBits)) & kLaneMaxBypass, 1, kLaneBypassBits);
+    // count nibbles forward: 15 while the remainder >= 15, then the remainder
+    int full = 0, v = n_bypass;
+    while (v >= (int)kLaneMaxBypass) { ++full; v -= kLaneMaxBypass; }
+    lane_put<kWrite>(x, ptr, count, (uint32_t)v, 1, kLaneBypassBits);
+    for (int j = 0; j < full; ++j) lane_put<kWrite>(x, ptr, count, kLaneMaxBypass, 1, kLaneBypassBits);
+    lane_put<kWrite>(x, ptr, count, start, freq, kLanePrecision);
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(32) rans_lane_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t n, int S,
+                                                              LaneTables T, uint32_t *__restrict__ states, uint32_t *__restrict__ words,
+                                                              const uint32_t *__restrict__ lane_off, uint8_t *__restrict__ out, size_t cap,
+                                                              int *__restrict__ status)
+{
+    const int b = blockIdx.y, lane = blockIdx.x * 32 + threadIdx.x;
+    if (lane >= S) return;
+    const int32_t *sym = symbols + (int64_t)b * n, *idx = indexes + (int64_t)b * n;
+    const int64_t steps = lane < n ? (n - lane + S - 1) / S : 0;
+    uint32_t x = kLaneL, count = 0;
+    uint16_t *ptr = nullptr;
+    if (kWrite) {
+        if (*status != LANE_OK) return;
+        const size_t payload = 16 + (size_t)8 * S;
+        ptr = reinterpret_cast<uint16_t *>(out + (size_t)b * cap + payload) + lane_off[(size_t)b * S + lane] + words[(size_t)b * S + lane];
+    }
+    int bad = 0;
+    for (int64_t hi = steps; hi > 0; hi -= kLaneChunk) {
+        const int m = hi < kLaneChunk ? (int)hi : kLaneChunk;
+        // ---- off the chain: symbols, indexes and CDF entries of the chunk (position hi - 1 - k, k = 0 .. m - 1) ----
+        int32_t sv[kLaneChunk], iv[kLaneChunk];
+#pragma unroll
+        for (int k = 0; k < kLaneChunk; ++k) {
+            const int64_t i = (int64_t)lane + (hi - 1 - k) * S;
+            sv[k] = k < m ? __ldg(sym + i) : 0;
+            iv[k] = k < m ? __ldg(idx + i) : 0;
+        }
+        uint32_t tok[kLaneChunk], raw[kLaneChunk];      // tok = start << 16 | (freq - 1); bit k of esc: symbol k is escaped (raw bits in raw[k])
+        uint32_t esc = 0;
+#pragma unroll
+        for (int k = 0; k < kLaneChunk; ++k) {
+            tok[k] = 0; raw[k] = 0;
+            if (k < m) {
+                const int32_t ix = iv[k];
+                if (ix < 0 || ix >= T.n_cdfs) { bad |= LANE_BAD_INDEX; continue; }
+                const int32_t max_value = __ldg(T.sizes + ix) - 2;
+                if (max_value < 0 || max_value + 2 > T.stride) { bad |= LANE_BAD_CDF; continue; }
+                int32_t value = sv[k] - __ldg(T.offsets + ix);
+                if (value < 0) { raw[k] = (uint32_t)(-2 * (int64_t)value - 1); value = max_value; esc |= 1u << k; }
+                else if (value >= max_value) { raw[k] = (uint32_t)(2 * ((int64_t)value - max_value)); value = max_value; esc |= 1u << k; }
+                const int32_t *row = T.cdfs + (size_t)ix * T.stride;
+                const int32_t c0 = __ldg(row + value), c1 = __ldg(row + value + 1);
+                if (c1 <= c0 || c1 - c0 > (1 << kLanePrecision) || c0 < 0) { bad |= LANE_BAD_CDF; continue; }
+                tok[k] = ((uint32_t)c0 << 16) | (uint32_t)(c1 - c0 - 1);
+            }
+        }
+        // ---- on the chain ----
+#pragma unroll
+        for (int k = 0; k < kLaneChunk; ++k) {
+            if (k >= m || bad) continue;
+            const uint32_t start = tok[k] >> 16, freq = (tok[k] & 0xffffu) + 1;
+            if ((esc >> k) & 1u) lane_put_escape<kWrite>(x, ptr, count, raw[k], start, freq);
+            else lane_put<kWrite>(x, ptr, count, start, freq, kLanePrecision);
+        }
+    }
+    if (bad) atomicOr(status, bad);
+    if (!kWrite) {
+        states[(size_t)b * S + lane] = x;
+        words[(size_t)b * S + lane] = count;
+    }
+}
+
+// one CTA per image: exclusive scan of the lane word counts, header, total size
+__global__ void __launch_bounds__(256) rans_lane_header_kernel(int64_t n, int S, const uint32_t *__restrict__ states, const uint32_t *__restrict__ words,
+                                                               uint32_t *__restrict__ lane_off, uint8_t *__restrict__ out, size_t cap,
+                                                               uint64_t *__restrict__ nbytes, int *__restrict__ status)
+{
+    __shared__ uint32_t s_off[kMaxLanes + 1];
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int l = 0; l < S; ++l) { s_off[l] = acc; acc += words[(size_t)b * S + l]; }
+        s_off[S] = acc;
+    }
+    __syncthreads();
+    const size_t total = (16 + (size_t)8 * S + (size_t)2 * s_off[S] + 3) & ~(size_t)3;
+    if (threadIdx.x == 0) {
+        nbytes[b] = total;
+        if (total > cap) atomicOr(status, LANE_CAPACITY);
+    }
+    if (total > cap) return;
+    uint32_t *hdr = reinterpret_cast<uint32_t *>(out + (size_t)b * cap);
+    if (threadIdx.x == 0) { hdr[0] = kLaneMagic; hdr[1] = (uint32_t)n; hdr[2] = (uint32_t)S; hdr[3] = 0; }
+    for (int l = threadIdx.x; l < S; l += blockDim.x) {
+        hdr[4 + l] = states[(size_t)b * S + l];
+        hdr[4 + S + l] = words[(size_t)b * S + l];
+        lane_off[(size_t)b * S + l] = s_off[l];
+    }
+    // zero the padding half-word
+    if (threadIdx.x == 0 && (s_off[S] & 1)) reinterpret_cast<uint16_t *>(out + (size_t)b * cap + 16 + (size_t)8 * S)[s_off[S]] = 0;
+}
+
+__device__ __forceinline__ uint32_t lane_get_bits(uint32_t &x, const uint16_t *&ptr, const uint16_t *end, bool &ok)
+{
+    const uint32_t val = x & kLaneMaxBypass;
+    x >>= kLaneBypassBits;
+    if (x < kLaneL) {
+        if (ptr >= end) { ok = false; return val; }
+        x = (x << 16) | *ptr++;
+    }
+    return val;
+}
+
+__global__ void __launch_bounds__(32) rans_lane_decode_kernel(const uint8_t *__restrict__ streams, const uint64_t *__restrict__ stream_off,
+                                                              const uint64_t *__restrict__ stream_bytes, const int32_t *__restrict__ indexes,
+                                                              int64_t n, LaneTables T, int32_t *__restrict__ out, int *__restrict__ status)
+{
+    const int b = blockIdx.y, lane = blockIdx.x * 32 + threadIdx.x;
+    const uint8_t *s = streams + stream_off[b];
+    const uint64_t len = stream_bytes[b];
+    if (len < 16) { if (lane == 0) atomicOr(status, LANE_BAD_STREAM); return; }
+    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(s);
+    const int S = (int)hdr[2];
+    if (hdr[0] != kLaneMagic || hdr[1] != (uint32_t)n || S < 1 || S > kMaxLanes || len < 16 + (uint64_t)8 * S) {
+        if (lane == 0) atomicOr(status, LANE_BAD_STREAM);
+        return;
+    }
+    if (lane >= S) return;
+    uint64_t off = 0, all = 0;
+    for (int l = 0; l < S; ++l) {
+        const uint32_t w = hdr[4 + S + l];
+        if (l < lane) off += w;
+        all += w;
+    }
+    if (16 + (uint64_t)8 * S + 2 * all > len) { atomicOr(status, LANE_BAD_STREAM); return; }
+    const uint16_t *ptr = reinterpret_cast<const uint16_t *>(s + 16 + (size_t)8 * S) + off;
+    const uint16_t *end = ptr + hdr[4 + S + lane];
+    uint32_t x = hdr[4 + lane];
+    const int32_t *idx = indexes + (int64_t)b * n;
+    int32_t *o = out + (int64_t)b * n;
+    const int64_t steps = lane < n ? (n - lane + S - 1) / S : 0;
+    bool ok = true;
+    for (int64_t lo = 0; lo < steps && ok; lo += kLaneChunk) {
+        const int m = steps - lo < kLaneChunk ? (int)(steps - lo) : kLaneChunk;
+        int32_t iv[kLaneChunk];
+#pragma unroll
+        for (int k = 0; k < kLaneChunk; ++k) iv[k] = k < m ? __ldg(idx + (int64_t)lane + (lo + k) * S) : 0;
+#pragma unroll 1
+        for (int k = 0; k < m && ok; ++k) {
+            const int32_t ix = iv[k];
+            if (ix < 0 || ix >= T.n_cdfs) { atomicOr(status, LANE_BAD_INDEX); ok = false; break; }
+            const int32_t *row = T.cdfs + (size_t)ix * T.stride;
+            const int32_t lenr = __ldg(T.sizes + ix), max_value = lenr - 2;
+            if (max_value < 0 || lenr > T.stride) { atomicOr(status, LANE_BAD_CDF); ok = false; break; }
+            const uint32_t cum = x & 0xffffu;
+            // largest s with row[s] <= cum: binary search over the increasing row
+            int lo_s = 0, hi_s = lenr - 1;
+            if (__ldg(row) > (int32_t)cum) { ok = false; break; }
+            while (hi_s - lo_s > 1) {
+                const int mid = (lo_s + hi_s) >> 1;
+                if (__ldg(row + mid) <= (int32_t)cum) lo_s = mid; else hi_s = mid;
+            }
+            int32_t sidx = lo_s;
+            if (sidx > max_value) { ok = false; break; }
+            const uint32_t start = (uint32_t)__ldg(row + sidx), freq = (uint32_t)__ldg(row + sidx + 1) - start;
+            x = freq * (x >> kLanePrecision) + cum - start;
+            if (x < kLaneL) {
+                if (ptr >= end) { ok = false; break; }
+                x = (x << 16) | *ptr++;
+            }
+            int32_t value = sidx;
+            if (value == max_value) {
+                int32_t val = (int32_t)lane_get_bits(x, ptr, end, ok);
+                int32_t n_bypass = val;
+                while (ok && val == (int32_t)kLaneMaxBypass) {
+                    val = (int32_t)lane_get_bits(x, ptr, end, ok);
+                    n_bypass += val;
+                }
+                if (n_bypass > 8) { ok = false; break; }
+                uint32_t raw = 0;
+                for (int j = 0; j < n_bypass && ok; ++j) raw |= lane_get_bits(x, ptr, end, ok) << (j * kLaneBypassBits);
+                value = (int32_t)(raw >> 1);
+                if (raw & 1) value = -value - 1;
+                else value += max_value;
+            }
+            o[(int64_t)lane + (lo + k) * S] = value + __ldg(T.offsets + ix);
+        }
+    }
+    if (!ok || ptr != end || x != kLaneL) atomicOr(status, LANE_BAD_STREAM);
+}
+
+static int lanes_for(int64_t n)
+{
+    int s = 4;
+    while (s < 256 && (int64_t)s * 2 * 8192 <= n) s *= 2;
+    return s;
+}
+
+}  // namespace mmc
+
+using namespace mmc;
+
+extern "C" {
+
+int mmc_rans_lanes_default(int64_t n) { return lanes_for(n); }
+
+int mmc_rans_device_workspace(int batch, int lanes, size_t *bytes)
+{
+    MMC_CHECK_ARG(batch >= 0 && lanes >= 1 && lanes <= kMaxLanes && bytes, "mmc_rans_device_workspace: bad argument");
+    // states, words, lane offsets (u32 each) + status (int, 16-byte slot)
+    *bytes = (size_t)3 * 4 * (size_t)batch * lanes + 16;
+    return MMC_OK;
+}
+
+int mmc_rans_encode_device(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n, const int32_t *cdfs, int n_cdfs,
+                           int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets, int lanes, uint8_t *out,
+                           size_t cap_per_stream, uint64_t *nbytes, void *workspace, int *status, void *stream)
+{
+    const char *name = "mmc_rans_encode_device";
+    MMC_CHECK_ARG(batch >= 0 && n >= 0 && n < (1ll << 32) && lanes >= 1 && lanes <= kMaxLanes, "%s: bad argument (lanes in [1, %d])", name, kMaxLanes);
+    MMC_CHECK_ARG(n_cdfs >= 1 && cdf_stride >= 2, "%s: bad CDF table", name);
+    MMC_CHECK_ARG(cap_per_stream % 4 == 0 && cap_per_stream >= 16 + (size_t)8 * lanes, "%s: capacity must be a multiple of 4 and hold the header", name);
+    if (batch == 0) return MMC_OK;
+    MMC_CHECK_ARG(symbols && indexes && cdfs && cdf_sizes && offsets && out && nbytes && workspace && status, "%s: NULL buffer", name);
+    MMC_CHECK_ARG(batch <= 65535, "%s: batch <= 65535", name);
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *states = (uint32_t *)workspace, *words = states + (size_t)batch * lanes, *lane_off = words + (size_t)batch * lanes;
+    LaneTables T{cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets};
+    MMC_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+    const dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)batch);
+    rans_lane_encode_kernel<false><<<grid, 32, 0, st>>>(symbols, indexes, n, lanes, T, states, words, lane_off, out, cap_per_stream, status);
+    MMC_CHECK_LAUNCH(name);
+    rans_lane_header_kernel<<<batch, 256, 0, st>>>(n, lanes, states, words, lane_off, out, cap_per_stream, nbytes, status);
+    MMC_CHECK_LAUNCH(name);
+    rans_lane_encode_kernel<true><<<grid, 32, 0, st>>>(symbols, indexes, n, lanes, T, states, words, lane_off, out, cap_per_stream, status);
+    MMC_CHECK_LAUNCH(name);
+    return MMC_OK;
+}
+
+int mmc_rans_decode_device(const uint8_t *streams, const uint64_t *stream_offsets, const uint64_t *stream_bytes, const int32_t *indexes,
+                           int batch, int64_t n, int max_lanes, const int32_t *cdfs, int n_cdfs, int cdf_stride, const int32_t *cdf_sizes,
+                           const int32_t *offsets, int32_t *symbols_out, int *status, void *stream)
+{
+    const char *name = "mmc_rans_decode_device";
+    MMC_CHECK_ARG(batch >= 0 && n >= 0 && n < (1ll << 32) && max_lanes >= 1 && max_lanes <= kMaxLanes, "%s: bad argument", name);
+    MMC_CHECK_ARG(n_cdfs >= 1 && cdf_stride >= 2, "%s: bad CDF table", name);
+    if (batch == 0) return MMC_OK;
+    MMC_CHECK_ARG(streams && stream_offsets && stream_bytes && indexes && cdfs && cdf_sizes && offsets && symbols_out && status, "%s: NULL buffer", name);
+    MMC_CHECK_ARG(batch <= 65535, "%s: batch <= 65535", name);
+    cudaStream_t st = (cudaStream_t)stream;
+    LaneTables T{cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets};
+    MMC_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+    const dim3 grid((unsigned)((max_lanes + 31) / 32), (unsigned)batch);
+    rans_lane_decode_kernel<<<grid, 32, 0, st>>>(streams, stream_offsets, stream_bytes, indexes, n, T, symbols_out, status);
+    MMC_CHECK_LAUNCH(name);
+    return MMC_OK;
+}
+
+}  // extern "C"

@@ -24,7 +24,7 @@ from ._lib import MmcodecError, build  # noqa: F401
 from .entropy_models import EntropyBottleneck, EntropyModel, GaussianConditional  # noqa: F401
 from .layers import GDN, LowerBound, NonNegativeParametrizer, conv, deconv  # noqa: F401
 from .models import (CompressionModel, FactorizedPrior, MeanScaleHyperprior, ScaleHyperprior,  # noqa: F401
-                     build_model, get_scale_table)
+                     build_model, get_scale_table, set_entropy_coder)
 
 from .models_mm import (ESA, Guided_compresser, JointAutoregressiveHierarchicalPriors, JointAutoregressiveHierarchicalPriors_D,  # noqa: F401
                         JointAutoregressiveHierarchicalPriors_R, MaskedConv2d)

@@ -6,6 +6,8 @@ compress() is two stages with different owners: the transforms, quantisation and
 in a loop they run back to back; here ``submit(x)`` enqueues the GPU stage, stages the int32 symbols / indexes into one of
 ``depth`` sets of pinned host buffers and hands them to a coding worker, so the next ``submit`` can start its kernels while the
 previous batch is being coded (the C coder releases the GIL).  The byte strings are those of ``net.compress(x)``.
+With the device coder selected (``mmcodec.set_entropy_coder(net, "ans-lanes")``) the symbols never leave the GPU: the coding kernels
+follow the transforms on the same stream and only the containers are copied back; the worker just slices the staged bytes.
 
     pipe = mmcodec.CompressPipeline(net)
     futures = [pipe.submit(x) for x in batches]          # at most `depth` batches in flight: submit blocks on the oldest
@@ -54,18 +56,33 @@ class CompressPipeline:
         with torch.no_grad():
             c = self.net.symbols_and_indexes(x)
         names = [k for k in ("y", "z") if f"{k}_symbols" in c]
-        staged = {k: (self._stage(bufs, k + "s", c[f"{k}_symbols"]), self._stage(bufs, k + "i", c[f"{k}_indexes"])) for k in names}
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(x.device))
         net = self.net
 
         def tabs(em):
             return em._quantized_cdf, em._cdf_length, em._offset
         # hyperprior models: y is coded with the Gaussian conditional's tables, z with the bottleneck's; factorized: y with the bottleneck's
-        tables = {"y": tabs(net.gaussian_conditional if "z" in names else net.entropy_bottleneck)}
+        models = {"y": net.gaussian_conditional if "z" in names else net.entropy_bottleneck}
         if "z" in names:
-            tables["z"] = tabs(net.entropy_bottleneck)
+            models["z"] = net.entropy_bottleneck
+        tables = {k: tabs(m) for k, m in models.items()}
         shape = c.get("shape")
+        if all(m._coder() == "ans-lanes" for m in models.values()):
+            # device coder: the symbols stay on the GPU; only the containers (and their sizes) travel, staged in this set's pinned buffers
+            pinned = bufs.setdefault("lane", {})
+            handles = [ops.rans_encode_device_launch(c[f"{k}_symbols"], c[f"{k}_indexes"], *tables[k], pinned=pinned) for k in names]
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(x.device))
+
+            def collect():
+                ev.synchronize()
+                return {"strings": [h.collect() for h in handles], "shape": shape}
+
+            fut = self._pool.submit(collect)
+            self._inflight.append(fut)
+            return fut
+        staged = {k: (self._stage(bufs, k + "s", c[f"{k}_symbols"]), self._stage(bufs, k + "i", c[f"{k}_indexes"])) for k in names}
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(x.device))
 
         def code():
             ev.synchronize()

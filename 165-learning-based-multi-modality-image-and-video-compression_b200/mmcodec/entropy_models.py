@@ -131,10 +131,30 @@ class EntropyModel(nn.Module):
 
     def compress(self, inputs, indexes, means=None):
         """entropy_models.py:237-270: one rANS stream per image, byte-identical to the reference coder."""
-        if self.entropy_coder_name != "ans":
-            raise NotImplementedError(f'entropy coder "{self.entropy_coder_name}" is not available; libmmcodec implements "ans"')
         symbols, indexes = self.symbols_and_indexes(inputs, indexes, means)
+        return self.encode_symbols(symbols, indexes)
+
+    # Entropy coders: "ans" = the reference's stream (compressai.ans, one serial rANS chain per image; coded on host threads,
+    # byte-identical); "ans-lanes" = the same symbols / tables / escape scheme in libmmcodec's own lane container, coded ON THE
+    # DEVICE (csrc/rans_device.cu) -- not readable by the reference, chosen explicitly: EntropyModel(entropy_coder="ans-lanes") or
+    # mmcodec.set_entropy_coder(net, "ans-lanes").
+    CODERS = ("ans", "ans-lanes")
+
+    def _coder(self) -> str:
+        if self.entropy_coder_name not in self.CODERS:
+            raise NotImplementedError(f'entropy coder "{self.entropy_coder_name}" is not available; libmmcodec implements {self.CODERS}')
+        return self.entropy_coder_name
+
+    def encode_symbols(self, symbols, indexes):
+        """int32 symbols / indexes (B, ...) -> list of B byte strings with this model's tables and coder."""
+        if self._coder() == "ans-lanes":
+            return ops.rans_encode_device(symbols, indexes, self._quantized_cdf, self._cdf_length, self._offset)
         return ops.rans_encode(symbols, indexes, self._quantized_cdf, self._cdf_length, self._offset)
+
+    def decode_symbols(self, strings, indexes):
+        if self._coder() == "ans-lanes":
+            return ops.rans_decode_device(list(strings), indexes.int(), self._quantized_cdf, self._cdf_length, self._offset)
+        return ops.rans_decode(list(strings), indexes.int(), self._quantized_cdf, self._cdf_length, self._offset)
 
     def decompress(self, strings, indexes, dtype: torch.dtype = torch.float, means: Tensor = None):
         """entropy_models.py:272-327"""
@@ -154,7 +174,7 @@ class EntropyModel(nn.Module):
                 for i in range(2, len(indexes.size())):
                     if means.size(i) != 1:
                         raise ValueError("Invalid means parameters")
-        symbols = ops.rans_decode(list(strings), indexes.int(), self._quantized_cdf, self._cdf_length, self._offset)
+        symbols = self.decode_symbols(strings, indexes)
         return self.dequantize(symbols, means, dtype)
 
 

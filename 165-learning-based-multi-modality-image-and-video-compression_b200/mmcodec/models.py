@@ -22,7 +22,7 @@ from .layers import GDN, conv, deconv
 from .transforms import TransformStack, current_precision, run_layers
 
 __all__ = ["CompressionModel", "FactorizedPrior", "ScaleHyperprior", "MeanScaleHyperprior", "get_scale_table",
-           "SCALES_MIN", "SCALES_MAX", "SCALES_LEVELS", "MODELS", "CFGS", "build_model"]
+           "SCALES_MIN", "SCALES_MAX", "SCALES_LEVELS", "MODELS", "CFGS", "build_model", "set_entropy_coder"]
 
 SCALES_MIN = 0.11
 SCALES_MAX = 256
@@ -295,10 +295,11 @@ class ScaleHyperprior(CompressionModel):
         return em._quantized_cdf, em._cdf_length, em._offset
 
     def compress(self, x):
-        """models/google.py:324-332 (mean-scale: :393-404): symbols / indexes on the GPU, rANS streams on the host."""
+        """models/google.py:324-332 (mean-scale: :393-404): symbols / indexes on the GPU; rANS streams on the host ("ans", the
+        reference's byte-identical stream) or on the device ("ans-lanes", see EntropyModel.CODERS / set_entropy_coder)."""
         c = self.symbols_and_indexes(x)
-        y_strings = ops.rans_encode(c["y_symbols"], c["y_indexes"], *self._coder_tables(self.gaussian_conditional))
-        z_strings = ops.rans_encode(c["z_symbols"], c["z_indexes"], *self._coder_tables(self.entropy_bottleneck))
+        y_strings = self.gaussian_conditional.encode_symbols(c["y_symbols"], c["y_indexes"])
+        z_strings = self.entropy_bottleneck.encode_symbols(c["z_symbols"], c["z_indexes"])
         return {"strings": [y_strings, z_strings], "shape": c["shape"]}
 
     def _synthesis_from(self, y_hat):
@@ -379,6 +380,18 @@ CFGS = {
     "bmshj2018-hyperprior": {q: ((128, 192) if q <= 5 else (192, 320)) for q in range(1, 9)},
     "mbt2018-mean": {q: ((128, 192) if q <= 4 else (192, 320)) for q in range(1, 9)},
 }
+
+
+def set_entropy_coder(net: nn.Module, name: str) -> nn.Module:
+    """Select the entropy coder of every entropy model of ``net``: "ans" (reference-compatible streams, host threads) or
+    "ans-lanes" (libmmcodec's lane container, coded on the device).  compress() and decompress() must use the same coder."""
+    from .entropy_models import EntropyModel
+    if name not in EntropyModel.CODERS:
+        raise ValueError(f'Invalid entropy coder "{name}" (available: {EntropyModel.CODERS})')
+    for m in net.modules():
+        if isinstance(m, EntropyModel):
+            m.entropy_coder_name = name
+    return net
 
 
 def build_model(architecture: str, quality: int, channel: int = 3, **kwargs):

@@ -385,6 +385,139 @@ def rans_decode(strings, indexes: Tensor, cdf: Tensor, cdf_lengths: Tensor, offs
     return res.to(indexes.device) if isinstance(indexes, torch.Tensor) else res
 
 
+# ---- device coder (csrc/rans_device.cu): the "lane container", symbols never leave the GPU --------------------------
+LANE_MAGIC = b"MMCL"
+_LANE_STATUS = {1: "an index is outside the CDF table", 2: "a CDF row is not strictly increasing within 2^16", 4: "output capacity too small",
+                8: "stream is malformed, truncated or does not match the CDF tables"}
+
+
+def _lane_status_error(name: str, st: int):
+    msg = "; ".join(v for k, v in _LANE_STATUS.items() if st & k) or f"status {st}"
+    return ValueError(f"{name}: {msg}")
+
+
+def _i32dev(t: Tensor, device) -> Tensor:
+    t = t.detach()
+    if t.device != device:
+        t = t.to(device)
+    return (t if t.dtype == torch.int32 else t.int()).contiguous()
+
+
+def rans_lanes_default(n: int) -> int:
+    return int(L.lib().mmc_rans_lanes_default(int(n)))
+
+
+class LaneEncodeHandle:
+    """An enqueued device encode: the containers sit in ``out`` (uint8 [B][cap], device), their sizes and the status word in ``meta``;
+    the first ``head`` bytes of every row and ``meta`` are on their way to pinned host buffers on the launching stream.
+    ``collect()`` (after that stream -- or an event recorded on it -- has been waited for) returns the B byte strings."""
+
+    def __init__(self, args, out, meta, out_h, meta_h, B, head):
+        self.args, self.out, self.meta, self.out_h, self.meta_h, self.B, self.head = args, out, meta, out_h, meta_h, B, head
+
+    def collect(self):
+        B = self.B
+        st = int(self.meta_h[B + 1].item()) & 0xffffffff
+        if st == 4 and B:
+            # capacity too small (escape-heavy data): re-run blocking with the exact size the header pass reported
+            return rans_encode_device(*self.args, cap=(int(self.meta_h[:B].max().item()) + 3) & ~3)
+        if st:
+            raise _lane_status_error("rans_encode_device", st)
+        sizes = [int(v) for v in self.meta_h[:B].tolist()]
+        host = self.out_h.numpy()
+        res = []
+        for b, nb in enumerate(sizes):
+            if nb <= self.head:
+                res.append(host[b, :nb].tobytes())
+            else:       # longer than the staged head: fetch the row's tail (synchronous, rare)
+                res.append(self.out[b, :nb].cpu().numpy().tobytes())
+        return res
+
+
+_lane_pinned = __import__("threading").local()
+
+
+def rans_encode_device_launch(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_lengths: Tensor, offsets: Tensor,
+                              lanes: Optional[int] = None, cap: Optional[int] = None, pinned: Optional[dict] = None) -> LaneEncodeHandle:
+    """Enqueue the device encode of a batch and the device->host copies of its result on the current stream; no synchronisation.
+    ``pinned``: a dict the caller owns for the staging buffers (one per in-flight batch); default: a per-thread cache."""
+    _require_cuda(symbols, indexes)
+    dev = symbols.device
+    sym, idx = _i32dev(symbols, dev), _i32dev(indexes, dev)
+    if sym.shape != idx.shape:
+        raise ValueError("rans_encode_device: symbols / indexes shape mismatch")
+    B = sym.shape[0]
+    n = sym[0].numel() if B else 0
+    tab, lens, offs = _i32dev(cdf, dev), _i32dev(cdf_lengths, dev).reshape(-1), _i32dev(offsets, dev).reshape(-1)
+    S = int(lanes) if lanes is not None else rans_lanes_default(n)
+    nb = ctypes.c_size_t()
+    L.check(L.lib().mmc_rans_device_workspace(B, S, ctypes.byref(nb)))
+    ws = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=dev)
+    meta = torch.zeros(B + 2, dtype=torch.int64, device=dev)          # nbytes[B], pad, status (int32 in the last slot)
+    if cap is None:
+        cap = (16 + 8 * S + 2 * n + 64 + 3) & ~3                         # one word per symbol: enough unless escapes dominate
+    out = torch.empty((max(B, 1), cap), dtype=torch.uint8, device=dev)
+    with _Timed("rans_encode|coder"):
+        L.check(L.lib().mmc_rans_encode_device(_ptr(sym), _ptr(idx), B, n, _ptr(tab), tab.shape[0], tab.shape[1], _ptr(lens), _ptr(offs), S,
+                                               _ptr(out), cap, _ptr(meta), _ptr(ws), _ptr(meta[B + 1:]), _stream()))
+    # stage the result: sizes + status, and the head of every container (2 bits per symbol covers typical rates; longer rows are
+    # fetched in collect())
+    head = min(cap, (16 + 8 * S + n // 4 + 1024 + 3) & ~3)
+    if pinned is None:
+        pinned = getattr(_lane_pinned, "bufs", None)
+        if pinned is None:
+            pinned = _lane_pinned.bufs = {}
+    key = ("lane", id(cdf) if not isinstance(cdf, torch.Tensor) else cdf.data_ptr())
+    buf = pinned.get(key)
+    if buf is None or buf[0].shape[0] < max(B, 1) or buf[0].shape[1] < head or buf[1].numel() < B + 2:
+        buf = pinned[key] = (torch.empty((max(B, 1), head), dtype=torch.uint8).pin_memory(), torch.empty(B + 2, dtype=torch.int64).pin_memory())
+    out_h, meta_h = buf[0][: max(B, 1), :head], buf[1][: B + 2]
+    out_h.copy_(out[:, :head], non_blocking=True)
+    meta_h.copy_(meta, non_blocking=True)
+    return LaneEncodeHandle((symbols, indexes, cdf, cdf_lengths, offsets, lanes), out, meta, out_h, meta_h, B, head)
+
+
+def rans_encode_device(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf_lengths: Tensor, offsets: Tensor, lanes: Optional[int] = None,
+                       cap: Optional[int] = None):
+    """Entropy-code every image of a batch ON THE DEVICE into lane containers (see csrc/rans_device.cu): same symbols, CDF tables,
+    indexes and escape scheme as ``rans_encode``, a different (not reference-compatible) container.  symbols / indexes: (B, ...)
+    CUDA tensors.  Returns a list of B byte strings (blocking; ``rans_encode_device_launch`` is the asynchronous form)."""
+    h = rans_encode_device_launch(symbols, indexes, cdf, cdf_lengths, offsets, lanes, cap)
+    torch.cuda.current_stream().synchronize()
+    return h.collect()
+
+
+def rans_decode_device(strings, indexes: Tensor, cdf: Tensor, cdf_lengths: Tensor, offsets: Tensor) -> Tensor:
+    """Decode lane containers produced by ``rans_encode_device``; returns int32 symbols shaped like ``indexes`` on its device."""
+    _require_cuda(indexes)
+    dev = indexes.device
+    idx = _i32dev(indexes, dev)
+    B = idx.shape[0]
+    if len(strings) != B:
+        raise ValueError("rans_decode_device: one stream per image expected")
+    n = idx[0].numel() if B else 0
+    max_lanes = 1
+    for s_ in strings:
+        if len(s_) < 16 or len(s_) % 4 or s_[:4] != LANE_MAGIC:
+            raise ValueError("rans_decode_device: not a lane container (these streams come from the host / reference coder?)")
+        max_lanes = max(max_lanes, int.from_bytes(s_[8:12], "little"))
+    if max_lanes > 1024:
+        raise ValueError("rans_decode_device: malformed header (lane count)")
+    tab, lens, offs = _i32dev(cdf, dev), _i32dev(cdf_lengths, dev).reshape(-1), _i32dev(offsets, dev).reshape(-1)
+    sizes = np.array([len(s_) for s_ in strings], dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64) if B else np.zeros(0, np.int64)
+    blob = torch.from_numpy(np.frombuffer(b"".join(strings), dtype=np.uint8).copy() if B else np.zeros(4, np.uint8)).to(dev)
+    meta = torch.from_numpy(np.concatenate([starts, sizes, [0]]).astype(np.int64)).to(dev)
+    out = torch.empty(idx.shape, dtype=torch.int32, device=dev)
+    with _Timed("rans_decode|coder"):
+        L.check(L.lib().mmc_rans_decode_device(_ptr(blob), _ptr(meta), _ptr(meta[B:]), _ptr(idx), B, n, max_lanes, _ptr(tab), tab.shape[0], tab.shape[1],
+                                               _ptr(lens), _ptr(offs), _ptr(out), _ptr(meta[2 * B:]), _stream()))
+    st = int(meta[2 * B].item()) & 0xffffffff
+    if st:
+        raise _lane_status_error("rans_decode_device", st)
+    return out
+
+
 # ---- GDN -----------------------------------------------------------------------------------------
 def gdn_reparam(beta: Tensor, gamma: Tensor, beta_bound: float, gamma_bound: float, pedestal: float,
                 want_bf16: bool = False):

@@ -597,7 +597,7 @@ def main():
         #      micro-batches overlap.  Headline e2e = what the reference's evaluation loop keeps of a forward (per-image bpp and
         #      MSE -> PSNR, eval_model/__main__t.py:151-173), reduced on the device inside the same CUDA graph and read back
         #      (8 bytes per image); `e2e_full_outputs` = the same call returning x_hat + likelihoods to pinned host memory. ----
-        e2e_full = e2e_u8 = None
+        e2e_full = e2e_u8 = device_coder_rec = None
         if call == "forward":
             def time_pipe(pipe, x_in=None):
                 x_in = x_host if x_in is None else x_in
@@ -677,6 +677,49 @@ def main():
                 torch.cuda.synchronize()
                 ms_e2e = (time.perf_counter() - t0) * 1e3
                 pipe.close()
+                # the same pipeline with the DEVICE coder (lane container, csrc/rans_device.cu): symbols never leave the GPU
+                host_strings = res["strings"]
+                mmcodec.set_entropy_coder(net, "ans-lanes")
+                try:
+                    pipe = mmcodec.CompressPipeline(net, depth=2)
+                    x_dev.copy_(x_host, non_blocking=True)
+                    first = pipe.submit(x_dev).result()
+                    hat_dev = net.decompress(first["strings"], first["shape"])["x_hat"]
+                    barrier()
+                    t0 = time.perf_counter()
+                    futs = []
+                    for _ in range(args.steps):
+                        x_dev.copy_(x_host, non_blocking=True)
+                        futs.append(pipe.submit(x_dev))
+                    res_dev = [f.result() for f in futs][-1]
+                    torch.cuda.synchronize()
+                    ms_dev = (time.perf_counter() - t0) * 1e3 / args.steps
+                    pipe.close()
+                    # coding kernels alone, event-timed on the launching stream (y and z of one batch)
+                    c_ = net.symbols_and_indexes(x_dev)
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    ev0.record()
+                    for _ in range(args.steps):
+                        hy = ops.rans_encode_device_launch(c_["y_symbols"], c_["y_indexes"], *net._coder_tables(net.gaussian_conditional))
+                        hz = ops.rans_encode_device_launch(c_["z_symbols"], c_["z_indexes"], *net._coder_tables(net.entropy_bottleneck))
+                    ev1.record()
+                    torch.cuda.synchronize()
+                    ms_code = ev0.elapsed_time(ev1) / args.steps
+                finally:
+                    mmcodec.set_entropy_coder(net, "ans")
+                hat_host = net.decompress(host_strings, res["shape"])["x_hat"]
+                if not torch.equal(hat_dev, hat_host):
+                    raise SystemExit("device-coder round trip differs from the host-coder round trip")
+                nb_host = sum(len(s_) for ss in host_strings for s_ in ss)
+                nb_dev = sum(len(s_) for ss in res_dev["strings"] for s_ in ss)
+                device_coder_rec = {"value": B * world / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev,
+                                    "coder_ms_per_step": ms_code, "bytes_per_step": nb_dev, "bytes_per_step_host_coder": nb_host,
+                                    "rate_overhead": nb_dev / nb_host - 1.0,
+                                    "lanes_y": ops.rans_lanes_default(c_["y_symbols"][0].numel()),
+                                    "round_trip": "decompress(x_hat) bit-identical to the host-coder round trip",
+                                    "api": 'mmcodec.set_entropy_coder(net, "ans-lanes"); mmcodec.CompressPipeline(net).submit(x) -> lane containers '
+                                           "(not reference-compatible; same symbols, tables and escape scheme)"}
             e2e_bpp = None
             d2h = (sum(v.numel() * 4 for v in res.values()) if call == "symbols"
                    else sum(len(s_) for ss in res["strings"] for s_ in ss) + 4 * B * (res["shape"][0] * res["shape"][1]) * 0)
@@ -783,6 +826,8 @@ def main():
         e2e_full["value"] = B * world / (e2e_full["ms_per_step"] * 1e-3)
         e2e_full["unit"] = UNIT
         line["e2e_full_outputs"] = e2e_full
+    if call == "compress" and device_coder_rec:
+        line["e2e_device_coder"] = device_coder_rec
     if call == "compress" and e2e_sync_ms:
         line["e2e_sync_compress"] = {"value": B * world / (e2e_sync_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_sync_ms,
                                      "api": "net.compress(x_pinned.to(device)) called in a loop (GPU stage and host coding back to back)"}

@@ -451,6 +451,31 @@ MMC_API int mmc_window_attention_bwd(const void *q, const void *kv, const float 
                                      int heads, int head_dim, int window, int shift, float scale, void *dq, void *dkv, float *dtable,
                                      void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Range-ANS coder on the device (csrc/rans_device.cu).  The reference's stream is one serial rANS
+ * chain per image (cpp_exts/rans/rans_interface.cpp:108-200) and stays on host threads (mmc_rans_encode_batch_host, byte-identical).
+ * These entry points code the SAME symbols against the SAME quantised CDF tables / indexes / escape scheme into a container of
+ * our own in which an image's symbols are dealt round-robin onto `lanes` independent 32-bit-state / 16-bit-word rANS lanes
+ * (layout in the file header; CPU restatement oracle/lane_rans.py), so symbols and indexes never leave the GPU.
+ * All pointers are DEVICE pointers; calls are asynchronous on `stream`.
+ *   symbols / indexes: int32 [batch][n] in the reference's flattening order; cdfs int32 [n_cdfs][cdf_stride], cdf_sizes / offsets
+ *   int32 [n_cdfs] (EntropyModel._quantized_cdf / _cdf_length / _offset, entropy_models.py:216-235).
+ *   out: [batch][cap_per_stream] bytes (cap % 4 == 0); nbytes[b] = container size (written even if it does not fit);
+ *   status: one int, 0 = ok, bit 0 index out of range, bit 1 bad CDF row, bit 2 capacity too small, bit 3 malformed stream.
+ *   workspace: mmc_rans_device_workspace bytes.  mmc_rans_lanes_default(n): lane count used when the caller has no preference
+ *   (a power of two in [4, 256], about one lane per 8192..16384 symbols: header overhead 8 bytes per lane).
+ * Decoding: streams = concatenated containers, stream_offsets[b] (multiples of 4) / stream_bytes[b] uint64; max_lanes >= the
+ * largest lane count in the batch; symbols_out int32 [batch][n]. */
+MMC_API int mmc_rans_lanes_default(int64_t n);
+MMC_API int mmc_rans_device_workspace(int batch, int lanes, size_t *bytes);
+MMC_API int mmc_rans_encode_device(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n, const int32_t *cdfs, int n_cdfs,
+                                   int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets, int lanes, uint8_t *out,
+                                   size_t cap_per_stream, uint64_t *nbytes, void *workspace, int *status, void *stream);
+MMC_API int mmc_rans_decode_device(const uint8_t *streams, const uint64_t *stream_offsets, const uint64_t *stream_bytes,
+                                   const int32_t *indexes, int batch, int64_t n, int max_lanes, const int32_t *cdfs, int n_cdfs,
+                                   int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets, int32_t *symbols_out, int *status,
+                                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

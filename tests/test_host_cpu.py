@@ -239,6 +239,38 @@ def test_rans_fast_path_exact_and_mixed_streams():
     assert len(strings[1]) > len(strings[0])
 
 
+def test_lane_container_oracle_round_trip_and_token_parity():
+    """oracle/lane_rans.py (the CPU restatement of the device coder's container, csrc/rans_device.cu): round trips for ragged
+    sizes / lane counts / escapes, carries exactly the symbols the reference-compatible host coder carries, and costs at most the
+    lane headers more than the reference's stream."""
+    from mmcodec import ops
+    from oracle import lane_rans
+    gc = mmcodec.GaussianConditional(None)
+    gc.update_scale_table(mmcodec.models.get_scale_table())
+    tabs = (gc._quantized_cdf, gc._cdf_length, gc._offset)
+    cdfs, sizes, offs = (t.numpy() for t in tabs)
+    g = torch.Generator().manual_seed(3)
+    for n, lanes in ((0, 4), (1, 4), (5, 8), (100, 1), (257, 7), (3000, 4), (3000, None)):
+        idx = torch.randint(0, 64, (1, n), generator=g, dtype=torch.int32)
+        scale = torch.tensor(mmcodec.models.get_scale_table())[idx.long()]
+        sym = torch.round(torch.randn(1, n, generator=g) * scale).to(torch.int32)
+        if n >= 5:
+            sym[0, ::4] = torch.randint(-70000, 70000, (len(sym[0, ::4]),), generator=g, dtype=torch.int32)     # escapes
+            sym[0, 1] = 2 ** 30
+            sym[0, 2] = -2 ** 30
+        stream = lane_rans.encode(sym[0].tolist(), idx[0].tolist(), cdfs, sizes, offs, lanes)
+        S = lanes if lanes is not None else lane_rans.lanes_default(n)
+        assert stream[:4] == b"MMCL" and len(stream) % 4 == 0
+        assert lane_rans.decode(stream, idx[0].tolist(), cdfs, sizes, offs) == sym[0].tolist()
+        host = ops.rans_encode(sym, idx, *tabs)
+        assert torch.equal(ops.rans_decode(host, idx, *tabs), sym)            # same symbols through the reference-compatible stream
+        # rate: the reference's stream + the lane headers (8 bytes per lane + 16) + at most one 16-bit word of slack per lane
+        assert len(stream) <= len(host[0]) + 16 + 10 * S + 4, (n, lanes, len(stream), len(host[0]))
+    assert lane_rans.lanes_default(295_000) == 32 and lane_rans.lanes_default(1_570_000) == 128 and lane_rans.lanes_default(10) == 4
+    with pytest.raises(ValueError):
+        lane_rans.decode(b"XXXX" + stream[4:], idx[0].tolist(), cdfs, sizes, offs)
+
+
 def _shard_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
