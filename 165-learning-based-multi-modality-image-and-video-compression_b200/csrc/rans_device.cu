@@ -17,10 +17,11 @@
 //       if (x >= ((2^16 >> bits) << 16) * freq) { emit low 16 bits of x; x >>= 16; }       x = ((x / freq) << bits) + x % freq + start
 // starting from x = 2^16; state[l] is the final x, payload words are stored in the order the decoder reads them (reverse of
 // emission).  The decoder starts from state[l] and per token does  slot = x & (2^bits - 1);  x = freq * (x >> bits) + slot - start;
-// if (x < 2^16) x = (x << 16) | next word.  A CPU restatement of exactly this text is oracle/lane_rans.py (tests compare bytes).
+// if (x < 2^16) x = (x << 16) | next word.  The tests hold a CPU restatement of exactly this text and compare bytes.
 //
 // Kernels: lanes are threads (32 lanes per warp read symbols / indexes coalesced); the per-lane chain is serial, so the loads of a
 // chunk of 32 steps (symbol, index -> CDF entry) are issued ahead of the chain and only the state arithmetic stays on it.
+//   table   rans_lane_table:         (start, freq, exact 64-bit reciprocal of freq) per CDF entry, so the chain has no division
 //   pass 1  rans_lane_encode<false>: final state and word count of every lane        (no stores)
 //   scan    rans_lane_header:        lane offsets, header, total size, capacity check  (one CTA per image)
 //   pass 2  rans_lane_encode<true>:  the same chain again, words written in place
@@ -57,9 +58,53 @@ __device__ __forceinline__ void lane_put(uint32_t &x, uint16_t *&ptr, uint32_t &
     x = (q << bits) + (x - q * freq) + start;
 }
 
+// One entry per (CDF row, value): what the chain needs for the 16-bit main token, prepared off the chain.
+//   tok = start << 16 | (freq - 1);  rcp = ceil(2^64 / freq) (0 for freq == 1): x / freq == umul64hi(x, rcp) EXACTLY for x < 2^32,
+//   freq <= 2^16 (the error of the product is < 2^-32, the fractional part of x / freq is <= 1 - 2^-16);  rcp == ~0: invalid row entry.
+struct __align__(16) LaneEntry {
+    uint32_t tok, pad;
+    uint64_t rcp;
+};
+constexpr uint64_t kLaneBadEntry = ~0ull;
+
+// the main token on the chain: ~12 dependent instructions (the plain version's 32-bit division alone is ~20)
+template <bool kWrite>
+__device__ __forceinline__ void lane_put_main(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t tok, uint64_t rcp)
+{
+    const uint32_t start = tok >> 16, freq = (tok & 0xffffu) + 1;
+    if ((x >> 16) >= freq) {                       // x >= freq << 16
+        if (kWrite) *--ptr = (uint16_t)(x & 0xffffu);
+        ++count;
+        x >>= 16;
+    }
+    const uint32_t q = rcp ? (uint32_t)__umul64hi((uint64_t)x, rcp) : x;
+    x = (q << kLanePrecision) + (x - q * freq) + start;
+}
+
+__global__ void __launch_bounds__(256) rans_lane_table_kernel(const int32_t *__restrict__ cdfs, const int32_t *__restrict__ sizes, int n_cdfs, int stride,
+                                                              LaneEntry *__restrict__ tab)
+{
+    const int64_t n = (int64_t)n_cdfs * stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(i / stride), v = (int)(i - (int64_t)row * stride);
+        LaneEntry e;
+        e.tok = 0; e.pad = 0; e.rcp = kLaneBadEntry;
+        const int len = sizes[row];
+        if (len >= 2 && len <= stride && v + 1 < len) {
+            const int32_t c0 = cdfs[i], c1 = cdfs[i + 1];
+            if (c0 >= 0 && c1 > c0 && c1 - c0 <= (1 << kLanePrecision) && c0 < (1 << kLanePrecision)) {
+                const uint32_t freq = (uint32_t)(c1 - c0);
+                e.tok = ((uint32_t)c0 << 16) | (freq - 1);
+                e.rcp = freq == 1 ? 0ull : (~0ull / freq) + 1;          // = ceil(2^64 / freq) for every freq >= 2
+            }
+        }
+        tab[i] = e;
+    }
+}
+
 // all tokens of an escaped symbol, last token first (the forward order is: main token, count nibbles, raw nibbles)
 template <bool kWrite>
-__device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t raw, uint32_t start, uint32_t freq)
+__device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t raw, uint32_t tok, uint64_t rcp)
 {
     int n_bypass = 0;
     while (n_bypass < 8 && (raw >> (n_bypass * kLaneBypassBits)) != 0) ++n_bypass;
@@ -69,14 +114,14 @@ __device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32
     while (v >= (int)kLaneMaxBypass) { ++full; v -= kLaneMaxBypass; }
     lane_put<kWrite>(x, ptr, count, (uint32_t)v, 1, kLaneBypassBits);
     for (int j = 0; j < full; ++j) lane_put<kWrite>(x, ptr, count, kLaneMaxBypass, 1, kLaneBypassBits);
-    lane_put<kWrite>(x, ptr, count, start, freq, kLanePrecision);
+    lane_put_main<kWrite>(x, ptr, count, tok, rcp);
 }
 
 template <bool kWrite>
 __global__ void __launch_bounds__(32) rans_lane_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t n, int S,
-                                                              LaneTables T, uint32_t *__restrict__ states, uint32_t *__restrict__ words,
-                                                              const uint32_t *__restrict__ lane_off, uint8_t *__restrict__ out, size_t cap,
-                                                              int *__restrict__ status)
+                                                              LaneTables T, const LaneEntry *__restrict__ tab, uint32_t *__restrict__ states,
+                                                              uint32_t *__restrict__ words, const uint32_t *__restrict__ lane_off,
+                                                              uint8_t *__restrict__ out, size_t cap, int *__restrict__ status)
 {
     const int b = blockIdx.y, lane = blockIdx.x * 32 + threadIdx.x;
     if (lane >= S) return;
@@ -112,7 +157,8 @@ __global__ void __launch_bounds__(32) rans_lane_encode_kernel(const int32_t *__r
             mv[k] = __ldg(T.sizes + ix) - 2;
             ov[k] = __ldg(T.offsets + ix);
         }
-        uint32_t tok[kLaneChunk], raw[kLaneChunk];      // tok = start << 16 | (freq - 1); bit k of esc: symbol k is escaped (raw bits in raw[k])
+        uint32_t tok[kLaneChunk], raw[kLaneChunk];      // bit k of esc: symbol k is escaped (raw bits in raw[k])
+        uint64_t rcp[kLaneChunk];
         uint32_t esc = 0;
 #pragma unroll
         for (int k = 0; k < kLaneChunk; ++k) {
@@ -123,20 +169,18 @@ __global__ void __launch_bounds__(32) rans_lane_encode_kernel(const int32_t *__r
             raw[k] = neg ? (uint32_t)(-2 * (int64_t)value - 1) : (over ? (uint32_t)(2 * ((int64_t)value - max_value)) : 0u);
             esc |= (neg || over) ? (1u << k) : 0u;
             value = (neg || over) ? max_value : value;
-            const int32_t *row = T.cdfs + (size_t)iv[k] * T.stride;
-            const int32_t c0 = __ldg(row + value), c1 = __ldg(row + value + 1);
-            const bool okc = c1 > c0 && c1 - c0 <= (1 << kLanePrecision) && c0 >= 0;
-            bad |= okc ? 0 : LANE_BAD_CDF;
-            tok[k] = okc ? (((uint32_t)c0 << 16) | (uint32_t)(c1 - c0 - 1)) : 0u;
+            const uint4 e = __ldg(reinterpret_cast<const uint4 *>(tab + (size_t)iv[k] * T.stride + value));      // one 16-byte load per symbol
+            tok[k] = e.x;
+            rcp[k] = ((uint64_t)e.w << 32) | e.z;
+            bad |= (rcp[k] == kLaneBadEntry) ? LANE_BAD_CDF : 0;
         }
         if (bad) break;
         // ---- on the chain ----
 #pragma unroll
         for (int k = 0; k < kLaneChunk; ++k) {
             if (k >= m) continue;
-            const uint32_t start = tok[k] >> 16, freq = (tok[k] & 0xffffu) + 1;
-            if ((esc >> k) & 1u) lane_put_escape<kWrite>(x, ptr, count, raw[k], start, freq);
-            else lane_put<kWrite>(x, ptr, count, start, freq, kLanePrecision);
+            if ((esc >> k) & 1u) lane_put_escape<kWrite>(x, ptr, count, raw[k], tok[k], rcp[k]);
+            else lane_put_main<kWrite>(x, ptr, count, tok[k], rcp[k]);
         }
     }
     if (bad) atomicOr(status, bad);
@@ -265,10 +309,12 @@ __global__ void __launch_bounds__(32) rans_lane_decode_kernel(const uint8_t *__r
     if (!ok || ptr != end || x != kLaneL) atomicOr(status, LANE_BAD_STREAM);
 }
 
+// Lane count: the smallest power of two that keeps a lane's chain at <= 8192 symbols, within [4, 1024] -- the chain length is the
+// coding time (two passes of ~0.1-0.2 us per symbol on one thread), the lane count the header overhead (8 bytes per lane).
 static int lanes_for(int64_t n)
 {
     int s = 4;
-    while (s < 256 && (int64_t)s * 2 * 8192 <= n) s *= 2;
+    while (s < kMaxLanes && (int64_t)s * 8192 < n) s *= 2;
     return s;
 }
 
@@ -280,11 +326,11 @@ extern "C" {
 
 int mmc_rans_lanes_default(int64_t n) { return lanes_for(n); }
 
-int mmc_rans_device_workspace(int batch, int lanes, size_t *bytes)
+int mmc_rans_device_workspace(int batch, int lanes, int n_cdfs, int cdf_stride, size_t *bytes)
 {
-    MMC_CHECK_ARG(batch >= 0 && lanes >= 1 && lanes <= kMaxLanes && bytes, "mmc_rans_device_workspace: bad argument");
-    // states, words, lane offsets (u32 each) + status (int, 16-byte slot)
-    *bytes = (size_t)3 * 4 * (size_t)batch * lanes + 16;
+    MMC_CHECK_ARG(batch >= 0 && lanes >= 1 && lanes <= kMaxLanes && n_cdfs >= 1 && cdf_stride >= 2 && bytes, "mmc_rans_device_workspace: bad argument");
+    // encoder table (16 bytes per CDF entry, rebuilt by every call: a few microseconds) + states, words, lane offsets (u32 each)
+    *bytes = (size_t)16 * n_cdfs * cdf_stride + (size_t)3 * 4 * (size_t)batch * lanes + 64;
     return MMC_OK;
 }
 
@@ -300,15 +346,19 @@ int mmc_rans_encode_device(const int32_t *symbols, const int32_t *indexes, int b
     MMC_CHECK_ARG((n == 0 || (symbols && indexes)) && cdfs && cdf_sizes && offsets && out && nbytes && workspace && status, "%s: NULL buffer", name);
     MMC_CHECK_ARG(batch <= 65535, "%s: batch <= 65535", name);
     cudaStream_t st = (cudaStream_t)stream;
-    uint32_t *states = (uint32_t *)workspace, *words = states + (size_t)batch * lanes, *lane_off = words + (size_t)batch * lanes;
+    MMC_CHECK_ARG(aligned16(workspace), "%s: workspace must be 16-byte aligned", name);
+    LaneEntry *tab = (LaneEntry *)workspace;
+    uint32_t *states = (uint32_t *)(tab + (size_t)n_cdfs * cdf_stride), *words = states + (size_t)batch * lanes, *lane_off = words + (size_t)batch * lanes;
     LaneTables T{cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets};
     MMC_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int), st));
+    rans_lane_table_kernel<<<elementwise_grid((int64_t)n_cdfs * cdf_stride, 256), 256, 0, st>>>(cdfs, cdf_sizes, n_cdfs, cdf_stride, tab);
+    MMC_CHECK_LAUNCH(name);
     const dim3 grid((unsigned)((lanes + 31) / 32), (unsigned)batch);
-    rans_lane_encode_kernel<false><<<grid, 32, 0, st>>>(symbols, indexes, n, lanes, T, states, words, lane_off, out, cap_per_stream, status);
+    rans_lane_encode_kernel<false><<<grid, 32, 0, st>>>(symbols, indexes, n, lanes, T, tab, states, words, lane_off, out, cap_per_stream, status);
     MMC_CHECK_LAUNCH(name);
     rans_lane_header_kernel<<<batch, 256, 0, st>>>(n, lanes, states, words, lane_off, out, cap_per_stream, nbytes, status);
     MMC_CHECK_LAUNCH(name);
-    rans_lane_encode_kernel<true><<<grid, 32, 0, st>>>(symbols, indexes, n, lanes, T, states, words, lane_off, out, cap_per_stream, status);
+    rans_lane_encode_kernel<true><<<grid, 32, 0, st>>>(symbols, indexes, n, lanes, T, tab, states, words, lane_off, out, cap_per_stream, status);
     MMC_CHECK_LAUNCH(name);
     return MMC_OK;
 }

@@ -111,7 +111,7 @@ _PROTOS = {
     "mmc_gelu_bwd_bf16": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "mmc_layernorm_bwd_bf16": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "mmc_rans_lanes_default": (c_int, [c_i64]),
-    "mmc_rans_device_workspace": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_size_t)]),
+    "mmc_rans_device_workspace": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_size_t)]),
     "mmc_rans_encode_device": (c_int, [c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, ctypes.c_size_t, c_vp, c_vp, c_vp, c_vp]),
     "mmc_rans_decode_device": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mmc_window_attention_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),

@@ -451,7 +451,7 @@ def rans_encode_device_launch(symbols: Tensor, indexes: Tensor, cdf: Tensor, cdf
     tab, lens, offs = _i32dev(cdf, dev), _i32dev(cdf_lengths, dev).reshape(-1), _i32dev(offsets, dev).reshape(-1)
     S = int(lanes) if lanes is not None else rans_lanes_default(n)
     nb = ctypes.c_size_t()
-    L.check(L.lib().mmc_rans_device_workspace(B, S, ctypes.byref(nb)))
+    L.check(L.lib().mmc_rans_device_workspace(B, S, tab.shape[0], tab.shape[1], ctypes.byref(nb)))
     ws = torch.empty(max(nb.value, 16), dtype=torch.uint8, device=dev)
     meta = torch.zeros(B + 2, dtype=torch.int64, device=dev)          # nbytes[B], pad, status (int32 in the last slot)
     if cap is None:

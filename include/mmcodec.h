@@ -462,12 +462,13 @@ MMC_API int mmc_window_attention_bwd(const void *q, const void *kv, const float 
  *   int32 [n_cdfs] (EntropyModel._quantized_cdf / _cdf_length / _offset, entropy_models.py:216-235).
  *   out: [batch][cap_per_stream] bytes (cap % 4 == 0); nbytes[b] = container size (written even if it does not fit);
  *   status: one int, 0 = ok, bit 0 index out of range, bit 1 bad CDF row, bit 2 capacity too small, bit 3 malformed stream.
- *   workspace: mmc_rans_device_workspace bytes.  mmc_rans_lanes_default(n): lane count used when the caller has no preference
- *   (a power of two in [4, 256], about one lane per 8192..16384 symbols: header overhead 8 bytes per lane).
+ *   workspace: mmc_rans_device_workspace bytes, 16-byte aligned (holds the per-call encoder table: start / freq / exact 64-bit
+ *   reciprocal per CDF entry).  mmc_rans_lanes_default(n): lane count used when the caller has no preference (the smallest power
+ *   of two in [4, 1024] with at most 8192 symbols per lane: header overhead 8 bytes per lane).
  * Decoding: streams = concatenated containers, stream_offsets[b] (multiples of 4) / stream_bytes[b] uint64; max_lanes >= the
  * largest lane count in the batch; symbols_out int32 [batch][n]. */
 MMC_API int mmc_rans_lanes_default(int64_t n);
-MMC_API int mmc_rans_device_workspace(int batch, int lanes, size_t *bytes);
+MMC_API int mmc_rans_device_workspace(int batch, int lanes, int n_cdfs, int cdf_stride, size_t *bytes);
 MMC_API int mmc_rans_encode_device(const int32_t *symbols, const int32_t *indexes, int batch, int64_t n, const int32_t *cdfs, int n_cdfs,
                                    int cdf_stride, const int32_t *cdf_sizes, const int32_t *offsets, int lanes, uint8_t *out,
                                    size_t cap_per_stream, uint64_t *nbytes, void *workspace, int *status, void *stream);

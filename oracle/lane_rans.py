@@ -28,9 +28,9 @@ LANE_L = 1 << 16
 
 
 def lanes_default(n: int) -> int:
-    """A power of two in [4, 256]: doubled while every lane would still hold at least 8192 symbols."""
+    """The smallest power of two in [4, 1024] that keeps a lane at <= 8192 symbols."""
     s = 4
-    while s < 256 and s * 2 * 8192 <= n:
+    while s < 1024 and s * 8192 < n:
         s *= 2
     return s
 

@@ -62,14 +62,14 @@ def test_full_size_round_trip_and_rate_vs_host_coder(gc_tables):
     streams = ops.rans_encode_device(sd, idd, *gc_tables)
     assert all(s[:4] == ops.LANE_MAGIC for s in streams)
     S = ops.rans_lanes_default(n)
-    assert S == lane_rans.lanes_default(n) == 128
+    assert S == lane_rans.lanes_default(n) == 256
     assert torch.equal(ops.rans_decode_device(streams, idd, *gc_tables).cpu(), sym)
     host = ops.rans_encode(sym, idx, *gc_tables)            # the reference-compatible stream of the same symbols
     assert torch.equal(ops.rans_decode(host, idx, *gc_tables), sym)
     for b in range(4):
         extra = len(streams[b]) - len(host[b])
-        assert extra <= 16 + 10 * S + 4, (b, extra)
-        assert extra / len(host[b]) < 0.01                  # < 1 % rate overhead at this size
+        assert extra <= 16 + 14 * S + 4, (b, extra)      # 8 bytes of header + <= 6 bytes of flush / rounding per lane
+        assert extra / len(host[b]) < 0.01                  # < 1 % rate overhead at this size and rate (~5 bits per symbol)
     # a second batch through the asynchronous form, two launches in flight
     h1 = ops.rans_encode_device_launch(sd[:2], idd[:2], *gc_tables, pinned={})
     h2 = ops.rans_encode_device_launch(sd[2:], idd[2:], *gc_tables, pinned={})
@@ -138,6 +138,6 @@ def test_models_compress_with_the_device_coder(arch):
     assert piped[0]["strings"] == out["strings"] and piped[1]["strings"] == out["strings"]
     total = lambda strings: sum(len(s) for group in strings for s in group)
     # tiny images: the lane headers (4 lanes per tensor: 48 bytes) are visible, the payload is not larger
-    assert total(out["strings"]) <= total(ref["strings"]) + 3 * 2 * (16 + 10 * 4 + 4)
+    assert total(out["strings"]) <= total(ref["strings"]) + 3 * 2 * (16 + 14 * 4 + 4)
     with pytest.raises(ValueError):
         mmcodec.set_entropy_coder(net, "rangecoder")
