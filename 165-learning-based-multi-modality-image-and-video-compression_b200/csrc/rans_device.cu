@@ -21,7 +21,7 @@
 //
 // Kernels: lanes are threads (32 lanes per warp read symbols / indexes coalesced); the per-lane chain is serial, so the loads of a
 // chunk of 32 steps (symbol, index -> CDF entry) are issued ahead of the chain and only the state arithmetic stays on it.
-//   table   rans_lane_table:         (start, freq, exact 64-bit reciprocal of freq) per CDF entry, so the chain has no division
+//   table   rans_lane_table:         (start, freq, 32-bit reciprocal of freq) per CDF entry, so the chain has no division
 //   pass 1  rans_lane_encode<false>: final state and word count of every lane        (no stores)
 //   scan    rans_lane_header:        lane offsets, header, total size, capacity check  (one CTA per image)
 //   pass 2  rans_lane_encode<true>:  the same chain again, words written in place
@@ -58,18 +58,16 @@ __device__ __forceinline__ void lane_put(uint32_t &x, uint16_t *&ptr, uint32_t &
     x = (q << bits) + (x - q * freq) + start;
 }
 
-// One entry per (CDF row, value): what the chain needs for the 16-bit main token, prepared off the chain.
-//   tok = start << 16 | (freq - 1);  rcp = ceil(2^64 / freq) (0 for freq == 1): x / freq == umul64hi(x, rcp) EXACTLY for x < 2^32,
-//   freq <= 2^16 (the error of the product is < 2^-32, the fractional part of x / freq is <= 1 - 2^-16);  rcp == ~0: invalid row entry.
-struct __align__(16) LaneEntry {
-    uint32_t tok, pad;
-    uint64_t rcp;
+// One 8-byte entry per (CDF row, value): what the chain needs for the 16-bit main token, prepared off the chain.
+//   tok = start << 16 | (freq - 1);  rcp = floor(2^32 / freq) (2^32 - 1 for freq == 1): umulhi(x, rcp) is x / freq or one less for every
+//   x < 2^32 (x rcp / 2^32 lies in (x / freq - 1, x / freq]), so ONE compare-and-fix makes the quotient exact;  rcp == 0: invalid entry.
+struct __align__(8) LaneEntry {
+    uint32_t tok, rcp;
 };
-constexpr uint64_t kLaneBadEntry = ~0ull;
 
-// the main token on the chain: ~12 dependent instructions (the plain version's 32-bit division alone is ~20)
+// the main token on the chain: ~11 dependent instructions, no division
 template <bool kWrite>
-__device__ __forceinline__ void lane_put_main(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t tok, uint64_t rcp)
+__device__ __forceinline__ void lane_put_main(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t tok, uint32_t rcp)
 {
     const uint32_t start = tok >> 16, freq = (tok & 0xffffu) + 1;
     if ((x >> 16) >= freq) {                       // x >= freq << 16
@@ -77,8 +75,9 @@ __device__ __forceinline__ void lane_put_main(uint32_t &x, uint16_t *&ptr, uint3
         ++count;
         x >>= 16;
     }
-    const uint32_t q = rcp ? (uint32_t)__umul64hi((uint64_t)x, rcp) : x;
-    x = (q << kLanePrecision) + (x - q * freq) + start;
+    uint32_t q = __umulhi(x, rcp), r = x - q * freq;
+    if (r >= freq) { ++q; r -= freq; }
+    x = (q << kLanePrecision) + r + start;
 }
 
 __global__ void __launch_bounds__(256) rans_lane_table_kernel(const int32_t *__restrict__ cdfs, const int32_t *__restrict__ sizes, int n_cdfs, int stride,
@@ -88,14 +87,14 @@ __global__ void __launch_bounds__(256) rans_lane_table_kernel(const int32_t *__r
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int row = (int)(i / stride), v = (int)(i - (int64_t)row * stride);
         LaneEntry e;
-        e.tok = 0; e.pad = 0; e.rcp = kLaneBadEntry;
+        e.tok = 0; e.rcp = 0;
         const int len = sizes[row];
         if (len >= 2 && len <= stride && v + 1 < len) {
             const int32_t c0 = cdfs[i], c1 = cdfs[i + 1];
             if (c0 >= 0 && c1 > c0 && c1 - c0 <= (1 << kLanePrecision) && c0 < (1 << kLanePrecision)) {
                 const uint32_t freq = (uint32_t)(c1 - c0);
                 e.tok = ((uint32_t)c0 << 16) | (freq - 1);
-                e.rcp = freq == 1 ? 0ull : (~0ull / freq) + 1;          // = ceil(2^64 / freq) for every freq >= 2
+                e.rcp = freq == 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / freq);
             }
         }
         tab[i] = e;
@@ -104,7 +103,7 @@ __global__ void __launch_bounds__(256) rans_lane_table_kernel(const int32_t *__r
 
 // all tokens of an escaped symbol, last token first (the forward order is: main token, count nibbles, raw nibbles)
 template <bool kWrite>
-__device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t raw, uint32_t tok, uint64_t rcp)
+__device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t raw, uint32_t tok, uint32_t rcp)
 {
     int n_bypass = 0;
     while (n_bypass < 8 && (raw >> (n_bypass * kLaneBypassBits)) != 0) ++n_bypass;
@@ -117,13 +116,21 @@ __device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32
     lane_put_main<kWrite>(x, ptr, count, tok, rcp);
 }
 
+constexpr int kLaneSmemRows = 2048;     // CDF rows whose length / offset are staged in shared memory (more: read from global memory)
+
 template <bool kWrite>
 __global__ void __launch_bounds__(32) rans_lane_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t n, int S,
                                                               LaneTables T, const LaneEntry *__restrict__ tab, uint32_t *__restrict__ states,
                                                               uint32_t *__restrict__ words, const uint32_t *__restrict__ lane_off,
                                                               uint8_t *__restrict__ out, size_t cap, int *__restrict__ status)
 {
+    __shared__ int32_t s_max[kLaneSmemRows], s_offs[kLaneSmemRows];      // per row: length - 2, offset
     const int b = blockIdx.y, lane = blockIdx.x * 32 + threadIdx.x;
+    const bool in_smem = T.n_cdfs <= kLaneSmemRows;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < T.n_cdfs; i += 32) { s_max[i] = __ldg(T.sizes + i) - 2; s_offs[i] = __ldg(T.offsets + i); }
+        __syncwarp();
+    }
     if (lane >= S) return;
     const int32_t *sym = symbols + (int64_t)b * n, *idx = indexes + (int64_t)b * n;
     const int64_t steps = lane < n ? (n - lane + S - 1) / S : 0;
@@ -137,50 +144,51 @@ __global__ void __launch_bounds__(32) rans_lane_encode_kernel(const int32_t *__r
     int bad = 0;
     for (int64_t hi = steps; hi > 0; hi -= kLaneChunk) {
         const int m = hi < kLaneChunk ? (int)hi : kLaneChunk;
-        // ---- off the chain: symbols, indexes and CDF entries of the chunk (position hi - 1 - k, k = 0 .. m - 1).  Three rounds of
-        //      loads, each BRANCH-FREE (out-of-range indexes / values are clamped and flagged, never skipped) so that the 32 loads of a
-        //      round are independent instructions in flight together: with an early-out per symbol the compiler must keep every
-        //      symbol's load -> test -> load sequence in order, and the chunk cost 32 x 2 memory latencies (measured 1.4k cycles per
-        //      symbol instead of ~100) ----
-        int32_t sv[kLaneChunk], iv[kLaneChunk], mv[kLaneChunk], ov[kLaneChunk];
+        // A lone warp per SM issues a dependent instruction every ~4-5 cycles and has nobody to hide a memory latency behind, so the
+        // chunk is three phases separated by compiler barriers (without them the loads sink down to their uses and every symbol
+        // pays its own two memory round trips: measured 820 cycles per symbol):
+        //   (1) 64 coalesced loads: symbols and indexes of the chunk's positions hi - 1 - k, k = 0 .. m - 1;
+        //   (2) per symbol, branch-free: row length / offset from shared memory, escape test, ONE 8-byte table load -- 32 in flight;
+        //   (3) the serial chain on registers only.
+        // Out-of-range indexes / values are clamped and flagged, never skipped (a skip is a branch between the loads).
+        int32_t sv[kLaneChunk], iv[kLaneChunk];
 #pragma unroll
         for (int k = 0; k < kLaneChunk; ++k) {
             const int64_t i = (int64_t)lane + (hi - 1 - (k < m ? k : 0)) * S;      // k >= m: re-read a valid position, ignored below
             sv[k] = __ldg(sym + i);
             iv[k] = __ldg(idx + i);
         }
+        asm volatile("" ::: "memory");
+        uint32_t raw[kLaneChunk];      // bit k of esc: symbol k is escaped (raw bits in raw[k])
+        uint2 ent[kLaneChunk];
+        uint32_t esc = 0;
 #pragma unroll
         for (int k = 0; k < kLaneChunk; ++k) {
             const int32_t ix = min(max(iv[k], 0), T.n_cdfs - 1);
             bad |= (ix != iv[k]) ? LANE_BAD_INDEX : 0;
-            iv[k] = ix;
-            mv[k] = __ldg(T.sizes + ix) - 2;
-            ov[k] = __ldg(T.offsets + ix);
-        }
-        uint32_t tok[kLaneChunk], raw[kLaneChunk];      // bit k of esc: symbol k is escaped (raw bits in raw[k])
-        uint64_t rcp[kLaneChunk];
-        uint32_t esc = 0;
-#pragma unroll
-        for (int k = 0; k < kLaneChunk; ++k) {
-            const int32_t max_value = min(max(mv[k], 0), T.stride - 2);
-            bad |= (max_value != mv[k]) ? LANE_BAD_CDF : 0;
-            int32_t value = sv[k] - ov[k];
+            const int32_t mv = in_smem ? s_max[ix] : __ldg(T.sizes + ix) - 2;
+            const int32_t ov = in_smem ? s_offs[ix] : __ldg(T.offsets + ix);
+            const int32_t max_value = min(max(mv, 0), T.stride - 2);
+            bad |= (max_value != mv) ? LANE_BAD_CDF : 0;
+            const int32_t value = sv[k] - ov;
             const bool neg = value < 0, over = value >= max_value;
-            raw[k] = neg ? (uint32_t)(-2 * (int64_t)value - 1) : (over ? (uint32_t)(2 * ((int64_t)value - max_value)) : 0u);
+            // raw = -2 value - 1 (value < 0), 2 (value - max_value) (value >= max_value): unsigned 32-bit forms of rans_interface.cpp:124-131
+            const uint32_t raw_neg = (uint32_t)(-(value + 1)) * 2u + 1u, raw_over = (uint32_t)(value - max_value) * 2u;
+            raw[k] = neg ? raw_neg : (over ? raw_over : 0u);
             esc |= (neg || over) ? (1u << k) : 0u;
-            value = (neg || over) ? max_value : value;
-            const uint4 e = __ldg(reinterpret_cast<const uint4 *>(tab + (size_t)iv[k] * T.stride + value));      // one 16-byte load per symbol
-            tok[k] = e.x;
-            rcp[k] = ((uint64_t)e.w << 32) | e.z;
-            bad |= (rcp[k] == kLaneBadEntry) ? LANE_BAD_CDF : 0;
+            const int32_t v = (neg || over) ? max_value : value;
+            ent[k] = __ldg(reinterpret_cast<const uint2 *>(tab + (size_t)ix * T.stride + v));
         }
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < kLaneChunk; ++k) bad |= (ent[k].y == 0u) ? LANE_BAD_CDF : 0;
         if (bad) break;
         // ---- on the chain ----
 #pragma unroll
         for (int k = 0; k < kLaneChunk; ++k) {
             if (k >= m) continue;
-            if ((esc >> k) & 1u) lane_put_escape<kWrite>(x, ptr, count, raw[k], tok[k], rcp[k]);
-            else lane_put_main<kWrite>(x, ptr, count, tok[k], rcp[k]);
+            if ((esc >> k) & 1u) lane_put_escape<kWrite>(x, ptr, count, raw[k], ent[k].x, ent[k].y);
+            else lane_put_main<kWrite>(x, ptr, count, ent[k].x, ent[k].y);
         }
     }
     if (bad) atomicOr(status, bad);
@@ -197,9 +205,12 @@ __global__ void __launch_bounds__(256) rans_lane_header_kernel(int64_t n, int S,
 {
     __shared__ uint32_t s_off[kMaxLanes + 1];
     const int b = blockIdx.x;
+    // word counts into shared memory with parallel loads, then the (short) serial scan there instead of S dependent global loads
+    for (int l = threadIdx.x; l < S; l += blockDim.x) s_off[l] = words[(size_t)b * S + l];
+    __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
-        for (int l = 0; l < S; ++l) { s_off[l] = acc; acc += words[(size_t)b * S + l]; }
+        for (int l = 0; l < S; ++l) { const uint32_t w = s_off[l]; s_off[l] = acc; acc += w; }
         s_off[S] = acc;
     }
     __syncthreads();
@@ -329,8 +340,8 @@ int mmc_rans_lanes_default(int64_t n) { return lanes_for(n); }
 int mmc_rans_device_workspace(int batch, int lanes, int n_cdfs, int cdf_stride, size_t *bytes)
 {
     MMC_CHECK_ARG(batch >= 0 && lanes >= 1 && lanes <= kMaxLanes && n_cdfs >= 1 && cdf_stride >= 2 && bytes, "mmc_rans_device_workspace: bad argument");
-    // encoder table (16 bytes per CDF entry, rebuilt by every call: a few microseconds) + states, words, lane offsets (u32 each)
-    *bytes = (size_t)16 * n_cdfs * cdf_stride + (size_t)3 * 4 * (size_t)batch * lanes + 64;
+    // encoder table (8 bytes per CDF entry, rebuilt by every call: a few microseconds) + states, words, lane offsets (u32 each)
+    *bytes = (size_t)8 * n_cdfs * cdf_stride + (size_t)3 * 4 * (size_t)batch * lanes + 64;
     return MMC_OK;
 }
 

@@ -36,6 +36,7 @@ class CompressPipeline:
         self._sets: List[Dict[str, torch.Tensor]] = [dict() for _ in range(self.depth)]
         self._inflight = collections.deque()
         self._n = 0
+        self._code_streams = None
 
     def _stage(self, bufs: Dict[str, torch.Tensor], name: str, t: torch.Tensor) -> torch.Tensor:
         """logical-order int32 copy of a device tensor in this set's pinned buffer (asynchronous on the current stream)"""
@@ -68,13 +69,27 @@ class CompressPipeline:
         shape = c.get("shape")
         if all(m._coder() == "ans-lanes" for m in models.values()):
             # device coder: the symbols stay on the GPU; only the containers (and their sizes) travel, staged in this set's pinned buffers
+            # The coding kernels are a few hundred serial chains (one warp per SM, no shared memory): they run on side streams -- y and
+            # z each on its own -- next to the NEXT batch's transforms instead of in front of them.  The handles keep the symbol /
+            # index tensors alive until the side streams are done with them (collect() waits for that).
             pinned = bufs.setdefault("lane", {})
-            handles = [ops.rans_encode_device_launch(c[f"{k}_symbols"], c[f"{k}_indexes"], *tables[k], pinned=pinned) for k in names]
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(x.device))
+            main = torch.cuda.current_stream(x.device)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            if self._code_streams is None:
+                self._code_streams = [torch.cuda.Stream(device=x.device) for _ in range(2)]
+            handles, done = [], []
+            for k, st in zip(names, self._code_streams):
+                with torch.cuda.stream(st):
+                    st.wait_event(ready)
+                    handles.append(ops.rans_encode_device_launch(c[f"{k}_symbols"], c[f"{k}_indexes"], *tables[k], pinned=pinned))
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    done.append(ev)
 
             def collect():
-                ev.synchronize()
+                for ev_ in done:
+                    ev_.synchronize()
                 return {"strings": [h.collect() for h in handles], "shape": shape}
 
             fut = self._pool.submit(collect)

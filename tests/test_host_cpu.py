@@ -10,7 +10,13 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import PKG_DIR, ROOT
+# (not `from conftest import ...`: spawned gloo workers inherit sys.path, and a test that imported the reference put ITS
+#  conftest.py in front of ours)
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG_DIR = os.path.join(ROOT, "165-learning-based-multi-modality-image-and-video-compression_b200")
+for _p in (ROOT, PKG_DIR, os.path.join(ROOT, "tests", "golden")):
+    if _p not in __import__("sys").path:
+        __import__("sys").path.insert(0, _p)
 
 import mmcodec
 from mmcodec import _lib
