@@ -37,6 +37,7 @@ class CompressPipeline:
         self._inflight = collections.deque()
         self._n = 0
         self._code_streams = None
+        self._copy_stream = None
 
     def _stage(self, bufs: Dict[str, torch.Tensor], name: str, t: torch.Tensor) -> torch.Tensor:
         """logical-order int32 copy of a device tensor in this set's pinned buffer (asynchronous on the current stream)"""
@@ -49,13 +50,38 @@ class CompressPipeline:
         view.copy_(t, non_blocking=True)
         return view
 
+    def _upload(self, bufs, x_host: torch.Tensor) -> torch.Tensor:
+        """Host images (pinned memory for a truly asynchronous copy) -> this set's device input buffer on a COPY stream: the
+        host->device copy of batch i + 1 runs under the kernels of batch i instead of in front of its own."""
+        dev = next(self.net.parameters()).device
+        buf = bufs.get("x_dev")
+        if buf is None or buf.shape != x_host.shape or buf.dtype != x_host.dtype:
+            buf = bufs["x_dev"] = torch.empty(x_host.shape, dtype=x_host.dtype, device=dev)
+            bufs.pop("x_free", None)
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._copy_stream):
+            if "x_free" in bufs:
+                self._copy_stream.wait_event(bufs["x_free"])
+            buf.copy_(x_host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        return buf
+
     def submit(self, x: torch.Tensor) -> Future:
+        """Enqueue one batch: a CUDA tensor, or host images (see _upload).  Returns a Future of compress()'s result."""
         if len(self._inflight) >= self.depth:
             self._inflight.popleft().result()          # the buffer set about to be reused has been coded
         bufs = self._sets[self._n % self.depth]
         self._n += 1
+        if not x.is_cuda:
+            x = self._upload(bufs, x)
         with torch.no_grad():
             c = self.net.symbols_and_indexes(x)
+        if "x_dev" in bufs:                             # this set's input buffer may be overwritten once the GPU stage has read it
+            bufs["x_free"] = torch.cuda.Event()
+            bufs["x_free"].record(torch.cuda.current_stream(x.device))
         names = [k for k in ("y", "z") if f"{k}_symbols" in c]
         net = self.net
 

@@ -127,7 +127,8 @@ def test_models_compress_with_the_device_coder(arch):
             out = net.compress(x)
             hat = net.decompress(out["strings"], out["shape"])["x_hat"]
             pipe = mmcodec.CompressPipeline(net)
-            piped = [f.result() for f in [pipe.submit(x), pipe.submit(x)]]
+            x_pinned = x.cpu().pin_memory()                           # host input: uploaded on the pipeline's copy stream
+            piped = [f.result() for f in [pipe.submit(x), pipe.submit(x_pinned), pipe.submit(x_pinned)]]
             pipe.close()
             with pytest.raises(ValueError):
                 net.decompress(ref["strings"], ref["shape"])          # reference-format streams into the lane decoder
@@ -135,7 +136,7 @@ def test_models_compress_with_the_device_coder(arch):
             mmcodec.set_entropy_coder(net, "ans")
     assert all(s[:4] == ops.LANE_MAGIC for group in out["strings"] for s in group)
     assert torch.equal(hat, ref_hat)                                  # same symbols -> same reconstruction, bit for bit
-    assert piped[0]["strings"] == out["strings"] and piped[1]["strings"] == out["strings"]
+    assert all(p["strings"] == out["strings"] for p in piped) and len(piped) == 3
     total = lambda strings: sum(len(s) for group in strings for s in group)
     # tiny images: the lane headers (4 lanes per tensor: 48 bytes) are visible, the payload is not larger
     assert total(out["strings"]) <= total(ref["strings"]) + 3 * 2 * (16 + 14 * 4 + 4)
