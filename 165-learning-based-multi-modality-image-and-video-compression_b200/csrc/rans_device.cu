@@ -34,7 +34,7 @@ constexpr int kLaneBypassBits = 4;
 constexpr uint32_t kLaneMaxBypass = (1u << kLaneBypassBits) - 1;
 constexpr uint32_t kLaneL = 1u << 16;
 constexpr uint32_t kLaneMagic = 0x4C434D4Du;   // "MMCL"
-constexpr int kLaneChunk = 32;
+constexpr int kLaneChunk = 32;          // decoder: indexes prefetched per chunk
 constexpr int kMaxLanes = 1024;
 
 enum LaneStatus { LANE_OK = 0, LANE_BAD_INDEX = 1, LANE_BAD_CDF = 2, LANE_CAPACITY = 4, LANE_BAD_STREAM = 8 };
@@ -101,10 +101,17 @@ __global__ void __launch_bounds__(256) rans_lane_table_kernel(const int32_t *__r
     }
 }
 
-// all tokens of an escaped symbol, last token first (the forward order is: main token, count nibbles, raw nibbles)
+// all tokens of an escaped symbol, last token first (the forward order is: main token, count nibbles, raw nibbles).  The lane
+// state goes in and out BY VALUE: reference parameters of a non-inlined function would pin x / count / ptr to the stack
+struct LaneState {
+    uint32_t x, count;
+    uint16_t *ptr;
+};
 template <bool kWrite>
-__device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32_t &count, uint32_t raw, uint32_t tok, uint32_t rcp)
+__device__ __noinline__ LaneState lane_put_escape(LaneState st, uint32_t raw, uint32_t tok, uint32_t rcp)
 {
+    uint32_t x = st.x, count = st.count;
+    uint16_t *ptr = st.ptr;
     int n_bypass = 0;
     while (n_bypass < 8 && (raw >> (n_bypass * kLaneBypassBits)) != 0) ++n_bypass;
     for (int j = n_bypass - 1; j >= 0; --j) lane_put<kWrite>(x, ptr, count, (raw >> (j * kLaneBypassBits)) & kLaneMaxBypass, 1, kLaneBypassBits);
@@ -114,10 +121,64 @@ __device__ __noinline__ void lane_put_escape(uint32_t &x, uint16_t *&ptr, uint32
     lane_put<kWrite>(x, ptr, count, (uint32_t)v, 1, kLaneBypassBits);
     for (int j = 0; j < full; ++j) lane_put<kWrite>(x, ptr, count, kLaneMaxBypass, 1, kLaneBypassBits);
     lane_put_main<kWrite>(x, ptr, count, tok, rcp);
+    return LaneState{x, count, ptr};
 }
 
-constexpr int kLaneSmemRows = 2048;     // CDF rows whose length / offset are staged in shared memory (more: read from global memory)
+constexpr int kLaneSmemRows = 512;      // CDF rows whose length / offset are staged in shared memory (more: read from global memory)
+constexpr int kCh = 16;                 // steps per chunk of the software pipeline below
 
+struct LaneChunk {                      // one chunk's operands, ready for the chain
+    uint2 ent[kCh];                     // (tok, rcp) table entries
+    uint32_t raw[kCh];                  // raw bits of escaped symbols
+    uint32_t esc;                       // bit k: symbol k is escaped
+};
+
+// positions hi - 1 - k (k = 0 .. kCh - 1) of this lane, clamped to its first position: always a valid address, extras are ignored
+__device__ __forceinline__ void lane_load(const int32_t *__restrict__ sym, const int32_t *__restrict__ idx, int lane, int S, int64_t hi,
+                                          int32_t (&sv)[kCh], int32_t (&iv)[kCh])
+{
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+        int64_t step = hi - 1 - k;
+        step = step < 0 ? 0 : step;
+        const int64_t i = (int64_t)lane + step * S;
+        sv[k] = __ldg(sym + i);
+        iv[k] = __ldg(idx + i);
+    }
+}
+
+// symbol / index -> table entry, branch-free: out-of-range indexes and row lengths are clamped and FLAGGED, never skipped
+__device__ __forceinline__ void lane_prep(const LaneTables &T, const LaneEntry *__restrict__ tab, const int32_t *s_max, const int32_t *s_offs, bool in_smem,
+                                          const int32_t (&sv)[kCh], const int32_t (&iv)[kCh], LaneChunk &c, int &bad)
+{
+    c.esc = 0;
+#pragma unroll
+    for (int k = 0; k < kCh; ++k) {
+        const int32_t ix = min(max(iv[k], 0), T.n_cdfs - 1);
+        bad |= (ix != iv[k]) ? LANE_BAD_INDEX : 0;
+        const int32_t mv = in_smem ? s_max[ix] : __ldg(T.sizes + ix) - 2;
+        const int32_t ov = in_smem ? s_offs[ix] : __ldg(T.offsets + ix);
+        const int32_t max_value = min(max(mv, 0), T.stride - 2);
+        bad |= (max_value != mv) ? LANE_BAD_CDF : 0;
+        const int32_t value = sv[k] - ov;
+        const bool neg = value < 0, over = value >= max_value;
+        // raw = -2 value - 1 (value < 0), 2 (value - max_value) (value >= max_value): unsigned 32-bit forms of rans_interface.cpp:124-131
+        const uint32_t raw_neg = (uint32_t)(-(value + 1)) * 2u + 1u, raw_over = (uint32_t)(value - max_value) * 2u;
+        c.raw[k] = neg ? raw_neg : (over ? raw_over : 0u);
+        c.esc |= (neg || over) ? (1u << k) : 0u;
+        const int32_t v = (neg || over) ? max_value : value;
+        c.ent[k] = __ldg(reinterpret_cast<const uint2 *>(tab + (size_t)ix * T.stride + v));
+    }
+}
+
+// Encoder of one lane per thread.  A lone warp per SM issues a DEPENDENT instruction only every ~4-5 cycles and has no other warp
+// to hide a memory latency behind, so the loop is a three-deep software pipeline over chunks of kCh steps: while the chain of
+// chunk c runs on registers, the table entries of chunk c + 1 are being fetched (their addresses computed from the symbols /
+// indexes loaded one iteration earlier) and the symbols / indexes of chunk c + 2 are being loaded.  The preparation of the next
+// chunk sits in the SAME basic block as the (branch-free) chain of the current one, so the instruction scheduler fills the
+// chain's latency slots with it; loads are consumed one loop iteration after they are issued, so they cannot sink to their uses
+// (without this structure every symbol paid its own two memory round trips: measured 820 cycles per symbol, then ~500 with the
+// phases merely separated).  Chunks that contain an escaped symbol or are ragged take the per-step path.
 template <bool kWrite>
 __global__ void __launch_bounds__(32) rans_lane_encode_kernel(const int32_t *__restrict__ symbols, const int32_t *__restrict__ indexes, int64_t n, int S,
                                                               LaneTables T, const LaneEntry *__restrict__ tab, uint32_t *__restrict__ states,
@@ -142,53 +203,37 @@ __global__ void __launch_bounds__(32) rans_lane_encode_kernel(const int32_t *__r
         ptr = reinterpret_cast<uint16_t *>(out + (size_t)b * cap + payload) + lane_off[(size_t)b * S + lane] + words[(size_t)b * S + lane];
     }
     int bad = 0;
-    for (int64_t hi = steps; hi > 0; hi -= kLaneChunk) {
-        const int m = hi < kLaneChunk ? (int)hi : kLaneChunk;
-        // A lone warp per SM issues a dependent instruction every ~4-5 cycles and has nobody to hide a memory latency behind, so the
-        // chunk is three phases separated by compiler barriers (without them the loads sink down to their uses and every symbol
-        // pays its own two memory round trips: measured 820 cycles per symbol):
-        //   (1) 64 coalesced loads: symbols and indexes of the chunk's positions hi - 1 - k, k = 0 .. m - 1;
-        //   (2) per symbol, branch-free: row length / offset from shared memory, escape test, ONE 8-byte table load -- 32 in flight;
-        //   (3) the serial chain on registers only.
-        // Out-of-range indexes / values are clamped and flagged, never skipped (a skip is a branch between the loads).
-        int32_t sv[kLaneChunk], iv[kLaneChunk];
+    if (steps > 0) {
+        int32_t sv[kCh], iv[kCh];
+        LaneChunk cur, nxt;
+        int64_t hi = steps;                                  // the current chunk covers steps [hi - kCh, hi) of this lane, last first
+        lane_load(sym, idx, lane, S, hi, sv, iv);
+        lane_prep(T, tab, s_max, s_offs, in_smem, sv, iv, cur, bad);
+        lane_load(sym, idx, lane, S, hi - kCh, sv, iv);
+        for (; hi > 0; hi -= kCh) {
+            const int m = hi < kCh ? (int)hi : kCh;
+            if (cur.esc == 0 && m == kCh) {
+                // ---- the common case: one basic block = preparation of chunk c + 1, loads of chunk c + 2, chain of chunk c ----
+                lane_prep(T, tab, s_max, s_offs, in_smem, sv, iv, nxt, bad);
+                lane_load(sym, idx, lane, S, hi - 2 * kCh, sv, iv);
 #pragma unroll
-        for (int k = 0; k < kLaneChunk; ++k) {
-            const int64_t i = (int64_t)lane + (hi - 1 - (k < m ? k : 0)) * S;      // k >= m: re-read a valid position, ignored below
-            sv[k] = __ldg(sym + i);
-            iv[k] = __ldg(idx + i);
-        }
-        asm volatile("" ::: "memory");
-        uint32_t raw[kLaneChunk];      // bit k of esc: symbol k is escaped (raw bits in raw[k])
-        uint2 ent[kLaneChunk];
-        uint32_t esc = 0;
+                for (int k = 0; k < kCh; ++k) lane_put_main<kWrite>(x, ptr, count, cur.ent[k].x, cur.ent[k].y);
+            } else {
+                lane_prep(T, tab, s_max, s_offs, in_smem, sv, iv, nxt, bad);
+                lane_load(sym, idx, lane, S, hi - 2 * kCh, sv, iv);
 #pragma unroll
-        for (int k = 0; k < kLaneChunk; ++k) {
-            const int32_t ix = min(max(iv[k], 0), T.n_cdfs - 1);
-            bad |= (ix != iv[k]) ? LANE_BAD_INDEX : 0;
-            const int32_t mv = in_smem ? s_max[ix] : __ldg(T.sizes + ix) - 2;
-            const int32_t ov = in_smem ? s_offs[ix] : __ldg(T.offsets + ix);
-            const int32_t max_value = min(max(mv, 0), T.stride - 2);
-            bad |= (max_value != mv) ? LANE_BAD_CDF : 0;
-            const int32_t value = sv[k] - ov;
-            const bool neg = value < 0, over = value >= max_value;
-            // raw = -2 value - 1 (value < 0), 2 (value - max_value) (value >= max_value): unsigned 32-bit forms of rans_interface.cpp:124-131
-            const uint32_t raw_neg = (uint32_t)(-(value + 1)) * 2u + 1u, raw_over = (uint32_t)(value - max_value) * 2u;
-            raw[k] = neg ? raw_neg : (over ? raw_over : 0u);
-            esc |= (neg || over) ? (1u << k) : 0u;
-            const int32_t v = (neg || over) ? max_value : value;
-            ent[k] = __ldg(reinterpret_cast<const uint2 *>(tab + (size_t)ix * T.stride + v));
-        }
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int k = 0; k < kLaneChunk; ++k) bad |= (ent[k].y == 0u) ? LANE_BAD_CDF : 0;
-        if (bad) break;
-        // ---- on the chain ----
-#pragma unroll
-        for (int k = 0; k < kLaneChunk; ++k) {
-            if (k >= m) continue;
-            if ((esc >> k) & 1u) lane_put_escape<kWrite>(x, ptr, count, raw[k], ent[k].x, ent[k].y);
-            else lane_put_main<kWrite>(x, ptr, count, ent[k].x, ent[k].y);
+                for (int k = 0; k < kCh; ++k) {          // static indices: the chunk stays in registers
+                    if (k >= m) continue;
+                    if ((cur.esc >> k) & 1u) {
+                        const LaneState r = lane_put_escape<kWrite>(LaneState{x, count, ptr}, cur.raw[k], cur.ent[k].x, cur.ent[k].y);
+                        x = r.x; count = r.count; ptr = r.ptr;
+                    } else {
+                        lane_put_main<kWrite>(x, ptr, count, cur.ent[k].x, cur.ent[k].y);
+                    }
+                }
+            }
+            cur = nxt;
+            if (bad) break;
         }
     }
     if (bad) atomicOr(status, bad);
