@@ -365,12 +365,14 @@ __global__ void __launch_bounds__(32) rans_lane_decode_kernel(const uint8_t *__r
     if (!ok || ptr != end || x != kLaneL) atomicOr(status, LANE_BAD_STREAM);
 }
 
-// Lane count: the smallest power of two that keeps a lane's chain at <= 8192 symbols, within [4, 1024] -- the chain length is the
-// coding time (two passes of ~0.1-0.2 us per symbol on one thread), the lane count the header overhead (8 bytes per lane).
+// Lane count: the smallest power of two that keeps a lane's chain at <= 8192 symbols, within [4, 1024]; small tensors (the hyper
+// latents) are then split further, up to 64 lanes, while a lane keeps >= 2048 symbols -- the chain length is the coding time
+// (two passes of ~0.15 us per symbol on one thread), the lane count the header overhead (8 bytes per lane).
 static int lanes_for(int64_t n)
 {
     int s = 4;
     while (s < kMaxLanes && (int64_t)s * 8192 < n) s *= 2;
+    while (s < 64 && n / (2 * s) >= 2048) s *= 2;
     return s;
 }
 

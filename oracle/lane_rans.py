@@ -28,9 +28,12 @@ LANE_L = 1 << 16
 
 
 def lanes_default(n: int) -> int:
-    """The smallest power of two in [4, 1024] that keeps a lane at <= 8192 symbols."""
+    """The smallest power of two in [4, 1024] that keeps a lane at <= 8192 symbols; small tensors are split further, up to 64
+    lanes, while a lane keeps >= 2048 symbols."""
     s = 4
     while s < 1024 and s * 8192 < n:
+        s *= 2
+    while s < 64 and n // (2 * s) >= 2048:
         s *= 2
     return s
 

@@ -138,7 +138,7 @@ def test_models_compress_with_the_device_coder(arch):
     assert torch.equal(hat, ref_hat)                                  # same symbols -> same reconstruction, bit for bit
     assert all(p["strings"] == out["strings"] for p in piped) and len(piped) == 3
     total = lambda strings: sum(len(s) for group in strings for s in group)
-    # tiny images: the lane headers (4 lanes per tensor: 48 bytes) are visible, the payload is not larger
-    assert total(out["strings"]) <= total(ref["strings"]) + 3 * 2 * (16 + 14 * 4 + 4)
+    # tiny images: the lane headers (<= 8 lanes per tensor: 80 bytes) are visible, the payload is not larger
+    assert total(out["strings"]) <= total(ref["strings"]) + 3 * 2 * (16 + 14 * 8 + 4)
     with pytest.raises(ValueError):
         mmcodec.set_entropy_coder(net, "rangecoder")

@@ -273,7 +273,7 @@ def test_lane_container_oracle_round_trip_and_token_parity():
         # rate: the reference's stream + the lane headers (8 bytes per lane + 16) + each lane's own flush (its 32-bit end state carries
         # ~2 bytes less than it occupies) and word rounding: <= 6 bytes per lane
         assert len(stream) <= len(host[0]) + 16 + 14 * S + 4, (n, lanes, len(stream), len(host[0]))
-    assert lane_rans.lanes_default(295_000) == 64 and lane_rans.lanes_default(1_570_000) == 256 and lane_rans.lanes_default(10) == 4
+    assert [lane_rans.lanes_default(v) for v in (10, 18_432, 97_920, 295_000, 1_570_000, 2_611_200)] == [4, 8, 32, 64, 256, 512]
     with pytest.raises(ValueError):
         lane_rans.decode(b"XXXX" + stream[4:], idx[0].tolist(), cdfs, sizes, offs)
 
