@@ -685,14 +685,23 @@ def main():
                     x_dev.copy_(x_host, non_blocking=True)
                     first = pipe.submit(x_dev).result()
                     hat_dev = net.decompress(first["strings"], first["shape"])["x_hat"]
-                    barrier()
-                    t0 = time.perf_counter()
-                    futs = []
-                    for _ in range(args.steps):
-                        futs.append(pipe.submit(x_host))          # pinned host batch: uploaded on the pipeline's copy stream
-                    res_dev = [f.result() for f in futs][-1]
-                    torch.cuda.synchronize()
-                    ms_dev = (time.perf_counter() - t0) * 1e3 / args.steps
+                    ms_variants = {}
+                    for variant in ("main_stream_upload", "copy_stream_upload"):
+                        # the host->device copy of the batch either in front of its kernels on the main stream, or on the pipeline's
+                        # copy stream under the previous batch's kernels (submit() of a pinned host tensor); both are reported
+                        barrier()
+                        t0 = time.perf_counter()
+                        futs = []
+                        for _ in range(args.steps):
+                            if variant == "main_stream_upload":
+                                x_dev.copy_(x_host, non_blocking=True)
+                                futs.append(pipe.submit(x_dev))
+                            else:
+                                futs.append(pipe.submit(x_host))
+                        res_dev = [f.result() for f in futs][-1]
+                        torch.cuda.synchronize()
+                        ms_variants[variant] = (time.perf_counter() - t0) * 1e3 / args.steps
+                    ms_dev = min(ms_variants.values())
                     pipe.close()
                     # coding kernels alone, event-timed on the launching stream (y and z of one batch)
                     c_ = net.symbols_and_indexes(x_dev)
@@ -713,7 +722,7 @@ def main():
                 nb_host = sum(len(s_) for ss in host_strings for s_ in ss)
                 nb_dev = sum(len(s_) for ss in res_dev["strings"] for s_ in ss)
                 device_coder_rec = {"value": B * world / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev,
-                                    "coder_ms_per_step": ms_code, "bytes_per_step": nb_dev, "bytes_per_step_host_coder": nb_host,
+                                    "ms_per_step_by_upload": ms_variants, "coder_ms_per_step": ms_code, "bytes_per_step": nb_dev, "bytes_per_step_host_coder": nb_host,
                                     "rate_overhead": nb_dev / nb_host - 1.0,
                                     "lanes_y": ops.rans_lanes_default(c_["y_symbols"][0].numel()),
                                     "round_trip": "decompress(x_hat) bit-identical to the host-coder round trip",
