@@ -1534,7 +1534,10 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
     }
     // (the same threshold holds for the plain bias / activation epilogue: ssf2020's 128 -> 128 encoder layers 0.90 -> 0.73 ms per GOP
     //  with the pair kernel, its transposed-conv decoder layers 0.92 -> 0.98 ms)
-    int need_kb = 24;
+    // Round 2, after the lean issue loops and the late accumulator hand-back: the fused-GDN transposed convolutions gain from the
+    // pair kernel too (probe on cfg 2, batch 64: g_s.0 0.131 -> 0.120 ms, g_s.2 0.364 -> 0.342, g_s.4 1.400 -> 1.334), so layers
+    // with a GDN epilogue take it from 8 K blocks per tile on; the plain epilogue keeps the round-1 threshold.
+    int need_kb = (d->gdn != MMC_GDN_NONE) ? 8 : 24;
     if (const char *g = getenv("MMC_TC_PAIR_MINKB")) need_kb = atoi(g);
     P.pair = (pair_ok && min_kb >= need_kb && tpp * pl.n_phases >= 4 * kNumSMs) ? 1 : 0;
     if (const char *g = getenv("MMC_TC_PAIR")) {   // 0: never, 2: whenever the shape allows it (tests), else the default rule
