@@ -72,13 +72,13 @@ WORKLOAD = WORKLOADS["hyperprior"][6]
 
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the default workload's largest kernels, from the
-# committed `ncu --set full` capture profiles/r02_ncu_conv_tc_full.csv (batch 64 x 768x512).  NOT equal to the algorithmic bytes
+# committed `ncu --set full` capture profiles/r02_ncu_conv_tc_full_v2.csv (batch 64 x 768x512).  NOT equal to the algorithmic bytes
 # for the transposed convolutions: their four output phases each stream the input once (tiles are phase-major), so g_s.4 reads
 # 1.61 GB for a 0.40 GB input (algorithmic: 0.40 + 1.57 GB = 1.97 GB, measured 3.18 GB = 1.6x); the strided convolutions and the
 # edge layers read their input once.
-NCU_DRAM_BYTES = {"g_s.4|tc": 1.611681e9 + 1.569827e9, "g_a.2|tc": 1.613883e9 + 0.390282e9, "g_a.0|tc": 0.408379e9 + 1.557423e9,
-                  "g_s.6|tc": 1.621646e9 + 0.289706e9, "g_s.2|tc": 0.401357e9 + 0.361804e9}
-NCU_SOURCE = "profiles/r02_ncu_conv_tc_full.csv (ncu --set full, profiles/_fwd_once.py, bytes per launch)"
+NCU_DRAM_BYTES = {"g_s.4|tc": 1.614860e9 + 1.570030e9, "g_a.2|tc": 1.616450e9 + 0.390040e9, "g_a.0|tc": 0.408460e9 + 1.559840e9,
+                  "g_s.6|tc": 1.620720e9 + 0.290400e9, "g_s.2|tc": 0.401640e9 + 0.361080e9}
+NCU_SOURCE = "profiles/r02_ncu_conv_tc_full_v2.csv (ncu --set full, profiles/_fwd_once.py, bytes per launch; round-end default path)"
 
 
 def shard_range(total: int, rank: int, world: int):
