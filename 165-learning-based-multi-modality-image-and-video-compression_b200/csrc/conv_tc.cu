@@ -534,6 +534,47 @@ __device__ __forceinline__ void epilogue_gdn_rows(const GdnCtx &g, uint32_t &gdn
     if (g.first_warp && (threadIdx.x & 31) == 0) mbar_arrive(g.empty_bar);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// col2im gather of the reconstruction layer (MODE_SCATTER, k = 5, stride 2), on raw shared-memory addresses.
+// Round 2 (ncu source view of g_s.6, profiles/r02_ncu_scatter_source.txt): the first version walked generic pointers -- every one
+// of the 25 product loads of a work item carried its own 64-bit address arithmetic (LEA / IMAD.WIDE / LD), and the item -> (pixel,
+// channel) decomposition (three integer divisions) was redone for every tile: ~840 SASS instructions per item, the epilogue was
+// ISSUE-bound (2.5k cycles per tile against 0.5k for the tile's TMA stream).  Here the 25 loads are ld.shared with immediate
+// offsets off 9 (dy, dx) row bases, and the work items of a thread are decomposed once, before the tile loop.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
+// base: byte address of S[centre pixel][c]; sp4: bytes per product row; rowp: bytes per tile row of product rows (TW * sp4).
+// Output pixel (2a + py, 2b + px) sums the taps with ky = py, kx = px (mod 2); tap (ky, kx) comes from input pixel
+// (a + (py + 2 - ky) / 2, b + (px + 2 - kx) / 2)  (oy = 2 iy - 2 + ky).  COUT = 0: channel count at run time.
+template <int COUT>
+__device__ __forceinline__ void gather_k5s2(uint32_t base, uint32_t sp4, uint32_t rowp, int cout_rt, float &o00, float &o01, float &o10, float &o11)
+{
+    const uint32_t cs = (uint32_t)(COUT > 0 ? COUT : cout_rt) * 4u;
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+        const int py = ky & 1, dy = (py + 2 - ky) / 2;
+        const uint32_t rb = base + (uint32_t)(dy * (int)rowp);
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+            const int px = kx & 1, dx = (px + 2 - kx) / 2;
+            const float v = lds_f32(rb + (uint32_t)(dx * (int)sp4) + (uint32_t)(ky * 5 + kx) * cs);
+            if (py == 0 && px == 0) o00 += v;
+            else if (py == 0) o01 += v;
+            else if (px == 0) o10 += v;
+            else o11 += v;
+        }
+    }
+}
+constexpr int kScatterItems = 3;    // work items per gather thread: ceil(6 * 14 * 4 / 128)
+
 enum { EPI_PLAIN = 0, EPI_GDN = 1, EPI_SCATTER = 2 };
 
 template <int kEpi, int kNCH, bool kPair, int kParts, int kTeams>
@@ -563,7 +604,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
     float *sStage = reinterpret_cast<float *>(sG);                  // MODE_SCATTER: [128][spitch] fp32 products
     // resident weights (b_resident): one [Ntile][64] bf16 tile per K block, after the GDN / staging region
     const size_t epi_bytes = (kEpi == EPI_GDN) ? (size_t)P.Cout * P.Cout * 2 + (P.a_tmem ? 0 : (size_t)(P.Cout / 64) * kABytes)
-                           : (kEpi == EPI_SCATTER) ? 2 * (((size_t)128 * P.spitch * sizeof(float) + 1023) & ~(size_t)1023) : 0;
+                           : (kEpi == EPI_SCATTER) ? kParts * (((size_t)128 * P.spitch * sizeof(float) + 1023) & ~(size_t)1023) : 0;
     uint8_t *sBres = sG + epi_bytes;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -902,12 +943,33 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
         int acc_i = 0;
         uint32_t acc_ph = 0;
         const uint32_t empty_leader = kPair ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+        // col2im gather: this thread's work items e = et + 128 i -> (channel c, interior input pixel (ay, ax)), tile independent
+        uint32_t sc_soff[kScatterItems];    // byte offset of S[centre pixel][c] in the team's staging buffer
+        int sc_yx[kScatterItems];           // (c << 24) | (ay << 16) | ax, -1: no item
+        int64_t sc_out[kScatterItems];      // output offset relative to the tile's first interior output pixel of channel 0
+        int sc_items = 0;                   // work items per tile (all threads)
+        if constexpr (kEpi == EPI_SCATTER) {
+            const int et = (threadIdx.x - 32 * kSvcWarps) & 127;
+            const int ih = P.TH - P.halo_lo - P.halo_hi, iw = P.TW - P.halo_lo - P.halo_hi;
+            const int items = ih * iw * P.Cout;
+            sc_items = items;
+#pragma unroll
+            for (int i = 0; i < kScatterItems; ++i) {
+                const int e = et + 128 * i;
+                const int ax = e % iw, r2 = e / iw;
+                const int ay = r2 % ih, c = r2 / ih;
+                sc_yx[i] = e < items ? ((c << 24) | (ay << 16) | ax) : -1;
+                sc_soff[i] = e < items ? (uint32_t)((((P.halo_lo + ay) * P.TW + P.halo_lo + ax) * P.spitch + c) * 4) : (uint32_t)(((P.halo_lo * P.TW + P.halo_lo) * P.spitch) * 4);    // no item: any valid product row
+                sc_out[i] = ((int64_t)c * P.Ho + ay * P.out_stride) * P.Wo + ax * P.out_stride;
+            }
+        }
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
             if (kPair) ti.init(P, tile);
-            // col2im epilogue: two independent teams of 4 warps (one warp per TMEM lane quarter) take alternate tiles, each with its
-            // own staging buffer and named barrier, so that one team's TMEM / shared-memory latencies overlap the other's work.
-            // acc_stages is even there, hence every accumulator stage (and its barriers) always belongs to the same team.
-            if (kEpi == EPI_SCATTER && (it & 1) != half) continue;
+            // col2im epilogue: kParts (2-4) independent teams of 4 warps (one warp per TMEM lane quarter) take tiles round robin, each
+            // with its own staging buffer and named barrier, so that one team's TMEM / shared-memory latencies overlap the others' work
+            // (a team is a serial chain of dependent latencies: with two teams the layer ran at ~0.3 instructions per scheduler cycle).
+            // acc_stages is a multiple of kParts there, hence every accumulator stage (and its barriers) always belongs to the same team.
+            if (kEpi == EPI_SCATTER && (it % kParts) != half) continue;
             if (kTeams == 2 && (it & 1) != team) continue;             // GDN teams: alternate tiles
             const TileCoord t = ti.coord(P);
             const int as = acc_i;                       // accumulator ring position of this tile
@@ -922,19 +984,26 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             if (kEpi == EPI_SCATTER) {
                 // ---- GEMM + col2im: column n = (ky*k + kx)*Cout + c holds x[q] . w[:, c, ky, kx] for INPUT pixel q ----
                 float *stage = sStage + (size_t)half * ((((size_t)128 * P.spitch * sizeof(float) + 1023) & ~(size_t)1023) / sizeof(float));
+                const uint32_t stage_a = smem_u32(stage);
                 {
                     const int nch = P.Ntile >> 4;
-                    float *srow = stage + (size_t)row * P.spitch;
-                    for (int ch = 0; ch < nch; ++ch) {
-                        float v[16];
-                        tmem_ld16(acc_addr + (ch << 4), v);
-                        tmem_ld_wait();
-                        // scalar stores with an ODD row pitch: conflict-free here (lanes = rows) and in the gather below
-                        // (lanes = neighbouring pixels = neighbouring rows); 16-byte stores would need a pitch that is a
-                        // multiple of 4 and make the gather 4-way bank conflicted
-                        float *dst = srow + (ch << 4);
+                    const uint32_t srow = stage_a + (uint32_t)(row * P.spitch) * 4u;
+                    // scalar stores with an ODD row pitch: conflict-free here (lanes = rows) and in the gather below
+                    // (lanes = neighbouring pixels = neighbouring rows); 16-byte stores would need a pitch that is a
+                    // multiple of 4 and make the gather 4-way bank conflicted.  Four TMEM loads in flight per wait.
+                    for (int ch = 0; ch < nch; ch += 4) {
+                        float v[4][16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) dst[i] = v[i];
+                        for (int u = 0; u < 4; ++u)
+                            if (ch + u < nch) tmem_ld16(acc_addr + ((ch + u) << 4), v[u]);
+                        tmem_ld_wait();
+                        const uint32_t dst = srow + (uint32_t)(ch << 6);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (ch + u < nch) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) sts_f32(dst + 64 * u + 4 * i, v[u][i]);
+                            }
                     }
                 }
                 // the accumulator is drained: hand the TMEM stage back before the gather pass
@@ -942,9 +1011,48 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-                {
-                    // Gather: one work item per (interior input-resolution pixel a, channel c) produces the s x s output
-                    // block (s*a + p); every product S[q][(ky,kx,c)] is consumed exactly once.
+                if (P.k == 5 && P.out_stride == 2) {
+                    // Gather (k = 5, stride 2): one work item per (interior input-resolution pixel a, channel c) produces the 2 x 2
+                    // output block at 2 a; every product S[q][(ky,kx,c)] is consumed exactly once.
+                    const int oyb = (t.y0 + P.halo_lo) * 2, oxb = (t.x0 + P.halo_lo) * 2;
+                    float *tile_out = (float *)P.y + ((int64_t)t.b * P.Cout * P.Ho + oyb) * P.Wo + oxb;
+                    const uint32_t sp4 = (uint32_t)P.spitch * 4u, rowp = sp4 * (uint32_t)P.TW;
+                    const bool even_w = (P.Wo & 1) == 0;
+                    // all product loads of this thread's items are issued before the first use (a missing item reads the first interior
+                    // pixel's products and is dropped at the store): the gather is a latency chain of 25 loads + adds per item otherwise
+                    float o[kScatterItems][4];
+#pragma unroll
+                    for (int i = 0; i < kScatterItems; ++i) {
+                        if (i * 128 >= sc_items) break;                       // uniform: item slots in use = ceil(items / 128)
+                        const uint32_t base = stage_a + sc_soff[i];
+                        const float b0 = bias_s[(sc_yx[i] >> 24) & 3];
+                        o[i][0] = o[i][1] = o[i][2] = o[i][3] = b0;           // same summation order as the generic loop: bias, then the taps
+                        if (P.Cout == 3) gather_k5s2<3>(base, sp4, rowp, 3, o[i][0], o[i][1], o[i][2], o[i][3]);
+                        else if (P.Cout == 1) gather_k5s2<1>(base, sp4, rowp, 1, o[i][0], o[i][1], o[i][2], o[i][3]);
+                        else gather_k5s2<0>(base, sp4, rowp, P.Cout, o[i][0], o[i][1], o[i][2], o[i][3]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < kScatterItems; ++i) {
+                        if (i * 128 >= sc_items) break;
+                        if (sc_yx[i] < 0) continue;
+                        const int oy0 = oyb + 2 * ((sc_yx[i] >> 16) & 0xff), ox0 = oxb + 2 * (sc_yx[i] & 0xffff);
+                        if (oy0 >= P.Ho || ox0 >= P.Wo) continue;
+                        const float o00 = act_tc(o[i][0], P.act), o01 = act_tc(o[i][1], P.act);
+                        const float o10 = act_tc(o[i][2], P.act), o11 = act_tc(o[i][3], P.act);
+                        float *row0 = tile_out + sc_out[i];
+                        const bool two_x = ox0 + 1 < P.Wo, two_y = oy0 + 1 < P.Ho;
+                        if (two_x && even_w) {
+                            *reinterpret_cast<float2 *>(row0) = make_float2(o00, o01);
+                            if (two_y) *reinterpret_cast<float2 *>(row0 + P.Wo) = make_float2(o10, o11);
+                        } else {
+                            row0[0] = o00;
+                            if (two_x) row0[1] = o01;
+                            if (two_y) { row0[P.Wo] = o10; if (two_x) row0[P.Wo + 1] = o11; }
+                        }
+                    }
+                } else {
+                    // Generic gather (other kernel sizes / strides): one work item per (interior input-resolution pixel a, channel c)
+                    // produces the s x s output block (s*a + p); every product S[q][(ky,kx,c)] is consumed exactly once.
                     const int s = P.out_stride, k = P.k;
                     const int ih = P.TH - P.halo_lo - P.halo_hi, iw = P.TW - P.halo_lo - P.halo_hi;   // interior (input res)
                     const int items = ih * iw * P.Cout;
@@ -957,34 +1065,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                         const int oy0 = (t.y0 + P.halo_lo + ay) * s, ox0 = (t.x0 + P.halo_lo + ax) * s;
                         if (oy0 >= P.Ho || ox0 >= P.Wo) continue;
                         const float b0 = bias_s[c];
-                        if (k == 5 && s == 2) {
-                            // pad = 2: ky has the parity of oy; input row = a + (py + 2 - ky) / 2  (all compile-time)
-                            float o00 = b0, o01 = b0, o10 = b0, o11 = b0;
-                            const float *base = stage + (size_t)((P.halo_lo + ay) * P.TW + (P.halo_lo + ax)) * P.spitch + c;
-#pragma unroll
-                            for (int ky = 0; ky < 5; ++ky) {
-#pragma unroll
-                                for (int kx = 0; kx < 5; ++kx) {
-                                    const int py = ky & 1, px = kx & 1;
-                                    const int dy = (py + 2 - ky) / 2, dx = (px + 2 - kx) / 2;
-                                    const float v = base[(dy * P.TW + dx) * P.spitch + (ky * 5 + kx) * P.Cout];
-                                    if (py == 0 && px == 0) o00 += v;
-                                    else if (py == 0) o01 += v;
-                                    else if (px == 0) o10 += v;
-                                    else o11 += v;
-                                }
-                            }
-                            float *row0 = yo + (((int64_t)t.b * P.Cout + c) * P.Ho + oy0) * P.Wo + ox0;
-                            const bool two_x = ox0 + 1 < P.Wo, two_y = oy0 + 1 < P.Ho;
-                            if (two_x && ((P.Wo & 1) == 0)) {
-                                *reinterpret_cast<float2 *>(row0) = make_float2(act_tc(o00, P.act), act_tc(o01, P.act));
-                                if (two_y) *reinterpret_cast<float2 *>(row0 + P.Wo) = make_float2(act_tc(o10, P.act), act_tc(o11, P.act));
-                            } else {
-                                row0[0] = act_tc(o00, P.act);
-                                if (two_x) row0[1] = act_tc(o01, P.act);
-                                if (two_y) { row0[P.Wo] = act_tc(o10, P.act); if (two_x) row0[P.Wo + 1] = act_tc(o11, P.act); }
-                            }
-                        } else {
+                        {
                             for (int py = 0; py < s; ++py)
                                 for (int px = 0; px < s; ++px) {
                                     const int oy = oy0 + py, ox = ox0 + px;
@@ -1461,6 +1542,7 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
         P.step_y = P.TH - pl.halo_lo - pl.halo_hi; P.step_x = P.TW - pl.halo_lo - pl.halo_hi;
         P.off_y = P.off_x = pl.halo_lo;
         P.spitch = P.Ntile | 1;                          // odd pitch (floats): see the staging stores in the kernel
+        MMC_UNSUPPORTED(P.step_y * P.step_x * d->Cout > 128 * kScatterItems, "%s: more than %d col2im work items per tile", name, 128 * kScatterItems);
     } else {
         pick_tile(P.Gh, P.Gw, pl.mode == MODE_PAD8 ? 1 : P.a_sx, P.a_sy, &P.TH, &P.TW);
         // Tap groups (see struct Group): taps with the same x offset whose y offsets differ by multiples of the A-grid stride
@@ -1567,8 +1649,15 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
     if (const char *g = getenv("MMC_TC_TEAMS")) teams = atoi(g) == 2;
     teams = teams && d->gdn != MMC_GDN_NONE && !P.pair && (d->Cout == 64 || d->Cout == 128) && P.Ntile == d->Cout;
     if (teams) { P.acc_stages = 3; P.a_tmem = 1; P.gdn_chunk = 0; }
+    // col2im epilogue teams (4 warps each).  Default 3: measured on cfg 2 (g_s.6, batch 64) -- see the table in DESIGN.md 4.1
+    int sc_teams = 3;
+    if (const char *g = getenv("MMC_TC_SCATTER_TEAMS")) { const int v = atoi(g); if (v >= 2 && v <= 4) sc_teams = v; }
     if (pl.mode == MODE_SCATTER) {
-        P.acc_stages &= ~1;    // the two col2im epilogue teams own alternate accumulator stages
+        // every team has its own fp32 staging tile: keep room for the resident weights and three activation stages
+        const size_t staging = (((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023;
+        const size_t b_res = (size_t)pl.ntaps * pl.kchunks * P.Ntile * 128;
+        while (sc_teams > 2 && (P.acc_stages < sc_teams || sc_teams * staging + b_res + 3 * kABytes > (size_t)200 * 1024)) --sc_teams;
+        P.acc_stages -= P.acc_stages % sc_teams;    // the col2im epilogue teams own the accumulator stages round robin
         MMC_UNSUPPORTED(P.acc_stages < 2, "%s: the reconstruction kernel needs two accumulator stages (N tile %d)", name, P.Ntile);
     }
     MMC_UNSUPPORTED((teams ? 3 * P.Ntile + d->Cout : P.acc_stages * P.Ntile + P.gdn_chunk + (P.a_tmem ? d->Cout / 2 : 0)) > 512 || (P.gdn_chunk % 16) != 0,
@@ -1576,7 +1665,7 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
 
     size_t fixed = 1024;  // alignment slack
     if (d->gdn != MMC_GDN_NONE) fixed += (size_t)d->Cout * d->Cout * 2 + (P.a_tmem ? 0 : (size_t)(d->Cout / 64) * kABytes);
-    if (pl.mode == MODE_SCATTER) fixed += 2 * ((((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023);   // one staging buffer per epilogue team
+    if (pl.mode == MODE_SCATTER) fixed += sc_teams * ((((size_t)128 * P.spitch * sizeof(float)) + 1023) & ~(size_t)1023);   // one staging buffer per epilogue team
     // Small layers (image-edge conv, reconstruction deconv): keep every weight tile resident in shared memory so that
     // the K blocks stream activations only (halves the L2 -> SM traffic of those layers).
     const size_t b_total = (size_t)pl.ntaps * pl.kchunks * P.Ntile * 128;
@@ -1649,7 +1738,11 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl.mode == MODE_SCATTER) return launch_tc<EPI_SCATTER, 0>(P, fixed, stage_bytes, st, name);
+    if (pl.mode == MODE_SCATTER) {
+        if (sc_teams == 4) return launch_tc<EPI_SCATTER, 0, false, 4>(P, fixed, stage_bytes, st, name);
+        if (sc_teams == 3) return launch_tc<EPI_SCATTER, 0, false, 3>(P, fixed, stage_bytes, st, name);
+        return launch_tc<EPI_SCATTER, 0>(P, fixed, stage_bytes, st, name);
+    }
     if (d->gdn != MMC_GDN_NONE) {
         // one kernel per channel count (16-column chunks per epilogue thread = Cout / 32) so that each gets its own
         // register allocation: C=128 keeps 64 activations per thread in registers, C=192 keeps 96
