@@ -630,6 +630,14 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         }
     }
+    // Programmatic dependent launch (launch_tc sets cudaLaunchAttributeProgrammaticStreamSerialization): everything above -- barrier
+    // init, tensor-map prefetch, the TMEM allocation -- touches only this CTA's own state and may run while the previous kernel of the
+    // stream is still draining; from here on global memory written by it (activations; on a first forward also packed weights and
+    // the GDN parameters) is read, so every thread waits for its completion and memory flush first.  The early launch_dependents lets
+    // the NEXT kernel's CTAs take over SMs as this (persistent, one CTA per SM) grid's CTAs exit one by one: its prologue and first
+    // operand loads overlap this kernel's tail instead of following a full grid drain + launch.  Both are no-ops without the attribute.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (kEpi == EPI_GDN) {
         // pair mode: this CTA supplies weight (and bias) rows [rank * Ntile / 2, (rank + 1) * Ntile / 2) of the main-loop B operand
         const int brows = kPair ? P.Ntile / 2 : P.Ntile;
@@ -1398,18 +1406,29 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         Q.st_b = r % Q.B;
         Q.st_ph = r / Q.B;
     }
+    // Programmatic dependent launch between consecutive layers (see the griddepcontrol pair in the kernel).  MMC_TC_PDL=0: plain
+    // stream order (measurement aid).
+    static const bool use_pdl = getenv("MMC_TC_PDL") ? atoi(getenv("MMC_TC_PDL")) != 0 : false;   // opt-in until measured
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attrs[2];
+    int nattr = 0;
+    if (use_pdl) {
+        attrs[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attrs[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    cfg.blockDim = dim3(tc_threads(kParts, kTeams)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attrs;
     if (kPair) {
         // 2-CTA clusters: even grid, as many pairs as the device can keep resident
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cudaLaunchAttribute attr;
+        cudaLaunchAttribute &attr = attrs[nattr++];
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.blockDim = dim3(tc_threads(kParts, kTeams)); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = &attr; cfg.numAttrs = 1;
+        cfg.numAttrs = nattr;
         static PerDevice<int> max_pairs_dev;
         int max_pairs = max_pairs_dev.cur().load(std::memory_order_relaxed);
         if (max_pairs == 0) {
-            cfg.gridDim = dim3(kNumSMs);
+            cfg.gridDim = dim3(kNumSMs & ~1);
             int n = 0;
             MMC_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams>, &cfg));
             max_pairs = n > 0 ? n : 1;
@@ -1423,8 +1442,10 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         count_launch();
         return MMC_OK;
     }
-    conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams><<<grid, tc_threads(kParts, kTeams), smem, st>>>(Q);
-    MMC_CHECK_LAUNCH(name);
+    cfg.numAttrs = nattr;
+    cfg.gridDim = dim3(grid);
+    MMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams>, Q));
+    count_launch();
     return MMC_OK;
 }
 
