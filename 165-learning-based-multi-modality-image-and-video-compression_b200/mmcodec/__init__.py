@@ -11,10 +11,11 @@
     mmcodec.training         RateDistortionLoss, configure_optimizers, GradBucketReducer (NCCL), TrainStep
     mmcodec.transforms_functional   rgb2ycbcr, ycbcr2rgb, yuv_444_to_420, yuv_420_to_444 (compressai.transforms.functional)
     mmcodec.ops              functional access to every entry point of include/mmcodec.h
+    mmcodec.library          torch.library ops (mmcodec::gdn, mmcodec::lower_bound) + the stand-ins torch.jit.script compiles
 
 All compute runs in libmmcodec.so (hand-written CUDA for sm_100a).  No CPU fallback.
 """
-from . import _lib, compress_pipeline, entropy_models, graphs, host_pipeline, layers, models, models_master, models_mm, models_video, ops, training, transforms, transforms_functional  # noqa: F401
+from . import _lib, compress_pipeline, entropy_models, graphs, host_pipeline, layers, library, models, models_master, models_mm, models_video, ops, training, transforms, transforms_functional  # noqa: F401
 from .accelerate import accelerate  # noqa: F401
 from .graphs import GraphedForward  # noqa: F401
 from .transforms import precision  # noqa: F401

@@ -46,6 +46,11 @@ class LowerBound(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         return _LowerBoundFunction.apply(x, self._sync_bound())
 
+    def __prepare_scriptable__(self):
+        # torch.jit.script compiles a stand-in whose forward is the registered op mmcodec::lower_bound (mmcodec/library.py)
+        from .library import ScriptableLowerBound
+        return ScriptableLowerBound(self)
+
     def _sync_bound(self) -> float:
         # the buffer may have been overwritten by load_state_dict; read it back once per version
         v = (self.bound._version, self.bound.data_ptr())
@@ -76,6 +81,10 @@ class NonNegativeParametrizer(nn.Module):
     def forward(self, x: Tensor) -> Tensor:
         out = self.lower_bound(x)
         return out ** 2 - self.pedestal
+
+    def __prepare_scriptable__(self):
+        from .library import ScriptableNonNegativeParametrizer
+        return ScriptableNonNegativeParametrizer(self)
 
 
 class GDN(nn.Module):
@@ -117,6 +126,12 @@ class GDN(nn.Module):
         # recorded (mmcodec.autograd._GdnFn); otherwise it is the plain forward kernel
         from . import autograd as AG
         return AG.gdn_forward(self, x)
+
+    def __prepare_scriptable__(self):
+        # compressai tests/test_scripting.py:37-59 scripts GDN: the scripted module is one call of the registered op mmcodec::gdn
+        # on the same Parameters (mmcodec/library.py)
+        from .library import ScriptableGDN
+        return ScriptableGDN(self)
 
 
 class _PackedWeightMixin:

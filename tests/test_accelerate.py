@@ -56,6 +56,10 @@ def test_accelerate_live_reference_models():
         with pytest.raises(RuntimeError, match="CUDA tensors only"):
             net(torch.rand(1, 3, 64, 64))
         assert mmcodec.accelerate(net)._mmc_accelerated_modules == 0   # idempotent: nothing left to swap
+        # the reference scripts its GDN (tests/test_scripting.py:37-59): the accelerated one still scripts, into the registered op,
+        # on the live Parameters
+        sg = torch.jit.script(net.g_a[1])
+        assert "ops.mmcodec.gdn" in sg.code and sg.state_dict()["gamma"].data_ptr() == net.g_a[1].gamma.data_ptr()
 
 
 # ---- foreign stand-ins: the attribute sets of the reference's classes, none of this package's types ---------------------------

@@ -434,3 +434,26 @@ def test_bench_reference_arm_of_the_pair_workloads():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "master-train"],
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0 and "unavailable" in json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_torchscript_stand_ins_and_op_schemas():
+    """torch.jit.script of the layer mirrors compiles (compressai tests/test_scripting.py:37-59) into one call of a registered
+    torch.library op; the scripted module keeps the reference's state_dict keys and shares the Parameters; no CPU kernel exists."""
+    import torch
+    import mmcodec
+    g = mmcodec.GDN(128)
+    m = torch.jit.script(g)
+    assert "ops.mmcodec.gdn" in m.code
+    assert list(m.state_dict().keys()) == ["beta", "gamma", "beta_reparam.pedestal", "beta_reparam.lower_bound.bound",
+                                           "gamma_reparam.pedestal", "gamma_reparam.lower_bound.bound"]
+    assert m.state_dict()["beta"].data_ptr() == g.beta.data_ptr()
+    assert "ops.mmcodec.lower_bound" in torch.jit.script(mmcodec.LowerBound(0.11)).code
+    schema = str(torch.ops.mmcodec.gdn.default._schema)
+    assert schema == "mmcodec::gdn(Tensor x, Tensor beta, Tensor gamma, float beta_bound, float gamma_bound, float pedestal, bool inverse) -> Tensor"
+    # fake (meta) implementation: shape / dtype propagation without a device
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        y = torch.ops.mmcodec.gdn(torch.empty(2, 128, 4, 4), torch.empty(128), torch.empty(128, 128), 1e-3, 4e-6, 1.5e-11, False)
+        assert tuple(y.shape) == (2, 128, 4, 4) and y.dtype == torch.float32
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        m(torch.rand(1, 128, 1, 1))                      # CPU tensor: loud failure, there is no CPU path
