@@ -34,7 +34,7 @@ def _pinned_like(shape, channels_last: bool) -> Tensor:
 
 class HostPipeline:
     def __init__(self, net, micro_batch: int = 8, device: Optional[torch.device] = None, use_graphs: bool = True, outputs: str = "full",
-                 concurrent_slots: Optional[bool] = None):
+                 concurrent_slots: Optional[bool] = None, n_slots: int = 2):
         if outputs not in ("full", "metrics"):
             raise ValueError('outputs must be "full" (x_hat + likelihoods) or "metrics" (per-image bpp and mse)')
         self.outputs = outputs
@@ -52,6 +52,9 @@ class HostPipeline:
         # own memory pool).  Measured: +7 % when the copy is cheap (uint8 input: 8,993 -> 9,599 img/s), -3 % when the pipeline is bound
         # by the fp32 host->device copy (8,478 -> 8,274 img/s) -- so the default (None) enables it for uint8 inputs only.
         self.concurrent_slots = concurrent_slots
+        # input slots (device staging buffers, one captured graph each): the host->device copy of micro-batch i + n_slots - 1 may run
+        # while micro-batch i computes.  Even, so that a slot always replays on the same run stream.
+        self.n_slots = max(2, int(n_slots) + (int(n_slots) & 1))
         self.s_run2 = torch.cuda.Stream(self.device)
         self._slots = None
         self._u8_slots = None
@@ -68,18 +71,18 @@ class HostPipeline:
             self._graphs = None
             self._param_sig = sig
         if self._slots is None or tuple(self._slots[0].shape) != shape:
-            self._slots = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._slots = [torch.zeros(shape, dtype=torch.float32, device=self.device) for _ in range(self.n_slots)]
             self._u8_slots = None
             self._graphs = None
         if x_host.dtype == torch.uint8 and self._u8_slots is None:
             # 8-bit images (as decoded from PNG): the copy carries one byte per sample, ToTensor's /255 runs on the device
-            self._u8_slots = [torch.zeros(shape, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._u8_slots = [torch.zeros(shape, dtype=torch.uint8, device=self.device) for _ in range(self.n_slots)]
         if self.use_graphs and self._graphs is None:
             graphs = []
             with torch.cuda.stream(self.s_run), torch.no_grad():
                 self._forward(self._slots[0])     # fills the per-parameter caches (packed weights, LUTs) outside the capture
                 torch.cuda.synchronize(self.device)
-                for k in range(2):
+                for k in range(self.n_slots):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=self.s_run):
                         o = self._forward(self._slots[k])
@@ -128,8 +131,8 @@ class HostPipeline:
         start.record(caller)
         for s in (self.s_h2d, self.s_run, self.s_run2, self.s_d2h):
             s.wait_event(start)
-        slot_free = [None, None]      # event: kernels that read slot k have finished
-        out_free = [None, None]       # event: the captured outputs of slot k have been copied to the host
+        slot_free = [None] * self.n_slots      # event: kernels that read slot k have finished
+        out_free = [None] * self.n_slots       # event: the captured outputs of slot k have been copied to the host
         last_d2h = None
         result = out if out is not None else self._out
         if result is not None and next(iter(result.values())).shape[0] != B:
@@ -137,14 +140,14 @@ class HostPipeline:
         i = 0
         for lo in range(0, B, mb):
             hi = min(lo + mb, B)
-            k = i & 1
+            k = i % self.n_slots
             with torch.cuda.stream(self.s_h2d):
                 if slot_free[k] is not None:
                     self.s_h2d.wait_event(slot_free[k])
                 (self._u8_slots if as_u8 else slots)[k][: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(self.s_h2d)
-            s_run = self.s_run2 if (k and concurrent) else self.s_run
+            s_run = self.s_run2 if ((k & 1) and concurrent) else self.s_run
             with torch.cuda.stream(s_run):
                 s_run.wait_event(ev_in)
                 if out_free[k] is not None:

@@ -11,9 +11,11 @@ net = net.cuda()
 x = torch.rand(64, 3, 512, 768).pin_memory()
 variants = [(8, False), (8, True), (16, False), (16, True), (4, True), (32, False)]
 if len(sys.argv) > 1:
-    variants = [(int(a.split(",")[0]), a.split(",")[1] == "1") for a in sys.argv[1:]]
-for mb, conc in variants:
-    pipe = mmcodec.HostPipeline(net, micro_batch=mb, outputs="metrics", concurrent_slots=conc)
+    variants = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]]
+for var in variants:
+    mb, conc = var[0], bool(var[1])
+    slots = var[2] if len(var) > 2 else 2
+    pipe = mmcodec.HostPipeline(net, micro_batch=mb, outputs="metrics", concurrent_slots=conc, n_slots=slots)
     for _ in range(3):
         r = pipe(x)
     torch.cuda.synchronize()
@@ -24,5 +26,5 @@ for mb, conc in variants:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    print(f"micro_batch={mb} concurrent={int(conc)} ms_per_step={ms:.3f} img/s={64e3 / ms:.0f} bpp={float(r['bpp'].mean()):.6f}", flush=True)
+    print(f"micro_batch={mb} concurrent={int(conc)} slots={slots} ms_per_step={ms:.3f} img/s={64e3 / ms:.0f} bpp={float(r['bpp'].mean()):.6f}", flush=True)
     del pipe
