@@ -110,6 +110,8 @@ struct TcParams {
     int act, gdn, out_f32, out2;
     int gdn_chunk;
     int tiles_per_phase, total_tiles;
+    int phase_inner;     // transposed convolutions: the stride^2 output phases of a wave of spatial tiles run back to back (see map_tile)
+    int n_virtual;       // bound of the persistent loops' running index (== total_tiles unless phase_inner)
     int st_nb, st_tx, st_ty, st_b, st_ph;   // gridDim.x decomposed in the radices (n_blocks, tiles_x, tiles_y, B, phase)
     const float *bias;
     const float *beta;
@@ -194,6 +196,23 @@ struct TileIter {
     }
     __device__ __forceinline__ TileCoord coord(const TcParams &P) const { return make_coord(P, phase, b, ty, tx, nb); }
 };
+
+// Persistent-loop index -> tile.  Default: tile = index, i.e. phase-major -- every output phase of a transposed convolution sweeps the
+// whole input, which is therefore read from HBM stride^2 times (round-2 ncu: g_s.4 reads 1.61 GB for a 0.40 GB input).  With
+// P.phase_inner iteration k of CTA c is (wave w = k / n_phases, phase p = k % n_phases) -> spatial tile w * gridDim + c of phase p:
+// all CTAs run the same phase at the same time (same work per CTA, the tap counts differ between phases), a CTA pair keeps two
+// adjacent spatial tiles of ONE phase, and the 148 input patches of a wave are re-read from L2 by the three following phases.
+// Returns false once the CTA has run out of spatial tiles (only ever at the end of its loop: every role breaks at the same index).
+__device__ __forceinline__ bool map_tile(const TcParams &P, int v, int &tile)
+{
+    tile = v;
+    if (!P.phase_inner) return true;
+    const int k = v / (int)gridDim.x;
+    const int w = k / P.n_phases, p = k - w * P.n_phases;
+    const int sp = w * (int)gridDim.x + (int)blockIdx.x;
+    tile = p * P.tiles_per_phase + sp;
+    return sp < P.tiles_per_phase;
+}
 
 __device__ __forceinline__ void load16f(const float *sm, float *o)
 {
@@ -693,8 +712,10 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                 uint32_t st[2] = {0, 0}, ph[2] = {0, 0};
                 uint32_t r = 0;
                 const uint32_t rtoggle = P.issuers == 2 ? 1u : 0u;
-                for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti.advance(P), r ^= rtoggle) {
-                    if (kPair) ti.init(P, tile);
+                for (int v = blockIdx.x; v < P.n_virtual; v += gridDim.x, ti.advance(P), r ^= rtoggle) {
+                    int tile;
+                    if (!map_tile(P, v, tile)) break;
+                    if (kPair || P.phase_inner) ti.init(P, tile);
                     const TileCoord t = ti.coord(P);
                     const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
                     const int g_end = P.group_begin[t.phase + 1];
@@ -703,7 +724,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                         const Group G = P.groups[gi];
                         const int ax = cx + G.ox, ay = cy + G.oy;
                         for (int kc = 0; kc < kchunks; ++kc) {
-                            const bool live = !(dbg_no_tma && (phase_r != 0 || tile >= (int)(blockIdx.x + 2 * gridDim.x)));
+                            const bool live = !(dbg_no_tma && (phase_r != 0 || v >= (int)(blockIdx.x + 2 * gridDim.x)));
                             const uint32_t slot = r * nA + stage_r;
                             const uint32_t dst = smem0 + slot * abytes;
                             mbar_wait_a(empty0 + slot * 8, phase_r ^ 1);
@@ -726,8 +747,10 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                     st[r] = stage_r; ph[r] = phase_r;
                 }
             } else
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti.advance(P)) {
-                if (kPair) ti.init(P, tile);
+            for (int v = blockIdx.x; v < P.n_virtual; v += gridDim.x, ti.advance(P)) {
+                int tile;
+                if (!map_tile(P, v, tile)) break;
+                if (kPair || P.phase_inner) ti.init(P, tile);
                 const TileCoord t = ti.coord(P);
                 const int cx = t.x0 * P.a_sx, cy = t.y0 * P.a_sy;
                 const int tp_end = P.phase_begin[t.phase + 1];
@@ -742,9 +765,9 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                             if (kc < kchunks1) tma_load_4d_pair_a(&P.tmA, fb, a_s, kc * 64, ax, ay, t.b);
                             else tma_load_4d_pair_a(&P.tmA2, fb, a_s, (kc - kchunks1) * 64, ax, ay, t.b);
                             tma_load_2d_pair_a(&P.tmB, fb, a_s + kABytes, kc * 64, brow);
-                        } else if (dbg_no_tma && (phase != 0 || tile != (int)blockIdx.x)) {   // profiling: MMA-only rate
+                        } else if (dbg_no_tma && (phase != 0 || v != (int)blockIdx.x)) {   // profiling: MMA-only rate
                             mbar_arrive_a(full0 + stage * 8);
-                        } else if (P.debug >= 4 && (phase != 0 || tile != (int)blockIdx.x)) {
+                        } else if (P.debug >= 4 && (phase != 0 || v != (int)blockIdx.x)) {
                             // profiling: 4 = no A loads after priming, 5 = no B loads (which operand stream bounds the layer?)
                             const uint32_t fb = full0 + stage * 8;
                             mbar_expect_tx_a(fb, P.debug == 4 ? sbytes - kABytes : (uint32_t)kABytes);
@@ -778,10 +801,11 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             const bool dbg_no_tma = P.debug == 1;
             uint32_t st[2] = {0, 0}, ph[2] = {0, 0};
             uint32_t r = 0;
-            int tphase = 0, next_phase_tile = P.tiles_per_phase;
             const uint32_t rtoggle = P.issuers == 2 ? 1u : 0u;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, r ^= rtoggle) {
-                while (tile >= next_phase_tile) { ++tphase; next_phase_tile += P.tiles_per_phase; }
+            for (int v = blockIdx.x; v < P.n_virtual; v += gridDim.x, r ^= rtoggle) {
+                int tile;
+                if (!map_tile(P, v, tile)) break;
+                const int tphase = tile / P.tiles_per_phase;
                 int n0 = 0;
                 if (P.n_blocks > 1) n0 = ((tile - tphase * P.tiles_per_phase) % P.n_blocks) * P.Ntile;
                 const int brow_off = n0 + (kPair ? (int)rank * half_n : 0);
@@ -792,7 +816,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                     for (int kc = 0; kc < kchunks; ++kc) {
                         for (int j = 0; j < ntaps; ++j) {
                             const int brow = P.gbrow[tap0 + j] + brow_off;
-                            const bool live = !(dbg_no_tma && (bphase != 0 || tile >= (int)(blockIdx.x + 2 * gridDim.x)));
+                            const bool live = !(dbg_no_tma && (bphase != 0 || v >= (int)(blockIdx.x + 2 * gridDim.x)));
                             const uint32_t slot = r * nB + bi;
                             const uint32_t dst = b_s0 + slot * bbytes;
                             mbar_wait_a(bempty0 + slot * 8, bphase ^ 1);
@@ -842,12 +866,13 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             const uint32_t g_full0 = smem_u32(&full_bar[0]) + g_ring * g_nA * 8, g_empty0 = smem_u32(&empty_bar[0]) + g_ring * g_nA * 8;
             uint32_t g_bi = 0, g_bphase = 0, g_boff16 = 0;
             if (resident) mbar_wait(&bres_bar, 0);
-            int tphase = 0, next_phase_tile = P.tiles_per_phase;   // tiles are phase-major: the phase changes every tiles_per_phase tiles
             uint32_t acc_i = 0, acc_ph = 0;
             const uint32_t my_parity = warp == 3 ? 1u : 0u;
             uint32_t it_par = 0;
-            for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, it_par ^= 1) {
-                while (tile >= next_phase_tile) { ++tphase; next_phase_tile += P.tiles_per_phase; }
+            for (int v = blockIdx.x; v < P.n_virtual; v += gridDim.x, it_par ^= 1) {
+                int tile;
+                if (!map_tile(P, v, tile)) break;
+                const int tphase = tile / P.tiles_per_phase;
                 const int nkb = (P.phase_begin[tphase + 1] - P.phase_begin[tphase]) * kchunks;
                 if (P.grouped && P.issuers == 2 && it_par != my_parity) {
                     // the other issuer's tile (it has its own operand rings): only the accumulator ring is shared
@@ -971,8 +996,10 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
                 sc_out[i] = ((int64_t)c * P.Ho + ay * P.out_stride) * P.Wo + ax * P.out_stride;
             }
         }
-        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
-            if (kPair) ti.init(P, tile);
+        for (int v = blockIdx.x; v < P.n_virtual; v += gridDim.x, ++it, ti.advance(P), acc_ph ^= (acc_i + 1 == P.acc_stages), acc_i = (acc_i + 1 == P.acc_stages) ? 0 : acc_i + 1) {
+            int tile;
+            if (!map_tile(P, v, tile)) break;
+            if (kPair || P.phase_inner) ti.init(P, tile);
             // col2im epilogue: kParts (2-4) independent teams of 4 warps (one warp per TMEM lane quarter) take tiles round robin, each
             // with its own staging buffer and named barrier, so that one team's TMEM / shared-memory latencies overlap the others' work
             // (a team is a serial chain of dependent latencies: with two teams the layer ran at ~0.3 instructions per scheduler cycle).
@@ -1387,7 +1414,12 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         Q.num_stages = stages;
         smem = fixed + (size_t)stages * stage_bytes;
     }
-    int grid = Q.total_tiles < kNumSMs ? Q.total_tiles : kNumSMs;
+    // phase_inner: a CTA's index selects its spatial tiles, every CTA walks all phases (map_tile)
+    const int work = Q.phase_inner ? Q.tiles_per_phase : Q.total_tiles;
+    int grid = work < kNumSMs ? work : kNumSMs;
+    auto set_virtual = [&](int g) {
+        Q.n_virtual = Q.phase_inner ? ((Q.tiles_per_phase + g - 1) / g) * Q.n_phases * g : Q.total_tiles;
+    };
     if (const char *g = getenv("MMC_TC_DEBUG")) Q.debug = atoi(g);
     Q.direct_store = 1;   // measured: g_a.0 1.04 -> 0.99 ms, g_s.2 0.38 -> 0.37 ms vs the staged, coalesced copy-out (MMC_TC_GDN_DIRECT=0)
     if (const char *g = getenv("MMC_TC_GDN_DIRECT")) Q.direct_store = atoi(g);
@@ -1438,12 +1470,14 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
         if (grid > 2 * max_pairs) grid = 2 * max_pairs;
         if (grid < 2) grid = 2;
         cfg.gridDim = dim3(grid);
+        set_virtual(grid);
         MMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams>, Q));
         count_launch();
         return MMC_OK;
     }
     cfg.numAttrs = nattr;
     cfg.gridDim = dim3(grid);
+    set_virtual(grid);
     MMC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<kEpi, kNCH, kPair, kParts, kTeams>, Q));
     count_launch();
     return MMC_OK;
@@ -1651,6 +1685,18 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
     MMC_CHECK_ARG(tpp * P.n_phases < (1ll << 31), "%s: too many tiles", name);
     P.tiles_per_phase = (int)tpp;
     P.total_tiles = (int)(tpp * P.n_phases);
+    // Transposed convolutions with enough spatial tiles for many waves: run the stride^2 phases of a wave back to back, so that the
+    // input is read from HBM once instead of once per phase (map_tile).  Small layers keep the phase-major order: it spreads
+    // phases x tiles over the SMs, the other order only tiles.  MMC_TC_PHASE_INNER=0 / 1: never / whenever there are phases.
+    // The phases of the LAST wave run on a partly empty machine, so the order pays only when that wave is a small part of the layer:
+    // cfg 2, batch 64: g_s.4 (12 288 spatial tiles) 1.397 -> 1.343 ms, DRAM reads 1.61 -> 0.40 GB; g_s.2 (3 072) 0.334 -> 0.332 ms,
+    // 0.40 -> 0.10 GB; g_s.0 (768 tiles = 5.2 waves) 0.105 -> 0.122 ms, hence the 4 % rule.
+    {
+        const int64_t waves = (tpp + kNumSMs - 1) / kNumSMs;
+        P.phase_inner = (pl.mode == MODE_STD && pl.n_phases > 1 && waves * kNumSMs * 100 <= tpp * 104) ? 1 : 0;
+    }
+    if (const char *g = getenv("MMC_TC_PHASE_INNER")) P.phase_inner = (pl.mode == MODE_STD && pl.n_phases > 1 && atoi(g) != 0) ? 1 : 0;
+    MMC_CHECK_ARG((tpp + kNumSMs) * P.n_phases < (1ll << 31), "%s: too many tiles", name);
     // GDN kernels only: for the plain bias / activation epilogue the extra MMA and the shared memory of the constant tiles cost more
     // than the 16 adds per chunk they replace (measured on ssf2020: 12.8 -> 14.1 ms per GOP with it)
     P.bias_mma = (d->gdn != MMC_GDN_NONE) ? 1 : 0;

@@ -72,13 +72,12 @@ WORKLOAD = WORKLOADS["hyperprior"][6]
 
 
 # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the default workload's largest kernels, from the
-# committed `ncu --set full` capture profiles/r02_ncu_conv_tc_full_v2.csv (batch 64 x 768x512).  NOT equal to the algorithmic bytes
-# for the transposed convolutions: their four output phases each stream the input once (tiles are phase-major), so g_s.4 reads
-# 1.61 GB for a 0.40 GB input (algorithmic: 0.40 + 1.57 GB = 1.97 GB, measured 3.18 GB = 1.6x); the strided convolutions and the
-# edge layers read their input once.
-NCU_DRAM_BYTES = {"g_s.4|tc": 1.614860e9 + 1.570030e9, "g_a.2|tc": 1.616450e9 + 0.390040e9, "g_a.0|tc": 0.408460e9 + 1.559840e9,
-                  "g_s.6|tc": 1.620720e9 + 0.290400e9, "g_s.2|tc": 0.401640e9 + 0.361080e9}
-NCU_SOURCE = "profiles/r02_ncu_conv_tc_full_v2.csv (ncu --set full, profiles/_fwd_once.py, bytes per launch; round-end default path)"
+# committed ncu capture profiles/r02_ncu_conv_phase_inner.csv (batch 64 x 768x512, round-end default path).  With the phase-inner
+# tile order the large transposed convolutions read their input from HBM once (g_s.4: 0.404 GB read for a 0.403 GB input,
+# 1.553 GB written: 1.96 GB against 1.97 GB algorithmic; before: 1.61 GB read, 3.18 GB in total = 1.6x).
+NCU_DRAM_BYTES = {"g_s.4|tc": 0.403608e9 + 1.553492e9, "g_a.2|tc": 1.612e9 + 0.384e9, "g_a.0|tc": 0.408e9 + 1.557e9,
+                  "g_s.6|tc": 1.622228e9 + 0.287555e9, "g_s.2|tc": 0.101597e9 + 0.345687e9}
+NCU_SOURCE = "profiles/r02_ncu_conv_phase_inner.csv (ncu dram__bytes_read/write.sum per launch, profiles/_fwd_once.py; round-end default path)"
 
 
 def shard_range(total: int, rank: int, world: int):
