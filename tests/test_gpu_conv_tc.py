@@ -261,3 +261,72 @@ def test_two_source_conv_equals_concatenation(kind, c1, c2, cout, k, s, gdn):
         want = run_layers(layers, torch.cat((x1, x2), dim=-1), "nhwc_bf16", out_fmt)
         got = run_layers(layers, (x1, x2), "nhwc_bf16", out_fmt)
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("cin,cout,gdn,h,w,B,pair", [
+    (128, 128, L.GDN_INVERSE, 40, 56, 3, "0"),     # single-CTA kernel, ragged tiles
+    (32, 128, L.GDN_INVERSE, 64, 96, 4, "2"),      # CTA-pair kernel, 192 spatial tiles: more than one wave of 148
+    (192, 128, L.GDN_NONE, 17, 23, 2, "0"),        # plain epilogue, odd sizes
+])
+def test_phase_inner_tile_order_is_bit_identical(cin, cout, gdn, h, w, B, pair):
+    """MMC_TC_PHASE_INNER=1 (the stride^2 output phases of a wave of spatial tiles run back to back: the input is read from HBM once)
+    only reorders the tiles of a transposed convolution: outputs are bit-identical to the phase-major order, and within the bf16
+    tolerance of the oracle.  The default rule switches it on for layers of many waves only, so it is forced here."""
+    import os
+    rs = np.random.RandomState(cin + cout + h)
+    k, s = 5, 2
+    x = bf16_round(rs.standard_normal((B, cin, h, w)).astype(np.float32))
+    wt = bf16_round((rs.standard_normal((cin, cout, k, k)) * (2.0 / np.sqrt(cin * k * k / (s * s)))).astype(np.float32))
+    b = rs.standard_normal(cout).astype(np.float32)
+    gw = {}
+    _gdn(rs, gw, "g", cout)
+    beta_eff = gamma_bf16 = None
+    if gdn != L.GDN_NONE:
+        beta_eff, _, gamma_bf16 = ops.gdn_reparam(torch.from_numpy(gw["g.beta"]).to(dev()), torch.from_numpy(gw["g.gamma"]).to(dev()),
+                                                  oracle.gdn_beta_bound(), oracle.GDN_GAMMA_BOUND, oracle.GDN_PEDESTAL, want_bf16=True)
+    xin = torch.from_numpy(x).to(dev()).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    d = ops.conv_desc(True, B, h, w, cin, cout, k, s, L.BF16, L.NHWC, L.BF16, L.NHWC, gdn=gdn)
+    packed = ops.conv_pack_weights(d, torch.from_numpy(wt).to(dev()))
+    outs = {}
+    for inner in ("0", "1"):
+        env = {"MMC_TC_PHASE_INNER": inner, "MMC_TC_PAIR": pair}
+        os.environ.update(env)
+        try:
+            outs[inner] = ops.conv_forward_tc(d, xin, packed, torch.from_numpy(b).to(dev()), beta_eff, gamma_bf16).float()
+            torch.cuda.synchronize()
+        finally:
+            for k_ in env:
+                os.environ.pop(k_, None)
+    assert torch.equal(outs["0"], outs["1"])
+    ref = oracle.conv_transpose2d(x, wt, b, stride=s, act=None)
+    if gdn != L.GDN_NONE:
+        ref = oracle.gdn_forward(ref, gw["g.beta"], gw["g.gamma"], inverse=True)
+    yy = outs["1"].permute(0, 3, 1, 2).cpu().numpy()
+    assert np.abs(yy - ref).max() < 1e-2 * float(np.abs(ref).max())
+
+
+@pytest.mark.parametrize("teams", ["2", "3", "4"])
+def test_reconstruction_layer_team_counts(teams):
+    """The col2im epilogue of the reconstruction layer with 2 / 3 / 4 teams of four warps (MMC_TC_SCATTER_TEAMS; default 3): every
+    team count gives the same bits (each output pixel is summed by one thread in a fixed order), at more than one wave of tiles."""
+    import os
+    rs = np.random.RandomState(11)
+    B, cin, cout, k, s, h, w = 3, 128, 3, 5, 2, 70, 90           # 12 x 7 x 3 = 252 overlapping tiles, ragged right / bottom edges
+    x = bf16_round(rs.standard_normal((B, cin, h, w)).astype(np.float32))
+    wt = bf16_round((rs.standard_normal((cin, cout, k, k)) * (2.0 / np.sqrt(cin * k * k / 4))).astype(np.float32))
+    b = rs.standard_normal(cout).astype(np.float32)
+    xin = torch.from_numpy(x).to(dev()).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    d = ops.conv_desc(True, B, h, w, cin, cout, k, s, L.BF16, L.NHWC, L.F32, L.NCHW)
+    packed = ops.conv_pack_weights(d, torch.from_numpy(wt).to(dev()))
+    outs = {}
+    for t in ("default", teams):
+        if t != "default":
+            os.environ["MMC_TC_SCATTER_TEAMS"] = t
+        try:
+            outs[t] = ops.conv_forward_tc(d, xin, packed, torch.from_numpy(b).to(dev()))
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("MMC_TC_SCATTER_TEAMS", None)
+    assert torch.equal(outs["default"], outs[teams])
+    ref = oracle.conv_transpose2d(x, wt, b, stride=s, act=None)
+    assert np.abs(outs[teams].cpu().numpy() - ref).max() < 2e-3 * float(np.abs(ref).max())
