@@ -110,6 +110,7 @@ struct TcParams {
     int act, gdn, out_f32, out2;
     int gdn_chunk;
     int tiles_per_phase, total_tiles;
+    int epi_pipe;        // GDN epilogue software-pipelined over two tiles (epilogue_gdn_pipe)
     int phase_inner;     // transposed convolutions: the stride^2 output phases of a wave of spatial tiles run back to back (see map_tile)
     int n_virtual;       // bound of the persistent loops' running index (== total_tiles unless phase_inner)
     int st_nb, st_tx, st_ty, st_b, st_ph;   // gridDim.x decomposed in the radices (n_blocks, tiles_x, tiles_y, B, phase)
@@ -555,6 +556,176 @@ __device__ __forceinline__ void epilogue_gdn_rows(const GdnCtx &g, uint32_t &gdn
 
 
 // ---------------------------------------------------------------------------------------------
+// Software-pipelined GDN / IGDN epilogue (single team, C <= 128, bf16 NHWC output without secondary outputs).
+// epilogue_gdn is a serial chain per tile: read x, square, norm MMAs, WAIT for them (behind whatever the main loop has queued in the
+// in-order tensor pipe: ~20 % of the chain, ncu source view of g_a.0), read the norm, scale, store; the chain -- 5.1k cycles per tile
+// in g_a.0, 6.4k in g_s.4 -- bounds every fused layer whose main loop is shorter.  Here the wait of tile i is filled with pass 1 of
+// tile i + 1:
+//     pass 1 (i + 1): x -> bf16 pairs in registers (32 instead of 64 registers, which is what lets two tiles be in flight),
+//                     x^2 -> TMEM operand block (i + 1) & 1
+//     wait norm(i);  pass 2 (i): y = x * rsqrt(norm) (IGDN: * sqrt), 256-bit stores
+//     one team barrier;  norm MMAs (i + 1) issued, accumulator stage (i + 1) handed back
+// TMEM: 2 accumulator stages + norm + two x^2 operand blocks = 2 C + C + 2 C / 2 = 512 columns at C = 128.  One team barrier per
+// tile instead of three.  x is rounded to bf16 BEFORE the scaling (the output is bf16 either way): |y - y_ref| <= 2^-8 |y| instead of
+// 2^-9, inside the 1e-2 bf16 tolerance of BASELINE.json; the norm itself is computed from the fp32 x as before.
+// Tried: the second warp of every TMEM lane quarter running the two passes in the opposite order (to keep the quarter's tcgen05.ld
+// port busy while the other warp is in its MUFU / store phase) -- g_a.0 0.78 -> 1.2 ms: that warp starts with the norm wait.
+// ---------------------------------------------------------------------------------------------
+struct PipeTile {
+    int64_t pix_off;
+    int as;
+    uint32_t aphase;
+    bool valid;
+};
+
+template <int NCH, bool kPair, int kParts>
+__device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tmem_base, uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar,
+                                                  uint64_t *gdn_bar, uint64_t *gload_bar, const uint8_t *sG, uint32_t s_ones, uint32_t s_beta)
+{
+    constexpr int kEpiThreads = 128 * kParts;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = warp & 3, half = (warp - kSvcWarps) >> 2;
+    const int row = q * 32 + lane, th = row / P.TW, tw = row - th * P.TW;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t norm_col = (uint32_t)(P.acc_stages * P.Ntile), a_col0 = norm_col + (uint32_t)P.gdn_chunk;
+    const bool first_warp = warp == kSvcWarps, inverse = P.gdn == MMC_GDN_INVERSE;
+    const uint32_t empty_leader = kPair ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    const uint32_t idesc = make_idesc(P.Ntile), gm = smem_u32(sG);
+    uint32_t gdn_phase = 0;
+    auto chunk_of = [&](int j) { return half * NCH + j; };
+
+    // tile -> coordinates, accumulator stage (ring position of the it-th tile of this CTA)
+    int acc_i = 0;
+    uint32_t acc_ph = 0;
+    auto setup = [&](int tile, PipeTile &t) {
+        TileIter ti;
+        ti.init(P, tile);
+        const TileCoord c = ti.coord(P);
+        const int gy = c.y0 + th, gx = c.x0 + tw;
+        const int py = c.phase / P.out_stride, px = c.phase - py * P.out_stride;
+        t.valid = gy < P.Gh && gx < P.Gw && c.b < P.B;
+        t.pix_off = (((int64_t)c.b * P.Ho + gy * P.out_stride + py) * P.Wo + gx * P.out_stride + px) * P.Cout + c.n0;
+        t.as = acc_i; t.aphase = acc_ph;
+        if (++acc_i == P.acc_stages) { acc_i = 0; acc_ph ^= 1; }
+    };
+    // pass 1: x -> packed bf16 registers, x^2 -> operand block r
+    auto pass1 = [&](const PipeTile &t, uint32_t r, uint32_t (&xp)[NCH * 8]) {
+        mbar_wait(&tmem_full_bar[t.as], t.aphase);
+        tc_fence_after();
+        const uint32_t acc = lane_base + (uint32_t)(t.as * P.Ntile), a_col = a_col0 + r * (uint32_t)(P.Cout / 2);
+#pragma unroll
+        for (int j = 0; j < NCH; j += 2) {
+            float x[2][16];
+            tmem_ld16(acc + (uint32_t)(chunk_of(j) << 4), x[0]);
+            tmem_ld16(acc + (uint32_t)(chunk_of(j + 1) << 4), x[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int c0 = chunk_of(j + u) << 4;
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    pk[i] = pack_bf16(x[u][2 * i] * x[u][2 * i], x[u][2 * i + 1] * x[u][2 * i + 1]);
+                    xp[(j + u) * 8 + i] = pack_bf16(x[u][2 * i], x[u][2 * i + 1]);
+                }
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(lane_base + a_col + (uint32_t)(c0 >> 1)),
+                             "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+            }
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+    };
+    // norm MMAs of a tile (team's first warp, after the team barrier): norm = x^2 gamma'^T + beta', then the accumulator stage goes back
+    bool gamma_ready = false;
+    auto issue_norm = [&](const PipeTile &t, uint32_t r) {
+        if (!first_warp) return;
+        if (!gamma_ready) { mbar_wait(gload_bar, 0); gamma_ready = true; }
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t a_col = a_col0 + r * (uint32_t)(P.Cout / 2);
+#pragma unroll
+            for (int kc = 0; kc < NCH * kParts / 4; ++kc) {
+                const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * P.Cout * 128));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma_ts(tmem_base + norm_col, tmem_base + a_col + (uint32_t)((kc * 4 + k) * 8), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+            }
+            tc_mma(tmem_base + norm_col, make_desc_ns(s_ones), make_desc_ns(s_beta), idesc, 1);
+            tc_commit(gdn_bar);
+            // every thread of the team read this tile's accumulator before the barrier that precedes this call
+            if (kPair) mbar_arrive_cluster(empty_leader + (uint32_t)(t.as * sizeof(uint64_t)));
+            else mbar_arrive(&tmem_empty_bar[t.as]);
+        }
+        __syncwarp();
+    };
+    // pass 2: y = x * rsqrt(norm) (IGDN: * sqrt), straight from registers to global memory
+    auto pass2 = [&](const PipeTile &t, const uint32_t (&xp)[NCH * 8]) {
+        mbar_wait(gdn_bar, gdn_phase);
+        gdn_phase ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int jb = 0; jb < NCH; jb += 2) {
+            float nrm[2][16];
+            tmem_ld16(lane_base + norm_col + (uint32_t)(chunk_of(jb) << 4), nrm[0]);
+            tmem_ld16(lane_base + norm_col + (uint32_t)(chunk_of(jb + 1) << 4), nrm[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                uint32_t o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t w = xp[(jb + u) * 8 + i];
+                    const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+                    const float n0 = nrm[u][2 * i], n1 = nrm[u][2 * i + 1];
+                    o[i] = pack_bf16(x0 * (inverse ? sqrt_fast(n0) : rsqrt_fast(n0)), x1 * (inverse ? sqrt_fast(n1) : rsqrt_fast(n1)));
+                }
+                if (t.valid) {
+                    __nv_bfloat16 *dst = (__nv_bfloat16 *)P.y + t.pix_off + (chunk_of(jb + u) << 4);
+                    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+                }
+            }
+        }
+        tc_fence_before();
+    };
+    auto team_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
+
+    int v = blockIdx.x, tile;
+    if (v >= P.n_virtual || !map_tile(P, v, tile)) return;
+    PipeTile cur, nxt;
+    uint32_t xa[NCH * 8], xb[NCH * 8];
+    uint32_t r = 0;
+    setup(tile, cur);
+    pass1(cur, r, xa);
+    team_barrier();
+    issue_norm(cur, r);
+    for (;;) {
+        // invariant: xa holds tile `cur`, whose norm MMAs have been issued from operand block r
+        v += gridDim.x;
+        const bool more = v < P.n_virtual && map_tile(P, v, tile);
+        if (more) {
+            setup(tile, nxt);
+            pass1(nxt, r ^ 1, xb);
+        }
+        pass2(cur, xa);
+        if (!more) break;
+        team_barrier();                       // norm(cur) consumed by every thread, x^2(nxt) complete
+        issue_norm(nxt, r ^ 1);
+        // roles swap: the compiler keeps xa / xb in registers because the loop is unrolled by two below
+        v += gridDim.x;
+        const bool more2 = v < P.n_virtual && map_tile(P, v, tile);
+        if (more2) {
+            setup(tile, cur);
+            pass1(cur, r, xa);
+        }
+        pass2(nxt, xb);
+        if (!more2) break;
+        team_barrier();
+        issue_norm(cur, r);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // col2im gather of the reconstruction layer (MODE_SCATTER, k = 5, stride 2), on raw shared-memory addresses.
 // Round 2 (ncu source view of g_s.6, profiles/r02_ncu_scatter_source.txt): the first version walked generic pointers -- every one
 // of the 25 product loads of a work item carried its own 64-bit address arithmetic (LEA / IMAD.WIDE / LD), and the item -> (pixel,
@@ -960,6 +1131,10 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             }
         }
         __syncwarp();
+    } else if (warp >= kSvcWarps && kEpi == EPI_GDN && kTeams == 1 && (kNCH == 4 || kNCH == 2) && P.epi_pipe) {
+        // ===================== epilogue, software-pipelined over two tiles (GDN, C <= 128) ============
+        if constexpr (kEpi == EPI_GDN && kTeams == 1 && (kNCH == 4 || kNCH == 2))
+            epilogue_gdn_pipe<kNCH, kPair, kParts>(P, tmem_base, tmem_full_bar, tmem_empty_bar, &gdn_bar[0], &gload_bar, sG, smem_u32(s_ones), smem_u32(s_betaB));
     } else if (warp >= kSvcWarps) {
         // ===================== epilogue: 8 warps, 2 per TMEM lane quarter, each pair splits the columns ============
         const int q = warp & 3;                 // TMEM lane quarter this warp can access
@@ -1426,6 +1601,7 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
     if (Q.a_tmem) Q.direct_store = 1;    // no shared-memory x^2 tile to stage the copy-out in
     Q.late_release = 1;
     if (const char *g = getenv("MMC_TC_LATE_RELEASE")) Q.late_release = atoi(g) != 0;   // 0: round-1 behaviour (measurement aid)
+    if (Q.epi_pipe) Q.late_release = 1;  // the pipelined epilogue hands the accumulator back from the norm-issuing thread (one arrival)
     if (const char *g = getenv("MMC_TC_GRID")) {   // profiling aid: restrict the persistent grid (profiles/probe_grid.py)
         int v = atoi(g);
         if (v >= 1 && v < grid) grid = v;
@@ -1716,6 +1892,18 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
     if (const char *g = getenv("MMC_TC_TEAMS")) teams = atoi(g) == 2;
     teams = teams && d->gdn != MMC_GDN_NONE && !P.pair && (d->Cout == 64 || d->Cout == 128) && P.Ntile == d->Cout;
     if (teams) { P.acc_stages = 3; P.a_tmem = 1; P.gdn_chunk = 0; }
+    // Software-pipelined GDN epilogue (epilogue_gdn_pipe): C in {64, 128}, bf16 NHWC output, no secondary output.  Two x^2 operand
+    // blocks in TMEM (2 x C / 2 columns) next to the norm block, which fit the 64 columns the single-team layout leaves free at C = 128 (2 accumulator
+    // stages either way).  MMC_TC_EPI_PIPE=0 / 1 overrides.
+    bool epi_pipe = true;     // measured (cfg 2, batch 64): g_a.0 0.859 -> 0.783 ms, g_s.2 0.330 -> 0.321, g_s.4 1.306 -> 1.289; step -2 %
+    if (const char *g = getenv("MMC_TC_EPI_PIPE")) epi_pipe = atoi(g) != 0;
+    epi_pipe = epi_pipe && d->gdn != MMC_GDN_NONE && !teams && P.a_tmem && (d->Cout == 64 || d->Cout == 128) && P.Ntile == d->Cout &&
+               !P.out_f32 && !P.out2 && pl.mode != MODE_SCATTER;
+    if (epi_pipe) {
+        P.epi_pipe = 1;
+        P.acc_stages = (512 - P.gdn_chunk - d->Cout) / P.Ntile;
+        if (P.acc_stages > kMaxAccStages) P.acc_stages = kMaxAccStages;
+    }
     // col2im epilogue teams (4 warps each).  Default 3: measured on cfg 2 (g_s.6, batch 64) -- see the table in DESIGN.md 4.1
     int sc_teams = 3;
     if (const char *g = getenv("MMC_TC_SCATTER_TEAMS")) { const int v = atoi(g); if (v >= 2 && v <= 4) sc_teams = v; }
@@ -1727,7 +1915,7 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
         P.acc_stages -= P.acc_stages % sc_teams;    // the col2im epilogue teams own the accumulator stages round robin
         MMC_UNSUPPORTED(P.acc_stages < 2, "%s: the reconstruction kernel needs two accumulator stages (N tile %d)", name, P.Ntile);
     }
-    MMC_UNSUPPORTED((teams ? 3 * P.Ntile + d->Cout : P.acc_stages * P.Ntile + P.gdn_chunk + (P.a_tmem ? d->Cout / 2 : 0)) > 512 || (P.gdn_chunk % 16) != 0,
+    MMC_UNSUPPORTED((teams ? 3 * P.Ntile + d->Cout : P.acc_stages * P.Ntile + P.gdn_chunk + (P.a_tmem ? (P.epi_pipe ? d->Cout : d->Cout / 2) : 0)) > 512 || (P.gdn_chunk % 16) != 0 || (P.epi_pipe && P.acc_stages < 2),
                     "%s: TMEM budget exceeded", name);
 
     size_t fixed = 1024;  // alignment slack

@@ -219,8 +219,13 @@ def test_opt_in_main_loop_and_epilogue_variants(transposed, cin, cout, k, s, gdn
     d = ops.conv_desc(transposed, B, h, w, cin, cout, k, s, L.BF16, L.NHWC, L.BF16, L.NHWC, gdn=gdn)
     packed = ops.conv_pack_weights(d, torch.from_numpy(wt).to(dev()))
     outs = {}
-    for name, env in (("default", {}), ("teams", {"MMC_TC_TEAMS": "2"}), ("grouped", {"MMC_TC_GROUPED": "1"}),
-                      ("both", {"MMC_TC_GROUPED": "1", "MMC_TC_TEAMS": "2"}), ("both+pair", {"MMC_TC_GROUPED": "1", "MMC_TC_TEAMS": "2", "MMC_TC_PAIR": "2"})):
+    # "default" here = the single-team epilogue WITHOUT the two-tile software pipeline (MMC_TC_EPI_PIPE=0), which keeps x in fp32
+    # registers like the teams epilogue does; "pipe" = the round-end default (x held as bf16 pairs across the norm contraction)
+    nopipe = {"MMC_TC_EPI_PIPE": "0"}
+    for name, env in (("default", dict(nopipe)), ("teams", {"MMC_TC_TEAMS": "2", **nopipe}), ("grouped", {"MMC_TC_GROUPED": "1", **nopipe}),
+                      ("both", {"MMC_TC_GROUPED": "1", "MMC_TC_TEAMS": "2", **nopipe}),
+                      ("both+pair", {"MMC_TC_GROUPED": "1", "MMC_TC_TEAMS": "2", "MMC_TC_PAIR": "2", **nopipe}),
+                      ("pipe", {"MMC_TC_EPI_PIPE": "1"}), ("pipe+pair", {"MMC_TC_EPI_PIPE": "1", "MMC_TC_PAIR": "2"})):
         os.environ.update(env)
         try:
             outs[name] = ops.conv_forward_tc(d, xin, packed, torch.from_numpy(b).to(dev()), beta_eff, gamma_bf16).float()
@@ -237,6 +242,12 @@ def test_opt_in_main_loop_and_epilogue_variants(transposed, cin, cout, k, s, gdn
         assert np.abs(yy - ref).max() < 1e-2 * float(np.abs(ref).max()), name
     assert float((outs["grouped"] - outs["default"]).abs().max()) <= 2e-2 * float(outs["default"].abs().max())
     assert torch.equal(outs["both"], outs["grouped"])
+    # the pipelined epilogue rounds x to bf16 before the scaling: at most one bf16 step (2^-8 relative) from the fp32-x result
+    assert torch.equal(outs["pipe"], outs["pipe+pair"])
+    if gdn != L.GDN_NONE:
+        assert float(((outs["pipe"] - outs["default"]).abs() / outs["default"].abs().clamp_min(1e-3)).max()) <= 2.0 ** -7
+    else:
+        assert torch.equal(outs["pipe"], outs["default"])
 
 
 @pytest.mark.parametrize("kind,c1,c2,cout,k,s,gdn", [
