@@ -613,20 +613,27 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
         mbar_wait(&tmem_full_bar[t.as], t.aphase);
         tc_fence_after();
         const uint32_t acc = lane_base + (uint32_t)(t.as * P.Ntile), a_col = a_col0 + r * (uint32_t)(P.Cout / 2);
+        // the loads of chunk pair j + 2 are in flight while pair j is squared and packed (tcgen05.wait::ld waits for ALL outstanding
+        // loads, so the pipeline is two deep: load, wait, load next, compute, wait, compute)
+        float x[2][2][16];
+        tmem_ld16(acc + (uint32_t)(chunk_of(0) << 4), x[0][0]);
+        tmem_ld16(acc + (uint32_t)(chunk_of(1) << 4), x[0][1]);
 #pragma unroll
         for (int j = 0; j < NCH; j += 2) {
-            float x[2][16];
-            tmem_ld16(acc + (uint32_t)(chunk_of(j) << 4), x[0]);
-            tmem_ld16(acc + (uint32_t)(chunk_of(j + 1) << 4), x[1]);
+            const int b = (j >> 1) & 1;
             tmem_ld_wait();
+            if (j + 2 < NCH) {
+                tmem_ld16(acc + (uint32_t)(chunk_of(j + 2) << 4), x[b ^ 1][0]);
+                tmem_ld16(acc + (uint32_t)(chunk_of(j + 3) << 4), x[b ^ 1][1]);
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const int c0 = chunk_of(j + u) << 4;
                 uint32_t pk[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    pk[i] = pack_bf16(x[u][2 * i] * x[u][2 * i], x[u][2 * i + 1] * x[u][2 * i + 1]);
-                    xp[(j + u) * 8 + i] = pack_bf16(x[u][2 * i], x[u][2 * i + 1]);
+                    pk[i] = pack_bf16(x[b][u][2 * i] * x[b][u][2 * i], x[b][u][2 * i + 1] * x[b][u][2 * i + 1]);
+                    xp[(j + u) * 8 + i] = pack_bf16(x[b][u][2 * i], x[b][u][2 * i + 1]);
                 }
                 asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(lane_base + a_col + (uint32_t)(c0 >> 1)),
                              "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
@@ -663,12 +670,17 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
         mbar_wait(gdn_bar, gdn_phase);
         gdn_phase ^= 1;
         tc_fence_after();
+        float nrm[2][2][16];
+        tmem_ld16(lane_base + norm_col + (uint32_t)(chunk_of(0) << 4), nrm[0][0]);
+        tmem_ld16(lane_base + norm_col + (uint32_t)(chunk_of(1) << 4), nrm[0][1]);
 #pragma unroll
         for (int jb = 0; jb < NCH; jb += 2) {
-            float nrm[2][16];
-            tmem_ld16(lane_base + norm_col + (uint32_t)(chunk_of(jb) << 4), nrm[0]);
-            tmem_ld16(lane_base + norm_col + (uint32_t)(chunk_of(jb + 1) << 4), nrm[1]);
+            const int b = (jb >> 1) & 1;
             tmem_ld_wait();
+            if (jb + 2 < NCH) {
+                tmem_ld16(lane_base + norm_col + (uint32_t)(chunk_of(jb + 2) << 4), nrm[b ^ 1][0]);
+                tmem_ld16(lane_base + norm_col + (uint32_t)(chunk_of(jb + 3) << 4), nrm[b ^ 1][1]);
+            }
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 uint32_t o[8];
@@ -676,7 +688,7 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
                 for (int i = 0; i < 8; ++i) {
                     const uint32_t w = xp[(jb + u) * 8 + i];
                     const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
-                    const float n0 = nrm[u][2 * i], n1 = nrm[u][2 * i + 1];
+                    const float n0 = nrm[b][u][2 * i], n1 = nrm[b][u][2 * i + 1];
                     o[i] = pack_bf16(x0 * (inverse ? sqrt_fast(n0) : rsqrt_fast(n0)), x1 * (inverse ? sqrt_fast(n1) : rsqrt_fast(n1)));
                 }
                 if (t.valid) {
