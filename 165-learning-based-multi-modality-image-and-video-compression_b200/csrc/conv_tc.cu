@@ -700,6 +700,80 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
         }
         tc_fence_before();
     };
+    // pass 1 of tile n chained with pass 2 of tile c: the first norm loads of c are issued before the last chunk pair of n is squared,
+    // so the TMEM read port has work during that arithmetic as well
+    auto square_pack = [&](const float (&xv)[2][16], int j, uint32_t a_col, uint32_t (&xp)[NCH * 8]) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c0 = chunk_of(j + u) << 4;
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                pk[i] = pack_bf16(xv[u][2 * i] * xv[u][2 * i], xv[u][2 * i + 1] * xv[u][2 * i + 1]);
+                xp[(j + u) * 8 + i] = pack_bf16(xv[u][2 * i], xv[u][2 * i + 1]);
+            }
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(lane_base + a_col + (uint32_t)(c0 >> 1)),
+                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+        }
+    };
+    auto scale_store = [&](const PipeTile &t, const float (&nv)[2][16], int jb, const uint32_t (&xp)[NCH * 8]) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t w = xp[(jb + u) * 8 + i];
+                const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+                const float n0 = nv[u][2 * i], n1 = nv[u][2 * i + 1];
+                o[i] = pack_bf16(x0 * (inverse ? sqrt_fast(n0) : rsqrt_fast(n0)), x1 * (inverse ? sqrt_fast(n1) : rsqrt_fast(n1)));
+            }
+            if (t.valid) {
+                __nv_bfloat16 *dst = (__nv_bfloat16 *)P.y + t.pix_off + (chunk_of(jb + u) << 4);
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                             "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+            }
+        }
+    };
+    auto fused = [&](const PipeTile &c, const uint32_t (&xc)[NCH * 8], const PipeTile &n, uint32_t rn, uint32_t (&xn)[NCH * 8]) {
+        mbar_wait(&tmem_full_bar[n.as], n.aphase);
+        tc_fence_after();
+        const uint32_t acc = lane_base + (uint32_t)(n.as * P.Ntile), a_col = a_col0 + rn * (uint32_t)(P.Cout / 2);
+        const uint32_t nb = lane_base + norm_col;
+        float buf[2][2][16];
+        tmem_ld16(acc + (uint32_t)(chunk_of(0) << 4), buf[0][0]);
+        tmem_ld16(acc + (uint32_t)(chunk_of(1) << 4), buf[0][1]);
+        // ---- pass 1 (n): all chunk pairs but the last ----
+#pragma unroll
+        for (int j = 0; j + 2 < NCH; j += 2) {
+            const int b = (j >> 1) & 1;
+            tmem_ld_wait();
+            tmem_ld16(acc + (uint32_t)(chunk_of(j + 2) << 4), buf[b ^ 1][0]);
+            tmem_ld16(acc + (uint32_t)(chunk_of(j + 3) << 4), buf[b ^ 1][1]);
+            square_pack(buf[b], j, a_col, xn);
+        }
+        constexpr int bl = ((NCH - 2) >> 1) & 1;       // buffer of the last x chunk pair
+        tmem_ld_wait();
+        // ---- norm(c) is needed from here on; its first chunk pair loads while the last x pair is squared ----
+        mbar_wait(gdn_bar, gdn_phase);
+        gdn_phase ^= 1;
+        tc_fence_after();
+        tmem_ld16(nb + (uint32_t)(chunk_of(0) << 4), buf[bl ^ 1][0]);
+        tmem_ld16(nb + (uint32_t)(chunk_of(1) << 4), buf[bl ^ 1][1]);
+        square_pack(buf[bl], NCH - 2, a_col, xn);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // ---- pass 2 (c) ----
+#pragma unroll
+        for (int jb = 0; jb < NCH; jb += 2) {
+            const int b = (bl ^ 1) ^ ((jb >> 1) & 1);
+            tmem_ld_wait();
+            if (jb + 2 < NCH) {
+                tmem_ld16(nb + (uint32_t)(chunk_of(jb + 2) << 4), buf[b ^ 1][0]);
+                tmem_ld16(nb + (uint32_t)(chunk_of(jb + 3) << 4), buf[b ^ 1][1]);
+            }
+            scale_store(c, buf[b], jb, xc);
+        }
+        tc_fence_before();
+    };
     auto team_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
 
     int v = blockIdx.x, tile;
@@ -717,10 +791,11 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
         const bool more = v < P.n_virtual && map_tile(P, v, tile);
         if (more) {
             setup(tile, nxt);
-            pass1(nxt, r ^ 1, xb);
+            fused(cur, xa, nxt, r ^ 1, xb);
+        } else {
+            pass2(cur, xa);
+            break;
         }
-        pass2(cur, xa);
-        if (!more) break;
         team_barrier();                       // norm(cur) consumed by every thread, x^2(nxt) complete
         issue_norm(nxt, r ^ 1);
         // roles swap: the compiler keeps xa / xb in registers because the loop is unrolled by two below
@@ -728,10 +803,11 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
         const bool more2 = v < P.n_virtual && map_tile(P, v, tile);
         if (more2) {
             setup(tile, cur);
-            pass1(cur, r, xa);
+            fused(nxt, xb, cur, r, xa);
+        } else {
+            pass2(nxt, xb);
+            break;
         }
-        pass2(nxt, xb);
-        if (!more2) break;
         team_barrier();
         issue_norm(cur, r);
     }
