@@ -74,6 +74,23 @@ struct Group {
     uint8_t tap0;        // first entry of this group in gbrow[]
 };
 
+// n / d for 0 <= n < 2^31 without an integer division (the tile-index decomposition runs once per tile in every warp role; ncu source
+// view of g_a.0: the four divisions of TileIter::init were ~10 % of the epilogue's issue slots).  Granlund-Montgomery round-up method.
+struct FastDiv {
+    uint32_t mul, shift, d;
+    __host__ void set(int div)
+    {
+        d = (uint32_t)div;
+        if (div <= 1) { mul = 0; shift = 0; return; }
+        int l = 0;
+        while ((1u << l) < d) ++l;                    // ceil(log2 d)
+        const int p = 31 + l;
+        mul = (uint32_t)((((uint64_t)1 << p) + d - 1) / d);
+        shift = (uint32_t)(p - 32);
+    }
+    __device__ __forceinline__ int div(int n) const { return d <= 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shift); }
+};
+
 struct TcParams {
     CUtensorMap tmA, tmB, tmG, tmA2;   // tmA2: second activation source (channels Cin1 .. Cin-1), see mmc_conv_forward_tc2
     Tap taps[kMaxTaps];
@@ -111,6 +128,7 @@ struct TcParams {
     int gdn_chunk;
     int tiles_per_phase, total_tiles;
     int epi_pipe;        // GDN epilogue software-pipelined over two tiles (epilogue_gdn_pipe)
+    FastDiv fd_tpp, fd_nb, fd_tx, fd_ty, fd_grid, fd_nph;   // divisions of the tile-index decomposition
     int phase_inner;     // transposed convolutions: the stride^2 output phases of a wave of spatial tiles run back to back (see map_tile)
     int n_virtual;       // bound of the persistent loops' running index (== total_tiles unless phase_inner)
     int st_nb, st_tx, st_ty, st_b, st_ph;   // gridDim.x decomposed in the radices (n_blocks, tiles_x, tiles_y, B, phase)
@@ -176,12 +194,12 @@ struct TileIter {
     int nb, tx, ty, b, phase;
     __device__ __forceinline__ void init(const TcParams &P, int tile)
     {
-        phase = tile / P.tiles_per_phase;
-        int r = tile - phase * P.tiles_per_phase;
-        nb = r % P.n_blocks; r /= P.n_blocks;
-        tx = r % P.tiles_x;  r /= P.tiles_x;
-        ty = r % P.tiles_y;
-        b = r / P.tiles_y;
+        phase = P.fd_tpp.div(tile);
+        int r = tile - phase * P.tiles_per_phase, q;
+        q = P.fd_nb.div(r); nb = r - q * P.n_blocks; r = q;
+        q = P.fd_tx.div(r); tx = r - q * P.tiles_x;  r = q;
+        q = P.fd_ty.div(r); ty = r - q * P.tiles_y;
+        b = q;
     }
     __device__ __forceinline__ void advance(const TcParams &P)
     {
@@ -208,8 +226,8 @@ __device__ __forceinline__ bool map_tile(const TcParams &P, int v, int &tile)
 {
     tile = v;
     if (!P.phase_inner) return true;
-    const int k = v / (int)gridDim.x;
-    const int w = k / P.n_phases, p = k - w * P.n_phases;
+    const int k = P.fd_grid.div(v);
+    const int w = P.fd_nph.div(k), p = k - w * P.n_phases;
     const int sp = w * (int)gridDim.x + (int)blockIdx.x;
     tile = p * P.tiles_per_phase + sp;
     return sp < P.tiles_per_phase;
@@ -597,12 +615,17 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
     // tile -> coordinates, accumulator stage (ring position of the it-th tile of this CTA)
     int acc_i = 0;
     uint32_t acc_ph = 0;
+    TileIter ti;
+    bool ti_started = false;
     auto setup = [&](int tile, PipeTile &t) {
-        TileIter ti;
-        ti.init(P, tile);
+        // consecutive tiles of a CTA are gridDim apart unless the phases are interleaved; a pair's padded last index must decode to
+        // b == B (masked), which the carry chain of advance() does not do
+        if (kPair || P.phase_inner || !ti_started) ti.init(P, tile);
+        else ti.advance(P);
+        ti_started = true;
         const TileCoord c = ti.coord(P);
         const int gy = c.y0 + th, gx = c.x0 + tw;
-        const int py = c.phase / P.out_stride, px = c.phase - py * P.out_stride;
+        const int py = P.out_stride == 2 ? (c.phase >> 1) : 0, px = P.out_stride == 2 ? (c.phase & 1) : 0;   // stride in {1, 2}
         t.valid = gy < P.Gh && gx < P.Gw && c.b < P.B;
         t.pix_off = (((int64_t)c.b * P.Ho + gy * P.out_stride + py) * P.Wo + gx * P.out_stride + px) * P.Cout + c.n0;
         t.as = acc_i; t.aphase = acc_ph;
@@ -1064,7 +1087,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             for (int v = blockIdx.x; v < P.n_virtual; v += gridDim.x, r ^= rtoggle) {
                 int tile;
                 if (!map_tile(P, v, tile)) break;
-                const int tphase = tile / P.tiles_per_phase;
+                const int tphase = P.fd_tpp.div(tile);
                 int n0 = 0;
                 if (P.n_blocks > 1) n0 = ((tile - tphase * P.tiles_per_phase) % P.n_blocks) * P.Ntile;
                 const int brow_off = n0 + (kPair ? (int)rank * half_n : 0);
@@ -1131,7 +1154,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             for (int v = blockIdx.x; v < P.n_virtual; v += gridDim.x, it_par ^= 1) {
                 int tile;
                 if (!map_tile(P, v, tile)) break;
-                const int tphase = tile / P.tiles_per_phase;
+                const int tphase = P.fd_tpp.div(tile);
                 const int nkb = (P.phase_begin[tphase + 1] - P.phase_begin[tphase]) * kchunks;
                 if (P.grouped && P.issuers == 2 && it_par != my_parity) {
                     // the other issuer's tile (it has its own operand rings): only the accumulator ring is shared
@@ -1682,6 +1705,8 @@ static int launch_tc(const TcParams &P, size_t fixed, size_t stage_bytes, cudaSt
     int grid = work < kNumSMs ? work : kNumSMs;
     auto set_virtual = [&](int g) {
         Q.n_virtual = Q.phase_inner ? ((Q.tiles_per_phase + g - 1) / g) * Q.n_phases * g : Q.total_tiles;
+        Q.fd_tpp.set(Q.tiles_per_phase); Q.fd_nb.set(Q.n_blocks); Q.fd_tx.set(Q.tiles_x); Q.fd_ty.set(Q.tiles_y);
+        Q.fd_grid.set(g); Q.fd_nph.set(Q.n_phases);
     };
     if (const char *g = getenv("MMC_TC_DEBUG")) Q.debug = atoi(g);
     Q.direct_store = 1;   // measured: g_a.0 1.04 -> 0.99 ms, g_s.2 0.38 -> 0.37 ms vs the staged, coalesced copy-out (MMC_TC_GDN_DIRECT=0)
