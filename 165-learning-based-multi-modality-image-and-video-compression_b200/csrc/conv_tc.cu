@@ -606,9 +606,7 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
     const int row = q * 32 + lane, th = row / P.TW, tw = row - th * P.TW;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t norm_col = (uint32_t)(P.acc_stages * P.Ntile), a_col0 = norm_col + (uint32_t)P.gdn_chunk;
-    const bool first_warp = warp == kSvcWarps, inverse = P.gdn == MMC_GDN_INVERSE;
-    const uint32_t empty_leader = kPair ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
-    const uint32_t idesc = make_idesc(P.Ntile), gm = smem_u32(sG);
+    const bool inverse = P.gdn == MMC_GDN_INVERSE;
     uint32_t gdn_phase = 0;
     auto chunk_of = [&](int j) { return half * NCH + j; };
 
@@ -664,29 +662,6 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
-    };
-    // norm MMAs of a tile (team's first warp, after the team barrier): norm = x^2 gamma'^T + beta', then the accumulator stage goes back
-    bool gamma_ready = false;
-    auto issue_norm = [&](const PipeTile &t, uint32_t r) {
-        if (!first_warp) return;
-        if (!gamma_ready) { mbar_wait(gload_bar, 0); gamma_ready = true; }
-        tc_fence_after();
-        if (elect_one()) {
-            const uint32_t a_col = a_col0 + r * (uint32_t)(P.Cout / 2);
-#pragma unroll
-            for (int kc = 0; kc < NCH * kParts / 4; ++kc) {
-                const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * P.Cout * 128));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    tc_mma_ts(tmem_base + norm_col, tmem_base + a_col + (uint32_t)((kc * 4 + k) * 8), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
-            }
-            tc_mma(tmem_base + norm_col, make_desc_ns(s_ones), make_desc_ns(s_beta), idesc, 1);
-            tc_commit(gdn_bar);
-            // every thread of the team read this tile's accumulator before the barrier that precedes this call
-            if (kPair) mbar_arrive_cluster(empty_leader + (uint32_t)(t.as * sizeof(uint64_t)));
-            else mbar_arrive(&tmem_empty_bar[t.as]);
-        }
-        __syncwarp();
     };
     // pass 2: y = x * rsqrt(norm) (IGDN: * sqrt), straight from registers to global memory
     auto pass2 = [&](const PipeTile &t, const uint32_t (&xp)[NCH * 8]) {
@@ -797,7 +772,11 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
         }
         tc_fence_before();
     };
-    auto team_barrier = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); };
+    // The epilogue threads only ARRIVE: what the hand-over protects (x^2 of the next tile complete, its accumulator and the current
+    // norm read by everybody) is needed by the thread that issues the next norm MMAs -- service warp 3 (norm_issuer_pipe), which
+    // waits on the same named barrier.  No epilogue thread can arrive twice before the issuer has passed: its next arrival comes
+    // after a wait for the norm that issuer produces.  (ncu: 11 % of the epilogue warps' time was the team barrier.)
+    auto team_arrive = [&]() { asm volatile("bar.arrive 1, %0;" ::"n"(kEpiThreads + 32) : "memory"); };
 
     int v = blockIdx.x, tile;
     if (v >= P.n_virtual || !map_tile(P, v, tile)) return;
@@ -806,8 +785,7 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
     uint32_t r = 0;
     setup(tile, cur);
     pass1(cur, r, xa);
-    team_barrier();
-    issue_norm(cur, r);
+    team_arrive();
     for (;;) {
         // invariant: xa holds tile `cur`, whose norm MMAs have been issued from operand block r
         v += gridDim.x;
@@ -819,8 +797,7 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
             pass2(cur, xa);
             break;
         }
-        team_barrier();                       // norm(cur) consumed by every thread, x^2(nxt) complete
-        issue_norm(nxt, r ^ 1);
+        team_arrive();                        // norm(cur) consumed by this thread, its part of x^2(nxt) complete
         // roles swap: the compiler keeps xa / xb in registers because the loop is unrolled by two below
         v += gridDim.x;
         const bool more2 = v < P.n_virtual && map_tile(P, v, tile);
@@ -831,8 +808,46 @@ __device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tm
             pass2(nxt, xb);
             break;
         }
-        team_barrier();
-        issue_norm(cur, r);
+        team_arrive();
+    }
+}
+
+// Service warp 3 of the pipelined GDN epilogue: per tile, wait for the epilogue threads' hand-over, issue the tile's norm contraction
+// (norm = x^2 gamma'^T + beta' from the tile's x^2 operand block) and hand the accumulator stage back to the main-loop issuer.
+template <int NCH, bool kPair, int kParts>
+__device__ __forceinline__ void norm_issuer_pipe(const TcParams &P, uint32_t tmem_base, uint64_t *tmem_empty_bar, uint64_t *gdn_bar, uint64_t *gload_bar,
+                                                 const uint8_t *sG, uint32_t s_ones, uint32_t s_beta)
+{
+    constexpr int kEpiThreads = 128 * kParts;
+    const uint32_t norm_col = (uint32_t)(P.acc_stages * P.Ntile), a_col0 = norm_col + (uint32_t)P.gdn_chunk;
+    const uint32_t empty_leader = kPair ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    const uint32_t idesc = make_idesc(P.Ntile), gm = smem_u32(sG);
+    uint32_t r = 0;
+    int as = 0;
+    bool first = true;
+    for (int v = blockIdx.x; v < P.n_virtual; v += gridDim.x) {
+        int tile;
+        if (!map_tile(P, v, tile)) break;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads + 32) : "memory");
+        if (first) { mbar_wait(gload_bar, 0); first = false; }
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t a_col = a_col0 + r * (uint32_t)(P.Cout / 2);
+#pragma unroll
+            for (int kc = 0; kc < NCH * kParts / 4; ++kc) {
+                const uint64_t bdesc = make_desc(gm + (uint32_t)(kc * P.Cout * 128));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    tc_mma_ts(tmem_base + norm_col, tmem_base + a_col + (uint32_t)((kc * 4 + k) * 8), bdesc + (uint64_t)(k * 2), idesc, (kc | k) != 0);
+            }
+            tc_mma(tmem_base + norm_col, make_desc_ns(s_ones), make_desc_ns(s_beta), idesc, 1);
+            tc_commit(gdn_bar);
+            if (kPair) mbar_arrive_cluster(empty_leader + (uint32_t)(as * sizeof(uint64_t)));
+            else mbar_arrive(&tmem_empty_bar[as]);
+        }
+        __syncwarp();
+        r ^= 1;
+        if (++as == P.acc_stages) as = 0;
     }
 }
 
@@ -1119,6 +1134,10 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
             }
         }
         __syncwarp();
+    } else if (warp == 3 && kEpi == EPI_GDN && kTeams == 1 && (kNCH == 4 || kNCH == 2) && P.epi_pipe) {
+        // ===================== norm-contraction issuer of the pipelined GDN epilogue =====================
+        if constexpr (kEpi == EPI_GDN && kTeams == 1 && (kNCH == 4 || kNCH == 2))
+            norm_issuer_pipe<kNCH, kPair, kParts>(P, tmem_base, tmem_empty_bar, &gdn_bar[0], &gload_bar, sG, smem_u32(s_ones), smem_u32(s_betaB));
     } else if ((warp == 1 || (warp == 3 && P.grouped && P.issuers == 2)) && (!kPair || rank == 0)) {
         // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
         // grouped mode: TWO issuing threads (warps 1 and 3) take alternate tiles -- different accumulator stages, so no ordering
@@ -2011,7 +2030,8 @@ static int conv_forward_tc_impl(const mmc_conv_desc *d, const void *x, const voi
     bool epi_pipe = true;     // measured (cfg 2, batch 64): g_a.0 0.859 -> 0.783 ms, g_s.2 0.330 -> 0.321, g_s.4 1.306 -> 1.289; step -2 %
     if (const char *g = getenv("MMC_TC_EPI_PIPE")) epi_pipe = atoi(g) != 0;
     epi_pipe = epi_pipe && d->gdn != MMC_GDN_NONE && !teams && P.a_tmem && (d->Cout == 64 || d->Cout == 128) && P.Ntile == d->Cout &&
-               !P.out_f32 && !P.out2 && pl.mode != MODE_SCATTER;
+               !P.out_f32 && !P.out2 && pl.mode != MODE_SCATTER &&
+               !(getenv("MMC_TC_ISSUERS") && atoi(getenv("MMC_TC_ISSUERS")) == 2);    // warp 3 is the norm issuer here
     if (epi_pipe) {
         P.epi_pipe = 1;
         P.acc_stages = (512 - P.gdn_chunk - d->Cout) / P.Ntile;
