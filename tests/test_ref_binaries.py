@@ -28,11 +28,18 @@ from mmcodec import ops  # noqa: E402
 
 
 def _ref():
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
-    import _CXX
-    import ans
-    return ans, _CXX
+    # pybind11 registers the coder classes process-wide: if the reference package itself was imported earlier in this process
+    # (tests/test_accelerate.py builds it in a scratch directory), its `compressai.ans` IS the same code -- reuse it; otherwise load
+    # oracle/_ref and publish it under the reference's module names so that a later import of the package reuses ours
+    ans, cxx = sys.modules.get("compressai.ans"), sys.modules.get("compressai._CXX")
+    if ans is None or cxx is None:
+        if REF_DIR not in sys.path:
+            sys.path.insert(0, REF_DIR)
+        import _CXX as cxx
+        import ans
+        sys.modules.setdefault("compressai.ans", ans)
+        sys.modules.setdefault("compressai._CXX", cxx)
+    return ans, cxx
 
 
 def _tables():
