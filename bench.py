@@ -80,6 +80,26 @@ NCU_DRAM_BYTES = {"g_s.4|tc": 0.403608e9 + 1.553492e9, "g_a.2|tc": 1.612e9 + 0.3
 NCU_SOURCE = "profiles/r02_ncu_conv_phase_inner.csv (ncu dram__bytes_read/write.sum per launch, profiles/_fwd_once.py; round-end default path)"
 
 
+def reference_coder_seconds(entropy_model, symbols, indexes):
+    """One image coded by the REFERENCE'S OWN rANS coder (oracle/_ref/ans*.so: compressai/cpp_exts/rans/rans_interface.cpp compiled by
+    `make -C oracle ref`), marshalled the way the reference does it (entropy_models.py:260-269: `.tolist()` per image, then
+    `encode_with_indexes`).  Returns (seconds, bytes) or raises if the binary was never built.  cpu_baseline leg only."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    ans = sys.modules.get("compressai.ans")
+    if ans is None:
+        if ref_dir not in sys.path:
+            sys.path.insert(0, ref_dir)
+        import ans
+    cdf = entropy_model._quantized_cdf.cpu().tolist()
+    lens = entropy_model._cdf_length.reshape(-1).int().cpu().tolist()
+    offs = entropy_model._offset.reshape(-1).int().cpu().tolist()
+    sym, idx = symbols.cpu(), indexes.cpu()
+    enc = ans.RansEncoder()
+    t0 = time.perf_counter()
+    out = enc.encode_with_indexes(sym.reshape(-1).int().tolist(), idx.reshape(-1).int().tolist(), cdf, lens, offs)
+    return time.perf_counter() - t0, out
+
+
 def shard_range(total: int, rank: int, world: int):
     """Contiguous shard [lo, hi) of `total` independent units for `rank` (no collective needed)."""
     base, rem = divmod(total, world)
@@ -658,7 +678,22 @@ def main():
             torch.cuda.synchronize()
             ms_e2e = (time.perf_counter() - t0) * 1e3
             e2e_sync_ms = None
+            ref_coder_rec = None
             if call == "compress":
+                # reported baseline: the reference's own coder binary on the symbols of image 0 (one thread, as the reference runs it)
+                try:
+                    si = net.symbols_and_indexes(x_dev)
+                    secs, nsym, same = 0.0, 0, True
+                    for nm, em, k in (("y", net.gaussian_conditional, 0), ("z", net.entropy_bottleneck, 1)):
+                        t_, bytes_ = reference_coder_seconds(em, si[f"{nm}_symbols"][0], si[f"{nm}_indexes"][0])
+                        secs += t_
+                        nsym += si[f"{nm}_symbols"][0].numel()
+                        same = same and bytes_ == res["strings"][k][0]
+                    ref_coder_rec = {"kind": "reference", "what": "oracle/_ref ans.RansEncoder (the reference's rans_interface.cpp), image 0, .tolist() marshalling included",
+                                     "cores": 1, "value": 1.0 / secs, "unit": "img/s", "ns_per_symbol": secs / nsym * 1e9,
+                                     "bytes_identical_to_net_compress": bool(same)}
+                except Exception as e:      # binary not built next to the reference: say so, keep the line
+                    ref_coder_rec = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
                 # the same call through mmcodec.CompressPipeline: host rANS coding of batch i overlaps the GPU work of batch i + 1
                 e2e_sync_ms = ms_e2e / args.steps
                 pipe = mmcodec.CompressPipeline(net, depth=2)
@@ -835,6 +870,8 @@ def main():
         line["e2e_full_outputs"] = e2e_full
     if call == "compress" and device_coder_rec:
         line["e2e_device_coder"] = device_coder_rec
+    if call == "compress" and ref_coder_rec:
+        line["reference_coder_baseline"] = ref_coder_rec
     if call == "compress" and e2e_sync_ms:
         line["e2e_sync_compress"] = {"value": B * world / (e2e_sync_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_sync_ms,
                                      "api": "net.compress(x_pinned.to(device)) called in a loop (GPU stage and host coding back to back)"}
