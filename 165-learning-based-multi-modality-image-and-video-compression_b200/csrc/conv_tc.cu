@@ -582,9 +582,9 @@ __device__ __forceinline__ void epilogue_gdn_rows(const GdnCtx &g, uint32_t &gdn
 //     pass 1 (i + 1): x -> bf16 pairs in registers (32 instead of 64 registers, which is what lets two tiles be in flight),
 //                     x^2 -> TMEM operand block (i + 1) & 1
 //     wait norm(i);  pass 2 (i): y = x * rsqrt(norm) (IGDN: * sqrt), 256-bit stores
-//     one team barrier;  norm MMAs (i + 1) issued, accumulator stage (i + 1) handed back
-// TMEM: 2 accumulator stages + norm + two x^2 operand blocks = 2 C + C + 2 C / 2 = 512 columns at C = 128.  One team barrier per
-// tile instead of three.  x is rounded to bf16 BEFORE the scaling (the output is bf16 either way): |y - y_ref| <= 2^-8 |y| instead of
+//     hand-over (bar.arrive);  service warp 3 (norm_issuer_pipe) issues the norm MMAs (i + 1) and hands accumulator stage (i + 1) back
+// TMEM: 2 accumulator stages + norm + two x^2 operand blocks = 2 C + C + 2 C / 2 = 512 columns at C = 128.  One non-blocking
+// hand-over per tile instead of three team barriers.  x is rounded to bf16 BEFORE the scaling (the output is bf16 either way): |y - y_ref| <= 2^-8 |y| instead of
 // 2^-9, inside the 1e-2 bf16 tolerance of BASELINE.json; the norm itself is computed from the fp32 x as before.
 // Tried: the second warp of every TMEM lane quarter running the two passes in the opposite order (to keep the quarter's tcgen05.ld
 // port busy while the other warp is in its MUFU / store phase) -- g_a.0 0.78 -> 1.2 ms: that warp starts with the norm wait.
@@ -597,8 +597,7 @@ struct PipeTile {
 };
 
 template <int NCH, bool kPair, int kParts>
-__device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tmem_base, uint64_t *tmem_full_bar, uint64_t *tmem_empty_bar,
-                                                  uint64_t *gdn_bar, uint64_t *gload_bar, const uint8_t *sG, uint32_t s_ones, uint32_t s_beta)
+__device__ __forceinline__ void epilogue_gdn_pipe(const TcParams &P, uint32_t tmem_base, uint64_t *tmem_full_bar, uint64_t *gdn_bar)
 {
     constexpr int kEpiThreads = 128 * kParts;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1264,7 +1263,7 @@ __global__ void __launch_bounds__(tc_threads(kParts, kTeams), 1) conv_tc_kernel(
     } else if (warp >= kSvcWarps && kEpi == EPI_GDN && kTeams == 1 && (kNCH == 4 || kNCH == 2) && P.epi_pipe) {
         // ===================== epilogue, software-pipelined over two tiles (GDN, C <= 128) ============
         if constexpr (kEpi == EPI_GDN && kTeams == 1 && (kNCH == 4 || kNCH == 2))
-            epilogue_gdn_pipe<kNCH, kPair, kParts>(P, tmem_base, tmem_full_bar, tmem_empty_bar, &gdn_bar[0], &gload_bar, sG, smem_u32(s_ones), smem_u32(s_betaB));
+            epilogue_gdn_pipe<kNCH, kPair, kParts>(P, tmem_base, tmem_full_bar, &gdn_bar[0]);
     } else if (warp >= kSvcWarps) {
         // ===================== epilogue: 8 warps, 2 per TMEM lane quarter, each pair splits the columns ============
         const int q = warp & 3;                 // TMEM lane quarter this warp can access
